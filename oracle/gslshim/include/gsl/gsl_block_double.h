@@ -1,0 +1,2 @@
+/* stub: forwards to the from-scratch GSL-subset shim (test infrastructure, not GSL) */
+#include "gslshim.h"
