@@ -1,0 +1,175 @@
+/*
+ * xpsi_b200.h -- C ABI of the B200-native X-PSI likelihood hot path.
+ *
+ * The reference (X-PSI v3.3.0) has no FFI: its seam is "a Python callable that
+ * takes and returns numpy arrays" (SURVEY.md s8b).  Each entry point below is
+ * what a ctypes/cffi binding of that seam calls; the reference interface it
+ * replaces is cited as <reference-relative path>:<lines>.  The Python mirror
+ * of those callables lives in xpsi_b200/ (same names, argument order and
+ * return conventions as the reference), INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; all arrays C-contiguous float64
+ *     unless stated (int = 32-bit).  Pointers are HOST memory unless the
+ *     function name ends in _device.
+ *   - return value: 0 success; 1 the reference's numerical ERROR (its
+ *     "(1, None)" return); <0 API/CUDA failure (message via
+ *     xpsi_b200_last_error()).  Nothing is retained past a call except through
+ *     explicit *_create / *_destroy handles.
+ *   - there is no CPU fallback: every call fails with XPSI_B200_ENODEVICE when
+ *     no CUDA device is usable.
+ */
+#ifndef XPSI_B200_H
+#define XPSI_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XPSI_B200_OK 0
+#define XPSI_B200_ENUMERICAL 1      /* reference returns (1, None) / raises PulseError */
+#define XPSI_B200_EUNSUPPORTED 3    /* configuration outside the kernels' coverage   */
+#define XPSI_B200_ESLIM 11          /* eval_marginal_likelihood slim early exit       */
+#define XPSI_B200_EQUADRATURE 12    /* marginal integral non-positive                 */
+#define XPSI_B200_EINVAL (-1)
+#define XPSI_B200_ECUDA (-2)
+#define XPSI_B200_ENODEVICE (-3)
+
+/* atmosphere extension ids, xpsi/surface_radiation_field/hot_wrapper.pyx:72-252 */
+#define XPSI_B200_ATM_BB 1
+#define XPSI_B200_ATM_NUM4D 2
+/* global interpolant ids, xpsi/tools/core.pyx:21 */
+#define XPSI_B200_INTERP_AKIMA 0
+#define XPSI_B200_INTERP_STEFFEN 1
+
+const char* xpsi_b200_last_error(void);
+int xpsi_b200_device_count(void);
+int xpsi_b200_set_device(int device);
+/* counters for bench.py: kernels launched / bytes moved by this library so far */
+void xpsi_b200_counters(long long* kernel_launches, long long* h2d_bytes, long long* d2h_bytes);
+void* xpsi_b200_stream(void);   /* cudaStream_t all work is issued on */
+
+/* ---- preloaded atmosphere table ------------------------------------------
+ * replaces init_preload / _preloaded, surface_radiation_field/preload.pyx:6-44
+ * (tuple (logT, logg, mu, logE, buf) of xpsi/Photosphere.py:208-217).        */
+typedef struct xpsi_b200_atmosphere xpsi_b200_atmosphere;
+xpsi_b200_atmosphere* xpsi_b200_atmosphere_create(const double* logT, int nT, const double* logg,
+                                                  int ng, const double* mu, int nmu,
+                                                  const double* logE, int nE, const double* buf);
+void xpsi_b200_atmosphere_destroy(xpsi_b200_atmosphere* atm);
+
+/* ---- cellmesh.integrator_for_azimuthal_invariance.integrate -----------------
+ * replaces xpsi/cellmesh/integrator_for_azimuthal_invariance.pyx:70-665
+ * (call site xpsi/HotRegion.py:1169-1197).  flux_out is [n_energies][n_phases].
+ * correction_srcCellParams / elsewhere atmosphere / disc (R_in < 1e6) are not
+ * yet covered: passing them returns XPSI_B200_EUNSUPPORTED.                   */
+int xpsi_b200_integrate_azimuthal_invariance(
+    double R, double omega, double r_s, double inclination,
+    int n_rings, int n_azi,
+    const double* cellArea, const double* radialCoords_of_parallels, const double* r_s_over_r,
+    const double* theta, const double* phi,
+    const double* srcCellParams, int n_params, const int* CELL_RADIATES,
+    const double* correction_srcCellParams,
+    int numRays, const double* deflection, const double* cos_alpha, const double* lag,
+    const double* maxDeflection, const double* cos_gammaArray,
+    int n_energies, const double* energies, int n_leaves, const double* leaves,
+    int n_phases, const double* phases,
+    const xpsi_b200_atmosphere* hot_atmosphere, const xpsi_b200_atmosphere* elsewhere_atmosphere,
+    int hot_atm_ext, int else_atm_ext, int beam_opt, int image_order_limit, double R_in,
+    int phase_interpolant, double* flux_out);
+
+/* ---- tools.energy_integrator -------------------------------------------------
+ * replaces xpsi/tools/energy_integrator.pyx:27-114.  signal [n_energies][n_phases],
+ * out [n_in][n_phases] (the reference's transposed return).                    */
+int xpsi_b200_energy_integrator(const double* signal, int n_energies, int n_phases,
+                                const double* log10_energies, const double* log10_edges, int n_in,
+                                int phase_interpolant, double* out);
+
+/* ---- Instrument.__call__ -------------------------------------------------------
+ * replaces numpy.dot(matrix[o0:o1, i0:i1], signal), xpsi/Instrument.py:192-197.
+ * matrix is the full [n_rows][n_cols] response; signal [i1-i0][n_phases];
+ * out [o1-o0][n_phases].                                                         */
+int xpsi_b200_instrument_fold(const double* matrix, int n_rows, int n_cols, int i0, int i1, int o0,
+                              int o1, const double* signal, int n_phases, double* out);
+
+/* ---- likelihoods.precomputation / eval_marginal_likelihood -----------------------
+ * replace xpsi/likelihoods/default_background_marginalisation.pyx:38-68 and :450-734.
+ * components: n_comp arrays [n_chan][n_phases] sharing one phase grid
+ * component_phases[n_phases] (cycles).  background may be NULL.  Returns 0,
+ * XPSI_B200_ESLIM or XPSI_B200_EQUADRATURE (the two cases where the reference
+ * returns a random near-llzero value); *lnL is then unspecified.               */
+int xpsi_b200_precomputation(const int* counts, int n_chan, int n_bins, double* out);
+int xpsi_b200_eval_marginal_likelihood(
+    double exposure_time, const double* phases, int n_bins, const double* counts, int n_chan,
+    const double* const* components, int n_comp, const double* component_phases, int n_phases,
+    const double* phase_shifts, const double* neg_sum_ln_data_factorial, const double* support,
+    double epsilon, double sigmas, double llzero, int allow_negative, double slim,
+    const double* background, int phase_interpolant,
+    double* lnL, double* expected_counts, double* mcl_background,
+    double* mcl_background_given_support);
+
+/* ---- batched likelihood pipeline (additional API) -------------
+ * One handle holds every theta-independent constant on the device; eval takes a
+ * batch of B parameter vectors already reduced to integrator inputs (mesh +
+ * rays per hot-region member, the outputs of Star.update / HotRegion.embed,
+ * xpsi/HotRegion.py:1033-1070) and returns lnL[B], status[B].                  */
+typedef struct xpsi_b200_pipeline xpsi_b200_pipeline;
+
+typedef struct {
+  int n_components;          /* hot regions (likelihood signal components)              */
+  int n_members;             /* integrator calls per theta (>= n_components)            */
+  const int* member_component; /* [n_members] component each member's flux is added to  */
+  int max_rings, max_azi;    /* padded mesh dims                                        */
+  int n_rays, n_params;
+  int n_energies; const double* energies;        /* keV */
+  int n_leaves; const double* leaves;            /* rad */
+  int n_phases; const double* phases;            /* rad; cycles = phases / 2 pi          */
+  int hot_atm_ext; const xpsi_b200_atmosphere* hot_atmosphere;
+  int image_order_limit;
+  int phase_interpolant;
+  /* instrument */
+  int n_in; const double* energy_edges;          /* [n_in+1] keV                          */
+  int n_chan; const double* response;            /* [n_chan][n_in]                        */
+  /* data + likelihood settings */
+  int n_bins; const double* data_phases;         /* [n_bins+1] cycles                     */
+  const double* counts;                          /* [n_chan][n_bins]                      */
+  const double* support;                         /* [n_chan][2]                           */
+  double exposure_time, epsilon, sigmas, llzero, slim;
+  int allow_negative;
+} xpsi_b200_pipeline_config;
+
+typedef struct {
+  /* per theta [B] */
+  const double* omega; const double* inclination; const double* d_sq;
+  const double* phase_shifts;                    /* [B][n_components] cycles              */
+  /* per member instance q = b*n_members + m, padded to (max_rings, max_azi) */
+  const int* n_rings; const int* n_azi;          /* [B*M]                                 */
+  const double* cellArea; const double* phi;     /* [B*M][max_rings][max_azi]             */
+  const double* theta;                           /* [B*M][max_rings] ring colatitude      */
+  const double* radial; const double* r_s_over_r;/* [B*M][max_rings]                      */
+  const double* srcParams;                       /* [B*M][max_rings][n_params]            */
+  const double* deflection; const double* cos_alpha; const double* lag; /* [B*M][max_rings][n_rays] */
+  const double* maxDeflection; const double* cos_gamma;                 /* [B*M][max_rings] */
+} xpsi_b200_batch;
+
+xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* cfg, int max_batch);
+void xpsi_b200_pipeline_destroy(xpsi_b200_pipeline* p);
+/* host buffers: copies in, runs, copies lnL/status out (the e2e path) */
+int xpsi_b200_pipeline_eval(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch* host_batch,
+                            double* lnL, int* status);
+/* stage a host batch on the device once; eval_resident then times kernels only */
+int xpsi_b200_pipeline_upload(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch* host_batch);
+int xpsi_b200_pipeline_eval_resident(xpsi_b200_pipeline* p, int B);
+int xpsi_b200_pipeline_download(xpsi_b200_pipeline* p, int B, double* lnL, int* status);
+/* optional: fetch intermediate device results of the last eval (NULL to skip) */
+int xpsi_b200_pipeline_fetch(xpsi_b200_pipeline* p, int B, double* flux /*[B*M][E][P] raw*/,
+                             double* folded /*[B][C][chan][P]*/, double* expected /*[B][chan][bins]*/);
+/* per-stage device time of the last eval_resident in ms: integrate, energy, fold, marginal */
+int xpsi_b200_pipeline_stage_ms(xpsi_b200_pipeline* p, float ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

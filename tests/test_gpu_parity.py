@@ -1,0 +1,202 @@
+"""GPU parity tests: the CUDA hot path (called through the C ABI via the
+reference-shaped Python callables) against golden vectors recorded from the
+reference build (tests/golden/make_golden.py).
+
+Tolerances are BASELINE.json's: pulse signals 1e-8 relative, lnL 1e-6 absolute.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+PULSE_RTOL = 1.0e-8
+LNL_ATOL = 1.0e-6
+
+
+def _integrate_args(d, prefix, atmosphere):
+    g = lambda k: d[prefix + k]
+    iol = int(g("image_order_limit")) if (prefix + "image_order_limit") in d.files else None
+    return (1, float(g("R")), float(g("omega")), float(g("r_s")), float(g("inclination")),
+            g("cellArea"), g("radialCoords_of_parallels"), g("r_s_over_r"), g("theta"), g("phi"),
+            g("srcCellParams"), g("CELL_RADIATES"), None, int(g("numRays")), g("deflection"),
+            g("cos_alpha"), g("lag"), g("maxDeflection"), g("cos_gammaArray"), g("energies"),
+            g("leaves"), g("phases"), atmosphere, (), int(g("hot_atm_ext")), 1, int(g("beam_opt")), iol)
+
+
+def _pulse_err(out, ref):
+    """elementwise error relative to the largest value of the same energy row"""
+    scale = np.max(np.abs(ref), axis=1, keepdims=True)
+    scale[scale == 0.0] = 1.0
+    return float(np.max(np.abs(out - ref) / scale))
+
+
+def test_c1_integrate_blackbody(c1):
+    from xpsi_b200.cellmesh.integrator_for_azimuthal_invariance import integrate
+    status, flux = integrate(*_integrate_args(c1, "int0_", ()))
+    assert status == 0
+    assert flux.shape == c1["int0_flux"].shape
+    err = _pulse_err(flux, c1["int0_flux"])
+    print("C1 flux max rel err", err, "global", rel_err(flux, c1["int0_flux"]))
+    assert err < PULSE_RTOL
+
+
+def test_c1_energy_integrator(c1):
+    from xpsi_b200.tools import energy_integrator
+    signal = c1["int0_flux"] / c1["d_sq"]
+    out = energy_integrator(1, signal, c1["eint_log10_energies"], c1["eint_log10_edges"])
+    ref = c1["eint0_out"]
+    assert out.shape == ref.shape
+    err = rel_err(out, ref)
+    print("C1 energy_integrator rel err", err)
+    assert err < PULSE_RTOL
+
+
+def test_c1_fold(c1):
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.instrument import Instrument
+    matrix = syn.c1_response()[0]
+    inst = Instrument(matrix)
+    out = inst(c1["eint0_out"], (0, matrix.shape[1]), (0, matrix.shape[0]))
+    ref = c1["marg_components_0"]
+    err = rel_err(out, ref)
+    print("C1 fold rel err", err)
+    assert err < 1.0e-13
+
+
+def _marginal(d, prefix):
+    from xpsi_b200.likelihoods import eval_marginal_likelihood
+    n = int(d[prefix + "n_components"])
+    comps = tuple(d["%scomponents_%d" % (prefix, i)] for i in range(n))
+    cph = tuple(d["%scomponent_phases_%d" % (prefix, i)] for i in range(n))
+    return eval_marginal_likelihood(float(d[prefix + "exposure_time"]), d[prefix + "phases"],
+                                    d[prefix + "counts"], comps, cph, d[prefix + "phase_shifts"],
+                                    d[prefix + "precomp"], d[prefix + "support"],
+                                    int(d[prefix + "workspace_intervals"]), float(d[prefix + "epsabs"]),
+                                    float(d[prefix + "epsrel"]), float(d[prefix + "epsilon"]),
+                                    float(d[prefix + "sigmas"]), float(d[prefix + "llzero"]))
+
+
+def test_c1_marginal_likelihood(c1):
+    lnL, star, mcl, mcl_s = _marginal(c1, "marg_")
+    print("C1 lnL", lnL, "ref", float(c1["marg_lnL"]), "diff", lnL - float(c1["marg_lnL"]))
+    assert abs(lnL - float(c1["marg_lnL"])) < LNL_ATOL
+    assert rel_err(star, c1["marg_expected_counts"]) < PULSE_RTOL
+    assert rel_err(mcl, c1["marg_mcl_background"]) < 1.0e-6
+    # the reference's own published known answer (xpsi/tests/test_likelihood.py:134, rtol 1e-5)
+    assert abs(lnL - float(c1["known_answer_lnL"])) < 1.0e-5 * abs(float(c1["known_answer_lnL"]))
+
+
+def test_c1_precomputation(c1):
+    from xpsi_b200.likelihoods import precomputation
+    out = precomputation(c1["marg_counts"].astype(np.int32))
+    assert np.max(np.abs(out - c1["marg_precomp"])) < 1.0e-9
+
+
+def test_c1_chain_end_to_end(c1):
+    """integrate -> /d_sq -> energy_integrator -> fold -> marginal, all on the GPU,
+    against the reference's lnL."""
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.cellmesh.integrator_for_azimuthal_invariance import integrate
+    from xpsi_b200.instrument import fold
+    from xpsi_b200.likelihoods import eval_marginal_likelihood
+    from xpsi_b200.tools import energy_integrator
+    status, flux = integrate(*_integrate_args(c1, "int0_", ()))
+    assert status == 0
+    integrated = energy_integrator(1, flux / c1["d_sq"], c1["eint_log10_energies"], c1["eint_log10_edges"])
+    matrix = syn.c1_response()[0]
+    folded = fold(matrix, integrated, (0, matrix.shape[1]), (0, matrix.shape[0]))
+    d, p = c1, "marg_"
+    lnL = eval_marginal_likelihood(float(d[p + "exposure_time"]), d[p + "phases"], d[p + "counts"],
+                                   (folded,), (d[p + "component_phases_0"],), d[p + "phase_shifts"],
+                                   d[p + "precomp"], d[p + "support"], 1000, 0.0, 1e-8, 1e-3, 10.0, -1e90)[0]
+    print("C1 chain lnL", lnL, "diff", lnL - float(c1["lnL_total"]))
+    assert abs(lnL - float(c1["lnL_total"])) < LNL_ATOL
+
+
+@pytest.mark.parametrize("t,m", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_m2_integrate_num4d(m2, t, m):
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.cellmesh.integrator_for_azimuthal_invariance import integrate
+    table = test_m2_integrate_num4d.__dict__.setdefault("table", syn.nsx_like_table())
+    prefix = "t%d_int%d_" % (t, m)
+    status, flux = integrate(*_integrate_args(m2, prefix, table))
+    assert status == 0
+    ref = m2[prefix + "flux"]
+    err = _pulse_err(flux, ref)
+    print("M2 theta %d member %d flux rel err" % (t, m), err)
+    assert err < PULSE_RTOL
+
+
+def test_m2_marginal_likelihood(m2):
+    for t in range(int(m2["n_theta"])):
+        p = "t%d_marg_" % t
+        lnL = _marginal(m2, p)[0]
+        print("M2 theta", t, "lnL", lnL, "diff", lnL - float(m2[p + "lnL"]))
+        assert abs(lnL - float(m2[p + "lnL"])) < LNL_ATOL
+
+
+def test_m2_energy_integrator_and_fold(m2):
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.instrument import fold
+    from xpsi_b200.tools import energy_integrator
+    signal = m2["t0_int0_flux"] / m2["t0_d_sq"]
+    out = energy_integrator(1, signal, m2["t0_eint_log10_energies"], m2["t0_eint_log10_edges"])
+    assert rel_err(out, m2["t0_eint0_out"]) < PULSE_RTOL
+    matrix = syn.nicer_like_response()[0]
+    folded = fold(matrix, m2["t0_eint0_out"], (0, matrix.shape[1]), (0, matrix.shape[0]))
+    err = rel_err(folded, m2["t0_marg_components_0"])
+    print("M2 fold rel err", err)
+    assert err < 1.0e-12
+
+
+def _m2_pipeline(m2, max_batch=8):
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.pipeline import BatchedLikelihood
+    matrix, edges, channels, ch_edges = syn.nicer_like_response()
+    return BatchedLikelihood(member_component=[0, 1], max_rings=64, max_azi=64, n_rays=200,
+                             energies=m2["t0_int0_energies"], leaves=m2["t0_int0_leaves"],
+                             phases=m2["t0_int0_phases"], hot_atm_ext=2,
+                             hot_atmosphere=syn.nsx_like_table(), image_order_limit=3,
+                             response=matrix, energy_edges=edges, counts=m2["counts"],
+                             data_phases=np.linspace(0.0, 1.0, 33), exposure_time=syn.M2_EXPOSURE,
+                             max_batch=max_batch)
+
+
+def fill_m2_batch(m2, batch, order):
+    for b, t in enumerate(order):
+        batch.omega[b] = m2["t%d_int0_omega" % t]
+        batch.inclination[b] = m2["t%d_int0_inclination" % t]
+        batch.d_sq[b] = m2["t%d_d_sq" % t]
+        batch.phase_shifts[b] = m2["t%d_marg_phase_shifts" % t]
+        for m in range(2):
+            g = lambda k: m2["t%d_int%d_%s" % (t, m, k)]
+            batch.set_member(b, m, g("cellArea"), g("theta"), g("phi"), g("radialCoords_of_parallels"),
+                             g("r_s_over_r"), g("srcCellParams"), g("deflection"), g("cos_alpha"),
+                             g("lag"), g("maxDeflection"), g("cos_gammaArray"))
+
+
+def test_m2_batched_pipeline(m2):
+    pipe = _m2_pipeline(m2)
+    order = [0, 1, 1, 0, 0]
+    batch = pipe.new_batch(len(order))
+    fill_m2_batch(m2, batch, order)
+    lnL, status = pipe(batch)
+    print("pipeline lnL", lnL, "status", status, "stages", pipe.stage_ms())
+    assert (status == 0).all()
+    for b, t in enumerate(order):
+        ref = float(m2["t%d_lnL_total" % t])
+        print("  theta", t, "lnL", lnL[b], "ref", ref, "diff", lnL[b] - ref)
+        assert abs(lnL[b] - ref) < LNL_ATOL
+    flux, folded, expected = pipe.fetch(len(order))
+    for b, t in enumerate(order):
+        for m in range(2):
+            ref = m2["t%d_int%d_flux" % (t, m)]
+            got = flux[b * 2 + m] / (m2["t0_int0_energies"][:, None] * 1.60217662e-16)
+            assert _pulse_err(got, ref) < PULSE_RTOL
+            assert rel_err(folded[b, m], m2["t%d_marg_components_%d" % (t, m)]) < PULSE_RTOL
+        assert rel_err(expected[b], m2["t%d_marg_expected_counts" % t]) < PULSE_RTOL
+    # identical inputs in different batch slots give identical answers up to the
+    # order of the fp64 ring reduction
+    assert abs(lnL[0] - lnL[3]) < 1e-7 and abs(lnL[1] - lnL[2]) < 1e-7

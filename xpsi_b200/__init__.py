@@ -1,0 +1,15 @@
+"""xpsi_b200 -- B200-native likelihood hot path behind the X-PSI call signatures.
+
+Sub-modules mirror the reference layout for the path (same callables, same
+positional order, same return conventions):
+
+    xpsi_b200.cellmesh.integrator_for_azimuthal_invariance.integrate
+    xpsi_b200.tools.energy_integrator
+    xpsi_b200.instrument.fold / Instrument
+    xpsi_b200.likelihoods.precomputation / eval_marginal_likelihood
+    xpsi_b200.pipeline.BatchedLikelihood            (additional, batched)
+
+Everything computes on the GPU through libxpsi_b200.so; there is no CPU path.
+``xpsi_b200.synthetic`` (pure numpy) defines the synthetic workloads.
+"""
+__version__ = "0.1.0"

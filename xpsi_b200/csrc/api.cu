@@ -1,0 +1,558 @@
+// C ABI of the B200-native X-PSI likelihood hot path (include/xpsi_b200.h).
+// Host-side plumbing only: device buffers, one stream, handles for the
+// theta-independent constants, and the batched pipeline that chains the kernels.
+#include "../../include/xpsi_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+cudaStream_t g_stream = nullptr;
+long long g_launches = 0, g_h2d = 0, g_d2h = 0;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* where) {
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? XPSI_B200_ENODEVICE : XPSI_B200_ECUDA;
+}
+#define CK(call)                                              \
+  do {                                                        \
+    cudaError_t _e = (call);                                  \
+    if (_e != cudaSuccess) return cuda_fail(_e, #call);       \
+  } while (0)
+
+int ensure_stream() {
+  if (g_stream) return 0;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_err = "xpsi_b200: no usable CUDA device (the hot path has no CPU fallback)";
+    return XPSI_B200_ENODEVICE;
+  }
+  CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  return 0;
+}
+
+// device buffer with explicit lifetime
+template <class T>
+struct Dev {
+  T* p = nullptr;
+  size_t n = 0;
+  Dev() {}
+  Dev(const Dev&) = delete;
+  Dev& operator=(const Dev&) = delete;
+  ~Dev() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; }
+    n = count;
+    return cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+  }
+  cudaError_t upload(const T* h, size_t count) {
+    cudaError_t e = alloc(count);
+    if (e != cudaSuccess) return e;
+    g_h2d += (long long)(count * sizeof(T));
+    return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, g_stream);
+  }
+  cudaError_t download(T* h, size_t count) const {
+    g_d2h += (long long)(count * sizeof(T));
+    return cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, g_stream);
+  }
+};
+
+int slab_rows_budget(const xb::AtmTable& t, const double* energies, int n_energies) {
+  // rows of the logE axis a ring can reach: span of the energy grid plus the
+  // Doppler/redshift spread across one ring (|beta| < 0.45 => < 0.42 dex) + stencil
+  if (t.min_dlogE <= 0.0) return t.nE;
+  const double span = log10(energies[n_energies - 1] / energies[0]) + 0.42;
+  int rows = (int)ceil(span / t.min_dlogE) + 10;
+  return rows > t.nE ? t.nE : rows;
+}
+
+}  // namespace
+
+struct xpsi_b200_atmosphere {
+  Dev<double> logT, logg, mu, logE, buf;
+  xb::AtmTable view;
+};
+
+extern "C" {
+
+const char* xpsi_b200_last_error(void) { return g_err.c_str(); }
+
+int xpsi_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int xpsi_b200_set_device(int device) {
+  CK(cudaSetDevice(device));
+  return 0;
+}
+
+void xpsi_b200_counters(long long* k, long long* h2d, long long* d2h) {
+  if (k) *k = g_launches;
+  if (h2d) *h2d = g_h2d;
+  if (d2h) *d2h = g_d2h;
+}
+
+void* xpsi_b200_stream(void) { return ensure_stream() == 0 ? (void*)g_stream : nullptr; }
+
+xpsi_b200_atmosphere* xpsi_b200_atmosphere_create(const double* logT, int nT, const double* logg,
+                                                  int ng, const double* mu, int nmu,
+                                                  const double* logE, int nE, const double* buf) {
+  if (ensure_stream() != 0) return nullptr;
+  if (nT < 4 || ng < 4 || nmu < 4 || nE < 4) { g_err = "atmosphere axes need >= 4 nodes"; return nullptr; }
+  xpsi_b200_atmosphere* a = new xpsi_b200_atmosphere();
+  cudaError_t e = a->logT.upload(logT, nT);
+  if (e == cudaSuccess) e = a->logg.upload(logg, ng);
+  if (e == cudaSuccess) e = a->mu.upload(mu, nmu);
+  if (e == cudaSuccess) e = a->logE.upload(logE, nE);
+  if (e == cudaSuccess) e = a->buf.upload(buf, (size_t)nT * ng * nmu * nE);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+  if (e != cudaSuccess) { cuda_fail(e, "atmosphere_create"); delete a; return nullptr; }
+  double dmin = 1e300;
+  for (int i = 1; i < nE; ++i) dmin = fmin(dmin, logE[i] - logE[i - 1]);
+  a->view = xb::AtmTable{a->logT.p, a->logg.p, a->mu.p, a->logE.p, a->buf.p, nT, ng, nmu, nE, dmin};
+  return a;
+}
+
+void xpsi_b200_atmosphere_destroy(xpsi_b200_atmosphere* atm) { delete atm; }
+
+int xpsi_b200_integrate_azimuthal_invariance(
+    double R, double omega, double r_s, double inclination, int n_rings, int n_azi,
+    const double* cellArea, const double* radial, const double* r_s_over_r, const double* theta,
+    const double* phi, const double* srcCellParams, int n_params, const int* CELL_RADIATES,
+    const double* correction_srcCellParams, int numRays, const double* deflection,
+    const double* cos_alpha, const double* lag, const double* maxDeflection,
+    const double* cos_gammaArray, int n_energies, const double* energies, int n_leaves,
+    const double* leaves, int n_phases, const double* phases,
+    const xpsi_b200_atmosphere* hot_atmosphere, const xpsi_b200_atmosphere* elsewhere_atmosphere,
+    int hot_atm_ext, int else_atm_ext, int beam_opt, int image_order_limit, double R_in,
+    int phase_interpolant, double* flux_out) {
+  (void)R; (void)r_s; (void)else_atm_ext; (void)elsewhere_atmosphere;
+  int rc = ensure_stream();
+  if (rc) return rc;
+  if (correction_srcCellParams) return fail(XPSI_B200_EUNSUPPORTED, "elsewhere correction is not covered yet");
+  if (R_in < 1.0e6) return fail(XPSI_B200_EUNSUPPORTED, "disc occultation (R_in < 1e6) is not covered yet");
+  if (beam_opt != 0) return fail(XPSI_B200_EUNSUPPORTED, "beam_opt != 0 is not covered yet");
+  if (hot_atm_ext != XPSI_B200_ATM_BB && hot_atm_ext != XPSI_B200_ATM_NUM4D)
+    return fail(XPSI_B200_EUNSUPPORTED, "hot_atm_ext must be 1 (BB) or 2 (Num4D)");
+  if (hot_atm_ext == XPSI_B200_ATM_NUM4D && !hot_atmosphere)
+    return fail(XPSI_B200_EINVAL, "Num4D needs a preloaded atmosphere");
+  if (phase_interpolant != 0 && phase_interpolant != 1)
+    return fail(XPSI_B200_EUNSUPPORTED, "phase interpolant must be Akima (0) or Steffen (1)");
+  if (n_rings < 1 || n_azi < 1 || numRays < 3 || n_energies < 1 || n_leaves < 5 || n_phases < 1 || n_params < 1)
+    return fail(XPSI_B200_EINVAL, "bad dimensions");
+
+  const size_t nc = (size_t)n_rings * n_azi, nr = (size_t)n_rings * numRays;
+  Dev<double> d_area, d_radial, d_rsr, d_theta, d_phi, d_par, d_defl, d_ca, d_lag, d_maxd, d_cg, d_E, d_L,
+      d_P, d_flux, d_scal;
+  Dev<int> d_rad, d_status;
+  const double scal[2] = {omega, inclination};
+  CK(d_scal.upload(scal, 2));
+  CK(d_area.upload(cellArea, nc)); CK(d_radial.upload(radial, n_rings)); CK(d_rsr.upload(r_s_over_r, n_rings));
+  CK(d_theta.upload(theta, nc)); CK(d_phi.upload(phi, nc)); CK(d_par.upload(srcCellParams, nc * n_params));
+  CK(d_rad.upload(CELL_RADIATES, nc));
+  CK(d_defl.upload(deflection, nr)); CK(d_ca.upload(cos_alpha, nr)); CK(d_lag.upload(lag, nr));
+  CK(d_maxd.upload(maxDeflection, n_rings)); CK(d_cg.upload(cos_gammaArray, n_rings));
+  CK(d_E.upload(energies, n_energies)); CK(d_L.upload(leaves, n_leaves)); CK(d_P.upload(phases, n_phases));
+  CK(d_flux.alloc((size_t)n_energies * n_phases));
+  CK(cudaMemsetAsync(d_flux.p, 0, (size_t)n_energies * n_phases * sizeof(double), g_stream));
+  CK(d_status.alloc(1));
+  CK(cudaMemsetAsync(d_status.p, 0, sizeof(int), g_stream));
+
+  xb::AzinvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Q = 1; a.n_rings = n_rings; a.n_azi = n_azi; a.n_rays = numRays; a.n_energies = n_energies;
+  a.n_leaves = n_leaves; a.n_phases = n_phases; a.n_params = n_params;
+  a.omega = d_scal.p; a.inclination = d_scal.p + 1;
+  a.cellArea = d_area.p; a.phi = d_phi.p; a.theta = d_theta.p; a.theta_ring_stride = n_azi;
+  a.radial = d_radial.p; a.r_s_over_r = d_rsr.p; a.srcParams = d_par.p; a.params_per_cell = 1;
+  a.radiates = d_rad.p; a.deflection = d_defl.p; a.cos_alpha = d_ca.p; a.lag = d_lag.p;
+  a.maxDeflection = d_maxd.p; a.cos_gamma = d_cg.p; a.energies = d_E.p; a.leaves = d_L.p; a.phases = d_P.p;
+  a.hot_atm_ext = hot_atm_ext;
+  if (hot_atm_ext == XPSI_B200_ATM_NUM4D) {
+    a.hot = hot_atmosphere->view;
+    a.slab_ne_max = slab_rows_budget(a.hot, energies, n_energies);
+  }
+  a.image_order_limit = image_order_limit > 0 ? image_order_limit : 0;
+  a.n_img_max = image_order_limit > 0 ? image_order_limit : xb::kMaxImages;
+  if (a.n_img_max > xb::kMaxImages) return fail(XPSI_B200_EUNSUPPORTED, "image_order_limit > 6");
+  a.phase_interp = phase_interpolant;
+  a.scale_by_energy = 1;
+  a.flux = d_flux.p; a.status = d_status.p;
+  cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_integrate_azinv");
+  g_launches += 2;
+  int status = 0;
+  CK(d_flux.download(flux_out, (size_t)n_energies * n_phases));
+  CK(d_status.download(&status, 1));
+  CK(cudaStreamSynchronize(g_stream));
+  if (status != 0) return fail(status, status == 1 ? "numerical error in pulse integration" : "unsupported configuration");
+  return 0;
+}
+
+int xpsi_b200_energy_integrator(const double* signal, int n_energies, int n_phases,
+                                const double* log10_energies, const double* log10_edges, int n_in,
+                                int phase_interpolant, double* out) {
+  int rc = ensure_stream();
+  if (rc) return rc;
+  if (n_energies < 5 || n_phases < 1 || n_in < 1) return fail(XPSI_B200_EINVAL, "bad dimensions");
+  Dev<double> d_sig, d_x, d_edges, d_out;
+  CK(d_sig.upload(signal, (size_t)n_energies * n_phases));
+  CK(d_x.upload(log10_energies, n_energies));
+  CK(d_edges.upload(log10_edges, n_in + 1));
+  CK(d_out.alloc((size_t)n_in * n_phases));
+  xb::EnergyIntegArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Q = 1; a.n_energies = n_energies; a.n_phases = n_phases; a.n_in = n_in;
+  a.signal = d_sig.p; a.log10_energies = d_x.p; a.log10_edges = d_edges.p; a.interp = phase_interpolant;
+  a.out = d_out.p; a.q_per_b = 1;
+  cudaError_t e = xb::launch_energy_integrator(a, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_energy_integrator");
+  g_launches += 1;
+  std::vector<double> tmp((size_t)n_in * n_phases);
+  CK(d_out.download(tmp.data(), tmp.size()));
+  CK(cudaStreamSynchronize(g_stream));
+  for (int p = 0; p < n_phases; ++p)           // device layout [p][j] -> reference layout [j][p]
+    for (int j = 0; j < n_in; ++j) out[(size_t)j * n_phases + p] = tmp[(size_t)p * n_in + j];
+  return 0;
+}
+
+int xpsi_b200_instrument_fold(const double* matrix, int n_rows, int n_cols, int i0, int i1, int o0,
+                              int o1, const double* signal, int n_phases, double* out) {
+  int rc = ensure_stream();
+  if (rc) return rc;
+  if (i0 < 0 || i1 > n_cols || i1 <= i0 || o0 < 0 || o1 > n_rows || o1 <= o0 || n_phases < 1)
+    return fail(XPSI_B200_EINVAL, "bad ranges");
+  const int n_in = i1 - i0, n_chan = o1 - o0;
+  Dev<double> d_m, d_x, d_out;
+  CK(d_m.upload(matrix + (size_t)o0 * n_cols, (size_t)n_chan * n_cols));
+  // device operand layout is [phase][input interval]
+  std::vector<double> xt((size_t)n_phases * n_in);
+  for (int j = 0; j < n_in; ++j)
+    for (int p = 0; p < n_phases; ++p) xt[(size_t)p * n_in + j] = signal[(size_t)j * n_phases + p];
+  CK(d_x.upload(xt.data(), xt.size()));
+  CK(d_out.alloc((size_t)n_chan * n_phases));
+  xb::FoldArgs a;
+  a.n_cols = 1; a.n_phases = n_phases; a.n_in = n_in; a.n_chan = n_chan;
+  a.matrix = d_m.p; a.ld_matrix = n_cols; a.in0 = i0; a.x = d_x.p; a.out = d_out.p;
+  cudaError_t e = xb::launch_fold(a, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_fold");
+  g_launches += 1;
+  CK(d_out.download(out, (size_t)n_chan * n_phases));
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int xpsi_b200_precomputation(const int* counts, int n_chan, int n_bins, double* out) {
+  int rc = ensure_stream();
+  if (rc) return rc;
+  Dev<int> d_c; Dev<double> d_o;
+  CK(d_c.upload(counts, (size_t)n_chan * n_bins));
+  CK(d_o.alloc(n_chan));
+  cudaError_t e = xb::launch_precomputation(d_c.p, n_chan, n_bins, d_o.p, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_precomputation");
+  g_launches += 1;
+  CK(d_o.download(out, n_chan));
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int xpsi_b200_eval_marginal_likelihood(
+    double exposure_time, const double* phases, int n_bins, const double* counts, int n_chan,
+    const double* const* components, int n_comp, const double* component_phases, int n_phases,
+    const double* phase_shifts, const double* precomp, const double* support, double epsilon,
+    double sigmas, double llzero, int allow_negative, double slim, const double* background,
+    int phase_interpolant, double* lnL, double* expected_counts, double* mcl_background,
+    double* mcl_background_given_support) {
+  int rc = ensure_stream();
+  if (rc) return rc;
+  if (n_bins < 1 || n_bins > 32) return fail(XPSI_B200_EUNSUPPORTED, "1..32 phase bins supported");
+  if (n_comp < 1 || n_chan < 1 || n_phases < 5) return fail(XPSI_B200_EINVAL, "bad dimensions");
+  Dev<double> d_pulses, d_cph, d_sh, d_dph, d_cnt, d_pre, d_sup, d_bg, d_clnl, d_exp, d_mb, d_mbs, d_lnl;
+  Dev<int> d_cst, d_st;
+  const size_t np = (size_t)n_chan * n_phases;
+  CK(d_pulses.alloc(np * n_comp));
+  for (int c = 0; c < n_comp; ++c) {
+    g_h2d += (long long)(np * sizeof(double));
+    CK(cudaMemcpyAsync(d_pulses.p + c * np, components[c], np * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  }
+  CK(d_cph.upload(component_phases, n_phases)); CK(d_sh.upload(phase_shifts, n_comp));
+  CK(d_dph.upload(phases, n_bins + 1)); CK(d_cnt.upload(counts, (size_t)n_chan * n_bins));
+  CK(d_pre.upload(precomp, n_chan)); CK(d_sup.upload(support, (size_t)n_chan * 2));
+  if (background) CK(d_bg.upload(background, (size_t)n_chan * n_bins));
+  CK(d_clnl.alloc(n_chan)); CK(d_cst.alloc(n_chan)); CK(d_exp.alloc((size_t)n_chan * n_bins));
+  CK(d_mb.alloc(n_chan)); CK(d_mbs.alloc(n_chan)); CK(d_lnl.alloc(1)); CK(d_st.alloc(1));
+  CK(cudaMemsetAsync(d_st.p, 0, sizeof(int), g_stream));
+  xb::MarginalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = 1; a.n_comp = n_comp; a.n_chan = n_chan; a.n_phases = n_phases; a.n_bins = n_bins;
+  a.pulses = d_pulses.p; a.comp_phases = d_cph.p; a.phase_shifts = d_sh.p; a.data_phases = d_dph.p;
+  a.counts = d_cnt.p; a.precomp = d_pre.p; a.support = d_sup.p; a.background = background ? d_bg.p : nullptr;
+  a.exposure_time = exposure_time; a.epsilon = epsilon; a.sigmas = sigmas; a.llzero = llzero; a.slim = slim;
+  a.allow_negative = allow_negative; a.interp = phase_interpolant;
+  a.chan_lnL = d_clnl.p; a.chan_status = d_cst.p; a.expected = d_exp.p; a.mcl_bg = d_mb.p;
+  a.mcl_bg_support = d_mbs.p; a.lnL = d_lnl.p; a.status = d_st.p;
+  cudaError_t e = xb::launch_marginal(a, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_marginal");
+  g_launches += 2;
+  int status = 0;
+  CK(d_lnl.download(lnL, 1)); CK(d_st.download(&status, 1));
+  if (expected_counts) CK(d_exp.download(expected_counts, (size_t)n_chan * n_bins));
+  if (mcl_background) CK(d_mb.download(mcl_background, n_chan));
+  if (mcl_background_given_support) CK(d_mbs.download(mcl_background_given_support, n_chan));
+  CK(cudaStreamSynchronize(g_stream));
+  if (status != 0) return fail(status, status == 11 ? "model exceeds data by more than slim sigma" : "marginal integral failed");
+  return 0;
+}
+
+}  // extern "C"
+
+// ===========================================================================
+// batched pipeline
+// ===========================================================================
+struct xpsi_b200_pipeline {
+  xpsi_b200_pipeline_config cfg;
+  int max_batch = 0, slab_rows = 0;
+  std::vector<int> member_component;
+  const xpsi_b200_atmosphere* atm = nullptr;
+  // constants
+  Dev<double> energies, log10E, leaves, phases, phase_cycles, log10_edges, response, data_phases, counts,
+      support, precomp;
+  Dev<int> col_of_q;
+  // per-batch inputs
+  Dev<double> omega, inclination, d_sq, shifts, omega_q, incl_q, cellArea, phi, theta, radial, rsr, params,
+      defl, calpha, lag, maxd, cgamma;
+  Dev<int> n_rings, n_azi;
+  // intermediates / outputs
+  Dev<double> flux, xin, folded, chan_lnL, expected, lnL;
+  Dev<int> chan_status, status_q, status;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float stage_ms[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+__global__ void k_expand_scalars(const double* omega, const double* incl, int B, int M, double* omega_q,
+                                 double* incl_q) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= B * M) return;
+  omega_q[q] = omega[q / M]; incl_q[q] = incl[q / M];
+}
+
+__global__ void k_member_status(const int* status_q, int B, int M, int* status) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int s = 0;
+  for (int m = 0; m < M; ++m) if (status_q[b * M + m] != 0 && s == 0) s = status_q[b * M + m];
+  status[b] = s;
+}
+
+int pipeline_upload(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch* h) {
+  const xpsi_b200_pipeline_config& c = p->cfg;
+  const size_t Q = (size_t)B * c.n_members, R = c.max_rings, A = c.max_azi;
+  CK(p->omega.upload(h->omega, B)); CK(p->inclination.upload(h->inclination, B));
+  CK(p->d_sq.upload(h->d_sq, B)); CK(p->shifts.upload(h->phase_shifts, (size_t)B * c.n_components));
+  CK(p->n_rings.upload(h->n_rings, Q)); CK(p->n_azi.upload(h->n_azi, Q));
+  CK(p->cellArea.upload(h->cellArea, Q * R * A)); CK(p->phi.upload(h->phi, Q * R * A));
+  CK(p->theta.upload(h->theta, Q * R)); CK(p->radial.upload(h->radial, Q * R));
+  CK(p->rsr.upload(h->r_s_over_r, Q * R)); CK(p->params.upload(h->srcParams, Q * R * c.n_params));
+  CK(p->defl.upload(h->deflection, Q * R * c.n_rays)); CK(p->calpha.upload(h->cos_alpha, Q * R * c.n_rays));
+  CK(p->lag.upload(h->lag, Q * R * c.n_rays)); CK(p->maxd.upload(h->maxDeflection, Q * R));
+  CK(p->cgamma.upload(h->cos_gamma, Q * R));
+  return 0;
+}
+
+int pipeline_run(xpsi_b200_pipeline* p, int B) {
+  const xpsi_b200_pipeline_config& c = p->cfg;
+  const int M = c.n_members, C = c.n_components, Q = B * M;
+  const size_t nflux = (size_t)Q * c.n_energies * c.n_phases;
+  CK(cudaEventRecord(p->ev[0], g_stream));
+  k_expand_scalars<<<(Q + 127) / 128, 128, 0, g_stream>>>(p->omega.p, p->inclination.p, B, M, p->omega_q.p, p->incl_q.p);
+  CK(cudaMemsetAsync(p->flux.p, 0, nflux * sizeof(double), g_stream));
+  CK(cudaMemsetAsync(p->status_q.p, 0, Q * sizeof(int), g_stream));
+  xb::AzinvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Q = Q; a.n_rings = c.max_rings; a.n_azi = c.max_azi; a.n_rays = c.n_rays; a.n_energies = c.n_energies;
+  a.n_leaves = c.n_leaves; a.n_phases = c.n_phases; a.n_params = c.n_params;
+  a.n_rings_q = p->n_rings.p; a.n_azi_q = p->n_azi.p;
+  a.omega = p->omega_q.p; a.inclination = p->incl_q.p;
+  a.cellArea = p->cellArea.p; a.phi = p->phi.p; a.theta = p->theta.p; a.theta_ring_stride = 1;
+  a.radial = p->radial.p; a.r_s_over_r = p->rsr.p; a.srcParams = p->params.p; a.params_per_cell = 0;
+  a.radiates = nullptr; a.deflection = p->defl.p; a.cos_alpha = p->calpha.p; a.lag = p->lag.p;
+  a.maxDeflection = p->maxd.p; a.cos_gamma = p->cgamma.p;
+  a.energies = p->energies.p; a.leaves = p->leaves.p; a.phases = p->phases.p;
+  a.hot_atm_ext = c.hot_atm_ext;
+  if (c.hot_atm_ext == XPSI_B200_ATM_NUM4D) { a.hot = p->atm->view; a.slab_ne_max = p->slab_rows; }
+  a.image_order_limit = c.image_order_limit > 0 ? c.image_order_limit : 0;
+  a.n_img_max = c.image_order_limit > 0 ? c.image_order_limit : xb::kMaxImages;
+  a.phase_interp = c.phase_interpolant;
+  a.scale_by_energy = 0;
+  a.flux = p->flux.p; a.status = p->status_q.p;
+  cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_integrate_azinv");
+  CK(cudaEventRecord(p->ev[1], g_stream));
+
+  xb::EnergyIntegArgs ei;
+  memset(&ei, 0, sizeof(ei));
+  ei.Q = Q; ei.n_energies = c.n_energies; ei.n_phases = c.n_phases; ei.n_in = c.n_in;
+  ei.signal = p->flux.p; ei.raw_energies = p->energies.p; ei.div_b = p->d_sq.p; ei.q_per_b = M;
+  ei.log10_energies = p->log10E.p; ei.log10_edges = p->log10_edges.p; ei.interp = c.phase_interpolant;
+  ei.col_of_q = p->col_of_q.p; ei.accumulate = (M > C) ? 1 : 0; ei.out = p->xin.p;
+  if (ei.accumulate)
+    CK(cudaMemsetAsync(p->xin.p, 0, (size_t)B * C * c.n_phases * c.n_in * sizeof(double), g_stream));
+  e = xb::launch_energy_integrator(ei, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_energy_integrator");
+  CK(cudaEventRecord(p->ev[2], g_stream));
+
+  xb::FoldArgs f;
+  f.n_cols = B * C; f.n_phases = c.n_phases; f.n_in = c.n_in; f.n_chan = c.n_chan;
+  f.matrix = p->response.p; f.ld_matrix = c.n_in; f.in0 = 0; f.x = p->xin.p; f.out = p->folded.p;
+  e = xb::launch_fold(f, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_fold");
+  CK(cudaEventRecord(p->ev[3], g_stream));
+
+  k_member_status<<<(B + 127) / 128, 128, 0, g_stream>>>(p->status_q.p, B, M, p->status.p);
+  xb::MarginalArgs m;
+  memset(&m, 0, sizeof(m));
+  m.B = B; m.n_comp = C; m.n_chan = c.n_chan; m.n_phases = c.n_phases; m.n_bins = c.n_bins;
+  m.pulses = p->folded.p; m.comp_phases = p->phase_cycles.p; m.phase_shifts = p->shifts.p;
+  m.data_phases = p->data_phases.p; m.counts = p->counts.p; m.precomp = p->precomp.p; m.support = p->support.p;
+  m.exposure_time = c.exposure_time; m.epsilon = c.epsilon; m.sigmas = c.sigmas; m.llzero = c.llzero;
+  m.slim = c.slim; m.allow_negative = c.allow_negative; m.interp = c.phase_interpolant;
+  m.chan_lnL = p->chan_lnL.p; m.chan_status = p->chan_status.p; m.expected = p->expected.p;
+  m.lnL = p->lnL.p; m.status = p->status.p;
+  e = xb::launch_marginal(m, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_marginal");
+  CK(cudaEventRecord(p->ev[4], g_stream));
+  g_launches += 7;   // expand, integrate, energy, fold, member-status, marginal, channel-sum
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* cfg, int max_batch) {
+  if (ensure_stream() != 0) return nullptr;
+  const xpsi_b200_pipeline_config& c = *cfg;
+  if (max_batch < 1 || c.n_components < 1 || c.n_members < c.n_components || c.n_bins < 1 || c.n_bins > 32 ||
+      c.n_energies < 5 || c.n_leaves < 5 || c.n_phases < 5 ||
+      (c.hot_atm_ext != XPSI_B200_ATM_BB && c.hot_atm_ext != XPSI_B200_ATM_NUM4D) ||
+      (c.hot_atm_ext == XPSI_B200_ATM_NUM4D && !c.hot_atmosphere)) {
+    g_err = "pipeline_create: invalid configuration";
+    return nullptr;
+  }
+  xpsi_b200_pipeline* p = new xpsi_b200_pipeline();
+  p->cfg = c;
+  p->max_batch = max_batch;
+  p->atm = c.hot_atmosphere;
+  p->member_component.assign(c.member_component, c.member_component + c.n_members);
+  p->cfg.member_component = p->member_component.data();
+  const int M = c.n_members, C = c.n_components;
+  const size_t B = max_batch, Q = B * M, R = c.max_rings, A = c.max_azi;
+  std::vector<double> l10E(c.n_energies), l10edges(c.n_in + 1), cyc(c.n_phases);
+  for (int i = 0; i < c.n_energies; ++i) l10E[i] = log10(c.energies[i]);
+  for (int i = 0; i <= c.n_in; ++i) l10edges[i] = log10(c.energy_edges[i]);
+  for (int i = 0; i < c.n_phases; ++i) cyc[i] = c.phases[i] / (2.0 * M_PI);
+  std::vector<int> colq(Q);
+  for (size_t b = 0; b < B; ++b)
+    for (int m = 0; m < M; ++m) colq[b * M + m] = (int)(b * C + c.member_component[m]);
+  std::vector<int> icounts((size_t)c.n_chan * c.n_bins);
+  for (size_t i = 0; i < icounts.size(); ++i) icounts[i] = (int)c.counts[i];
+  Dev<int> d_ic;
+  cudaError_t e = cudaSuccess;
+  auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+  ok(p->energies.upload(c.energies, c.n_energies)); ok(p->log10E.upload(l10E.data(), c.n_energies));
+  ok(p->leaves.upload(c.leaves, c.n_leaves)); ok(p->phases.upload(c.phases, c.n_phases));
+  ok(p->phase_cycles.upload(cyc.data(), c.n_phases)); ok(p->log10_edges.upload(l10edges.data(), c.n_in + 1));
+  ok(p->response.upload(c.response, (size_t)c.n_chan * c.n_in));
+  ok(p->data_phases.upload(c.data_phases, c.n_bins + 1));
+  ok(p->counts.upload(c.counts, (size_t)c.n_chan * c.n_bins)); ok(p->support.upload(c.support, (size_t)c.n_chan * 2));
+  ok(p->col_of_q.upload(colq.data(), Q)); ok(d_ic.upload(icounts.data(), icounts.size()));
+  ok(p->precomp.alloc(c.n_chan));
+  if (e == cudaSuccess) e = xb::launch_precomputation(d_ic.p, c.n_chan, c.n_bins, p->precomp.p, g_stream);
+  ok(p->omega.alloc(B)); ok(p->inclination.alloc(B)); ok(p->d_sq.alloc(B)); ok(p->shifts.alloc(B * C));
+  ok(p->omega_q.alloc(Q)); ok(p->incl_q.alloc(Q)); ok(p->n_rings.alloc(Q)); ok(p->n_azi.alloc(Q));
+  ok(p->cellArea.alloc(Q * R * A)); ok(p->phi.alloc(Q * R * A)); ok(p->theta.alloc(Q * R));
+  ok(p->radial.alloc(Q * R)); ok(p->rsr.alloc(Q * R)); ok(p->params.alloc(Q * R * c.n_params));
+  ok(p->defl.alloc(Q * R * c.n_rays)); ok(p->calpha.alloc(Q * R * c.n_rays)); ok(p->lag.alloc(Q * R * c.n_rays));
+  ok(p->maxd.alloc(Q * R)); ok(p->cgamma.alloc(Q * R));
+  ok(p->flux.alloc(Q * c.n_energies * c.n_phases)); ok(p->xin.alloc(B * C * c.n_phases * c.n_in));
+  ok(p->folded.alloc(B * C * c.n_chan * c.n_phases)); ok(p->chan_lnL.alloc(B * c.n_chan));
+  ok(p->chan_status.alloc(B * c.n_chan)); ok(p->expected.alloc(B * c.n_chan * c.n_bins));
+  ok(p->lnL.alloc(B)); ok(p->status_q.alloc(Q)); ok(p->status.alloc(B));
+  for (int i = 0; i < 5; ++i) ok(cudaEventCreate(&p->ev[i]));
+  ok(cudaStreamSynchronize(g_stream));
+  if (e != cudaSuccess) { cuda_fail(e, "pipeline_create"); delete p; return nullptr; }
+  if (c.hot_atm_ext == XPSI_B200_ATM_NUM4D) p->slab_rows = slab_rows_budget(p->atm->view, c.energies, c.n_energies);
+  g_launches += 1;
+  return p;
+}
+
+void xpsi_b200_pipeline_destroy(xpsi_b200_pipeline* p) {
+  if (!p) return;
+  for (int i = 0; i < 5; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+  delete p;
+}
+
+int xpsi_b200_pipeline_upload(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch* h) {
+  if (!p || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
+  int rc = pipeline_upload(p, B, h);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int xpsi_b200_pipeline_eval_resident(xpsi_b200_pipeline* p, int B) {
+  if (!p || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
+  return pipeline_run(p, B);
+}
+
+int xpsi_b200_pipeline_download(xpsi_b200_pipeline* p, int B, double* lnL, int* status) {
+  if (!p || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
+  CK(p->lnL.download(lnL, B));
+  CK(p->status.download(status, B));
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int xpsi_b200_pipeline_eval(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch* h, double* lnL, int* status) {
+  if (!p || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
+  int rc = pipeline_upload(p, B, h);
+  if (rc) return rc;
+  rc = pipeline_run(p, B);
+  if (rc) return rc;
+  return xpsi_b200_pipeline_download(p, B, lnL, status);
+}
+
+int xpsi_b200_pipeline_fetch(xpsi_b200_pipeline* p, int B, double* flux, double* folded, double* expected) {
+  if (!p || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
+  const xpsi_b200_pipeline_config& c = p->cfg;
+  if (flux) CK(p->flux.download(flux, (size_t)B * c.n_members * c.n_energies * c.n_phases));
+  if (folded) CK(p->folded.download(folded, (size_t)B * c.n_components * c.n_chan * c.n_phases));
+  if (expected) CK(p->expected.download(expected, (size_t)B * c.n_chan * c.n_bins));
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int xpsi_b200_pipeline_stage_ms(xpsi_b200_pipeline* p, float ms[4]) {
+  if (!p) return fail(XPSI_B200_EINVAL, "null pipeline");
+  CK(cudaEventSynchronize(p->ev[4]));
+  for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms[i], p->ev[i], p->ev[i + 1]));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// Kernel argument blocks and launchers (internal; the public surface is
+// include/xpsi_b200.h).  All pointers are DEVICE pointers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace xb {
+
+constexpr int kMaxImages = 6;
+
+// a5: the reference's _preloaded struct (surface_radiation_field/preload.pxd:3-14)
+struct AtmTable {
+  const double* logT; const double* logg; const double* mu; const double* logE;
+  const double* buf;                 // C-order [T][g][mu][E]
+  int nT, ng, nmu, nE;
+  double min_dlogE;                  // smallest spacing of the logE axis (host-computed)
+};
+
+// a1: integrator_for_azimuthal_invariance.integrate, batched over Q member instances.
+// Per-instance arrays are padded to (n_rings, n_azi); true sizes in n_rings_q/n_azi_q
+// (nullptr => every instance uses the padded size).
+struct AzinvArgs {
+  int Q, n_rings, n_azi, n_rays, n_energies, n_leaves, n_phases, n_params;
+  const int* n_rings_q; const int* n_azi_q;
+  const double* omega; const double* inclination;                  // [Q]
+  const double* cellArea; const double* phi;                       // [Q][R][A]
+  const double* theta; int theta_ring_stride;                      // theta[ring*stride] = ring colatitude
+  const double* radial; const double* r_s_over_r;                  // [Q][R]
+  const double* srcParams; int params_per_cell;                    // [Q][R][A][n] or [Q][R][n]
+  const int* radiates;                                             // [Q][R][A]
+  const double* deflection; const double* cos_alpha; const double* lag;   // [Q][R][N_R]
+  const double* maxDeflection; const double* cos_gamma;            // [Q][R]
+  const double* energies; const double* leaves; const double* phases;
+  AtmTable hot;
+  int hot_atm_ext;                   // 1 blackbody, 2 Num4D (hot_wrapper.pyx:72-252)
+  int image_order_limit;             // 0 => infer ceil(maxDeflection/pi)
+  int n_img_max;
+  int phase_interp;                  // tools/core.pyx:21  0 Akima(periodic) 1 Steffen
+  int slab_ne_max;                   // Num4D: energy rows budgeted for the (mu,E) slab
+  int scale_by_energy;               // apply flux /= E keV (pyx:610-612)
+  double* flux;                      // [Q][N_E][N_P], zero-initialised by the caller
+  int* status;                       // [Q]
+};
+cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream);
+
+// a9: tools/energy_integrator.pyx:27-114, one spline per (signal q, phase column)
+struct EnergyIntegArgs {
+  int Q, n_energies, n_phases, n_in;
+  const double* signal;              // [Q][N_E][N_P]
+  const double* raw_energies;        // nullptr, or [N_E] keV: signal is a raw integrator sum and is
+                                     //   first divided by E keV (integrator pyx:610-612)
+  const double* div_b; int q_per_b;  // nullptr, or [Q/q_per_b]: then divided by d_sq (Likelihood.py:361-364)
+  const double* log10_energies;      // [N_E]
+  const double* log10_edges;         // [n_in + 1]
+  int interp;                        // phase interpolant (!), energy_integrator.pyx:54
+  // out[(col_of_q[q]*N_P + p) * n_in + j]  (+= when accumulate)
+  const int* col_of_q;               // nullptr => q
+  int accumulate;
+  const double* attenuation;         // nullptr or [n_in] (Interstellar.__call__)
+  double* out;
+};
+cudaError_t launch_energy_integrator(EnergyIntegArgs a, cudaStream_t stream);
+
+// a11: Instrument.__call__  C[col][chan][p] = sum_in R[chan][in] X[(col,p)][in]
+struct FoldArgs {
+  int n_cols;                        // number of (theta, component) signals
+  int n_phases, n_in, n_chan;
+  const double* matrix;              // [n_chan][ld_matrix], first used column = in0
+  int ld_matrix, in0;
+  const double* x;                   // [n_cols * n_phases][n_in]
+  double* out;                       // [n_cols][n_chan][n_phases]
+};
+cudaError_t launch_fold(FoldArgs a, cudaStream_t stream);
+
+// a12-a14: expected counts + background-marginalised likelihood
+struct MarginalArgs {
+  int B, n_comp, n_chan, n_phases, n_bins;
+  const double* pulses;              // [B][n_comp][n_chan][n_phases]  count rate
+  const double* comp_phases;         // [n_phases] cycles (shared by components)
+  const double* phase_shifts;        // [B][n_comp]
+  const double* data_phases;         // [n_bins + 1]
+  const double* counts;              // [n_chan][n_bins]
+  const double* precomp;             // [n_chan]
+  const double* support;             // [n_chan][2]
+  const double* background;          // nullptr or [n_chan][n_bins]
+  double exposure_time, epsilon, sigmas, llzero, slim;
+  int allow_negative, interp;
+  double* chan_lnL;                  // [B][n_chan]
+  int* chan_status;                  // [B][n_chan]
+  double* expected;                  // nullptr or [B][n_chan][n_bins]
+  double* mcl_bg;                    // nullptr or [B][n_chan]
+  double* mcl_bg_support;            // nullptr or [B][n_chan]
+  double* lnL;                       // [B]
+  int* status;                       // [B]
+};
+cudaError_t launch_marginal(MarginalArgs a, cudaStream_t stream);
+
+// a13: precomputation
+cudaError_t launch_precomputation(const int* counts, int n_chan, int n_bins, double* out,
+                                  cudaStream_t stream);
+
+}  // namespace xb

@@ -1,0 +1,311 @@
+// Expected counts and the background-marginalised Poisson likelihood.
+//
+// Replaces xpsi/tools/compute_expected_counts.pyx:66-197 and
+// xpsi/likelihoods/default_background_marginalisation.pyx:84-447,450-734.
+//
+// One warp per (parameter vector, channel):
+//   * the channel's pulse of each component is splined in phase (the global
+//     phase interpolant), lane j integrates data phase bin j with the
+//     reference's shift / wrap / clip rules;
+//   * the Newton search for the ML background uses warp reductions over bins;
+//   * the marginal integral replaces GSL CQUAD by a fixed-order rule that is
+//     converged far below the reference's epsrel: the log-integrand is concave
+//     in B, so the warp first brackets the super-level set {x(B) >= max-45} by
+//     probing 32 points at a time (zooming while it is under-resolved) and then
+//     applies 24 panels x 8-point Gauss-Legendre with one node per lane.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace xb {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kMaxBins = 32;
+
+__constant__ double c_gl8_x[8] = {
+    -9.60289856497536176e-01, -7.96666477413626728e-01, -5.25532409916328991e-01,
+    -1.83434642495649780e-01, 1.83434642495649780e-01,  5.25532409916328991e-01,
+    7.96666477413626728e-01,  9.60289856497536176e-01};
+__constant__ double c_gl8_w[8] = {
+    1.01228536290377064e-01, 2.22381034453374427e-01, 3.13706645877886880e-01,
+    3.62683783378361657e-01, 3.62683783378361657e-01, 3.13706645877886880e-01,
+    2.22381034453374427e-01, 1.01228536290377064e-01};
+
+// exact integral of the phase spline between a <= b (both inside the node range)
+__device__ __forceinline__ double spline_integ(const double* x, const double* c, int n, double a,
+                                               double b) {
+  if (!(b > a)) return 0.0;
+  const int ia = interval_search(x, n, a);
+  const int ib = interval_search(x, n, b);
+  double val = 0.0;
+  for (int i = ia; i <= ib; ++i) {
+    const double x0 = x[i];
+    const double r1 = (i == ia) ? a - x0 : 0.0;
+    const double r2 = (i == ib) ? b - x0 : x[i + 1] - x0;
+    val += cubic_piece_integral(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3], r1, r2);
+  }
+  return val;
+}
+
+// log of the marginal integrand without the -A shift (pyx:84-138); -inf encodes
+// "integrand is exactly zero"
+__device__ __forceinline__ double log_integrand(const double* star, const double* data, int n,
+                                                double SCALE, double B) {
+  double x = 0.0;
+  for (int j = 0; j < n; ++j) {
+    const double c = SCALE * (star[j] + B);
+    if (c > 0.0) x += data[j] * log(c) - c;
+    else if (are_equal(c, 0.0) && are_equal(data[j], 0.0)) {}
+    else return -INFINITY;
+  }
+  return x;
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a) {
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int chan = blockIdx.x * kWarpsPerBlock + warp;
+  const int b = blockIdx.y;
+  const int N_P = a.n_phases, n = a.n_bins;
+  extern __shared__ double smem[];
+  double* s_x = smem;                                            // comp phases (shared by warps)
+  double* w_base = smem + N_P + (long)warp * (5 * N_P + 2 * kMaxBins);
+  double* s_y = w_base;                                          // [N_P]
+  double* s_c = s_y + N_P;                                       // [N_P][4]
+  double* s_star = s_c + 4 * N_P;                                // [32]
+  double* s_data = s_star + kMaxBins;                            // [32]
+  for (int i = threadIdx.x; i < N_P; i += blockDim.x) s_x[i] = a.comp_phases[i];
+  __syncthreads();
+  if (chan >= a.n_chan) return;            // whole warps only; no block barrier below
+
+  const double nd = (double)n;
+  const double T = a.exposure_time;
+  const double SCALE = T / nd;
+  const bool periodic = (a.interp != kSteffen);
+
+  // ---- expected star count rate per bin (compute_expected_counts.pyx:66-197) ----------
+  double star = 0.0;
+  for (int c = 0; c < a.n_comp; ++c) {
+    const double* pulse = a.pulses + (((long)b * a.n_comp + c) * a.n_chan + chan) * N_P;
+    for (int i = lane; i < N_P; i += 32) s_y[i] = pulse[i];
+    __syncwarp();
+    for (int i = lane; i < N_P - 1; i += 32) {
+      double bb, cc, dd;
+      interp_coeffs(a.interp, periodic, s_x, s_y, N_P, i, &bb, &cc, &dd);
+      s_c[4 * i] = s_y[i]; s_c[4 * i + 1] = bb; s_c[4 * i + 2] = cc; s_c[4 * i + 3] = dd;
+    }
+    __syncwarp();
+    if (lane < n) {
+      const double shift = a.phase_shifts[(long)b * a.n_comp + c];
+      double pa = a.data_phases[lane] + shift;
+      double pb = a.data_phases[lane + 1] + shift;
+      if (are_equal(pb - pa, 1.0)) { pa = 0.0; pb = 1.0; }
+      else { pa -= floor(pa); pb -= floor(pb); }
+      if (pa < pb) {
+        const double v = spline_integ(s_x, s_c, N_P, pa, pb);
+        if (v > 0.0 || a.allow_negative) star += v;
+      } else {
+        double v = spline_integ(s_x, s_c, N_P, pa, 1.0);
+        if (v > 0.0 || a.allow_negative) star += v;
+        v = spline_integ(s_x, s_c, N_P, 0.0, pb);
+        if (v > 0.0 || a.allow_negative) star += v;
+      }
+    }
+    __syncwarp();
+  }
+  if (star < 0.0) star = 0.0;
+  double d = 0.0;
+  if (lane < n) {
+    if (a.background) star += a.background[(long)chan * n + lane];
+    star *= nd;                                                // pyx:659-665
+    d = a.counts[(long)chan * n + lane];
+  } else star = 0.0;
+  s_star[lane] = star; s_data[lane] = d;
+  __syncwarp();
+  double av_STAR = warp_sum(star);
+  double av_DATA = warp_sum(d);
+
+  int status = 0;
+  double loglike = 0.0, B = 0.0;
+  const double sup0 = a.support[2 * chan], sup1 = a.support[2 * chan + 1];
+
+  if (a.slim >= 0.0) {                                         // pyx:677-684
+    const double limit = av_STAR * SCALE - a.slim * sqrt(av_STAR * SCALE) - av_DATA;
+    if (limit > 0.0) status = 1;
+  }
+  av_STAR /= nd;
+  av_DATA /= T;
+
+  if (status == 0) {
+    if (are_equal(av_DATA, 0.0) && are_equal(av_STAR, 0.0)) {  // pyx:287-301
+      double lower = 0.0;
+      if (lower < sup0) lower = sup0;
+      double upper = 10.0 / T;
+      if (upper > sup1 && sup1 > 0.0) upper = sup1;
+      B = 0.0;
+      loglike = log((exp(-1.0 * lower * T) - exp(-1.0 * upper * T)) / T);
+    } else {
+      double B_min = 0.0;
+      B = av_DATA - av_STAR;
+      if (B <= B_min) {                                        // pyx:309-332
+        const unsigned zero_star = __ballot_sync(0xffffffffu, lane < n && are_equal(star, 0.0));
+        if (zero_star) {
+          // smallest positive count among the bins
+          double m = (lane < n && d > 0.0) ? d : INFINITY;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+          if (isinf(m)) { B = 0.0; B_min = 0.0; }
+          else { B = 0.01 * m / SCALE; B_min = 0.1 * B; }
+        } else {
+          B = B_min;
+        }
+      }
+      // Newton iterations (pyx:336-352); delta() = pyx:140-173
+      double std, dB;
+      {
+        const double r = (lane < n) ? d / (star + B) : 0.0;
+        const double y = warp_sum(r);
+        const double x = warp_sum((lane < n) ? r / (star + B) : 0.0);
+        std = sqrt(2.0 / (2.0 * x));
+        dB = -1.0 * (2.0 * T - 2.0 * y) / (2.0 * x);
+      }
+      int counter = 0, iters = 0;
+      while (fabs(dB) > a.epsilon * std && counter < 2) {
+        B += dB;
+        if (B < B_min) {
+          if (B_min > 0.0) counter += 1; else counter = 2;
+          B = B_min;
+        }
+        const double r = (lane < n) ? d / (star + B) : 0.0;
+        const double y = warp_sum(r);
+        const double x = warp_sum((lane < n) ? r / (star + B) : 0.0);
+        std = sqrt(2.0 / (2.0 * x));
+        dB = -1.0 * (2.0 * T - 2.0 * y) / (2.0 * x);
+        if (++iters > 500) { status = 2; break; }
+      }
+      double std_est = warp_sum((lane < n) ? d / ((star + B) * (star + B)) : 0.0);
+      std_est = std_est > 0.0 ? sqrt(1.0 / std_est) : 1e90;
+      double lower = B - a.sigmas * std_est;
+      double upper = B + a.sigmas * std_est;
+      if (lower < B_min) lower = B_min;
+      double Bfi = B;                                          // pyx:366-393
+      if (lower < sup0) {
+        lower = sup0;
+        if (upper < sup0 && sup1 > 0.0) { upper = sup1; Bfi = sup0; }
+        else if (upper < sup0) { upper = sup0 + a.sigmas * std_est; Bfi = sup0; }
+      }
+      if (upper > sup1 && sup1 > 0.0) {
+        upper = sup1;
+        if (lower > sup1) { lower = sup0; Bfi = sup1; }
+      }
+      if (Bfi < lower) Bfi = lower; else if (Bfi > upper) Bfi = upper;
+      // A: log-integrand at the clipped ML background (pyx:397-408)
+      double A;
+      {
+        double term = 0.0;
+        if (lane < n) {
+          const double c = SCALE * (star + Bfi);
+          if (c > 0.0) term = d * log(c) - c;
+          else if (are_equal(c, 0.0) && are_equal(d, 0.0)) term = 0.0;
+          else term = a.llzero;
+        }
+        A = warp_sum(term);
+      }
+      // ---- marginal integral over [lower, upper] (replaces pyx:416-419) -------------
+      double result = 0.0;
+      if (status == 0 && upper > lower) {
+        double lo = lower, hi = upper;
+        for (int zoom = 0; zoom < 6; ++zoom) {
+          const double h = (hi - lo) / 31.0;
+          const double Bp = (lane == 31) ? hi : lo + h * lane;
+          const double xl = log_integrand(s_star, s_data, n, SCALE, Bp);
+          const double ref = fmax(warp_max(xl), A);
+          const unsigned mask = __ballot_sync(0xffffffffu, xl >= ref - 45.0);
+          if (mask == 0u) {              // peak narrower than the probe spacing: centre on Bfi
+            lo = fmax(lo, Bfi - h); hi = fmin(hi, Bfi + h);
+            continue;
+          }
+          const int first = __ffs(mask) - 1, last = 31 - __clz(mask);
+          const double nlo = (first > 0) ? lo + h * (first - 1) : lo;
+          const double nhi = (last < 31) ? ((last + 1 == 31) ? hi : lo + h * (last + 1)) : hi;
+          const bool resolved = (last - first) >= 8;
+          lo = nlo; hi = nhi;
+          if (resolved) break;
+        }
+        const double hp = (hi - lo) / 24.0;
+        double acc = 0.0;
+#pragma unroll 1
+        for (int batch = 0; batch < 6; ++batch) {
+          const int node = batch * 32 + lane;
+          const int panel = node >> 3, g = node & 7;
+          const double Bq = lo + hp * ((double)panel + 0.5 + 0.5 * c_gl8_x[g]);
+          const double xq = log_integrand(s_star, s_data, n, SCALE, Bq);
+          acc += 0.5 * hp * c_gl8_w[g] * exp(xq - A);           // exp(-inf) = 0
+        }
+        result = warp_sum(acc);
+      }
+      if (result > 0.0) loglike = log(result) + A + a.precomp[chan];   // pyx:423-424
+      else if (status == 0) status = 2;
+    }
+  }
+
+  // ---- outputs (pyx:431-447) --------------------------------------------------------
+  if (lane == 0) {
+    a.chan_lnL[(long)b * a.n_chan + chan] = loglike;
+    a.chan_status[(long)b * a.n_chan + chan] = status;
+    if (a.mcl_bg) a.mcl_bg[(long)b * a.n_chan + chan] = B * T;
+  }
+  double Bc = B;
+  if (Bc < sup0) Bc = sup0; else if (Bc > sup1 && sup1 > 0.0) Bc = sup1;
+  if (lane == 0 && a.mcl_bg_support) a.mcl_bg_support[(long)b * a.n_chan + chan] = Bc * T;
+  if (a.expected && lane < n)
+    a.expected[((long)b * a.n_chan + chan) * n + lane] = (status == 0) ? SCALE * (star + Bc) : star;
+}
+
+// ordered reduction over channels; the first failing channel decides the status
+// (the reference breaks out of its channel loop there, pyx:681-684,716-719)
+__global__ void k_sum_channels(const double* chan_lnL, const int* chan_status, int n_chan,
+                               double* lnL, int* status) {
+  const int b = blockIdx.x;
+  __shared__ double s_sum[256];
+  __shared__ int s_bad[256];
+  double s = 0.0;
+  int bad = n_chan;
+  for (int c = threadIdx.x; c < n_chan; c += blockDim.x) {
+    s += chan_lnL[(long)b * n_chan + c];
+    if (chan_status[(long)b * n_chan + c] != 0 && c < bad) bad = c;
+  }
+  s_sum[threadIdx.x] = s; s_bad[threadIdx.x] = bad;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+      s_bad[threadIdx.x] = min(s_bad[threadIdx.x], s_bad[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    lnL[b] = s_sum[0];
+    // a status already raised upstream (integrator failure) is kept
+    if (status[b] == 0) status[b] = (s_bad[0] < n_chan) ? 10 + chan_status[(long)b * n_chan + s_bad[0]] : 0;
+  }
+}
+
+cudaError_t launch_marginal(MarginalArgs a, cudaStream_t stream) {
+  if (a.n_bins > kMaxBins || a.n_bins < 1) return cudaErrorNotSupported;
+  if (a.n_phases < 5) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)a.n_phases + kWarpsPerBlock * (5ul * a.n_phases + 2 * kMaxBins)) * sizeof(double);
+  dim3 grid((a.n_chan + kWarpsPerBlock - 1) / kWarpsPerBlock, a.B);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_marginal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k_marginal<<<grid, 32 * kWarpsPerBlock, smem, stream>>>(a);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  if (a.lnL) {
+    k_sum_channels<<<a.B, 256, 0, stream>>>(a.chan_lnL, a.chan_status, a.n_chan, a.lnL, a.status);
+    err = cudaGetLastError();
+  }
+  return err;
+}
+
+}  // namespace xb

@@ -1,0 +1,171 @@
+// Instrument-folding kernels: energy integration of the specific flux over the
+// instrument's input intervals, and the response-matrix contraction.
+//
+// Replaces xpsi/tools/energy_integrator.pyx:27-114 and the numpy.dot in
+// xpsi/Instrument.py:192-197 (called from xpsi/Signal.py:419-439).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace xb {
+
+// ---------------------------------------------------------------------------
+// energy_integrator: one CTA per (signal q, phase column p).  The spline over
+// log10 E (the *phase* interpolant, energy_integrator.pyx:54) is held as
+// per-interval cubic coefficients in shared memory; threads then own input
+// intervals and integrate the exact piecewise cubic across them.
+// Output is written [signal column][input interval] (interval fastest) so the
+// response contraction reads both operands along K.
+// ---------------------------------------------------------------------------
+constexpr int kEIThreads = 128;
+
+__global__ void __launch_bounds__(kEIThreads) k_energy_integrator(EnergyIntegArgs a) {
+  const int p = blockIdx.x, q = blockIdx.y;
+  const int N_E = a.n_energies, N_P = a.n_phases, n_in = a.n_in;
+  extern __shared__ double smem[];
+  double* s_x = smem;                 // log10 E
+  double* s_y = s_x + N_E;            // 10^x * signal * ln 10   (pyx:81-82)
+  double* s_c = s_y + N_E;            // [N_E-1][4]
+  const double div = a.div_b ? a.div_b[q / a.q_per_b] : 1.0;
+  const double* sig = a.signal + (long)q * N_E * N_P + p;
+  for (int e = threadIdx.x; e < N_E; e += kEIThreads) {
+    const double x = a.log10_energies[e];
+    s_x[e] = x;
+    double v = sig[(long)e * N_P];
+    if (a.raw_energies) v = v / (a.raw_energies[e] * kKeV);
+    if (a.div_b) v = v / div;
+    s_y[e] = pow(10.0, x) * v * log(10.0);
+  }
+  __syncthreads();
+  const bool periodic = (a.interp != kSteffen);
+  for (int i = threadIdx.x; i < N_E - 1; i += kEIThreads) {
+    double b, c, d;
+    interp_coeffs(a.interp, periodic, s_x, s_y, N_E, i, &b, &c, &d);
+    s_c[4 * i] = s_y[i]; s_c[4 * i + 1] = b; s_c[4 * i + 2] = c; s_c[4 * i + 3] = d;
+  }
+  __syncthreads();
+  const double xmin = s_x[0], xmax = s_x[N_E - 1];
+  const int col = a.col_of_q ? a.col_of_q[q] : q;
+  double* out = a.out + ((long)col * N_P + p) * n_in;
+  for (int j = threadIdx.x; j < n_in; j += kEIThreads) {
+    double lo = a.log10_edges[j];
+    double hi = a.log10_edges[j + 1];
+    double val = 0.0;
+    // the reference stops after the first interval that pokes past the last
+    // energy (pyx:91-103): later intervals stay zero
+    if (!(lo > xmax) && !(j > 0 && a.log10_edges[j] > xmax)) {
+      if (hi > xmax) hi = xmax;
+      if (lo < xmin) lo = (xmin - lo <= 1.0e-9 * (1.0 + fabs(xmin))) ? xmin : nan("");
+      if (lo == lo && hi > lo) {
+        const int ia = interval_search(s_x, N_E, lo);
+        const int ib = interval_search(s_x, N_E, hi);
+        for (int i = ia; i <= ib; ++i) {
+          const double x0 = s_x[i];
+          const double r1 = (i == ia) ? lo - x0 : 0.0;
+          const double r2 = (i == ib) ? hi - x0 : s_x[i + 1] - x0;
+          val += cubic_piece_integral(s_c[4 * i], s_c[4 * i + 1], s_c[4 * i + 2], s_c[4 * i + 3], r1, r2);
+        }
+      } else if (lo != lo) {
+        val = lo;
+      }
+    }
+    if (a.attenuation) val *= a.attenuation[j];
+    if (a.accumulate) atomicAdd(out + j, val); else out[j] = val;
+  }
+}
+
+cudaError_t launch_energy_integrator(EnergyIntegArgs a, cudaStream_t stream) {
+  if (a.n_energies < 5) return cudaErrorInvalidValue;       // Akima needs >= 5 nodes
+  const size_t smem = (size_t)a.n_energies * 6 * sizeof(double);
+  dim3 grid(a.n_phases, a.Q);
+  k_energy_integrator<<<grid, kEIThreads, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Response contraction.  out[col][chan][p] = sum_k R[chan][in0+k] * X[col*P+p][k]
+// A plain fp64 SIMT GEMM: 64x64 output tile per CTA, 16-deep K slabs staged in
+// shared memory (transposed so the inner product reads are conflict-free), each
+// thread a 4x4 register block.  fp64 has no tcgen05 kind; DFMA is the roofline.
+// ---------------------------------------------------------------------------
+constexpr int kBM = 64, kBN = 64, kBK = 16, kFoldThreads = 256;
+
+__global__ void __launch_bounds__(kFoldThreads) k_fold(FoldArgs a) {
+  __shared__ double As[kBK][kBM + 4];
+  __shared__ double Bs[kBK][kBN + 4];
+  const int m0 = blockIdx.y * kBM;       // channel tile
+  const long n0 = (long)blockIdx.x * kBN;  // (col,p) tile
+  const long N = (long)a.n_cols * a.n_phases;
+  const int K = a.n_in;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  // loader mapping: 64 rows x 16 k = 1024 elements, 4 per thread, k fastest
+  const int lr = threadIdx.x / 4;            // 0..63 row
+  const int lk = (threadIdx.x % 4) * 4;      // 0,4,8,12
+  for (int k0 = 0; k0 < K; k0 += kBK) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + lk + u;
+      const int m = m0 + lr;
+      const long n = n0 + lr;
+      As[lk + u][lr] = (m < a.n_chan && k < K) ? a.matrix[(long)m * a.ld_matrix + a.in0 + k] : 0.0;
+      Bs[lk + u][lr] = (n < N && k < K) ? a.x[n * K + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kBK; ++k) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= a.n_chan) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      const long col = n / a.n_phases;
+      const int p = (int)(n - col * a.n_phases);
+      a.out[(col * a.n_chan + m) * a.n_phases + p] = acc[i][j];
+    }
+  }
+}
+
+cudaError_t launch_fold(FoldArgs a, cudaStream_t stream) {
+  const long N = (long)a.n_cols * a.n_phases;
+  dim3 grid((unsigned)((N + kBN - 1) / kBN), (unsigned)((a.n_chan + kBM - 1) / kBM));
+  k_fold<<<grid, kFoldThreads, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// precomputation: -sum_j ln(d_ij!)   (default_background_marginalisation.pyx:38-68)
+// ---------------------------------------------------------------------------
+__global__ void k_precomputation(const int* counts, int n_chan, int n_bins, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_chan) return;
+  double s = 0.0;
+  for (int j = 0; j < n_bins; ++j) s += lgamma((double)(unsigned int)counts[(long)i * n_bins + j] + 1.0);
+  out[i] = -1.0 * s;
+}
+
+cudaError_t launch_precomputation(const int* counts, int n_chan, int n_bins, double* out,
+                                  cudaStream_t stream) {
+  k_precomputation<<<(n_chan + 127) / 128, 128, 0, stream>>>(counts, n_chan, n_bins, out);
+  return cudaGetLastError();
+}
+
+}  // namespace xb

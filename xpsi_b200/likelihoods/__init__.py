@@ -1,0 +1,77 @@
+"""GPU drop-ins for ``xpsi.likelihoods.default_background_marginalisation``."""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from ..tools import phase_interpolant_id
+
+
+def precomputation(data):
+    """-sum_j ln(d_ij!) per channel
+    (xpsi/likelihoods/default_background_marginalisation.pyx:38-68)."""
+    data = _lib.as_i4(data, 2)
+    out = np.empty(data.shape[0], dtype=np.float64)
+    _lib.check(_lib.lib.xpsi_b200_precomputation(_lib.iptr(data), data.shape[0], data.shape[1],
+                                                 _lib.dptr(out)))
+    return out
+
+
+def eval_marginal_likelihood(exposure_time, phases, counts, components, component_phases,
+                             phase_shifts, neg_sum_ln_data_factorial, support,
+                             workspace_intervals, epsabs, epsrel, epsilon, sigmas, llzero,
+                             allow_negative=False, slim=20.0, background=None):
+    """Same signature and 4-tuple return as
+    xpsi/likelihoods/default_background_marginalisation.pyx:450-466.
+
+    ``workspace_intervals``, ``epsabs`` and ``epsrel`` configure GSL CQUAD in the
+    reference; the GPU quadrature is fixed-order and converged below 1e-12, so
+    they are accepted and ignored.  On the two paths where the reference
+    returns a *random* near-``llzero`` number (slim early exit, non-positive
+    integral) the same convention is followed.
+    """
+    phases = _lib.as_f8(phases, 1)
+    counts = _lib.as_f8(counts, 2)
+    support = _lib.as_f8(support, 2)
+    precomp = _lib.as_f8(neg_sum_ln_data_factorial, 1)
+    comps = [_lib.as_f8(c, 2) for c in components]
+    cph = [_lib.as_f8(p, 1) for p in component_phases]
+    shifts = _lib.as_f8(phase_shifts, 1)
+    n_chan = counts.shape[0]
+    if support.shape[0] != n_chan:
+        raise TypeError('The number of energy channels in the background support does not match to that of the data.')
+    if (support[:, 1] == 0).any():
+        raise TypeError('Background upper limit cannot be set to 0.')
+    if ((support[:, 1] > 0) & (support[:, 1] - support[:, 0] < 0)).any():
+        raise TypeError('Background upper limit must be higher than the lower limit.')
+    for c, p in zip(comps, cph):
+        if c.shape != (n_chan, cph[0].shape[0]) or not np.array_equal(p, cph[0]):
+            raise NotImplementedError("xpsi_b200: components must share one phase grid")
+    if isinstance(allow_negative, (bool, np.bool_, int)):
+        allow = int(bool(allow_negative))
+    else:
+        vals = [bool(v) for v in allow_negative]
+        if len(vals) != len(comps):
+            raise ValueError('Number of allow_negative declarations does not match the number of components..')
+        if any(v != vals[0] for v in vals):
+            raise NotImplementedError("xpsi_b200: per-component allow_negative must be uniform")
+        allow = int(vals[0])
+    bg = _lib.as_f8(background, 2) if background is not None else None
+    n_bins = phases.shape[0] - 1
+    arr = (_lib.c_double_p * len(comps))(*[_lib.dptr(c) for c in comps])
+    lnL = C.c_double(0.0)
+    star = np.zeros((n_chan, n_bins), dtype=np.float64)
+    mcl = np.zeros(n_chan, dtype=np.float64)
+    mcl_s = np.zeros(n_chan, dtype=np.float64)
+    rc = _lib.lib.xpsi_b200_eval_marginal_likelihood(
+        float(exposure_time), _lib.dptr(phases), n_bins, _lib.dptr(counts), n_chan, arr, len(comps),
+        _lib.dptr(cph[0]), cph[0].shape[0], _lib.dptr(shifts), _lib.dptr(precomp), _lib.dptr(support),
+        float(epsilon), float(sigmas), float(llzero), allow, float(slim),
+        _lib.dptr(bg) if bg is not None else None, phase_interpolant_id(),
+        C.cast(C.pointer(lnL), _lib.c_double_p), _lib.dptr(star), _lib.dptr(mcl), _lib.dptr(mcl_s))
+    if rc in (_lib.ESLIM, _lib.EQUADRATURE):
+        return (llzero * (0.1 + 0.9 * np.random.rand()), star, mcl, mcl_s)
+    if rc == _lib.EUNSUPPORTED:
+        raise NotImplementedError("xpsi_b200: " + _lib.last_error())
+    _lib.check(rc)
+    return (lnL.value, star, mcl, mcl_s)

@@ -1,0 +1,202 @@
+"""Batched likelihood pipeline: integrate -> energy-integrate -> fold -> marginal
+likelihood for B parameter vectors per call, entirely on one GPU.
+
+This is the batched sibling of ``xpsi.Likelihood.__call__``
+(xpsi/Likelihood.py:297-511): the scalar call evaluates one parameter vector
+through Python glue between four compiled stages; here the same four stages run
+as kernels over a leading batch axis and only ``lnL[B]`` / ``status[B]`` return.
+Inputs are the per-member integrator arguments that ``HotRegion.embed``
+produces (xpsi/HotRegion.py:1033-1070).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+MEMBER_FIELDS = ("cellArea", "phi", "theta", "radial", "r_s_over_r", "srcParams",
+                 "deflection", "cos_alpha", "lag", "maxDeflection", "cos_gamma")
+
+
+class HostBatch:
+    """Padded, C-contiguous host arrays for B parameter vectors x M members."""
+
+    def __init__(self, B, M, C_, max_rings, max_azi, n_rays, n_params, pinned=False):
+        self.B, self.M = B, M
+        Q = B * M
+        alloc = self._pinned if pinned else np.zeros
+        self.omega = alloc((B,), np.float64)
+        self.inclination = alloc((B,), np.float64)
+        self.d_sq = alloc((B,), np.float64)
+        self.phase_shifts = alloc((B, C_), np.float64)
+        self.n_rings = alloc((Q,), np.int32)
+        self.n_azi = alloc((Q,), np.int32)
+        self.cellArea = alloc((Q, max_rings, max_azi), np.float64)
+        self.phi = alloc((Q, max_rings, max_azi), np.float64)
+        self.theta = alloc((Q, max_rings), np.float64)
+        self.radial = alloc((Q, max_rings), np.float64)
+        self.r_s_over_r = alloc((Q, max_rings), np.float64)
+        self.srcParams = alloc((Q, max_rings, n_params), np.float64)
+        self.deflection = alloc((Q, max_rings, n_rays), np.float64)
+        self.cos_alpha = alloc((Q, max_rings, n_rays), np.float64)
+        self.lag = alloc((Q, max_rings, n_rays), np.float64)
+        self.maxDeflection = alloc((Q, max_rings), np.float64)
+        self.cos_gamma = alloc((Q, max_rings), np.float64)
+
+    @staticmethod
+    def _pinned(shape, dtype):
+        import torch   # device-memory plumbing only: page-locked host staging
+        t = torch.zeros(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32).pin_memory()
+        a = t.numpy()
+        a._keep = t if hasattr(a, "__dict__") else None
+        HostBatch._pins.append(t)
+        return a
+    _pins = []
+
+    def set_member(self, b, m, cellArea, theta, phi, radial, r_s_over_r, srcCellParams,
+                   deflection, cos_alpha, lag, maxDeflection, cos_gamma):
+        """Fill member ``m`` of parameter vector ``b`` from the reference-shaped
+        integrator arguments (cellArea/theta/phi ``[R,A]``, srcCellParams ``[R,A,n]``)."""
+        q = b * self.M + m
+        R, A = cellArea.shape
+        if R > self.cellArea.shape[1] or A > self.cellArea.shape[2]:
+            raise ValueError("mesh %dx%d exceeds the padded size" % (R, A))
+        self.n_rings[q] = R
+        self.n_azi[q] = A
+        self.cellArea[q].fill(0.0)
+        self.cellArea[q, :R, :A] = cellArea
+        self.phi[q, :R, :A] = phi
+        self.theta[q, :R] = theta[:, 0]
+        self.radial[q, :R] = radial
+        self.r_s_over_r[q, :R] = r_s_over_r
+        # all cells of a ring share the parameter vector of its first radiating
+        # cell (integrator_for_azimuthal_invariance.pyx:286-296,463)
+        rad = cellArea > 0.0
+        J = np.argmax(rad, axis=1)
+        self.srcParams[q, :R] = srcCellParams[np.arange(R), J]
+        self.deflection[q, :R] = deflection
+        self.cos_alpha[q, :R] = cos_alpha
+        self.lag[q, :R] = lag
+        self.maxDeflection[q, :R] = maxDeflection
+        self.cos_gamma[q, :R] = cos_gamma
+
+    def nbytes(self):
+        return sum(getattr(self, f).nbytes for f in
+                   ("omega", "inclination", "d_sq", "phase_shifts", "n_rings", "n_azi") + MEMBER_FIELDS)
+
+    def struct(self):
+        s = _lib.Batch()
+        for f in ("omega", "inclination", "d_sq", "phase_shifts") + MEMBER_FIELDS:
+            setattr(s, f, _lib.dptr(getattr(self, f)))
+        s.n_rings = _lib.iptr(self.n_rings)
+        s.n_azi = _lib.iptr(self.n_azi)
+        return s
+
+
+class BatchedLikelihood:
+    """Device-resident likelihood for a fixed model configuration.
+
+    Parameters mirror what the reference objects hold: ``energies`` (keV,
+    ``Signal.energies``), ``leaves``/``phases`` (radians, ``HotRegion``),
+    ``response[n_chan, n_in]`` + ``energy_edges`` (``Instrument``), ``counts``,
+    ``data_phases``, ``exposure_time`` (``Data``), ``support`` and the
+    ``eval_marginal_likelihood`` settings (``CustomSignal``).
+    """
+
+    def __init__(self, *, member_component, max_rings, max_azi, n_rays, energies, leaves, phases,
+                 hot_atm_ext, hot_atmosphere=None, image_order_limit=None, response, energy_edges,
+                 counts, data_phases, exposure_time, support=None, epsilon=1.0e-3, sigmas=10.0,
+                 llzero=-1.0e90, slim=20.0, allow_negative=False, n_params=2, max_batch=64,
+                 phase_interpolant='Akima'):
+        self._keep = []
+
+        def keep(a, dt=np.float64):
+            a = np.ascontiguousarray(a, dtype=dt)
+            self._keep.append(a)
+            return a
+        mc = keep(member_component, np.int32)
+        self.n_members = int(mc.size)
+        self.n_components = int(mc.max()) + 1
+        energies, leaves, phases = keep(energies), keep(leaves), keep(phases)
+        response, energy_edges = keep(response), keep(energy_edges)
+        counts, data_phases = keep(counts), keep(data_phases)
+        n_chan, n_in = response.shape
+        if support is None:
+            support = -1.0 * np.ones((n_chan, 2))
+            support[:, 0] = 0.0
+        support = keep(support)
+        self.atm = _lib.Atmosphere.get(hot_atmosphere) if hot_atm_ext == 2 else None
+        cfg = _lib.PipelineConfig()
+        cfg.n_components, cfg.n_members, cfg.member_component = self.n_components, self.n_members, _lib.iptr(mc)
+        cfg.max_rings, cfg.max_azi, cfg.n_rays, cfg.n_params = int(max_rings), int(max_azi), int(n_rays), int(n_params)
+        cfg.n_energies, cfg.energies = energies.size, _lib.dptr(energies)
+        cfg.n_leaves, cfg.leaves = leaves.size, _lib.dptr(leaves)
+        cfg.n_phases, cfg.phases = phases.size, _lib.dptr(phases)
+        cfg.hot_atm_ext = int(hot_atm_ext)
+        cfg.hot_atmosphere = self.atm.handle if self.atm is not None else None
+        cfg.image_order_limit = int(image_order_limit) if image_order_limit else 0
+        cfg.phase_interpolant = _lib.INTERPOLANTS[phase_interpolant]
+        cfg.n_in, cfg.energy_edges = n_in, _lib.dptr(energy_edges)
+        cfg.n_chan, cfg.response = n_chan, _lib.dptr(response)
+        cfg.n_bins, cfg.data_phases = data_phases.size - 1, _lib.dptr(data_phases)
+        cfg.counts, cfg.support = _lib.dptr(counts), _lib.dptr(support)
+        cfg.exposure_time, cfg.epsilon, cfg.sigmas = float(exposure_time), float(epsilon), float(sigmas)
+        cfg.llzero, cfg.slim, cfg.allow_negative = float(llzero), float(slim), int(bool(allow_negative))
+        self.cfg = cfg
+        self.max_batch = int(max_batch)
+        self.shape = dict(max_rings=int(max_rings), max_azi=int(max_azi), n_rays=int(n_rays),
+                          n_params=int(n_params), n_energies=energies.size, n_phases=phases.size,
+                          n_chan=n_chan, n_in=n_in, n_bins=data_phases.size - 1)
+        self.handle = _lib.lib.xpsi_b200_pipeline_create(C.byref(cfg), self.max_batch)
+        if not self.handle:
+            raise _lib.XpsiB200Error("pipeline_create failed: %s" % _lib.last_error())
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib.xpsi_b200_pipeline_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def new_batch(self, B, pinned=False):
+        s = self.shape
+        return HostBatch(B, self.n_members, self.n_components, s["max_rings"], s["max_azi"],
+                         s["n_rays"], s["n_params"], pinned=pinned)
+
+    def __call__(self, batch):
+        """Host buffers in, ``(lnL[B], status[B])`` out (H2D + kernels + D2H)."""
+        lnL = np.empty(batch.B, dtype=np.float64)
+        status = np.empty(batch.B, dtype=np.int32)
+        st = batch.struct()
+        _lib.check(_lib.lib.xpsi_b200_pipeline_eval(self.handle, batch.B, C.byref(st),
+                                                    _lib.dptr(lnL), _lib.iptr(status)))
+        return lnL, status
+
+    def upload(self, batch):
+        st = batch.struct()
+        _lib.check(_lib.lib.xpsi_b200_pipeline_upload(self.handle, batch.B, C.byref(st)))
+
+    def eval_resident(self, B):
+        _lib.check(_lib.lib.xpsi_b200_pipeline_eval_resident(self.handle, B))
+
+    def download(self, B):
+        lnL = np.empty(B, dtype=np.float64)
+        status = np.empty(B, dtype=np.int32)
+        _lib.check(_lib.lib.xpsi_b200_pipeline_download(self.handle, B, _lib.dptr(lnL), _lib.iptr(status)))
+        return lnL, status
+
+    def fetch(self, B, flux=True, folded=True, expected=True):
+        s = self.shape
+        f = np.empty((B * self.n_members, s["n_energies"], s["n_phases"])) if flux else None
+        g = np.empty((B, self.n_components, s["n_chan"], s["n_phases"])) if folded else None
+        e = np.empty((B, s["n_chan"], s["n_bins"])) if expected else None
+        _lib.check(_lib.lib.xpsi_b200_pipeline_fetch(
+            self.handle, B, _lib.dptr(f) if flux else None, _lib.dptr(g) if folded else None,
+            _lib.dptr(e) if expected else None))
+        return f, g, e
+
+    def stage_ms(self):
+        ms = (C.c_float * 4)()
+        _lib.check(_lib.lib.xpsi_b200_pipeline_stage_ms(self.handle, ms))
+        return dict(integrate=ms[0], energy=ms[1], fold=ms[2], marginal=ms[3])
