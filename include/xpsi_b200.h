@@ -50,6 +50,9 @@ int xpsi_b200_set_device(int device);
 /* counters for bench.py: kernels launched / bytes moved by this library so far */
 void xpsi_b200_counters(long long* kernel_launches, long long* h2d_bytes, long long* d2h_bytes);
 void* xpsi_b200_stream(void);   /* cudaStream_t all work is issued on */
+/* measured fp64 FMA peak of the current device (register-resident DFMA chains): the
+ * roofline denominator bench.py reports against */
+int xpsi_b200_fp64_peak_tflops(double* tflops);
 
 /* ---- preloaded atmosphere table ------------------------------------------
  * replaces init_preload / _preloaded, surface_radiation_field/preload.pyx:6-44
@@ -166,6 +169,9 @@ int xpsi_b200_pipeline_download(xpsi_b200_pipeline* p, int B, double* lnL, int* 
 /* optional: fetch intermediate device results of the last eval (NULL to skip) */
 int xpsi_b200_pipeline_fetch(xpsi_b200_pipeline* p, int B, double* flux /*[B*M][E][P] raw*/,
                              double* folded /*[B][C][chan][P]*/, double* expected /*[B][chan][bins]*/);
+/* algorithmic-work counters of the integrator: enable!=0 makes later evals
+ * count; out (if non-NULL and counting was on) receives H, V, RI, K of the last eval */
+int xpsi_b200_pipeline_work_counters(xpsi_b200_pipeline* p, int enable, unsigned long long out[4]);
 /* per-stage device time of the last eval_resident in ms: integrate, energy, fold, marginal */
 int xpsi_b200_pipeline_stage_ms(xpsi_b200_pipeline* p, float ms[4]);
 

@@ -122,6 +122,8 @@ _proto("xpsi_b200_pipeline_upload", C.c_int, [C.c_void_p, C.c_int, C.POINTER(Bat
 _proto("xpsi_b200_pipeline_eval_resident", C.c_int, [C.c_void_p, C.c_int])
 _proto("xpsi_b200_pipeline_download", C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p])
 _proto("xpsi_b200_pipeline_fetch", C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p])
+_proto("xpsi_b200_fp64_peak_tflops", C.c_int, [c_double_p])
+_proto("xpsi_b200_pipeline_work_counters", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)])
 _proto("xpsi_b200_pipeline_stage_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)])
 
 EXPORTED = [
@@ -131,7 +133,8 @@ EXPORTED = [
     "xpsi_b200_instrument_fold", "xpsi_b200_precomputation", "xpsi_b200_eval_marginal_likelihood",
     "xpsi_b200_pipeline_create", "xpsi_b200_pipeline_destroy", "xpsi_b200_pipeline_eval",
     "xpsi_b200_pipeline_upload", "xpsi_b200_pipeline_eval_resident", "xpsi_b200_pipeline_download",
-    "xpsi_b200_pipeline_fetch", "xpsi_b200_pipeline_stage_ms",
+    "xpsi_b200_pipeline_fetch", "xpsi_b200_pipeline_stage_ms", "xpsi_b200_fp64_peak_tflops",
+    "xpsi_b200_pipeline_work_counters",
 ]
 
 

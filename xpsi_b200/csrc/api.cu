@@ -106,6 +106,15 @@ void xpsi_b200_counters(long long* k, long long* h2d, long long* d2h) {
   if (d2h) *d2h = g_d2h;
 }
 
+int xpsi_b200_fp64_peak_tflops(double* tflops) {
+  int rc = ensure_stream();
+  if (rc) return rc;
+  cudaError_t e = xb::measure_fp64_peak(tflops, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "measure_fp64_peak");
+  g_launches += 6;
+  return 0;
+}
+
 void* xpsi_b200_stream(void) { return ensure_stream() == 0 ? (void*)g_stream : nullptr; }
 
 xpsi_b200_atmosphere* xpsi_b200_atmosphere_create(const double* logT, int nT, const double* logg,
@@ -339,6 +348,8 @@ struct xpsi_b200_pipeline {
   // intermediates / outputs
   Dev<double> flux, xin, folded, chan_lnL, expected, lnL;
   Dev<int> chan_status, status_q, status;
+  Dev<unsigned long long> work;
+  int count_work = 0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float stage_ms[4] = {0, 0, 0, 0};
 };
@@ -401,6 +412,8 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   a.phase_interp = c.phase_interpolant;
   a.scale_by_energy = 0;
   a.flux = p->flux.p; a.status = p->status_q.p;
+  a.work = p->count_work ? p->work.p : nullptr;
+  if (a.work) CK(cudaMemsetAsync(p->work.p, 0, 4 * sizeof(unsigned long long), g_stream));
   cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_integrate_azinv");
   CK(cudaEventRecord(p->ev[1], g_stream));
@@ -493,7 +506,7 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
   ok(p->flux.alloc(Q * c.n_energies * c.n_phases)); ok(p->xin.alloc(B * C * c.n_phases * c.n_in));
   ok(p->folded.alloc(B * C * c.n_chan * c.n_phases)); ok(p->chan_lnL.alloc(B * c.n_chan));
   ok(p->chan_status.alloc(B * c.n_chan)); ok(p->expected.alloc(B * c.n_chan * c.n_bins));
-  ok(p->lnL.alloc(B)); ok(p->status_q.alloc(Q)); ok(p->status.alloc(B));
+  ok(p->lnL.alloc(B)); ok(p->status_q.alloc(Q)); ok(p->status.alloc(B)); ok(p->work.alloc(4));
   for (int i = 0; i < 5; ++i) ok(cudaEventCreate(&p->ev[i]));
   ok(cudaStreamSynchronize(g_stream));
   if (e != cudaSuccess) { cuda_fail(e, "pipeline_create"); delete p; return nullptr; }
@@ -545,6 +558,16 @@ int xpsi_b200_pipeline_fetch(xpsi_b200_pipeline* p, int B, double* flux, double*
   if (folded) CK(p->folded.download(folded, (size_t)B * c.n_components * c.n_chan * c.n_phases));
   if (expected) CK(p->expected.download(expected, (size_t)B * c.n_chan * c.n_bins));
   CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int xpsi_b200_pipeline_work_counters(xpsi_b200_pipeline* p, int enable, unsigned long long out[4]) {
+  if (!p) return fail(XPSI_B200_EINVAL, "null pipeline");
+  if (out && p->count_work) {
+    CK(cudaMemcpyAsync(out, p->work.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+  }
+  p->count_work = enable;
   return 0;
 }
 

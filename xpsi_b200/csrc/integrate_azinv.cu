@@ -332,6 +332,19 @@ k_integrate_azinv(AzinvArgs a) {
   __syncthreads();
   if (s_fail) return;
   n_img = s_nimg;
+  if (a.work && tid == 0) {        // algorithmic-work counters for the roofline
+    int reached = (n_img < ((a.image_order_limit > 0) ? a.image_order_limit : n_img_max)) ? n_img + 1 : n_img;
+    unsigned long long V = 0, Kc = 0;
+    for (int I = 0; I < n_img; ++I) {
+      const LeafSet S = leaf_set(s_leafd, s_leafi, I, N_L, ATM == 2);
+      for (int l = 0; l < N_L; ++l) V += S.vis[l] ? 1 : 0;
+    }
+    for (int j = 0; j < A_; ++j) Kc += (s_area[j] >= 0.0) ? 1 : 0;
+    atomicAdd(a.work + 0, (unsigned long long)reached * leaf_lim);
+    atomicAdd(a.work + 1, V);
+    atomicAdd(a.work + 2, (unsigned long long)n_img);
+    atomicAdd(a.work + 3, Kc * n_img);
+  }
   if (n_img == 0) return;
 
   // ---- Num4D: per-leaf mu stencils -------------------------------------------------------

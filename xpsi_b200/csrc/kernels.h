@@ -40,6 +40,8 @@ struct AzinvArgs {
   int scale_by_energy;               // apply flux /= E keV (pyx:610-612)
   double* flux;                      // [Q][N_E][N_P], zero-initialised by the caller
   int* status;                       // [Q]
+  unsigned long long* work;          // nullptr or [4]: H half-leaf visits, V visible leaves,
+                                     //   RI (ring,image) pairs reaching the phase stage, K radiating cells over RI
 };
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream);
 
@@ -94,6 +96,9 @@ struct MarginalArgs {
   int* status;                       // [B]
 };
 cudaError_t launch_marginal(MarginalArgs a, cudaStream_t stream);
+
+// peak fp64 FMA rate of the device, measured with a register-resident DFMA chain
+cudaError_t measure_fp64_peak(double* tflops, cudaStream_t stream);
 
 // a13: precomputation
 cudaError_t launch_precomputation(const int* counts, int n_chan, int n_bins, double* out,

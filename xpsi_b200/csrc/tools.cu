@@ -168,4 +168,47 @@ cudaError_t launch_precomputation(const int* counts, int n_chan, int n_bins, dou
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// fp64 roofline denominator: 8 independent DFMA chains per thread, all in
+// registers, 148 x 8 CTAs of 256 threads.
+// ---------------------------------------------------------------------------
+__global__ void k_dfma_peak(double* sink, int iters, double x0) {
+  double a0 = x0, a1 = x0 + 1, a2 = x0 + 2, a3 = x0 + 3, a4 = x0 + 4, a5 = x0 + 5, a6 = x0 + 6, a7 = x0 + 7;
+  const double m = 1.0000001, c = 1.0e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) sink[0] = s;
+}
+
+cudaError_t measure_fp64_peak(double* tflops, cudaStream_t stream) {
+  double* sink = nullptr;
+  cudaError_t e = cudaMalloc(&sink, sizeof(double));
+  if (e != cudaSuccess) return e;
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0); cudaEventCreate(&t1);
+  const int blocks = 148 * 8, threads = 256, iters = 4096;
+  k_dfma_peak<<<blocks, threads, 0, stream>>>(sink, 64, 1.0);       // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(t0, stream);
+    k_dfma_peak<<<blocks, threads, 0, stream>>>(sink, iters, 1.0);
+    cudaEventRecord(t1, stream);
+    cudaEventSynchronize(t1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    if (ms < best) best = ms;
+  }
+  e = cudaGetLastError();
+  const double flops = 2.0 * 64.0 * (double)iters * blocks * threads;
+  *tflops = flops / (best * 1.0e-3) / 1.0e12;
+  cudaEventDestroy(t0); cudaEventDestroy(t1); cudaFree(sink);
+  return e;
+}
+
 }  // namespace xb

@@ -43,15 +43,14 @@ class HostBatch:
         self.maxDeflection = alloc((Q, max_rings), np.float64)
         self.cos_gamma = alloc((Q, max_rings), np.float64)
 
+    _pins = []
+
     @staticmethod
     def _pinned(shape, dtype):
         import torch   # device-memory plumbing only: page-locked host staging
         t = torch.zeros(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32).pin_memory()
-        a = t.numpy()
-        a._keep = t if hasattr(a, "__dict__") else None
-        HostBatch._pins.append(t)
-        return a
-    _pins = []
+        HostBatch._pins.append(t)      # the numpy view below borrows the tensor's storage
+        return t.numpy()
 
     def set_member(self, b, m, cellArea, theta, phi, radial, r_s_over_r, srcCellParams,
                    deflection, cos_alpha, lag, maxDeflection, cos_gamma):
@@ -195,6 +194,13 @@ class BatchedLikelihood:
             self.handle, B, _lib.dptr(f) if flux else None, _lib.dptr(g) if folded else None,
             _lib.dptr(e) if expected else None))
         return f, g, e
+
+    def count_work(self, enable=True):
+        """Toggle the integrator's algorithmic-work counters; returns the counters of the
+        last counted eval as dict(H, V, RI, K)."""
+        out = (C.c_ulonglong * 4)()
+        _lib.check(_lib.lib.xpsi_b200_pipeline_work_counters(self.handle, int(enable), out))
+        return dict(H=out[0], V=out[1], RI=out[2], K=out[3])
 
     def stage_ms(self):
         ms = (C.c_float * 4)()
