@@ -69,15 +69,6 @@ struct Dev {
   }
 };
 
-int slab_rows_budget(const xb::AtmTable& t, const double* energies, int n_energies) {
-  // rows of the logE axis a ring can reach: span of the energy grid plus the
-  // Doppler/redshift spread across one ring (|beta| < 0.45 => < 0.42 dex) + stencil
-  if (t.min_dlogE <= 0.0) return t.nE;
-  const double span = log10(energies[n_energies - 1] / energies[0]) + 0.42;
-  int rows = (int)ceil(span / t.min_dlogE) + 10;
-  return rows > t.nE ? t.nE : rows;
-}
-
 }  // namespace
 
 struct xpsi_b200_atmosphere {
@@ -193,7 +184,7 @@ int xpsi_b200_integrate_azimuthal_invariance(
   a.hot_atm_ext = hot_atm_ext;
   if (hot_atm_ext == XPSI_B200_ATM_NUM4D) {
     a.hot = hot_atmosphere->view;
-    a.slab_ne_max = slab_rows_budget(a.hot, energies, n_energies);
+    a.slab_ne_max = xb::azinv_slab_rows_budget(a.hot, energies, n_energies);
   }
   a.image_order_limit = image_order_limit > 0 ? image_order_limit : 0;
   a.n_img_max = image_order_limit > 0 ? image_order_limit : xb::kMaxImages;
@@ -201,9 +192,13 @@ int xpsi_b200_integrate_azimuthal_invariance(
   a.phase_interp = phase_interpolant;
   a.scale_by_energy = 1;
   a.flux = d_flux.p; a.status = d_status.p;
+  Dev<double> d_ws; Dev<int> d_wsn;
+  CK(d_ws.alloc(xb::azinv_workspace_doubles(1, n_rings, a.n_img_max, n_leaves)));
+  CK(d_wsn.alloc(n_rings));
+  a.ws_leaf = d_ws.p; a.ws_nimg = d_wsn.p;
   cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_integrate_azinv");
-  g_launches += 2;
+  g_launches += 3;
   int status = 0;
   CK(d_flux.download(flux_out, (size_t)n_energies * n_phases));
   CK(d_status.download(&status, 1));
@@ -349,6 +344,7 @@ struct xpsi_b200_pipeline {
   Dev<double> flux, xin, folded, chan_lnL, expected, lnL;
   Dev<int> chan_status, status_q, status;
   Dev<unsigned long long> work;
+  Dev<double> ws_leaf; Dev<int> ws_nimg;
   int count_work = 0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float stage_ms[4] = {0, 0, 0, 0};
@@ -412,6 +408,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   a.phase_interp = c.phase_interpolant;
   a.scale_by_energy = 0;
   a.flux = p->flux.p; a.status = p->status_q.p;
+  a.ws_leaf = p->ws_leaf.p; a.ws_nimg = p->ws_nimg.p;
   a.work = p->count_work ? p->work.p : nullptr;
   if (a.work) CK(cudaMemsetAsync(p->work.p, 0, 4 * sizeof(unsigned long long), g_stream));
   cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
@@ -450,7 +447,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   e = xb::launch_marginal(m, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_marginal");
   CK(cudaEventRecord(p->ev[4], g_stream));
-  g_launches += 7;   // expand, integrate, energy, fold, member-status, marginal, channel-sum
+  g_launches += 8;   // expand, geometry, flux, energy, fold, member-status, marginal, channel-sum
   return 0;
 }
 
@@ -507,10 +504,15 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
   ok(p->folded.alloc(B * C * c.n_chan * c.n_phases)); ok(p->chan_lnL.alloc(B * c.n_chan));
   ok(p->chan_status.alloc(B * c.n_chan)); ok(p->expected.alloc(B * c.n_chan * c.n_bins));
   ok(p->lnL.alloc(B)); ok(p->status_q.alloc(Q)); ok(p->status.alloc(B)); ok(p->work.alloc(4));
+  {
+    const int nimg = c.image_order_limit > 0 ? c.image_order_limit : xb::kMaxImages;
+    ok(p->ws_leaf.alloc(xb::azinv_workspace_doubles((int)Q, c.max_rings, nimg, c.n_leaves)));
+    ok(p->ws_nimg.alloc(Q * R));
+  }
   for (int i = 0; i < 5; ++i) ok(cudaEventCreate(&p->ev[i]));
   ok(cudaStreamSynchronize(g_stream));
   if (e != cudaSuccess) { cuda_fail(e, "pipeline_create"); delete p; return nullptr; }
-  if (c.hot_atm_ext == XPSI_B200_ATM_NUM4D) p->slab_rows = slab_rows_budget(p->atm->view, c.energies, c.n_energies);
+  if (c.hot_atm_ext == XPSI_B200_ATM_NUM4D) p->slab_rows = xb::azinv_slab_rows_budget(p->atm->view, c.energies, c.n_energies);
   g_launches += 1;
   return p;
 }

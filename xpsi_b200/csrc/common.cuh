@@ -137,6 +137,26 @@ __device__ __forceinline__ void akima_from_slopes(double mm2, double mm1, double
   *d = (bb + tL - 2.0 * m0) / (h * h);
 }
 
+// same, with the interval width supplied as its reciprocal
+__device__ __forceinline__ void akima_from_slopes_ih(double mm2, double mm1, double m0, double mp1,
+                                                     double mp2, double ih, double* b, double* c,
+                                                     double* d) {
+  const double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
+  if (NE == 0.0) { *b = m0; *c = 0.0; *d = 0.0; return; }
+  const double NE_next = fabs(mp2 - mp1) + fabs(m0 - mm1);
+  const double alpha = fabs(mm1 - mm2) / NE;
+  double tL;
+  if (NE_next == 0.0) tL = m0;
+  else {
+    const double alpha1 = fabs(m0 - mm1) / NE_next;
+    tL = (1.0 - alpha1) * m0 + alpha1 * mp1;
+  }
+  const double bb = (1.0 - alpha) * mm1 + alpha * m0;
+  *b = bb;
+  *c = (3.0 * m0 - 2.0 * bb - tL) * ih;
+  *d = (bb + tL - 2.0 * m0) * (ih * ih);
+}
+
 template <class X, class Y>
 __device__ __forceinline__ void akima_coeffs(const X& x, const Y& y, int n, int i, bool periodic,
                                              double* b, double* c, double* d) {

@@ -4,139 +4,101 @@
 // reference's dominant hot loop) together with the atmosphere evaluations it
 // calls: hot_BB.pyx:54-98 and hot_Num4D.pyx:248-460.
 //
-// B200 mapping (not a translation of the OpenMP loop nest):
-//   * one CTA per (member instance q, mesh ring i); the batch axis q = theta x
-//     member is just the second grid dimension;
-//   * ring constants, the ring's ray row and its cos(psi) image live in shared
-//     memory; the three Steffen splines of the reference are never
-//     materialised -- each half-leaf thread rebuilds the two node slopes it
-//     needs in registers;
-//   * geometry of all image orders is done at once (one thread per (image,
-//     half-leaf)); the reference's sequential visibility state machine is
-//     replayed verbatim by one thread per image;
+// B200 mapping (not a translation of the OpenMP loop nest) -- two kernels:
+//
+// k_azinv_geometry   one CTA per (member instance q, ring).  The ring's ray row
+//   and its cos(psi) image are staged in shared memory; one thread per (image
+//   order, half-leaf) evaluates deflection / cos(alpha) / lag through Steffen
+//   pieces rebuilt in registers, then Doppler, redshift and the solid-angle
+//   Jacobian.  The reference's sequential visibility state machine is replayed
+//   verbatim by one thread per image order.  Output per (q, ring, image): four
+//   N_L-vectors PHASE, Z (log10 Z for Num4D), mu*eta, GEOM (0 = leaf dark).
+//
+// k_azinv_flux<ATM>  one CTA per (q, ring, chunk of 8 energies): thousands of
+//   small CTAs, ~50 KB of shared memory each, 4 resident per SM.
 //   * Num4D: the 4-D table is contracted over (log T, log g) -- constant on a
-//     ring -- into a (mu, E) slab restricted to the reachable energy rows and
-//     kept in shared memory, so every intensity is a 4x4 stencil on-chip;
-//   * energies are processed in tiles; for each tile the leaf profile and its
-//     phase-spline coefficients are built in shared memory, then each thread
-//     owns (output phase, 4 energies), walks the ring's radiating cells and
-//     accumulates in registers, reloading spline coefficients only when the
-//     cell crosses into the next leaf interval;
-//   * rings are combined with fp64 RED atomics into flux[q, E, P].
+//     ring -- into a (mu, E) slab restricted to the ~16 energy rows this chunk
+//     can reach; every intensity is then a 4x4 stencil on-chip with
+//     precomputed Lagrange denominators.
+//   * the leaf profile and its phase-spline (Akima periodic / Steffen)
+//     coefficients are built in shared memory.
+//   * accumulation over the ring's cells uses interval moments: for an output
+//     phase k the cells falling in one leaf interval m share the cubic, so
+//     sum_j A_j S(x_j) = c0 W0 + c1 W1 + c2 W2 + c3 W3 with W_p = sum_j A_j d_j^p.
+//     One thread owns phase k and all 8 energies: it walks the cells once,
+//     and per touched interval spends 4 FMAs per energy instead of 4 per cell.
+//     The reference adds a cell only where the spline is positive
+//     (pyx:593); intervals whose cubic is not provably non-negative (Bernstein
+//     coefficients) are flagged per energy and evaluated cell by cell.
+//   * rings/chunks are combined with fp64 RED atomics into flux[q, E, P].
 #include "common.cuh"
 #include "kernels.h"
 
 namespace xb {
 
-constexpr int kET = 8;        // energies per tile
-constexpr int kEG = 4;        // energies per thread item
-constexpr int kThreads = 256;
-
-struct LeafSet {              // per image order, N_L entries each
-  double* phase;              // PHASE as left by the visibility state machine
-  double* ptrue;              // leaf + lag for visible leaves
-  double* Z;                  // total redshift eta * Grav_z
-  double* abb;                // mu * eta
-  double* geom;               // mu |deriv| Grav_z eta^3 / (1 + beta cos xi)
-  double* muw;                // Num4D: 4 Lagrange weights in mu
-  int* mub;                   // Num4D: base node in mu
-  int* vis;                   // leaf carries signal
-};
-
-// leaf arrays are laid out [image][field][N_L]; resolved arithmetically so the
-// image index never forces the pointer table into local memory
-__device__ __forceinline__ LeafSet leaf_set(double* dbase, int* ibase, int I, int N_L, bool num4d) {
-  const int nf = num4d ? 9 : 5;
-  double* d = dbase + (long)I * nf * N_L;
-  int* ii = ibase + (long)I * 2 * N_L;
-  LeafSet S;
-  S.phase = d; S.ptrue = d + N_L; S.Z = d + 2 * N_L; S.abb = d + 3 * N_L; S.geom = d + 4 * N_L;
-  S.muw = num4d ? d + 5 * N_L : nullptr;
-  S.vis = ii; S.mub = ii + N_L;
-  return S;
-}
+constexpr int kNEC = 8;            // energies per flux CTA
+constexpr int kGeomThreads = 128;
+constexpr int kFluxThreads = 128;
 
 __device__ __forceinline__ double bb_intensity(double E, double kT) {
   return E * E * E / (exp(E / kT) - 1.0);     // hot_BB.pyx:85-87
 }
 
+// leaf workspace layout: [ring][image][4][N_L]
+__device__ __forceinline__ double* leaf_ptr(double* ws, long ring, int n_img_max, int I, int N_L) {
+  return ws + ((ring * n_img_max + I) * 4) * (long)N_L;
+}
+
+// ===========================================================================
+// geometry
+// ===========================================================================
 template <int ATM>
-__global__ void __launch_bounds__(kThreads)
-k_integrate_azinv(AzinvArgs a) {
+__global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
   const int i = blockIdx.x;                 // ring
   const int q = blockIdx.y;                 // member instance
   const int tid = threadIdx.x;
   const int R_ = a.n_rings_q ? a.n_rings_q[q] : a.n_rings;
   const int A_ = a.n_azi_q ? a.n_azi_q[q] : a.n_azi;
-  if (i >= R_) return;
-  const int N_R = a.n_rays, N_E = a.n_energies, N_L = a.n_leaves, N_P = a.n_phases;
   const long ring = (long)q * a.n_rings + i;           // padded ring index
-  const long cell0 = ring * a.n_azi;                    // padded cell row
+  if (i >= R_) { if (tid == 0) a.ws_nimg[ring] = 0; return; }
+  const int N_R = a.n_rays, N_L = a.n_leaves;
+  const long cell0 = ring * a.n_azi;
   const int leaf_lim = (N_L % 2 == 0) ? N_L / 2 : (N_L + 1) / 2;
+  const int n_img_max = a.n_img_max;
 
   extern __shared__ double smem[];
-  __shared__ int s_J, s_jhalf, s_nimg, s_fail, s_elo, s_ne;
+  __shared__ int s_J, s_jhalf, s_nimg;
   __shared__ int s_inv2[kMaxImages], s_dom[kMaxImages], s_mono[kMaxImages];
-  __shared__ double s_wT[4], s_wG[4];
-  __shared__ int s_bT, s_bG;
 
-  // ---- does the ring radiate? (pyx:286-296) --------------------------------
-  if (tid == 0) { s_J = A_; s_jhalf = N_R - 1; s_fail = 0; }
+  // ---- does the ring radiate? (pyx:286-296); a null mask means cellArea > 0 (HotRegion.py:965)
+  if (tid == 0) { s_J = A_; s_jhalf = N_R - 1; }
   if (tid < kMaxImages) { s_inv2[tid] = 0; s_dom[tid] = 0; s_mono[tid] = 0; }
   __syncthreads();
-  // CELL_RADIATES (HotRegion.py:965); a null mask means cellArea > 0
-  auto radiates = [&](int j) -> bool {
-    return a.radiates ? (a.radiates[cell0 + j] == 1) : (a.cellArea[cell0 + j] > 0.0);
-  };
-  for (int j = tid; j < A_; j += kThreads)
-    if (radiates(j)) atomicMin(&s_J, j);
+  for (int j = tid; j < A_; j += kGeomThreads) {
+    const bool rad = a.radiates ? (a.radiates[cell0 + j] == 1) : (a.cellArea[cell0 + j] > 0.0);
+    if (rad) atomicMin(&s_J, j);
+  }
   __syncthreads();
   const int J = s_J;
-  if (J >= A_) return;
+  if (J >= A_) { if (tid == 0) a.ws_nimg[ring] = 0; return; }
 
-  // ---- shared-memory carve --------------------------------------------------
   double* sp = smem;
   double* s_defl = sp; sp += N_R;
   double* s_calpha = sp; sp += N_R;
   double* s_lag = sp; sp += N_R;
   double* s_cosd = sp; sp += N_R;
-  double* s_phi = sp; sp += a.n_azi;
-  double* s_area = sp; sp += a.n_azi;
-  double* s_E = sp; sp += N_E;
-  double* s_logE = sp; sp += N_E;
-  double* s_y = sp; sp += kET * N_L;
-  double* s_coef = sp; sp += kET * N_L * 4;
-  const int n_img_max = a.n_img_max;
-  double* s_leafd = sp; sp += (long)n_img_max * (ATM == 2 ? 9 : 5) * N_L;
-  double* s_axE = nullptr; double* s_axMu = nullptr; double* s_slab = nullptr;
-  if (ATM == 2) {
-    s_axE = sp; sp += a.hot.nE;
-    s_axMu = sp; sp += a.hot.nmu;
-    s_slab = sp; sp += (long)a.hot.nmu * a.slab_ne_max;
-  }
-  int* s_leafi = reinterpret_cast<int*>(sp);
+  double* s_ptrue = sp; sp += (long)n_img_max * N_L;
+  double* s_phase = sp; sp += (long)n_img_max * N_L;
+  int* s_vis = reinterpret_cast<int*>(sp);              // [n_img_max][N_L]
 
-  // ---- stage the ring ---------------------------------------------------------
   const double* g_defl = a.deflection + ring * N_R;
   const double* g_calpha = a.cos_alpha + ring * N_R;
   const double* g_lag = a.lag + ring * N_R;
-  for (int r = tid; r < N_R; r += kThreads) {
+  for (int r = tid; r < N_R; r += kGeomThreads) {
     const double d = g_defl[r];
     s_defl[r] = d; s_calpha[r] = g_calpha[r]; s_lag[r] = g_lag[r];
     s_cosd[r] = cos(d);                                   // pyx:216-218
     if (d > kHalfPi) atomicMin(&s_jhalf, r);              // pyx:301-303
-  }
-  for (int j = tid; j < A_; j += kThreads) {
-    s_phi[j] = a.phi[cell0 + j];
-    s_area[j] = radiates(j) ? a.cellArea[cell0 + j] : -1.0;   // <0: cell is dark
-  }
-  for (int e = tid; e < N_E; e += kThreads) {
-    const double E = a.energies[e];
-    s_E[e] = E; s_logE[e] = log10(E);
-  }
-  if (ATM == 2) {
-    for (int e = tid; e < a.hot.nE; e += kThreads) s_axE[e] = a.hot.logE[e];
-    for (int m = tid; m < a.hot.nmu; m += kThreads) s_axMu[m] = a.hot.mu[m];
   }
 
   // ---- ring constants (pyx:318-331) ---------------------------------------------
@@ -144,8 +106,7 @@ k_integrate_azinv(AzinvArgs a) {
   const double omega = a.omega[q];
   const double sin_i = sin(inclination), cos_i = cos(inclination);
   const double radius = a.radial[ring];
-  const double rsr = a.r_s_over_r[ring];
-  const double Grav_z = sqrt(1.0 - rsr);
+  const double Grav_z = sqrt(1.0 - a.r_s_over_r[ring]);
   const double cos_gamma = a.cos_gamma[ring];
   const double sin_gamma = sqrt(1.0 - cos_gamma * cos_gamma);
   const double theta_i = a.theta[ring * a.theta_ring_stride];
@@ -154,66 +115,20 @@ k_integrate_azinv(AzinvArgs a) {
   const double beta = radius * omega * sin_theta_i / (kC * Grav_z);
   const double Lorentz = sqrt(1.0 - beta * beta);
   const double maxDefl = a.maxDeflection[ring];
-  const double* VEC = a.srcParams + (a.params_per_cell ? (cell0 + J) : ring) * a.n_params;
-  const double logT = VEC[0];
-  const double kT = kKBOverKeV * pow(10.0, logT);
-  const double log_kT = log10(kT);
   int n_img = a.image_order_limit > 0 ? a.image_order_limit : (int)ceil(maxDefl / kPi);
   if (n_img > n_img_max) n_img = n_img_max;
   __syncthreads();
   const int jhalf = s_jhalf;        // first ray with deflection > pi/2 (clamped)
-
-  // ---- Num4D: (T,g) stencil + reachable energy rows, then contract the slab --------
-  if (ATM == 2) {
-    if (tid == 0) {
-      View vT{a.hot.logT, 1}, vG{a.hot.logg, 1};
-      s_bT = lagrange_base(vT, a.hot.nT, logT);
-      s_bG = lagrange_base(vG, a.hot.ng, VEC[1]);
-      double w[4];
-      lagrange_weights(vT, s_bT, logT, w);
-      for (int k = 0; k < 4; ++k) s_wT[k] = w[k];
-      lagrange_weights(vG, s_bG, VEC[1], w);
-      for (int k = 0; k < 4; ++k) s_wG[k] = w[k];
-      // log10(E'/kT) spans [logE_0 - log Zmax, logE_last - log Zmin] - log kT
-      const double Zmax = Lorentz / (1.0 - fabs(beta)) * Grav_z;
-      const double Zmin = Lorentz / (1.0 + fabs(beta)) * Grav_z;
-      const double vlo = s_logE[0] - log10(Zmax) - log_kT - 1.0e-9;
-      const double vhi = s_logE[N_E - 1] - log10(Zmin) - log_kT + 1.0e-9;
-      const int elo = lagrange_base(s_axE, a.hot.nE, vlo);
-      const int ehi = lagrange_base(s_axE, a.hot.nE, vhi) + 4;      // exclusive
-      if (ehi - elo > a.slab_ne_max) {      // budget too small for this ring: refuse, never clamp
-        atomicExch(a.status + q, kUnsupported);
-        s_fail = 1;
-      }
-      s_elo = elo; s_ne = ehi - elo;
-    }
-    __syncthreads();
-    if (s_fail) return;
-    const int elo = s_elo, ne = s_ne, nmu = a.hot.nmu;
-    const long S0 = (long)a.hot.ng * nmu * a.hot.nE, S1 = (long)nmu * a.hot.nE, S2 = a.hot.nE;
-    for (int t = tid; t < nmu * ne; t += kThreads) {
-      const int m = t / ne, e = t - m * ne;
-      const double* base = a.hot.buf + (long)s_bT * S0 + (long)s_bG * S1 + (long)m * S2 + elo + e;
-      double acc = 0.0;
-#pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        double inner = 0.0;
-#pragma unroll
-        for (int y = 0; y < 4; ++y) inner += s_wG[y] * __ldg(base + x * S0 + y * S1);
-        acc += s_wT[x] * inner;
-      }
-      s_slab[t] = acc;
-    }
-  }
 
   // ---- geometry of every (image, half-leaf) (pyx:342-441) ----------------------------
   View vDefl{s_defl, 1}, vCalpha{s_calpha, 1}, vLag{s_lag, 1};
   View vAltX{s_cosd + jhalf, -1}, vAltY{s_calpha + jhalf, -1};   // pyx:305-308
   const int n_alt = jhalf + 1;
   const double alt_xmin = s_cosd[jhalf];
-  for (int t = tid; t < n_img * leaf_lim; t += kThreads) {
+  for (int t = tid; t < n_img * leaf_lim; t += kGeomThreads) {
     const int I = t / leaf_lim, k = t - I * leaf_lim;
-    const LeafSet S = leaf_set(s_leafd, s_leafi, I, N_L, ATM == 2);
+    double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
+    double* wZ = W + N_L; double* wAbb = W + 2 * N_L; double* wGeom = W + 3 * N_L;
     const double leaf_k = a.leaves[k];
     double cos_psi = cos_i * cos_theta_i + sin_i * sin_theta_i * cos(leaf_k);
     double psi = eval_image_deflection(I, acos(cos_psi));
@@ -262,36 +177,40 @@ k_integrate_azinv(AzinvArgs a) {
                         (k == leaf_lim - 1 && (N_L % 2 == 0));
       if (!take) continue;
       const int kdx = ks == 0 ? k : N_L - 1 - k;
-      S.vis[kdx] = visible;
-      if (!visible) continue;
+      s_vis[I * N_L + kdx] = visible;
+      if (!visible) { wGeom[kdx] = 0.0; wZ[kdx] = 1.0; wAbb[kdx] = 0.0; continue; }
       double superlum, eta;
       if (!are_equal(psi, 0.0)) {
         const double cos_xi = sin_alpha * sin_i * sin(a.leaves[kdx]) / sin_psi;
         superlum = 1.0 + beta * cos_xi;
         eta = Lorentz / superlum;
       } else { superlum = 1.0; eta = Lorentz; }
-      S.Z[kdx] = eta * Grav_z;
-      S.abb[kdx] = mu * eta;
-      S.geom[kdx] = mu * fabs(deriv) * Grav_z * eta * eta * eta / superlum;
-      S.ptrue[kdx] = a.leaves[kdx] + lagv;
+      const double Z = eta * Grav_z;
+      wZ[kdx] = (ATM == 2) ? log10(Z) : Z;
+      wAbb[kdx] = mu * eta;
+      wGeom[kdx] = mu * fabs(deriv) * Grav_z * eta * eta * eta / superlum;
+      s_ptrue[I * N_L + kdx] = a.leaves[kdx] + lagv;
     }
   }
   __syncthreads();
 
   // ---- visibility state machine, one thread per image (pyx:339-563, verbatim order) ----
   if (tid < n_img) {
-    const LeafSet S = leaf_set(s_leafd, s_leafi, tid, N_L, ATM == 2);
-    double* PH = S.phase;
+    double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, tid, N_L);
+    double* wZ = W + N_L; double* wAbb = W + 2 * N_L; double* wGeom = W + 3 * N_L;
+    double* PH = s_phase + tid * N_L;
+    const double* PT = s_ptrue + tid * N_L;
+    int* vis = s_vis + tid * N_L;
     int Inv = 2, k0 = 0;
     for (int k = 0; k < leaf_lim; ++k) {
-      if (S.vis[k]) {
-        PH[k] = S.ptrue[k];
+      if (vis[k]) {
+        PH[k] = PT[k];
         const bool mirror = (0 < k && k < leaf_lim - 1) || (k == leaf_lim - 1 && N_L % 2 == 0);
-        if (mirror) PH[N_L - 1 - k] = S.ptrue[N_L - 1 - k];
+        if (mirror) PH[N_L - 1 - k] = PT[N_L - 1 - k];
         if (k == 0) {
-          PH[N_L - 1] = PH[0] + kTwoPi;            // leaf N_L-1 is a copy of leaf 0
-          S.Z[N_L - 1] = S.Z[0]; S.abb[N_L - 1] = S.abb[0]; S.geom[N_L - 1] = S.geom[0];
-          S.vis[N_L - 1] = 1;
+          PH[N_L - 1] = PH[0] + kTwoPi;            // leaf N_L-1 is a copy of leaf 0 (pyx:480-484)
+          wZ[N_L - 1] = wZ[0]; wAbb[N_L - 1] = wAbb[0]; wGeom[N_L - 1] = wGeom[0];
+          vis[N_L - 1] = 1;
         } else if (Inv == 2) {
           const double step = a.leaves[k] / (double)k;
           for (int m = N_L - k; m < N_L; ++m) PH[m] = PH[m - 1] + step;
@@ -305,7 +224,7 @@ k_integrate_azinv(AzinvArgs a) {
         }
         Inv = 0;
       } else {
-        if (k == 0) S.vis[N_L - 1] = 0;
+        if (k == 0) { vis[N_L - 1] = 0; wGeom[N_L - 1] = 0.0; wZ[N_L - 1] = 1.0; wAbb[N_L - 1] = 0.0; }
         if (Inv == 0) {
           const double step = (PH[N_L - k] - PH[k - 1]) / (double)(N_L - 2 * k + 1);
           for (int m = k; m < N_L - k; ++m) PH[m] = PH[m - 1] + step;
@@ -326,164 +245,330 @@ k_integrate_azinv(AzinvArgs a) {
     int n = 0, bad = 0;
     while (n < n_img && !s_inv2[n]) { bad |= s_dom[n] | s_mono[n]; ++n; }
     if (n < n_img) bad |= s_dom[n];          // that order's leaf loop did run
-    if (bad) atomicExch(a.status + q, kNumericalError);
-    s_nimg = n; s_fail = bad;
+    if (bad) { atomicExch(a.status + q, kNumericalError); n = 0; }
+    if (a.work && !bad) {        // algorithmic-work counters for the roofline
+      const int reached = (n < n_img) ? n + 1 : n;
+      unsigned long long V = 0, Kc = 0;
+      for (int I = 0; I < n; ++I)
+        for (int l = 0; l < N_L; ++l) V += s_vis[I * N_L + l] ? 1 : 0;
+      for (int j = 0; j < A_; ++j)
+        Kc += (a.radiates ? (a.radiates[cell0 + j] == 1) : (a.cellArea[cell0 + j] > 0.0)) ? 1 : 0;
+      atomicAdd(a.work + 0, (unsigned long long)reached * leaf_lim);
+      atomicAdd(a.work + 1, V);
+      atomicAdd(a.work + 2, (unsigned long long)n);
+      atomicAdd(a.work + 3, Kc * n);
+    }
+    s_nimg = n;
+    a.ws_nimg[ring] = n;
   }
   __syncthreads();
-  if (s_fail) return;
   n_img = s_nimg;
-  if (a.work && tid == 0) {        // algorithmic-work counters for the roofline
-    int reached = (n_img < ((a.image_order_limit > 0) ? a.image_order_limit : n_img_max)) ? n_img + 1 : n_img;
-    unsigned long long V = 0, Kc = 0;
-    for (int I = 0; I < n_img; ++I) {
-      const LeafSet S = leaf_set(s_leafd, s_leafi, I, N_L, ATM == 2);
-      for (int l = 0; l < N_L; ++l) V += S.vis[l] ? 1 : 0;
-    }
-    for (int j = 0; j < A_; ++j) Kc += (s_area[j] >= 0.0) ? 1 : 0;
-    atomicAdd(a.work + 0, (unsigned long long)reached * leaf_lim);
-    atomicAdd(a.work + 1, V);
-    atomicAdd(a.work + 2, (unsigned long long)n_img);
-    atomicAdd(a.work + 3, Kc * n_img);
+  for (int t = tid; t < n_img * N_L; t += kGeomThreads) {
+    const int I = t / N_L, l = t - I * N_L;
+    leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L)[l] = s_phase[t];
   }
-  if (n_img == 0) return;
+}
 
-  // ---- Num4D: per-leaf mu stencils -------------------------------------------------------
+// ===========================================================================
+// flux
+// ===========================================================================
+// x = phase + cell azimuth, brought into [first, last] by whole turns (pyx:575-583)
+__device__ __forceinline__ double wrap_phase(double x, double first, double last) {
+  if (x > last) { while (x > last) x -= kTwoPi; }
+  else if (x < first) { while (x < first) x += kTwoPi; }
+  return x;
+}
+
+template <int ATM>
+__global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
+  const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
+  const int i = blockIdx.x / n_chunks;
+  const int chunk = blockIdx.x - i * n_chunks;
+  const int q = blockIdx.y;
+  const int tid = threadIdx.x;
+  const long ring = (long)q * a.n_rings + i;
+  const int n_img = a.ws_nimg[ring];
+  if (n_img == 0) return;
+  const int A_ = a.n_azi_q ? a.n_azi_q[q] : a.n_azi;
+  const int N_E = a.n_energies, N_L = a.n_leaves, N_P = a.n_phases;
+  const long cell0 = ring * a.n_azi;
+  const int e0 = chunk * kNEC;
+  const int ne = min(kNEC, N_E - e0);
+  const int n_img_max = a.n_img_max;
+
+  extern __shared__ double smem[];
+  __shared__ int s_ncell, s_J, s_fail, s_elo, s_nrows, s_bT, s_bG;
+  __shared__ double s_wT[4], s_wG[4], s_wlo[kFluxThreads / 32], s_whi[kFluxThreads / 32];
+  double* sp = smem;
+  double* s_cphi = sp; sp += a.n_azi;
+  double* s_carea = sp; sp += a.n_azi;
+  double* s_PH = sp; sp += N_L;
+  double* s_Z = sp; sp += N_L;
+  double* s_aux = sp; sp += N_L;          // mu*eta, then 1/h of the leaf intervals
+  double* s_geom = sp; sp += N_L;
+  double* s_y = sp; sp += kNEC * N_L;
+  double* s_coef = sp; sp += (long)kNEC * N_L * 4;
+  double* s_muw = nullptr; double* s_axE = nullptr; double* s_invden = nullptr;
+  double* s_axMu = nullptr; double* s_slab = nullptr;
   if (ATM == 2) {
-    for (int t = tid; t < n_img * N_L; t += kThreads) {
+    s_muw = sp; sp += 4 * N_L;
+    s_axE = sp; sp += a.slab_ne_max;
+    s_invden = sp; sp += 4 * a.slab_ne_max;
+    s_axMu = sp; sp += a.hot.nmu;
+    s_slab = sp; sp += (long)a.hot.nmu * a.slab_ne_max;
+  }
+  int* s_mub = reinterpret_cast<int*>(sp);
+  unsigned* s_flag = reinterpret_cast<unsigned*>(s_mub + N_L);
+
+  // ---- compact list of the ring's radiating cells -----------------------------------
+  if (tid == 0) { s_ncell = 0; s_J = A_; s_fail = 0; }
+  __syncthreads();
+  if (tid < 32) {       // ordered compaction by one warp keeps cells ascending in azimuth
+    int base = 0;
+    for (int j0 = 0; j0 < A_; j0 += 32) {
+      const int j = j0 + tid;
+      bool rad = false;
+      double area = 0.0, phi = 0.0;
+      if (j < A_) {
+        rad = a.radiates ? (a.radiates[cell0 + j] == 1) : (a.cellArea[cell0 + j] > 0.0);
+        area = a.cellArea[cell0 + j]; phi = a.phi[cell0 + j];
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, rad);
+      if (rad) {
+        const int pos = base + __popc(m & ((1u << tid) - 1u));
+        s_cphi[pos] = phi; s_carea[pos] = area;
+      }
+      if (m && base == 0 && tid == 0) s_J = j0 + __ffs(m) - 1;
+      base += __popc(m);
+    }
+    if (tid == 0) s_ncell = base;
+  }
+  __syncthreads();
+  const int n_cells = s_ncell;
+  if (n_cells == 0) return;
+  const int J = s_J;
+  const double* VEC = a.srcParams + (a.params_per_cell ? (cell0 + J) : ring) * a.n_params;
+  const double logT = VEC[0];
+  const double kT = kKBOverKeV * pow(10.0, logT);
+  const double log_kT = log10(kT);
+
+  // ---- Num4D: slab for the energy rows this chunk reaches ---------------------------------
+  if (ATM == 2) {
+    // range of log10 Z over the visible leaves of all images
+    double zlo = 1e300, zhi = -1e300;
+    for (int t = tid; t < n_img * N_L; t += kFluxThreads) {
       const int I = t / N_L, l = t - I * N_L;
-      const LeafSet S = leaf_set(s_leafd, s_leafi, I, N_L, true);
-      if (!S.vis[l]) continue;
-      const double v = S.abb[l];
-      const int b = lagrange_base(s_axMu, a.hot.nmu, v);
-      double w[4];
-      lagrange_weights(s_axMu, b, v, w);
-      S.mub[l] = b;
+      const double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
+      if (W[3 * N_L + l] != 0.0) { const double z = W[N_L + l]; zlo = fmin(zlo, z); zhi = fmax(zhi, z); }
+    }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) S.muw[4 * l + k] = w[k];
-      S.Z[l] = log10(S.Z[l]);                // only log10 Z is needed from here on
+    for (int o = 16; o > 0; o >>= 1) {
+      zlo = fmin(zlo, __shfl_xor_sync(0xffffffffu, zlo, o));
+      zhi = fmax(zhi, __shfl_xor_sync(0xffffffffu, zhi, o));
+    }
+    if ((tid & 31) == 0) { s_wlo[tid >> 5] = zlo; s_whi[tid >> 5] = zhi; }
+    for (int m = tid; m < a.hot.nmu; m += kFluxThreads) s_axMu[m] = a.hot.mu[m];
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < kFluxThreads / 32; ++w) { zlo = fmin(zlo, s_wlo[w]); zhi = fmax(zhi, s_whi[w]); }
+      View vT{a.hot.logT, 1}, vG{a.hot.logg, 1}, vE{a.hot.logE, 1};
+      s_bT = lagrange_base(vT, a.hot.nT, logT);
+      s_bG = lagrange_base(vG, a.hot.ng, VEC[1]);
+      double w[4];
+      lagrange_weights(vT, s_bT, logT, w);
+      for (int x = 0; x < 4; ++x) s_wT[x] = w[x];
+      lagrange_weights(vG, s_bG, VEC[1], w);
+      for (int x = 0; x < 4; ++x) s_wG[x] = w[x];
+      if (zlo > zhi) { s_elo = 0; s_nrows = 4; }                 // nothing visible
+      else {
+        const double vlo = log10(a.energies[e0]) - zhi - log_kT - 1.0e-9;
+        const double vhi = log10(a.energies[e0 + ne - 1]) - zlo - log_kT + 1.0e-9;
+        const int elo = lagrange_base(vE, a.hot.nE, vlo);
+        const int ehi = lagrange_base(vE, a.hot.nE, vhi) + 4;    // exclusive
+        if (ehi - elo > a.slab_ne_max) {      // budget too small for this ring: refuse, never clamp
+          atomicExch(a.status + q, kUnsupported);
+          s_fail = 1;
+        }
+        s_elo = elo; s_nrows = ehi - elo;
+      }
     }
     __syncthreads();
+    if (s_fail) return;
+    const int elo = s_elo, nrows = s_nrows, nmu = a.hot.nmu;
+    for (int r = tid; r < nrows; r += kFluxThreads) s_axE[r] = a.hot.logE[elo + r];
+    __syncthreads();
+    for (int r = tid; r + 3 < nrows; r += kFluxThreads) {     // Lagrange denominators per base row
+      const double p0 = s_axE[r], p1 = s_axE[r + 1], p2 = s_axE[r + 2], p3 = s_axE[r + 3];
+      s_invden[4 * r + 0] = 1.0 / (p0 - p1) / (p0 - p2) / (p0 - p3);
+      s_invden[4 * r + 1] = 1.0 / (p1 - p0) / (p1 - p2) / (p1 - p3);
+      s_invden[4 * r + 2] = 1.0 / (p2 - p0) / (p2 - p1) / (p2 - p3);
+      s_invden[4 * r + 3] = 1.0 / (p3 - p0) / (p3 - p1) / (p3 - p2);
+    }
+    const long S0 = (long)a.hot.ng * nmu * a.hot.nE, S1 = (long)nmu * a.hot.nE, S2 = a.hot.nE;
+    for (int t = tid; t < nmu * nrows; t += kFluxThreads) {
+      const int m = t / nrows, e = t - m * nrows;
+      const double* base = a.hot.buf + (long)s_bT * S0 + (long)s_bG * S1 + (long)m * S2 + elo + e;
+      double acc = 0.0;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        double inner = 0.0;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) inner += s_wG[y] * __ldg(base + x * S0 + y * S1);
+        acc += s_wT[x] * inner;
+      }
+      s_slab[t] = acc;
+    }
   }
 
   const double norm = (ATM == 2) ? (kErg / kHKeV) * pow(10.0, 3.0 * logT)
                                  : kErg * kPlanckDistConst;
   const int interp_kind = a.phase_interp;
-  const bool periodic = (interp_kind != kSteffen);
-  double* flux_q = a.flux + (long)q * N_E * N_P;
+  const int k = tid;                         // output phase owned in the accumulation stage
+  const double phk = (k < N_P) ? a.phases[k] : 0.0;
+  double acc[kNEC];
+#pragma unroll
+  for (int g = 0; g < kNEC; ++g) acc[g] = 0.0;
 
-  // ---- energy tiles ------------------------------------------------------------------------
-  for (int e0 = 0; e0 < N_E; e0 += kET) {
-    const int et = min(kET, N_E - e0);
-    const int n_groups = (et + kEG - 1) / kEG;
-    const int n_items = n_groups * N_P;
-    // every thread owns at most two (phase, energy-group) items per tile
-    double acc[2][kEG];
+  for (int I = 0; I < n_img; ++I) {
+    __syncthreads();
+    // ---- leaf arrays of this image ------------------------------------------------------
+    const double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
+    for (int l = tid; l < N_L; l += kFluxThreads) {
+      s_PH[l] = W[l]; s_Z[l] = W[N_L + l]; s_aux[l] = W[2 * N_L + l]; s_geom[l] = W[3 * N_L + l];
+      s_flag[l] = 0u;
+    }
+    __syncthreads();
+    if (ATM == 2) {
+      for (int l = tid; l < N_L; l += kFluxThreads) {
+        if (s_geom[l] == 0.0) continue;
+        const double v = s_aux[l];
+        const int b = lagrange_base(s_axMu, a.hot.nmu, v);
+        double w[4];
+        lagrange_weights(s_axMu, b, v, w);
+        s_mub[l] = b;
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+        for (int x = 0; x < 4; ++x) s_muw[4 * l + x] = w[x];
+      }
+      __syncthreads();
+    }
+    for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
+    // ---- (1) leaf profile (pyx:445-478) -----------------------------------------------------
+    for (int t = tid; t < ne * N_L; t += kFluxThreads) {
+      const int e = t / N_L, l = t - e * N_L;
+      double val = 0.0;
+      const double geom = s_geom[l];
+      if (geom != 0.0) {
+        if (ATM == 1) {
+          val = bb_intensity(a.energies[e0 + e] / s_Z[l], kT) * norm * geom;
+        } else {
+          const double v = log10(a.energies[e0 + e]) - s_Z[l] - log_kT;     // log10(E'/kT)
+          const int nrows = s_nrows;
+          int bE = interval_search(s_axE, nrows, v) - 1;                    // base node (App. C.5)
+          if (s_elo + bE < 0) bE = -s_elo;
+          if (s_elo + bE > a.hot.nE - 4) bE = a.hot.nE - 4 - s_elo;
+          const double d0 = v - s_axE[bE], d1 = v - s_axE[bE + 1], d2 = v - s_axE[bE + 2],
+                       d3 = v - s_axE[bE + 3];
+          const double* iv = s_invden + 4 * bE;
+          const double wE0 = d1 * d2 * d3 * iv[0], wE1 = d0 * d2 * d3 * iv[1],
+                       wE2 = d0 * d1 * d3 * iv[2], wE3 = d0 * d1 * d2 * iv[3];
+          const double* row = s_slab + (long)s_mub[l] * nrows + bE;
+          const double* wM = s_muw + 4 * l;
+          double sum = 0.0;
 #pragma unroll
-      for (int g = 0; g < kEG; ++g) acc[s][g] = 0.0;
-
-    for (int I = 0; I < n_img; ++I) {
-      const LeafSet S = leaf_set(s_leafd, s_leafi, I, N_L, ATM == 2);
-      // (1) leaf profile for the tile (pyx:445-478)
-      for (int t = tid; t < et * N_L; t += kThreads) {
-        const int e = t / N_L, l = t - e * N_L;
-        double val = 0.0;
-        if (S.vis[l]) {
-          if (ATM == 1) {
-            val = bb_intensity(s_E[e0 + e] / S.Z[l], kT) * norm * S.geom[l];
-          } else {
-            const double v = s_logE[e0 + e] - S.Z[l] - log_kT;     // log10(E'/kT)
-            int bE = lagrange_base(s_axE, a.hot.nE, v);
-            double wE[4];
-            lagrange_weights(s_axE, bE, v, wE);
-            bE -= s_elo;                       // inside the slab by construction of [elo, ehi)
-            const double* row = s_slab + (long)S.mub[l] * s_ne + bE;
-            const double* wM = S.muw + 4 * l;
-            double sum = 0.0;
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-              const double* r = row + x * s_ne;
-              sum += wM[x] * (wE[0] * r[0] + wE[1] * r[1] + wE[2] * r[2] + wE[3] * r[3]);
-            }
-            if (sum < 0.0) sum = 0.0;                              // hot_Num4D.pyx:436-437
-            val = sum * norm * S.geom[l];
+          for (int x = 0; x < 4; ++x) {
+            const double* r = row + x * nrows;
+            sum += wM[x] * (wE0 * r[0] + wE1 * r[1] + wE2 * r[2] + wE3 * r[3]);
           }
+          if (sum < 0.0) sum = 0.0;                              // hot_Num4D.pyx:436-437
+          val = sum * norm * geom;
         }
-        s_y[e * N_L + l] = val;
       }
-      __syncthreads();
-      // (2) phase-spline coefficients (pyx:566-569)
-      View vPH{S.phase, 1};
-      for (int t = tid; t < et * (N_L - 1); t += kThreads) {
-        const int e = t / (N_L - 1), l = t - e * (N_L - 1);
-        View vY{s_y + e * N_L, 1};
-        double b, c, d;
-        interp_coeffs(interp_kind, periodic, vPH, vY, N_L, l, &b, &c, &d);
-        double* o = s_coef + ((long)e * N_L + l) * 4;
-        o[0] = vY[l]; o[1] = b; o[2] = c; o[3] = d;
+      s_y[e * N_L + l] = val;
+    }
+    __syncthreads();
+    // ---- (2) phase-spline coefficients + positivity flags (pyx:566-569) ----------------------
+    for (int t = tid; t < ne * (N_L - 1); t += kFluxThreads) {
+      const int e = t / (N_L - 1), l = t - e * (N_L - 1);
+      const double* y = s_y + e * N_L;
+      double b, c, d;
+      if (interp_kind == kSteffen) {
+        steffen_coeffs(s_PH, y, N_L, l, &b, &c, &d);
+      } else {
+        // Akima (periodic ghosts) with interval slopes taken as dy * (1/h)
+        auto slope = [&](int ii) -> double {
+          if (ii < 0) ii += N_L - 1; else if (ii > N_L - 2) ii -= N_L - 1;
+          return (y[ii + 1] - y[ii]) * s_aux[ii];
+        };
+        akima_from_slopes_ih(slope(l - 2), slope(l - 1), slope(l), slope(l + 1), slope(l + 2),
+                             s_aux[l], &b, &c, &d);
       }
-      __syncthreads();
-      // (3) evaluate at cell-shifted phases and accumulate (pyx:571-596)
-      const double ph_first = S.phase[0], ph_last = S.phase[N_L - 1];
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int item = tid + s * kThreads;
-        if (item >= n_items) break;
-        const int g = item / N_P, k = item - g * N_P;
-        const int eb = g * kEG;
-        const int ng = min(kEG, et - eb);
-        const double phk = a.phases[k];
-        int idx = -1;
-        double xprev = 0.0;
-        double c0[kEG], c1[kEG], c2[kEG], c3[kEG];
-        int loaded = -1;
-        for (int j = 0; j < A_; ++j) {
-          const double area = s_area[j];
-          if (area < 0.0) continue;
-          double x = phk + s_phi[j];
-          if (x > ph_last) { while (x > ph_last) x -= kTwoPi; }
-          else if (x < ph_first) { while (x < ph_first) x += kTwoPi; }
-          if (x < ph_first || x > ph_last) { atomicExch(a.status + q, kNumericalError); continue; }
-          if (idx < 0 || x < xprev) idx = interval_search(vPH, N_L, x);
-          else idx = interval_walk(vPH, N_L, x, idx);
+      const double y0 = y[l];
+      double* o = s_coef + ((long)e * N_L + l) * 4;
+      o[0] = y0; o[1] = b; o[2] = c; o[3] = d;
+      // Bernstein coefficients of the cubic on [0,h]: all >= 0  =>  spline >= 0 there
+      const double h = s_PH[l + 1] - s_PH[l];
+      const double B1 = y0 + b * h * (1.0 / 3.0);
+      const double B2 = y0 + h * ((2.0 / 3.0) * b + c * h * (1.0 / 3.0));
+      const double B3 = y0 + h * (b + h * (c + h * d));
+      if (y0 < 0.0 || B1 < 0.0 || B2 < 0.0 || B3 < 0.0) atomicOr(&s_flag[l], 1u << e);
+    }
+    __syncthreads();
+    // ---- (3) interval moments over the ring's cells, then 4 FMAs per energy (pyx:571-596) -----
+    if (k < N_P) {
+      const double ph_first = s_PH[0], ph_last = s_PH[N_L - 1];
+      int c = 0;
+      int m = -1;
+      double xprev = 0.0;
+      while (c < n_cells) {
+        double x = wrap_phase(phk + s_cphi[c], ph_first, ph_last);
+        if (x < ph_first || x > ph_last) { atomicExch(a.status + q, kNumericalError); ++c; continue; }
+        if (m < 0 || x < xprev) m = interval_search(s_PH, N_L, x);
+        else m = interval_walk(s_PH, N_L, x, m);
+        const double xm = s_PH[m], xn = s_PH[m + 1];
+        const bool last_iv = (m == N_L - 2);
+        double W0 = 0.0, W1 = 0.0, W2 = 0.0, W3 = 0.0;
+        const int c_start = c;
+        for (;;) {                                // absorb the cells that fall in interval m
+          const double d = x - xm;
+          const double A = s_carea[c];
+          W0 += A;
+          double t = A * d; W1 += t;
+          t *= d; W2 += t;
+          t *= d; W3 += t;
           xprev = x;
-          if (idx != loaded) {
+          ++c;
+          if (c >= n_cells) break;
+          x = wrap_phase(phk + s_cphi[c], ph_first, ph_last);
+          if (!(x >= xm && (x < xn || (last_iv && x <= xn)))) break;
+        }
+        const unsigned fl = s_flag[m];
+        const double* cp = s_coef + (long)m * 4;
 #pragma unroll
-            for (int gg = 0; gg < kEG; ++gg) {
-              if (gg < ng) {
-                const double2* cp =
-                    reinterpret_cast<const double2*>(s_coef + ((long)(eb + gg) * N_L + idx) * 4);
-                const double2 lo = cp[0], hi = cp[1];
-                c0[gg] = lo.x; c1[gg] = lo.y; c2[gg] = hi.x; c3[gg] = hi.y;
+        for (int g = 0; g < kNEC; ++g) {
+          if (g < ne) {
+            const double2 lo = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4);
+            const double2 hi = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4 + 2);
+            if (!((fl >> g) & 1u)) {
+              acc[g] += lo.x * W0 + lo.y * W1 + hi.x * W2 + hi.y * W3;
+            } else {                              // cubic may dip below zero: cell by cell (pyx:593)
+              for (int cc = c_start; cc < c; ++cc) {
+                const double xc = wrap_phase(phk + s_cphi[cc], ph_first, ph_last);
+                const double d = xc - xm;
+                const double f = lo.x + d * (lo.y + d * (hi.x + d * hi.y));
+                if (f > 0.0) acc[g] += s_carea[cc] * f;
               }
             }
-            loaded = idx;
-          }
-          const double d = x - S.phase[idx];
-#pragma unroll
-          for (int gg = 0; gg < kEG; ++gg) {
-            if (gg < ng) {
-              const double f = c0[gg] + d * (c1[gg] + d * (c2[gg] + d * c3[gg]));
-              if (f > 0.0) acc[s][gg] += area * f;
-            }
           }
         }
       }
-      __syncthreads();
     }
-    // (4) ring contribution -> flux[q, e, k]
+  }
+  // ---- ring/chunk contribution -> flux[q, e, k] -------------------------------------------------
+  if (k < N_P) {
+    double* flux_q = a.flux + (long)q * N_E * N_P;
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int item = tid + s * kThreads;
-      if (item >= n_items) break;
-      const int g = item / N_P, k = item - g * N_P;
-#pragma unroll
-      for (int gg = 0; gg < kEG; ++gg) {
-        const int e = e0 + g * kEG + gg;
-        if (g * kEG + gg < et && acc[s][gg] != 0.0) atomicAdd(flux_q + (long)e * N_P + k, acc[s][gg]);
-      }
-    }
+    for (int g = 0; g < kNEC; ++g)
+      if (g < ne && acc[g] != 0.0) atomicAdd(flux_q + (long)(e0 + g) * N_P + k, acc[g]);
   }
 }
 
@@ -496,37 +581,60 @@ __global__ void k_scale_flux(double* flux, const double* energies, int Q, int N_
   }
 }
 
-size_t azinv_smem_bytes(const AzinvArgs& a, int atm) {
-  size_t d = 4ul * a.n_rays + 2ul * a.n_azi + 2ul * a.n_energies + (size_t)kET * a.n_leaves * 5;
-  d += (size_t)a.n_img_max * a.n_leaves * (5 + (atm == 2 ? 4 : 0));
-  if (atm == 2) d += a.hot.nE + a.hot.nmu + (size_t)a.hot.nmu * a.slab_ne_max;
-  size_t bytes = d * sizeof(double);
-  bytes += ((size_t)a.n_img_max * a.n_leaves * 2) * sizeof(int);
-  return bytes;
+static size_t geom_smem_bytes(const AzinvArgs& a) {
+  return (4ul * a.n_rays + 2ul * a.n_img_max * a.n_leaves) * sizeof(double) +
+         (size_t)a.n_img_max * a.n_leaves * sizeof(int);
+}
+
+static size_t flux_smem_bytes(const AzinvArgs& a, int atm) {
+  size_t d = 2ul * a.n_azi + 4ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 5;
+  if (atm == 2) d += 4ul * a.n_leaves + 5ul * a.slab_ne_max + a.hot.nmu + (size_t)a.hot.nmu * a.slab_ne_max;
+  return d * sizeof(double) + 2ul * a.n_leaves * sizeof(int);
+}
+
+size_t azinv_workspace_doubles(int Q, int n_rings, int n_img_max, int n_leaves) {
+  return (size_t)Q * n_rings * n_img_max * 4 * n_leaves;
+}
+
+int azinv_slab_rows_budget(const AtmTable& t, const double* energies, int n_energies) {
+  // energy rows of the table one flux CTA can reach: the span of its kNEC energies plus the
+  // Doppler spread over the ring's leaves (|beta| < 0.45 => < 0.42 dex) plus the 4-node stencil
+  if (t.min_dlogE <= 0.0) return t.nE;
+  double span = 0.0;
+  for (int e0 = 0; e0 < n_energies; e0 += kNEC) {
+    const int e1 = (e0 + kNEC < n_energies ? e0 + kNEC : n_energies) - 1;
+    const double s = log10(energies[e1] / energies[e0]);
+    if (s > span) span = s;
+  }
+  const int rows = (int)ceil((span + 0.42) / t.min_dlogE) + 8;
+  return rows > t.nE ? t.nE : rows;
 }
 
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
-  if (a.n_phases * ((kET + kEG - 1) / kEG) > 2 * kThreads) return cudaErrorInvalidValue;
+  if (a.n_phases > kFluxThreads) return cudaErrorInvalidValue;
   if (a.n_img_max > kMaxImages || a.n_img_max < 1) return cudaErrorInvalidValue;
+  if (!a.ws_leaf || !a.ws_nimg) return cudaErrorInvalidValue;
   const int atm = a.hot_atm_ext;
+  if (atm != 1 && atm != 2) return cudaErrorNotSupported;
   if (atm == 2) {
     if (a.slab_ne_max <= 0 || a.slab_ne_max > a.hot.nE) a.slab_ne_max = a.hot.nE;
     if (a.slab_ne_max < 8) a.slab_ne_max = 8;
   }
-  size_t smem = azinv_smem_bytes(a, atm);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  dim3 grid(a.n_rings, a.Q);
+  const size_t gsm = geom_smem_bytes(a), fsm = flux_smem_bytes(a, atm);
+  if (gsm > 227 * 1024 || fsm > 227 * 1024) return cudaErrorInvalidValue;
+  const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
+  dim3 ggrid(a.n_rings, a.Q), fgrid(a.n_rings * n_chunks, a.Q);
   cudaError_t err;
   if (atm == 1) {
-    err = cudaFuncSetAttribute(k_integrate_azinv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    k_integrate_azinv<1><<<grid, kThreads, smem, stream>>>(a);
-  } else if (atm == 2) {
-    err = cudaFuncSetAttribute(k_integrate_azinv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    k_integrate_azinv<2><<<grid, kThreads, smem, stream>>>(a);
+    if ((err = cudaFuncSetAttribute(k_azinv_geometry<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(k_azinv_flux<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)) != cudaSuccess) return err;
+    k_azinv_geometry<1><<<ggrid, kGeomThreads, gsm, stream>>>(a);
+    k_azinv_flux<1><<<fgrid, kFluxThreads, fsm, stream>>>(a);
   } else {
-    return cudaErrorNotSupported;
+    if ((err = cudaFuncSetAttribute(k_azinv_geometry<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(k_azinv_flux<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)) != cudaSuccess) return err;
+    k_azinv_geometry<2><<<ggrid, kGeomThreads, gsm, stream>>>(a);
+    k_azinv_flux<2><<<fgrid, kFluxThreads, fsm, stream>>>(a);
   }
   err = cudaGetLastError();
   if (err != cudaSuccess) return err;

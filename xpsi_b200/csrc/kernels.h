@@ -40,10 +40,14 @@ struct AzinvArgs {
   int scale_by_energy;               // apply flux /= E keV (pyx:610-612)
   double* flux;                      // [Q][N_E][N_P], zero-initialised by the caller
   int* status;                       // [Q]
+  double* ws_leaf;                   // workspace [Q][n_rings][n_img_max][4][N_L] (geometry -> flux)
+  int* ws_nimg;                      // workspace [Q][n_rings]: image orders to integrate per ring
   unsigned long long* work;          // nullptr or [4]: H half-leaf visits, V visible leaves,
                                      //   RI (ring,image) pairs reaching the phase stage, K radiating cells over RI
 };
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream);
+size_t azinv_workspace_doubles(int Q, int n_rings, int n_img_max, int n_leaves);
+int azinv_slab_rows_budget(const AtmTable& t, const double* host_energies, int n_energies);
 
 // a9: tools/energy_integrator.pyx:27-114, one spline per (signal q, phase column)
 struct EnergyIntegArgs {
