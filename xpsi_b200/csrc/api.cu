@@ -184,7 +184,7 @@ int xpsi_b200_integrate_azimuthal_invariance(
   a.hot_atm_ext = hot_atm_ext;
   if (hot_atm_ext == XPSI_B200_ATM_NUM4D) {
     a.hot = hot_atmosphere->view;
-    a.slab_ne_max = xb::azinv_slab_rows_budget(a.hot, energies, n_energies);
+    xb::azinv_slab_budgets(a.hot, energies, n_energies, &a.slab_ne_max, &a.slab_rows_ring);
   }
   a.image_order_limit = image_order_limit > 0 ? image_order_limit : 0;
   a.n_img_max = image_order_limit > 0 ? image_order_limit : xb::kMaxImages;
@@ -192,13 +192,16 @@ int xpsi_b200_integrate_azimuthal_invariance(
   a.phase_interp = phase_interpolant;
   a.scale_by_energy = 1;
   a.flux = d_flux.p; a.status = d_status.p;
-  Dev<double> d_ws; Dev<int> d_wsn;
-  CK(d_ws.alloc(xb::azinv_workspace_doubles(1, n_rings, a.n_img_max, n_leaves)));
-  CK(d_wsn.alloc(n_rings));
-  a.ws_leaf = d_ws.p; a.ws_nimg = d_wsn.p;
+  Dev<double> d_ws, d_wh, d_wslab; Dev<int> d_wi;
+  {
+    size_t nl, nh, ni, ns;
+    xb::azinv_workspace_sizes(a, &nl, &nh, &ni, &ns);
+    CK(d_ws.alloc(nl)); CK(d_wh.alloc(nh)); CK(d_wi.alloc(ni)); CK(d_wslab.alloc(ns));
+  }
+  a.ws_leaf = d_ws.p; a.ws_hdr = d_wh.p; a.ws_ihdr = d_wi.p; a.ws_slab = d_wslab.p;
   cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_integrate_azinv");
-  g_launches += 3;
+  g_launches += (hot_atm_ext == XPSI_B200_ATM_NUM4D) ? 4 : 3;
   int status = 0;
   CK(d_flux.download(flux_out, (size_t)n_energies * n_phases));
   CK(d_status.download(&status, 1));
@@ -329,7 +332,7 @@ int xpsi_b200_eval_marginal_likelihood(
 // ===========================================================================
 struct xpsi_b200_pipeline {
   xpsi_b200_pipeline_config cfg;
-  int max_batch = 0, slab_rows = 0;
+  int max_batch = 0, slab_rows_chunk = 0, slab_rows_ring = 0;
   std::vector<int> member_component;
   const xpsi_b200_atmosphere* atm = nullptr;
   // constants
@@ -344,7 +347,7 @@ struct xpsi_b200_pipeline {
   Dev<double> flux, xin, folded, chan_lnL, expected, lnL;
   Dev<int> chan_status, status_q, status;
   Dev<unsigned long long> work;
-  Dev<double> ws_leaf; Dev<int> ws_nimg;
+  Dev<double> ws_leaf, ws_hdr, ws_slab; Dev<int> ws_ihdr;
   int count_work = 0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float stage_ms[4] = {0, 0, 0, 0};
@@ -402,13 +405,15 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   a.maxDeflection = p->maxd.p; a.cos_gamma = p->cgamma.p;
   a.energies = p->energies.p; a.leaves = p->leaves.p; a.phases = p->phases.p;
   a.hot_atm_ext = c.hot_atm_ext;
-  if (c.hot_atm_ext == XPSI_B200_ATM_NUM4D) { a.hot = p->atm->view; a.slab_ne_max = p->slab_rows; }
+  if (c.hot_atm_ext == XPSI_B200_ATM_NUM4D) {
+    a.hot = p->atm->view; a.slab_ne_max = p->slab_rows_chunk; a.slab_rows_ring = p->slab_rows_ring;
+  }
   a.image_order_limit = c.image_order_limit > 0 ? c.image_order_limit : 0;
   a.n_img_max = c.image_order_limit > 0 ? c.image_order_limit : xb::kMaxImages;
   a.phase_interp = c.phase_interpolant;
   a.scale_by_energy = 0;
   a.flux = p->flux.p; a.status = p->status_q.p;
-  a.ws_leaf = p->ws_leaf.p; a.ws_nimg = p->ws_nimg.p;
+  a.ws_leaf = p->ws_leaf.p; a.ws_hdr = p->ws_hdr.p; a.ws_ihdr = p->ws_ihdr.p; a.ws_slab = p->ws_slab.p;
   a.work = p->count_work ? p->work.p : nullptr;
   if (a.work) CK(cudaMemsetAsync(p->work.p, 0, 4 * sizeof(unsigned long long), g_stream));
   cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
@@ -447,7 +452,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   e = xb::launch_marginal(m, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_marginal");
   CK(cudaEventRecord(p->ev[4], g_stream));
-  g_launches += 8;   // expand, geometry, flux, energy, fold, member-status, marginal, channel-sum
+  g_launches += 8 + (c.hot_atm_ext == XPSI_B200_ATM_NUM4D ? 1 : 0);   // expand, geometry, [slab], flux, energy, fold, member-status, marginal, channel-sum
   return 0;
 }
 
@@ -505,14 +510,22 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
   ok(p->chan_status.alloc(B * c.n_chan)); ok(p->expected.alloc(B * c.n_chan * c.n_bins));
   ok(p->lnL.alloc(B)); ok(p->status_q.alloc(Q)); ok(p->status.alloc(B)); ok(p->work.alloc(4));
   {
-    const int nimg = c.image_order_limit > 0 ? c.image_order_limit : xb::kMaxImages;
-    ok(p->ws_leaf.alloc(xb::azinv_workspace_doubles((int)Q, c.max_rings, nimg, c.n_leaves)));
-    ok(p->ws_nimg.alloc(Q * R));
+    xb::AzinvArgs w;
+    memset(&w, 0, sizeof(w));
+    w.Q = (int)Q; w.n_rings = c.max_rings; w.n_leaves = c.n_leaves; w.hot_atm_ext = c.hot_atm_ext;
+    w.n_img_max = c.image_order_limit > 0 ? c.image_order_limit : xb::kMaxImages;
+    if (c.hot_atm_ext == XPSI_B200_ATM_NUM4D) {
+      w.hot = p->atm->view;
+      xb::azinv_slab_budgets(w.hot, c.energies, c.n_energies, &p->slab_rows_chunk, &p->slab_rows_ring);
+      w.slab_rows_ring = p->slab_rows_ring;
+    }
+    size_t nl, nh, ni, ns;
+    xb::azinv_workspace_sizes(w, &nl, &nh, &ni, &ns);
+    ok(p->ws_leaf.alloc(nl)); ok(p->ws_hdr.alloc(nh)); ok(p->ws_ihdr.alloc(ni)); ok(p->ws_slab.alloc(ns));
   }
   for (int i = 0; i < 5; ++i) ok(cudaEventCreate(&p->ev[i]));
   ok(cudaStreamSynchronize(g_stream));
   if (e != cudaSuccess) { cuda_fail(e, "pipeline_create"); delete p; return nullptr; }
-  if (c.hot_atm_ext == XPSI_B200_ATM_NUM4D) p->slab_rows = xb::azinv_slab_rows_budget(p->atm->view, c.energies, c.n_energies);
   g_launches += 1;
   return p;
 }

@@ -12,14 +12,18 @@
 //   pieces rebuilt in registers, then Doppler, redshift and the solid-angle
 //   Jacobian.  The reference's sequential visibility state machine is replayed
 //   verbatim by one thread per image order.  Output per (q, ring, image): four
-//   N_L-vectors PHASE, Z (log10 Z for Num4D), mu*eta, GEOM (0 = leaf dark).
+//   N_L-vectors PHASE, Z (log10 Z for Num4D), mu*eta, GEOM (0 = leaf dark), plus a
+//   ring header (image orders to integrate, (T,g) Lagrange stencil, redshift range).
+//
+// k_azinv_slab       Num4D only, one CTA per (q, ring): contracts the 4-D table over
+//   (log T, log g) -- constant on a ring -- into a (mu, E) slab restricted to the
+//   energy rows the ring can reach, written to an L2-resident workspace.
 //
 // k_azinv_flux<ATM>  one CTA per (q, ring, chunk of 8 energies): thousands of
 //   small CTAs, ~50 KB of shared memory each, 4 resident per SM.
-//   * Num4D: the 4-D table is contracted over (log T, log g) -- constant on a
-//     ring -- into a (mu, E) slab restricted to the ~16 energy rows this chunk
-//     can reach; every intensity is then a 4x4 stencil on-chip with
-//     precomputed Lagrange denominators.
+//   * Num4D: the ~16 energy rows of the ring's slab this chunk can reach are
+//     copied to shared memory; every intensity is then a 4x4 stencil on-chip
+//     with precomputed Lagrange denominators.
 //   * the leaf profile and its phase-spline (Akima periodic / Steffen)
 //     coefficients are built in shared memory.
 //   * accumulation over the ring's cells uses interval moments: for an output
@@ -44,6 +48,23 @@ __device__ __forceinline__ double bb_intensity(double E, double kT) {
   return E * E * E / (exp(E / kT) - 1.0);     // hot_BB.pyx:85-87
 }
 
+// per-ring headers written by the geometry kernel
+//   ints   [0] image orders to integrate  [1] first radiating cell  [2],[3] (T,g) base nodes
+//          [4],[5] first row / row count of the ring's slab (written by k_azinv_slab)
+//   doubles [0],[1] min/max of Z (log10 Z for Num4D) over lit leaves  [2..5] T weights
+//          [6..9] g weights  [10] log10 T  [11] log10 g
+constexpr int kIHdr = 8, kDHdr = 12;
+
+// order-preserving map double <-> unsigned 64 (for shared-memory atomicMin/Max)
+__device__ __forceinline__ unsigned long long order_key(double v) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_order(unsigned long long k) {
+  const unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+
 // leaf workspace layout: [ring][image][4][N_L]
 __device__ __forceinline__ double* leaf_ptr(double* ws, long ring, int n_img_max, int I, int N_L) {
   return ws + ((ring * n_img_max + I) * 4) * (long)N_L;
@@ -60,7 +81,7 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
   const int R_ = a.n_rings_q ? a.n_rings_q[q] : a.n_rings;
   const int A_ = a.n_azi_q ? a.n_azi_q[q] : a.n_azi;
   const long ring = (long)q * a.n_rings + i;           // padded ring index
-  if (i >= R_) { if (tid == 0) a.ws_nimg[ring] = 0; return; }
+  if (i >= R_) { if (tid == 0) a.ws_ihdr[ring * kIHdr] = 0; return; }
   const int N_R = a.n_rays, N_L = a.n_leaves;
   const long cell0 = ring * a.n_azi;
   const int leaf_lim = (N_L % 2 == 0) ? N_L / 2 : (N_L + 1) / 2;
@@ -69,10 +90,11 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
   extern __shared__ double smem[];
   __shared__ int s_J, s_jhalf, s_nimg;
   __shared__ int s_inv2[kMaxImages], s_dom[kMaxImages], s_mono[kMaxImages];
+  __shared__ unsigned long long s_zlo[kMaxImages], s_zhi[kMaxImages];   // order-preserving keys
 
   // ---- does the ring radiate? (pyx:286-296); a null mask means cellArea > 0 (HotRegion.py:965)
   if (tid == 0) { s_J = A_; s_jhalf = N_R - 1; }
-  if (tid < kMaxImages) { s_inv2[tid] = 0; s_dom[tid] = 0; s_mono[tid] = 0; }
+  if (tid < kMaxImages) { s_inv2[tid] = 0; s_dom[tid] = 0; s_mono[tid] = 0; s_zlo[tid] = ~0ull; s_zhi[tid] = 0ull; }
   __syncthreads();
   for (int j = tid; j < A_; j += kGeomThreads) {
     const bool rad = a.radiates ? (a.radiates[cell0 + j] == 1) : (a.cellArea[cell0 + j] > 0.0);
@@ -80,7 +102,7 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
   }
   __syncthreads();
   const int J = s_J;
-  if (J >= A_) { if (tid == 0) a.ws_nimg[ring] = 0; return; }
+  if (J >= A_) { if (tid == 0) a.ws_ihdr[ring * kIHdr] = 0; return; }
 
   double* sp = smem;
   double* s_defl = sp; sp += N_R;
@@ -186,7 +208,10 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
         eta = Lorentz / superlum;
       } else { superlum = 1.0; eta = Lorentz; }
       const double Z = eta * Grav_z;
-      wZ[kdx] = (ATM == 2) ? log10(Z) : Z;
+      const double zstore = (ATM == 2) ? log10(Z) : Z;
+      wZ[kdx] = zstore;
+      atomicMin(&s_zlo[I], order_key(zstore));
+      atomicMax(&s_zhi[I], order_key(zstore));
       wAbb[kdx] = mu * eta;
       wGeom[kdx] = mu * fabs(deriv) * Grav_z * eta * eta * eta / superlum;
       s_ptrue[I * N_L + kdx] = a.leaves[kdx] + lagv;
@@ -259,7 +284,28 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
       atomicAdd(a.work + 3, Kc * n);
     }
     s_nimg = n;
-    a.ws_nimg[ring] = n;
+    int* ih = a.ws_ihdr + ring * kIHdr;
+    double* dh = a.ws_hdr + ring * kDHdr;
+    ih[0] = n; ih[1] = J;
+    const double* VEC = a.srcParams + (a.params_per_cell ? (cell0 + J) : ring) * a.n_params;
+    double zlo = 1e300, zhi = -1e300;
+    for (int I = 0; I < n; ++I) {
+      if (s_zhi[I] == 0ull) continue;
+      zlo = fmin(zlo, key_order(s_zlo[I])); zhi = fmax(zhi, key_order(s_zhi[I]));
+    }
+    dh[0] = zlo; dh[1] = zhi; dh[10] = VEC[0];
+    if (ATM == 2 && n > 0) {     // (T,g) stencil of the ring, hot_Num4D.pyx:295-409
+      View vT{a.hot.logT, 1}, vG{a.hot.logg, 1};
+      const int bT = lagrange_base(vT, a.hot.nT, VEC[0]);
+      const int bG = lagrange_base(vG, a.hot.ng, VEC[1]);
+      double w[4];
+      lagrange_weights(vT, bT, VEC[0], w);
+      for (int x = 0; x < 4; ++x) dh[2 + x] = w[x];
+      lagrange_weights(vG, bG, VEC[1], w);
+      for (int x = 0; x < 4; ++x) dh[6 + x] = w[x];
+      ih[2] = bT; ih[3] = bG;
+      dh[11] = VEC[1];
+    }
   }
   __syncthreads();
   n_img = s_nimg;
@@ -270,15 +316,62 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
 }
 
 // ===========================================================================
-// flux
+// slab (Num4D)
 // ===========================================================================
-// x = phase + cell azimuth, brought into [first, last] by whole turns (pyx:575-583)
-__device__ __forceinline__ double wrap_phase(double x, double first, double last) {
-  if (x > last) { while (x > last) x -= kTwoPi; }
-  else if (x < first) { while (x < first) x += kTwoPi; }
-  return x;
+// energy rows of the table needed for log10(E'/kT) in [vlo, vhi]: [elo, ehi)
+template <class P>
+__device__ __forceinline__ void row_range(const P& axis, int nE, double vlo, double vhi, int* elo, int* ehi) {
+  *elo = lagrange_base(axis, nE, vlo - 1.0e-9);
+  *ehi = lagrange_base(axis, nE, vhi + 1.0e-9) + 4;
 }
 
+constexpr int kSlabThreads = 256;
+
+__global__ void __launch_bounds__(kSlabThreads) k_azinv_slab(AzinvArgs a) {
+  const int i = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
+  const long ring = (long)q * a.n_rings + i;
+  int* ih = a.ws_ihdr + ring * kIHdr;
+  if (ih[0] == 0) return;
+  const double* dh = a.ws_hdr + ring * kDHdr;
+  __shared__ int s_elo, s_nrows;
+  __shared__ double s_wT[4], s_wG[4];
+  if (tid == 0) {
+    const double zlo = dh[0], zhi = dh[1];
+    const double log_kT = log10(kKBOverKeV * pow(10.0, dh[10]));
+    View vE{a.hot.logE, 1};
+    int elo = 0, ehi = 4;
+    if (zlo <= zhi)
+      row_range(vE, a.hot.nE, log10(a.energies[0]) - zhi - log_kT,
+                log10(a.energies[a.n_energies - 1]) - zlo - log_kT, &elo, &ehi);
+    if (ehi - elo > a.slab_rows_ring) { atomicExch(a.status + q, kUnsupported); ih[0] = 0; ehi = elo; }
+    ih[4] = elo; ih[5] = ehi - elo;
+    s_elo = elo; s_nrows = ehi - elo;
+    for (int x = 0; x < 4; ++x) { s_wT[x] = dh[2 + x]; s_wG[x] = dh[6 + x]; }
+  }
+  __syncthreads();
+  const int elo = s_elo, nrows = s_nrows, nmu = a.hot.nmu;
+  if (nrows == 0) return;
+  const int bT = ih[2], bG = ih[3];
+  const long S0 = (long)a.hot.ng * nmu * a.hot.nE, S1 = (long)nmu * a.hot.nE, S2 = a.hot.nE;
+  double* out = a.ws_slab + ring * (long)nmu * a.slab_rows_ring;
+  for (int t = tid; t < nmu * nrows; t += kSlabThreads) {
+    const int m = t / nrows, e = t - m * nrows;
+    const double* base = a.hot.buf + (long)bT * S0 + (long)bG * S1 + (long)m * S2 + elo + e;
+    double acc = 0.0;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      double inner = 0.0;
+#pragma unroll
+      for (int y = 0; y < 4; ++y) inner += s_wG[y] * __ldg(base + x * S0 + y * S1);
+      acc += s_wT[x] * inner;
+    }
+    out[(long)m * a.slab_rows_ring + e] = acc;
+  }
+}
+
+// ===========================================================================
+// flux
+// ===========================================================================
 template <int ATM>
 __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
@@ -287,8 +380,10 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
   const int q = blockIdx.y;
   const int tid = threadIdx.x;
   const long ring = (long)q * a.n_rings + i;
-  const int n_img = a.ws_nimg[ring];
+  const int* ih = a.ws_ihdr + ring * kIHdr;
+  const int n_img = ih[0];
   if (n_img == 0) return;
+  const double* dh = a.ws_hdr + ring * kDHdr;
   const int A_ = a.n_azi_q ? a.n_azi_q[q] : a.n_azi;
   const int N_E = a.n_energies, N_L = a.n_leaves, N_P = a.n_phases;
   const long cell0 = ring * a.n_azi;
@@ -297,8 +392,8 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
   const int n_img_max = a.n_img_max;
 
   extern __shared__ double smem[];
-  __shared__ int s_ncell, s_J, s_fail, s_elo, s_nrows, s_bT, s_bG;
-  __shared__ double s_wT[4], s_wG[4], s_wlo[kFluxThreads / 32], s_whi[kFluxThreads / 32];
+  __shared__ int s_ncell;
+  __shared__ double s_E[kNEC], s_logE[kNEC];
   double* sp = smem;
   double* s_cphi = sp; sp += a.n_azi;
   double* s_carea = sp; sp += a.n_azi;
@@ -320,83 +415,63 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
   int* s_mub = reinterpret_cast<int*>(sp);
   unsigned* s_flag = reinterpret_cast<unsigned*>(s_mub + N_L);
 
-  // ---- compact list of the ring's radiating cells -----------------------------------
-  if (tid == 0) { s_ncell = 0; s_J = A_; s_fail = 0; }
-  __syncthreads();
-  if (tid < 32) {       // ordered compaction by one warp keeps cells ascending in azimuth
+  // ---- compact list of the ring's radiating cells (one warp: keeps azimuth order) ------
+  if (tid < 32) {
     int base = 0;
     for (int j0 = 0; j0 < A_; j0 += 32) {
       const int j = j0 + tid;
       bool rad = false;
       double area = 0.0, phi = 0.0;
       if (j < A_) {
-        rad = a.radiates ? (a.radiates[cell0 + j] == 1) : (a.cellArea[cell0 + j] > 0.0);
         area = a.cellArea[cell0 + j]; phi = a.phi[cell0 + j];
+        rad = a.radiates ? (a.radiates[cell0 + j] == 1) : (area > 0.0);
       }
       const unsigned m = __ballot_sync(0xffffffffu, rad);
       if (rad) {
         const int pos = base + __popc(m & ((1u << tid) - 1u));
         s_cphi[pos] = phi; s_carea[pos] = area;
       }
-      if (m && base == 0 && tid == 0) s_J = j0 + __ffs(m) - 1;
       base += __popc(m);
     }
     if (tid == 0) s_ncell = base;
+  } else if (tid < 32 + kNEC) {
+    const int e = tid - 32;
+    const double E = a.energies[e0 + (e < ne ? e : 0)];
+    s_E[e] = E; s_logE[e] = log10(E);
+  }
+  const double logT = dh[10];
+  const double kT = kKBOverKeV * pow(10.0, logT);
+  const double log_kT = log10(kT);
+
+  // ---- Num4D: copy the rows of the ring's slab this chunk reaches ------------------------
+  int nrows = 0, elo_tab = 0;
+  if (ATM == 2) {
+    const int elo_ring = ih[4], nrows_ring = ih[5];
+    const double zlo = dh[0], zhi = dh[1];
+    // every thread derives the same chunk range from the ring's axis segment (no serial section)
+    View vE{a.hot.logE + elo_ring, 1};
+    int lo_c = 0, hi_c = 4;
+    if (zlo <= zhi)
+      row_range(vE, nrows_ring, log10(a.energies[e0]) - zhi - log_kT,
+                log10(a.energies[e0 + ne - 1]) - zlo - log_kT, &lo_c, &hi_c);
+    nrows = hi_c - lo_c;
+    elo_tab = elo_ring + lo_c;
+    if (nrows > a.slab_ne_max) {       // budget too small for this ring: refuse, never clamp
+      if (tid == 0) atomicExch(a.status + q, kUnsupported);
+      return;
+    }
+    for (int m = tid; m < a.hot.nmu; m += kFluxThreads) s_axMu[m] = a.hot.mu[m];
+    for (int r = tid; r < nrows; r += kFluxThreads) s_axE[r] = a.hot.logE[elo_tab + r];
+    const double* src = a.ws_slab + ring * (long)a.hot.nmu * a.slab_rows_ring + lo_c;
+    for (int t = tid; t < a.hot.nmu * nrows; t += kFluxThreads) {
+      const int m = t / nrows, e = t - m * nrows;
+      s_slab[t] = src[(long)m * a.slab_rows_ring + e];
+    }
   }
   __syncthreads();
   const int n_cells = s_ncell;
   if (n_cells == 0) return;
-  const int J = s_J;
-  const double* VEC = a.srcParams + (a.params_per_cell ? (cell0 + J) : ring) * a.n_params;
-  const double logT = VEC[0];
-  const double kT = kKBOverKeV * pow(10.0, logT);
-  const double log_kT = log10(kT);
-
-  // ---- Num4D: slab for the energy rows this chunk reaches ---------------------------------
   if (ATM == 2) {
-    // range of log10 Z over the visible leaves of all images
-    double zlo = 1e300, zhi = -1e300;
-    for (int t = tid; t < n_img * N_L; t += kFluxThreads) {
-      const int I = t / N_L, l = t - I * N_L;
-      const double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
-      if (W[3 * N_L + l] != 0.0) { const double z = W[N_L + l]; zlo = fmin(zlo, z); zhi = fmax(zhi, z); }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      zlo = fmin(zlo, __shfl_xor_sync(0xffffffffu, zlo, o));
-      zhi = fmax(zhi, __shfl_xor_sync(0xffffffffu, zhi, o));
-    }
-    if ((tid & 31) == 0) { s_wlo[tid >> 5] = zlo; s_whi[tid >> 5] = zhi; }
-    for (int m = tid; m < a.hot.nmu; m += kFluxThreads) s_axMu[m] = a.hot.mu[m];
-    __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < kFluxThreads / 32; ++w) { zlo = fmin(zlo, s_wlo[w]); zhi = fmax(zhi, s_whi[w]); }
-      View vT{a.hot.logT, 1}, vG{a.hot.logg, 1}, vE{a.hot.logE, 1};
-      s_bT = lagrange_base(vT, a.hot.nT, logT);
-      s_bG = lagrange_base(vG, a.hot.ng, VEC[1]);
-      double w[4];
-      lagrange_weights(vT, s_bT, logT, w);
-      for (int x = 0; x < 4; ++x) s_wT[x] = w[x];
-      lagrange_weights(vG, s_bG, VEC[1], w);
-      for (int x = 0; x < 4; ++x) s_wG[x] = w[x];
-      if (zlo > zhi) { s_elo = 0; s_nrows = 4; }                 // nothing visible
-      else {
-        const double vlo = log10(a.energies[e0]) - zhi - log_kT - 1.0e-9;
-        const double vhi = log10(a.energies[e0 + ne - 1]) - zlo - log_kT + 1.0e-9;
-        const int elo = lagrange_base(vE, a.hot.nE, vlo);
-        const int ehi = lagrange_base(vE, a.hot.nE, vhi) + 4;    // exclusive
-        if (ehi - elo > a.slab_ne_max) {      // budget too small for this ring: refuse, never clamp
-          atomicExch(a.status + q, kUnsupported);
-          s_fail = 1;
-        }
-        s_elo = elo; s_nrows = ehi - elo;
-      }
-    }
-    __syncthreads();
-    if (s_fail) return;
-    const int elo = s_elo, nrows = s_nrows, nmu = a.hot.nmu;
-    for (int r = tid; r < nrows; r += kFluxThreads) s_axE[r] = a.hot.logE[elo + r];
-    __syncthreads();
     for (int r = tid; r + 3 < nrows; r += kFluxThreads) {     // Lagrange denominators per base row
       const double p0 = s_axE[r], p1 = s_axE[r + 1], p2 = s_axE[r + 2], p3 = s_axE[r + 3];
       s_invden[4 * r + 0] = 1.0 / (p0 - p1) / (p0 - p2) / (p0 - p3);
@@ -404,21 +479,9 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
       s_invden[4 * r + 2] = 1.0 / (p2 - p0) / (p2 - p1) / (p2 - p3);
       s_invden[4 * r + 3] = 1.0 / (p3 - p0) / (p3 - p1) / (p3 - p2);
     }
-    const long S0 = (long)a.hot.ng * nmu * a.hot.nE, S1 = (long)nmu * a.hot.nE, S2 = a.hot.nE;
-    for (int t = tid; t < nmu * nrows; t += kFluxThreads) {
-      const int m = t / nrows, e = t - m * nrows;
-      const double* base = a.hot.buf + (long)s_bT * S0 + (long)s_bG * S1 + (long)m * S2 + elo + e;
-      double acc = 0.0;
-#pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        double inner = 0.0;
-#pragma unroll
-        for (int y = 0; y < 4; ++y) inner += s_wG[y] * __ldg(base + x * S0 + y * S1);
-        acc += s_wT[x] * inner;
-      }
-      s_slab[t] = acc;
-    }
   }
+  // mean spacing of the axis segment: first guess of the energy stencil (then walked)
+  const double inv_dE = (ATM == 2 && nrows > 1) ? (double)(nrows - 1) / (s_axE[nrows - 1] - s_axE[0]) : 0.0;
 
   const double norm = (ATM == 2) ? (kErg / kHKeV) * pow(10.0, 3.0 * logT)
                                  : kErg * kPlanckDistConst;
@@ -459,13 +522,13 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
       const double geom = s_geom[l];
       if (geom != 0.0) {
         if (ATM == 1) {
-          val = bb_intensity(a.energies[e0 + e] / s_Z[l], kT) * norm * geom;
+          val = bb_intensity(s_E[e] / s_Z[l], kT) * norm * geom;
         } else {
-          const double v = log10(a.energies[e0 + e]) - s_Z[l] - log_kT;     // log10(E'/kT)
-          const int nrows = s_nrows;
-          int bE = interval_search(s_axE, nrows, v) - 1;                    // base node (App. C.5)
-          if (s_elo + bE < 0) bE = -s_elo;
-          if (s_elo + bE > a.hot.nE - 4) bE = a.hot.nE - 4 - s_elo;
+          const double v = s_logE[e] - s_Z[l] - log_kT;                     // log10(E'/kT)
+          int j = interval_walk(s_axE, nrows, v, (int)((v - s_axE[0]) * inv_dE));
+          int bE = j - 1;                                                   // base node (App. C.5)
+          if (elo_tab + bE < 0) bE = -elo_tab;
+          if (elo_tab + bE > a.hot.nE - 4) bE = a.hot.nE - 4 - elo_tab;
           const double d0 = v - s_axE[bE], d1 = v - s_axE[bE + 1], d2 = v - s_axE[bE + 2],
                        d3 = v - s_axE[bE + 3];
           const double* iv = s_invden + 4 * bE;
@@ -505,24 +568,35 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
       const double y0 = y[l];
       double* o = s_coef + ((long)e * N_L + l) * 4;
       o[0] = y0; o[1] = b; o[2] = c; o[3] = d;
-      // Bernstein coefficients of the cubic on [0,h]: all >= 0  =>  spline >= 0 there
+      // Bernstein coefficients of the cubic on [0,h] (end values are the nodes themselves):
+      // all >= 0  =>  the spline is >= 0 on the interval
       const double h = s_PH[l + 1] - s_PH[l];
       const double B1 = y0 + b * h * (1.0 / 3.0);
       const double B2 = y0 + h * ((2.0 / 3.0) * b + c * h * (1.0 / 3.0));
-      const double B3 = y0 + h * (b + h * (c + h * d));
-      if (y0 < 0.0 || B1 < 0.0 || B2 < 0.0 || B3 < 0.0) atomicOr(&s_flag[l], 1u << e);
+      if (y0 < 0.0 || B1 < 0.0 || B2 < 0.0 || y[l + 1] < 0.0) atomicOr(&s_flag[l], 1u << e);
     }
     __syncthreads();
     // ---- (3) interval moments over the ring's cells, then 4 FMAs per energy (pyx:571-596) -----
     if (k < N_P) {
       const double ph_first = s_PH[0], ph_last = s_PH[N_L - 1];
+      // cells ascend in azimuth, so the whole-turn offset that brings phase+azimuth into
+      // [first,last] (pyx:575-583) only ever steps down by 2 pi along the walk
       int c = 0;
       int m = -1;
-      double xprev = 0.0;
+      double off = 0.0;
+      bool searched = false;
       while (c < n_cells) {
-        double x = wrap_phase(phk + s_cphi[c], ph_first, ph_last);
-        if (x < ph_first || x > ph_last) { atomicExch(a.status + q, kNumericalError); ++c; continue; }
-        if (m < 0 || x < xprev) m = interval_search(s_PH, N_L, x);
+        double x = phk + s_cphi[c] + off;
+        if (x > ph_last || x < ph_first) {
+          double xr = phk + s_cphi[c];
+          if (xr > ph_last) { while (xr > ph_last) xr -= kTwoPi; }
+          else if (xr < ph_first) { while (xr < ph_first) xr += kTwoPi; }
+          if (xr < ph_first || xr > ph_last) { atomicExch(a.status + q, kNumericalError); ++c; continue; }
+          off = xr - (phk + s_cphi[c]);
+          x = xr;
+          searched = false;
+        }
+        if (!searched) { m = interval_search(s_PH, N_L, x); searched = true; }
         else m = interval_walk(s_PH, N_L, x, m);
         const double xm = s_PH[m], xn = s_PH[m + 1];
         const bool last_iv = (m == N_L - 2);
@@ -535,28 +609,42 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
           double t = A * d; W1 += t;
           t *= d; W2 += t;
           t *= d; W3 += t;
-          xprev = x;
           ++c;
           if (c >= n_cells) break;
-          x = wrap_phase(phk + s_cphi[c], ph_first, ph_last);
-          if (!(x >= xm && (x < xn || (last_iv && x <= xn)))) break;
+          x = phk + s_cphi[c] + off;
+          if (!(x >= xm && (x < xn || (last_iv && x <= xn)))) break;   // next interval, or wrap (x > last)
         }
         const unsigned fl = s_flag[m];
         const double* cp = s_coef + (long)m * 4;
+        if (fl == 0u) {
 #pragma unroll
-        for (int g = 0; g < kNEC; ++g) {
-          if (g < ne) {
-            const double2 lo = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4);
-            const double2 hi = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4 + 2);
-            if (!((fl >> g) & 1u)) {
+          for (int g = 0; g < kNEC; ++g) {
+            if (g < ne) {
+              const double2 lo = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4);
+              const double2 hi = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4 + 2);
               acc[g] += lo.x * W0 + lo.y * W1 + hi.x * W2 + hi.y * W3;
-            } else {                              // cubic may dip below zero: cell by cell (pyx:593)
-              for (int cc = c_start; cc < c; ++cc) {
-                const double xc = wrap_phase(phk + s_cphi[cc], ph_first, ph_last);
-                const double d = xc - xm;
-                const double f = lo.x + d * (lo.y + d * (hi.x + d * hi.y));
-                if (f > 0.0) acc[g] += s_carea[cc] * f;
+            }
+          }
+        } else {
+          // some energy's cubic may dip below zero on this interval: the reference adds a cell
+          // only where the spline is positive (pyx:593), so go cell by cell for those energies
+          for (int cc = c_start; cc < c; ++cc) {
+            const double d = (phk + s_cphi[cc] + off) - xm;
+            const double A = s_carea[cc];
+#pragma unroll
+            for (int g = 0; g < kNEC; ++g) {
+              if (g < ne && ((fl >> g) & 1u)) {
+                const double* cg = cp + (long)g * N_L * 4;
+                const double f = cg[0] + d * (cg[1] + d * (cg[2] + d * cg[3]));
+                if (f > 0.0) acc[g] += A * f;
               }
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < kNEC; ++g) {
+            if (g < ne && !((fl >> g) & 1u)) {
+              const double* cg = cp + (long)g * N_L * 4;
+              acc[g] += cg[0] * W0 + cg[1] * W1 + cg[2] * W2 + cg[3] * W3;
             }
           }
         }
@@ -592,34 +680,42 @@ static size_t flux_smem_bytes(const AzinvArgs& a, int atm) {
   return d * sizeof(double) + 2ul * a.n_leaves * sizeof(int);
 }
 
-size_t azinv_workspace_doubles(int Q, int n_rings, int n_img_max, int n_leaves) {
-  return (size_t)Q * n_rings * n_img_max * 4 * n_leaves;
+// Doppler spread of log10 Z over one ring allowed for when sizing buffers:
+// log10((1+b)/(1-b)) at |beta| = 0.23 (700 Hz, 16 km).  Rings beyond it are refused
+// (status 3), never clamped.
+constexpr double kDopplerDex = 0.2;
+
+void azinv_workspace_sizes(const AzinvArgs& a, size_t* leaf_doubles, size_t* hdr_doubles, size_t* ihdr_ints,
+                           size_t* slab_doubles) {
+  const size_t rings = (size_t)a.Q * a.n_rings;
+  *leaf_doubles = rings * a.n_img_max * 4 * a.n_leaves;
+  *hdr_doubles = rings * kDHdr;
+  *ihdr_ints = rings * kIHdr;
+  *slab_doubles = (a.hot_atm_ext == 2) ? rings * (size_t)a.hot.nmu * a.slab_rows_ring : 0;
 }
 
-int azinv_slab_rows_budget(const AtmTable& t, const double* energies, int n_energies) {
-  // energy rows of the table one flux CTA can reach: the span of its kNEC energies plus the
-  // Doppler spread over the ring's leaves (|beta| < 0.45 => < 0.42 dex) plus the 4-node stencil
-  if (t.min_dlogE <= 0.0) return t.nE;
+void azinv_slab_budgets(const AtmTable& t, const double* energies, int n_energies, int* rows_chunk,
+                        int* rows_ring) {
+  if (t.min_dlogE <= 0.0) { *rows_chunk = t.nE; *rows_ring = t.nE; return; }
   double span = 0.0;
   for (int e0 = 0; e0 < n_energies; e0 += kNEC) {
     const int e1 = (e0 + kNEC < n_energies ? e0 + kNEC : n_energies) - 1;
     const double s = log10(energies[e1] / energies[e0]);
     if (s > span) span = s;
   }
-  const int rows = (int)ceil((span + 0.42) / t.min_dlogE) + 8;
-  return rows > t.nE ? t.nE : rows;
+  int rc = (int)ceil((span + kDopplerDex) / t.min_dlogE) + 6;
+  int rr = (int)ceil((log10(energies[n_energies - 1] / energies[0]) + kDopplerDex) / t.min_dlogE) + 6;
+  *rows_chunk = rc > t.nE ? t.nE : rc;
+  *rows_ring = rr > t.nE ? t.nE : rr;
 }
 
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   if (a.n_phases > kFluxThreads) return cudaErrorInvalidValue;
   if (a.n_img_max > kMaxImages || a.n_img_max < 1) return cudaErrorInvalidValue;
-  if (!a.ws_leaf || !a.ws_nimg) return cudaErrorInvalidValue;
+  if (!a.ws_leaf || !a.ws_ihdr || !a.ws_hdr) return cudaErrorInvalidValue;
   const int atm = a.hot_atm_ext;
   if (atm != 1 && atm != 2) return cudaErrorNotSupported;
-  if (atm == 2) {
-    if (a.slab_ne_max <= 0 || a.slab_ne_max > a.hot.nE) a.slab_ne_max = a.hot.nE;
-    if (a.slab_ne_max < 8) a.slab_ne_max = 8;
-  }
+  if (atm == 2 && (!a.ws_slab || a.slab_ne_max < 4 || a.slab_rows_ring < 4)) return cudaErrorInvalidValue;
   const size_t gsm = geom_smem_bytes(a), fsm = flux_smem_bytes(a, atm);
   if (gsm > 227 * 1024 || fsm > 227 * 1024) return cudaErrorInvalidValue;
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
@@ -634,6 +730,7 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
     if ((err = cudaFuncSetAttribute(k_azinv_geometry<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(k_azinv_flux<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)) != cudaSuccess) return err;
     k_azinv_geometry<2><<<ggrid, kGeomThreads, gsm, stream>>>(a);
+    k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a);
     k_azinv_flux<2><<<fgrid, kFluxThreads, fsm, stream>>>(a);
   }
   err = cudaGetLastError();

@@ -36,18 +36,23 @@ struct AzinvArgs {
   int image_order_limit;             // 0 => infer ceil(maxDeflection/pi)
   int n_img_max;
   int phase_interp;                  // tools/core.pyx:21  0 Akima(periodic) 1 Steffen
-  int slab_ne_max;                   // Num4D: energy rows budgeted for the (mu,E) slab
+  int slab_ne_max;                   // Num4D: energy rows a flux CTA may hold in shared memory
+  int slab_rows_ring;                // Num4D: energy rows per ring in the slab workspace
   int scale_by_energy;               // apply flux /= E keV (pyx:610-612)
   double* flux;                      // [Q][N_E][N_P], zero-initialised by the caller
   int* status;                       // [Q]
-  double* ws_leaf;                   // workspace [Q][n_rings][n_img_max][4][N_L] (geometry -> flux)
-  int* ws_nimg;                      // workspace [Q][n_rings]: image orders to integrate per ring
+  // workspaces (sizes from azinv_workspace_sizes)
+  double* ws_leaf;                   // [Q][n_rings][n_img_max][4][N_L]   geometry -> flux
+  double* ws_hdr; int* ws_ihdr;      // per-ring headers
+  double* ws_slab;                   // Num4D: [Q][n_rings][nmu][slab_rows_ring]
   unsigned long long* work;          // nullptr or [4]: H half-leaf visits, V visible leaves,
                                      //   RI (ring,image) pairs reaching the phase stage, K radiating cells over RI
 };
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream);
-size_t azinv_workspace_doubles(int Q, int n_rings, int n_img_max, int n_leaves);
-int azinv_slab_rows_budget(const AtmTable& t, const double* host_energies, int n_energies);
+void azinv_workspace_sizes(const AzinvArgs& a, size_t* leaf_doubles, size_t* hdr_doubles, size_t* ihdr_ints,
+                           size_t* slab_doubles);
+void azinv_slab_budgets(const AtmTable& t, const double* host_energies, int n_energies, int* rows_chunk,
+                        int* rows_ring);
 
 // a9: tools/energy_integrator.pyx:27-114, one spline per (signal q, phase column)
 struct EnergyIntegArgs {
