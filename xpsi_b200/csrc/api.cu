@@ -69,6 +69,27 @@ struct Dev {
   }
 };
 
+// per channel tile, the span of input intervals holding any non-zero response entry
+std::vector<int> response_k_ranges(const double* m, int n_chan, int ld, int in0, int n_in) {
+  const int T = xb::fold_tile_rows();
+  const int nt = (n_chan + T - 1) / T;
+  std::vector<int> r(2 * nt);
+  for (int t = 0; t < nt; ++t) {
+    int lo = n_in, hi = 0;
+    for (int c = t * T; c < n_chan && c < (t + 1) * T; ++c) {
+      const double* row = m + (size_t)c * ld + in0;
+      int a = 0, b = n_in;
+      while (a < n_in && row[a] == 0.0) ++a;
+      while (b > a && row[b - 1] == 0.0) --b;
+      if (a < lo) lo = a;
+      if (b > hi) hi = b;
+    }
+    if (hi < lo) { lo = 0; hi = 0; }
+    r[2 * t] = lo; r[2 * t + 1] = hi;
+  }
+  return r;
+}
+
 }  // namespace
 
 struct xpsi_b200_atmosphere {
@@ -167,6 +188,10 @@ int xpsi_b200_integrate_azimuthal_invariance(
   CK(d_defl.upload(deflection, nr)); CK(d_ca.upload(cos_alpha, nr)); CK(d_lag.upload(lag, nr));
   CK(d_maxd.upload(maxDeflection, n_rings)); CK(d_cg.upload(cos_gammaArray, n_rings));
   CK(d_E.upload(energies, n_energies)); CK(d_L.upload(leaves, n_leaves)); CK(d_P.upload(phases, n_phases));
+  std::vector<double> l10E(n_energies);
+  for (int i = 0; i < n_energies; ++i) l10E[i] = log10(energies[i]);
+  Dev<double> d_l10E;
+  CK(d_l10E.upload(l10E.data(), n_energies));
   CK(d_flux.alloc((size_t)n_energies * n_phases));
   CK(cudaMemsetAsync(d_flux.p, 0, (size_t)n_energies * n_phases * sizeof(double), g_stream));
   CK(d_status.alloc(1));
@@ -181,6 +206,7 @@ int xpsi_b200_integrate_azimuthal_invariance(
   a.radial = d_radial.p; a.r_s_over_r = d_rsr.p; a.srcParams = d_par.p; a.params_per_cell = 1;
   a.radiates = d_rad.p; a.deflection = d_defl.p; a.cos_alpha = d_ca.p; a.lag = d_lag.p;
   a.maxDeflection = d_maxd.p; a.cos_gamma = d_cg.p; a.energies = d_E.p; a.leaves = d_L.p; a.phases = d_P.p;
+  a.log10_energies = d_l10E.p;
   a.hot_atm_ext = hot_atm_ext;
   if (hot_atm_ext == XPSI_B200_ATM_NUM4D) {
     a.hot = hot_atmosphere->view;
@@ -252,9 +278,12 @@ int xpsi_b200_instrument_fold(const double* matrix, int n_rows, int n_cols, int 
     for (int p = 0; p < n_phases; ++p) xt[(size_t)p * n_in + j] = signal[(size_t)j * n_phases + p];
   CK(d_x.upload(xt.data(), xt.size()));
   CK(d_out.alloc((size_t)n_chan * n_phases));
+  std::vector<int> kr = response_k_ranges(matrix + (size_t)o0 * n_cols, n_chan, n_cols, i0, n_in);
+  Dev<int> d_kr;
+  CK(d_kr.upload(kr.data(), kr.size()));
   xb::FoldArgs a;
   a.n_cols = 1; a.n_phases = n_phases; a.n_in = n_in; a.n_chan = n_chan;
-  a.matrix = d_m.p; a.ld_matrix = n_cols; a.in0 = i0; a.x = d_x.p; a.out = d_out.p;
+  a.matrix = d_m.p; a.ld_matrix = n_cols; a.in0 = i0; a.x = d_x.p; a.out = d_out.p; a.k_range = d_kr.p;
   cudaError_t e = xb::launch_fold(a, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_fold");
   g_launches += 1;
@@ -338,7 +367,7 @@ struct xpsi_b200_pipeline {
   // constants
   Dev<double> energies, log10E, leaves, phases, phase_cycles, log10_edges, response, data_phases, counts,
       support, precomp;
-  Dev<int> col_of_q;
+  Dev<int> col_of_q, k_range;
   // per-batch inputs
   Dev<double> omega, inclination, d_sq, shifts, omega_q, incl_q, cellArea, phi, theta, radial, rsr, params,
       defl, calpha, lag, maxd, cgamma;
@@ -404,6 +433,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   a.radiates = nullptr; a.deflection = p->defl.p; a.cos_alpha = p->calpha.p; a.lag = p->lag.p;
   a.maxDeflection = p->maxd.p; a.cos_gamma = p->cgamma.p;
   a.energies = p->energies.p; a.leaves = p->leaves.p; a.phases = p->phases.p;
+  a.log10_energies = p->log10E.p;
   a.hot_atm_ext = c.hot_atm_ext;
   if (c.hot_atm_ext == XPSI_B200_ATM_NUM4D) {
     a.hot = p->atm->view; a.slab_ne_max = p->slab_rows_chunk; a.slab_rows_ring = p->slab_rows_ring;
@@ -435,6 +465,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   xb::FoldArgs f;
   f.n_cols = B * C; f.n_phases = c.n_phases; f.n_in = c.n_in; f.n_chan = c.n_chan;
   f.matrix = p->response.p; f.ld_matrix = c.n_in; f.in0 = 0; f.x = p->xin.p; f.out = p->folded.p;
+  f.k_range = p->k_range.p;
   e = xb::launch_fold(f, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_fold");
   CK(cudaEventRecord(p->ev[3], g_stream));
@@ -494,6 +525,11 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
   ok(p->leaves.upload(c.leaves, c.n_leaves)); ok(p->phases.upload(c.phases, c.n_phases));
   ok(p->phase_cycles.upload(cyc.data(), c.n_phases)); ok(p->log10_edges.upload(l10edges.data(), c.n_in + 1));
   ok(p->response.upload(c.response, (size_t)c.n_chan * c.n_in));
+  {
+    std::vector<int> kr = response_k_ranges(c.response, c.n_chan, c.n_in, 0, c.n_in);
+    ok(p->k_range.upload(kr.data(), kr.size()));
+    ok(cudaStreamSynchronize(g_stream));       // kr is a temporary
+  }
   ok(p->data_phases.upload(c.data_phases, c.n_bins + 1));
   ok(p->counts.upload(c.counts, (size_t)c.n_chan * c.n_bins)); ok(p->support.upload(c.support, (size_t)c.n_chan * 2));
   ok(p->col_of_q.upload(colq.data(), Q)); ok(d_ic.upload(icounts.data(), icounts.size()));
@@ -513,6 +549,7 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
     xb::AzinvArgs w;
     memset(&w, 0, sizeof(w));
     w.Q = (int)Q; w.n_rings = c.max_rings; w.n_leaves = c.n_leaves; w.hot_atm_ext = c.hot_atm_ext;
+    w.n_energies = c.n_energies;
     w.n_img_max = c.image_order_limit > 0 ? c.image_order_limit : xb::kMaxImages;
     if (c.hot_atm_ext == XPSI_B200_ATM_NUM4D) {
       w.hot = p->atm->view;

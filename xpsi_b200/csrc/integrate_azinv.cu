@@ -52,8 +52,9 @@ __device__ __forceinline__ double bb_intensity(double E, double kT) {
 //   ints   [0] image orders to integrate  [1] first radiating cell  [2],[3] (T,g) base nodes
 //          [4],[5] first row / row count of the ring's slab (written by k_azinv_slab)
 //   doubles [0],[1] min/max of Z (log10 Z for Num4D) over lit leaves  [2..5] T weights
-//          [6..9] g weights  [10] log10 T  [11] log10 g
-constexpr int kIHdr = 8, kDHdr = 12;
+//          [6..9] g weights  [10] log10 T  [11] log10 g  [12] kT (keV)  [13] log10 kT
+//          [14] intensity normalisation (hot_BB.pyx:98 / hot_Num4D.pyx:436-460)
+constexpr int kIHdr = 8, kDHdr = 16;
 
 // order-preserving map double <-> unsigned 64 (for shared-memory atomicMin/Max)
 __device__ __forceinline__ unsigned long long order_key(double v) {
@@ -294,6 +295,11 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
       zlo = fmin(zlo, key_order(s_zlo[I])); zhi = fmax(zhi, key_order(s_zhi[I]));
     }
     dh[0] = zlo; dh[1] = zhi; dh[10] = VEC[0];
+    {
+      const double kT = kKBOverKeV * pow(10.0, VEC[0]);
+      dh[12] = kT; dh[13] = log10(kT);
+      dh[14] = (ATM == 2) ? (kErg / kHKeV) * pow(10.0, 3.0 * VEC[0]) : kErg * kPlanckDistConst;
+    }
     if (ATM == 2 && n > 0) {     // (T,g) stencil of the ring, hot_Num4D.pyx:295-409
       View vT{a.hot.logT, 1}, vG{a.hot.logg, 1};
       const int bT = lagrange_base(vT, a.hot.nT, VEC[0]);
@@ -335,18 +341,27 @@ __global__ void __launch_bounds__(kSlabThreads) k_azinv_slab(AzinvArgs a) {
   const double* dh = a.ws_hdr + ring * kDHdr;
   __shared__ int s_elo, s_nrows;
   __shared__ double s_wT[4], s_wG[4];
+  const double zlo = dh[0], zhi = dh[1], log_kT = dh[13];
+  const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
+  View vE{a.hot.logE, 1};
   if (tid == 0) {
-    const double zlo = dh[0], zhi = dh[1];
-    const double log_kT = log10(kKBOverKeV * pow(10.0, dh[10]));
-    View vE{a.hot.logE, 1};
     int elo = 0, ehi = 4;
     if (zlo <= zhi)
-      row_range(vE, a.hot.nE, log10(a.energies[0]) - zhi - log_kT,
-                log10(a.energies[a.n_energies - 1]) - zlo - log_kT, &elo, &ehi);
+      row_range(vE, a.hot.nE, a.log10_energies[0] - zhi - log_kT,
+                a.log10_energies[a.n_energies - 1] - zlo - log_kT, &elo, &ehi);
     if (ehi - elo > a.slab_rows_ring) { atomicExch(a.status + q, kUnsupported); ih[0] = 0; ehi = elo; }
     ih[4] = elo; ih[5] = ehi - elo;
     s_elo = elo; s_nrows = ehi - elo;
     for (int x = 0; x < 4; ++x) { s_wT[x] = dh[2 + x]; s_wG[x] = dh[6 + x]; }
+  }
+  // energy rows each 8-energy chunk of this ring reaches (first table row, count)
+  for (int c = tid; c < n_chunks; c += kSlabThreads) {
+    const int e0 = c * kNEC, e1 = min(e0 + kNEC, a.n_energies) - 1;
+    int lo = 0, hi = 4;
+    if (zlo <= zhi)
+      row_range(vE, a.hot.nE, a.log10_energies[e0] - zhi - log_kT, a.log10_energies[e1] - zlo - log_kT, &lo, &hi);
+    int2 r; r.x = lo; r.y = hi - lo;
+    reinterpret_cast<int2*>(a.ws_chunk)[ring * n_chunks + c] = r;
   }
   __syncthreads();
   const int elo = s_elo, nrows = s_nrows, nmu = a.hot.nmu;
@@ -354,8 +369,9 @@ __global__ void __launch_bounds__(kSlabThreads) k_azinv_slab(AzinvArgs a) {
   const int bT = ih[2], bG = ih[3];
   const long S0 = (long)a.hot.ng * nmu * a.hot.nE, S1 = (long)nmu * a.hot.nE, S2 = a.hot.nE;
   double* out = a.ws_slab + ring * (long)nmu * a.slab_rows_ring;
-  for (int t = tid; t < nmu * nrows; t += kSlabThreads) {
-    const int m = t / nrows, e = t - m * nrows;
+  const int tw = tid & 31, wid = tid >> 5;        // a warp per mu row, lanes along the energy rows
+  for (int m = wid; m < nmu; m += kSlabThreads / 32)
+  for (int e = tw; e < nrows; e += 32) {
     const double* base = a.hot.buf + (long)bT * S0 + (long)bG * S1 + (long)m * S2 + elo + e;
     double acc = 0.0;
 #pragma unroll
@@ -394,6 +410,7 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
   extern __shared__ double smem[];
   __shared__ int s_ncell;
   __shared__ double s_E[kNEC], s_logE[kNEC];
+  const double kT = dh[12], log_kT = dh[13], norm = dh[14];
   double* sp = smem;
   double* s_cphi = sp; sp += a.n_azi;
   double* s_carea = sp; sp += a.n_azi;
@@ -436,26 +453,18 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
     if (tid == 0) s_ncell = base;
   } else if (tid < 32 + kNEC) {
     const int e = tid - 32;
-    const double E = a.energies[e0 + (e < ne ? e : 0)];
-    s_E[e] = E; s_logE[e] = log10(E);
+    s_E[e] = a.energies[e0 + (e < ne ? e : 0)];
+    s_logE[e] = a.log10_energies[e0 + (e < ne ? e : 0)];
   }
-  const double logT = dh[10];
-  const double kT = kKBOverKeV * pow(10.0, logT);
-  const double log_kT = log10(kT);
 
   // ---- Num4D: copy the rows of the ring's slab this chunk reaches ------------------------
   int nrows = 0, elo_tab = 0;
   if (ATM == 2) {
-    const int elo_ring = ih[4], nrows_ring = ih[5];
-    const double zlo = dh[0], zhi = dh[1];
-    // every thread derives the same chunk range from the ring's axis segment (no serial section)
-    View vE{a.hot.logE + elo_ring, 1};
-    int lo_c = 0, hi_c = 4;
-    if (zlo <= zhi)
-      row_range(vE, nrows_ring, log10(a.energies[e0]) - zhi - log_kT,
-                log10(a.energies[e0 + ne - 1]) - zlo - log_kT, &lo_c, &hi_c);
-    nrows = hi_c - lo_c;
-    elo_tab = elo_ring + lo_c;
+    const int elo_ring = ih[4];
+    const int2 cr = reinterpret_cast<const int2*>(a.ws_chunk)[ring * n_chunks + chunk];
+    nrows = cr.y;
+    elo_tab = cr.x;
+    const int lo_c = elo_tab - elo_ring;
     if (nrows > a.slab_ne_max) {       // budget too small for this ring: refuse, never clamp
       if (tid == 0) atomicExch(a.status + q, kUnsupported);
       return;
@@ -463,9 +472,10 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
     for (int m = tid; m < a.hot.nmu; m += kFluxThreads) s_axMu[m] = a.hot.mu[m];
     for (int r = tid; r < nrows; r += kFluxThreads) s_axE[r] = a.hot.logE[elo_tab + r];
     const double* src = a.ws_slab + ring * (long)a.hot.nmu * a.slab_rows_ring + lo_c;
-    for (int t = tid; t < a.hot.nmu * nrows; t += kFluxThreads) {
-      const int m = t / nrows, e = t - m * nrows;
-      s_slab[t] = src[(long)m * a.slab_rows_ring + e];
+    {   // half a warp per mu row (a chunk reaches ~16 rows)
+      const int sub = tid & 15, grp = tid >> 4;
+      for (int m = grp; m < a.hot.nmu; m += kFluxThreads / 16)
+        for (int e = sub; e < nrows; e += 16) s_slab[m * nrows + e] = src[(long)m * a.slab_rows_ring + e];
     }
   }
   __syncthreads();
@@ -483,8 +493,6 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
   // mean spacing of the axis segment: first guess of the energy stencil (then walked)
   const double inv_dE = (ATM == 2 && nrows > 1) ? (double)(nrows - 1) / (s_axE[nrows - 1] - s_axE[0]) : 0.0;
 
-  const double norm = (ATM == 2) ? (kErg / kHKeV) * pow(10.0, 3.0 * logT)
-                                 : kErg * kPlanckDistConst;
   const int interp_kind = a.phase_interp;
   const int k = tid;                         // output phase owned in the accumulation stage
   const double phk = (k < N_P) ? a.phases[k] : 0.0;
@@ -510,14 +518,14 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
         lagrange_weights(s_axMu, b, v, w);
         s_mub[l] = b;
 #pragma unroll
-        for (int x = 0; x < 4; ++x) s_muw[4 * l + x] = w[x];
+        for (int x = 0; x < 4; ++x) s_muw[x * N_L + l] = w[x];
       }
       __syncthreads();
     }
     for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
     // ---- (1) leaf profile (pyx:445-478) -----------------------------------------------------
-    for (int t = tid; t < ne * N_L; t += kFluxThreads) {
-      const int e = t / N_L, l = t - e * N_L;
+    for (int t = tid, e = 0, l = tid; t < ne * N_L; t += kFluxThreads, l += kFluxThreads) {
+      while (l >= N_L) { l -= N_L; ++e; }
       double val = 0.0;
       const double geom = s_geom[l];
       if (geom != 0.0) {
@@ -535,12 +543,11 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
           const double wE0 = d1 * d2 * d3 * iv[0], wE1 = d0 * d2 * d3 * iv[1],
                        wE2 = d0 * d1 * d3 * iv[2], wE3 = d0 * d1 * d2 * iv[3];
           const double* row = s_slab + (long)s_mub[l] * nrows + bE;
-          const double* wM = s_muw + 4 * l;
           double sum = 0.0;
 #pragma unroll
           for (int x = 0; x < 4; ++x) {
             const double* r = row + x * nrows;
-            sum += wM[x] * (wE0 * r[0] + wE1 * r[1] + wE2 * r[2] + wE3 * r[3]);
+            sum += s_muw[x * N_L + l] * (wE0 * r[0] + wE1 * r[1] + wE2 * r[2] + wE3 * r[3]);
           }
           if (sum < 0.0) sum = 0.0;                              // hot_Num4D.pyx:436-437
           val = sum * norm * geom;
@@ -550,8 +557,8 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
     }
     __syncthreads();
     // ---- (2) phase-spline coefficients + positivity flags (pyx:566-569) ----------------------
-    for (int t = tid; t < ne * (N_L - 1); t += kFluxThreads) {
-      const int e = t / (N_L - 1), l = t - e * (N_L - 1);
+    for (int t = tid, e = 0, l = tid; t < ne * (N_L - 1); t += kFluxThreads, l += kFluxThreads) {
+      while (l >= N_L - 1) { l -= N_L - 1; ++e; }
       const double* y = s_y + e * N_L;
       double b, c, d;
       if (interp_kind == kSteffen) {
@@ -566,8 +573,8 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
                              s_aux[l], &b, &c, &d);
       }
       const double y0 = y[l];
-      double* o = s_coef + ((long)e * N_L + l) * 4;
-      o[0] = y0; o[1] = b; o[2] = c; o[3] = d;
+      double2* o = reinterpret_cast<double2*>(s_coef + ((long)e * N_L + l) * 4);
+      o[0] = make_double2(y0, b); o[1] = make_double2(c, d);
       // Bernstein coefficients of the cubic on [0,h] (end values are the nodes themselves):
       // all >= 0  =>  the spline is >= 0 on the interval
       const double h = s_PH[l + 1] - s_PH[l];
@@ -688,9 +695,10 @@ constexpr double kDopplerDex = 0.2;
 void azinv_workspace_sizes(const AzinvArgs& a, size_t* leaf_doubles, size_t* hdr_doubles, size_t* ihdr_ints,
                            size_t* slab_doubles) {
   const size_t rings = (size_t)a.Q * a.n_rings;
+  // ihdr_ints also covers the per-chunk row table: [rings][n_chunks] int2 after the headers
   *leaf_doubles = rings * a.n_img_max * 4 * a.n_leaves;
   *hdr_doubles = rings * kDHdr;
-  *ihdr_ints = rings * kIHdr;
+  *ihdr_ints = rings * kIHdr + rings * 2 * (size_t)((a.n_energies + kNEC - 1) / kNEC);
   *slab_doubles = (a.hot_atm_ext == 2) ? rings * (size_t)a.hot.nmu * a.slab_rows_ring : 0;
 }
 
@@ -712,7 +720,8 @@ void azinv_slab_budgets(const AtmTable& t, const double* energies, int n_energie
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   if (a.n_phases > kFluxThreads) return cudaErrorInvalidValue;
   if (a.n_img_max > kMaxImages || a.n_img_max < 1) return cudaErrorInvalidValue;
-  if (!a.ws_leaf || !a.ws_ihdr || !a.ws_hdr) return cudaErrorInvalidValue;
+  if (!a.ws_leaf || !a.ws_ihdr || !a.ws_hdr || !a.log10_energies) return cudaErrorInvalidValue;
+  a.ws_chunk = a.ws_ihdr + (size_t)a.Q * a.n_rings * kIHdr;      // 8-byte aligned: kIHdr is even
   const int atm = a.hot_atm_ext;
   if (atm != 1 && atm != 2) return cudaErrorNotSupported;
   if (atm == 2 && (!a.ws_slab || a.slab_ne_max < 4 || a.slab_rows_ring < 4)) return cudaErrorInvalidValue;

@@ -31,6 +31,7 @@ struct AzinvArgs {
   const double* deflection; const double* cos_alpha; const double* lag;   // [Q][R][N_R]
   const double* maxDeflection; const double* cos_gamma;            // [Q][R]
   const double* energies; const double* leaves; const double* phases;
+  const double* log10_energies;                                    // [N_E]
   AtmTable hot;
   int hot_atm_ext;                   // 1 blackbody, 2 Num4D (hot_wrapper.pyx:72-252)
   int image_order_limit;             // 0 => infer ceil(maxDeflection/pi)
@@ -43,7 +44,8 @@ struct AzinvArgs {
   int* status;                       // [Q]
   // workspaces (sizes from azinv_workspace_sizes)
   double* ws_leaf;                   // [Q][n_rings][n_img_max][4][N_L]   geometry -> flux
-  double* ws_hdr; int* ws_ihdr;      // per-ring headers
+  double* ws_hdr; int* ws_ihdr;      // per-ring headers (+ per-chunk row table behind ws_ihdr)
+  int* ws_chunk;                     // set by the launcher
   double* ws_slab;                   // Num4D: [Q][n_rings][nmu][slab_rows_ring]
   unsigned long long* work;          // nullptr or [4]: H half-leaf visits, V visible leaves,
                                      //   RI (ring,image) pairs reaching the phase stage, K radiating cells over RI
@@ -80,8 +82,11 @@ struct FoldArgs {
   int ld_matrix, in0;
   const double* x;                   // [n_cols * n_phases][n_in]
   double* out;                       // [n_cols][n_chan][n_phases]
+  const int* k_range;                // nullptr, or per fold_tile_rows()-channel tile: [k_begin, k_end)
+                                     //   of input intervals (relative to in0) with a non-zero entry
 };
 cudaError_t launch_fold(FoldArgs a, cudaStream_t stream);
+int fold_tile_rows();
 
 // a12-a14: expected counts + background-marginalised likelihood
 struct MarginalArgs {

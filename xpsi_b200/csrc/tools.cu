@@ -83,49 +83,74 @@ cudaError_t launch_energy_integrator(EnergyIntegArgs a, cudaStream_t stream) {
 
 // ---------------------------------------------------------------------------
 // Response contraction.  out[col][chan][p] = sum_k R[chan][in0+k] * X[col*P+p][k]
-// A plain fp64 SIMT GEMM: 64x64 output tile per CTA, 16-deep K slabs staged in
-// shared memory (transposed so the inner product reads are conflict-free), each
-// thread a 4x4 register block.  fp64 has no tcgen05 kind; DFMA is the roofline.
+//
+// fp64 has no tcgen05 kind, so this is a SIMT DFMA GEMM shaped for the problem:
+// M = channels (a few hundred), N = (theta, component, phase) columns (huge), K =
+// input intervals.  64(M) x 128(N) output tile per CTA, 16-deep K slabs staged in
+// shared memory k-major (conflict-free, 128-bit reads), each thread a 4x8 register
+// block, next slab prefetched into registers while the current one is multiplied.
+// A response is zero above the redistribution band: k_range gives, per 64-channel
+// tile, the span of input intervals with any non-zero entry, and the K loop only
+// visits that span (adding zeros changes nothing).
 // ---------------------------------------------------------------------------
-constexpr int kBM = 64, kBN = 64, kBK = 16, kFoldThreads = 256;
+constexpr int kBM = 64, kBN = 128, kBK = 16, kFoldThreads = 256;
 
-__global__ void __launch_bounds__(kFoldThreads) k_fold(FoldArgs a) {
-  __shared__ double As[kBK][kBM + 4];
-  __shared__ double Bs[kBK][kBN + 4];
-  const int m0 = blockIdx.y * kBM;       // channel tile
-  const long n0 = (long)blockIdx.x * kBN;  // (col,p) tile
+__global__ void __launch_bounds__(kFoldThreads, 2) k_fold(FoldArgs a) {
+  __shared__ __align__(16) double As[kBK][kBM];
+  __shared__ __align__(16) double Bs[kBK][kBN];
+  const int mt = blockIdx.y;
+  const int m0 = mt * kBM;                       // channel tile
+  const long n0 = (long)blockIdx.x * kBN;        // (col,p) tile
   const long N = (long)a.n_cols * a.n_phases;
   const int K = a.n_in;
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  double acc[4][4];
+  int kb = 0, ke = K;
+  if (a.k_range) { kb = a.k_range[2 * mt]; ke = a.k_range[2 * mt + 1]; }
+  kb = (kb / kBK) * kBK;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;     // tx -> 8 columns (4 pairs), ty -> 4 rows
+  double acc[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  // loader mapping: 64 rows x 16 k = 1024 elements, 4 per thread, k fastest
-  const int lr = threadIdx.x / 4;            // 0..63 row
-  const int lk = (threadIdx.x % 4) * 4;      // 0,4,8,12
-  for (int k0 = 0; k0 < K; k0 += kBK) {
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  // loaders: A 64 rows x 16 k (4 per thread), B 128 rows x 16 k (8 per thread); k fastest in memory
+  const int ar = threadIdx.x / 4, ak = (threadIdx.x % 4) * 4;
+  const int br = threadIdx.x / 2, bk = (threadIdx.x % 2) * 8;
+  const bool a_ok = (m0 + ar) < a.n_chan;
+  const bool b_ok = (n0 + br) < N;
+  const double* ap = a.matrix + (long)(m0 + ar) * a.ld_matrix + a.in0;
+  const double* bp = a.x + (n0 + br) * (long)K;
+  double ra[4], rb[8];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int k = k0 + lk + u;
-      const int m = m0 + lr;
-      const long n = n0 + lr;
-      As[lk + u][lr] = (m < a.n_chan && k < K) ? a.matrix[(long)m * a.ld_matrix + a.in0 + k] : 0.0;
-      Bs[lk + u][lr] = (n < N && k < K) ? a.x[n * K + k] : 0.0;
-    }
+    for (int u = 0; u < 4; ++u) { const int k = k0 + ak + u; ra[u] = (a_ok && k < ke) ? ap[k] : 0.0; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int k = k0 + bk + u; rb[u] = (b_ok && k < ke) ? bp[k] : 0.0; }
+  };
+  if (kb < ke) fetch(kb);
+  for (int k0 = kb; k0 < ke; k0 += kBK) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) As[ak + u][ar] = ra[u];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) Bs[bk + u][br] = rb[u];
     __syncthreads();
+    if (k0 + kBK < ke) fetch(k0 + kBK);          // overlaps the multiply below
 #pragma unroll
     for (int k = 0; k < kBK; ++k) {
-      double av[4], bv[4];
+      const double2 a01 = *reinterpret_cast<const double2*>(&As[k][ty * 4]);
+      const double2 a23 = *reinterpret_cast<const double2*>(&As[k][ty * 4 + 2]);
+      const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+      double bv[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) {
+        // columns owned by a thread are {2 tx, 2 tx + 1} + 32 j: a warp reads 16 consecutive
+        // 16-byte words per j -- no bank conflicts
+        const double2 b2 = *reinterpret_cast<const double2*>(&Bs[k][tx * 2 + 32 * j]);
+        bv[2 * j] = b2.x; bv[2 * j + 1] = b2.y;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+        for (int j = 0; j < 8; ++j) acc[i][j] += av[i] * bv[j];
     }
     __syncthreads();
   }
@@ -134,8 +159,8 @@ __global__ void __launch_bounds__(kFoldThreads) k_fold(FoldArgs a) {
     const int m = m0 + ty * 4 + i;
     if (m >= a.n_chan) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const long n = n0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const long n = n0 + tx * 2 + 32 * (j >> 1) + (j & 1);
       if (n >= N) continue;
       const long col = n / a.n_phases;
       const int p = (int)(n - col * a.n_phases);
@@ -143,6 +168,8 @@ __global__ void __launch_bounds__(kFoldThreads) k_fold(FoldArgs a) {
     }
   }
 }
+
+int fold_tile_rows() { return kBM; }
 
 cudaError_t launch_fold(FoldArgs a, cudaStream_t stream) {
   const long N = (long)a.n_cols * a.n_phases;
