@@ -1,0 +1,117 @@
+"""ctypes front-end of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs -- never by xpsi_b200/.
+Function signatures mirror the reference's Python callables so the parity tests
+read like the reference's own.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+def _load():
+    if not os.path.isfile(_LIB):
+        subprocess.check_call(["make", "-C", _HERE])
+    return C.CDLL(_LIB)
+
+
+lib = _load()
+
+
+def _d(a):
+    return a.ctypes.data_as(dp)
+
+
+def _f8(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+INTERP = {'Akima': 0, 'Steffen': 1, 'Cubic': 2}
+
+
+def integrate(numThreads, R, omega, r_s, inclination, cellArea, radialCoords_of_parallels, r_s_over_r,
+              theta, phi, srcCellParams, CELL_RADIATES, correction_srcCellParams, numRays, deflection,
+              cos_alpha, lag, maxDeflection, cos_gammaArray, energies, leaves, phases, hot_atmosphere,
+              elsewhere_atmosphere, hot_atm_ext, else_atm_ext, beam_opt, image_order_limit=None,
+              R_in=1e6, phase_interpolant='Akima'):
+    """xpsi/cellmesh/integrator_for_azimuthal_invariance.pyx:70-98 (no correction, no disc)."""
+    assert correction_srcCellParams is None and beam_opt == 0 and R_in >= 1e6
+    cellArea, theta, phi = _f8(cellArea), _f8(theta), _f8(phi)
+    par = _f8(srcCellParams)
+    rad = np.ascontiguousarray(CELL_RADIATES, dtype=np.int32)
+    arrs = [_f8(x) for x in (radialCoords_of_parallels, r_s_over_r, deflection, cos_alpha, lag,
+                             maxDeflection, cos_gammaArray, energies, leaves, phases)]
+    radial, rsr, defl, ca, lg, maxd, cg, E, L, P = arrs
+    if hot_atmosphere:
+        tab = [_f8(t) for t in hot_atmosphere]
+    else:
+        tab = [np.zeros(4)] * 5
+    flux = np.zeros((E.size, P.size))
+    rc = lib.oracle_integrate_azinv(
+        C.c_double(omega), C.c_double(inclination), C.c_int(cellArea.shape[0]), C.c_int(cellArea.shape[1]),
+        _d(cellArea), _d(radial), _d(rsr), _d(theta), _d(phi), _d(par), C.c_int(par.shape[2]),
+        rad.ctypes.data_as(ip), C.c_int(int(numRays)), _d(defl), _d(ca), _d(lg), _d(maxd), _d(cg),
+        C.c_int(E.size), _d(E), C.c_int(L.size), _d(L), C.c_int(P.size), _d(P), C.c_int(int(hot_atm_ext)),
+        _d(tab[0]), C.c_int(tab[0].size), _d(tab[1]), C.c_int(tab[1].size), _d(tab[2]), C.c_int(tab[2].size),
+        _d(tab[3]), C.c_int(tab[3].size), _d(tab[4]),
+        C.c_int(int(image_order_limit) if image_order_limit else 0), C.c_int(INTERP[phase_interpolant]), _d(flux))
+    return (1, None) if rc else (0, flux)
+
+
+def energy_integrator(N_Ts, signal, energies, energy_edges, phase_interpolant='Akima'):
+    """xpsi/tools/energy_integrator.pyx:27-114."""
+    signal, energies, energy_edges = _f8(signal), _f8(energies), _f8(energy_edges)
+    out = np.zeros((energy_edges.size - 1, signal.shape[1]))
+    lib.oracle_energy_integrator(_d(signal), C.c_int(signal.shape[0]), C.c_int(signal.shape[1]), _d(energies),
+                                 _d(energy_edges), C.c_int(energy_edges.size - 1),
+                                 C.c_int(INTERP[phase_interpolant]), _d(out))
+    return out
+
+
+def fold(matrix, signal):
+    """numpy.dot(matrix, signal), xpsi/Instrument.py:192-197."""
+    matrix, signal = _f8(matrix), _f8(signal)
+    out = np.zeros((matrix.shape[0], signal.shape[1]))
+    lib.oracle_fold(_d(matrix), C.c_int(matrix.shape[0]), C.c_int(matrix.shape[1]), _d(signal),
+                    C.c_int(signal.shape[1]), _d(out))
+    return out
+
+
+def precomputation(data):
+    data = np.ascontiguousarray(data, dtype=np.int32)
+    out = np.zeros(data.shape[0])
+    lib.oracle_precomputation(data.ctypes.data_as(ip), C.c_int(data.shape[0]), C.c_int(data.shape[1]), _d(out))
+    return out
+
+
+def eval_marginal_likelihood(exposure_time, phases, counts, components, component_phases, phase_shifts,
+                             neg_sum_ln_data_factorial, support, workspace_intervals, epsabs, epsrel,
+                             epsilon, sigmas, llzero, allow_negative=False, slim=20.0, background=None,
+                             phase_interpolant='Akima'):
+    """xpsi/likelihoods/default_background_marginalisation.pyx:450-734.
+    Returns (status, lnL, expected counts, ML background, ML background given support)."""
+    phases, counts, support = _f8(phases), _f8(counts), _f8(support)
+    comps = [_f8(c) for c in components]
+    cph = _f8(component_phases[0])
+    shifts, pre = _f8(phase_shifts), _f8(neg_sum_ln_data_factorial)
+    bg = _f8(background) if background is not None else None
+    arr = (dp * len(comps))(*[_d(c) for c in comps])
+    lnL = C.c_double(0.0)
+    n_chan, n_bins = counts.shape
+    star, mcl, mcls = np.zeros((n_chan, n_bins)), np.zeros(n_chan), np.zeros(n_chan)
+    rc = lib.oracle_eval_marginal_likelihood(
+        C.c_double(exposure_time), _d(phases), C.c_int(n_bins), _d(counts), C.c_int(n_chan), arr,
+        C.c_int(len(comps)), _d(cph), C.c_int(cph.size), _d(shifts), _d(pre), _d(support),
+        C.c_int(int(workspace_intervals)), C.c_double(epsabs), C.c_double(epsrel), C.c_double(epsilon),
+        C.c_double(sigmas), C.c_double(llzero), C.c_int(int(bool(allow_negative))), C.c_double(slim),
+        _d(bg) if bg is not None else None, C.c_int(INTERP[phase_interpolant]), C.byref(lnL), _d(star),
+        _d(mcl), _d(mcls))
+    return rc, lnL.value, star, mcl, mcls
