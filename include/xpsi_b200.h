@@ -83,12 +83,38 @@ int xpsi_b200_integrate_azimuthal_invariance(
     int hot_atm_ext, int else_atm_ext, int beam_opt, int image_order_limit, double R_in,
     int phase_interpolant, double* flux_out);
 
+/* ---- cellmesh.integrator_for_time_invariance.integrate ------------------------------
+ * replaces xpsi/cellmesh/integrator_for_time_invariance.pyx:59-338 (call sites
+ * xpsi/Elsewhere.py:418-438, xpsi/Everywhere.py:581-601).  theta/phi [n][n],
+ * srcCellParams [n][n][n_params], rays [n][numRays]; flux_out [n_energies].            */
+int xpsi_b200_integrate_time_invariance(
+    double R, double omega, double r_s, double inclination, int sqrt_numPix, double cellArea,
+    const double* radialCoords_of_parallels, const double* r_s_over_r, const double* theta,
+    const double* phi, const double* srcCellParams, int n_params, int numRays,
+    const double* deflection, const double* cos_alpha, const double* maxDeflection,
+    const double* cos_gammaArray, int n_energies, const double* energies,
+    const xpsi_b200_atmosphere* atmosphere, int atm_ext, int image_order_limit, double* flux_out);
+
 /* ---- tools.energy_integrator -------------------------------------------------
  * replaces xpsi/tools/energy_integrator.pyx:27-114.  signal [n_energies][n_phases],
  * out [n_in][n_phases] (the reference's transposed return).                    */
 int xpsi_b200_energy_integrator(const double* signal, int n_energies, int n_phases,
                                 const double* log10_energies, const double* log10_edges, int n_in,
                                 int phase_interpolant, double* out);
+
+/* ---- tools.phase_integrator / phase_interpolator / energy_interpolator ----------------
+ * replace xpsi/tools/phase_integrator.pyx:23-121 (out [n_rows][n_bins]),
+ * phase_interpolator.pyx:25-98 (out [n_rows][n_new]) and energy_interpolator.pyx:27-125
+ * (signal [n_energies][n_phases], out [n_new][n_phases]; the *energy* interpolant).     */
+int xpsi_b200_phase_integrator(double exposure_time, const double* phases, int n_bins, const double* signal,
+                               int n_rows, const double* signal_phases, int n_phases, double phase_shift,
+                               int allow_negative, int phase_interpolant, double* out);
+int xpsi_b200_phase_interpolator(const double* new_phases, int n_new, const double* phases, int n_phases,
+                                 const double* signal, int n_rows, double phase_shift, int allow_negative,
+                                 int phase_interpolant, double* out);
+int xpsi_b200_energy_interpolator(const double* signal, int n_energies, int n_phases, const double* log10_energies,
+                                  const double* new_log10_energies, int n_new, int energy_interpolant,
+                                  double* out);
 
 /* ---- Instrument.__call__ -------------------------------------------------------
  * replaces numpy.dot(matrix[o0:o1, i0:i1], signal), xpsi/Instrument.py:192-197.

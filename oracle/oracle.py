@@ -115,3 +115,54 @@ def eval_marginal_likelihood(exposure_time, phases, counts, components, componen
         _d(bg) if bg is not None else None, C.c_int(INTERP[phase_interpolant]), C.byref(lnL), _d(star),
         _d(mcl), _d(mcls))
     return rc, lnL.value, star, mcl, mcls
+
+
+def phase_integrator(exposure_time, phases, signal, signal_phases, phase_shift, allow_negative=0,
+                     phase_interpolant='Akima'):
+    """xpsi/tools/phase_integrator.pyx:23-121."""
+    phases, signal, signal_phases = _f8(phases), _f8(signal), _f8(signal_phases)
+    out = np.zeros((signal.shape[0], phases.size - 1))
+    lib.oracle_phase_integrator(C.c_double(exposure_time), _d(phases), C.c_int(phases.size - 1), _d(signal),
+                                C.c_int(signal.shape[0]), _d(signal_phases), C.c_int(signal_phases.size),
+                                C.c_double(phase_shift), C.c_int(int(bool(allow_negative))),
+                                C.c_int(INTERP[phase_interpolant]), _d(out))
+    return out
+
+
+def phase_interpolator(new_phases, phases, signal, phase_shift, allow_negative=0, phase_interpolant='Akima'):
+    """xpsi/tools/phase_interpolator.pyx:25-98."""
+    new_phases, phases, signal = _f8(new_phases), _f8(phases), _f8(signal)
+    out = np.zeros((signal.shape[0], new_phases.size))
+    lib.oracle_phase_interpolator(_d(new_phases), C.c_int(new_phases.size), _d(phases), C.c_int(phases.size),
+                                  _d(signal), C.c_int(signal.shape[0]), C.c_double(phase_shift),
+                                  C.c_int(int(bool(allow_negative))), C.c_int(INTERP[phase_interpolant]), _d(out))
+    return out
+
+
+def energy_interpolator(N_Ts, signal, energies, new_energies, energy_interpolant='Steffen'):
+    """xpsi/tools/energy_interpolator.pyx:27-125."""
+    signal, energies, new_energies = _f8(signal), _f8(energies), _f8(new_energies)
+    out = np.zeros((new_energies.size, signal.shape[1]))
+    lib.oracle_energy_interpolator(_d(signal), C.c_int(signal.shape[0]), C.c_int(signal.shape[1]), _d(energies),
+                                   _d(new_energies), C.c_int(new_energies.size),
+                                   C.c_int(INTERP[energy_interpolant]), _d(out))
+    return out
+
+
+def integrate_time_invariance(numThreads, R, omega, r_s, inclination, sqrt_numPix, cellArea,
+                              radialCoords_of_parallels, r_s_over_r, theta, phi, srcCellParams, numRays,
+                              deflection, cos_alpha, maxDeflection, cos_gammaArray, energies, atmosphere,
+                              atm_ext, image_order_limit=None, *args):
+    """xpsi/cellmesh/integrator_for_time_invariance.pyx:59-80."""
+    theta, phi, par = _f8(theta), _f8(phi), _f8(srcCellParams)
+    radial, rsr, defl, ca, maxd, cg, E = [_f8(x) for x in (radialCoords_of_parallels, r_s_over_r, deflection,
+                                                            cos_alpha, maxDeflection, cos_gammaArray, energies)]
+    tab = [_f8(t) for t in atmosphere] if atmosphere else [np.zeros(4)] * 5
+    flux = np.zeros(E.size)
+    rc = lib.oracle_integrate_tinv(
+        C.c_double(omega), C.c_double(inclination), C.c_int(int(sqrt_numPix)), C.c_double(cellArea), _d(radial),
+        _d(rsr), _d(theta), _d(phi), _d(par), C.c_int(par.shape[2]), C.c_int(int(numRays)), _d(defl), _d(ca),
+        _d(maxd), _d(cg), C.c_int(E.size), _d(E), C.c_int(int(atm_ext)), _d(tab[0]), C.c_int(tab[0].size),
+        _d(tab[1]), C.c_int(tab[1].size), _d(tab[2]), C.c_int(tab[2].size), _d(tab[3]), C.c_int(tab[3].size),
+        _d(tab[4]), C.c_int(int(image_order_limit) if image_order_limit else 0), _d(flux))
+    return (1, None) if rc else (0, flux)

@@ -478,3 +478,162 @@ int oracle_eval_marginal_likelihood(
   *lnL = LOGLIKE;
   return rc;
 }
+
+/* ------------------------------------------------- tools/phase_integrator.pyx:23-121 */
+int oracle_phase_integrator(double exposure_time, const double *phases, int n_bins, const double *signal,
+                            int n_rows, const double *signal_phases, int N_P, double phase_shift,
+                            int allow_negative, int phase_interp, double *out /*[n_rows][n_bins]*/) {
+  gsl_interp *it = gsl_interp_alloc(phase_interpolant(phase_interp), N_P);
+  gsl_interp_accel *acc = gsl_interp_accel_alloc();
+  memset(out, 0, sizeof(double) * (size_t)n_rows * n_bins);
+  for (int i = 0; i < n_rows; i++) {
+    const double *sp = signal + (size_t)i * N_P;
+    gsl_interp_accel_reset(acc);
+    gsl_interp_init(it, signal_phases, sp, N_P);
+    for (int j = 0; j < n_bins; j++) {
+      double a = phases[j] + phase_shift, b = phases[j + 1] + phase_shift, v;
+      double *o = out + (size_t)i * n_bins + j;
+      if (b - a == 1.0) { a = 0.0; b = 1.0; } else { a -= floor(a); b -= floor(b); }
+      if (a < b) {
+        v = gsl_interp_eval_integ(it, signal_phases, sp, a, b, acc);
+        if (v > 0.0 || allow_negative) *o = v;
+      } else {
+        v = gsl_interp_eval_integ(it, signal_phases, sp, a, 1.0, acc);
+        if (v > 0.0 || allow_negative) *o = v;
+        v = gsl_interp_eval_integ(it, signal_phases, sp, 0.0, b, acc);
+        if (v > 0.0 || allow_negative) *o += v;
+      }
+      *o *= exposure_time;
+    }
+  }
+  gsl_interp_free(it); gsl_interp_accel_free(acc);
+  return ORACLE_OK;
+}
+
+/* ------------------------------------------------- tools/phase_interpolator.pyx:25-98 */
+int oracle_phase_interpolator(const double *new_phases, int n_new, const double *phases, int N_P,
+                              const double *signal, int n_rows, double phase_shift, int allow_negative,
+                              int phase_interp, double *out /*[n_rows][n_new]*/) {
+  gsl_interp *it = gsl_interp_alloc(phase_interpolant(phase_interp), N_P);
+  gsl_interp_accel *acc = gsl_interp_accel_alloc();
+  memset(out, 0, sizeof(double) * (size_t)n_rows * n_new);
+  for (int i = 0; i < n_rows; i++) {
+    const double *sp = signal + (size_t)i * N_P;
+    gsl_interp_accel_reset(acc);
+    gsl_interp_init(it, phases, sp, N_P);
+    for (int j = 0; j < n_new; j++) {
+      double PHASE = new_phases[j] + phase_shift;
+      PHASE -= floor(PHASE);
+      double v = gsl_interp_eval(it, phases, sp, PHASE, acc);
+      if (v > 0.0 || allow_negative) out[(size_t)i * n_new + j] = v;
+    }
+  }
+  gsl_interp_free(it); gsl_interp_accel_free(acc);
+  return ORACLE_OK;
+}
+
+/* ------------------------------------------------- tools/energy_interpolator.pyx:27-125 */
+int oracle_energy_interpolator(const double *signal, int N_E, int N_P, const double *energies,
+                               const double *new_energies, int n_new, int energy_interp,
+                               double *out /*[n_new][N_P]*/) {
+  const gsl_interp_type *T = energy_interp == 0 ? gsl_interp_akima
+                           : (energy_interp == 2 ? gsl_interp_cspline : gsl_interp_steffen);  /* core.pyx:101-116 */
+  gsl_interp *it = gsl_interp_alloc(T, N_E);
+  gsl_interp_accel *acc = gsl_interp_accel_alloc();
+  double *cpy = malloc(sizeof(double) * N_E);
+  const double max_energy = energies[N_E - 1];
+  memset(out, 0, sizeof(double) * (size_t)n_new * N_P);
+  for (int i = 0; i < N_P; i++) {
+    int mode = 1;
+    for (int j = 0; j < N_E; j++) if (signal[(size_t)j * N_P + i] <= 0.0) mode = 0;
+    for (int j = 0; j < N_E; j++) cpy[j] = mode ? log10(signal[(size_t)j * N_P + i]) : signal[(size_t)j * N_P + i];
+    gsl_interp_accel_reset(acc);
+    gsl_interp_init(it, energies, cpy, N_E);
+    for (int j = 0; j < n_new; j++) {
+      if (new_energies[j] > max_energy) continue;
+      double v = gsl_interp_eval(it, energies, cpy, new_energies[j], acc);
+      out[(size_t)j * N_P + i] = mode ? pow(10.0, v) : v;
+    }
+  }
+  gsl_interp_free(it); gsl_interp_accel_free(acc); free(cpy);
+  return ORACLE_OK;
+}
+
+/* -------------------------- elsewhere_wrapper.pyx:23-81 + integrator_for_time_invariance.pyx:59-338 */
+int oracle_integrate_tinv(
+    double omega, double inclination, int n, double cellArea, const double *radial, const double *r_s_over_r,
+    const double *theta, const double *phi, const double *srcCellParams, int n_params, int N_R,
+    const double *deflection, const double *cos_alpha, const double *maxDeflection,
+    const double *cos_gammaArray, int N_E, const double *energies, int atm_ext, const double *logT, int nT,
+    const double *logg, int ng, const double *mu_ax, int nmu, const double *logE, int nE, const double *buf,
+    int image_order_limit, double *flux) {
+  atm_table tab = {{logT, logg, mu_ax, logE}, {nT, ng, nmu, nE}, buf};
+  const double sin_i = sin(inclination), cos_i = cos(inclination);
+  int terminate = 0;
+  double *cos_deflection = malloc(sizeof(double) * N_R), *cos_alpha_alt = malloc(sizeof(double) * N_R);
+  gsl_interp_accel *acc_a = gsl_interp_accel_alloc(), *acc_alt = gsl_interp_accel_alloc();
+  gsl_interp *interp_alpha = gsl_interp_alloc(gsl_interp_steffen, N_R);
+  memset(flux, 0, sizeof(double) * N_E);
+  for (int i = 0; i < n && !terminate; i++) {
+    const double *defl = deflection + (size_t)i * N_R, *calpha = cos_alpha + (size_t)i * N_R;
+    for (int j = 0; j < N_R; j++) { cos_deflection[j] = cos(defl[N_R - j - 1]); cos_alpha_alt[j] = calpha[N_R - j - 1]; }
+    int jh = 0;
+    while (jh < N_R - 1 && defl[jh] <= M_PI / 2.0) jh++;
+    const double *defl_alt_ptr = cos_deflection + (N_R - jh - 1), *alpha_alt_ptr = cos_alpha_alt + (N_R - jh - 1);
+    gsl_interp *interp_alt = gsl_interp_alloc(gsl_interp_steffen, jh + 1);
+    gsl_interp_init(interp_alt, defl_alt_ptr, alpha_alt_ptr, jh + 1);
+    gsl_interp_accel_reset(acc_alt); gsl_interp_accel_reset(acc_a);
+    gsl_interp_init(interp_alpha, defl, calpha, N_R);
+    const double Grav_z = sqrt(1.0 - r_s_over_r[i]);
+    const double cos_gamma = cos_gammaArray[i], sin_gamma = sqrt(1.0 - cos_gamma * cos_gamma);
+    const double cos_theta_i = cos(theta[(size_t)i * n]), sin_theta_i = sin(theta[(size_t)i * n]);
+    const double theta_i_over_pi = theta[(size_t)i * n] / M_PI;
+    const double beta = radial[i] * omega * sin_theta_i / (C_LIGHT * Grav_z);
+    const double Lorentz = sqrt(1.0 - beta * beta);
+    for (int j = 0; j < n && !terminate; j++) {
+      const double ph = phi[(size_t)i * n + j];
+      const double _cos_psi = cos_i * cos_theta_i + sin_i * sin_theta_i * cos(ph);
+      const double _psi = acos(_cos_psi);
+      const int _IO = image_order_limit > 0 ? image_order_limit : (int)ceil(maxDeflection[i] / M_PI);
+      for (int I = 0; I < _IO; I++) {
+        double cos_psi = _cos_psi, psi = eval_image_deflection(I, _psi), sin_psi = sin(psi), _cos_alpha, deriv;
+        if (!are_equal(psi, 0.0) && are_equal(sin_psi, 0.0)) {
+          double _i = cos_i >= 0.0 ? inclination + inclination * 1.0e-6 : inclination - inclination * 1.0e-6;
+          cos_psi = cos(_i) * cos_theta_i + sin(_i) * sin_theta_i * cos(ph);
+          psi = eval_image_deflection(I, acos(cos_psi));
+          sin_psi = sin(psi);
+        }
+        if (psi > maxDeflection[i]) break;
+        if (psi < interp_alpha->xmin || psi > interp_alpha->xmax) { terminate = 1; break; }
+        const int use_alt = (psi <= M_PI / 2.0 && cos_psi >= interp_alt->xmin);
+        if (use_alt) _cos_alpha = gsl_interp_eval(interp_alt, defl_alt_ptr, alpha_alt_ptr, cos_psi, acc_alt);
+        else _cos_alpha = gsl_interp_eval(interp_alpha, defl, calpha, psi, acc_a);
+        const double sin_alpha = sqrt(1.0 - _cos_alpha * _cos_alpha);
+        double mu = _cos_alpha * cos_gamma;
+        if (!are_equal(psi, 0.0)) {
+          double cos_delta = (cos_i - cos_theta_i * cos_psi) / (sin_theta_i * sin_psi);
+          if (theta_i_over_pi < 0.5) mu = mu + sin_alpha * sin_gamma * cos_delta;
+          else mu = mu - sin_alpha * sin_gamma * cos_delta;
+        }
+        if (mu > 0.0) {
+          double eta;
+          if (!are_equal(sin_psi, 0.0)) eta = Lorentz / (1.0 + beta * (sin_alpha * sin_i * sin(ph) / sin_psi));
+          else eta = Lorentz;
+          if (use_alt) deriv = gsl_interp_eval_deriv(interp_alt, defl_alt_ptr, alpha_alt_ptr, cos_psi, acc_alt);
+          else {
+            deriv = gsl_interp_eval_deriv(interp_alpha, defl, calpha, psi, acc_a);
+            deriv = exp(log(fabs(deriv)) - log(fabs(sin_psi)));
+          }
+          const double _Z = eta * Grav_z, _ABB = mu * eta, _GEOM = mu * fabs(deriv) * Grav_z * eta * eta * eta;
+          const double *VEC = srcCellParams + ((size_t)i * n + j) * n_params;
+          for (int e = 0; e < N_E; e++) flux[e] += eval_hot(atm_ext, &tab, energies[e] / _Z, _ABB, VEC) * _GEOM;
+        }
+      }
+    }
+    gsl_interp_free(interp_alt);
+  }
+  for (int e = 0; e < N_E; e++) flux[e] *= cellArea * eval_hot_norm(atm_ext) / (energies[e] * KEV);
+  gsl_interp_free(interp_alpha); gsl_interp_accel_free(acc_a); gsl_interp_accel_free(acc_alt);
+  free(cos_deflection); free(cos_alpha_alt);
+  return terminate ? ORACLE_ERROR : ORACLE_OK;
+}

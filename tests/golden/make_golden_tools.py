@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Golden vectors for the stand-alone signal tools, recorded from the
+reference build in oracle/_ref: tools.phase_integrator, phase_interpolator, energy_interpolator.
+Inputs are the C1 fixture's folded signal / flux, so the shapes are the reference's own."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_env  # noqa: E402
+
+xpsi = ref_env.import_reference()
+from xpsi.tools import energy_interpolator, phase_integrator, phase_interpolator  # noqa: E402
+
+c1 = np.load(os.path.join(HERE, "c1_st_bb.npz"))
+pulse = np.ascontiguousarray(c1["marg_components_0"][::8])            # [37, 64] count-rate rows
+sig_phases = c1["marg_component_phases_0"]
+edges = c1["marg_phases"]
+flux = np.ascontiguousarray(c1["int0_flux"][:, ::4])                  # [128, 16]
+log10E = np.log10(c1["int0_energies"])
+new_E = np.linspace(log10E[0], log10E[-1] + 0.05, 57)                   # a few points beyond the last energy
+out = {"pulse": pulse, "sig_phases": sig_phases, "edges": edges, "flux": flux, "log10E": log10E, "new_E": new_E}
+for shift in (0.0, 0.37, -0.2):
+    tag = ("%+.2f" % shift).replace(".", "p").replace("+", "P").replace("-", "M")
+    out["pint_" + tag] = phase_integrator(1000.0, edges, pulse, sig_phases, shift)
+    out["pitp_" + tag] = phase_interpolator(np.linspace(0.0, 1.0, 41), sig_phases, pulse, shift)
+out["shifts"] = np.array([0.0, 0.37, -0.2])
+out["new_phases"] = np.linspace(0.0, 1.0, 41)
+out["eitp"] = energy_interpolator(1, flux, log10E, new_E)
+flux_neg = flux.copy(); flux_neg[5, 3] = 0.0                           # forces the linear (non-log) mode in one column
+out["flux_neg"] = flux_neg
+out["eitp_neg"] = energy_interpolator(1, flux_neg, log10E, new_E)
+np.savez_compressed(os.path.join(HERE, "tools.npz"), **out)
+print("tools.npz", os.path.getsize(os.path.join(HERE, "tools.npz")) // 1024, "KiB")

@@ -200,3 +200,88 @@ def test_m2_batched_pipeline(m2):
     # identical inputs in different batch slots give identical answers up to the
     # order of the fp64 ring reduction
     assert abs(lnL[0] - lnL[3]) < 1e-7 and abs(lnL[1] - lnL[2]) < 1e-7
+
+
+def test_signal_tools_against_reference_golden():
+    """tools.phase_integrator / phase_interpolator / energy_interpolator (row a12)."""
+    import os
+    from conftest import GOLDEN
+    from xpsi_b200.tools import energy_interpolator, phase_integrator, phase_interpolator
+    d = np.load(os.path.join(GOLDEN, "tools.npz"))
+    tag = lambda s: ("%+.2f" % s).replace(".", "p").replace("+", "P").replace("-", "M")
+    for shift in d["shifts"]:
+        out = phase_integrator(1000.0, d["edges"], d["pulse"], d["sig_phases"], float(shift))
+        assert out.shape == d["pint_" + tag(shift)].shape
+        assert rel_err(out, d["pint_" + tag(shift)]) < PULSE_RTOL
+        out = phase_interpolator(d["new_phases"], d["sig_phases"], d["pulse"], float(shift))
+        assert rel_err(out, d["pitp_" + tag(shift)]) < PULSE_RTOL
+    out = energy_interpolator(1, d["flux"], d["log10E"], d["new_E"])
+    assert out.shape == d["eitp"].shape
+    print("energy_interpolator rel err", rel_err(out, d["eitp"]))
+    assert rel_err(out, d["eitp"]) < PULSE_RTOL
+    assert rel_err(energy_interpolator(1, d["flux_neg"], d["log10E"], d["new_E"]), d["eitp_neg"]) < PULSE_RTOL
+
+
+def test_signal_tools_against_oracle_on_seeded_inputs():
+    """Same three tools vs the CPU oracle on seeded ragged inputs (odd sizes, both interpolants)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import oracle as orc
+    from xpsi_b200 import tools
+    rng = np.random.default_rng(7)
+    try:
+        for kind in ("Akima", "Steffen"):
+            tools.set_phase_interpolant(kind)
+            for n_nodes, n_rows, n_bins in ((5, 1, 1), (33, 7, 13), (101, 3, 32)):
+                ph = np.linspace(0.0, 1.0, n_nodes)
+                sig = np.abs(np.sin(2 * np.pi * ph)[None, :] * rng.uniform(0.5, 2.0, (n_rows, 1)) + rng.uniform(0, .3, (n_rows, n_nodes)))
+                sig[:, -1] = sig[:, 0]
+                edges = np.linspace(0.0, 1.0, n_bins + 1)
+                shift = float(rng.uniform(-0.5, 0.5))
+                a = tools.phase_integrator(10.0, edges, sig, ph, shift)
+                b = orc.phase_integrator(10.0, edges, sig, ph, shift, phase_interpolant=kind)
+                assert rel_err(a, b) < 1e-12
+                newp = np.sort(rng.uniform(0, 1, 17))
+                a = tools.phase_interpolator(newp, ph, sig, shift, allow_negative=1)
+                b = orc.phase_interpolator(newp, ph, sig, shift, allow_negative=1, phase_interpolant=kind)
+                assert rel_err(a, b) < 1e-12
+    finally:
+        tools.set_phase_interpolant("Akima")
+
+
+def _tinv_args(d, prefix, atmosphere):
+    g = lambda k: d[prefix + k]
+    return (1, float(g("R")), float(g("omega")), float(g("r_s")), float(g("inclination")), int(g("sqrt_numPix")),
+            float(g("cellArea")), g("radialCoords_of_parallels"), g("r_s_over_r"), g("theta"), g("phi"),
+            g("srcCellParams"), int(g("numRays")), g("deflection"), g("cos_alpha"), g("maxDeflection"),
+            g("cos_gammaArray"), g("energies"), atmosphere, int(g("atm_ext")), int(g("image_order_limit")))
+
+
+def test_time_invariant_integrator_everywhere_and_elsewhere():
+    """integrator_for_time_invariance (row a3): Everywhere BB / Num4D and Elsewhere Num4D."""
+    import os
+    from conftest import GOLDEN
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.cellmesh.integrator_for_time_invariance import integrate
+    table = syn.nsx_like_table()
+    ev = np.load(os.path.join(GOLDEN, "m4_everywhere.npz"))
+    el = np.load(os.path.join(GOLDEN, "m4_elsewhere.npz"))
+    for d, prefix, atm in ((ev, "bb_", ()), (ev, "num4d_", table), (el, "else_", table)):
+        status, flux = integrate(*_tinv_args(d, prefix, atm))
+        assert status == 0
+        err = float(np.max(np.abs(flux - d[prefix + "flux"]) / np.max(np.abs(d[prefix + "flux"]))))
+        el_err = float(np.max(np.abs(flux / d[prefix + "flux"] - 1.0)))
+        print("time-invariant", prefix, "rel err", err, "elementwise", el_err)
+        assert err < PULSE_RTOL
+    # a ring whose cells do NOT share (T, g) takes the per-cell 4-D path
+    d = ev
+    par = d["num4d_srcCellParams"].copy()
+    par[:, ::2, 0] -= 0.05
+    args = list(_tinv_args(d, "num4d_", table)); args[11] = par
+    status, flux = integrate(*args)
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "oracle"))
+    import oracle as orc
+    s2, ref = orc.integrate_time_invariance(*args)
+    assert status == 0 and s2 == 0
+    assert float(np.max(np.abs(flux - ref) / np.max(np.abs(ref)))) < PULSE_RTOL

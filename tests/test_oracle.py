@@ -116,3 +116,39 @@ def test_gslshim_against_scipy():
     cp = mk("gsl_interp_cspline_periodic", y2)
     ref = CubicSpline(x, y2, bc_type="periodic")
     assert max(abs(L.gsl_interp_eval(cp, xp, y2p, v, None) - ref(v)) for v in q) < 1e-12
+
+
+def _tag(shift):
+    return ("%+.2f" % shift).replace(".", "p").replace("+", "P").replace("-", "M")
+
+
+def test_oracle_signal_tools():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "tools.npz"))
+    for shift in d["shifts"]:
+        out = orc.phase_integrator(1000.0, d["edges"], d["pulse"], d["sig_phases"], float(shift))
+        assert rel_err(out, d["pint_" + _tag(shift)]) < 1e-13
+        out = orc.phase_interpolator(d["new_phases"], d["sig_phases"], d["pulse"], float(shift))
+        assert rel_err(out, d["pitp_" + _tag(shift)]) < 1e-13
+    assert rel_err(orc.energy_interpolator(1, d["flux"], d["log10E"], d["new_E"]), d["eitp"]) < 1e-12
+    assert rel_err(orc.energy_interpolator(1, d["flux_neg"], d["log10E"], d["new_E"]), d["eitp_neg"]) < 1e-12
+
+
+def _tinv_args(d, prefix, atmosphere):
+    g = lambda k: d[prefix + k]
+    return (1, float(g("R")), float(g("omega")), float(g("r_s")), float(g("inclination")), int(g("sqrt_numPix")),
+            float(g("cellArea")), g("radialCoords_of_parallels"), g("r_s_over_r"), g("theta"), g("phi"),
+            g("srcCellParams"), int(g("numRays")), g("deflection"), g("cos_alpha"), g("maxDeflection"),
+            g("cos_gammaArray"), g("energies"), atmosphere, int(g("atm_ext")), int(g("image_order_limit")))
+
+
+def test_oracle_time_invariant_integrator():
+    from xpsi_b200 import synthetic as syn
+    table = syn.nsx_like_table()
+    ev = np.load(os.path.join(ROOT, "tests", "golden", "m4_everywhere.npz"))
+    s, f = orc.integrate_time_invariance(*_tinv_args(ev, "bb_", ()))
+    assert s == 0 and rel_err(f, ev["bb_flux"]) < 1e-12
+    s, f = orc.integrate_time_invariance(*_tinv_args(ev, "num4d_", table))
+    assert s == 0 and rel_err(f, ev["num4d_flux"]) < 1e-8
+    el = np.load(os.path.join(ROOT, "tests", "golden", "m4_elsewhere.npz"))
+    s, f = orc.integrate_time_invariance(*_tinv_args(el, "else_", table))
+    assert s == 0 and rel_err(f, el["else_flux"]) < 1e-8

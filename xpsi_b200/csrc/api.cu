@@ -236,6 +236,51 @@ int xpsi_b200_integrate_azimuthal_invariance(
   return 0;
 }
 
+int xpsi_b200_integrate_time_invariance(
+    double R, double omega, double r_s, double inclination, int sqrt_numPix, double cellArea,
+    const double* radial, const double* r_s_over_r, const double* theta, const double* phi,
+    const double* srcCellParams, int n_params, int numRays, const double* deflection,
+    const double* cos_alpha, const double* maxDeflection, const double* cos_gammaArray, int n_energies,
+    const double* energies, const xpsi_b200_atmosphere* atmosphere, int atm_ext, int image_order_limit,
+    double* flux_out) {
+  (void)R; (void)r_s;
+  int rc = ensure_stream();
+  if (rc) return rc;
+  if (atm_ext != XPSI_B200_ATM_BB && atm_ext != XPSI_B200_ATM_NUM4D)
+    return fail(XPSI_B200_EUNSUPPORTED, "atm_ext must be 1 (BB) or 2 (Num4D)");
+  if (atm_ext == XPSI_B200_ATM_NUM4D && !atmosphere) return fail(XPSI_B200_EINVAL, "Num4D needs a preloaded atmosphere");
+  if (sqrt_numPix < 1 || numRays < 3 || n_energies < 1 || n_energies > 256 || n_params < 1)
+    return fail(XPSI_B200_EINVAL, "bad dimensions (at most 256 energies)");
+  const size_t n = sqrt_numPix, nc = n * n, nr = n * numRays;
+  Dev<double> d_scal, d_radial, d_rsr, d_theta, d_phi, d_par, d_defl, d_ca, d_maxd, d_cg, d_E, d_flux;
+  Dev<int> d_status;
+  const double scal[3] = {omega, inclination, cellArea};
+  CK(d_scal.upload(scal, 3));
+  CK(d_radial.upload(radial, n)); CK(d_rsr.upload(r_s_over_r, n)); CK(d_theta.upload(theta, nc));
+  CK(d_phi.upload(phi, nc)); CK(d_par.upload(srcCellParams, nc * n_params));
+  CK(d_defl.upload(deflection, nr)); CK(d_ca.upload(cos_alpha, nr));
+  CK(d_maxd.upload(maxDeflection, n)); CK(d_cg.upload(cos_gammaArray, n)); CK(d_E.upload(energies, n_energies));
+  CK(d_flux.alloc(n_energies)); CK(cudaMemsetAsync(d_flux.p, 0, n_energies * sizeof(double), g_stream));
+  CK(d_status.alloc(1)); CK(cudaMemsetAsync(d_status.p, 0, sizeof(int), g_stream));
+  xb::TinvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Q = 1; a.sqrt_numPix = sqrt_numPix; a.n_rays = numRays; a.n_energies = n_energies; a.n_params = n_params;
+  a.omega = d_scal.p; a.inclination = d_scal.p + 1; a.cellArea = d_scal.p + 2;
+  a.radial = d_radial.p; a.r_s_over_r = d_rsr.p; a.theta = d_theta.p; a.phi = d_phi.p; a.srcParams = d_par.p;
+  a.deflection = d_defl.p; a.cos_alpha = d_ca.p; a.maxDeflection = d_maxd.p; a.cos_gamma = d_cg.p;
+  a.energies = d_E.p; a.atm_ext = atm_ext; a.image_order_limit = image_order_limit > 0 ? image_order_limit : 0;
+  if (atm_ext == XPSI_B200_ATM_NUM4D) { a.atm = atmosphere->view; a.slab_rows = xb::tinv_slab_rows(a.atm, energies, n_energies); }
+  a.flux = d_flux.p; a.status = d_status.p;
+  cudaError_t e = xb::launch_integrate_tinv(a, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_integrate_tinv");
+  g_launches += 2;
+  int status = 0;
+  CK(d_flux.download(flux_out, n_energies)); CK(d_status.download(&status, 1));
+  CK(cudaStreamSynchronize(g_stream));
+  if (status != 0) return fail(status, status == 1 ? "numerical error in time-invariant integration" : "unsupported configuration");
+  return 0;
+}
+
 int xpsi_b200_energy_integrator(const double* signal, int n_energies, int n_phases,
                                 const double* log10_energies, const double* log10_edges, int n_in,
                                 int phase_interpolant, double* out) {
@@ -290,6 +335,53 @@ int xpsi_b200_instrument_fold(const double* matrix, int n_rows, int n_cols, int 
   CK(d_out.download(out, (size_t)n_chan * n_phases));
   CK(cudaStreamSynchronize(g_stream));
   return 0;
+}
+
+static int row_spline_call(const double* x, int n_nodes, const double* y, int n_rows, long yrs, long yns,
+                           size_t y_count, const double* q, int n_q, int n_out, int op, double shift,
+                           double scale, int allow_negative, int interp, int periodic, double* out,
+                           long ors, long ocs) {
+  int rc = ensure_stream();
+  if (rc) return rc;
+  if (interp != 0 && interp != 1) return fail(XPSI_B200_EUNSUPPORTED, "interpolant must be Akima (0) or Steffen (1)");
+  if (n_nodes < (interp == 0 ? 5 : 3) || n_rows < 1 || n_out < 1) return fail(XPSI_B200_EINVAL, "bad dimensions");
+  Dev<double> d_x, d_y, d_q, d_o;
+  CK(d_x.upload(x, n_nodes)); CK(d_y.upload(y, y_count)); CK(d_q.upload(q, n_q));
+  CK(d_o.alloc((size_t)n_rows * n_out));
+  xb::RowSplineArgs a;
+  a.n_rows = n_rows; a.n_nodes = n_nodes; a.n_out = n_out; a.x = d_x.p; a.y = d_y.p;
+  a.y_row_stride = yrs; a.y_node_stride = yns; a.q = d_q.p; a.op = op; a.shift = shift; a.scale = scale;
+  a.allow_negative = allow_negative; a.interp = interp; a.periodic = periodic; a.out = d_o.p;
+  a.out_row_stride = ors; a.out_col_stride = ocs;
+  cudaError_t e = xb::launch_row_spline(a, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_row_spline");
+  g_launches += 1;
+  CK(d_o.download(out, (size_t)n_rows * n_out));
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int xpsi_b200_phase_integrator(double exposure_time, const double* phases, int n_bins, const double* signal,
+                               int n_rows, const double* signal_phases, int n_phases, double phase_shift,
+                               int allow_negative, int phase_interpolant, double* out) {
+  return row_spline_call(signal_phases, n_phases, signal, n_rows, n_phases, 1, (size_t)n_rows * n_phases, phases,
+                         n_bins + 1, n_bins, 0, phase_shift, exposure_time, allow_negative, phase_interpolant, 1,
+                         out, n_bins, 1);
+}
+
+int xpsi_b200_phase_interpolator(const double* new_phases, int n_new, const double* phases, int n_phases,
+                                 const double* signal, int n_rows, double phase_shift, int allow_negative,
+                                 int phase_interpolant, double* out) {
+  return row_spline_call(phases, n_phases, signal, n_rows, n_phases, 1, (size_t)n_rows * n_phases, new_phases,
+                         n_new, n_new, 1, phase_shift, 1.0, allow_negative, phase_interpolant, 1, out, n_new, 1);
+}
+
+int xpsi_b200_energy_interpolator(const double* signal, int n_energies, int n_phases, const double* log10_energies,
+                                  const double* new_log10_energies, int n_new, int energy_interpolant,
+                                  double* out) {
+  // one spline per phase column; result laid out [n_new][n_phases] like the reference's transposed return
+  return row_spline_call(log10_energies, n_energies, signal, n_phases, 1, n_phases, (size_t)n_energies * n_phases,
+                         new_log10_energies, n_new, n_new, 2, 0.0, 1.0, 1, energy_interpolant, 0, out, 1, n_phases);
 }
 
 int xpsi_b200_precomputation(const int* counts, int n_chan, int n_bins, double* out) {

@@ -56,6 +56,25 @@ void azinv_workspace_sizes(const AzinvArgs& a, size_t* leaf_doubles, size_t* hdr
 void azinv_slab_budgets(const AtmTable& t, const double* host_energies, int n_energies, int* rows_chunk,
                         int* rows_ring);
 
+// a3: integrator_for_time_invariance.integrate, batched over Q instances (square meshes n x n)
+struct TinvArgs {
+  int Q, sqrt_numPix, n_rays, n_energies, n_params;
+  const double* omega; const double* inclination; const double* cellArea;       // [Q]
+  const double* radial; const double* r_s_over_r;                               // [Q][n]
+  const double* theta; const double* phi;                                       // [Q][n][n]
+  const double* srcParams;                                                      // [Q][n][n][n_params]
+  const double* deflection; const double* cos_alpha;                            // [Q][n][N_R]
+  const double* maxDeflection; const double* cos_gamma;                         // [Q][n]
+  const double* energies;
+  AtmTable atm; int atm_ext;         // elsewhere_wrapper.pyx:23-81: 1 blackbody, 2 Num4D
+  int image_order_limit;
+  int slab_rows;                     // Num4D: energy rows budgeted for the per-ring slab
+  double* flux;                      // [Q][N_E], zero-initialised by the caller
+  int* status;                       // [Q]
+};
+cudaError_t launch_integrate_tinv(TinvArgs a, cudaStream_t stream);
+int tinv_slab_rows(const AtmTable& t, const double* host_energies, int n_energies);
+
 // a9: tools/energy_integrator.pyx:27-114, one spline per (signal q, phase column)
 struct EnergyIntegArgs {
   int Q, n_energies, n_phases, n_in;
@@ -110,6 +129,19 @@ struct MarginalArgs {
   int* status;                       // [B]
 };
 cudaError_t launch_marginal(MarginalArgs a, cudaStream_t stream);
+
+// a12: row-wise spline tools (phase_integrator / phase_interpolator / energy_interpolator)
+struct RowSplineArgs {
+  int n_rows, n_nodes, n_out;
+  const double* x;                   // [n_nodes] node abscissae
+  const double* y; long y_row_stride, y_node_stride;
+  const double* q;                   // op 0: [n_out+1] bin edges; op 1,2: [n_out] points
+  int op;                            // 0 integrate phase bins, 1 interpolate in phase, 2 interpolate in energy
+  double shift, scale;
+  int allow_negative, interp, periodic;
+  double* out; long out_row_stride, out_col_stride;
+};
+cudaError_t launch_row_spline(RowSplineArgs a, cudaStream_t stream);
 
 // peak fp64 FMA rate of the device, measured with a register-resident DFMA chain
 cudaError_t measure_fp64_peak(double* tflops, cudaStream_t stream);

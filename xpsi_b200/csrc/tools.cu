@@ -196,6 +196,97 @@ cudaError_t launch_precomputation(const int* counts, int n_chan, int n_bins, dou
 }
 
 // ---------------------------------------------------------------------------
+// Row-wise spline tools: tools/phase_integrator.pyx:23-121, phase_interpolator.pyx:25-98,
+// energy_interpolator.pyx:27-125.  One CTA per signal row; coefficients in shared memory.
+// ---------------------------------------------------------------------------
+constexpr int kRowThreads = 128;
+
+__global__ void __launch_bounds__(kRowThreads) k_row_spline(RowSplineArgs a) {
+  const int row = blockIdx.x, n = a.n_nodes;
+  extern __shared__ double smem[];
+  double* s_x = smem;
+  double* s_y = s_x + n;
+  double* s_c = s_y + n;
+  const double* yrow = a.y + (long)row * a.y_row_stride;
+  int positive = 1;
+  for (int i = threadIdx.x; i < n; i += kRowThreads) {
+    s_x[i] = a.x[i];
+    const double v = yrow[(long)i * a.y_node_stride];
+    s_y[i] = v;
+    if (v <= 0.0) positive = 0;
+  }
+  // energy_interpolator works in log10 space when the whole column is positive (pyx:86-96)
+  const int log_mode = (a.op == 2) ? __syncthreads_and(positive) : (__syncthreads(), 0);
+  if (log_mode) {
+    for (int i = threadIdx.x; i < n; i += kRowThreads) s_y[i] = log10(s_y[i]);
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n - 1; i += kRowThreads) {
+    double b, c, d;
+    interp_coeffs(a.interp, a.periodic != 0, s_x, s_y, n, i, &b, &c, &d);
+    s_c[4 * i] = s_y[i]; s_c[4 * i + 1] = b; s_c[4 * i + 2] = c; s_c[4 * i + 3] = d;
+  }
+  __syncthreads();
+  auto integ = [&](double lo, double hi) -> double {
+    if (!(hi > lo)) return 0.0;
+    const int ia = interval_search(s_x, n, lo), ib = interval_search(s_x, n, hi);
+    double val = 0.0;
+    for (int i = ia; i <= ib; ++i) {
+      const double x0 = s_x[i];
+      const double r1 = (i == ia) ? lo - x0 : 0.0;
+      const double r2 = (i == ib) ? hi - x0 : s_x[i + 1] - x0;
+      val += cubic_piece_integral(s_c[4 * i], s_c[4 * i + 1], s_c[4 * i + 2], s_c[4 * i + 3], r1, r2);
+    }
+    return val;
+  };
+  auto eval = [&](double q) -> double {
+    const int i = interval_search(s_x, n, q);
+    const double t = q - s_x[i];
+    return s_c[4 * i] + t * (s_c[4 * i + 1] + t * (s_c[4 * i + 2] + t * s_c[4 * i + 3]));
+  };
+  for (int j = threadIdx.x; j < a.n_out; j += kRowThreads) {
+    double out = 0.0;
+    if (a.op == 0) {                                  // phase_integrator.pyx:86-115
+      double pa = a.q[j] + a.shift, pb = a.q[j + 1] + a.shift;
+      if (pb - pa == 1.0) { pa = 0.0; pb = 1.0; }
+      else { pa -= floor(pa); pb -= floor(pb); }
+      if (pa < pb) {
+        const double v = integ(pa, pb);
+        if (v > 0.0 || a.allow_negative) out = v;
+      } else {
+        double v = integ(pa, 1.0);
+        if (v > 0.0 || a.allow_negative) out = v;
+        v = integ(0.0, pb);
+        if (v > 0.0 || a.allow_negative) out += v;
+      }
+      out *= a.scale;
+    } else if (a.op == 1) {                           // phase_interpolator.pyx:85-93
+      double ph = a.q[j] + a.shift;
+      ph -= floor(ph);
+      const double v = eval(ph);
+      if (v > 0.0 || a.allow_negative) out = v;
+    } else {                                          // energy_interpolator.pyx:101-114
+      const double q = a.q[j];
+      if (q > s_x[n - 1]) out = 0.0;
+      else if (q < s_x[0]) out = nan("");
+      else { out = eval(q); if (log_mode) out = pow(10.0, out); }
+    }
+    a.out[(long)row * a.out_row_stride + (long)j * a.out_col_stride] = out;
+  }
+}
+
+cudaError_t launch_row_spline(RowSplineArgs a, cudaStream_t stream) {
+  if (a.n_nodes < 3) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)a.n_nodes * 6 * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_row_spline, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k_row_spline<<<a.n_rows, kRowThreads, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // fp64 roofline denominator: 8 independent DFMA chains per thread, all in
 // registers, 148 x 8 CTAs of 256 threads.
 // ---------------------------------------------------------------------------

@@ -63,3 +63,46 @@ def energy_integrator(N_Ts, signal, energies, energy_edges):
         _lib.dptr(signal), signal.shape[0], signal.shape[1], _lib.dptr(energies),
         _lib.dptr(energy_edges), n_in, _phase_interpolant, _lib.dptr(out)))
     return out
+
+
+def energy_interpolator(N_Ts, signal, energies, new_energies):
+    """Interpolate a signal in energy (xpsi/tools/energy_interpolator.pyx:27-125): spline in log10 E
+    with the global *energy* interpolant, in log10 of the signal when a column is strictly positive,
+    zero above the last energy.  Returns ``[len(new_energies), N_P]``."""
+    signal = _lib.as_f8(signal, 2)
+    energies = _lib.as_f8(energies, 1)
+    new_energies = _lib.as_f8(new_energies, 1)
+    if _energy_interpolant == 2:
+        raise NotImplementedError("xpsi_b200: the 'Cubic' energy interpolant is not covered")
+    out = np.empty((new_energies.shape[0], signal.shape[1]), dtype=np.float64)
+    _lib.check(_lib.lib.xpsi_b200_energy_interpolator(
+        _lib.dptr(signal), signal.shape[0], signal.shape[1], _lib.dptr(energies), _lib.dptr(new_energies),
+        new_energies.shape[0], _energy_interpolant, _lib.dptr(out)))
+    return out
+
+
+def phase_integrator(exposure_time, phases, signal, signal_phases, phase_shift, allow_negative=0):
+    """Integrate a phase-shifted signal over phase intervals and scale by the exposure time
+    (xpsi/tools/phase_integrator.pyx:23-121).  Returns ``[rows, len(phases)-1]``."""
+    phases = _lib.as_f8(phases, 1)
+    signal = _lib.as_f8(signal, 2)
+    signal_phases = _lib.as_f8(signal_phases, 1)
+    out = np.empty((signal.shape[0], phases.shape[0] - 1), dtype=np.float64)
+    _lib.check(_lib.lib.xpsi_b200_phase_integrator(
+        float(exposure_time), _lib.dptr(phases), phases.shape[0] - 1, _lib.dptr(signal), signal.shape[0],
+        _lib.dptr(signal_phases), signal_phases.shape[0], float(phase_shift), int(bool(allow_negative)),
+        _phase_interpolant, _lib.dptr(out)))
+    return out
+
+
+def phase_interpolator(new_phases, phases, signal, phase_shift, allow_negative=0):
+    """Interpolate a phase-shifted signal at new phases (xpsi/tools/phase_interpolator.pyx:25-98).
+    Returns ``[rows, len(new_phases)]``."""
+    new_phases = _lib.as_f8(new_phases, 1)
+    phases = _lib.as_f8(phases, 1)
+    signal = _lib.as_f8(signal, 2)
+    out = np.empty((signal.shape[0], new_phases.shape[0]), dtype=np.float64)
+    _lib.check(_lib.lib.xpsi_b200_phase_interpolator(
+        _lib.dptr(new_phases), new_phases.shape[0], _lib.dptr(phases), phases.shape[0], _lib.dptr(signal),
+        signal.shape[0], float(phase_shift), int(bool(allow_negative)), _phase_interpolant, _lib.dptr(out)))
+    return out
