@@ -66,8 +66,9 @@ void xpsi_b200_atmosphere_destroy(xpsi_b200_atmosphere* atm);
 /* ---- cellmesh.integrator_for_azimuthal_invariance.integrate -----------------
  * replaces xpsi/cellmesh/integrator_for_azimuthal_invariance.pyx:70-665
  * (call site xpsi/HotRegion.py:1169-1197).  flux_out is [n_energies][n_phases].
- * correction_srcCellParams / elsewhere atmosphere / disc (R_in < 1e6) are not
- * yet covered: passing them returns XPSI_B200_EUNSUPPORTED.                   */
+ * correction_srcCellParams (NULL or [n_rings][n_azi][n_params]) activates the elsewhere
+ * correction with else_atm_ext / elsewhere_atmosphere.  beam_opt != 0 and a disc
+ * (R_in < 1e6) are not covered: they return XPSI_B200_EUNSUPPORTED.              */
 int xpsi_b200_integrate_azimuthal_invariance(
     double R, double omega, double r_s, double inclination,
     int n_rings, int n_azi,
@@ -115,6 +116,11 @@ int xpsi_b200_phase_interpolator(const double* new_phases, int n_new, const doub
 int xpsi_b200_energy_interpolator(const double* signal, int n_energies, int n_phases, const double* log10_energies,
                                   const double* new_log10_energies, int n_new, int energy_interpolant,
                                   double* out);
+
+/* ---- Interstellar.__call__ ------------------------------------------------------------
+ * replaces the in-place row scaling of xpsi/Interstellar.py:27-58:
+ * signal[i][:] *= attenuation[i], signal [n_rows][n_cols] modified in place.           */
+int xpsi_b200_interstellar_attenuate(const double* attenuation, int n_rows, int n_cols, double* signal);
 
 /* ---- Instrument.__call__ -------------------------------------------------------
  * replaces numpy.dot(matrix[o0:o1, i0:i1], signal), xpsi/Instrument.py:192-197.

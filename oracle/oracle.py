@@ -42,8 +42,8 @@ def integrate(numThreads, R, omega, r_s, inclination, cellArea, radialCoords_of_
               cos_alpha, lag, maxDeflection, cos_gammaArray, energies, leaves, phases, hot_atmosphere,
               elsewhere_atmosphere, hot_atm_ext, else_atm_ext, beam_opt, image_order_limit=None,
               R_in=1e6, phase_interpolant='Akima'):
-    """xpsi/cellmesh/integrator_for_azimuthal_invariance.pyx:70-98 (no correction, no disc)."""
-    assert correction_srcCellParams is None and beam_opt == 0 and R_in >= 1e6
+    """xpsi/cellmesh/integrator_for_azimuthal_invariance.pyx:70-98 (no disc, beam_opt 0)."""
+    assert beam_opt == 0 and R_in >= 1e6
     cellArea, theta, phi = _f8(cellArea), _f8(theta), _f8(phi)
     par = _f8(srcCellParams)
     rad = np.ascontiguousarray(CELL_RADIATES, dtype=np.int32)
@@ -62,8 +62,20 @@ def integrate(numThreads, R, omega, r_s, inclination, cellArea, radialCoords_of_
         C.c_int(E.size), _d(E), C.c_int(L.size), _d(L), C.c_int(P.size), _d(P), C.c_int(int(hot_atm_ext)),
         _d(tab[0]), C.c_int(tab[0].size), _d(tab[1]), C.c_int(tab[1].size), _d(tab[2]), C.c_int(tab[2].size),
         _d(tab[3]), C.c_int(tab[3].size), _d(tab[4]),
-        C.c_int(int(image_order_limit) if image_order_limit else 0), C.c_int(INTERP[phase_interpolant]), _d(flux))
+        C.c_int(int(image_order_limit) if image_order_limit else 0), C.c_int(INTERP[phase_interpolant]), _d(flux),
+        *_correction_args(correction_srcCellParams, elsewhere_atmosphere, else_atm_ext))
     return (1, None) if rc else (0, flux)
+
+
+def _correction_args(correction, atmosphere, else_atm_ext):
+    if correction is None:
+        z = np.zeros(4)
+        return [None, C.c_int(0)] + [_d(z), C.c_int(4)] * 4 + [_d(z)]
+    corr = _f8(correction)
+    tab = [_f8(t) for t in atmosphere] if atmosphere else [np.zeros(4)] * 5
+    _correction_args.keep = (corr, tab)
+    return [_d(corr), C.c_int(int(else_atm_ext)), _d(tab[0]), C.c_int(tab[0].size), _d(tab[1]), C.c_int(tab[1].size),
+            _d(tab[2]), C.c_int(tab[2].size), _d(tab[3]), C.c_int(tab[3].size), _d(tab[4])]
 
 
 def energy_integrator(N_Ts, signal, energies, energy_edges, phase_interpolant='Akima'):

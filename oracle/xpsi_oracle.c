@@ -113,8 +113,13 @@ int oracle_integrate_azinv(
     const double *cos_gammaArray, int N_E, const double *energies, int N_L, const double *leaves,
     int N_P, const double *phases, int hot_atm_ext, const double *logT, int nT, const double *logg,
     int ng, const double *mu_ax, int nmu, const double *logE, int nE, const double *buf,
-    int image_order_limit, int phase_interp, double *flux) {
+    int image_order_limit, int phase_interp, double *flux,
+    /* elsewhere correction (pyx:257-268): NULL, or [n_rings][n_azi][n_params] + its atmosphere */
+    const double *correction, int else_atm_ext, const double *c_logT, int c_nT, const double *c_logg,
+    int c_ng, const double *c_mu, int c_nmu, const double *c_logE, int c_nE, const double *c_buf) {
   atm_table tab = {{logT, logg, mu_ax, logE}, {nT, ng, nmu, nE}, buf};
+  atm_table ctab = {{c_logT, c_logg, c_mu, c_logE}, {c_nT, c_ng, c_nmu, c_nE}, c_buf};
+  const int perform_correction = correction != NULL;
   const double sin_i = sin(inclination), cos_i = cos(inclination);
   const size_t leaf_lim = (N_L % 2 == 0) ? N_L / 2 : (N_L + 1) / 2;
   int terminate = 0;
@@ -212,7 +217,11 @@ int oracle_integrate_azinv(
               for (int p = 0; p < N_E; p++) {
                 double E_prime = energies[p] / _Z;
                 double I_E = eval_hot(hot_atm_ext, &tab, E_prime, _ABB, VEC);
-                PROFILE[(size_t)p * N_L + _kdx] = (I_E * eval_hot_norm(hot_atm_ext)) * _GEOM;
+                double correction_I_E = 0.0;
+                if (perform_correction)                                          /* :469-476 */
+                  correction_I_E = eval_hot(else_atm_ext, &ctab, E_prime, _ABB,
+                                            correction + ((size_t)i * n_azi + J) * n_params) * eval_hot_norm(else_atm_ext);
+                PROFILE[(size_t)p * N_L + _kdx] = (I_E * eval_hot_norm(hot_atm_ext) - correction_I_E) * _GEOM;
               }
             }
           }
@@ -257,7 +266,7 @@ int oracle_integrate_azinv(
             else if (x < PHASE[0]) { while (x < PHASE[0]) x += 2.0 * M_PI; }
             if (x < interp_PROFILE->xmin || x > interp_PROFILE->xmax) { terminate = 1; break; }
             double f = gsl_interp_eval(interp_PROFILE, PHASE, profile_ptr, x, acc_p);
-            if (f > 0.0) flux[(size_t)p * N_P + k] += cellArea[i * n_azi + j] * f;
+            if (f > 0.0 || perform_correction) flux[(size_t)p * N_P + k] += cellArea[i * n_azi + j] * f;
           }
         }
       }

@@ -59,7 +59,10 @@ class Recorder:
 
         def wrapped(*args, **kwargs):
             out = inner(*args, **kwargs)
-            self.calls["integrate"].append((args, kwargs, out))
+            # copy: Photosphere.integrate later adds the elsewhere spectrum to this array in place
+            # (xpsi/Photosphere.py:589-592)
+            kept = (out[0], None if out[1] is None else np.array(out[1]))
+            self.calls["integrate"].append((args, kwargs, kept))
             return out
         hot._integrator = wrapped
 

@@ -285,3 +285,47 @@ def test_time_invariant_integrator_everywhere_and_elsewhere():
     s2, ref = orc.integrate_time_invariance(*args)
     assert status == 0 and s2 == 0
     assert float(np.max(np.abs(flux - ref) / np.max(np.abs(ref)))) < PULSE_RTOL
+
+
+def test_m4_hot_regions_with_elsewhere_correction_and_interstellar():
+    """Config 4: hot regions with the elsewhere correction active (pyx:257-268,469-478), Elsewhere added to
+    the first hot region (Photosphere.py:589-592), interstellar attenuation (Interstellar.py:27-58), fold and
+    likelihood -- every stage on the GPU, against the reference's lnL."""
+    import os
+    from conftest import GOLDEN
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.cellmesh.integrator_for_azimuthal_invariance import integrate
+    from xpsi_b200.cellmesh.integrator_for_time_invariance import integrate as integrate_tinv
+    from xpsi_b200.instrument import fold
+    from xpsi_b200.interstellar import attenuate
+    from xpsi_b200.likelihoods import eval_marginal_likelihood
+    from xpsi_b200.tools import energy_integrator
+    d = np.load(os.path.join(GOLDEN, "m4_elsewhere.npz"))
+    table = syn.nsx_like_table()
+    matrix, edges = syn.nicer_like_response()[:2]
+    status, spectrum = integrate_tinv(*_tinv_args(d, "else_", table))
+    assert status == 0
+    comps = []
+    for m in range(2):
+        p = "int%d_" % m
+        args = list(_integrate_args(d, p, table))
+        args[12] = d[p + "correction_srcCellParams"]
+        args[23] = table
+        args[25] = int(d[p + "else_atm_ext"])
+        status, flux = integrate(*args)
+        assert status == 0
+        err = _pulse_err(flux, d[p + "flux"])
+        print("M4 member", m, "flux (with correction) rel err", err)
+        assert err < PULSE_RTOL
+        if m == 0:
+            flux = flux + spectrum[:, None]
+        integrated = energy_integrator(1, flux / d["d_sq"], np.log10(d["int0_energies"]), np.log10(edges))
+        attenuate(d["attenuation"], integrated)
+        comps.append(fold(matrix, integrated, (0, matrix.shape[1]), (0, matrix.shape[0])))
+        assert rel_err(comps[-1], d["marg_components_%d" % m]) < PULSE_RTOL
+    p = "marg_"
+    lnL = eval_marginal_likelihood(float(d[p + "exposure_time"]), d[p + "phases"], d[p + "counts"], tuple(comps),
+                                   (d[p + "component_phases_0"], d[p + "component_phases_1"]), d[p + "phase_shifts"],
+                                   d[p + "precomp"], d[p + "support"], 1000, 0.0, 1e-8, 1e-3, 10.0, -1e90)[0]
+    print("M4 lnL", lnL, "ref", float(d["lnL_total"]), "diff", lnL - float(d["lnL_total"]))
+    assert abs(lnL - float(d["lnL_total"])) < LNL_ATOL

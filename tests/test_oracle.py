@@ -152,3 +152,16 @@ def test_oracle_time_invariant_integrator():
     el = np.load(os.path.join(ROOT, "tests", "golden", "m4_elsewhere.npz"))
     s, f = orc.integrate_time_invariance(*_tinv_args(el, "else_", table))
     assert s == 0 and rel_err(f, el["else_flux"]) < 1e-8
+
+
+def test_oracle_integrate_with_elsewhere_correction():
+    from xpsi_b200 import synthetic as syn
+    table = syn.nsx_like_table()
+    d = np.load(os.path.join(ROOT, "tests", "golden", "m4_elsewhere.npz"))
+    for m in range(2):
+        p = "int%d_" % m
+        args = list(_integrate_args(d, p, table))
+        args[12] = d[p + "correction_srcCellParams"]; args[23] = table; args[25] = int(d[p + "else_atm_ext"])
+        status, flux = orc.integrate(*args)
+        assert status == 0
+        assert _pulse_err(flux, d[p + "flux"]) < 1e-8

@@ -118,6 +118,7 @@ _proto("xpsi_b200_phase_interpolator", C.c_int,
        [c_double_p, C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p])
 _proto("xpsi_b200_energy_interpolator", C.c_int,
        [c_double_p, C.c_int, C.c_int, c_double_p, c_double_p, C.c_int, C.c_int, c_double_p])
+_proto("xpsi_b200_interstellar_attenuate", C.c_int, [c_double_p, C.c_int, C.c_int, c_double_p])
 _proto("xpsi_b200_instrument_fold", C.c_int,
        [c_double_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p])
 _proto("xpsi_b200_precomputation", C.c_int, [c_int_p, C.c_int, C.c_int, c_double_p])
@@ -145,7 +146,7 @@ EXPORTED = [
     "xpsi_b200_pipeline_upload", "xpsi_b200_pipeline_eval_resident", "xpsi_b200_pipeline_download",
     "xpsi_b200_pipeline_fetch", "xpsi_b200_pipeline_stage_ms", "xpsi_b200_fp64_peak_tflops",
     "xpsi_b200_pipeline_work_counters", "xpsi_b200_phase_integrator", "xpsi_b200_phase_interpolator",
-    "xpsi_b200_energy_interpolator", "xpsi_b200_integrate_time_invariance",
+    "xpsi_b200_energy_interpolator", "xpsi_b200_integrate_time_invariance", "xpsi_b200_interstellar_attenuate",
 ]
 
 

@@ -161,10 +161,15 @@ int xpsi_b200_integrate_azimuthal_invariance(
     const xpsi_b200_atmosphere* hot_atmosphere, const xpsi_b200_atmosphere* elsewhere_atmosphere,
     int hot_atm_ext, int else_atm_ext, int beam_opt, int image_order_limit, double R_in,
     int phase_interpolant, double* flux_out) {
-  (void)R; (void)r_s; (void)else_atm_ext; (void)elsewhere_atmosphere;
+  (void)R; (void)r_s;
   int rc = ensure_stream();
   if (rc) return rc;
-  if (correction_srcCellParams) return fail(XPSI_B200_EUNSUPPORTED, "elsewhere correction is not covered yet");
+  if (correction_srcCellParams) {
+    if (else_atm_ext != XPSI_B200_ATM_BB && else_atm_ext != XPSI_B200_ATM_NUM4D)
+      return fail(XPSI_B200_EUNSUPPORTED, "else_atm_ext must be 1 (BB) or 2 (Num4D)");
+    if (else_atm_ext == XPSI_B200_ATM_NUM4D && !elsewhere_atmosphere)
+      return fail(XPSI_B200_EINVAL, "Num4D elsewhere correction needs a preloaded atmosphere");
+  }
   if (R_in < 1.0e6) return fail(XPSI_B200_EUNSUPPORTED, "disc occultation (R_in < 1e6) is not covered yet");
   if (beam_opt != 0) return fail(XPSI_B200_EUNSUPPORTED, "beam_opt != 0 is not covered yet");
   if (hot_atm_ext != XPSI_B200_ATM_BB && hot_atm_ext != XPSI_B200_ATM_NUM4D)
@@ -180,6 +185,8 @@ int xpsi_b200_integrate_azimuthal_invariance(
   Dev<double> d_area, d_radial, d_rsr, d_theta, d_phi, d_par, d_defl, d_ca, d_lag, d_maxd, d_cg, d_E, d_L,
       d_P, d_flux, d_scal;
   Dev<int> d_rad, d_status;
+  Dev<double> d_corr;
+  if (correction_srcCellParams) CK(d_corr.upload(correction_srcCellParams, nc * n_params));
   const double scal[2] = {omega, inclination};
   CK(d_scal.upload(scal, 2));
   CK(d_area.upload(cellArea, nc)); CK(d_radial.upload(radial, n_rings)); CK(d_rsr.upload(r_s_over_r, n_rings));
@@ -212,19 +219,30 @@ int xpsi_b200_integrate_azimuthal_invariance(
     a.hot = hot_atmosphere->view;
     xb::azinv_slab_budgets(a.hot, energies, n_energies, &a.slab_ne_max, &a.slab_rows_ring);
   }
+  if (correction_srcCellParams) {
+    a.corrParams = d_corr.p; a.else_atm_ext = else_atm_ext;
+    if (else_atm_ext == XPSI_B200_ATM_NUM4D) {
+      a.els = elsewhere_atmosphere->view;
+      int rc2 = 0, rr2 = 0;
+      xb::azinv_slab_budgets(a.els, energies, n_energies, &rc2, &rr2);
+      if (rc2 > a.slab_ne_max) a.slab_ne_max = rc2;
+      if (rr2 > a.slab_rows_ring) a.slab_rows_ring = rr2;
+    }
+  }
   a.image_order_limit = image_order_limit > 0 ? image_order_limit : 0;
   a.n_img_max = image_order_limit > 0 ? image_order_limit : xb::kMaxImages;
   if (a.n_img_max > xb::kMaxImages) return fail(XPSI_B200_EUNSUPPORTED, "image_order_limit > 6");
   a.phase_interp = phase_interpolant;
   a.scale_by_energy = 1;
   a.flux = d_flux.p; a.status = d_status.p;
-  Dev<double> d_ws, d_wh, d_wslab; Dev<int> d_wi;
+  Dev<double> d_ws, d_wh, d_wslab, d_wslab2; Dev<int> d_wi;
   {
     size_t nl, nh, ni, ns;
     xb::azinv_workspace_sizes(a, &nl, &nh, &ni, &ns);
     CK(d_ws.alloc(nl)); CK(d_wh.alloc(nh)); CK(d_wi.alloc(ni)); CK(d_wslab.alloc(ns));
+    if (a.else_atm_ext == XPSI_B200_ATM_NUM4D) CK(d_wslab2.alloc(ns));
   }
-  a.ws_leaf = d_ws.p; a.ws_hdr = d_wh.p; a.ws_ihdr = d_wi.p; a.ws_slab = d_wslab.p;
+  a.ws_leaf = d_ws.p; a.ws_hdr = d_wh.p; a.ws_ihdr = d_wi.p; a.ws_slab = d_wslab.p; a.ws_slab2 = d_wslab2.p;
   cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_integrate_azinv");
   g_launches += (hot_atm_ext == XPSI_B200_ATM_NUM4D) ? 4 : 3;
@@ -382,6 +400,20 @@ int xpsi_b200_energy_interpolator(const double* signal, int n_energies, int n_ph
   // one spline per phase column; result laid out [n_new][n_phases] like the reference's transposed return
   return row_spline_call(log10_energies, n_energies, signal, n_phases, 1, n_phases, (size_t)n_energies * n_phases,
                          new_log10_energies, n_new, n_new, 2, 0.0, 1.0, 1, energy_interpolant, 0, out, 1, n_phases);
+}
+
+int xpsi_b200_interstellar_attenuate(const double* attenuation, int n_rows, int n_cols, double* signal) {
+  int rc = ensure_stream();
+  if (rc) return rc;
+  if (n_rows < 1 || n_cols < 1) return fail(XPSI_B200_EINVAL, "bad dimensions");
+  Dev<double> d_a, d_s;
+  CK(d_a.upload(attenuation, n_rows)); CK(d_s.upload(signal, (size_t)n_rows * n_cols));
+  cudaError_t e = xb::launch_attenuate(d_a.p, n_rows, n_cols, d_s.p, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_attenuate");
+  g_launches += 1;
+  CK(d_s.download(signal, (size_t)n_rows * n_cols));
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
 }
 
 int xpsi_b200_precomputation(const int* counts, int n_chan, int n_bins, double* out) {

@@ -54,7 +54,9 @@ __device__ __forceinline__ double bb_intensity(double E, double kT) {
 //   doubles [0],[1] min/max of Z (log10 Z for Num4D) over lit leaves  [2..5] T weights
 //          [6..9] g weights  [10] log10 T  [11] log10 g  [12] kT (keV)  [13] log10 kT
 //          [14] intensity normalisation (hot_BB.pyx:98 / hot_Num4D.pyx:436-460)
-constexpr int kIHdr = 8, kDHdr = 16;
+//   elsewhere correction (pyx:257-268): the same block of doubles again at +kCorrD for the ring's
+//   correction parameters; ints [6],[7] its (T,g) base nodes, [8],[9] its slab rows
+constexpr int kIHdr = 12, kDHdr = 32, kCorrD = 16;
 
 // order-preserving map double <-> unsigned 64 (for shared-memory atomicMin/Max)
 __device__ __forceinline__ unsigned long long order_key(double v) {
@@ -300,6 +302,24 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
       dh[12] = kT; dh[13] = log10(kT);
       dh[14] = (ATM == 2) ? (kErg / kHKeV) * pow(10.0, 3.0 * VEC[0]) : kErg * kPlanckDistConst;
     }
+    if (a.corrParams && n > 0) {   // elsewhere atmosphere at the ring's correction parameters
+      const double* CV = a.corrParams + (a.params_per_cell ? (cell0 + J) : ring) * a.n_params;
+      const double kTc = kKBOverKeV * pow(10.0, CV[0]);
+      dh[kCorrD + 10] = CV[0]; dh[kCorrD + 12] = kTc; dh[kCorrD + 13] = log10(kTc);
+      dh[kCorrD + 14] = (a.else_atm_ext == 2) ? kErg / kHKeV * pow(10.0, 3.0 * CV[0]) : kErg * kPlanckDistConst;
+      if (a.else_atm_ext == 2) {
+        View vT{a.els.logT, 1}, vG{a.els.logg, 1};
+        const int bT = lagrange_base(vT, a.els.nT, CV[0]);
+        const int bG = lagrange_base(vG, a.els.ng, CV[1]);
+        double w[4];
+        lagrange_weights(vT, bT, CV[0], w);
+        for (int x = 0; x < 4; ++x) dh[kCorrD + 2 + x] = w[x];
+        lagrange_weights(vG, bG, CV[1], w);
+        for (int x = 0; x < 4; ++x) dh[kCorrD + 6 + x] = w[x];
+        ih[6] = bT; ih[7] = bG;
+        dh[kCorrD + 11] = CV[1];
+      }
+    }
     if (ATM == 2 && n > 0) {     // (T,g) stencil of the ring, hot_Num4D.pyx:295-409
       View vT{a.hot.logT, 1}, vG{a.hot.logg, 1};
       const int bT = lagrange_base(vT, a.hot.nT, VEC[0]);
@@ -333,46 +353,51 @@ __device__ __forceinline__ void row_range(const P& axis, int nE, double vlo, dou
 
 constexpr int kSlabThreads = 256;
 
-__global__ void __launch_bounds__(kSlabThreads) k_azinv_slab(AzinvArgs a) {
+// which = 0: hot atmosphere at the ring's parameters; 1: elsewhere atmosphere at the
+// ring's correction parameters (pyx:469-476)
+__global__ void __launch_bounds__(kSlabThreads) k_azinv_slab(AzinvArgs a, int which) {
   const int i = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
   const long ring = (long)q * a.n_rings + i;
   int* ih = a.ws_ihdr + ring * kIHdr;
   if (ih[0] == 0) return;
   const double* dh = a.ws_hdr + ring * kDHdr;
+  const AtmTable& T = which ? a.els : a.hot;
+  const int ho = which ? kCorrD : 0;             // header offset of this atmosphere's block
   __shared__ int s_elo, s_nrows;
   __shared__ double s_wT[4], s_wG[4];
-  const double zlo = dh[0], zhi = dh[1], log_kT = dh[13];
+  const double zlo = dh[0], zhi = dh[1], log_kT = dh[ho + 13];
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
-  View vE{a.hot.logE, 1};
+  View vE{T.logE, 1};
   if (tid == 0) {
     int elo = 0, ehi = 4;
     if (zlo <= zhi)
-      row_range(vE, a.hot.nE, a.log10_energies[0] - zhi - log_kT,
+      row_range(vE, T.nE, a.log10_energies[0] - zhi - log_kT,
                 a.log10_energies[a.n_energies - 1] - zlo - log_kT, &elo, &ehi);
     if (ehi - elo > a.slab_rows_ring) { atomicExch(a.status + q, kUnsupported); ih[0] = 0; ehi = elo; }
-    ih[4] = elo; ih[5] = ehi - elo;
+    ih[which ? 8 : 4] = elo; ih[which ? 9 : 5] = ehi - elo;
     s_elo = elo; s_nrows = ehi - elo;
-    for (int x = 0; x < 4; ++x) { s_wT[x] = dh[2 + x]; s_wG[x] = dh[6 + x]; }
+    for (int x = 0; x < 4; ++x) { s_wT[x] = dh[ho + 2 + x]; s_wG[x] = dh[ho + 6 + x]; }
   }
   // energy rows each 8-energy chunk of this ring reaches (first table row, count)
+  int2* chunk_tab = reinterpret_cast<int2*>(a.ws_chunk) + ((long)which * a.Q * a.n_rings + ring) * n_chunks;
   for (int c = tid; c < n_chunks; c += kSlabThreads) {
     const int e0 = c * kNEC, e1 = min(e0 + kNEC, a.n_energies) - 1;
     int lo = 0, hi = 4;
     if (zlo <= zhi)
-      row_range(vE, a.hot.nE, a.log10_energies[e0] - zhi - log_kT, a.log10_energies[e1] - zlo - log_kT, &lo, &hi);
+      row_range(vE, T.nE, a.log10_energies[e0] - zhi - log_kT, a.log10_energies[e1] - zlo - log_kT, &lo, &hi);
     int2 r; r.x = lo; r.y = hi - lo;
-    reinterpret_cast<int2*>(a.ws_chunk)[ring * n_chunks + c] = r;
+    chunk_tab[c] = r;
   }
   __syncthreads();
-  const int elo = s_elo, nrows = s_nrows, nmu = a.hot.nmu;
+  const int elo = s_elo, nrows = s_nrows, nmu = T.nmu;
   if (nrows == 0) return;
-  const int bT = ih[2], bG = ih[3];
-  const long S0 = (long)a.hot.ng * nmu * a.hot.nE, S1 = (long)nmu * a.hot.nE, S2 = a.hot.nE;
-  double* out = a.ws_slab + ring * (long)nmu * a.slab_rows_ring;
+  const int bT = ih[which ? 6 : 2], bG = ih[which ? 7 : 3];
+  const long S0 = (long)T.ng * nmu * T.nE, S1 = (long)nmu * T.nE, S2 = T.nE;
+  double* out = (which ? a.ws_slab2 : a.ws_slab) + ring * (long)nmu * a.slab_rows_ring;
   const int tw = tid & 31, wid = tid >> 5;        // a warp per mu row, lanes along the energy rows
   for (int m = wid; m < nmu; m += kSlabThreads / 32)
   for (int e = tw; e < nrows; e += 32) {
-    const double* base = a.hot.buf + (long)bT * S0 + (long)bG * S1 + (long)m * S2 + elo + e;
+    const double* base = T.buf + (long)bT * S0 + (long)bG * S1 + (long)m * S2 + elo + e;
     double acc = 0.0;
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
@@ -388,8 +413,88 @@ __global__ void __launch_bounds__(kSlabThreads) k_azinv_slab(AzinvArgs a) {
 // ===========================================================================
 // flux
 // ===========================================================================
-template <int ATM>
-__global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
+// shared-memory view of one Num4D atmosphere inside a flux CTA
+struct SlabCtx {
+  double* axE; double* invden; double* axMu; double* slab; double* muw; int* mub;
+  int nrows, elo_tab, nE, nmu;
+  double inv_dE, log_kT;
+};
+
+__device__ __forceinline__ double* slab_ctx_carve(SlabCtx& c, double* sp, int N_L, int rows_max, int nmu) {
+  c.muw = sp; sp += 4 * N_L;
+  c.axE = sp; sp += rows_max;
+  c.invden = sp; sp += 4 * rows_max;
+  c.axMu = sp; sp += nmu;
+  c.slab = sp; sp += (long)nmu * rows_max;
+  return sp;
+}
+
+// copy the rows of the ring's slab this chunk reaches; returns false if they do not fit
+__device__ __forceinline__ bool slab_ctx_load(SlabCtx& c, const AtmTable& T, const double* ring_slab,
+                                              int elo_ring, int2 chunk_rows, int rows_ring_stride,
+                                              int rows_max, int tid) {
+  c.nrows = chunk_rows.y; c.elo_tab = chunk_rows.x; c.nE = T.nE; c.nmu = T.nmu;
+  if (c.nrows > rows_max) return false;
+  const int lo_c = c.elo_tab - elo_ring;
+  for (int m = tid; m < T.nmu; m += kFluxThreads) c.axMu[m] = T.mu[m];
+  for (int r = tid; r < c.nrows; r += kFluxThreads) c.axE[r] = T.logE[c.elo_tab + r];
+  const double* src = ring_slab + lo_c;
+  const int sub = tid & 15, grp = tid >> 4;          // half a warp per mu row (a chunk reaches ~16 rows)
+  for (int m = grp; m < T.nmu; m += kFluxThreads / 16)
+    for (int e = sub; e < c.nrows; e += 16) c.slab[m * c.nrows + e] = src[(long)m * rows_ring_stride + e];
+  return true;
+}
+
+__device__ __forceinline__ void slab_ctx_finish(SlabCtx& c, int tid) {     // after a barrier
+  for (int r = tid; r + 3 < c.nrows; r += kFluxThreads) {       // Lagrange denominators per base row
+    const double p0 = c.axE[r], p1 = c.axE[r + 1], p2 = c.axE[r + 2], p3 = c.axE[r + 3];
+    c.invden[4 * r + 0] = 1.0 / (p0 - p1) / (p0 - p2) / (p0 - p3);
+    c.invden[4 * r + 1] = 1.0 / (p1 - p0) / (p1 - p2) / (p1 - p3);
+    c.invden[4 * r + 2] = 1.0 / (p2 - p0) / (p2 - p1) / (p2 - p3);
+    c.invden[4 * r + 3] = 1.0 / (p3 - p0) / (p3 - p1) / (p3 - p2);
+  }
+  // mean spacing of the axis segment: first guess of the energy stencil (then walked)
+  c.inv_dE = (c.nrows > 1) ? (double)(c.nrows - 1) / (c.axE[c.nrows - 1] - c.axE[0]) : 0.0;
+}
+
+// mu stencil of every lit leaf (geom != 0), weights stored [4][N_L]
+__device__ __forceinline__ void slab_ctx_leaf_stencils(const SlabCtx& c, const double* abb, const double* geom,
+                                                       int N_L, int tid) {
+  for (int l = tid; l < N_L; l += kFluxThreads) {
+    if (geom[l] == 0.0) continue;
+    const double v = abb[l];
+    const int b = lagrange_base(c.axMu, c.nmu, v);
+    double w[4];
+    lagrange_weights(c.axMu, b, v, w);
+    c.mub[l] = b;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) c.muw[x * N_L + l] = w[x];
+  }
+}
+
+// I / T^3 at log10(E'/kT) = v for leaf l: 4x4 (mu, E) stencil on the slab (hot_Num4D.pyx:416-437)
+__device__ __forceinline__ double slab_ctx_eval(const SlabCtx& c, double v, int l, int N_L) {
+  const int j = interval_walk(c.axE, c.nrows, v, (int)((v - c.axE[0]) * c.inv_dE));
+  int bE = j - 1;                                                   // base node (App. C.5)
+  if (c.elo_tab + bE < 0) bE = -c.elo_tab;
+  if (c.elo_tab + bE > c.nE - 4) bE = c.nE - 4 - c.elo_tab;
+  const double d0 = v - c.axE[bE], d1 = v - c.axE[bE + 1], d2 = v - c.axE[bE + 2], d3 = v - c.axE[bE + 3];
+  const double* iv = c.invden + 4 * bE;
+  const double wE0 = d1 * d2 * d3 * iv[0], wE1 = d0 * d2 * d3 * iv[1],
+               wE2 = d0 * d1 * d3 * iv[2], wE3 = d0 * d1 * d2 * iv[3];
+  const double* row = c.slab + (long)c.mub[l] * c.nrows + bE;
+  double sum = 0.0;
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const double* r = row + x * c.nrows;
+    sum += c.muw[x * N_L + l] * (wE0 * r[0] + wE1 * r[1] + wE2 * r[2] + wE3 * r[3]);
+  }
+  return sum < 0.0 ? 0.0 : sum;                                     // hot_Num4D.pyx:436-437
+}
+
+// ATM: hot atmosphere (1 BB, 2 Num4D).  CORR: elsewhere correction (0 none, 1 BB, 2 Num4D)
+template <int ATM, int CORR>
+__global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flux(AzinvArgs a) {
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
   const int i = blockIdx.x / n_chunks;
   const int chunk = blockIdx.x - i * n_chunks;
@@ -411,6 +516,7 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
   __shared__ int s_ncell;
   __shared__ double s_E[kNEC], s_logE[kNEC];
   const double kT = dh[12], log_kT = dh[13], norm = dh[14];
+  const double kT_c = dh[kCorrD + 12], log_kT_c = dh[kCorrD + 13], norm_c = dh[kCorrD + 14];
   double* sp = smem;
   double* s_cphi = sp; sp += a.n_azi;
   double* s_carea = sp; sp += a.n_azi;
@@ -420,17 +526,13 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
   double* s_geom = sp; sp += N_L;
   double* s_y = sp; sp += kNEC * N_L;
   double* s_coef = sp; sp += (long)kNEC * N_L * 4;
-  double* s_muw = nullptr; double* s_axE = nullptr; double* s_invden = nullptr;
-  double* s_axMu = nullptr; double* s_slab = nullptr;
-  if (ATM == 2) {
-    s_muw = sp; sp += 4 * N_L;
-    s_axE = sp; sp += a.slab_ne_max;
-    s_invden = sp; sp += 4 * a.slab_ne_max;
-    s_axMu = sp; sp += a.hot.nmu;
-    s_slab = sp; sp += (long)a.hot.nmu * a.slab_ne_max;
-  }
-  int* s_mub = reinterpret_cast<int*>(sp);
-  unsigned* s_flag = reinterpret_cast<unsigned*>(s_mub + N_L);
+  SlabCtx hot, els;
+  if (ATM == 2) sp = slab_ctx_carve(hot, sp, N_L, a.slab_ne_max, a.hot.nmu);
+  if (CORR == 2) sp = slab_ctx_carve(els, sp, N_L, a.slab_ne_max, a.els.nmu);
+  int* ip = reinterpret_cast<int*>(sp);
+  hot.mub = ip; ip += N_L;
+  els.mub = ip; if (CORR == 2) ip += N_L;
+  unsigned* s_flag = reinterpret_cast<unsigned*>(ip);
 
   // ---- compact list of the ring's radiating cells (one warp: keeps azimuth order) ------
   if (tid < 32) {
@@ -457,41 +559,30 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
     s_logE[e] = a.log10_energies[e0 + (e < ne ? e : 0)];
   }
 
-  // ---- Num4D: copy the rows of the ring's slab this chunk reaches ------------------------
-  int nrows = 0, elo_tab = 0;
+  // ---- Num4D: copy the rows of the ring's slab(s) this chunk reaches ------------------------
   if (ATM == 2) {
-    const int elo_ring = ih[4];
     const int2 cr = reinterpret_cast<const int2*>(a.ws_chunk)[ring * n_chunks + chunk];
-    nrows = cr.y;
-    elo_tab = cr.x;
-    const int lo_c = elo_tab - elo_ring;
-    if (nrows > a.slab_ne_max) {       // budget too small for this ring: refuse, never clamp
-      if (tid == 0) atomicExch(a.status + q, kUnsupported);
+    hot.log_kT = log_kT;
+    if (!slab_ctx_load(hot, a.hot, a.ws_slab + ring * (long)a.hot.nmu * a.slab_rows_ring, ih[4], cr,
+                       a.slab_rows_ring, a.slab_ne_max, tid)) {
+      if (tid == 0) atomicExch(a.status + q, kUnsupported);   // budget too small: refuse, never clamp
       return;
     }
-    for (int m = tid; m < a.hot.nmu; m += kFluxThreads) s_axMu[m] = a.hot.mu[m];
-    for (int r = tid; r < nrows; r += kFluxThreads) s_axE[r] = a.hot.logE[elo_tab + r];
-    const double* src = a.ws_slab + ring * (long)a.hot.nmu * a.slab_rows_ring + lo_c;
-    {   // half a warp per mu row (a chunk reaches ~16 rows)
-      const int sub = tid & 15, grp = tid >> 4;
-      for (int m = grp; m < a.hot.nmu; m += kFluxThreads / 16)
-        for (int e = sub; e < nrows; e += 16) s_slab[m * nrows + e] = src[(long)m * a.slab_rows_ring + e];
+  }
+  if (CORR == 2) {
+    const int2 cr = reinterpret_cast<const int2*>(a.ws_chunk)[((long)a.Q * a.n_rings + ring) * n_chunks + chunk];
+    els.log_kT = log_kT_c;
+    if (!slab_ctx_load(els, a.els, a.ws_slab2 + ring * (long)a.els.nmu * a.slab_rows_ring, ih[8], cr,
+                       a.slab_rows_ring, a.slab_ne_max, tid)) {
+      if (tid == 0) atomicExch(a.status + q, kUnsupported);
+      return;
     }
   }
   __syncthreads();
   const int n_cells = s_ncell;
   if (n_cells == 0) return;
-  if (ATM == 2) {
-    for (int r = tid; r + 3 < nrows; r += kFluxThreads) {     // Lagrange denominators per base row
-      const double p0 = s_axE[r], p1 = s_axE[r + 1], p2 = s_axE[r + 2], p3 = s_axE[r + 3];
-      s_invden[4 * r + 0] = 1.0 / (p0 - p1) / (p0 - p2) / (p0 - p3);
-      s_invden[4 * r + 1] = 1.0 / (p1 - p0) / (p1 - p2) / (p1 - p3);
-      s_invden[4 * r + 2] = 1.0 / (p2 - p0) / (p2 - p1) / (p2 - p3);
-      s_invden[4 * r + 3] = 1.0 / (p3 - p0) / (p3 - p1) / (p3 - p2);
-    }
-  }
-  // mean spacing of the axis segment: first guess of the energy stencil (then walked)
-  const double inv_dE = (ATM == 2 && nrows > 1) ? (double)(nrows - 1) / (s_axE[nrows - 1] - s_axE[0]) : 0.0;
+  if (ATM == 2) slab_ctx_finish(hot, tid);
+  if (CORR == 2) slab_ctx_finish(els, tid);
 
   const int interp_kind = a.phase_interp;
   const int k = tid;                         // output phase owned in the accumulation stage
@@ -509,17 +600,9 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
       s_flag[l] = 0u;
     }
     __syncthreads();
-    if (ATM == 2) {
-      for (int l = tid; l < N_L; l += kFluxThreads) {
-        if (s_geom[l] == 0.0) continue;
-        const double v = s_aux[l];
-        const int b = lagrange_base(s_axMu, a.hot.nmu, v);
-        double w[4];
-        lagrange_weights(s_axMu, b, v, w);
-        s_mub[l] = b;
-#pragma unroll
-        for (int x = 0; x < 4; ++x) s_muw[x * N_L + l] = w[x];
-      }
+    if (ATM == 2 || CORR == 2) {
+      if (ATM == 2) slab_ctx_leaf_stencils(hot, s_aux, s_geom, N_L, tid);
+      if (CORR == 2) slab_ctx_leaf_stencils(els, s_aux, s_geom, N_L, tid);
       __syncthreads();
     }
     for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
@@ -529,29 +612,19 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
       double val = 0.0;
       const double geom = s_geom[l];
       if (geom != 0.0) {
-        if (ATM == 1) {
-          val = bb_intensity(s_E[e] / s_Z[l], kT) * norm * geom;
-        } else {
-          const double v = s_logE[e] - s_Z[l] - log_kT;                     // log10(E'/kT)
-          int j = interval_walk(s_axE, nrows, v, (int)((v - s_axE[0]) * inv_dE));
-          int bE = j - 1;                                                   // base node (App. C.5)
-          if (elo_tab + bE < 0) bE = -elo_tab;
-          if (elo_tab + bE > a.hot.nE - 4) bE = a.hot.nE - 4 - elo_tab;
-          const double d0 = v - s_axE[bE], d1 = v - s_axE[bE + 1], d2 = v - s_axE[bE + 2],
-                       d3 = v - s_axE[bE + 3];
-          const double* iv = s_invden + 4 * bE;
-          const double wE0 = d1 * d2 * d3 * iv[0], wE1 = d0 * d2 * d3 * iv[1],
-                       wE2 = d0 * d1 * d3 * iv[2], wE3 = d0 * d1 * d2 * iv[3];
-          const double* row = s_slab + (long)s_mub[l] * nrows + bE;
-          double sum = 0.0;
-#pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            const double* r = row + x * nrows;
-            sum += s_muw[x * N_L + l] * (wE0 * r[0] + wE1 * r[1] + wE2 * r[2] + wE3 * r[3]);
-          }
-          if (sum < 0.0) sum = 0.0;                              // hot_Num4D.pyx:436-437
-          val = sum * norm * geom;
+        // s_Z holds Z for a blackbody hot atmosphere, log10 Z for Num4D
+        double I_E;
+        if (ATM == 1) I_E = bb_intensity(s_E[e] / s_Z[l], kT);
+        else I_E = slab_ctx_eval(hot, s_logE[e] - s_Z[l] - log_kT, l, N_L);
+        double corr = 0.0;
+        if (CORR == 1) {
+          const double Z = (ATM == 2) ? exp10(s_Z[l]) : s_Z[l];
+          corr = bb_intensity(s_E[e] / Z, kT_c) * norm_c;
+        } else if (CORR == 2) {
+          const double logZ = (ATM == 2) ? s_Z[l] : log10(s_Z[l]);
+          corr = slab_ctx_eval(els, s_logE[e] - logZ - log_kT_c, l, N_L) * norm_c;
         }
+        val = (I_E * norm - corr) * geom;                          // pyx:478
       }
       s_y[e * N_L + l] = val;
     }
@@ -575,12 +648,15 @@ __global__ void __launch_bounds__(kFluxThreads, 4) k_azinv_flux(AzinvArgs a) {
       const double y0 = y[l];
       double2* o = reinterpret_cast<double2*>(s_coef + ((long)e * N_L + l) * 4);
       o[0] = make_double2(y0, b); o[1] = make_double2(c, d);
-      // Bernstein coefficients of the cubic on [0,h] (end values are the nodes themselves):
-      // all >= 0  =>  the spline is >= 0 on the interval
-      const double h = s_PH[l + 1] - s_PH[l];
-      const double B1 = y0 + b * h * (1.0 / 3.0);
-      const double B2 = y0 + h * ((2.0 / 3.0) * b + c * h * (1.0 / 3.0));
-      if (y0 < 0.0 || B1 < 0.0 || B2 < 0.0 || y[l + 1] < 0.0) atomicOr(&s_flag[l], 1u << e);
+      if (CORR == 0) {
+        // Bernstein coefficients of the cubic on [0,h] (end values are the nodes themselves):
+        // all >= 0  =>  the spline is >= 0 on the interval.  With the correction active the
+        // reference adds every cell whatever its sign (pyx:593), so nothing is flagged.
+        const double h = s_PH[l + 1] - s_PH[l];
+        const double B1 = y0 + b * h * (1.0 / 3.0);
+        const double B2 = y0 + h * ((2.0 / 3.0) * b + c * h * (1.0 / 3.0));
+        if (y0 < 0.0 || B1 < 0.0 || B2 < 0.0 || y[l + 1] < 0.0) atomicOr(&s_flag[l], 1u << e);
+      }
     }
     __syncthreads();
     // ---- (3) interval moments over the ring's cells, then 4 FMAs per energy (pyx:571-596) -----
@@ -681,10 +757,11 @@ static size_t geom_smem_bytes(const AzinvArgs& a) {
          (size_t)a.n_img_max * a.n_leaves * sizeof(int);
 }
 
-static size_t flux_smem_bytes(const AzinvArgs& a, int atm) {
+static size_t flux_smem_bytes(const AzinvArgs& a, int atm, int corr) {
   size_t d = 2ul * a.n_azi + 4ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 5;
   if (atm == 2) d += 4ul * a.n_leaves + 5ul * a.slab_ne_max + a.hot.nmu + (size_t)a.hot.nmu * a.slab_ne_max;
-  return d * sizeof(double) + 2ul * a.n_leaves * sizeof(int);
+  if (corr == 2) d += 4ul * a.n_leaves + 5ul * a.slab_ne_max + a.els.nmu + (size_t)a.els.nmu * a.slab_ne_max;
+  return d * sizeof(double) + 3ul * a.n_leaves * sizeof(int);
 }
 
 // Doppler spread of log10 Z over one ring allowed for when sizing buffers:
@@ -698,8 +775,9 @@ void azinv_workspace_sizes(const AzinvArgs& a, size_t* leaf_doubles, size_t* hdr
   // ihdr_ints also covers the per-chunk row table: [rings][n_chunks] int2 after the headers
   *leaf_doubles = rings * a.n_img_max * 4 * a.n_leaves;
   *hdr_doubles = rings * kDHdr;
-  *ihdr_ints = rings * kIHdr + rings * 2 * (size_t)((a.n_energies + kNEC - 1) / kNEC);
-  *slab_doubles = (a.hot_atm_ext == 2) ? rings * (size_t)a.hot.nmu * a.slab_rows_ring : 0;
+  *ihdr_ints = rings * kIHdr + 2 * rings * 2 * (size_t)((a.n_energies + kNEC - 1) / kNEC);   // hot + correction tables
+  const int nmu = a.hot.nmu > a.els.nmu ? a.hot.nmu : a.els.nmu;
+  *slab_doubles = (a.hot_atm_ext == 2 || a.else_atm_ext == 2) ? rings * (size_t)nmu * a.slab_rows_ring : 0;
 }
 
 void azinv_slab_budgets(const AtmTable& t, const double* energies, int n_energies, int* rows_chunk,
@@ -717,31 +795,48 @@ void azinv_slab_budgets(const AtmTable& t, const double* energies, int n_energie
   *rows_ring = rr > t.nE ? t.nE : rr;
 }
 
+template <int ATM, int CORR>
+static cudaError_t launch_flux(const AzinvArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(k_azinv_flux<ATM, CORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  k_azinv_flux<ATM, CORR><<<grid, kFluxThreads, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   if (a.n_phases > kFluxThreads) return cudaErrorInvalidValue;
   if (a.n_img_max > kMaxImages || a.n_img_max < 1) return cudaErrorInvalidValue;
   if (!a.ws_leaf || !a.ws_ihdr || !a.ws_hdr || !a.log10_energies) return cudaErrorInvalidValue;
   a.ws_chunk = a.ws_ihdr + (size_t)a.Q * a.n_rings * kIHdr;      // 8-byte aligned: kIHdr is even
   const int atm = a.hot_atm_ext;
+  const int corr = a.corrParams ? a.else_atm_ext : 0;
   if (atm != 1 && atm != 2) return cudaErrorNotSupported;
-  if (atm == 2 && (!a.ws_slab || a.slab_ne_max < 4 || a.slab_rows_ring < 4)) return cudaErrorInvalidValue;
-  const size_t gsm = geom_smem_bytes(a), fsm = flux_smem_bytes(a, atm);
+  if (corr != 0 && corr != 1 && corr != 2) return cudaErrorNotSupported;
+  if (!a.corrParams) a.else_atm_ext = 0;
+  if ((atm == 2 && !a.ws_slab) || (corr == 2 && !a.ws_slab2)) return cudaErrorInvalidValue;
+  if ((atm == 2 || corr == 2) && (a.slab_ne_max < 4 || a.slab_rows_ring < 4)) return cudaErrorInvalidValue;
+  const size_t gsm = geom_smem_bytes(a), fsm = flux_smem_bytes(a, atm, corr);
   if (gsm > 227 * 1024 || fsm > 227 * 1024) return cudaErrorInvalidValue;
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
   dim3 ggrid(a.n_rings, a.Q), fgrid(a.n_rings * n_chunks, a.Q);
   cudaError_t err;
   if (atm == 1) {
     if ((err = cudaFuncSetAttribute(k_azinv_geometry<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(k_azinv_flux<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)) != cudaSuccess) return err;
     k_azinv_geometry<1><<<ggrid, kGeomThreads, gsm, stream>>>(a);
-    k_azinv_flux<1><<<fgrid, kFluxThreads, fsm, stream>>>(a);
   } else {
     if ((err = cudaFuncSetAttribute(k_azinv_geometry<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(k_azinv_flux<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)) != cudaSuccess) return err;
     k_azinv_geometry<2><<<ggrid, kGeomThreads, gsm, stream>>>(a);
-    k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a);
-    k_azinv_flux<2><<<fgrid, kFluxThreads, fsm, stream>>>(a);
+    k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 0);
   }
+  if (corr == 2) k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 1);
+  if ((err = cudaGetLastError()) != cudaSuccess) return err;
+  if (atm == 1 && corr == 0) err = launch_flux<1, 0>(a, fgrid, fsm, stream);
+  else if (atm == 1 && corr == 1) err = launch_flux<1, 1>(a, fgrid, fsm, stream);
+  else if (atm == 1 && corr == 2) err = launch_flux<1, 2>(a, fgrid, fsm, stream);
+  else if (atm == 2 && corr == 0) err = launch_flux<2, 0>(a, fgrid, fsm, stream);
+  else if (atm == 2 && corr == 1) err = launch_flux<2, 1>(a, fgrid, fsm, stream);
+  else err = launch_flux<2, 2>(a, fgrid, fsm, stream);
+  if (err != cudaSuccess) return err;
   err = cudaGetLastError();
   if (err != cudaSuccess) return err;
   if (a.scale_by_energy) {

@@ -28,6 +28,8 @@ struct AzinvArgs {
   const double* radial; const double* r_s_over_r;                  // [Q][R]
   const double* srcParams; int params_per_cell;                    // [Q][R][A][n] or [Q][R][n]
   const int* radiates;                                             // [Q][R][A]
+  const double* corrParams;          // nullptr, or the layout of srcParams: elsewhere correction (pyx:257-268)
+  AtmTable els; int else_atm_ext;    // elsewhere atmosphere for the correction (elsewhere_wrapper.pyx:23-81)
   const double* deflection; const double* cos_alpha; const double* lag;   // [Q][R][N_R]
   const double* maxDeflection; const double* cos_gamma;            // [Q][R]
   const double* energies; const double* leaves; const double* phases;
@@ -47,6 +49,7 @@ struct AzinvArgs {
   double* ws_hdr; int* ws_ihdr;      // per-ring headers (+ per-chunk row table behind ws_ihdr)
   int* ws_chunk;                     // set by the launcher
   double* ws_slab;                   // Num4D: [Q][n_rings][nmu][slab_rows_ring]
+  double* ws_slab2;                  // same for a Num4D elsewhere correction
   unsigned long long* work;          // nullptr or [4]: H half-leaf visits, V visible leaves,
                                      //   RI (ring,image) pairs reaching the phase stage, K radiating cells over RI
 };
@@ -129,6 +132,9 @@ struct MarginalArgs {
   int* status;                       // [B]
 };
 cudaError_t launch_marginal(MarginalArgs a, cudaStream_t stream);
+
+// a10: Interstellar.__call__
+cudaError_t launch_attenuate(const double* att, int n_rows, int n_cols, double* signal, cudaStream_t stream);
 
 // a12: row-wise spline tools (phase_integrator / phase_interpolator / energy_interpolator)
 struct RowSplineArgs {

@@ -196,6 +196,23 @@ cudaError_t launch_precomputation(const int* counts, int n_chan, int n_bins, dou
 }
 
 // ---------------------------------------------------------------------------
+// Interstellar.__call__ (xpsi/Interstellar.py:27-58): signal[i, :] *= attenuation[i]
+// ---------------------------------------------------------------------------
+__global__ void k_attenuate(const double* att, int n_rows, int n_cols, double* signal) {
+  const long n = (long)n_rows * n_cols;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x)
+    signal[t] *= att[t / n_cols];
+}
+
+cudaError_t launch_attenuate(const double* att, int n_rows, int n_cols, double* signal, cudaStream_t stream) {
+  const long n = (long)n_rows * n_cols;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_attenuate<<<blocks, 256, 0, stream>>>(att, n_rows, n_cols, signal);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // Row-wise spline tools: tools/phase_integrator.pyx:23-121, phase_interpolator.pyx:25-98,
 // energy_interpolator.pyx:27-125.  One CTA per signal row; coefficients in shared memory.
 // ---------------------------------------------------------------------------
