@@ -329,3 +329,46 @@ def test_m4_hot_regions_with_elsewhere_correction_and_interstellar():
                                    d[p + "precomp"], d[p + "support"], 1000, 0.0, 1e-8, 1e-3, 10.0, -1e90)[0]
     print("M4 lnL", lnL, "ref", float(d["lnL_total"]), "diff", lnL - float(d["lnL_total"]))
     assert abs(lnL - float(d["lnL_total"])) < LNL_ATOL
+
+
+def test_m3_cst_pdt_members_and_pipeline():
+    """Config 3: CST primary (omission hole) + PDT secondary (superseding + ceding member): three integrator
+    calls, members of a region summed after energy integration (Signal.py:419-429)."""
+    import os
+    from conftest import GOLDEN
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.cellmesh.integrator_for_azimuthal_invariance import integrate
+    from xpsi_b200.pipeline import BatchedLikelihood
+    d = np.load(os.path.join(GOLDEN, "m3_cst_pdt.npz"))
+    table = syn.nsx_like_table()
+    n_mem = int(d["n_members"])
+    for m in range(n_mem):
+        p = "int%d_" % m
+        status, flux = integrate(*_integrate_args(d, p, table))
+        assert status == 0
+        err = _pulse_err(flux, d[p + "flux"])
+        print("M3 member", m, "mesh", d[p + "cellArea"].shape, "flux rel err", err)
+        assert err < PULSE_RTOL
+    matrix, edges = syn.nicer_like_response()[:2]
+    pipe = BatchedLikelihood(member_component=d["member_component"], max_rings=44, max_azi=44, n_rays=512,
+                             energies=d["int0_energies"], leaves=d["int0_leaves"], phases=d["int0_phases"],
+                             hot_atm_ext=2, hot_atmosphere=table, image_order_limit=3, response=matrix,
+                             energy_edges=edges, counts=d["counts"], data_phases=np.linspace(0.0, 1.0, 33),
+                             exposure_time=syn.M2_EXPOSURE, max_batch=4)
+    B = 3
+    batch = pipe.new_batch(B)
+    for b in range(B):
+        batch.omega[b] = d["int0_omega"]; batch.inclination[b] = d["int0_inclination"]; batch.d_sq[b] = d["d_sq"]
+        batch.phase_shifts[b] = d["marg_phase_shifts"]
+        for m in range(n_mem):
+            g = lambda k: d["int%d_%s" % (m, k)]
+            batch.set_member(b, m, g("cellArea"), g("theta"), g("phi"), g("radialCoords_of_parallels"),
+                             g("r_s_over_r"), g("srcCellParams"), g("deflection"), g("cos_alpha"), g("lag"),
+                             g("maxDeflection"), g("cos_gammaArray"))
+    lnL, status = pipe(batch)
+    print("M3 pipeline lnL", lnL, "ref", float(d["lnL_total"]), "status", status)
+    assert (status == 0).all()
+    assert np.max(np.abs(lnL - float(d["lnL_total"]))) < LNL_ATOL
+    flux, folded, expected = pipe.fetch(B)
+    for c in range(2):
+        assert rel_err(folded[1, c], d["marg_components_%d" % c]) < PULSE_RTOL
