@@ -300,13 +300,12 @@ def main_ours(args):
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         import torch.distributed as dist
+        from xpsi_b200.sharding import gather_blocks
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        mine = torch.from_numpy(lnL).cuda()
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)            # the path's only collective: B/G doubles per rank
-        all_lnL = torch.cat(gathered).cpu().numpy()
+        # the path's only collective: one all_gather of B/G lnL + status per rank (NCCL over NVLink)
+        all_lnL, all_status = gather_blocks(lnL, status, B * world, device=torch.device("cuda", local))
     else:
-        all_lnL = lnL
+        all_lnL, all_status = lnL, status
     ms_total, ms_e2e = float(t[0]), float(t[1])
     n_evals_step = B * world
     value = n_evals_step * args.steps / (ms_total * 1e-3)
@@ -314,7 +313,7 @@ def main_ours(args):
 
     if rank != 0:
         return 0
-    ok = bool((status == 0).all())
+    ok = bool((all_status == 0).all())
     refs = [float(w["m2"]["t%d_lnL_total" % (b % w["n_theta"])]) for b in range(min(B, 4))]
     parity = float(max(abs(lnL[b] - refs[b]) for b in range(len(refs))))
     fl = flops_per_eval(work, B, pipe.shape, 2)
