@@ -189,6 +189,31 @@ typedef struct {
   const double* maxDeflection; const double* cos_gamma;                 /* [B*M][max_rings] */
 } xpsi_b200_batch;
 
+/* Parameter-level inputs for models whose hot-region members are simple circular spots (ST, ST-U):
+ * the library then runs the embed (mesh + rays, replacing HotRegion.embed, xpsi/HotRegion.py:1033-1070,
+ * mesh.pyx / mesh_tools.pyx / rays.pyx) on the GPU as well.                                          */
+typedef struct {
+  /* per theta [B]: derived spacetime scalars, xpsi/Spacetime.py:110-188 */
+  const double* R_eq; const double* r_s; const double* epsilon; const double* zeta;
+  const double* omega; const double* inclination; const double* d_sq;
+  const double* phase_shifts;                    /* [B][n_components] cycles                     */
+  /* per member instance [B*M] */
+  const double* colatitude; const double* ang_radius; const double* temperature;
+  const double* phi_shift;                       /* radians added to cell azimuths (pi: antiphased) */
+  double mode_frequency;                         /* Hz                                            */
+  int num_cells, min_sqrt_num_cells, max_sqrt_num_cells;
+} xpsi_b200_spot_batch;
+
+/* embed B parameter vectors on the device (inputs of the next eval_resident) */
+int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200_spot_batch* host);
+/* embed + evaluate + download: theta-level end-to-end call */
+int xpsi_b200_pipeline_eval_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200_spot_batch* host,
+                                  double* lnL, int* status);
+/* fetch the embedded integrator inputs of the last embed (any pointer may be NULL) */
+int xpsi_b200_pipeline_fetch_embed(xpsi_b200_pipeline* p, int B, int* n_rings, double* cellArea, double* phi,
+                                   double* theta, double* radial, double* srcParams, double* cos_gamma,
+                                   double* deflection, double* cos_alpha, double* lag, double* maxDeflection);
+
 xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* cfg, int max_batch);
 void xpsi_b200_pipeline_destroy(xpsi_b200_pipeline* p);
 /* host buffers: copies in, runs, copies lnL/status out (the e2e path) */

@@ -372,3 +372,52 @@ def test_m3_cst_pdt_members_and_pipeline():
     flux, folded, expected = pipe.fetch(B)
     for c in range(2):
         assert rel_err(folded[1, c], d["marg_components_%d" % c]) < PULSE_RTOL
+
+
+def test_gpu_embed_matches_reference_mesh_and_rays(m2):
+    """f1: mesh + rays of circular spots built on the GPU vs the reference's embed (golden fixture)."""
+    from xpsi_b200 import synthetic as syn
+    pipe = _m2_pipeline(m2, max_batch=4)
+    thetas = np.array([m2["t0_theta"], m2["t1_theta"]])
+    sb = syn.m2_spot_batch(pipe, thetas)
+    pipe.embed_spots(sb)
+    e = pipe.fetch_embed(2)
+    for t in range(2):
+        for m in range(2):
+            q = t * 2 + m
+            g = lambda k: m2["t%d_int%d_%s" % (t, m, k)]
+            n = g("cellArea").shape[0]
+            assert e["n_rings"][q] == n
+            full = g("cellArea").max()
+            errs = dict(
+                theta=np.max(np.abs(e["theta"][q, :n] - g("theta")[:, 0])),
+                phi=np.max(np.abs(e["phi"][q, :n, :n] - g("phi"))),
+                radial=np.max(np.abs(e["radial"][q, :n] / g("radialCoords_of_parallels") - 1.0)),
+                cos_gamma=np.max(np.abs(e["cos_gamma"][q, :n] - g("cos_gammaArray"))),
+                params=np.max(np.abs(e["srcParams"][q, :n] - g("srcCellParams")[:, 0, :])),
+                area=np.max(np.abs(e["cellArea"][q, :n, :n] - g("cellArea"))) / full,
+                cos_alpha=np.max(np.abs(e["cos_alpha"][q, :n] - g("cos_alpha"))),
+                deflection=np.max(np.abs(e["deflection"][q, :n] - g("deflection")) / np.maximum(g("deflection"), 1e-3)),
+                lag=np.max(np.abs(e["lag"][q, :n] - g("lag"))) / np.max(np.abs(g("lag"))),
+                maxDeflection=np.max(np.abs(e["maxDeflection"][q, :n] / g("maxDeflection") - 1.0)))
+            print("embed theta", t, "member", m, {k: float("%.2e" % v) for k, v in errs.items()})
+            assert ((e["cellArea"][q, :n, :n] > 0) == (g("cellArea") > 0)).all()
+            assert errs["theta"] < 1e-12 and errs["phi"] < 1e-13 and errs["radial"] < 1e-13
+            assert errs["cos_gamma"] < 1e-13 and errs["params"] < 1e-12
+            assert errs["area"] < 1e-9          # the reference's own quadrature tolerance is 1e-8
+            assert errs["cos_alpha"] < 1e-13 and errs["deflection"] < 1e-11 and errs["lag"] < 1e-10
+            assert errs["maxDeflection"] < 1e-11
+
+
+def test_theta_level_likelihood_with_gpu_embed(m2):
+    """theta -> lnL entirely on the GPU (embed + integrate + fold + likelihood) vs the reference's lnL."""
+    from xpsi_b200 import synthetic as syn
+    pipe = _m2_pipeline(m2, max_batch=8)
+    thetas = np.array([m2["t0_theta"], m2["t1_theta"], m2["t0_theta"]])
+    lnL, status = pipe.eval_spots(syn.m2_spot_batch(pipe, thetas))
+    assert (status == 0).all()
+    for b, t in enumerate((0, 1, 0)):
+        ref = float(m2["t%d_lnL_total" % t])
+        print("theta-level lnL", lnL[b], "ref", ref, "diff", lnL[b] - ref)
+        # mesh areas are only defined to the reference's own 1e-8 quadrature tolerance (DESIGN.md s5.5)
+        assert abs(lnL[b] - ref) < 1e-4

@@ -86,6 +86,16 @@ class Batch(C.Structure):
     ]
 
 
+class SpotBatch(C.Structure):
+    _fields_ = [
+        ("R_eq", c_double_p), ("r_s", c_double_p), ("epsilon", c_double_p), ("zeta", c_double_p),
+        ("omega", c_double_p), ("inclination", c_double_p), ("d_sq", c_double_p), ("phase_shifts", c_double_p),
+        ("colatitude", c_double_p), ("ang_radius", c_double_p), ("temperature", c_double_p),
+        ("phi_shift", c_double_p), ("mode_frequency", C.c_double),
+        ("num_cells", C.c_int), ("min_sqrt_num_cells", C.c_int), ("max_sqrt_num_cells", C.c_int),
+    ]
+
+
 def _proto(name, restype, argtypes):
     f = getattr(lib, name)
     f.restype = restype
@@ -135,6 +145,9 @@ _proto("xpsi_b200_pipeline_download", C.c_int, [C.c_void_p, C.c_int, c_double_p,
 _proto("xpsi_b200_pipeline_fetch", C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p])
 _proto("xpsi_b200_fp64_peak_tflops", C.c_int, [c_double_p])
 _proto("xpsi_b200_pipeline_work_counters", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)])
+_proto("xpsi_b200_pipeline_embed_spots", C.c_int, [C.c_void_p, C.c_int, C.POINTER(SpotBatch)])
+_proto("xpsi_b200_pipeline_eval_spots", C.c_int, [C.c_void_p, C.c_int, C.POINTER(SpotBatch), c_double_p, c_int_p])
+_proto("xpsi_b200_pipeline_fetch_embed", C.c_int, [C.c_void_p, C.c_int, c_int_p] + [c_double_p] * 10)
 _proto("xpsi_b200_pipeline_stage_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)])
 
 EXPORTED = [

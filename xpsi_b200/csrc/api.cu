@@ -501,7 +501,10 @@ struct xpsi_b200_pipeline {
   Dev<int> chan_status, status_q, status;
   Dev<unsigned long long> work;
   Dev<double> ws_leaf, ws_hdr, ws_slab; Dev<int> ws_ihdr;
+  // embed inputs / scratch
+  Dev<double> e_Req, e_rs, e_eps, e_zeta, e_colat, e_rad, e_temp, e_phish, e_maxAlpha;
   int count_work = 0;
+  int embed_status_valid = 0;        // status[] already carries embed failures for this batch
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float stage_ms[4] = {0, 0, 0, 0};
 };
@@ -515,15 +518,16 @@ __global__ void k_expand_scalars(const double* omega, const double* incl, int B,
   omega_q[q] = omega[q / M]; incl_q[q] = incl[q / M];
 }
 
-__global__ void k_member_status(const int* status_q, int B, int M, int* status) {
+__global__ void k_member_status(const int* status_q, int B, int M, int* status, int keep) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  int s = 0;
+  int s = keep ? status[b] : 0;
   for (int m = 0; m < M; ++m) if (status_q[b * M + m] != 0 && s == 0) s = status_q[b * M + m];
   status[b] = s;
 }
 
 int pipeline_upload(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch* h) {
+  p->embed_status_valid = 0;
   const xpsi_b200_pipeline_config& c = p->cfg;
   const size_t Q = (size_t)B * c.n_members, R = c.max_rings, A = c.max_azi;
   CK(p->omega.upload(h->omega, B)); CK(p->inclination.upload(h->inclination, B));
@@ -594,7 +598,8 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   if (e != cudaSuccess) return cuda_fail(e, "launch_fold");
   CK(cudaEventRecord(p->ev[3], g_stream));
 
-  k_member_status<<<(B + 127) / 128, 128, 0, g_stream>>>(p->status_q.p, B, M, p->status.p);
+  k_member_status<<<(B + 127) / 128, 128, 0, g_stream>>>(p->status_q.p, B, M, p->status.p, p->embed_status_valid);
+  p->embed_status_valid = 0;
   xb::MarginalArgs m;
   memset(&m, 0, sizeof(m));
   m.B = B; m.n_comp = C; m.n_chan = c.n_chan; m.n_phases = c.n_phases; m.n_bins = c.n_bins;
@@ -725,6 +730,66 @@ int xpsi_b200_pipeline_eval(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch*
   rc = pipeline_run(p, B);
   if (rc) return rc;
   return xpsi_b200_pipeline_download(p, B, lnL, status);
+}
+
+int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200_spot_batch* h) {
+  if (!p || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
+  const xpsi_b200_pipeline_config& c = p->cfg;
+  if (c.n_params != 2) return fail(XPSI_B200_EUNSUPPORTED, "spot embed needs n_params == 2 (log T, log g)");
+  const size_t M = c.n_members, Q = (size_t)B * M;
+  CK(p->omega.upload(h->omega, B)); CK(p->inclination.upload(h->inclination, B)); CK(p->d_sq.upload(h->d_sq, B));
+  CK(p->shifts.upload(h->phase_shifts, (size_t)B * c.n_components));
+  CK(p->e_Req.upload(h->R_eq, B)); CK(p->e_rs.upload(h->r_s, B)); CK(p->e_eps.upload(h->epsilon, B));
+  CK(p->e_zeta.upload(h->zeta, B)); CK(p->e_colat.upload(h->colatitude, Q)); CK(p->e_rad.upload(h->ang_radius, Q));
+  CK(p->e_temp.upload(h->temperature, Q)); CK(p->e_phish.upload(h->phi_shift, Q));
+  CK(p->e_maxAlpha.alloc((size_t)p->max_batch * M * c.max_rings));
+  CK(cudaMemsetAsync(p->status.p, 0, B * sizeof(int), g_stream));
+  xb::EmbedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.M = (int)M; a.max_rings = c.max_rings; a.max_azi = c.max_azi; a.n_rays = c.n_rays; a.n_params = c.n_params;
+  a.num_cells = h->num_cells; a.min_sqrt = h->min_sqrt_num_cells; a.max_sqrt = h->max_sqrt_num_cells;
+  a.mode_frequency = h->mode_frequency;
+  a.R_eq = p->e_Req.p; a.r_s = p->e_rs.p; a.epsilon = p->e_eps.p; a.zeta = p->e_zeta.p;
+  a.colatitude = p->e_colat.p; a.ang_radius = p->e_rad.p; a.temperature = p->e_temp.p; a.phi_shift = p->e_phish.p;
+  a.n_rings = p->n_rings.p; a.n_azi = p->n_azi.p; a.cellArea = p->cellArea.p; a.phi = p->phi.p; a.theta = p->theta.p;
+  a.radial = p->radial.p; a.r_s_over_r = p->rsr.p; a.srcParams = p->params.p; a.cos_gamma = p->cgamma.p;
+  a.maxAlpha = p->e_maxAlpha.p; a.deflection = p->defl.p; a.cos_alpha = p->calpha.p; a.lag = p->lag.p;
+  a.maxDeflection = p->maxd.p; a.status = p->status.p;
+  cudaError_t e = xb::launch_embed_spots(a, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_embed_spots");
+  p->embed_status_valid = 1;
+  g_launches += 2;
+  return 0;
+}
+
+int xpsi_b200_pipeline_eval_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200_spot_batch* h, double* lnL,
+                                  int* status) {
+  int rc = xpsi_b200_pipeline_embed_spots(p, B, h);
+  if (rc) return rc;
+  rc = pipeline_run(p, B);
+  if (rc) return rc;
+  return xpsi_b200_pipeline_download(p, B, lnL, status);
+}
+
+int xpsi_b200_pipeline_fetch_embed(xpsi_b200_pipeline* p, int B, int* n_rings, double* cellArea, double* phi,
+                                   double* theta, double* radial, double* srcParams, double* cos_gamma,
+                                   double* deflection, double* cos_alpha, double* lag, double* maxDeflection) {
+  if (!p || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
+  const xpsi_b200_pipeline_config& c = p->cfg;
+  const size_t Q = (size_t)B * c.n_members, R = c.max_rings, A = c.max_azi;
+  if (n_rings) CK(p->n_rings.download(n_rings, Q));
+  if (cellArea) CK(p->cellArea.download(cellArea, Q * R * A));
+  if (phi) CK(p->phi.download(phi, Q * R * A));
+  if (theta) CK(p->theta.download(theta, Q * R));
+  if (radial) CK(p->radial.download(radial, Q * R));
+  if (srcParams) CK(p->params.download(srcParams, Q * R * c.n_params));
+  if (cos_gamma) CK(p->cgamma.download(cos_gamma, Q * R));
+  if (deflection) CK(p->defl.download(deflection, Q * R * c.n_rays));
+  if (cos_alpha) CK(p->calpha.download(cos_alpha, Q * R * c.n_rays));
+  if (lag) CK(p->lag.download(lag, Q * R * c.n_rays));
+  if (maxDeflection) CK(p->maxd.download(maxDeflection, Q * R));
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
 }
 
 int xpsi_b200_pipeline_fetch(xpsi_b200_pipeline* p, int B, double* flux, double* folded, double* expected) {

@@ -1,0 +1,382 @@
+// GPU "embed": cell mesh of a circular hot spot and its rays, from model parameters.
+//
+// Replaces, for a simple circular superseding region away from the poles (the ST / ST-U
+// families: no omission, no ceding member), the per-parameter-vector producer of all
+// integrator inputs:
+//   xpsi/HotRegion.py:774-870  __construct_cellMesh -> mesh_tools.allocate_cells (:892-1000),
+//                              mesh.construct_spot_cellMesh (mesh.pyx:18-417)
+//   xpsi/HotRegion.py:903-951  __compute_rays -> rays.compute_rays (rays.pyx:249-390)
+//   xpsi/HotRegion.py:880-901  __calibrate_lag;  :953-1017 __compute_cellParamVecs
+//   surface_radiation_field/effective_gravity_universal.pyx
+// The reference evaluates the underlying 1-D integrals with adaptive GSL rules (CQUAD at
+// epsrel 1e-8 for the mesh, QAG-GK61 at 1e-12 for rays); here they are fixed-order
+// Gauss-Legendre rules on intervals split at the integrand's kinks, with a sqrt
+// substitution where the spot boundary is tangent to a parallel -- converged to <= 1e-12,
+// which is tighter than the reference's own tolerance.  Discretisation choices that are
+// *not* converged quantities are reproduced exactly: the 1000-node area table and its
+// Steffen inverse interpolation for the ring parallels, the equal-area ring/cell layout,
+// the 5-point boundary-cell test, the cos(alpha) ray grid.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace xb {
+
+__constant__ double c_gl16_x[16] = {-9.89400934991649939e-01, -9.44575023073232600e-01, -8.65631202387831755e-01, -7.55404408355002999e-01, -6.17876244402643771e-01, -4.58016777657227370e-01, -2.81603550779258915e-01, -9.50125098376374405e-02, 9.50125098376374405e-02, 2.81603550779258915e-01, 4.58016777657227370e-01, 6.17876244402643771e-01, 7.55404408355002999e-01, 8.65631202387831755e-01, 9.44575023073232600e-01, 9.89400934991649939e-01};
+__constant__ double c_gl16_w[16] = {2.71524594117541762e-02, 6.22535239386474565e-02, 9.51585116824926053e-02, 1.24628971255534071e-01, 1.49595988816576708e-01, 1.69156519395002647e-01, 1.82603415044923639e-01, 1.89450610455068641e-01, 1.89450610455068641e-01, 1.82603415044923639e-01, 1.69156519395002647e-01, 1.49595988816576708e-01, 1.24628971255534071e-01, 9.51585116824926053e-02, 6.22535239386474565e-02, 2.71524594117541762e-02};
+__constant__ double c_gl32_x[32] = {-9.97263861849481570e-01, -9.85611511545268382e-01, -9.64762255587506390e-01, -9.34906075937739667e-01, -8.96321155766052091e-01, -8.49367613732569970e-01, -7.94483795967942386e-01, -7.32182118740289711e-01, -6.63044266930215231e-01, -5.87715757240762304e-01, -5.06899908932229359e-01, -4.21351276130635333e-01, -3.31868602282127667e-01, -2.39287362252137065e-01, -1.44471961582796488e-01, -4.83076656877383243e-02, 4.83076656877383243e-02, 1.44471961582796488e-01, 2.39287362252137065e-01, 3.31868602282127667e-01, 4.21351276130635333e-01, 5.06899908932229359e-01, 5.87715757240762304e-01, 6.63044266930215231e-01, 7.32182118740289711e-01, 7.94483795967942386e-01, 8.49367613732569970e-01, 8.96321155766052091e-01, 9.34906075937739667e-01, 9.64762255587506390e-01, 9.85611511545268382e-01, 9.97263861849481570e-01};
+__constant__ double c_gl32_w[32] = {7.01861000947050576e-03, 1.62743947309057432e-02, 2.53920653092620241e-02, 3.42738629130217645e-02, 4.28358980222268357e-02, 5.09980592623760914e-02, 5.86840934785355650e-02, 6.58222227763616829e-02, 7.23457941088483381e-02, 7.81938957870702278e-02, 8.33119242269467070e-02, 8.76520930044037833e-02, 9.11738786957637798e-02, 9.38443990808045109e-02, 9.56387200792747083e-02, 9.65400885147276594e-02, 9.65400885147276594e-02, 9.56387200792747083e-02, 9.38443990808045109e-02, 9.11738786957637798e-02, 8.76520930044037833e-02, 8.33119242269467070e-02, 7.81938957870702278e-02, 7.23457941088483381e-02, 6.58222227763616829e-02, 5.86840934785355650e-02, 5.09980592623760914e-02, 4.28358980222268357e-02, 3.42738629130217645e-02, 2.53920653092620241e-02, 1.62743947309057432e-02, 7.01861000947050576e-03};
+
+// ---- oblate surface (AlGendy & Morsink 2014), mesh_tools.pyx:18-120 --------------------
+__device__ __forceinline__ double radius_normalised(double mu, double eps, double zeta) {
+  return 1.0 + eps * (-0.788 + 1.030 * zeta) * mu * mu;
+}
+__device__ __forceinline__ double f_theta(double mu, double rn, double eps, double zeta) {
+  const double d = -2.0 * eps * (-0.788 + 1.030 * zeta) * mu * sqrt(1.0 - mu * mu);
+  return d / (rn * sqrt(1.0 - 2.0 * zeta / rn));
+}
+// surface-area element per unit azimuth / R_eq^2 (mesh_tools.pyx:99-120); av=1 weights by theta
+__device__ __forceinline__ double area_element(double theta, double eps, double zeta, int av) {
+  if (are_equal(theta, 0.0)) return 0.0;
+  const double mu = cos(theta);
+  const double rn = radius_normalised(mu, eps, zeta);
+  const double f = f_theta(mu, rn, eps, zeta);
+  const double v = rn * rn * sqrt(1.0 + f * f) * sin(theta);
+  return av ? theta * v : v;
+}
+__device__ __forceinline__ double integrate_area(double lo, double hi, double eps, double zeta, int av) {
+  const double h = 0.5 * (hi - lo), m = 0.5 * (hi + lo);
+  double s = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < 32; ++k) s += c_gl32_w[k] * area_element(m + h * c_gl32_x[k], eps, zeta, av);
+  return h * s;
+}
+// effective_gravity_universal.pyx:12-71
+__device__ __forceinline__ double effective_gravity(double mu, double R_eq, double x, double eps) {
+  const double g_0 = x * kC * kC / (R_eq * sqrt(1.0 - 2.0 * x));
+  const double esq = eps, esqsq = eps * eps;
+  const double c_e = -0.791 + 0.776 * x, c_p = 1.138 - 1.431 * x;
+  const double d_e = (-1.315 + 2.431 * x) * esq * x, d_p = (0.653 - 2.864 * x) * esq * x;
+  const double d_60 = (13.47 - 27.13 * x) * esq * x;
+  const double f_e = -1.172 * x * esqsq, f_p = 0.975 * x * esqsq;
+  double g = 1.0;
+  g += (c_e + d_e + f_e) * esq * (1.0 - mu * mu);
+  g += (c_p + d_p + f_p - d_60) * esq * mu * mu;
+  g += d_60 * esq * fabs(mu);
+  return log10(g * g_0) + 2.0;
+}
+__device__ __forceinline__ double eval_psi(double theta, double phi, double THETA) {   // mesh_tools.pyx:156-160
+  return acos(cos(THETA) * cos(theta) + sin(THETA) * sin(theta) * cos(phi));
+}
+// half-width in azimuth of the spot at colatitude theta (mesh_tools.pyx:265-274)
+__device__ __forceinline__ double spot_halfwidth(double theta, double cosT, double sinT, double cos_rho) {
+  double c = (cos_rho - cosT * cos(theta)) / (sinT * sin(theta));
+  if (c > 1.0) c = 1.0;
+  if (c < -1.0) c = -1.0;
+  return acos(c);
+}
+
+// integral over theta in [s0, s1] of g(theta) with optional sqrt substitution at either end
+template <class G>
+__device__ __forceinline__ double gl16_piece(const G& g, double s0, double s1, bool sing0, bool sing1) {
+  double tot = 0.0;
+  if (!sing0 && !sing1) {
+    const double h = 0.5 * (s1 - s0), m = 0.5 * (s1 + s0);
+    for (int k = 0; k < 16; ++k) tot += c_gl16_w[k] * g(m + h * c_gl16_x[k]);
+    return h * tot;
+  }
+  const double mid = (sing0 && sing1) ? 0.5 * (s0 + s1) : (sing0 ? s1 : s0);
+  if (sing0) {             // theta = s0 + t^2
+    const double L = sqrt(mid - s0), h = 0.5 * L;
+    double s = 0.0;
+    for (int k = 0; k < 16; ++k) { const double t = h + h * c_gl16_x[k]; s += c_gl16_w[k] * g(s0 + t * t) * 2.0 * t; }
+    tot += h * s;
+  }
+  if (sing1) {             // theta = s1 - t^2
+    const double L = sqrt(s1 - mid), h = 0.5 * L;
+    double s = 0.0;
+    for (int k = 0; k < 16; ++k) { const double t = h + h * c_gl16_x[k]; s += c_gl16_w[k] * g(s1 - t * t) * 2.0 * t; }
+    tot += h * s;
+  }
+  return tot;
+}
+
+// area of cell [tha,thb] x [pa,pb] inside the spot / R_eq^2 (mesh_tools.pyx:303-388,429-473, superRadius = 0)
+__device__ double spot_cell_area(double tha, double thb, double pa, double pb, double eps, double zeta,
+                                 double TH, double rho) {
+  const double cosT = cos(TH), sinT = sin(TH), cos_rho = cos(rho);
+  const double lo = fmax(tha, TH - rho), hi = fmin(thb, TH + rho);
+  if (!(hi > lo)) return 0.0;
+  auto g = [&](double th) -> double {
+    const double a = spot_halfwidth(th, cosT, sinT, cos_rho);
+    const double ov = fmin(pb, a) - fmax(pa, -a);
+    return ov > 0.0 ? ov * area_element(th, eps, zeta, 0) : 0.0;
+  };
+  double bp[6];
+  int nb = 0;
+  bp[nb++] = lo; bp[nb++] = hi;
+  for (int s = 0; s < 2; ++s) {          // colatitudes where the spot boundary crosses phi = pa, pb
+    const double ph = s == 0 ? pa : pb;
+    const double A = cosT, B = sinT * cos(ph), Rn = sqrt(A * A + B * B);
+    if (fabs(cos_rho) <= Rn) {
+      const double base = atan2(B, A), d = acos(cos_rho / Rn);
+      if (base - d > lo && base - d < hi) bp[nb++] = base - d;
+      if (base + d > lo && base + d < hi) bp[nb++] = base + d;
+    }
+  }
+  for (int i = 1; i < nb; ++i) {         // insertion sort
+    const double v = bp[i];
+    int j = i - 1;
+    while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; --j; }
+    bp[j + 1] = v;
+  }
+  double tot = 0.0;
+  for (int i = 0; i + 1 < nb; ++i) {
+    const double s0 = bp[i], s1 = bp[i + 1];
+    if (!(s1 - s0 > 1.0e-15)) continue;
+    const bool sing0 = fabs(s0 - (TH - rho)) < 1.0e-14 || fabs(s0 - (TH + rho)) < 1.0e-14;
+    const bool sing1 = fabs(s1 - (TH - rho)) < 1.0e-14 || fabs(s1 - (TH + rho)) < 1.0e-14;
+    tot += gl16_piece(g, s0, s1, sing0, sing1);
+  }
+  return tot;
+}
+
+constexpr int kMeshThreads = 256;
+constexpr int kAreaNodes = 1000;          // mesh.pyx:40,88
+
+// One CTA per member instance q.
+__global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
+  const int q = blockIdx.x, b = q / a.M, tid = threadIdx.x;
+  const double R_eq = a.R_eq[b], eps = a.epsilon[b], zeta = a.zeta[b], r_s = a.r_s[b];
+  const double TH = a.colatitude[q], rho = a.ang_radius[q];
+  __shared__ double s_area[kAreaNodes], s_colat[kAreaNodes];
+  __shared__ double s_par[128], s_theta[128];
+  __shared__ double s_boxA, s_spotA;
+  __shared__ int s_n;
+  const double lo = TH - rho, hi = TH + rho;
+  if (lo < 0.0 || hi > kPi || !(rho > 0.0)) {        // polar cap: polar_mesh.pyx, not covered
+    if (tid == 0) { a.n_rings[q] = 0; a.n_azi[q] = 0; atomicExch(a.status + b, kUnsupported); }
+    return;
+  }
+  const double bphi = asin(sin(rho) / sin(TH));                     // mesh.pyx:59
+  // ---- allocate_cells (mesh_tools.pyx:892-1000): bounding-box area vs spot area ------------
+  if (tid < 32) {
+    const double h = 0.5 * (hi - lo), m = 0.5 * (hi + lo);
+    double v = c_gl32_w[tid] * area_element(m + h * c_gl32_x[tid], eps, zeta, 0);
+    v = warp_sum(v) * h;
+    // spot area: azimuthal width 2a(theta); sqrt substitution at both tangent parallels
+    const double cosT = cos(TH), sinT = sin(TH), cos_rho = cos(rho);
+    const double L = sqrt(m - lo), hh = 0.5 * L;
+    const double t = hh + hh * c_gl32_x[tid];
+    double s = c_gl32_w[tid] * 2.0 * t *
+               (2.0 * spot_halfwidth(lo + t * t, cosT, sinT, cos_rho) * area_element(lo + t * t, eps, zeta, 0) +
+                2.0 * spot_halfwidth(hi - t * t, cosT, sinT, cos_rho) * area_element(hi - t * t, eps, zeta, 0));
+    s = warp_sum(s) * hh;
+    if (tid == 0) {
+      s_boxA = 2.0 * bphi * v;
+      s_spotA = s;
+      double spotA = s;
+      if (are_equal(spotA * R_eq * R_eq, 0.0)) spotA = s_boxA / 1000.0;
+      double sq = ceil(sqrt((double)a.num_cells * s_boxA / spotA));
+      if (sq < a.min_sqrt) sq = a.min_sqrt; else if (sq > a.max_sqrt) sq = a.max_sqrt;
+      int n = (int)sq;
+      if (n % 2 != 0) n += 1;
+      s_n = n;
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n > a.max_rings || n > 128) {
+    if (tid == 0) { a.n_rings[q] = 0; a.n_azi[q] = 0; atomicExch(a.status + b, kUnsupported); }
+    return;
+  }
+  const double cellA = s_boxA / (double)(n * n);                    // per R_eq^2
+  const double dphi = 2.0 * bphi / (double)n;
+  const double eta = cellA / dphi;
+  // ---- equal-area parallels: 1000-node area table + Steffen inverse (mesh.pyx:88-131) -------
+  for (int i = tid; i < kAreaNodes; i += kMeshThreads) {
+    const double c = hi + (lo - hi) * ((double)i / (double)(kAreaNodes - 1));    // linspace(hi, lo, 1000)
+    s_colat[i] = (i == kAreaNodes - 1) ? lo : c;
+    s_area[i] = integrate_area(s_colat[i], hi, eps, zeta, 0);
+  }
+  __syncthreads();
+  for (int i = tid; i < n - 1; i += kMeshThreads) {
+    const double target = (double)n * eta - (double)(i + 1) * eta;
+    // the reference accumulates i_eta -= eta; reproduce the same rounding sequence
+    double ie = (double)n * eta;
+    for (int k = 0; k <= i; ++k) ie -= eta;
+    (void)target;
+    const int idx = interval_search(s_area, kAreaNodes, ie);
+    double val, der;
+    steffen_eval(s_area, s_colat, kAreaNodes, idx, ie, &val, &der);
+    s_par[i] = val;
+  }
+  __syncthreads();
+  // ---- rings (mesh.pyx:226-254) -----------------------------------------------------------------
+  const long ring0 = (long)q * a.max_rings;
+  for (int i = tid; i < n; i += kMeshThreads) {
+    const double l = (i == 0) ? lo : s_par[i - 1];
+    const double u = (i == n - 1) ? hi : s_par[i];
+    const double th = integrate_area(l, u, eps, zeta, 1) / eta;
+    s_theta[i] = th;
+    const double mu = cos(th);
+    const double rn = radius_normalised(mu, eps, zeta);
+    const double f = f_theta(mu, rn, eps, zeta);
+    const double cg = 1.0 / sqrt(1.0 + f * f);
+    a.theta[ring0 + i] = th;
+    a.radial[ring0 + i] = rn * R_eq;
+    a.r_s_over_r[ring0 + i] = r_s / (rn * R_eq);                   // HotRegion.py:913
+    a.cos_gamma[ring0 + i] = cg;
+    a.maxAlpha[ring0 + i] = kHalfPi + acos(cg);                     // mesh.pyx:253
+    a.srcParams[(ring0 + i) * 2 + 0] = a.temperature[q];            // HotRegion.py:965-994
+    a.srcParams[(ring0 + i) * 2 + 1] = effective_gravity(mu, R_eq, zeta, eps);
+  }
+  if (tid == 0) { a.n_rings[q] = n; a.n_azi[q] = n; }
+  __syncthreads();
+  // ---- cells (mesh.pyx:255-352 with superRadius = 0; mirror symmetry in azimuth) -----------------
+  const double phi_shift = a.phi_shift[q];
+  const int half = n / 2;
+  for (int t = tid; t < n * half; t += kMeshThreads) {
+    const int i = t / half, j = t - i * half;
+    const double l = (i == 0) ? lo : s_par[i - 1];
+    const double u = (i == n - 1) ? hi : s_par[i];
+    const double left = -bphi + dphi * (double)j;      // the reference accumulates leftmost += delta_phi
+    double lft = -bphi;
+    for (int k = 0; k < j; ++k) lft += dphi;
+    (void)left;
+    const double right = lft + dphi;
+    const int p1 = eval_psi(l, lft, TH) <= rho, p2 = eval_psi(u, lft, TH) <= rho;
+    const int p3 = eval_psi(l, right, TH) <= rho, p4 = eval_psi(u, right, TH) <= rho;
+    const int p5 = eval_psi(s_theta[i], lft + 0.5 * dphi, TH) <= rho;
+    double area = 0.0;
+    if (!(p1 == p2 && p2 == p3 && p3 == p4 && p4 == p5)) area = spot_cell_area(l, u, lft, right, eps, zeta, TH, rho);
+    else if (p5) area = cellA;
+    area *= R_eq * R_eq;
+    const long row = (ring0 + i) * a.max_azi;
+    a.cellArea[row + j] = area;
+    a.cellArea[row + n - 1 - j] = area;
+  }
+  // azimuths: linspace(-bphi + dphi/2, bphi - dphi/2, n) (+ pi if antiphased), HotRegion.py:834-837
+  for (int t = tid; t < n * n; t += kMeshThreads) {
+    const int i = t / n, j = t - i * n;
+    const double start = -bphi + 0.5 * dphi, stop = bphi - 0.5 * dphi;
+    const double step = (stop - start) / (double)(n - 1);
+    double ph = (j == n - 1) ? stop : start + step * (double)j;     // numpy.linspace
+    a.phi[(ring0 + i) * a.max_azi + j] = ph + phi_shift;
+  }
+  // zero the padding of this instance's cell rows
+  for (int t = tid; t < a.max_rings * a.max_azi; t += kMeshThreads) {
+    const int i = t / a.max_azi, j = t - i * a.max_azi;
+    if (i >= n || j >= n) a.cellArea[ring0 * a.max_azi + t] = 0.0;
+  }
+}
+
+// ---- rays (rays.pyx:61-247) ---------------------------------------------------------------------
+__device__ __forceinline__ double in_core(double x, double rc) {
+  const double o = 1.0 - x * x;
+  return 2.0 - x * x - o * o / (rc - 1.0);
+}
+__device__ __forceinline__ void ray_integrals(double cos_alpha, double r_s, double u, double* defl, double* lag) {
+  const double sas = 1.0 - cos_alpha * cos_alpha;
+  const double sa = sqrt(sas);
+  const double alpha = acos(cos_alpha);
+  const double b = sa / (u * sqrt(1.0 - u));
+  const double b_ph = 3.0 * sqrt(3.0) / 2.0;
+  if (b <= b_ph) {
+    const double Rr = 1.0 / u;
+    double sd = 0.0, sl = 0.0;
+    for (int k = 0; k < 32; ++k) {
+      const double x = 0.5 + 0.5 * c_gl32_x[k];
+      const double o = 1.0 - x * x;
+      const double f = sqrt(1.0 - sas + x * x * sas * (2.0 - x * x - o * o / (Rr - 1.0)));
+      sd += c_gl32_w[k] * (x / f);
+      sl += c_gl32_w[k] * (x / (f + f * f));
+    }
+    *defl = 0.5 * sd * 2.0 * b * u;
+    *lag = 0.5 * sl * 2.0 * b * b * u * r_s;
+  } else {
+    double rc, wR;
+    if (alpha <= kHalfPi && are_equal(sa, 1.0)) { rc = 1.0 / u; wR = 0.0; }
+    else {
+      rc = 2.0 * b * cos((atan(sqrt(4.0 * b * b / 27.0 - 1.0)) - kPi) / 3.0) / sqrt(3.0);
+      wR = sqrt(1.0 - rc * u);
+      if (wR != wR) wR = 0.0;
+    }
+    double d0 = 0.0, l0 = 0.0;                       // integrals over [wR, 1]
+    {
+      const double h = 0.5 * (1.0 - wR), m = 0.5 * (1.0 + wR);
+      for (int k = 0; k < 32; ++k) {
+        const double x = m + h * c_gl32_x[k];
+        const double X = 1.0 / sqrt(in_core(x, rc));
+        d0 += c_gl32_w[k] * X;
+        l0 += c_gl32_w[k] * (X * X / (x + X));
+      }
+      d0 *= h; l0 *= h;
+    }
+    if (alpha <= kHalfPi) {
+      *defl = d0 * 2.0 * b / rc;
+      *lag = l0 * 2.0 * b * b * r_s / rc;
+    } else {
+      double d1 = 0.0, l1 = 0.0;                     // integrals over [0, 1]
+      for (int k = 0; k < 32; ++k) {
+        const double x = 0.5 + 0.5 * c_gl32_x[k];
+        const double X = 1.0 / sqrt(in_core(x, rc));
+        d1 += c_gl32_w[k] * X;
+        l1 += c_gl32_w[k] * (X * X / (x + X));
+      }
+      d1 *= 0.5; l1 *= 0.5;
+      *defl = 2.0 * b * (2.0 * d1 - d0) / rc;
+      *lag = 2.0 * b * b * r_s * (2.0 * l1 - l0) / rc;
+      *lag += 2.0 * r_s * (1.0 / u - rc + log((1.0 / u - 1.0) / (rc - 1.0)));
+    }
+  }
+  *lag /= kC;
+}
+
+// grid (ring, q); threads over rays
+__global__ void __launch_bounds__(128) k_rays(EmbedArgs a) {
+  const int i = blockIdx.x, q = blockIdx.y, b = q / a.M;
+  const int n = a.n_rings[q];
+  if (i >= n) return;
+  const long ring = (long)q * a.max_rings + i;
+  const int N_R = a.n_rays;
+  const double u = a.r_s_over_r[ring], r_s = a.r_s[b];
+  double extreme = kHalfPi;                                        // rays.pyx:310-318
+  if (u < 2.0 / 3.0) extreme = kPi - asin(sqrt(1.0 - u) * (3.0 * sqrt(3.0) / 2.0) * u);
+  else if (!are_equal(u, 2.0 / 3.0)) extreme = asin(sqrt(1.0 - u) * (3.0 * sqrt(3.0) / 2.0) * u);
+  double maxAlpha = a.maxAlpha[ring];
+  if (maxAlpha >= (1.0 - 1.0e-8) * extreme) maxAlpha = (1.0 - 1.0e-8) * extreme;
+  const double inc = (1.0 - cos(maxAlpha)) / ((double)N_R - 1.0);
+  // lag calibration (HotRegion.py:880-901)
+  const double R_i = a.R_eq[b] / r_s;
+  const double Ccal = ((1.0 / u - R_i) + log((1.0 / u - 1.0) / (R_i - 1.0))) * (r_s / kC);
+  const double two_pi_f = kTwoPi * a.mode_frequency;
+  __shared__ int s_bad;
+  __shared__ double s_last[2];
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < N_R; j += blockDim.x) {
+    double ca = 1.0 - (double)j * inc, d = 0.0, l = 0.0;
+    if (j == 0) ca = 1.0;
+    else ray_integrals(ca, r_s, u, &d, &l);
+    if (d != d || l != l || d < 0.0) s_bad = 1;                    // the reference patches such rays linearly
+    a.cos_alpha[ring * N_R + j] = ca;
+    a.deflection[ring * N_R + j] = d;
+    a.lag[ring * N_R + j] = (l - Ccal) * two_pi_f;
+    if (j >= N_R - 2) s_last[j - (N_R - 2)] = d;
+    if (j == N_R - 1) a.maxDeflection[ring] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && (s_bad || !(s_last[1] > s_last[0]))) atomicExch(a.status + b, kNumericalError);   // rays.pyx:327-331
+}
+
+cudaError_t launch_embed_spots(EmbedArgs a, cudaStream_t stream) {
+  if (a.max_rings > 128 || a.n_params != 2) return cudaErrorInvalidValue;
+  k_spot_mesh<<<a.B * a.M, kMeshThreads, 0, stream>>>(a);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  dim3 grid(a.max_rings, a.B * a.M);
+  k_rays<<<grid, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace xb

@@ -78,6 +78,23 @@ struct TinvArgs {
 cudaError_t launch_integrate_tinv(TinvArgs a, cudaStream_t stream);
 int tinv_slab_rows(const AtmTable& t, const double* host_energies, int n_energies);
 
+// f1: embed of circular hot spots (mesh + rays) straight into the integrator's batch arrays
+struct EmbedArgs {
+  int B, M, max_rings, max_azi, n_rays, n_params;
+  int num_cells; double min_sqrt, max_sqrt;      // HotRegion(sqrt_num_cells^2, min_sqrt_num_cells, max_sqrt_num_cells)
+  double mode_frequency;                          // Photosphere['mode_frequency'] (HotRegion.py:887)
+  const double* R_eq; const double* r_s; const double* epsilon; const double* zeta;      // [B] Spacetime.py:110-188
+  const double* colatitude; const double* ang_radius; const double* temperature;        // [B*M]
+  const double* phi_shift;                        // [B*M] added to cell azimuths (pi if antiphased)
+  // outputs: the integrator's per-instance inputs (padded layout of AzinvArgs)
+  int* n_rings; int* n_azi;
+  double* cellArea; double* phi; double* theta; double* radial; double* r_s_over_r; double* srcParams;
+  double* cos_gamma; double* maxAlpha;
+  double* deflection; double* cos_alpha; double* lag; double* maxDeflection;
+  int* status;                                    // [B]
+};
+cudaError_t launch_embed_spots(EmbedArgs a, cudaStream_t stream);
+
 // a9: tools/energy_integrator.pyx:27-114, one spline per (signal q, phase column)
 struct EnergyIntegArgs {
   int Q, n_energies, n_phases, n_in;

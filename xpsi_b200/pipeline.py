@@ -92,6 +92,52 @@ class HostBatch:
         return s
 
 
+class SpotBatch:
+    """Parameter-level inputs for B parameter vectors whose M hot-region members are simple circular spots.
+
+    Per theta: the derived spacetime scalars of ``xpsi.Spacetime`` (xpsi/Spacetime.py:110-188); per member:
+    colatitude, angular radius, log10 temperature and the azimuth offset (pi for an antiphased region,
+    xpsi/HotRegion.py:834-837).  The mesh and rays are then built on the GPU.
+    """
+
+    def __init__(self, B, M, C_, mode_frequency, num_cells=1024, min_sqrt_num_cells=10, max_sqrt_num_cells=64):
+        self.B, self.M = B, M
+        z = lambda *shape: np.zeros(shape, dtype=np.float64)
+        self.R_eq, self.r_s, self.epsilon, self.zeta = z(B), z(B), z(B), z(B)
+        self.omega, self.inclination, self.d_sq = z(B), z(B), z(B)
+        self.phase_shifts = z(B, C_)
+        self.colatitude, self.ang_radius, self.temperature, self.phi_shift = z(B, M), z(B, M), z(B, M), z(B, M)
+        self.mode_frequency = float(mode_frequency)
+        self.num_cells, self.min_sqrt, self.max_sqrt = int(num_cells), int(min_sqrt_num_cells), int(max_sqrt_num_cells)
+
+    def set_spacetime(self, mass, radius, distance, cos_inclination, frequency):
+        """Vectorised ``xpsi.Spacetime`` derived quantities (xpsi/Spacetime.py:110-188)."""
+        from . import synthetic as syn
+        mass, radius, distance, cos_i = [np.asarray(v, dtype=np.float64) for v in (mass, radius, distance, cos_inclination)]
+        r_g = mass * syn.GM_SUN
+        self.r_s[:] = 2.0 * r_g
+        self.R_eq[:] = radius * syn.KM
+        M = mass * syn.GM_SUN * syn.C_LIGHT * syn.C_LIGHT / syn.G_NEWTON
+        Omega = 2.0 * np.pi * frequency
+        self.omega[:] = Omega
+        self.inclination[:] = np.arccos(cos_i)
+        self.d_sq[:] = (distance * syn.KPC) ** 2
+        self.zeta[:] = r_g / self.R_eq
+        self.epsilon[:] = Omega ** 2 * self.R_eq ** 3 / (syn.G_NEWTON * M)
+
+    def struct(self):
+        s = _lib.SpotBatch()
+        for f in ("R_eq", "r_s", "epsilon", "zeta", "omega", "inclination", "d_sq", "phase_shifts",
+                  "colatitude", "ang_radius", "temperature", "phi_shift"):
+            a = getattr(self, f)
+            if not a.flags.c_contiguous:
+                raise ValueError(f + " must be C-contiguous")
+            setattr(s, f, _lib.dptr(a))
+        s.mode_frequency = self.mode_frequency
+        s.num_cells, s.min_sqrt_num_cells, s.max_sqrt_num_cells = self.num_cells, self.min_sqrt, self.max_sqrt
+        return s
+
+
 class BatchedLikelihood:
     """Device-resident likelihood for a fixed model configuration.
 
@@ -171,6 +217,36 @@ class BatchedLikelihood:
         _lib.check(_lib.lib.xpsi_b200_pipeline_eval(self.handle, batch.B, C.byref(st),
                                                     _lib.dptr(lnL), _lib.iptr(status)))
         return lnL, status
+
+    def new_spot_batch(self, B, mode_frequency, **kw):
+        return SpotBatch(B, self.n_members, self.n_components, mode_frequency, **kw)
+
+    def eval_spots(self, spots):
+        """theta-level call: embed (mesh + rays) on the GPU, then the four likelihood stages."""
+        lnL = np.empty(spots.B, dtype=np.float64)
+        status = np.empty(spots.B, dtype=np.int32)
+        st = spots.struct()
+        _lib.check(_lib.lib.xpsi_b200_pipeline_eval_spots(self.handle, spots.B, C.byref(st), _lib.dptr(lnL),
+                                                          _lib.iptr(status)))
+        return lnL, status
+
+    def embed_spots(self, spots):
+        st = spots.struct()
+        _lib.check(_lib.lib.xpsi_b200_pipeline_embed_spots(self.handle, spots.B, C.byref(st)))
+
+    def fetch_embed(self, B):
+        """Integrator inputs produced by the last embed, as a dict of padded arrays."""
+        s = self.shape
+        Q, R, A, NR = B * self.n_members, s["max_rings"], s["max_azi"], s["n_rays"]
+        out = dict(n_rings=np.empty(Q, np.int32), cellArea=np.empty((Q, R, A)), phi=np.empty((Q, R, A)),
+                   theta=np.empty((Q, R)), radial=np.empty((Q, R)), srcParams=np.empty((Q, R, s["n_params"])),
+                   cos_gamma=np.empty((Q, R)), deflection=np.empty((Q, R, NR)), cos_alpha=np.empty((Q, R, NR)),
+                   lag=np.empty((Q, R, NR)), maxDeflection=np.empty((Q, R)))
+        _lib.check(_lib.lib.xpsi_b200_pipeline_fetch_embed(
+            self.handle, B, _lib.iptr(out["n_rings"]), *[_lib.dptr(out[k]) for k in
+                                                         ("cellArea", "phi", "theta", "radial", "srcParams", "cos_gamma",
+                                                          "deflection", "cos_alpha", "lag", "maxDeflection")]))
+        return out
 
     def upload(self, batch):
         st = batch.struct()

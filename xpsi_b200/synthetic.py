@@ -171,3 +171,21 @@ def m2_theta_batch(n, seed=20261017):
         out[k] = th
         k += 1
     return out
+
+
+def m2_spot_batch(pipe, thetas):
+    """Map ST-U parameter vectors (order ``M2_NAMES``) onto the pipeline's parameter-level inputs:
+    two circular spots, the secondary antiphased with ``T_s = T_p - M2_SECONDARY_DT``
+    (TestRun_Num.py:121-175)."""
+    thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+    B = thetas.shape[0]
+    sb = pipe.new_spot_batch(B, M2_FREQUENCY, num_cells=1024, min_sqrt_num_cells=10, max_sqrt_num_cells=64)
+    sb.set_spacetime(thetas[:, 0], thetas[:, 1], thetas[:, 2], thetas[:, 3], M2_FREQUENCY)
+    sb.phase_shifts[:, 0] = thetas[:, 4]
+    sb.phase_shifts[:, 1] = thetas[:, 8]
+    sb.colatitude[:, 0], sb.ang_radius[:, 0], sb.temperature[:, 0] = thetas[:, 5], thetas[:, 6], thetas[:, 7]
+    sb.colatitude[:, 1], sb.ang_radius[:, 1] = thetas[:, 9], thetas[:, 10]
+    sb.temperature[:, 1] = thetas[:, 7] - M2_SECONDARY_DT
+    sb.phi_shift[:, 0] = 0.0
+    sb.phi_shift[:, 1] = math.pi
+    return sb
