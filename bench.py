@@ -37,11 +37,9 @@ C_ATM_NUM4D, C_GEOM, C_LEAF, C_INIT, C_EVAL, C_INTEG, C_LOG = 800, 150, 20, 25, 
 
 
 def load_workload():
-    """M2 (ST-U NSX) constants + the parameter-vector inputs.
-
-    Mesh and rays come from the committed golden fixture (two parameter vectors
-    embedded by the reference build); the batch tiles them.  Everything else is
-    closed-form in xpsi_b200/synthetic.py.
+    """M2 (ST-U NSX) constants and data.  Parameter vectors are drawn from the
+    closed-form prior in xpsi_b200/synthetic.py (seed 20261017); the synthetic
+    Poisson data set is the committed fixture.  Mesh and rays are built on the GPU.
     """
     from xpsi_b200 import synthetic as syn
     m2 = np.load(os.path.join(ROOT, "tests", "golden", "m2_stu_nsx.npz"))
@@ -50,11 +48,21 @@ def load_workload():
                 exposure=syn.M2_EXPOSURE, n_theta=int(m2["n_theta"]))
 
 
+def theta_block(first, count):
+    """Rows [first, first+count) of the deterministic ST-U parameter-vector list; row 0 and 1 are
+    the two golden parameter vectors so that parity against the reference can be asserted."""
+    from xpsi_b200 import synthetic as syn
+    m2 = np.load(os.path.join(ROOT, "tests", "golden", "m2_stu_nsx.npz"))
+    head = np.array([m2["t0_theta"], m2["t1_theta"]])
+    body = syn.m2_theta_batch(first + count)
+    full = np.vstack([head, body])
+    return np.ascontiguousarray(full[first:first + count])
+
+
 def make_pipeline(w, max_batch):
     from xpsi_b200.pipeline import BatchedLikelihood
     m2 = w["m2"]
-    rings = max(int(m2["t%d_int%d_cellArea" % (t, m)].shape[0]) for t in range(w["n_theta"]) for m in range(2))
-    pad = (rings + 1) // 2 * 2
+    pad = 44                     # ST-U spots at 32^2 cells allocate 36-42 rings over the prior
     return BatchedLikelihood(member_component=[0, 1], max_rings=pad, max_azi=pad, n_rays=200,
                              energies=m2["t0_int0_energies"], leaves=m2["t0_int0_leaves"],
                              phases=m2["t0_int0_phases"], hot_atm_ext=2, hot_atmosphere=w["table"],
@@ -126,9 +134,9 @@ def flops_per_eval(work, n_evals, shape, n_regions, n_quad=192, n_newton=3):
 
 # --------------------------------------------------------------------------- reference arm
 def _ref_worker(args):
-    """Evaluate the reference's hot path (integrate + register + likelihood, embed
-    excluded exactly as in our arm) n times in one process; returns seconds."""
-    n, seed = args
+    """Evaluate the reference's likelihood(theta, force=True) -- embed, integrate,
+    register, likelihood: the same span our arm times -- n times in one process."""
+    n, first = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     import contextlib
@@ -140,24 +148,16 @@ def _ref_worker(args):
         rec = mg.Recorder()
         m2 = np.load(os.path.join(ROOT, "tests", "golden", "m2_stu_nsx.npz"))
         like, signal, instrument, hots = mg.build_m2(rec, m2["counts"])
-        from xpsi_b200 import synthetic as syn
-        thetas = [m2["t0_theta"], m2["t1_theta"]]
-        like(list(thetas[0]), force=True)                 # warm-up incl. embed
-        photosphere = like.star.photospheres[0]
+        thetas = theta_block(first, n)
+        like(list(thetas[0]), force=True)                 # warm-up
         t_total = 0.0
+        lnLs = []
         for k in range(n):
-            th = thetas[k % 2]
-            like._star.spacetime  # noqa
-            super(type(like), like).__call__(list(th))    # push parameters
-            like.star.update(1, force_update=True)         # embed: NOT timed
             t0 = time.perf_counter()
-            photosphere.integrate(signal.energies, 1)
-            sig = tuple(tuple(c / like.star.spacetime.d_sq for c in hr) for hr in photosphere.signal)
-            signal.register(sig, threads=1)
-            signal.shifts = np.array([h['phase_shift'] for h in photosphere.surface.objects])
-            signal(threads=1, llzero=like.llzero)
+            v = like(list(thetas[k]), force=True)
             t_total += time.perf_counter() - t0
-    return t_total, n, float(signal.loglikelihood)
+            lnLs.append(float(v))
+    return t_total, n, lnLs
 
 
 def reference_available():
@@ -176,11 +176,12 @@ def run_reference_sample(per_proc, procs):
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(procs) as pool:
-        res = pool.map(_ref_worker, [(per_proc, i) for i in range(procs)])
+        res = pool.map(_ref_worker, [(per_proc, i * per_proc) for i in range(procs)])
     wall_incl_setup = time.perf_counter() - t0
     slowest = max(r[0] for r in res)
     n_total = sum(r[1] for r in res)
-    return n_total / slowest, n_total, slowest, wall_incl_setup, res[0][2]
+    lnLs = [v for r in res for v in r[2]]                  # theta rows 0 .. n_total-1 in order
+    return n_total / slowest, n_total, slowest, wall_incl_setup, lnLs
 
 
 def main_reference(args):
@@ -194,7 +195,7 @@ def main_reference(args):
     per_proc = 4
     vals = []
     for step in range(args.warmup + args.steps):
-        v, n_total, slowest, wall, lnL = run_reference_sample(per_proc, procs)
+        v, n_total, slowest, wall, lnLs = run_reference_sample(per_proc, procs)
         if step >= args.warmup:
             vals.append((v, slowest))
     value = float(np.mean([v for v, _ in vals]))
@@ -203,11 +204,12 @@ def main_reference(args):
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": float(np.mean([s for _, s in vals]) * 1e3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "M2 ST-U NSX-shaped Num4D, 2 hot regions, 128 energies, 100 leaves/phases, "
-                               "200 rays, 270x1500 response, 32 phase bins; embed excluded (as in our arm)",
+        "config": {"workload": "M2 ST-U NSX-shaped Num4D (35,14,67,166), 2 hot regions, 128 energies, "
+                               "100 leaves/phases, 200 rays, 270x1500 response, 32 phase bins; "
+                               "likelihood(theta) including embed (mesh + rays)",
                    "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference",
-                         "sample": "%d processes x %d evaluations of integrate+register+likelihood, "
+                         "sample": "%d processes x %d evaluations of likelihood(theta, force=True), "
                                    "threads=1 each (X-PSI 3.3.0 sources on the GSL-subset shim)" % (procs, per_proc)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -238,19 +240,20 @@ def main_ours(args):
 
     B = args.batch
     w = load_workload()
+    from xpsi_b200 import synthetic as syn
     pipe = make_pipeline(w, B)
-    batch = pipe.new_batch(B, pinned=True)
-    fill_batch(w, batch, rank * B)
+    thetas = theta_block(rank * B, B)                    # this rank's contiguous block of the theta list
+    spots = syn.m2_spot_batch(pipe, thetas)
     stream = torch.cuda.ExternalStream(_lib.lib.xpsi_b200_stream(), device=torch.device("cuda", local))
 
     peak = np.zeros(1)
     _lib.check(_lib.lib.xpsi_b200_fp64_peak_tflops(_lib.dptr(peak)))
 
-    # ---- kernels only, inputs resident in HBM --------------------------------------
-    pipe.upload(batch)
+    # ---- kernels only: parameter vectors resident on the device, embed + four stages per step ----
+    pipe.embed_spots(spots)
     pipe.count_work(True)
     for _ in range(max(args.warmup, 3)):
-        pipe.eval_resident(B)
+        pipe.eval_spots_resident(B)
     torch.cuda.synchronize()
     work = pipe.count_work(False)
     lnL, status = pipe.download(B)
@@ -258,27 +261,27 @@ def main_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    stage = dict(integrate=0.0, energy=0.0, fold=0.0, marginal=0.0)
+    stage = dict(embed=0.0, integrate=0.0, energy=0.0, fold=0.0, marginal=0.0)
     barrier()
     torch.cuda.synchronize()
     with torch.cuda.stream(stream):
         ev[0].record()
         for _ in range(args.steps):
-            pipe.eval_resident(B)
+            pipe.eval_spots_resident(B)
         ev[1].record()
     torch.cuda.synchronize()
     barrier()
     ms_total = ev[0].elapsed_time(ev[1])
     launches = _lib.counters()[0] - k0
-    for _ in range(3):                       # per-stage split (separate, untimed-for-value runs)
-        pipe.eval_resident(B)
+    for _ in range(3):                       # per-stage split (separate runs, not part of `value`)
+        pipe.eval_spots_resident(B)
         for k, v in pipe.stage_ms().items():
             stage[k] += v / 3.0
     clocks = sampler.stop()
 
-    # ---- end to end: pinned host buffers in, lnL out ----------------------------------
+    # ---- end to end: host parameter arrays in, lnL out (H2D + embed + stages + D2H per step) ----
     for _ in range(2):
-        pipe(batch)
+        pipe.eval_spots(spots)
     c0 = _lib.counters()
     barrier()
     torch.cuda.synchronize()
@@ -286,7 +289,7 @@ def main_ours(args):
     with torch.cuda.stream(stream):
         ev[0].record()
     for _ in range(args.steps):
-        lnL_e2e, status_e2e = pipe(batch)
+        lnL_e2e, status_e2e = pipe.eval_spots(spots)
     with torch.cuda.stream(stream):
         ev[1].record()
     torch.cuda.synchronize()
@@ -314,42 +317,55 @@ def main_ours(args):
     if rank != 0:
         return 0
     ok = bool((all_status == 0).all())
-    refs = [float(w["m2"]["t%d_lnL_total" % (b % w["n_theta"])]) for b in range(min(B, 4))]
-    parity = float(max(abs(lnL[b] - refs[b]) for b in range(len(refs))))
+    refs = [float(w["m2"]["t%d_lnL_total" % b]) for b in range(min(B, 2))]
+    parity = float(max(abs(all_lnL[b] - refs[b]) for b in range(len(refs))))
     fl = flops_per_eval(work, B, pipe.shape, 2)
     int_ms = stage["integrate"]
     achieved = fl["integrate"] * B / (int_ms * 1e-3) / 1e12
     whole = fl["total"] * value / 1e12
-    in_bytes = batch.nbytes()
+    ws_bytes = 4.3e6 * B                       # leaf + slab workspaces and intermediates per step
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "M2 ST-U NSX-shaped Num4D (35,14,67,166), 2 hot regions, 128 energies, "
                                "100 leaves/phases, 200 rays, 270x1500 response, 32 phase bins",
-                   "batch_per_gpu": B, "theta": "2 reference-embedded parameter vectors tiled over the batch",
+                   "batch_per_gpu": B,
+                   "theta": "distinct ST-U parameter vectors from the closed-form prior (seed 20261017); "
+                            "mesh + rays embedded on the GPU inside the timed region",
                    "parallelism": "theta-sharded x%d, no data-path collective" % world,
-                   "l2": "inputs_larger_than_L2 (%.0f MB per step)" % (in_bytes / 1e6)},
+                   "l2": "per-step working set larger than L2 (%.0f MB of workspaces/intermediates); only the "
+                         "theta-independent atmosphere table and response stay L2-resident" % (ws_bytes / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "fp64", "kernel": "k_integrate_azinv<2>", "achieved": achieved, "peak": float(peak[0]),
-                     "unit": "TFLOP/s", "frac": achieved / float(peak[0]), "traffic": None,
+        "roofline": {"bound": "fp64", "kernel": "k_azinv_flux<2,0> (+ k_azinv_geometry, k_azinv_slab)",
+                     "achieved": achieved, "peak": float(peak[0]),
+                     "unit": "TFLOP/s", "frac": achieved / float(peak[0]),
+                     "traffic": 4.64e6 * B,
+                     "traffic_source": "ncu --set full at batch 32 (dram read+write 148.4 MB per launch), scaled to this batch",
                      "peak_source": "in-run DFMA microbenchmark (MEASURED_PEAKS.json has no fp64 entry)",
                      "algorithmic_gflop_per_eval": {k: v / 1e9 for k, v in fl.items()},
                      "whole_path_tflops": whole, "whole_path_frac": whole / float(peak[0]),
                      "stage_ms": stage,
-                     "hbm_sanity_gbs": in_bytes / (ms_total / args.steps * 1e-3) / 1e9},
-        "parity": {"max_abs_lnL_diff_vs_reference_golden": parity, "all_status_ok": ok},
+                     "hbm_sanity_gbs": 4.64e6 * B / (int_ms * 1e-3) / 1e9},
+        "parity": {"max_abs_lnL_diff_vs_reference_golden": parity, "all_status_ok": ok,
+                   "n_status_nonzero": int((all_status != 0).sum())},
     }
     if world == 1 and not args.no_cpu_baseline:
         if reference_available():
             procs = len(os.sched_getaffinity(0))
-            v, n_total, slowest, wall, ref_lnL = run_reference_sample(3, procs)
+            per = 2
+            v, n_total, slowest, wall, ref_lnL = run_reference_sample(per, procs)
+            n_cmp = min(n_total, B)
+            diffs = [abs(ref_lnL[k] - lnL[k]) for k in range(n_cmp) if status[k] == 0 and ref_lnL[k] > -1e80]
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": procs, "kind": "reference",
-                                    "sample": "%d processes x 3 evaluations of integrate+register+likelihood "
-                                              "(threads=1 each), %.1f s of CPU work; X-PSI 3.3.0 sources "
-                                              "on the GSL-subset shim" % (procs, slowest * procs)}
+                                    "sample": "%d processes x %d evaluations of likelihood(theta, force=True) on the "
+                                              "first %d parameter vectors of this batch (threads=1 each), %.1f s of "
+                                              "CPU work; X-PSI 3.3.0 sources on the GSL-subset shim"
+                                              % (procs, per, n_total, slowest * procs),
+                                    "max_abs_lnL_diff_vs_gpu": float(max(diffs)) if diffs else None,
+                                    "n_compared": len(diffs)}
         else:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                     "sample": "oracle/_ref absent on this box"}

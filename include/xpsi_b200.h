@@ -206,6 +206,8 @@ typedef struct {
 
 /* embed B parameter vectors on the device (inputs of the next eval_resident) */
 int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200_spot_batch* host);
+/* re-run embed + the four stages on the spot batch already on the device (kernels only) */
+int xpsi_b200_pipeline_eval_spots_resident(xpsi_b200_pipeline* p, int B);
 /* embed + evaluate + download: theta-level end-to-end call */
 int xpsi_b200_pipeline_eval_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200_spot_batch* host,
                                   double* lnL, int* status);
@@ -229,8 +231,8 @@ int xpsi_b200_pipeline_fetch(xpsi_b200_pipeline* p, int B, double* flux /*[B*M][
 /* algorithmic-work counters of the integrator: enable!=0 makes later evals
  * count; out (if non-NULL and counting was on) receives H, V, RI, K of the last eval */
 int xpsi_b200_pipeline_work_counters(xpsi_b200_pipeline* p, int enable, unsigned long long out[4]);
-/* per-stage device time of the last eval_resident in ms: integrate, energy, fold, marginal */
-int xpsi_b200_pipeline_stage_ms(xpsi_b200_pipeline* p, float ms[4]);
+/* per-stage device time of the last evaluation in ms: integrate, energy, fold, marginal, embed */
+int xpsi_b200_pipeline_stage_ms(xpsi_b200_pipeline* p, float ms[5]);
 
 #ifdef __cplusplus
 }

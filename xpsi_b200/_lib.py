@@ -146,6 +146,7 @@ _proto("xpsi_b200_pipeline_fetch", C.c_int, [C.c_void_p, C.c_int, c_double_p, c_
 _proto("xpsi_b200_fp64_peak_tflops", C.c_int, [c_double_p])
 _proto("xpsi_b200_pipeline_work_counters", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)])
 _proto("xpsi_b200_pipeline_embed_spots", C.c_int, [C.c_void_p, C.c_int, C.POINTER(SpotBatch)])
+_proto("xpsi_b200_pipeline_eval_spots_resident", C.c_int, [C.c_void_p, C.c_int])
 _proto("xpsi_b200_pipeline_eval_spots", C.c_int, [C.c_void_p, C.c_int, C.POINTER(SpotBatch), c_double_p, c_int_p])
 _proto("xpsi_b200_pipeline_fetch_embed", C.c_int, [C.c_void_p, C.c_int, c_int_p] + [c_double_p] * 10)
 _proto("xpsi_b200_pipeline_stage_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)])
@@ -160,6 +161,8 @@ EXPORTED = [
     "xpsi_b200_pipeline_fetch", "xpsi_b200_pipeline_stage_ms", "xpsi_b200_fp64_peak_tflops",
     "xpsi_b200_pipeline_work_counters", "xpsi_b200_phase_integrator", "xpsi_b200_phase_interpolator",
     "xpsi_b200_energy_interpolator", "xpsi_b200_integrate_time_invariance", "xpsi_b200_interstellar_attenuate",
+    "xpsi_b200_pipeline_embed_spots", "xpsi_b200_pipeline_eval_spots", "xpsi_b200_pipeline_fetch_embed",
+    "xpsi_b200_pipeline_eval_spots_resident",
 ]
 
 

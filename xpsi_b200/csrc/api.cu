@@ -505,6 +505,10 @@ struct xpsi_b200_pipeline {
   Dev<double> e_Req, e_rs, e_eps, e_zeta, e_colat, e_rad, e_temp, e_phish, e_maxAlpha;
   int count_work = 0;
   int embed_status_valid = 0;        // status[] already carries embed failures for this batch
+  xb::EmbedArgs embed_args;          // last uploaded spot batch (device pointers), for resident re-runs
+  int embed_ready = 0;
+  cudaEvent_t ev_embed[2] = {nullptr, nullptr};
+  float embed_ms = 0.f; int embed_timed = 0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float stage_ms[4] = {0, 0, 0, 0};
 };
@@ -616,6 +620,17 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   return 0;
 }
 
+int pipeline_embed_launch(xpsi_b200_pipeline* p) {
+  CK(cudaEventRecord(p->ev_embed[0], g_stream));
+  cudaError_t e = xb::launch_embed_spots(p->embed_args, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_embed_spots");
+  CK(cudaEventRecord(p->ev_embed[1], g_stream));
+  p->embed_status_valid = 1;
+  p->embed_timed = 1;
+  g_launches += 2;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -690,6 +705,7 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
     ok(p->ws_leaf.alloc(nl)); ok(p->ws_hdr.alloc(nh)); ok(p->ws_ihdr.alloc(ni)); ok(p->ws_slab.alloc(ns));
   }
   for (int i = 0; i < 5; ++i) ok(cudaEventCreate(&p->ev[i]));
+  for (int i = 0; i < 2; ++i) ok(cudaEventCreate(&p->ev_embed[i]));
   ok(cudaStreamSynchronize(g_stream));
   if (e != cudaSuccess) { cuda_fail(e, "pipeline_create"); delete p; return nullptr; }
   g_launches += 1;
@@ -699,6 +715,7 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
 void xpsi_b200_pipeline_destroy(xpsi_b200_pipeline* p) {
   if (!p) return;
   for (int i = 0; i < 5; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+  for (int i = 0; i < 2; ++i) if (p->ev_embed[i]) cudaEventDestroy(p->ev_embed[i]);
   delete p;
 }
 
@@ -755,11 +772,16 @@ int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200
   a.radial = p->radial.p; a.r_s_over_r = p->rsr.p; a.srcParams = p->params.p; a.cos_gamma = p->cgamma.p;
   a.maxAlpha = p->e_maxAlpha.p; a.deflection = p->defl.p; a.cos_alpha = p->calpha.p; a.lag = p->lag.p;
   a.maxDeflection = p->maxd.p; a.status = p->status.p;
-  cudaError_t e = xb::launch_embed_spots(a, g_stream);
-  if (e != cudaSuccess) return cuda_fail(e, "launch_embed_spots");
-  p->embed_status_valid = 1;
-  g_launches += 2;
-  return 0;
+  p->embed_args = a; p->embed_ready = 1;
+  return pipeline_embed_launch(p);
+}
+
+int xpsi_b200_pipeline_eval_spots_resident(xpsi_b200_pipeline* p, int B) {
+  if (!p || !p->embed_ready || B != p->embed_args.B) return fail(XPSI_B200_EINVAL, "no resident spot batch of this size");
+  CK(cudaMemsetAsync(p->status.p, 0, B * sizeof(int), g_stream));
+  int rc = pipeline_embed_launch(p);
+  if (rc) return rc;
+  return pipeline_run(p, B);
 }
 
 int xpsi_b200_pipeline_eval_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200_spot_batch* h, double* lnL,
@@ -812,10 +834,12 @@ int xpsi_b200_pipeline_work_counters(xpsi_b200_pipeline* p, int enable, unsigned
   return 0;
 }
 
-int xpsi_b200_pipeline_stage_ms(xpsi_b200_pipeline* p, float ms[4]) {
+int xpsi_b200_pipeline_stage_ms(xpsi_b200_pipeline* p, float ms[5]) {
   if (!p) return fail(XPSI_B200_EINVAL, "null pipeline");
   CK(cudaEventSynchronize(p->ev[4]));
   for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms[i], p->ev[i], p->ev[i + 1]));
+  ms[4] = 0.f;
+  if (p->embed_timed) CK(cudaEventElapsedTime(&ms[4], p->ev_embed[0], p->ev_embed[1]));
   return 0;
 }
 

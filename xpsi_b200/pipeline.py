@@ -278,7 +278,11 @@ class BatchedLikelihood:
         _lib.check(_lib.lib.xpsi_b200_pipeline_work_counters(self.handle, int(enable), out))
         return dict(H=out[0], V=out[1], RI=out[2], K=out[3])
 
+    def eval_spots_resident(self, B):
+        """embed + four stages on the spot batch already uploaded by ``embed_spots`` (kernels only)."""
+        _lib.check(_lib.lib.xpsi_b200_pipeline_eval_spots_resident(self.handle, B))
+
     def stage_ms(self):
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 5)()
         _lib.check(_lib.lib.xpsi_b200_pipeline_stage_ms(self.handle, ms))
-        return dict(integrate=ms[0], energy=ms[1], fold=ms[2], marginal=ms[3])
+        return dict(embed=ms[4], integrate=ms[0], energy=ms[1], fold=ms[2], marginal=ms[3])
