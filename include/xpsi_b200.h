@@ -145,6 +145,19 @@ int xpsi_b200_eval_marginal_likelihood(
     double* lnL, double* expected_counts, double* mcl_background,
     double* mcl_background_given_support);
 
+/* ---- likelihoods.poisson_likelihood_given_background / expected counts ----------------
+ * replaces xpsi/likelihoods/_poisson_likelihood_given_background.pyx:14-113 and
+ * tools/compute_expected_counts.pyx:200-315 (also the expected-count half of
+ * tools/synthesise.pyx): expected = T (star + background), background in count rate
+ * [n_chan][n_bins].  counts / neg_sum_ln_data_factorial / lnL may be NULL when only the
+ * expected counts are wanted.  Returns XPSI_B200_EQUADRATURE where the reference adds a
+ * random near-llzero penalty (zero expectation in a bin with counts).                  */
+int xpsi_b200_poisson_likelihood_given_background(
+    double exposure_time, const double* phases, int n_bins, const double* counts, int n_chan,
+    const double* const* components, int n_comp, const double* component_phases, int n_phases,
+    const double* phase_shifts, const double* background, const double* neg_sum_ln_data_factorial,
+    int allow_negative, int phase_interpolant, double* lnL, double* expected_counts);
+
 /* ---- batched likelihood pipeline (additional API) -------------
  * One handle holds every theta-independent constant on the device; eval takes a
  * batch of B parameter vectors already reduced to integrator inputs (mesh +

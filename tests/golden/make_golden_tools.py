@@ -35,3 +35,15 @@ out["flux_neg"] = flux_neg
 out["eitp_neg"] = energy_interpolator(1, flux_neg, log10E, new_E)
 np.savez_compressed(os.path.join(HERE, "tools.npz"), **out)
 print("tools.npz", os.path.getsize(os.path.join(HERE, "tools.npz")) // 1024, "KiB")
+
+# ---- _poisson_likelihood_given_background (row f4) on the C1 folded signal ----
+from xpsi.likelihoods._poisson_likelihood_given_background import poisson_likelihood_given_background  # noqa: E402
+comp = c1["marg_components_0"]
+bgr = np.abs(np.sin(np.arange(comp.shape[0] * 32, dtype=np.double)).reshape(comp.shape[0], 32)) * 0.05 + 0.01
+lnL_bg, expec_bg = poisson_likelihood_given_background(1000.0, edges, c1["marg_counts"], (comp,), (sig_phases,),
+                                                       np.array([0.13]), bgr, c1["marg_precomp"])
+out = dict(np.load(os.path.join(HERE, "tools.npz")))
+out.update({"plgb_background": bgr, "plgb_lnL": np.asarray(lnL_bg), "plgb_expected": np.asarray(expec_bg),
+            "plgb_shift": np.asarray(0.13)})
+np.savez_compressed(os.path.join(HERE, "tools.npz"), **out)
+print("tools.npz (+given-background likelihood)", os.path.getsize(os.path.join(HERE, "tools.npz")) // 1024, "KiB")

@@ -421,3 +421,21 @@ def test_theta_level_likelihood_with_gpu_embed(m2):
         print("theta-level lnL", lnL[b], "ref", ref, "diff", lnL[b] - ref)
         # mesh areas are only defined to the reference's own 1e-8 quadrature tolerance
         assert abs(lnL[b] - ref) < 1e-4
+
+
+def test_poisson_likelihood_given_background(c1):
+    """row f4: Poisson likelihood with a given background + expected counts."""
+    import os
+    from conftest import GOLDEN
+    from xpsi_b200.likelihoods import expected_counts, poisson_likelihood_given_background
+    d = np.load(os.path.join(GOLDEN, "tools.npz"))
+    comp = c1["marg_components_0"]
+    lnL, expec = poisson_likelihood_given_background(1000.0, d["edges"], c1["marg_counts"], (comp,),
+                                                     (d["sig_phases"],), np.array([float(d["plgb_shift"])]),
+                                                     d["plgb_background"], c1["marg_precomp"])
+    print("given-background lnL", lnL, "ref", float(d["plgb_lnL"]))
+    assert abs(lnL - float(d["plgb_lnL"])) < LNL_ATOL
+    assert rel_err(expec, d["plgb_expected"]) < PULSE_RTOL
+    e2 = expected_counts(1000.0, d["edges"], (comp,), (d["sig_phases"],), np.array([float(d["plgb_shift"])]),
+                         d["plgb_background"])
+    assert rel_err(e2, d["plgb_expected"]) < PULSE_RTOL

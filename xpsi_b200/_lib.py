@@ -136,6 +136,9 @@ _proto("xpsi_b200_eval_marginal_likelihood", C.c_int,
        [C.c_double, c_double_p, C.c_int, c_double_p, C.c_int, C.POINTER(c_double_p), C.c_int, c_double_p,
         C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double, C.c_double, C.c_int,
         C.c_double, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p])
+_proto("xpsi_b200_poisson_likelihood_given_background", C.c_int,
+       [C.c_double, c_double_p, C.c_int, c_double_p, C.c_int, C.POINTER(c_double_p), C.c_int, c_double_p,
+        C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p])
 _proto("xpsi_b200_pipeline_create", C.c_void_p, [C.POINTER(PipelineConfig), C.c_int])
 _proto("xpsi_b200_pipeline_destroy", None, [C.c_void_p])
 _proto("xpsi_b200_pipeline_eval", C.c_int, [C.c_void_p, C.c_int, C.POINTER(Batch), c_double_p, c_int_p])
@@ -162,7 +165,7 @@ EXPORTED = [
     "xpsi_b200_pipeline_work_counters", "xpsi_b200_phase_integrator", "xpsi_b200_phase_interpolator",
     "xpsi_b200_energy_interpolator", "xpsi_b200_integrate_time_invariance", "xpsi_b200_interstellar_attenuate",
     "xpsi_b200_pipeline_embed_spots", "xpsi_b200_pipeline_eval_spots", "xpsi_b200_pipeline_fetch_embed",
-    "xpsi_b200_pipeline_eval_spots_resident",
+    "xpsi_b200_pipeline_eval_spots_resident", "xpsi_b200_poisson_likelihood_given_background",
 ]
 
 

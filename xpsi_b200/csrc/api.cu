@@ -478,6 +478,53 @@ int xpsi_b200_eval_marginal_likelihood(
   return 0;
 }
 
+int xpsi_b200_poisson_likelihood_given_background(
+    double exposure_time, const double* phases, int n_bins, const double* counts, int n_chan,
+    const double* const* components, int n_comp, const double* component_phases, int n_phases,
+    const double* phase_shifts, const double* background, const double* neg_sum_ln_data_factorial,
+    int allow_negative, int phase_interpolant, double* lnL, double* expected_counts) {
+  int rc = ensure_stream();
+  if (rc) return rc;
+  if (n_bins < 1 || n_bins > 32) return fail(XPSI_B200_EUNSUPPORTED, "1..32 phase bins supported");
+  if (n_comp < 1 || n_chan < 1 || n_phases < 5 || !background) return fail(XPSI_B200_EINVAL, "bad arguments");
+  Dev<double> d_pulses, d_cph, d_sh, d_dph, d_cnt, d_pre, d_bg, d_clnl, d_exp, d_lnl, d_sup;
+  Dev<int> d_cst, d_st;
+  const size_t np = (size_t)n_chan * n_phases;
+  CK(d_pulses.alloc(np * n_comp));
+  for (int c = 0; c < n_comp; ++c) {
+    g_h2d += (long long)(np * sizeof(double));
+    CK(cudaMemcpyAsync(d_pulses.p + c * np, components[c], np * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  }
+  CK(d_cph.upload(component_phases, n_phases)); CK(d_sh.upload(phase_shifts, n_comp));
+  CK(d_dph.upload(phases, n_bins + 1));
+  if (counts) CK(d_cnt.upload(counts, (size_t)n_chan * n_bins));
+  if (neg_sum_ln_data_factorial) CK(d_pre.upload(neg_sum_ln_data_factorial, n_chan));
+  CK(d_bg.upload(background, (size_t)n_chan * n_bins));
+  std::vector<double> sup(2 * (size_t)n_chan, 0.0);
+  CK(d_sup.upload(sup.data(), sup.size()));
+  CK(d_clnl.alloc(n_chan)); CK(d_cst.alloc(n_chan)); CK(d_exp.alloc((size_t)n_chan * n_bins));
+  CK(d_lnl.alloc(1)); CK(d_st.alloc(1));
+  CK(cudaMemsetAsync(d_st.p, 0, sizeof(int), g_stream));
+  xb::MarginalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = 1; a.n_comp = n_comp; a.n_chan = n_chan; a.n_phases = n_phases; a.n_bins = n_bins;
+  a.pulses = d_pulses.p; a.comp_phases = d_cph.p; a.phase_shifts = d_sh.p; a.data_phases = d_dph.p;
+  a.counts = counts ? d_cnt.p : nullptr; a.precomp = neg_sum_ln_data_factorial ? d_pre.p : nullptr;
+  a.support = d_sup.p; a.background = d_bg.p; a.exposure_time = exposure_time; a.slim = -1.0;
+  a.allow_negative = allow_negative; a.interp = phase_interpolant; a.given_background = 1;
+  a.chan_lnL = d_clnl.p; a.chan_status = d_cst.p; a.expected = d_exp.p; a.lnL = d_lnl.p; a.status = d_st.p;
+  cudaError_t e = xb::launch_marginal(a, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_marginal");
+  g_launches += 2;
+  int status = 0;
+  if (lnL) CK(d_lnl.download(lnL, 1));
+  CK(d_st.download(&status, 1));
+  if (expected_counts) CK(d_exp.download(expected_counts, (size_t)n_chan * n_bins));
+  CK(cudaStreamSynchronize(g_stream));
+  if (status != 0 && counts) return fail(XPSI_B200_EQUADRATURE, "zero expectation in a bin that holds counts");
+  return 0;
+}
+
 }  // extern "C"
 
 // ===========================================================================

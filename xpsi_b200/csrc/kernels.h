@@ -140,6 +140,8 @@ struct MarginalArgs {
   const double* background;          // nullptr or [n_chan][n_bins]
   double exposure_time, epsilon, sigmas, llzero, slim;
   int allow_negative, interp;
+  int given_background;              // 1: _poisson_likelihood_given_background.pyx:14-113 (background required,
+                                     //    in count rate; expected = T (star + background); no marginalisation)
   double* chan_lnL;                  // [B][n_chan]
   int* chan_status;                  // [B][n_chan]
   double* expected;                  // nullptr or [B][n_chan][n_bins]

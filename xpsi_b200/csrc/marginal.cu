@@ -112,6 +112,26 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
     __syncwarp();
   }
   if (star < 0.0) star = 0.0;
+  if (a.given_background) {
+    // compute_expected_counts.pyx:300-305 + _poisson_likelihood_given_background.pyx:96-113
+    double term = 0.0, expec = 0.0;
+    int bad = 0;
+    if (lane < n) {
+      expec = (star + a.background[(long)chan * n + lane]) * T;
+      const double cnt = a.counts ? a.counts[(long)chan * n + lane] : 0.0;
+      if (expec > 0.0) term = cnt * log(expec) - expec;
+      else if (cnt == 0.0 && expec == 0.0) term = 0.0;
+      else bad = 1;
+      if (a.expected) a.expected[((long)b * a.n_chan + chan) * n + lane] = expec;
+    }
+    const double sum = warp_sum(term);
+    const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      a.chan_lnL[(long)b * a.n_chan + chan] = sum + (a.precomp ? a.precomp[chan] : 0.0);
+      a.chan_status[(long)b * a.n_chan + chan] = anybad ? 2 : 0;
+    }
+    return;
+  }
   double d = 0.0;
   if (lane < n) {
     if (a.background) star += a.background[(long)chan * n + lane];

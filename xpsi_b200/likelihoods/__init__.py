@@ -75,3 +75,57 @@ def eval_marginal_likelihood(exposure_time, phases, counts, components, componen
         raise NotImplementedError("xpsi_b200: " + _lib.last_error())
     _lib.check(rc)
     return (lnL.value, star, mcl, mcl_s)
+
+
+def _components(components, component_phases, n_chan):
+    comps = [_lib.as_f8(c, 2) for c in components]
+    cph = [_lib.as_f8(p, 1) for p in component_phases]
+    for c, p in zip(comps, cph):
+        if c.shape != (n_chan, cph[0].shape[0]) or not np.array_equal(p, cph[0]):
+            raise NotImplementedError("xpsi_b200: components must share one phase grid")
+    return comps, cph[0]
+
+
+def poisson_likelihood_given_background(exposure_time, phases, counts, components, component_phases,
+                                        phase_shifts, background, neg_sum_ln_data_factorial=None,
+                                        allow_negative=False):
+    """Poisson likelihood for a given background (count rate), same signature and ``(lnL, expected)``
+    return as xpsi/likelihoods/_poisson_likelihood_given_background.pyx:14-113."""
+    phases = _lib.as_f8(phases, 1)
+    counts = _lib.as_f8(counts, 2)
+    bg = _lib.as_f8(background, 2)
+    comps, cph = _components(components, component_phases, counts.shape[0])
+    shifts = _lib.as_f8(phase_shifts, 1)
+    pre = _lib.as_f8(neg_sum_ln_data_factorial, 1) if neg_sum_ln_data_factorial is not None else None
+    n_chan, n_bins = counts.shape
+    arr = (_lib.c_double_p * len(comps))(*[_lib.dptr(c) for c in comps])
+    lnL = C.c_double(0.0)
+    expec = np.zeros((n_chan, n_bins), dtype=np.float64)
+    rc = _lib.lib.xpsi_b200_poisson_likelihood_given_background(
+        float(exposure_time), _lib.dptr(phases), n_bins, _lib.dptr(counts), n_chan, arr, len(comps),
+        _lib.dptr(cph), cph.shape[0], _lib.dptr(shifts), _lib.dptr(bg), _lib.dptr(pre) if pre is not None else None,
+        int(bool(allow_negative)), phase_interpolant_id(), C.cast(C.pointer(lnL), _lib.c_double_p), _lib.dptr(expec))
+    if rc == _lib.EQUADRATURE:
+        return (-1.0e90 * (0.1 + 0.9 * np.random.rand()), expec)
+    if rc == _lib.EUNSUPPORTED:
+        raise NotImplementedError("xpsi_b200: " + _lib.last_error())
+    _lib.check(rc)
+    return (lnL.value, expec)
+
+
+def expected_counts(exposure_time, phases, components, component_phases, phase_shifts, background,
+                    allow_negative=False):
+    """Expected counts ``T (star + background)`` per (channel, phase bin): the deterministic half of
+    ``tools.synthesise_exposure`` (xpsi/tools/compute_expected_counts.pyx:200-315)."""
+    phases = _lib.as_f8(phases, 1)
+    bg = _lib.as_f8(background, 2)
+    comps, cph = _components(components, component_phases, bg.shape[0])
+    shifts = _lib.as_f8(phase_shifts, 1)
+    arr = (_lib.c_double_p * len(comps))(*[_lib.dptr(c) for c in comps])
+    expec = np.zeros(bg.shape, dtype=np.float64)
+    rc = _lib.lib.xpsi_b200_poisson_likelihood_given_background(
+        float(exposure_time), _lib.dptr(phases), phases.shape[0] - 1, None, bg.shape[0], arr, len(comps),
+        _lib.dptr(cph), cph.shape[0], _lib.dptr(shifts), _lib.dptr(bg), None, int(bool(allow_negative)),
+        phase_interpolant_id(), None, _lib.dptr(expec))
+    _lib.check(rc)
+    return expec

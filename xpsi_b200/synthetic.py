@@ -168,6 +168,9 @@ def m2_theta_batch(n, seed=20261017):
         # compactness: R >= 3 r_g  (TestRun_Num.py CustomPrior)
         if th[1] * KM < 3.0 * th[0] * GM_SUN:
             continue
+        # neither spot may cover a pole (those use the polar mesh, polar_mesh.pyx)
+        if th[5] - th[6] < 0.02 or th[9] + th[10] > math.pi - 0.02:
+            continue
         out[k] = th
         k += 1
     return out
