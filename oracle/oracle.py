@@ -43,7 +43,7 @@ def integrate(numThreads, R, omega, r_s, inclination, cellArea, radialCoords_of_
               elsewhere_atmosphere, hot_atm_ext, else_atm_ext, beam_opt, image_order_limit=None,
               R_in=1e6, phase_interpolant='Akima'):
     """xpsi/cellmesh/integrator_for_azimuthal_invariance.pyx:70-98 (no disc, beam_opt 0)."""
-    assert beam_opt == 0 and R_in >= 1e6
+    assert beam_opt in (0, 1, 2)
     cellArea, theta, phi = _f8(cellArea), _f8(theta), _f8(phi)
     par = _f8(srcCellParams)
     rad = np.ascontiguousarray(CELL_RADIATES, dtype=np.int32)
@@ -63,7 +63,8 @@ def integrate(numThreads, R, omega, r_s, inclination, cellArea, radialCoords_of_
         _d(tab[0]), C.c_int(tab[0].size), _d(tab[1]), C.c_int(tab[1].size), _d(tab[2]), C.c_int(tab[2].size),
         _d(tab[3]), C.c_int(tab[3].size), _d(tab[4]),
         C.c_int(int(image_order_limit) if image_order_limit else 0), C.c_int(INTERP[phase_interpolant]), _d(flux),
-        *_correction_args(correction_srcCellParams, elsewhere_atmosphere, else_atm_ext))
+        *(_correction_args(correction_srcCellParams, elsewhere_atmosphere, else_atm_ext) +
+          [C.c_double(float(R_in)), C.c_int(int(beam_opt))]))
     return (1, None) if rc else (0, flux)
 
 

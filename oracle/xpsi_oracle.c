@@ -104,6 +104,20 @@ static double eval_hot_norm(int atm_ext) {
   return atm_ext == 2 ? 1.0e-7 / H_KEV : 1.0e-7 * 5.040366110812353e22;          /* hot_Num4D.pyx:460, hot_BB.pyx:98 */
 }
 
+/* cellmesh/common_functions.pyx:110-138 */
+static int disk_block(double R_in, double cos_i, double cos_psi, double cos_theta_i, double r_s_over_r_i,
+                      double radius, double sin_alpha, double theta_i_over_pi) {
+  double cos_psi_d = (cos_i * cos_psi - cos_theta_i) /
+                     sqrt(cos_i * cos_i + cos_theta_i * cos_theta_i - 2 * cos_i * cos_theta_i * cos_psi);
+  double sin_psi_d = sqrt(1 - cos_psi_d * cos_psi_d);
+  double r_s_i = r_s_over_r_i * radius;
+  double impact_b = radius * sin_alpha / sqrt(1 - r_s_over_r_i);
+  double r_psi_d = sqrt((r_s_i * r_s_i * (1 - cos_psi_d) * (1 - cos_psi_d)) / (4 * (1 + cos_psi_d) * (1 + cos_psi_d)) +
+                        ((impact_b * impact_b) / (sin_psi_d * sin_psi_d))) -
+                   (r_s_i * (1 - cos_psi_d)) / (2 * (1 + cos_psi_d));
+  return (theta_i_over_pi < 0.5 || (theta_i_over_pi > 0.5 && r_psi_d < R_in)) ? 1 : 0;
+}
+
 /* ------------------------------------- integrator_for_azimuthal_invariance.pyx:70-665 */
 int oracle_integrate_azinv(
     double omega, double inclination, int n_rings, int n_azi, const double *cellArea,
@@ -116,7 +130,9 @@ int oracle_integrate_azinv(
     int image_order_limit, int phase_interp, double *flux,
     /* elsewhere correction (pyx:257-268): NULL, or [n_rings][n_azi][n_params] + its atmosphere */
     const double *correction, int else_atm_ext, const double *c_logT, int c_nT, const double *c_logg,
-    int c_ng, const double *c_mu, int c_nmu, const double *c_logE, int c_nE, const double *c_buf) {
+    int c_ng, const double *c_mu, int c_nmu, const double *c_logE, int c_nE, const double *c_buf,
+    /* disc inner radius (>= 1e6: none, pyx:390-396) and beaming option 0-2 (hot_wrapper.pyx:155-172) */
+    double R_in, int beam_opt) {
   atm_table tab = {{logT, logg, mu_ax, logE}, {nT, ng, nmu, nE}, buf};
   atm_table ctab = {{c_logT, c_logg, c_mu, c_logE}, {c_nT, c_ng, c_nmu, c_nE}, c_buf};
   const int perform_correction = correction != NULL;
@@ -191,7 +207,10 @@ int oracle_integrate_azinv(
             if (theta_i_over_pi < 0.5) mu = mu + sin_alpha * sin_gamma * cos_delta;
             else mu = mu - sin_alpha * sin_gamma * cos_delta;
           }
-          calc = mu > 0.0 ? 1 : 0;                                              /* R_in >= 1e6 */
+          if (mu > 0.0)
+            calc = (R_in < 1e6) ? disk_block(R_in, cos_i, cos_psi, cos_theta_i, r_s_over_r[i], radius, sin_alpha,
+                                             theta_i_over_pi)
+                                : 1;
         }
         if (calc) {
           if (use_alt) deriv = gsl_interp_eval_deriv(interp_alt, defl_alt_ptr, alpha_alt_ptr, cos_psi, acc_alt);
@@ -217,6 +236,13 @@ int oracle_integrate_azinv(
               for (int p = 0; p < N_E; p++) {
                 double E_prime = energies[p] / _Z;
                 double I_E = eval_hot(hot_atm_ext, &tab, E_prime, _ABB, VEC);
+                if (beam_opt == 1 || beam_opt == 2) {
+                  double abb = VEC[2], bbb = VEC[3], cbb = VEC[4], dbb = VEC[5];
+                  double fb = 1.0 + abb * pow(E_prime, cbb) * _ABB + bbb * pow(E_prime, dbb) * _ABB * _ABB;
+                  if (beam_opt == 2) fb *= 0.5 / (0.5 + (1.0 / 3.0) * abb * pow(E_prime, cbb) + (1.0 / 4.0) * bbb * pow(E_prime, dbb));
+                  I_E *= fb;
+                  if (I_E < 0.0) I_E = 0.0;
+                }
                 double correction_I_E = 0.0;
                 if (perform_correction)                                          /* :469-476 */
                   correction_I_E = eval_hot(else_atm_ext, &ctab, E_prime, _ABB,

@@ -439,3 +439,26 @@ def test_poisson_likelihood_given_background(c1):
     e2 = expected_counts(1000.0, d["edges"], (comp,), (d["sig_phases"],), np.array([float(d["plgb_shift"])]),
                          d["plgb_background"])
     assert rel_err(e2, d["plgb_expected"]) < PULSE_RTOL
+
+
+def test_integrator_disc_beaming_and_steffen_options(c1, m2):
+    """Optional branches of the integrator: disc occultation (common_functions.pyx:110-138), beaming options
+    1-2 (hot_wrapper.pyx:155-172), Steffen phase interpolant (tools/core.pyx:34-52)."""
+    from test_oracle import _option_cases
+    from xpsi_b200 import tools
+    from xpsi_b200.cellmesh.integrator_for_azimuthal_invariance import integrate
+    cases, d = _option_cases(c1, m2)
+    for name, a, kw, ref in cases:
+        status, flux = integrate(*a, **kw)
+        assert status == 0, name
+        err = _pulse_err(flux, ref)
+        print(name, "rel err", err)
+        assert err < PULSE_RTOL, name
+    try:
+        tools.set_phase_interpolant("Steffen")
+        status, flux = integrate(*_integrate_args(c1, "int0_", ()))
+        err = _pulse_err(flux, d["steffen_c1"])
+        print("Steffen phase interpolant rel err", err)
+        assert status == 0 and err < PULSE_RTOL
+    finally:
+        tools.set_phase_interpolant("Akima")

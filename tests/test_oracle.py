@@ -165,3 +165,30 @@ def test_oracle_integrate_with_elsewhere_correction():
         status, flux = orc.integrate(*args)
         assert status == 0
         assert _pulse_err(flux, d[p + "flux"]) < 1e-8
+
+
+def _option_cases(c1, m2):
+    from xpsi_b200 import synthetic as syn
+    d = np.load(os.path.join(ROOT, "tests", "golden", "options.npz"))
+    table = syn.nsx_like_table()
+    base = list(_integrate_args(c1, "int0_", ()))
+    cases = []
+    for R_in in (2.0e4, 5.0e4):
+        a = list(base); a[8] = d["disk_theta"]
+        cases.append(("disc R_in=%g" % R_in, a, dict(R_in=R_in), d["disk_flux_%d" % int(R_in)]))
+    for opt in (1, 2):
+        a = list(base); a[10] = d["beam_params_c1"]; a[26] = opt
+        cases.append(("beam %d BB" % opt, a, {}, d["beam%d_c1" % opt]))
+        a = list(_integrate_args(m2, "t0_int1_", table)); a[10] = d["beam_params_m2"]; a[26] = opt
+        cases.append(("beam %d Num4D" % opt, a, {}, d["beam%d_m2" % opt]))
+    return cases, d
+
+
+def test_oracle_disc_and_beaming_options(c1, m2):
+    cases, d = _option_cases(c1, m2)
+    for name, a, kw, ref in cases:
+        status, flux = orc.integrate(*a, **kw)
+        assert status == 0, name
+        assert _pulse_err(flux, ref) < 1e-8, name
+    status, flux = orc.integrate(*_integrate_args(c1, "int0_", ()), phase_interpolant="Steffen")
+    assert status == 0 and _pulse_err(flux, d["steffen_c1"]) < 1e-12

@@ -170,8 +170,9 @@ int xpsi_b200_integrate_azimuthal_invariance(
     if (else_atm_ext == XPSI_B200_ATM_NUM4D && !elsewhere_atmosphere)
       return fail(XPSI_B200_EINVAL, "Num4D elsewhere correction needs a preloaded atmosphere");
   }
-  if (R_in < 1.0e6) return fail(XPSI_B200_EUNSUPPORTED, "disc occultation (R_in < 1e6) is not covered yet");
-  if (beam_opt != 0) return fail(XPSI_B200_EUNSUPPORTED, "beam_opt != 0 is not covered yet");
+  if (beam_opt < 0 || beam_opt > 2)
+    return fail(XPSI_B200_EUNSUPPORTED, "beam_opt 3 (numerically normalised beaming) is not covered");
+  if (beam_opt != 0 && n_params < 6) return fail(XPSI_B200_EINVAL, "beam_opt needs srcCellParams[..., 2:6]");
   if (hot_atm_ext != XPSI_B200_ATM_BB && hot_atm_ext != XPSI_B200_ATM_NUM4D)
     return fail(XPSI_B200_EUNSUPPORTED, "hot_atm_ext must be 1 (BB) or 2 (Num4D)");
   if (hot_atm_ext == XPSI_B200_ATM_NUM4D && !hot_atmosphere)
@@ -232,6 +233,7 @@ int xpsi_b200_integrate_azimuthal_invariance(
   a.image_order_limit = image_order_limit > 0 ? image_order_limit : 0;
   a.n_img_max = image_order_limit > 0 ? image_order_limit : xb::kMaxImages;
   if (a.n_img_max > xb::kMaxImages) return fail(XPSI_B200_EUNSUPPORTED, "image_order_limit > 6");
+  a.beam_opt = beam_opt; a.R_in = R_in;
   a.phase_interp = phase_interpolant;
   a.scale_by_energy = 1;
   a.flux = d_flux.p; a.status = d_status.p;
@@ -620,6 +622,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   a.image_order_limit = c.image_order_limit > 0 ? c.image_order_limit : 0;
   a.n_img_max = c.image_order_limit > 0 ? c.image_order_limit : xb::kMaxImages;
   a.phase_interp = c.phase_interpolant;
+  a.R_in = 1.0e6;
   a.scale_by_energy = 0;
   a.flux = p->flux.p; a.status = p->status_q.p;
   a.ws_leaf = p->ws_leaf.p; a.ws_hdr = p->ws_hdr.p; a.ws_ihdr = p->ws_ihdr.p; a.ws_slab = p->ws_slab.p;

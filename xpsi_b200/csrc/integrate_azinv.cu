@@ -48,6 +48,21 @@ __device__ __forceinline__ double bb_intensity(double E, double kT) {
   return E * E * E / (exp(E / kT) - 1.0);     // hot_BB.pyx:85-87
 }
 
+// accretion-disc occultation, Ibragimov & Poutanen (2009) (common_functions.pyx:110-138): 1 = ray not blocked
+__device__ __forceinline__ int disk_block(double R_in, double cos_i, double cos_psi, double cos_theta_i,
+                                          double r_s_over_r_i, double radius, double sin_alpha,
+                                          double theta_i_over_pi) {
+  const double cos_psi_d = (cos_i * cos_psi - cos_theta_i) /
+                           sqrt(cos_i * cos_i + cos_theta_i * cos_theta_i - 2 * cos_i * cos_theta_i * cos_psi);
+  const double sin_psi_d = sqrt(1 - cos_psi_d * cos_psi_d);
+  const double r_s_i = r_s_over_r_i * radius;
+  const double impact_b = radius * sin_alpha / sqrt(1 - r_s_over_r_i);
+  const double r_psi_d = sqrt((r_s_i * r_s_i * (1 - cos_psi_d) * (1 - cos_psi_d)) / (4 * (1 + cos_psi_d) * (1 + cos_psi_d)) +
+                              ((impact_b * impact_b) / (sin_psi_d * sin_psi_d))) -
+                         (r_s_i * (1 - cos_psi_d)) / (2 * (1 + cos_psi_d));
+  return (theta_i_over_pi < 0.5 || (theta_i_over_pi > 0.5 && r_psi_d < R_in)) ? 1 : 0;
+}
+
 // per-ring headers written by the geometry kernel
 //   ints   [0] image orders to integrate  [1] first radiating cell  [2],[3] (T,g) base nodes
 //          [4],[5] first row / row count of the ring's slab (written by k_azinv_slab)
@@ -187,7 +202,10 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
           if (theta_i_over_pi < 0.5) mu += sin_alpha * sin_gamma * cos_delta;
           else mu -= sin_alpha * sin_gamma * cos_delta;
         }
-        if (mu > 0.0) visible = 1;      // R_in >= 1e6: no disc (pyx:390-396)
+        if (mu > 0.0)                   // pyx:390-396
+          visible = (a.R_in < 1.0e6) ? disk_block(a.R_in, cos_i, cos_psi, cos_theta_i, a.r_s_over_r[ring], radius,
+                                                   sin_alpha, theta_i_over_pi)
+                                     : 1;
       }
     }
     double lagv = 0.0;
@@ -522,7 +540,8 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
   double* s_carea = sp; sp += a.n_azi;
   double* s_PH = sp; sp += N_L;
   double* s_Z = sp; sp += N_L;
-  double* s_aux = sp; sp += N_L;          // mu*eta, then 1/h of the leaf intervals
+  double* s_aux = sp; sp += N_L;          // 1/h of the leaf intervals
+  double* s_abb = sp; sp += N_L;          // mu*eta
   double* s_geom = sp; sp += N_L;
   double* s_y = sp; sp += kNEC * N_L;
   double* s_coef = sp; sp += (long)kNEC * N_L * 4;
@@ -596,16 +615,16 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
     // ---- leaf arrays of this image ------------------------------------------------------
     const double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
     for (int l = tid; l < N_L; l += kFluxThreads) {
-      s_PH[l] = W[l]; s_Z[l] = W[N_L + l]; s_aux[l] = W[2 * N_L + l]; s_geom[l] = W[3 * N_L + l];
+      s_PH[l] = W[l]; s_Z[l] = W[N_L + l]; s_abb[l] = W[2 * N_L + l]; s_geom[l] = W[3 * N_L + l];
       s_flag[l] = 0u;
     }
     __syncthreads();
     if (ATM == 2 || CORR == 2) {
-      if (ATM == 2) slab_ctx_leaf_stencils(hot, s_aux, s_geom, N_L, tid);
-      if (CORR == 2) slab_ctx_leaf_stencils(els, s_aux, s_geom, N_L, tid);
-      __syncthreads();
+      if (ATM == 2) slab_ctx_leaf_stencils(hot, s_abb, s_geom, N_L, tid);
+      if (CORR == 2) slab_ctx_leaf_stencils(els, s_abb, s_geom, N_L, tid);
     }
     for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
+    __syncthreads();
     // ---- (1) leaf profile (pyx:445-478) -----------------------------------------------------
     for (int t = tid, e = 0, l = tid; t < ne * N_L; t += kFluxThreads, l += kFluxThreads) {
       while (l >= N_L) { l -= N_L; ++e; }
@@ -616,6 +635,17 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
         double I_E;
         if (ATM == 1) I_E = bb_intensity(s_E[e] / s_Z[l], kT);
         else I_E = slab_ctx_eval(hot, s_logE[e] - s_Z[l] - log_kT, l, N_L);
+        if (a.beam_opt != 0) {            // hot_wrapper.pyx:155-172 (options 1, 2)
+          const double* BV = a.srcParams + (a.params_per_cell ? (cell0 + ih[1]) : ring) * a.n_params;
+          const double abb = BV[2], bbb = BV[3], cbb = BV[4], dbb = BV[5];
+          const double Ep = (ATM == 2) ? s_E[e] * exp10(-s_Z[l]) : s_E[e] / s_Z[l];
+          const double mu_b = s_abb[l];
+          const double Ec = pow(Ep, cbb), Ed = pow(Ep, dbb);
+          double f = 1.0 + abb * Ec * mu_b + bbb * Ed * mu_b * mu_b;
+          if (a.beam_opt == 2) f *= 0.5 / (0.5 + (1.0 / 3.0) * abb * Ec + (1.0 / 4.0) * bbb * Ed);
+          I_E *= f;
+          if (I_E < 0.0) I_E = 0.0;       // hot_wrapper.pyx:197-199
+        }
         double corr = 0.0;
         if (CORR == 1) {
           const double Z = (ATM == 2) ? exp10(s_Z[l]) : s_Z[l];
@@ -758,7 +788,7 @@ static size_t geom_smem_bytes(const AzinvArgs& a) {
 }
 
 static size_t flux_smem_bytes(const AzinvArgs& a, int atm, int corr) {
-  size_t d = 2ul * a.n_azi + 4ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 5;
+  size_t d = 2ul * a.n_azi + 5ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 5;
   if (atm == 2) d += 4ul * a.n_leaves + 5ul * a.slab_ne_max + a.hot.nmu + (size_t)a.hot.nmu * a.slab_ne_max;
   if (corr == 2) d += 4ul * a.n_leaves + 5ul * a.slab_ne_max + a.els.nmu + (size_t)a.els.nmu * a.slab_ne_max;
   return d * sizeof(double) + 3ul * a.n_leaves * sizeof(int);
@@ -812,6 +842,8 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   const int corr = a.corrParams ? a.else_atm_ext : 0;
   if (atm != 1 && atm != 2) return cudaErrorNotSupported;
   if (corr != 0 && corr != 1 && corr != 2) return cudaErrorNotSupported;
+  if (a.beam_opt < 0 || a.beam_opt > 2 || (a.beam_opt != 0 && a.n_params < 6)) return cudaErrorNotSupported;
+  if (a.R_in <= 0.0) a.R_in = 1.0e6;
   if (!a.corrParams) a.else_atm_ext = 0;
   if ((atm == 2 && !a.ws_slab) || (corr == 2 && !a.ws_slab2)) return cudaErrorInvalidValue;
   if ((atm == 2 || corr == 2) && (a.slab_ne_max < 4 || a.slab_rows_ring < 4)) return cudaErrorInvalidValue;

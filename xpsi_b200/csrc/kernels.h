@@ -37,6 +37,8 @@ struct AzinvArgs {
   AtmTable hot;
   int hot_atm_ext;                   // 1 blackbody, 2 Num4D (hot_wrapper.pyx:72-252)
   int image_order_limit;             // 0 => infer ceil(maxDeflection/pi)
+  int beam_opt;                      // hot_wrapper.pyx:155-172: 0 none, 1, 2 (parameters VEC[2..5])
+  double R_in;                       // inner disc radius [m]; >= 1e6 means no disc (pyx:390-396)
   int n_img_max;
   int phase_interp;                  // tools/core.pyx:21  0 Akima(periodic) 1 Steffen
   int slab_ne_max;                   // Num4D: energy rows a flux CTA may hold in shared memory
