@@ -316,7 +316,11 @@ def main_ours(args):
 
     if rank != 0:
         return 0
-    ok = bool((all_status == 0).all())
+    # 11 = the reference's "slim" early exit (model exceeds the data by > 20 sigma in a channel,
+    # default_background_marginalisation.pyx:677-684): normal for prior draws far from the truth
+    codes, cnts = np.unique(all_status, return_counts=True)
+    status_counts = {str(int(c)): int(n) for c, n in zip(codes, cnts)}
+    ok = bool(np.isin(all_status, (0, 11)).all())
     refs = [float(w["m2"]["t%d_lnL_total" % b]) for b in range(min(B, 2))]
     parity = float(max(abs(all_lnL[b] - refs[b]) for b in range(len(refs))))
     fl = flops_per_eval(work, B, pipe.shape, 2)
@@ -349,8 +353,8 @@ def main_ours(args):
                      "whole_path_tflops": whole, "whole_path_frac": whole / float(peak[0]),
                      "stage_ms": stage,
                      "hbm_sanity_gbs": 4.64e6 * B / (int_ms * 1e-3) / 1e9},
-        "parity": {"max_abs_lnL_diff_vs_reference_golden": parity, "all_status_ok": ok,
-                   "n_status_nonzero": int((all_status != 0).sum())},
+        "parity": {"max_abs_lnL_diff_vs_reference_golden": parity, "no_unexpected_status": ok,
+                   "status_counts": status_counts},
     }
     if world == 1 and not args.no_cpu_baseline:
         if reference_available():

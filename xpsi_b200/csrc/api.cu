@@ -549,7 +549,8 @@ struct xpsi_b200_pipeline {
   Dev<double> flux, xin, folded, chan_lnL, expected, lnL;
   Dev<int> chan_status, status_q, status;
   Dev<unsigned long long> work;
-  Dev<double> ws_leaf, ws_hdr, ws_slab; Dev<int> ws_ihdr;
+  Dev<double> ws_leaf, ws_hdr, ws_slab, ws_mom; Dev<int> ws_ihdr, ws_cnt; Dev<int2> ws_meta;
+  int mom_cap = 0;
   // embed inputs / scratch
   Dev<double> e_Req, e_rs, e_eps, e_zeta, e_colat, e_rad, e_temp, e_phish, e_maxAlpha;
   int count_work = 0;
@@ -626,6 +627,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   a.scale_by_energy = 0;
   a.flux = p->flux.p; a.status = p->status_q.p;
   a.ws_leaf = p->ws_leaf.p; a.ws_hdr = p->ws_hdr.p; a.ws_ihdr = p->ws_ihdr.p; a.ws_slab = p->ws_slab.p;
+  a.ws_mom = p->ws_mom.p; a.ws_meta = p->ws_meta.p; a.ws_cnt = p->ws_cnt.p; a.mom_cap = p->mom_cap;
   a.work = p->count_work ? p->work.p : nullptr;
   if (a.work) CK(cudaMemsetAsync(p->work.p, 0, 4 * sizeof(unsigned long long), g_stream));
   cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
@@ -666,7 +668,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   e = xb::launch_marginal(m, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_marginal");
   CK(cudaEventRecord(p->ev[4], g_stream));
-  g_launches += 8 + (c.hot_atm_ext == XPSI_B200_ATM_NUM4D ? 1 : 0);   // expand, geometry, [slab], flux, energy, fold, member-status, marginal, channel-sum
+  g_launches += 9 + (c.hot_atm_ext == XPSI_B200_ATM_NUM4D ? 1 : 0);   // expand, geometry, [slab], moments, flux, energy, fold, member-status, marginal, channel-sum
   return 0;
 }
 
@@ -753,6 +755,13 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
     size_t nl, nh, ni, ns;
     xb::azinv_workspace_sizes(w, &nl, &nh, &ni, &ns);
     ok(p->ws_leaf.alloc(nl)); ok(p->ws_hdr.alloc(nh)); ok(p->ws_ihdr.alloc(ni)); ok(p->ws_slab.alloc(ns));
+    // moment workspace: 24 leaf intervals per output phase covers spots up to ~0.7 rad in azimuthal
+    // half-width at 100 leaves; wider rings fall back to walking inside the flux CTA
+    w.n_phases = c.n_phases; w.mom_cap = 24;
+    size_t nm, nt, nc;
+    xb::azinv_moment_sizes(w, &nm, &nt, &nc);
+    ok(p->ws_mom.alloc(nm)); ok(p->ws_meta.alloc(nt)); ok(p->ws_cnt.alloc(nc));
+    p->mom_cap = w.mom_cap;
   }
   for (int i = 0; i < 5; ++i) ok(cudaEventCreate(&p->ev[i]));
   for (int i = 0; i < 2; ++i) ok(cudaEventCreate(&p->ev_embed[i]));

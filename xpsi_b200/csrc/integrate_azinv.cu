@@ -428,6 +428,118 @@ __global__ void __launch_bounds__(kSlabThreads) k_azinv_slab(AzinvArgs a, int wh
   }
 }
 
+
+// Walk a ring's radiating cells (ascending azimuth) for output phase phk and hand every touched leaf
+// interval m to the visitor together with the area moments W_p = sum_j A_j d_j^p of the cells inside it
+// (d_j = phase + azimuth - PHASE[m], brought into [first,last] by whole turns, pyx:575-583).
+template <class Visitor>
+__device__ __forceinline__ void walk_cells(double phk, const double* s_PH, int N_L, const double* s_cphi,
+                                           const double* s_carea, int n_cells, int* status, Visitor&& visit) {
+  const double ph_first = s_PH[0], ph_last = s_PH[N_L - 1];
+  // cells ascend in azimuth, so the whole-turn offset only ever steps down by 2 pi along the walk
+  int c = 0;
+  int m = -1;
+  double off = 0.0;
+  bool searched = false;
+  while (c < n_cells) {
+    double x = phk + s_cphi[c] + off;
+    if (x > ph_last || x < ph_first) {
+      double xr = phk + s_cphi[c];
+      if (xr > ph_last) { while (xr > ph_last) xr -= kTwoPi; }
+      else if (xr < ph_first) { while (xr < ph_first) xr += kTwoPi; }
+      if (xr < ph_first || xr > ph_last) { atomicExch(status, kNumericalError); ++c; continue; }
+      off = xr - (phk + s_cphi[c]);
+      x = xr;
+      searched = false;
+    }
+    if (!searched) { m = interval_search(s_PH, N_L, x); searched = true; }
+    else m = interval_walk(s_PH, N_L, x, m);
+    const double xm = s_PH[m], xn = s_PH[m + 1];
+    const bool last_iv = (m == N_L - 2);
+    double W0 = 0.0, W1 = 0.0, W2 = 0.0, W3 = 0.0;
+    const int c_start = c;
+    for (;;) {                                // absorb the cells that fall in interval m
+      const double d = x - xm;
+      const double A = s_carea[c];
+      W0 += A;
+      double t = A * d; W1 += t;
+      t *= d; W2 += t;
+      t *= d; W3 += t;
+      ++c;
+      if (c >= n_cells) break;
+      x = phk + s_cphi[c] + off;
+      if (!(x >= xm && (x < xn || (last_iv && x <= xn)))) break;   // next interval, or wrap (x > last)
+    }
+    visit(m, W0, W1, W2, W3, c_start, c);
+  }
+}
+
+// compact list of a ring's radiating cells (one warp: keeps azimuth order); returns the count to lane 0..31
+__device__ __forceinline__ int compact_cells(const AzinvArgs& a, long cell0, int A_, int lane, double* s_cphi,
+                                             double* s_carea) {
+  int base = 0;
+  for (int j0 = 0; j0 < A_; j0 += 32) {
+    const int j = j0 + lane;
+    bool rad = false;
+    double area = 0.0, phi = 0.0;
+    if (j < A_) {
+      area = a.cellArea[cell0 + j]; phi = a.phi[cell0 + j];
+      rad = a.radiates ? (a.radiates[cell0 + j] == 1) : (area > 0.0);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, rad);
+    if (rad) {
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      s_cphi[pos] = phi; s_carea[pos] = area;
+    }
+    base += __popc(m);
+  }
+  return base;
+}
+
+// ===========================================================================
+// moments: the cell walk is identical for all energy chunks of a ring, so it is done once per
+// (ring, image order) here and handed to the flux CTAs through an L2-resident workspace
+// ===========================================================================
+constexpr int kMomThreads = 128;
+
+__global__ void __launch_bounds__(kMomThreads) k_azinv_moments(AzinvArgs a) {
+  const int i = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
+  const long ring = (long)q * a.n_rings + i;
+  const int n_img = a.ws_ihdr[ring * kIHdr];
+  if (n_img == 0) return;
+  const int A_ = a.n_azi_q ? a.n_azi_q[q] : a.n_azi;
+  const int N_L = a.n_leaves, N_P = a.n_phases, cap = a.mom_cap;
+  extern __shared__ double smem[];
+  __shared__ int s_ncell;
+  double* s_cphi = smem;
+  double* s_carea = s_cphi + a.n_azi;
+  double* s_PH = s_carea + a.n_azi;
+  if (tid < 32) { const int n = compact_cells(a, ring * a.n_azi, A_, tid, s_cphi, s_carea); if (tid == 0) s_ncell = n; }
+  const int k = tid;
+  const double phk = (k < N_P) ? a.phases[k] : 0.0;
+  for (int I = 0; I < n_img; ++I) {
+    __syncthreads();
+    const double* W = leaf_ptr(a.ws_leaf, ring, a.n_img_max, I, N_L);
+    for (int l = tid; l < N_L; l += kMomThreads) s_PH[l] = W[l];
+    __syncthreads();
+    if (k >= N_P) continue;
+    const long slot = ring * a.n_img_max + I;
+    double* mom = a.ws_mom + slot * (long)cap * 4 * N_P;
+    int2* meta = a.ws_meta + slot * (long)cap * N_P;
+    int cnt = 0;
+    walk_cells(phk, s_PH, N_L, s_cphi, s_carea, s_ncell, a.status + q,
+               [&](int m, double W0, double W1, double W2, double W3, int c0, int c1) {
+                 if (cnt < cap) {
+                   double* e = mom + (long)cnt * 4 * N_P + k;
+                   e[0] = W0; e[N_P] = W1; e[2 * N_P] = W2; e[3 * N_P] = W3;
+                   meta[(long)cnt * N_P + k] = make_int2(m, c0 | (c1 << 16));
+                 }
+                 ++cnt;
+               });
+    a.ws_cnt[slot * N_P + k] = (cnt <= cap) ? cnt : -1;      // -1: too many intervals, the flux CTA walks itself
+  }
+}
+
 // ===========================================================================
 // flux
 // ===========================================================================
@@ -555,23 +667,8 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
 
   // ---- compact list of the ring's radiating cells (one warp: keeps azimuth order) ------
   if (tid < 32) {
-    int base = 0;
-    for (int j0 = 0; j0 < A_; j0 += 32) {
-      const int j = j0 + tid;
-      bool rad = false;
-      double area = 0.0, phi = 0.0;
-      if (j < A_) {
-        area = a.cellArea[cell0 + j]; phi = a.phi[cell0 + j];
-        rad = a.radiates ? (a.radiates[cell0 + j] == 1) : (area > 0.0);
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, rad);
-      if (rad) {
-        const int pos = base + __popc(m & ((1u << tid) - 1u));
-        s_cphi[pos] = phi; s_carea[pos] = area;
-      }
-      base += __popc(m);
-    }
-    if (tid == 0) s_ncell = base;
+    const int n = compact_cells(a, cell0, A_, tid, s_cphi, s_carea);
+    if (tid == 0) s_ncell = n;
   } else if (tid < 32 + kNEC) {
     const int e = tid - 32;
     s_E[e] = a.energies[e0 + (e < ne ? e : 0)];
@@ -689,44 +786,10 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
       }
     }
     __syncthreads();
-    // ---- (3) interval moments over the ring's cells, then 4 FMAs per energy (pyx:571-596) -----
+    // ---- (3) interval moments x spline coefficients: 4 FMAs per (interval, energy) (pyx:571-596) -----
     if (k < N_P) {
       const double ph_first = s_PH[0], ph_last = s_PH[N_L - 1];
-      // cells ascend in azimuth, so the whole-turn offset that brings phase+azimuth into
-      // [first,last] (pyx:575-583) only ever steps down by 2 pi along the walk
-      int c = 0;
-      int m = -1;
-      double off = 0.0;
-      bool searched = false;
-      while (c < n_cells) {
-        double x = phk + s_cphi[c] + off;
-        if (x > ph_last || x < ph_first) {
-          double xr = phk + s_cphi[c];
-          if (xr > ph_last) { while (xr > ph_last) xr -= kTwoPi; }
-          else if (xr < ph_first) { while (xr < ph_first) xr += kTwoPi; }
-          if (xr < ph_first || xr > ph_last) { atomicExch(a.status + q, kNumericalError); ++c; continue; }
-          off = xr - (phk + s_cphi[c]);
-          x = xr;
-          searched = false;
-        }
-        if (!searched) { m = interval_search(s_PH, N_L, x); searched = true; }
-        else m = interval_walk(s_PH, N_L, x, m);
-        const double xm = s_PH[m], xn = s_PH[m + 1];
-        const bool last_iv = (m == N_L - 2);
-        double W0 = 0.0, W1 = 0.0, W2 = 0.0, W3 = 0.0;
-        const int c_start = c;
-        for (;;) {                                // absorb the cells that fall in interval m
-          const double d = x - xm;
-          const double A = s_carea[c];
-          W0 += A;
-          double t = A * d; W1 += t;
-          t *= d; W2 += t;
-          t *= d; W3 += t;
-          ++c;
-          if (c >= n_cells) break;
-          x = phk + s_cphi[c] + off;
-          if (!(x >= xm && (x < xn || (last_iv && x <= xn)))) break;   // next interval, or wrap (x > last)
-        }
+      auto flush = [&](int m, double W0, double W1, double W2, double W3, int c_start, int c_end) {
         const unsigned fl = s_flag[m];
         const double* cp = s_coef + (long)m * 4;
         if (fl == 0u) {
@@ -741,8 +804,12 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
         } else {
           // some energy's cubic may dip below zero on this interval: the reference adds a cell
           // only where the spline is positive (pyx:593), so go cell by cell for those energies
-          for (int cc = c_start; cc < c; ++cc) {
-            const double d = (phk + s_cphi[cc] + off) - xm;
+          const double xm = s_PH[m];
+          for (int cc = c_start; cc < c_end; ++cc) {
+            double xr = phk + s_cphi[cc];
+            if (xr > ph_last) { while (xr > ph_last) xr -= kTwoPi; }
+            else if (xr < ph_first) { while (xr < ph_first) xr += kTwoPi; }
+            const double d = xr - xm;
             const double A = s_carea[cc];
 #pragma unroll
             for (int g = 0; g < kNEC; ++g) {
@@ -761,6 +828,21 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
             }
           }
         }
+      };
+      const long slot = ring * n_img_max + I;
+      const int cnt = a.ws_mom ? a.ws_cnt[slot * N_P + k] : -1;
+      if (cnt >= 0) {
+        // moments prepared once per (ring, image) by k_azinv_moments; loads are coalesced over k
+        const double* mom = a.ws_mom + slot * (long)a.mom_cap * 4 * N_P + k;
+        const int2* meta = a.ws_meta + slot * (long)a.mom_cap * N_P + k;
+        for (int t = 0; t < cnt; ++t) {
+          const double* e = mom + (long)t * 4 * N_P;
+          const double W0 = e[0], W1 = e[N_P], W2 = e[2 * N_P], W3 = e[3 * N_P];
+          const int2 mt = meta[(long)t * N_P];
+          flush(mt.x, W0, W1, W2, W3, mt.y & 0xffff, mt.y >> 16);
+        }
+      } else {
+        walk_cells(phk, s_PH, N_L, s_cphi, s_carea, n_cells, a.status + q, flush);
       }
     }
   }
@@ -798,6 +880,13 @@ static size_t flux_smem_bytes(const AzinvArgs& a, int atm, int corr) {
 // log10((1+b)/(1-b)) at |beta| = 0.23 (700 Hz, 16 km).  Rings beyond it are refused
 // (status 3), never clamped.
 constexpr double kDopplerDex = 0.2;
+
+void azinv_moment_sizes(const AzinvArgs& a, size_t* mom_doubles, size_t* meta_int2, size_t* cnt_ints) {
+  const size_t slots = (size_t)a.Q * a.n_rings * a.n_img_max;
+  *mom_doubles = slots * a.mom_cap * 4 * a.n_phases;
+  *meta_int2 = slots * a.mom_cap * a.n_phases;
+  *cnt_ints = slots * a.n_phases;
+}
 
 void azinv_workspace_sizes(const AzinvArgs& a, size_t* leaf_doubles, size_t* hdr_doubles, size_t* ihdr_ints,
                            size_t* slab_doubles) {
@@ -861,6 +950,11 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
     k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 0);
   }
   if (corr == 2) k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 1);
+  if (a.ws_mom) {
+    if (!a.ws_meta || !a.ws_cnt || a.mom_cap < 1 || a.n_azi > 0xffff) return cudaErrorInvalidValue;
+    const size_t msm = (2ul * a.n_azi + a.n_leaves) * sizeof(double);
+    k_azinv_moments<<<ggrid, kMomThreads, msm, stream>>>(a);
+  }
   if ((err = cudaGetLastError()) != cudaSuccess) return err;
   if (atm == 1 && corr == 0) err = launch_flux<1, 0>(a, fgrid, fsm, stream);
   else if (atm == 1 && corr == 1) err = launch_flux<1, 1>(a, fgrid, fsm, stream);

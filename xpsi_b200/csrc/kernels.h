@@ -52,12 +52,15 @@ struct AzinvArgs {
   int* ws_chunk;                     // set by the launcher
   double* ws_slab;                   // Num4D: [Q][n_rings][nmu][slab_rows_ring]
   double* ws_slab2;                  // same for a Num4D elsewhere correction
+  // optional: interval moments of the cell walk, shared by a ring's energy chunks (azinv_moment_sizes)
+  double* ws_mom; int2* ws_meta; int* ws_cnt; int mom_cap;
   unsigned long long* work;          // nullptr or [4]: H half-leaf visits, V visible leaves,
                                      //   RI (ring,image) pairs reaching the phase stage, K radiating cells over RI
 };
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream);
 void azinv_workspace_sizes(const AzinvArgs& a, size_t* leaf_doubles, size_t* hdr_doubles, size_t* ihdr_ints,
                            size_t* slab_doubles);
+void azinv_moment_sizes(const AzinvArgs& a, size_t* mom_doubles, size_t* meta_int2, size_t* cnt_ints);
 void azinv_slab_budgets(const AtmTable& t, const double* host_energies, int n_energies, int* rows_chunk,
                         int* rows_ring);
 
