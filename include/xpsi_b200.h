@@ -85,6 +85,27 @@ int xpsi_b200_integrate_azimuthal_invariance(
     int hot_atm_ext, int else_atm_ext, int beam_opt, int image_order_limit, double R_in,
     int phase_interpolant, double* flux_out);
 
+/* ---- cellmesh.integrator.integrate (no azimuthal invariance) ------------------
+ * replaces xpsi/cellmesh/integrator.pyx:48-667 (bound by HotRegion.symmetry = False,
+ * xpsi/HotRegion.py:567-569, and Everywhere(time_invariant=False), xpsi/Everywhere.py:330-332).
+ * Same arguments as above; the atmosphere is evaluated with each CELL's srcCellParams /
+ * correction_srcCellParams.  R_in is accepted and ignored, as in the reference.  At most
+ * 128 phases. */
+int xpsi_b200_integrate_general(
+    double R, double omega, double r_s, double inclination,
+    int n_rings, int n_azi,
+    const double* cellArea, const double* radialCoords_of_parallels, const double* r_s_over_r,
+    const double* theta, const double* phi,
+    const double* srcCellParams, int n_params, const int* CELL_RADIATES,
+    const double* correction_srcCellParams,
+    int numRays, const double* deflection, const double* cos_alpha, const double* lag,
+    const double* maxDeflection, const double* cos_gammaArray,
+    int n_energies, const double* energies, int n_leaves, const double* leaves,
+    int n_phases, const double* phases,
+    const xpsi_b200_atmosphere* hot_atmosphere, const xpsi_b200_atmosphere* elsewhere_atmosphere,
+    int hot_atm_ext, int else_atm_ext, int beam_opt, int image_order_limit, double R_in,
+    int phase_interpolant, double* flux_out);
+
 /* ---- cellmesh.integrator_for_time_invariance.integrate ------------------------------
  * replaces xpsi/cellmesh/integrator_for_time_invariance.pyx:59-338 (call sites
  * xpsi/Elsewhere.py:418-438, xpsi/Everywhere.py:581-601).  theta/phi [n][n],

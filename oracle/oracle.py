@@ -68,6 +68,34 @@ def integrate(numThreads, R, omega, r_s, inclination, cellArea, radialCoords_of_
     return (1, None) if rc else (0, flux)
 
 
+def integrate_general(numThreads, R, omega, r_s, inclination, cellArea, radialCoords_of_parallels, r_s_over_r,
+                      theta, phi, srcCellParams, CELL_RADIATES, correction_srcCellParams, numRays, deflection,
+                      cos_alpha, lag, maxDeflection, cos_gammaArray, energies, leaves, phases, hot_atmosphere,
+                      elsewhere_atmosphere, hot_atm_ext, else_atm_ext, beam_opt, image_order_limit=None,
+                      R_in=1e6, phase_interpolant='Akima'):
+    """xpsi/cellmesh/integrator.pyx:48-76 (the integrator without azimuthal invariance)."""
+    assert beam_opt in (0, 1, 2)
+    cellArea, theta, phi = _f8(cellArea), _f8(theta), _f8(phi)
+    par = _f8(srcCellParams)
+    rad = np.ascontiguousarray(CELL_RADIATES, dtype=np.int32)
+    arrs = [_f8(x) for x in (radialCoords_of_parallels, r_s_over_r, deflection, cos_alpha, lag,
+                             maxDeflection, cos_gammaArray, energies, leaves, phases)]
+    radial, rsr, defl, ca, lg, maxd, cg, E, L, P = arrs
+    tab = [_f8(t) for t in hot_atmosphere] if hot_atmosphere else [np.zeros(4)] * 5
+    flux = np.zeros((E.size, P.size))
+    rc = lib.oracle_integrate_general(
+        C.c_double(omega), C.c_double(inclination), C.c_int(cellArea.shape[0]), C.c_int(cellArea.shape[1]),
+        _d(cellArea), _d(radial), _d(rsr), _d(theta), _d(phi), _d(par), C.c_int(par.shape[2]),
+        rad.ctypes.data_as(ip), C.c_int(int(numRays)), _d(defl), _d(ca), _d(lg), _d(maxd), _d(cg),
+        C.c_int(E.size), _d(E), C.c_int(L.size), _d(L), C.c_int(P.size), _d(P), C.c_int(int(hot_atm_ext)),
+        _d(tab[0]), C.c_int(tab[0].size), _d(tab[1]), C.c_int(tab[1].size), _d(tab[2]), C.c_int(tab[2].size),
+        _d(tab[3]), C.c_int(tab[3].size), _d(tab[4]),
+        C.c_int(int(image_order_limit) if image_order_limit else 0), C.c_int(INTERP[phase_interpolant]), _d(flux),
+        *(_correction_args(correction_srcCellParams, elsewhere_atmosphere, else_atm_ext) +
+          [C.c_int(int(beam_opt))]))
+    return (1, None) if rc else (0, flux)
+
+
 def _correction_args(correction, atmosphere, else_atm_ext):
     if correction is None:
         z = np.zeros(4)

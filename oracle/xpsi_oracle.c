@@ -672,3 +672,218 @@ int oracle_integrate_tinv(
   free(cos_deflection); free(cos_alpha_alt);
   return terminate ? ORACLE_ERROR : ORACLE_OK;
 }
+
+/* beaming modification of the hot intensity (hot_wrapper.pyx:155-199), options 1 and 2 */
+static double apply_beaming(int beam_opt, double I_E, double E_prime, double mu, const double *VEC) {
+  if (beam_opt != 1 && beam_opt != 2) return I_E;
+  double abb = VEC[2], bbb = VEC[3], cbb = VEC[4], dbb = VEC[5];
+  double fb = 1.0 + abb * pow(E_prime, cbb) * mu + bbb * pow(E_prime, dbb) * mu * mu;
+  if (beam_opt == 2) fb *= 0.5 / (0.5 + (1.0 / 3.0) * abb * pow(E_prime, cbb) + (1.0 / 4.0) * bbb * pow(E_prime, dbb));
+  I_E *= fb;
+  return I_E < 0.0 ? 0.0 : I_E;
+}
+
+/* ------------------------------------------------------------- cellmesh/integrator.pyx:48-667
+ * The integrator without azimuthal invariance: per (ring, image) the leaf quantities GEOM, Z, ABB
+ * are splined against the lagged leaf phase (GEOM with the phase interpolant, Z and ABB with Steffen,
+ * :537-542) and the atmosphere is evaluated per (cell, phase, energy) with the CELL's parameters
+ * (:544-592).  Argument list as oracle_integrate_azinv minus R_in (the general integrator ignores it). */
+int oracle_integrate_general(
+    double omega, double inclination, int n_rings, int n_azi, const double *cellArea,
+    const double *radial, const double *r_s_over_r, const double *theta, const double *phi,
+    const double *srcCellParams, int n_params, const int *CELL_RADIATES, int N_R,
+    const double *deflection, const double *cos_alpha, const double *lag, const double *maxDeflection,
+    const double *cos_gammaArray, int N_E, const double *energies, int N_L, const double *leaves,
+    int N_P, const double *phases, int hot_atm_ext, const double *logT, int nT, const double *logg,
+    int ng, const double *mu_ax, int nmu, const double *logE, int nE, const double *buf,
+    int image_order_limit, int phase_interp, double *flux,
+    const double *correction, int else_atm_ext, const double *c_logT, int c_nT, const double *c_logg,
+    int c_ng, const double *c_mu, int c_nmu, const double *c_logE, int c_nE, const double *c_buf,
+    int beam_opt) {
+  atm_table tab = {{logT, logg, mu_ax, logE}, {nT, ng, nmu, nE}, buf};
+  atm_table ctab = {{c_logT, c_logg, c_mu, c_logE}, {c_nT, c_ng, c_nmu, c_nE}, c_buf};
+  const int perform_correction = correction != NULL;
+  const double sin_i = sin(inclination), cos_i = cos(inclination);
+  const size_t NL = (size_t)N_L;
+  const size_t leaf_lim = (N_L % 2 == 0) ? NL / 2 : (NL + 1) / 2;                 /* :214-217 */
+  int terminate = 0;
+  double *PHASE = malloc(sizeof(double) * NL), *GEOM = calloc(NL, sizeof(double)), *Z = calloc(NL, sizeof(double)),
+         *ABB = calloc(NL, sizeof(double));
+  double *cos_deflection = malloc(sizeof(double) * N_R), *cos_alpha_alt = malloc(sizeof(double) * N_R);
+  gsl_interp_accel *acc_a = gsl_interp_accel_alloc(), *acc_alt = gsl_interp_accel_alloc(),
+                   *acc_l = gsl_interp_accel_alloc(), *acc_G = gsl_interp_accel_alloc(),
+                   *acc_Z = gsl_interp_accel_alloc(), *acc_A = gsl_interp_accel_alloc();
+  gsl_interp *interp_alpha = gsl_interp_alloc(gsl_interp_steffen, N_R);
+  gsl_interp *interp_lag = gsl_interp_alloc(gsl_interp_steffen, N_R);
+  gsl_interp *interp_Z = gsl_interp_alloc(gsl_interp_steffen, NL);                /* :174-179 */
+  gsl_interp *interp_ABB = gsl_interp_alloc(gsl_interp_steffen, NL);
+  gsl_interp *interp_GEOM = gsl_interp_alloc(phase_interpolant(phase_interp), NL);
+  memset(flux, 0, sizeof(double) * (size_t)N_E * N_P);
+
+  for (int i = 0; i < n_rings && !terminate; i++) {
+    int J = -1;
+    for (int j = 0; j < n_azi; j++) if (CELL_RADIATES[i * n_azi + j] == 1) { J = j; break; }   /* :264-274 */
+    if (J < 0) continue;
+    const double *defl = deflection + (size_t)i * N_R, *calpha = cos_alpha + (size_t)i * N_R,
+                 *lagr = lag + (size_t)i * N_R;
+    for (int j = 0; j < N_R; j++) {                                               /* :192-208 */
+      cos_deflection[j] = cos(defl[N_R - j - 1]);
+      cos_alpha_alt[j] = calpha[N_R - j - 1];
+    }
+    int jh = 0;
+    while (jh < N_R - 1 && defl[jh] <= M_PI / 2.0) jh++;                          /* :279-281 */
+    const double *defl_alt_ptr = cos_deflection + (N_R - jh - 1), *alpha_alt_ptr = cos_alpha_alt + (N_R - jh - 1);
+    gsl_interp *interp_alt = gsl_interp_alloc(gsl_interp_steffen, jh + 1);
+    gsl_interp_init(interp_alt, defl_alt_ptr, alpha_alt_ptr, jh + 1);
+    gsl_interp_accel_reset(acc_alt); gsl_interp_accel_reset(acc_a); gsl_interp_accel_reset(acc_l);
+    gsl_interp_init(interp_alpha, defl, calpha, N_R);
+    gsl_interp_init(interp_lag, defl, lagr, N_R);
+
+    const double radius = radial[i];                                              /* :294-306 */
+    const double Grav_z = sqrt(1.0 - r_s_over_r[i]);
+    const double cos_gamma = cos_gammaArray[i];
+    const double sin_gamma = sqrt(1.0 - cos_gamma * cos_gamma);
+    const double cos_theta_i = cos(theta[i * n_azi]), sin_theta_i = sin(theta[i * n_azi]);
+    const double theta_i_over_pi = theta[i * n_azi] / M_PI;
+    const double beta = radius * omega * sin_theta_i / (C_LIGHT * Grav_z);
+    const double Lorentz = sqrt(1.0 - beta * beta);
+    double _cos_alpha = -1.0, deriv = -1.0;
+    const int _IO = image_order_limit > 0 ? image_order_limit : (int)ceil(maxDeflection[i] / M_PI);
+
+    for (int I = 0; I < _IO && !terminate; I++) {
+      int InvisFlag = 2;
+      size_t _InvisPhase = 0;
+      for (size_t k = 0; k < NL; k++) {                                           /* :316, all leaves */
+        double cos_psi = cos_i * cos_theta_i + sin_i * sin_theta_i * cos(leaves[k]);
+        double psi = eval_image_deflection(I, acos(cos_psi));
+        double sin_psi = sin(psi), sin_alpha = 0.0, mu = 0.0;
+        int lit = 0;
+        if (!are_equal(psi, 0.0) && are_equal(sin_psi, 0.0)) {                    /* :321-334 */
+          double _i = cos_i >= 0.0 ? inclination + inclination * 1.0e-6 : inclination - inclination * 1.0e-6;
+          cos_psi = cos(_i) * cos_theta_i + sin(_i) * sin_theta_i * cos(leaves[k]);
+          psi = eval_image_deflection(I, acos(cos_psi));
+          sin_psi = sin(psi);
+        }
+        const int use_alt = (psi <= M_PI / 2.0 && cos_psi >= interp_alt->xmin);
+        if (psi <= maxDeflection[i]) {
+          if (psi < interp_alpha->xmin || psi > interp_alpha->xmax) { terminate = 1; break; }
+          if (use_alt) _cos_alpha = gsl_interp_eval(interp_alt, defl_alt_ptr, alpha_alt_ptr, cos_psi, acc_alt);
+          else _cos_alpha = gsl_interp_eval(interp_alpha, defl, calpha, psi, acc_a);
+          sin_alpha = sqrt(1.0 - _cos_alpha * _cos_alpha);
+          mu = _cos_alpha * cos_gamma;
+          if (!are_equal(psi, 0.0)) {
+            double cos_delta = (cos_i - cos_theta_i * cos_psi) / (sin_theta_i * sin_psi);
+            if (theta_i_over_pi < 0.5) mu = mu + sin_alpha * sin_gamma * cos_delta;
+            else mu = mu - sin_alpha * sin_gamma * cos_delta;
+          }
+          lit = mu > 0.0;
+        }
+        if (lit) {
+          if (use_alt) deriv = gsl_interp_eval_deriv(interp_alt, defl_alt_ptr, alpha_alt_ptr, cos_psi, acc_alt);
+          else {
+            deriv = gsl_interp_eval_deriv(interp_alpha, defl, calpha, psi, acc_a);
+            deriv = exp(log(fabs(deriv)) - log(fabs(sin_psi)));
+          }
+          if (psi < interp_lag->xmin || psi > interp_lag->xmax) { terminate = 1; break; }
+          double _phase_lag = gsl_interp_eval(interp_lag, defl, lagr, psi, acc_l);
+          for (int ks = 0; ks < 2; ks++) {                                        /* :376-398 */
+            if ((0 < k && k < leaf_lim - 1) || (k == 0 && ks == 0) ||
+                (k == leaf_lim - 1 && N_L % 2 == 1 && ks == 0) || (k == leaf_lim - 1 && N_L % 2 == 0)) {
+              size_t _kdx = ks == 0 ? k : NL - 1 - k;
+              double superlum, eta;
+              if (!are_equal(psi, 0.0)) {
+                double cos_xi = sin_alpha * sin_i * sin(leaves[_kdx]) / sin_psi;
+                superlum = 1.0 + beta * cos_xi;
+                eta = Lorentz / superlum;
+              } else { superlum = 1.0; eta = Lorentz; }
+              Z[_kdx] = eta * Grav_z;
+              ABB[_kdx] = mu * eta;
+              GEOM[_kdx] = mu * fabs(deriv) * Grav_z * eta * eta * eta / superlum;
+              PHASE[_kdx] = leaves[_kdx] + _phase_lag;
+            }
+          }
+          if (k == 0) {                                                           /* :400-405 */
+            PHASE[NL - 1] = PHASE[0] + 2.0 * M_PI;
+            Z[NL - 1] = Z[0]; ABB[NL - 1] = ABB[0]; GEOM[NL - 1] = GEOM[0];
+          } else if (InvisFlag == 2) {                                            /* :406-437 */
+            double step = leaves[k] / (double)k;
+            double Zs = (Z[k] - Z[NL - k - 1]) / (2.0 * (double)k);
+            double As = (ABB[k] - ABB[NL - k - 1]) / (2.0 * (double)k);
+            for (size_t m = NL - k; m < NL; m++) {
+              PHASE[m] = PHASE[m - 1] + step; Z[m] = Z[m - 1] + Zs; ABB[m] = ABB[m - 1] + As; GEOM[m] = 0.0;
+            }
+            PHASE[0] = PHASE[NL - 1] - 2.0 * M_PI;
+            Z[0] = Z[NL - 1]; ABB[0] = ABB[NL - 1]; GEOM[0] = GEOM[NL - 1];
+            for (size_t m = 1; m < k; m++) {
+              PHASE[m] = PHASE[m - 1] + step; Z[m] = Z[m - 1] + Zs; ABB[m] = ABB[m - 1] + As; GEOM[m] = 0.0;
+            }
+          } else if (InvisFlag == 1) {                                            /* :438-470 */
+            double den = (double)(k - _InvisPhase + 1);
+            double step = (PHASE[k] - PHASE[_InvisPhase - 1]) / den;
+            double Zs = (Z[k] - Z[_InvisPhase - 1]) / den, As = (ABB[k] - ABB[_InvisPhase - 1]) / den;
+            for (size_t m = _InvisPhase; m < k; m++) {
+              PHASE[m] = PHASE[m - 1] + step; Z[m] = Z[m - 1] + Zs; ABB[m] = ABB[m - 1] + As;
+            }
+            step = (PHASE[NL - _InvisPhase] - PHASE[NL - 1 - k]) / den;
+            Zs = (Z[NL - _InvisPhase] - Z[NL - 1 - k]) / den;
+            As = (ABB[NL - _InvisPhase] - ABB[NL - 1 - k]) / den;
+            for (size_t m = NL - k; m < NL - _InvisPhase; m++) {
+              PHASE[m] = PHASE[m - 1] + step; Z[m] = Z[m - 1] + Zs; ABB[m] = ABB[m - 1] + As;
+            }
+          }
+          InvisFlag = 0;
+        } else if (InvisFlag == 0) {                                              /* :475-499 / :500-520 */
+          /* size_t arithmetic as in the reference: for k past the half-way leaf the range is empty */
+          double den = (double)(size_t)(NL - 2 * k + 1);
+          double step = (PHASE[NL - k] - PHASE[k - 1]) / den;
+          double Zs = (Z[NL - k] - Z[k - 1]) / den, As = (ABB[NL - k] - ABB[k - 1]) / den;
+          for (size_t m = k; m < NL - k; m++) {
+            PHASE[m] = PHASE[m - 1] + step; Z[m] = Z[m - 1] + Zs; ABB[m] = ABB[m - 1] + As; GEOM[m] = 0.0;
+          }
+          InvisFlag = 1; _InvisPhase = k;
+        }
+      }
+      if (terminate) break;
+      if (InvisFlag == 2) break;                                                  /* :524-525 */
+      for (size_t m = 1; m < NL; m++) if (PHASE[m] <= PHASE[m - 1]) { terminate = 1; break; }
+      if (terminate) break;
+      gsl_interp_accel_reset(acc_Z); gsl_interp_init(interp_Z, PHASE, Z, NL);     /* :537-542 */
+      gsl_interp_accel_reset(acc_A); gsl_interp_init(interp_ABB, PHASE, ABB, NL);
+      gsl_interp_accel_reset(acc_G); gsl_interp_init(interp_GEOM, PHASE, GEOM, NL);
+      for (int j = 0; j < n_azi && !terminate; j++) {                             /* :544-592 */
+        if (CELL_RADIATES[i * n_azi + j] != 1) continue;
+        const double phi_shift = phi[i * n_azi + j];
+        const double *VEC = srcCellParams + ((size_t)i * n_azi + j) * n_params;
+        for (int k = 0; k < N_P; k++) {
+          double x = phases[k] + phi_shift;
+          if (x > PHASE[NL - 1]) { while (x > PHASE[NL - 1]) x -= 2.0 * M_PI; }
+          else if (x < PHASE[0]) { while (x < PHASE[0]) x += 2.0 * M_PI; }
+          if (x < interp_GEOM->xmin || x > interp_GEOM->xmax) { terminate = 1; break; }
+          double g = gsl_interp_eval(interp_GEOM, PHASE, GEOM, x, acc_G);
+          if (g > 0.0) {
+            double z = gsl_interp_eval(interp_Z, PHASE, Z, x, acc_Z);
+            double abb = gsl_interp_eval(interp_ABB, PHASE, ABB, x, acc_A);
+            for (int p = 0; p < N_E; p++) {
+              double E_prime = energies[p] / z;
+              double I_E = apply_beaming(beam_opt, eval_hot(hot_atm_ext, &tab, E_prime, abb, VEC), E_prime, abb, VEC);
+              I_E *= eval_hot_norm(hot_atm_ext);
+              double c = 0.0;
+              if (perform_correction)
+                c = eval_hot(else_atm_ext, &ctab, E_prime, abb, correction + ((size_t)i * n_azi + j) * n_params) *
+                    eval_hot_norm(else_atm_ext);
+              flux[(size_t)p * N_P + k] += cellArea[i * n_azi + j] * (I_E - c) * g;
+            }
+          }
+        }
+      }
+    }
+    gsl_interp_free(interp_alt);
+  }
+  for (int p = 0; p < N_E; p++) for (int k = 0; k < N_P; k++) flux[(size_t)p * N_P + k] /= (energies[p] * KEV);
+  gsl_interp_free(interp_alpha); gsl_interp_free(interp_lag); gsl_interp_free(interp_Z); gsl_interp_free(interp_ABB);
+  gsl_interp_free(interp_GEOM);
+  gsl_interp_accel_free(acc_a); gsl_interp_accel_free(acc_alt); gsl_interp_accel_free(acc_l);
+  gsl_interp_accel_free(acc_G); gsl_interp_accel_free(acc_Z); gsl_interp_accel_free(acc_A);
+  free(PHASE); free(GEOM); free(Z); free(ABB); free(cos_deflection); free(cos_alpha_alt);
+  return terminate ? ORACLE_ERROR : ORACLE_OK;
+}

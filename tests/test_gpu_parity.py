@@ -462,3 +462,38 @@ def test_integrator_disc_beaming_and_steffen_options(c1, m2):
         assert status == 0 and err < PULSE_RTOL
     finally:
         tools.set_phase_interpolant("Akima")
+
+
+def test_general_integrator_without_azimuthal_invariance(c1, m2):
+    """cellmesh.integrator.integrate (integrator.pyx:48-667): blackbody, beaming, Num4D with uniform and with
+    per-cell parameters, per-cell Num4D elsewhere correction, Steffen interpolant for the GEOM spline."""
+    from test_oracle import _general_cases
+    from xpsi_b200 import tools
+    from xpsi_b200.cellmesh.integrator import integrate
+    cases, d = _general_cases(c1, m2)
+    for name, a, kw, ref in cases:
+        status, flux = integrate(*a, **kw)
+        assert status == 0, name
+        err = _pulse_err(flux, ref)
+        print("general:", name, "rel err", err)
+        assert err < PULSE_RTOL, name
+    try:
+        tools.set_phase_interpolant("Steffen")
+        status, flux = integrate(*cases[0][1])
+        err = _pulse_err(flux, d["c1_steffen"])
+        print("general: Steffen rel err", err)
+        assert status == 0 and err < PULSE_RTOL
+    finally:
+        tools.set_phase_interpolant("Akima")
+    # full energy grid (4 chunks of 32 energies) against the CPU oracle
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import oracle as orc
+    from xpsi_b200 import synthetic as syn
+    a = list(_integrate_args(m2, "t1_int0_", syn.nsx_like_table()))
+    s0, f0 = orc.integrate_general(*a)
+    s1, f1 = integrate(*a)
+    assert s0 == 0 and s1 == 0
+    err = _pulse_err(f1, f0)
+    print("general: m2 t1 member 0, 128 energies vs oracle", err)
+    assert err < PULSE_RTOL

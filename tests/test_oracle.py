@@ -192,3 +192,38 @@ def test_oracle_disc_and_beaming_options(c1, m2):
         assert _pulse_err(flux, ref) < 1e-8, name
     status, flux = orc.integrate(*_integrate_args(c1, "int0_", ()), phase_interpolant="Steffen")
     assert status == 0 and _pulse_err(flux, d["steffen_c1"]) < 1e-12
+
+
+def _general_cases(c1, m2):
+    """inputs + reference outputs of tests/golden/make_golden_general.py (integrator.pyx, energies thinned)"""
+    from xpsi_b200 import synthetic as syn
+    d = np.load(os.path.join(ROOT, "tests", "golden", "general.npz"))
+    m4 = np.load(os.path.join(ROOT, "tests", "golden", "m4_elsewhere.npz"))
+    table = syn.nsx_like_table()
+    S = int(d["e_stride"])
+
+    def args(src, prefix, atmosphere):
+        a = list(_integrate_args(src, prefix, atmosphere))
+        a[19] = np.ascontiguousarray(a[19][::S])
+        return a
+    cases = []
+    cases.append(("c1", args(c1, "int0_", ()), {}, d["c1"]))
+    a = args(c1, "int0_", ()); a[10] = d["c1_beam_params"]; a[26] = 1
+    cases.append(("c1 beam 1", a, {}, d["c1_beam"]))
+    cases.append(("m2 uniform", args(m2, "t0_int1_", table), {}, d["m2"]))
+    a = args(m2, "t0_int1_", table); a[10] = d["m2_var_params"]
+    cases.append(("m2 per-cell parameters", a, {}, d["m2_var"]))
+    a = args(m4, "int0_", table); a[12] = d["m4_corr_params"]; a[23] = table; a[25] = 2
+    cases.append(("m4 per-cell Num4D correction", a, {}, d["m4_corr"]))
+    return cases, d
+
+
+def test_oracle_general_integrator(c1, m2):
+    cases, d = _general_cases(c1, m2)
+    for name, a, kw, ref in cases:
+        status, flux = orc.integrate_general(*a, **kw)
+        assert status == 0, name
+        assert _pulse_err(flux, ref) < 1e-12, name
+    a = cases[0][1]
+    status, flux = orc.integrate_general(*a, phase_interpolant="Steffen")
+    assert status == 0 and _pulse_err(flux, d["c1_steffen"]) < 1e-12

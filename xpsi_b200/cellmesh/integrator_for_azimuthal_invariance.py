@@ -15,6 +15,18 @@ def integrate(numThreads, R, omega, r_s, inclination, cellArea, radialCoords_of_
     ``(0, flux[N_E, N_P])`` on success, ``(1, None)`` on a numerical error.
     ``numThreads`` is accepted and ignored.
     """
+    return _integrate(_lib.lib.xpsi_b200_integrate_azimuthal_invariance, R, omega, r_s, inclination, cellArea,
+                      radialCoords_of_parallels, r_s_over_r, theta, phi, srcCellParams, CELL_RADIATES,
+                      correction_srcCellParams, numRays, deflection, cos_alpha, lag, maxDeflection,
+                      cos_gammaArray, energies, leaves, phases, hot_atmosphere, elsewhere_atmosphere,
+                      hot_atm_ext, else_atm_ext, beam_opt, image_order_limit, R_in)
+
+
+def _integrate(entry, R, omega, r_s, inclination, cellArea, radialCoords_of_parallels, r_s_over_r, theta, phi,
+               srcCellParams, CELL_RADIATES, correction_srcCellParams, numRays, deflection, cos_alpha, lag,
+               maxDeflection, cos_gammaArray, energies, leaves, phases, hot_atmosphere, elsewhere_atmosphere,
+               hot_atm_ext, else_atm_ext, beam_opt, image_order_limit, R_in):
+    """Marshal one hot-region member to a C-ABI pulse integrator (shared with ``cellmesh.integrator``)."""
     cellArea = _lib.as_f8(cellArea, 2)
     n_rings, n_azi = cellArea.shape
     theta = _lib.as_f8(theta, 2)
@@ -37,7 +49,7 @@ def integrate(numThreads, R, omega, r_s, inclination, cellArea, radialCoords_of_
     hot = _lib.Atmosphere.get(hot_atmosphere)
     els = _lib.Atmosphere.get(elsewhere_atmosphere) if corr is not None else None
     flux = np.zeros((energies.shape[0], phases.shape[0]), dtype=np.float64)
-    rc = _lib.lib.xpsi_b200_integrate_azimuthal_invariance(
+    rc = entry(
         float(R), float(omega), float(r_s), float(inclination), n_rings, n_azi,
         _lib.dptr(cellArea), _lib.dptr(radial), _lib.dptr(rsr), _lib.dptr(theta), _lib.dptr(phi),
         _lib.dptr(srcCellParams), srcCellParams.shape[2], _lib.iptr(CELL_RADIATES),

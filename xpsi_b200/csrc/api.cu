@@ -150,7 +150,8 @@ xpsi_b200_atmosphere* xpsi_b200_atmosphere_create(const double* logT, int nT, co
 
 void xpsi_b200_atmosphere_destroy(xpsi_b200_atmosphere* atm) { delete atm; }
 
-int xpsi_b200_integrate_azimuthal_invariance(
+static int integrate_member(
+    int general,
     double R, double omega, double r_s, double inclination, int n_rings, int n_azi,
     const double* cellArea, const double* radial, const double* r_s_over_r, const double* theta,
     const double* phi, const double* srcCellParams, int n_params, const int* CELL_RADIATES,
@@ -219,6 +220,7 @@ int xpsi_b200_integrate_azimuthal_invariance(
   if (hot_atm_ext == XPSI_B200_ATM_NUM4D) {
     a.hot = hot_atmosphere->view;
     xb::azinv_slab_budgets(a.hot, energies, n_energies, &a.slab_ne_max, &a.slab_rows_ring);
+    if (general) a.slab_ne_max = xb::general_slab_rows(a.hot, energies, n_energies);
   }
   if (correction_srcCellParams) {
     a.corrParams = d_corr.p; a.else_atm_ext = else_atm_ext;
@@ -226,6 +228,7 @@ int xpsi_b200_integrate_azimuthal_invariance(
       a.els = elsewhere_atmosphere->view;
       int rc2 = 0, rr2 = 0;
       xb::azinv_slab_budgets(a.els, energies, n_energies, &rc2, &rr2);
+      if (general) rc2 = xb::general_slab_rows(a.els, energies, n_energies);
       if (rc2 > a.slab_ne_max) a.slab_ne_max = rc2;
       if (rr2 > a.slab_rows_ring) a.slab_rows_ring = rr2;
     }
@@ -241,19 +244,58 @@ int xpsi_b200_integrate_azimuthal_invariance(
   {
     size_t nl, nh, ni, ns;
     xb::azinv_workspace_sizes(a, &nl, &nh, &ni, &ns);
-    CK(d_ws.alloc(nl)); CK(d_wh.alloc(nh)); CK(d_wi.alloc(ni)); CK(d_wslab.alloc(ns));
-    if (a.else_atm_ext == XPSI_B200_ATM_NUM4D) CK(d_wslab2.alloc(ns));
+    CK(d_ws.alloc(nl)); CK(d_wh.alloc(nh)); CK(d_wi.alloc(ni));
+    if (!general) {
+      CK(d_wslab.alloc(ns));
+      if (a.else_atm_ext == XPSI_B200_ATM_NUM4D) CK(d_wslab2.alloc(ns));
+    }
   }
   a.ws_leaf = d_ws.p; a.ws_hdr = d_wh.p; a.ws_ihdr = d_wi.p; a.ws_slab = d_wslab.p; a.ws_slab2 = d_wslab2.p;
-  cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
-  if (e != cudaSuccess) return cuda_fail(e, "launch_integrate_azinv");
-  g_launches += (hot_atm_ext == XPSI_B200_ATM_NUM4D) ? 4 : 3;
+  cudaError_t e = general ? xb::launch_integrate_general(a, g_stream) : xb::launch_integrate_azinv(a, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, general ? "launch_integrate_general" : "launch_integrate_azinv");
+  g_launches += general ? 3 : ((hot_atm_ext == XPSI_B200_ATM_NUM4D) ? 4 : 3);
   int status = 0;
   CK(d_flux.download(flux_out, (size_t)n_energies * n_phases));
   CK(d_status.download(&status, 1));
   CK(cudaStreamSynchronize(g_stream));
   if (status != 0) return fail(status, status == 1 ? "numerical error in pulse integration" : "unsupported configuration");
   return 0;
+}
+
+int xpsi_b200_integrate_azimuthal_invariance(
+    double R, double omega, double r_s, double inclination, int n_rings, int n_azi,
+    const double* cellArea, const double* radial, const double* r_s_over_r, const double* theta,
+    const double* phi, const double* srcCellParams, int n_params, const int* CELL_RADIATES,
+    const double* correction_srcCellParams, int numRays, const double* deflection,
+    const double* cos_alpha, const double* lag, const double* maxDeflection,
+    const double* cos_gammaArray, int n_energies, const double* energies, int n_leaves,
+    const double* leaves, int n_phases, const double* phases,
+    const xpsi_b200_atmosphere* hot_atmosphere, const xpsi_b200_atmosphere* elsewhere_atmosphere,
+    int hot_atm_ext, int else_atm_ext, int beam_opt, int image_order_limit, double R_in,
+    int phase_interpolant, double* flux_out) {
+  return integrate_member(0, R, omega, r_s, inclination, n_rings, n_azi, cellArea, radial, r_s_over_r, theta, phi,
+                          srcCellParams, n_params, CELL_RADIATES, correction_srcCellParams, numRays, deflection,
+                          cos_alpha, lag, maxDeflection, cos_gammaArray, n_energies, energies, n_leaves, leaves,
+                          n_phases, phases, hot_atmosphere, elsewhere_atmosphere, hot_atm_ext, else_atm_ext,
+                          beam_opt, image_order_limit, R_in, phase_interpolant, flux_out);
+}
+
+int xpsi_b200_integrate_general(
+    double R, double omega, double r_s, double inclination, int n_rings, int n_azi,
+    const double* cellArea, const double* radial, const double* r_s_over_r, const double* theta,
+    const double* phi, const double* srcCellParams, int n_params, const int* CELL_RADIATES,
+    const double* correction_srcCellParams, int numRays, const double* deflection,
+    const double* cos_alpha, const double* lag, const double* maxDeflection,
+    const double* cos_gammaArray, int n_energies, const double* energies, int n_leaves,
+    const double* leaves, int n_phases, const double* phases,
+    const xpsi_b200_atmosphere* hot_atmosphere, const xpsi_b200_atmosphere* elsewhere_atmosphere,
+    int hot_atm_ext, int else_atm_ext, int beam_opt, int image_order_limit, double R_in,
+    int phase_interpolant, double* flux_out) {
+  return integrate_member(1, R, omega, r_s, inclination, n_rings, n_azi, cellArea, radial, r_s_over_r, theta, phi,
+                          srcCellParams, n_params, CELL_RADIATES, correction_srcCellParams, numRays, deflection,
+                          cos_alpha, lag, maxDeflection, cos_gammaArray, n_energies, energies, n_leaves, leaves,
+                          n_phases, phases, hot_atmosphere, elsewhere_atmosphere, hot_atm_ext, else_atm_ext,
+                          beam_opt, image_order_limit, R_in, phase_interpolant, flux_out);
 }
 
 int xpsi_b200_integrate_time_invariance(

@@ -37,6 +37,7 @@
 //   * rings/chunks are combined with fp64 RED atomics into flux[q, E, P].
 #include "common.cuh"
 #include "kernels.h"
+#include "azinv_shared.cuh"
 
 namespace xb {
 
@@ -44,9 +45,6 @@ constexpr int kNEC = 8;            // energies per flux CTA
 constexpr int kGeomThreads = 128;
 constexpr int kFluxThreads = 128;
 
-__device__ __forceinline__ double bb_intensity(double E, double kT) {
-  return E * E * E / (exp(E / kT) - 1.0);     // hot_BB.pyx:85-87
-}
 
 // accretion-disc occultation, Ibragimov & Poutanen (2009) (common_functions.pyx:110-138): 1 = ray not blocked
 __device__ __forceinline__ int disk_block(double R_in, double cos_i, double cos_psi, double cos_theta_i,
@@ -63,16 +61,6 @@ __device__ __forceinline__ int disk_block(double R_in, double cos_i, double cos_
   return (theta_i_over_pi < 0.5 || (theta_i_over_pi > 0.5 && r_psi_d < R_in)) ? 1 : 0;
 }
 
-// per-ring headers written by the geometry kernel
-//   ints   [0] image orders to integrate  [1] first radiating cell  [2],[3] (T,g) base nodes
-//          [4],[5] first row / row count of the ring's slab (written by k_azinv_slab)
-//   doubles [0],[1] min/max of Z (log10 Z for Num4D) over lit leaves  [2..5] T weights
-//          [6..9] g weights  [10] log10 T  [11] log10 g  [12] kT (keV)  [13] log10 kT
-//          [14] intensity normalisation (hot_BB.pyx:98 / hot_Num4D.pyx:436-460)
-//   elsewhere correction (pyx:257-268): the same block of doubles again at +kCorrD for the ring's
-//   correction parameters; ints [6],[7] its (T,g) base nodes, [8],[9] its slab rows
-constexpr int kIHdr = 12, kDHdr = 32, kCorrD = 16;
-
 // order-preserving map double <-> unsigned 64 (for shared-memory atomicMin/Max)
 __device__ __forceinline__ unsigned long long order_key(double v) {
   const unsigned long long u = (unsigned long long)__double_as_longlong(v);
@@ -81,11 +69,6 @@ __device__ __forceinline__ unsigned long long order_key(double v) {
 __device__ __forceinline__ double key_order(unsigned long long k) {
   const unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
   return __longlong_as_double((long long)u);
-}
-
-// leaf workspace layout: [ring][image][4][N_L]
-__device__ __forceinline__ double* leaf_ptr(double* ws, long ring, int n_img_max, int I, int N_L) {
-  return ws + ((ring * n_img_max + I) * 4) * (long)N_L;
 }
 
 // ===========================================================================
@@ -129,6 +112,8 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
   double* s_cosd = sp; sp += N_R;
   double* s_ptrue = sp; sp += (long)n_img_max * N_L;
   double* s_phase = sp; sp += (long)n_img_max * N_L;
+  double* s_gZ = nullptr; double* s_gA = nullptr;       // general integrator: Z and mu*eta are splined too
+  if (a.general) { s_gZ = sp; sp += (long)n_img_max * N_L; s_gA = sp; sp += (long)n_img_max * N_L; }
   int* s_vis = reinterpret_cast<int*>(sp);              // [n_img_max][N_L]
 
   const double* g_defl = a.deflection + ring * N_R;
@@ -229,6 +214,12 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
         eta = Lorentz / superlum;
       } else { superlum = 1.0; eta = Lorentz; }
       const double Z = eta * Grav_z;
+      if (a.general) {                 // integrator.pyx:394-397: raw Z and mu*eta, splined over the leaves later
+        s_gZ[I * N_L + kdx] = Z; s_gA[I * N_L + kdx] = mu * eta;
+        wGeom[kdx] = mu * fabs(deriv) * Grav_z * eta * eta * eta / superlum;
+        s_ptrue[I * N_L + kdx] = a.leaves[kdx] + lagv;
+        continue;
+      }
       const double zstore = (ATM == 2) ? log10(Z) : Z;
       wZ[kdx] = zstore;
       atomicMin(&s_zlo[I], order_key(zstore));
@@ -248,6 +239,62 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
     const double* PT = s_ptrue + tid * N_L;
     int* vis = s_vis + tid * N_L;
     int Inv = 2, k0 = 0;
+    if (a.general) {
+      // integrator.pyx:316-520: the leaf loop runs over ALL leaves (the upper half only drives the
+      // flags and re-fills ranges), and Z / mu*eta are stepped linearly across dark ranges
+      double* Zs = s_gZ + tid * N_L;
+      double* As = s_gA + tid * N_L;
+      for (int k = 0; k < N_L; ++k) {
+        if (vis[k]) {
+          if (k < leaf_lim) {
+            PH[k] = PT[k];
+            const bool mirror = (0 < k && k < leaf_lim - 1) || (k == leaf_lim - 1 && N_L % 2 == 0);
+            if (mirror) PH[N_L - 1 - k] = PT[N_L - 1 - k];
+          }
+          if (k == 0) {
+            PH[N_L - 1] = PH[0] + kTwoPi;
+            Zs[N_L - 1] = Zs[0]; As[N_L - 1] = As[0]; wGeom[N_L - 1] = wGeom[0];
+            vis[N_L - 1] = 1;
+          } else if (Inv == 2) {
+            const double step = a.leaves[k] / (double)k;
+            const double zs = (Zs[k] - Zs[N_L - k - 1]) / (2.0 * (double)k);
+            const double as = (As[k] - As[N_L - k - 1]) / (2.0 * (double)k);
+            for (int m = N_L - k; m < N_L; ++m) {
+              PH[m] = PH[m - 1] + step; Zs[m] = Zs[m - 1] + zs; As[m] = As[m - 1] + as; wGeom[m] = 0.0;
+            }
+            PH[0] = PH[N_L - 1] - kTwoPi;
+            Zs[0] = Zs[N_L - 1]; As[0] = As[N_L - 1]; wGeom[0] = wGeom[N_L - 1];
+            for (int m = 1; m < k; ++m) {
+              PH[m] = PH[m - 1] + step; Zs[m] = Zs[m - 1] + zs; As[m] = As[m - 1] + as; wGeom[m] = 0.0;
+            }
+          } else if (Inv == 1) {
+            const double den = (double)(k - k0 + 1);
+            double step = (PH[k] - PH[k0 - 1]) / den;
+            double zs = (Zs[k] - Zs[k0 - 1]) / den, as = (As[k] - As[k0 - 1]) / den;
+            for (int m = k0; m < k; ++m) { PH[m] = PH[m - 1] + step; Zs[m] = Zs[m - 1] + zs; As[m] = As[m - 1] + as; }
+            step = (PH[N_L - k0] - PH[N_L - 1 - k]) / den;
+            zs = (Zs[N_L - k0] - Zs[N_L - 1 - k]) / den; as = (As[N_L - k0] - As[N_L - 1 - k]) / den;
+            for (int m = N_L - k; m < N_L - k0; ++m) {
+              PH[m] = PH[m - 1] + step; Zs[m] = Zs[m - 1] + zs; As[m] = As[m - 1] + as;
+            }
+          }
+          Inv = 0;
+        } else {
+          if (k == 0) { vis[N_L - 1] = 0; wGeom[N_L - 1] = 0.0; }
+          if (Inv == 0) {
+            if (N_L - k > k) {          // past the half-way leaf the reference's range is empty
+              const double den = (double)(N_L - 2 * k + 1);
+              const double step = (PH[N_L - k] - PH[k - 1]) / den;
+              const double zs = (Zs[N_L - k] - Zs[k - 1]) / den, as = (As[N_L - k] - As[k - 1]) / den;
+              for (int m = k; m < N_L - k; ++m) {
+                PH[m] = PH[m - 1] + step; Zs[m] = Zs[m - 1] + zs; As[m] = As[m - 1] + as; wGeom[m] = 0.0;
+              }
+            }
+            Inv = 1; k0 = k;
+          }
+        }
+      }
+    } else
     for (int k = 0; k < leaf_lim; ++k) {
       if (vis[k]) {
         PH[k] = PT[k];
@@ -355,7 +402,9 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
   n_img = s_nimg;
   for (int t = tid; t < n_img * N_L; t += kGeomThreads) {
     const int I = t / N_L, l = t - I * N_L;
-    leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L)[l] = s_phase[t];
+    double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
+    W[l] = s_phase[t];
+    if (a.general) { W[N_L + l] = s_gZ[t]; W[2 * N_L + l] = s_gA[t]; }
   }
 }
 
@@ -865,8 +914,23 @@ __global__ void k_scale_flux(double* flux, const double* energies, int Q, int N_
 }
 
 static size_t geom_smem_bytes(const AzinvArgs& a) {
-  return (4ul * a.n_rays + 2ul * a.n_img_max * a.n_leaves) * sizeof(double) +
+  return (4ul * a.n_rays + (a.general ? 4ul : 2ul) * a.n_img_max * a.n_leaves) * sizeof(double) +
          (size_t)a.n_img_max * a.n_leaves * sizeof(int);
+}
+
+cudaError_t launch_azinv_geometry(const AzinvArgs& a, cudaStream_t stream) {
+  const size_t gsm = geom_smem_bytes(a);
+  if (gsm > 227 * 1024) return cudaErrorInvalidValue;
+  dim3 ggrid(a.n_rings, a.Q);
+  cudaError_t err;
+  if (a.hot_atm_ext == 1) {
+    if ((err = cudaFuncSetAttribute(k_azinv_geometry<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm)) != cudaSuccess) return err;
+    k_azinv_geometry<1><<<ggrid, kGeomThreads, gsm, stream>>>(a);
+  } else {
+    if ((err = cudaFuncSetAttribute(k_azinv_geometry<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm)) != cudaSuccess) return err;
+    k_azinv_geometry<2><<<ggrid, kGeomThreads, gsm, stream>>>(a);
+  }
+  return cudaGetLastError();
 }
 
 static size_t flux_smem_bytes(const AzinvArgs& a, int atm, int corr) {
@@ -941,14 +1005,9 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
   dim3 ggrid(a.n_rings, a.Q), fgrid(a.n_rings * n_chunks, a.Q);
   cudaError_t err;
-  if (atm == 1) {
-    if ((err = cudaFuncSetAttribute(k_azinv_geometry<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm)) != cudaSuccess) return err;
-    k_azinv_geometry<1><<<ggrid, kGeomThreads, gsm, stream>>>(a);
-  } else {
-    if ((err = cudaFuncSetAttribute(k_azinv_geometry<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm)) != cudaSuccess) return err;
-    k_azinv_geometry<2><<<ggrid, kGeomThreads, gsm, stream>>>(a);
-    k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 0);
-  }
+  a.general = 0;
+  if ((err = launch_azinv_geometry(a, stream)) != cudaSuccess) return err;
+  if (atm == 2) k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 0);
   if (corr == 2) k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 1);
   if (a.ws_mom) {
     if (!a.ws_meta || !a.ws_cnt || a.mom_cap < 1 || a.n_azi > 0xffff) return cudaErrorInvalidValue;

@@ -44,6 +44,7 @@ struct AzinvArgs {
   int slab_ne_max;                   // Num4D: energy rows a flux CTA may hold in shared memory
   int slab_rows_ring;                // Num4D: energy rows per ring in the slab workspace
   int scale_by_energy;               // apply flux /= E keV (pyx:610-612)
+  int general;                       // set by the launchers: 1 = geometry for integrator.pyx (no azimuthal invariance)
   double* flux;                      // [Q][N_E][N_P], zero-initialised by the caller
   int* status;                       // [Q]
   // workspaces (sizes from azinv_workspace_sizes)
@@ -58,6 +59,10 @@ struct AzinvArgs {
                                      //   RI (ring,image) pairs reaching the phase stage, K radiating cells over RI
 };
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream);
+// a2: cellmesh/integrator.pyx (no azimuthal invariance); same argument block, parameters read per cell.
+// Uses ws_leaf / ws_hdr / ws_ihdr only; slab_ne_max = energy rows a CTA may hold (general_slab_rows)
+cudaError_t launch_integrate_general(AzinvArgs a, cudaStream_t stream);
+int general_slab_rows(const AtmTable& t, const double* host_energies, int n_energies);
 void azinv_workspace_sizes(const AzinvArgs& a, size_t* leaf_doubles, size_t* hdr_doubles, size_t* ihdr_ints,
                            size_t* slab_doubles);
 void azinv_moment_sizes(const AzinvArgs& a, size_t* mom_doubles, size_t* meta_int2, size_t* cnt_ints);
