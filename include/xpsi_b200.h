@@ -139,6 +139,16 @@ int xpsi_b200_energy_interpolator(const double* signal, int n_energies, int n_ph
                                   const double* new_log10_energies, int n_new, int energy_interpolant,
                                   double* out);
 
+/* ---- surface_radiation_field.intensity -----------------------------------------
+ * replaces xpsi/surface_radiation_field/core.pyx:125-308: photon specific intensity
+ * [photons/s/keV/cm^2/sr] at n points (energy keV, mu, local variables row) evaluated
+ * directly by the atmosphere extension: atm_ext 1 (hot_BB.pyx:54-98) or 2 (hot_Num4D.pyx:248-460);
+ * region_extension 0 = hot (beam_opt 0-3 of hot_wrapper.pyx:155-199, needs 7 variables per
+ * point when beam_opt != 0), 1 = elsewhere (beam_opt ignored, elsewhere_wrapper.pyx:50-68). */
+int xpsi_b200_intensity(int n, const double* energies, const double* mu, const double* local_variables,
+                        int n_vars, const xpsi_b200_atmosphere* atmosphere, int region_extension, int atm_ext,
+                        int beam_opt, double* out);
+
 /* ---- Interstellar.__call__ ------------------------------------------------------------
  * replaces the in-place row scaling of xpsi/Interstellar.py:27-58:
  * signal[i][:] *= attenuation[i], signal [n_rows][n_cols] modified in place.           */

@@ -96,6 +96,21 @@ def integrate_general(numThreads, R, omega, r_s, inclination, cellArea, radialCo
     return (1, None) if rc else (0, flux)
 
 
+def intensity(energies, mu, local_variables, atmosphere=None, stokesQ=0, region_extension='hot',
+              atmos_extension="BB", beam_opt=0, numTHREADS=1):
+    """xpsi/surface_radiation_field/core.pyx:125-308 ('BB' and 'Num4D', Stokes I)."""
+    assert stokesQ == 0 and atmos_extension in ("BB", "Num4D")
+    E, m, v = _f8(energies), _f8(mu), _f8(local_variables)
+    tab = [_f8(t) for t in atmosphere] if atmosphere else [np.zeros(4)] * 5
+    out = np.zeros(E.size)
+    lib.oracle_intensity(C.c_int(E.size), _d(E), _d(m), _d(v), C.c_int(v.shape[1]),
+                         C.c_int(0 if region_extension == 'hot' else 1), C.c_int(1 if atmos_extension == "BB" else 2),
+                         _d(tab[0]), C.c_int(tab[0].size), _d(tab[1]), C.c_int(tab[1].size), _d(tab[2]),
+                         C.c_int(tab[2].size), _d(tab[3]), C.c_int(tab[3].size), _d(tab[4]), C.c_int(int(beam_opt)),
+                         _d(out))
+    return out
+
+
 def _correction_args(correction, atmosphere, else_atm_ext):
     if correction is None:
         z = np.zeros(4)

@@ -887,3 +887,43 @@ int oracle_integrate_general(
   free(PHASE); free(GEOM); free(Z); free(ABB); free(cos_deflection); free(cos_alpha_alt);
   return terminate ? ORACLE_ERROR : ORACLE_OK;
 }
+
+/* -------------------------------------------- surface_radiation_field/core.pyx:125-308 (intensity)
+ * region 0 = hot (hot_wrapper.pyx:110-199 incl. beaming options 1-3), 1 = elsewhere
+ * (elsewhere_wrapper.pyx:50-68, beam_opt ignored). */
+int oracle_intensity(int n, const double *energies, const double *mu, const double *vars, int n_vars,
+                     int region, int atm_ext, const double *logT, int nT, const double *logg, int ng,
+                     const double *mu_ax, int nmu, const double *logE, int nE, const double *buf, int beam_opt,
+                     double *out) {
+  atm_table tab = {{logT, logg, mu_ax, logE}, {nT, ng, nmu, nE}, buf};
+  for (int i = 0; i < n; i++) {
+    const double *VEC = vars + (size_t)i * n_vars;
+    double E = energies[i], m = mu[i];
+    double I = eval_hot(atm_ext, &tab, E, m, VEC);
+    if (region == 0 && beam_opt != 0) {
+      double abb = VEC[2], bbb = VEC[3], cbb = VEC[4], dbb = VEC[5], nimu = VEC[6];
+      double beam = 0.0;
+      if (beam_opt == 1) beam = (1.0 + abb * pow(E, cbb) * m + bbb * pow(E, dbb) * m * m) * I;
+      if (beam_opt == 2) {
+        double anorm = 0.5 / (0.5 + (1.0 / 3.0) * abb * pow(E, cbb) + (1.0 / 4.0) * bbb * pow(E, dbb));
+        beam = anorm * (1.0 + abb * pow(E, cbb) * m + bbb * pow(E, dbb) * m * m) * I;
+      }
+      if (beam_opt == 3) {
+        double mu_imu = 0.0, I_nom = 0.0, I_denom = 0.0;
+        for (size_t imu = 0; imu < (size_t)nimu; imu++) {
+          mu_imu = mu_imu + (1.0 / nimu);
+          double dmu = (imu == 0 || imu == nimu - 1) ? (0.5 / nimu) : (1.0 / nimu);
+          double Ii = eval_hot(atm_ext, &tab, E, mu_imu, VEC);
+          double f = 1.0 + abb * pow(E, cbb) * mu_imu + bbb * pow(E, dbb) * mu_imu * mu_imu;
+          I_denom = I_denom + mu_imu * f * Ii * dmu;
+          I_nom = I_nom + mu_imu * Ii * dmu;
+        }
+        beam = are_equal(I_denom, 0.0) ? 0.0
+                                       : (I_nom / I_denom) * (1.0 + abb * pow(E, cbb) * m + bbb * pow(E, dbb) * m * m) * I;
+      }
+      I = beam < 0.0 ? 0.0 : beam;
+    }
+    out[i] = I * eval_hot_norm(atm_ext) / (E * KEV);
+  }
+  return ORACLE_OK;
+}

@@ -497,3 +497,17 @@ def test_general_integrator_without_azimuthal_invariance(c1, m2):
     err = _pulse_err(f1, f0)
     print("general: m2 t1 member 0, 128 energies vs oracle", err)
     assert err < PULSE_RTOL
+
+
+def test_surface_radiation_field_intensity():
+    """surface_radiation_field.intensity (core.pyx:125-308): BB / Num4D, hot with beam_opt 0-3, elsewhere."""
+    from test_oracle import _intensity_cases, _point_err
+    from xpsi_b200.surface_radiation_field import intensity
+    for name, a, ref in _intensity_cases():
+        err = _point_err(intensity(*a), ref)
+        print("intensity:", name, "point-wise rel err", err)
+        assert err < PULSE_RTOL, name
+    with pytest.raises(ValueError):
+        intensity(np.ones(2), np.ones(2), np.ones((2, 2)), None, 0, 'nowhere', 'BB')
+    with pytest.raises(ValueError):
+        intensity(np.ones(2), np.ones(2), np.ones((2, 2)), None, 0, 'hot', 'Num4D')

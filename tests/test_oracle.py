@@ -227,3 +227,29 @@ def test_oracle_general_integrator(c1, m2):
     a = cases[0][1]
     status, flux = orc.integrate_general(*a, phase_interpolant="Steffen")
     assert status == 0 and _pulse_err(flux, d["c1_steffen"]) < 1e-12
+
+
+def _intensity_cases():
+    from xpsi_b200 import synthetic as syn
+    d = np.load(os.path.join(ROOT, "tests", "golden", "intensity.npz"))
+    table = syn.nsx_like_table()
+    cases = []
+    for atm, name in ((None, "BB"), (table, "Num4D")):
+        for opt in (0, 1, 2, 3):
+            cases.append(("hot %s beam %d" % (name, opt),
+                          (d["energies"], d["mu"], d["local_variables"], atm, 0, 'hot', name, opt),
+                          d["hot_%s_beam%d" % (name, opt)]))
+        cases.append(("elsewhere %s" % name,
+                      (d["energies"], d["mu"], np.ascontiguousarray(d["local_variables"][:, :2]), atm, 0,
+                       'elsewhere', name, 0), d["elsewhere_%s" % name]))
+    return cases
+
+
+def _point_err(out, ref):
+    """point-wise relative error; points more than 30 decades below the largest carry no weight"""
+    return float(np.max(np.abs(out - ref) / np.maximum(np.abs(ref), 1e-30 * np.max(np.abs(ref)))))
+
+
+def test_oracle_intensity_seam():
+    for name, a, ref in _intensity_cases():
+        assert _point_err(orc.intensity(*a), ref) < 1e-9, name

@@ -121,6 +121,8 @@ _proto("xpsi_b200_integrate_general", C.c_int,
         C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
         C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, c_double_p,
         C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, c_double_p])
+_proto("xpsi_b200_intensity", C.c_int,
+       [C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p])
 _proto("xpsi_b200_integrate_time_invariance", C.c_int,
        [C.c_double] * 4 + [C.c_int, C.c_double] + [c_double_p] * 5 + [C.c_int, C.c_int] + [c_double_p] * 4 +
        [C.c_int, c_double_p, C.c_void_p, C.c_int, C.c_int, c_double_p])
@@ -162,7 +164,7 @@ _proto("xpsi_b200_pipeline_stage_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)
 EXPORTED = [
     "xpsi_b200_last_error", "xpsi_b200_device_count", "xpsi_b200_set_device", "xpsi_b200_counters",
     "xpsi_b200_stream", "xpsi_b200_atmosphere_create", "xpsi_b200_atmosphere_destroy",
-    "xpsi_b200_integrate_azimuthal_invariance", "xpsi_b200_integrate_general", "xpsi_b200_energy_integrator",
+    "xpsi_b200_integrate_azimuthal_invariance", "xpsi_b200_integrate_general", "xpsi_b200_intensity", "xpsi_b200_energy_integrator",
     "xpsi_b200_instrument_fold", "xpsi_b200_precomputation", "xpsi_b200_eval_marginal_likelihood",
     "xpsi_b200_pipeline_create", "xpsi_b200_pipeline_destroy", "xpsi_b200_pipeline_eval",
     "xpsi_b200_pipeline_upload", "xpsi_b200_pipeline_eval_resident", "xpsi_b200_pipeline_download",

@@ -446,6 +446,36 @@ int xpsi_b200_energy_interpolator(const double* signal, int n_energies, int n_ph
                          new_log10_energies, n_new, n_new, 2, 0.0, 1.0, 1, energy_interpolant, 0, out, 1, n_phases);
 }
 
+int xpsi_b200_intensity(int n, const double* energies, const double* mu, const double* local_variables,
+                        int n_vars, const xpsi_b200_atmosphere* atmosphere, int region_extension, int atm_ext,
+                        int beam_opt, double* out) {
+  int rc = ensure_stream();
+  if (rc) return rc;
+  if (n < 1 || n_vars < 1) return fail(XPSI_B200_EINVAL, "bad dimensions");
+  if (atm_ext != XPSI_B200_ATM_BB && atm_ext != XPSI_B200_ATM_NUM4D)
+    return fail(XPSI_B200_EUNSUPPORTED, "atmosphere extension must be BB (1) or Num4D (2)");
+  if (atm_ext == XPSI_B200_ATM_NUM4D && !atmosphere) return fail(XPSI_B200_EINVAL, "Num4D needs a preloaded atmosphere");
+  if (atm_ext == XPSI_B200_ATM_NUM4D && n_vars < 2) return fail(XPSI_B200_EINVAL, "Num4D needs (log T, log g)");
+  if (region_extension != 0 && region_extension != 1) return fail(XPSI_B200_EINVAL, "region must be 0 (hot) or 1 (elsewhere)");
+  if (beam_opt < 0 || beam_opt > 3) return fail(XPSI_B200_EINVAL, "beam_opt must be 0-3");
+  if (region_extension == 0 && beam_opt != 0 && n_vars < 7)
+    return fail(XPSI_B200_EINVAL, "beaming needs 7 local variables per point");
+  Dev<double> d_E, d_mu, d_v, d_o;
+  CK(d_E.upload(energies, n)); CK(d_mu.upload(mu, n)); CK(d_v.upload(local_variables, (size_t)n * n_vars));
+  CK(d_o.alloc(n));
+  xb::IntensityArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n; a.n_vars = n_vars; a.energies = d_E.p; a.mu = d_mu.p; a.vars = d_v.p;
+  if (atmosphere) a.atm = atmosphere->view;
+  a.atm_ext = atm_ext; a.region = region_extension; a.beam_opt = beam_opt; a.out = d_o.p;
+  cudaError_t e = xb::launch_intensity(a, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_intensity");
+  g_launches += 1;
+  CK(d_o.download(out, n));
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
 int xpsi_b200_interstellar_attenuate(const double* attenuation, int n_rows, int n_cols, double* signal) {
   int rc = ensure_stream();
   if (rc) return rc;

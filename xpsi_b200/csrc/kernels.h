@@ -162,6 +162,17 @@ struct MarginalArgs {
 };
 cudaError_t launch_marginal(MarginalArgs a, cudaStream_t stream);
 
+// surface_radiation_field.intensity (core.pyx:125-308): point-wise intensities from local variables
+struct IntensityArgs {
+  int n, n_vars;
+  const double* energies; const double* mu; const double* vars;     // [n], [n], [n][n_vars]
+  AtmTable atm; int atm_ext;         // 1 blackbody, 2 Num4D
+  int region;                        // 0 hot (beaming applies), 1 elsewhere
+  int beam_opt;                      // 0-3 (hot_wrapper.pyx:155-199)
+  double* out;                       // [n] photons/s/keV/cm^2/sr
+};
+cudaError_t launch_intensity(IntensityArgs a, cudaStream_t stream);
+
 // a10: Interstellar.__call__
 cudaError_t launch_attenuate(const double* att, int n_rows, int n_cols, double* signal, cudaStream_t stream);
 

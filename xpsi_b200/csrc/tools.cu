@@ -213,6 +213,81 @@ cudaError_t launch_attenuate(const double* att, int n_rows, int n_cols, double* 
 }
 
 // ---------------------------------------------------------------------------
+// surface_radiation_field.intensity (xpsi/surface_radiation_field/core.pyx:125-308): point-wise photon
+// specific intensity straight from local variables.  hot_BB.pyx:54-98 / hot_Num4D.pyx:248-460 with the
+// beaming modifications of hot_wrapper.pyx:155-199 (options 1-3); the elsewhere extension ignores beam_opt
+// (elsewhere_wrapper.pyx:50-68).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double point_num4d(const AtmTable& T, double logT, double logg, double mu, double E) {
+  View vT{T.logT, 1}, vG{T.logg, 1}, vM{T.mu, 1}, vE{T.logE, 1};
+  const double v = log10(E / (kKBOverKeV * pow(10.0, logT)));
+  const int bT = lagrange_base(vT, T.nT, logT), bG = lagrange_base(vG, T.ng, logg);
+  const int bM = lagrange_base(vM, T.nmu, mu), bE = lagrange_base(vE, T.nE, v);
+  double wT[4], wG[4], wM[4], wE[4];
+  lagrange_weights(vT, bT, logT, wT); lagrange_weights(vG, bG, logg, wG);
+  lagrange_weights(vM, bM, mu, wM); lagrange_weights(vE, bE, v, wE);
+  const long S0 = (long)T.ng * T.nmu * T.nE, S1 = (long)T.nmu * T.nE, S2 = T.nE;
+  double sum = 0.0;
+  for (int x = 0; x < 4; ++x)
+    for (int y = 0; y < 4; ++y) {
+      const double* base = T.buf + (long)(bT + x) * S0 + (long)(bG + y) * S1 + (long)bM * S2 + bE;
+      double inner = 0.0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const double* r = base + m * S2;
+        inner += wM[m] * (wE[0] * __ldg(r) + wE[1] * __ldg(r + 1) + wE[2] * __ldg(r + 2) + wE[3] * __ldg(r + 3));
+      }
+      sum += wT[x] * wG[y] * inner;
+    }
+  if (sum < 0.0) return 0.0;                                   // hot_Num4D.pyx:436-437
+  return sum * pow(10.0, 3.0 * logT);
+}
+
+__global__ void k_intensity(IntensityArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const double E = a.energies[i], mu = a.mu[i];
+  const double* VEC = a.vars + (long)i * a.n_vars;
+  auto base = [&](double m) -> double {
+    if (a.atm_ext == 2) return point_num4d(a.atm, VEC[0], VEC[1], m, E);
+    const double kT = kKBOverKeV * pow(10.0, VEC[0]);
+    return E * E * E / (exp(E / kT) - 1.0);
+  };
+  double I = base(mu);
+  if (a.region == 0 && a.beam_opt != 0) {
+    const double ab = VEC[2], bb = VEC[3], cb = VEC[4], db = VEC[5];
+    const double Ec = pow(E, cb), Ed = pow(E, db);
+    const double f = 1.0 + ab * Ec * mu + bb * Ed * mu * mu;
+    if (a.beam_opt == 1) I = f * I;
+    else if (a.beam_opt == 2) I = 0.5 / (0.5 + (1.0 / 3.0) * ab * Ec + (1.0 / 4.0) * bb * Ed) * f * I;
+    else {                                                     // numerical re-normalisation, hot_wrapper.pyx:173-192
+      const double nimu = VEC[6];
+      const long n = (long)nimu;
+      double mu_i = 0.0, nom = 0.0, den = 0.0;
+      for (long im = 0; im < n; ++im) {
+        mu_i = mu_i + (1.0 / nimu);
+        const double dmu = (im == 0 || (double)im == nimu - 1) ? (0.5 / nimu) : (1.0 / nimu);
+        const double Ii = base(mu_i);
+        const double fi = 1.0 + ab * Ec * mu_i + bb * Ed * mu_i * mu_i;
+        den = den + mu_i * fi * Ii * dmu;
+        nom = nom + mu_i * Ii * dmu;
+      }
+      I = are_equal(den, 0.0) ? 0.0 : (nom / den) * f * I;
+    }
+    if (I < 0.0) I = 0.0;
+  }
+  const double norm = (a.atm_ext == 2) ? kErg / kHKeV : kErg * kPlanckDistConst;
+  a.out[i] = I * (norm / (E * kKeV));                          // core.pyx:306
+}
+
+cudaError_t launch_intensity(IntensityArgs a, cudaStream_t stream) {
+  if (a.atm_ext != 1 && a.atm_ext != 2) return cudaErrorNotSupported;
+  if (a.beam_opt < 0 || a.beam_opt > 3) return cudaErrorNotSupported;
+  k_intensity<<<(a.n + 127) / 128, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // Row-wise spline tools: tools/phase_integrator.pyx:23-121, phase_interpolator.pyx:25-98,
 // energy_interpolator.pyx:27-125.  One CTA per signal row; coefficients in shared memory.
 // ---------------------------------------------------------------------------
