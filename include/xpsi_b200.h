@@ -67,9 +67,9 @@ void xpsi_b200_atmosphere_destroy(xpsi_b200_atmosphere* atm);
  * replaces xpsi/cellmesh/integrator_for_azimuthal_invariance.pyx:70-665
  * (call site xpsi/HotRegion.py:1169-1197).  flux_out is [n_energies][n_phases].
  * correction_srcCellParams (NULL or [n_rings][n_azi][n_params]) activates the elsewhere
- * correction with else_atm_ext / elsewhere_atmosphere.  beam_opt 0-2 (hot_wrapper.pyx:155-172,
- * parameters in srcCellParams[..., 2:6]) and the disc occultation for R_in < 1e6
- * (common_functions.pyx:110-138) are covered; beam_opt 3 returns XPSI_B200_EUNSUPPORTED. */
+ * correction with else_atm_ext / elsewhere_atmosphere.  beam_opt 0-3 (hot_wrapper.pyx:155-199,
+ * parameters in srcCellParams[..., 2:7]) and the disc occultation for R_in < 1e6
+ * (common_functions.pyx:110-138) are covered. */
 int xpsi_b200_integrate_azimuthal_invariance(
     double R, double omega, double r_s, double inclination,
     int n_rings, int n_azi,

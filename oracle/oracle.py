@@ -43,7 +43,7 @@ def integrate(numThreads, R, omega, r_s, inclination, cellArea, radialCoords_of_
               elsewhere_atmosphere, hot_atm_ext, else_atm_ext, beam_opt, image_order_limit=None,
               R_in=1e6, phase_interpolant='Akima'):
     """xpsi/cellmesh/integrator_for_azimuthal_invariance.pyx:70-98 (no disc, beam_opt 0)."""
-    assert beam_opt in (0, 1, 2)
+    assert beam_opt in (0, 1, 2, 3)
     cellArea, theta, phi = _f8(cellArea), _f8(theta), _f8(phi)
     par = _f8(srcCellParams)
     rad = np.ascontiguousarray(CELL_RADIATES, dtype=np.int32)
@@ -74,7 +74,7 @@ def integrate_general(numThreads, R, omega, r_s, inclination, cellArea, radialCo
                       elsewhere_atmosphere, hot_atm_ext, else_atm_ext, beam_opt, image_order_limit=None,
                       R_in=1e6, phase_interpolant='Akima'):
     """xpsi/cellmesh/integrator.pyx:48-76 (the integrator without azimuthal invariance)."""
-    assert beam_opt in (0, 1, 2)
+    assert beam_opt in (0, 1, 2, 3)
     cellArea, theta, phi = _f8(cellArea), _f8(theta), _f8(phi)
     par = _f8(srcCellParams)
     rad = np.ascontiguousarray(CELL_RADIATES, dtype=np.int32)

@@ -104,6 +104,37 @@ static double eval_hot_norm(int atm_ext) {
   return atm_ext == 2 ? 1.0e-7 / H_KEV : 1.0e-7 * 5.040366110812353e22;          /* hot_Num4D.pyx:460, hot_BB.pyx:98 */
 }
 
+/* hot_wrapper.pyx:110-199: intensity with the beaming modifications (options 1-3) */
+static double eval_hot_I(int beam_opt, int atm_ext, const atm_table *t, double E, double mu, const double *VEC) {
+  /* Option 3 sweeps mu up to 1 before every call, which leaves the Num4D stencil state at the top of the mu
+   * axis; the next query below the table then walks down to the first node and is clamped to it
+   * (hot_Num4D.pyx:301-323) -- with the sweep in between this happens on every call, not only the first. */
+  double mu_q = (beam_opt == 3 && atm_ext == 2 && mu < t->axis[2][0]) ? t->axis[2][0] : mu;
+  double I_hot = eval_hot(atm_ext, t, E, mu_q, VEC);
+  if (beam_opt == 0) return I_hot;
+  double abb = VEC[2], bbb = VEC[3], cbb = VEC[4], dbb = VEC[5], nimu = VEC[6];
+  double beam = 0.0;
+  if (beam_opt == 1) beam = (1.0 + abb * pow(E, cbb) * mu + bbb * pow(E, dbb) * mu * mu) * I_hot;
+  if (beam_opt == 2) {
+    double anorm = 0.5 / (0.5 + (1.0 / 3.0) * abb * pow(E, cbb) + (1.0 / 4.0) * bbb * pow(E, dbb));
+    beam = anorm * (1.0 + abb * pow(E, cbb) * mu + bbb * pow(E, dbb) * mu * mu) * I_hot;
+  }
+  if (beam_opt == 3) {                                  /* trapezoid over mu, :173-192 */
+    double mu_imu = 0.0, I_nom = 0.0, I_denom = 0.0;
+    for (size_t imu = 0; imu < (size_t)nimu; imu++) {
+      mu_imu = mu_imu + (1.0 / nimu);
+      double dmu = (imu == 0 || imu == nimu - 1) ? (0.5 / nimu) : (1.0 / nimu);
+      double Ii = eval_hot(atm_ext, t, E, mu_imu, VEC);
+      double f = 1.0 + abb * pow(E, cbb) * mu_imu + bbb * pow(E, dbb) * mu_imu * mu_imu;
+      I_denom = I_denom + mu_imu * f * Ii * dmu;
+      I_nom = I_nom + mu_imu * Ii * dmu;
+    }
+    beam = are_equal(I_denom, 0.0) ? 0.0
+                                   : (I_nom / I_denom) * (1.0 + abb * pow(E, cbb) * mu + bbb * pow(E, dbb) * mu * mu) * I_hot;
+  }
+  return beam < 0.0 ? 0.0 : beam;
+}
+
 /* cellmesh/common_functions.pyx:110-138 */
 static int disk_block(double R_in, double cos_i, double cos_psi, double cos_theta_i, double r_s_over_r_i,
                       double radius, double sin_alpha, double theta_i_over_pi) {
@@ -235,14 +266,7 @@ int oracle_integrate_azinv(
               PHASE[_kdx] = leaves[_kdx] + _phase_lag;
               for (int p = 0; p < N_E; p++) {
                 double E_prime = energies[p] / _Z;
-                double I_E = eval_hot(hot_atm_ext, &tab, E_prime, _ABB, VEC);
-                if (beam_opt == 1 || beam_opt == 2) {
-                  double abb = VEC[2], bbb = VEC[3], cbb = VEC[4], dbb = VEC[5];
-                  double fb = 1.0 + abb * pow(E_prime, cbb) * _ABB + bbb * pow(E_prime, dbb) * _ABB * _ABB;
-                  if (beam_opt == 2) fb *= 0.5 / (0.5 + (1.0 / 3.0) * abb * pow(E_prime, cbb) + (1.0 / 4.0) * bbb * pow(E_prime, dbb));
-                  I_E *= fb;
-                  if (I_E < 0.0) I_E = 0.0;
-                }
+                double I_E = eval_hot_I(beam_opt, hot_atm_ext, &tab, E_prime, _ABB, VEC);
                 double correction_I_E = 0.0;
                 if (perform_correction)                                          /* :469-476 */
                   correction_I_E = eval_hot(else_atm_ext, &ctab, E_prime, _ABB,
@@ -673,16 +697,6 @@ int oracle_integrate_tinv(
   return terminate ? ORACLE_ERROR : ORACLE_OK;
 }
 
-/* beaming modification of the hot intensity (hot_wrapper.pyx:155-199), options 1 and 2 */
-static double apply_beaming(int beam_opt, double I_E, double E_prime, double mu, const double *VEC) {
-  if (beam_opt != 1 && beam_opt != 2) return I_E;
-  double abb = VEC[2], bbb = VEC[3], cbb = VEC[4], dbb = VEC[5];
-  double fb = 1.0 + abb * pow(E_prime, cbb) * mu + bbb * pow(E_prime, dbb) * mu * mu;
-  if (beam_opt == 2) fb *= 0.5 / (0.5 + (1.0 / 3.0) * abb * pow(E_prime, cbb) + (1.0 / 4.0) * bbb * pow(E_prime, dbb));
-  I_E *= fb;
-  return I_E < 0.0 ? 0.0 : I_E;
-}
-
 /* ------------------------------------------------------------- cellmesh/integrator.pyx:48-667
  * The integrator without azimuthal invariance: per (ring, image) the leaf quantities GEOM, Z, ABB
  * are splined against the lagged leaf phase (GEOM with the phase interpolant, Z and ABB with Steffen,
@@ -865,7 +879,7 @@ int oracle_integrate_general(
             double abb = gsl_interp_eval(interp_ABB, PHASE, ABB, x, acc_A);
             for (int p = 0; p < N_E; p++) {
               double E_prime = energies[p] / z;
-              double I_E = apply_beaming(beam_opt, eval_hot(hot_atm_ext, &tab, E_prime, abb, VEC), E_prime, abb, VEC);
+              double I_E = eval_hot_I(beam_opt, hot_atm_ext, &tab, E_prime, abb, VEC);
               I_E *= eval_hot_norm(hot_atm_ext);
               double c = 0.0;
               if (perform_correction)
@@ -899,30 +913,7 @@ int oracle_intensity(int n, const double *energies, const double *mu, const doub
   for (int i = 0; i < n; i++) {
     const double *VEC = vars + (size_t)i * n_vars;
     double E = energies[i], m = mu[i];
-    double I = eval_hot(atm_ext, &tab, E, m, VEC);
-    if (region == 0 && beam_opt != 0) {
-      double abb = VEC[2], bbb = VEC[3], cbb = VEC[4], dbb = VEC[5], nimu = VEC[6];
-      double beam = 0.0;
-      if (beam_opt == 1) beam = (1.0 + abb * pow(E, cbb) * m + bbb * pow(E, dbb) * m * m) * I;
-      if (beam_opt == 2) {
-        double anorm = 0.5 / (0.5 + (1.0 / 3.0) * abb * pow(E, cbb) + (1.0 / 4.0) * bbb * pow(E, dbb));
-        beam = anorm * (1.0 + abb * pow(E, cbb) * m + bbb * pow(E, dbb) * m * m) * I;
-      }
-      if (beam_opt == 3) {
-        double mu_imu = 0.0, I_nom = 0.0, I_denom = 0.0;
-        for (size_t imu = 0; imu < (size_t)nimu; imu++) {
-          mu_imu = mu_imu + (1.0 / nimu);
-          double dmu = (imu == 0 || imu == nimu - 1) ? (0.5 / nimu) : (1.0 / nimu);
-          double Ii = eval_hot(atm_ext, &tab, E, mu_imu, VEC);
-          double f = 1.0 + abb * pow(E, cbb) * mu_imu + bbb * pow(E, dbb) * mu_imu * mu_imu;
-          I_denom = I_denom + mu_imu * f * Ii * dmu;
-          I_nom = I_nom + mu_imu * Ii * dmu;
-        }
-        beam = are_equal(I_denom, 0.0) ? 0.0
-                                       : (I_nom / I_denom) * (1.0 + abb * pow(E, cbb) * m + bbb * pow(E, dbb) * m * m) * I;
-      }
-      I = beam < 0.0 ? 0.0 : beam;
-    }
+    double I = region == 0 ? eval_hot_I(beam_opt, atm_ext, &tab, E, m, VEC) : eval_hot(atm_ext, &tab, E, m, VEC);
     out[i] = I * eval_hot_norm(atm_ext) / (E * KEV);
   }
   return ORACLE_OK;

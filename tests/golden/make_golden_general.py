@@ -53,8 +53,15 @@ out["c1"] = run(args_of(c1, "int0_", ()))
 bp = np.zeros(c1["int0_srcCellParams"].shape[:2] + (7,))
 bp[..., :2] = c1["int0_srcCellParams"]
 bp[..., 2:6] = [0.15, -0.08, 0.3, 0.5]
+bp[..., 6] = 24.0
 out["c1_beam_params"] = np.ascontiguousarray(bp)
 out["c1_beam"] = run(args_of(c1, "int0_", (), out["c1_beam_params"], 1))
+bm = np.zeros(m2["t0_int1_srcCellParams"].shape[:2] + (7,))
+bm[..., :2] = m2["t0_int1_srcCellParams"]
+bm[..., 2:6] = [0.15, -0.08, 0.3, 0.5]
+bm[..., 6] = 24.0
+out["m2_beam_params"] = np.ascontiguousarray(bm)
+out["m2_beam3"] = run(args_of(m2, "t0_int1_", table, out["m2_beam_params"], 3))
 xpsi.set_phase_interpolant('Steffen')
 out["c1_steffen"] = run(args_of(c1, "int0_", ()))
 xpsi.set_phase_interpolant('Akima')

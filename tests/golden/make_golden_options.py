@@ -2,7 +2,7 @@
 """Golden vectors for the integrator's optional branches, recorded by calling the reference's
 integrator_for_azimuthal_invariance.integrate directly on fixture inputs:
   * disc occultation (R_in < 1e6, common_functions.pyx:110-138) on the C1 blackbody inputs
-  * beaming options 1 and 2 (hot_wrapper.pyx:155-172) on C1 (BB) and on an M2 member (Num4D)
+  * beaming options 1, 2 and 3 (hot_wrapper.pyx:155-199; 3 with nimu = 24) on C1 (BB) and on an M2 member (Num4D)
   * the Steffen phase interpolant (tools/core.pyx:34-52)"""
 import os
 import sys
@@ -34,6 +34,7 @@ def beam_params(base):
     out = np.zeros(base.shape[:2] + (7,))
     out[..., :2] = base
     out[..., 2:6] = [0.15, -0.08, 0.3, 0.5]
+    out[..., 6] = 24.0
     return np.ascontiguousarray(out)
 
 
@@ -54,7 +55,7 @@ s, f = integrate(*a)
 out["disk_flux_none"] = np.array(f)
 out["beam_params_c1"] = beam_params(c1["int0_srcCellParams"])
 out["beam_params_m2"] = beam_params(m2["t0_int1_srcCellParams"])
-for opt in (1, 2):
+for opt in (1, 2, 3):
     s, f = integrate(*args_of(c1, "int0_", (), out["beam_params_c1"], opt))
     assert s == 0
     out["beam%d_c1" % opt] = np.array(f)

@@ -176,7 +176,7 @@ def _option_cases(c1, m2):
     for R_in in (2.0e4, 5.0e4):
         a = list(base); a[8] = d["disk_theta"]
         cases.append(("disc R_in=%g" % R_in, a, dict(R_in=R_in), d["disk_flux_%d" % int(R_in)]))
-    for opt in (1, 2):
+    for opt in (1, 2, 3):
         a = list(base); a[10] = d["beam_params_c1"]; a[26] = opt
         cases.append(("beam %d BB" % opt, a, {}, d["beam%d_c1" % opt]))
         a = list(_integrate_args(m2, "t0_int1_", table)); a[10] = d["beam_params_m2"]; a[26] = opt
@@ -210,6 +210,8 @@ def _general_cases(c1, m2):
     cases.append(("c1", args(c1, "int0_", ()), {}, d["c1"]))
     a = args(c1, "int0_", ()); a[10] = d["c1_beam_params"]; a[26] = 1
     cases.append(("c1 beam 1", a, {}, d["c1_beam"]))
+    a = args(m2, "t0_int1_", table); a[10] = d["m2_beam_params"]; a[26] = 3
+    cases.append(("m2 beam 3", a, {}, d["m2_beam3"]))
     cases.append(("m2 uniform", args(m2, "t0_int1_", table), {}, d["m2"]))
     a = args(m2, "t0_int1_", table); a[10] = d["m2_var_params"]
     cases.append(("m2 per-cell parameters", a, {}, d["m2_var"]))

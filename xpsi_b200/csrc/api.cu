@@ -171,9 +171,8 @@ static int integrate_member(
     if (else_atm_ext == XPSI_B200_ATM_NUM4D && !elsewhere_atmosphere)
       return fail(XPSI_B200_EINVAL, "Num4D elsewhere correction needs a preloaded atmosphere");
   }
-  if (beam_opt < 0 || beam_opt > 2)
-    return fail(XPSI_B200_EUNSUPPORTED, "beam_opt 3 (numerically normalised beaming) is not covered");
-  if (beam_opt != 0 && n_params < 6) return fail(XPSI_B200_EINVAL, "beam_opt needs srcCellParams[..., 2:6]");
+  if (beam_opt < 0 || beam_opt > 3) return fail(XPSI_B200_EINVAL, "beam_opt must be 0-3");
+  if (beam_opt != 0 && n_params < 7) return fail(XPSI_B200_EINVAL, "beam_opt needs srcCellParams[..., 2:7]");
   if (hot_atm_ext != XPSI_B200_ATM_BB && hot_atm_ext != XPSI_B200_ATM_NUM4D)
     return fail(XPSI_B200_EUNSUPPORTED, "hot_atm_ext must be 1 (BB) or 2 (Num4D)");
   if (hot_atm_ext == XPSI_B200_ATM_NUM4D && !hot_atmosphere)

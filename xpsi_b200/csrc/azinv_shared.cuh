@@ -25,6 +25,35 @@ __device__ __forceinline__ double* leaf_ptr(double* ws, long ring, int n_img_max
   return ws + ((ring * n_img_max + I) * 4) * (long)N_L;
 }
 
+// beaming modification of the hot intensity (hot_wrapper.pyx:155-199).  I_hot and eval_mu(mu') are in the
+// reference's eval_hot units (Num4D: including the 10^(3 log T) factor) because option 3 compares its
+// normalisation integral with zero at an absolute 1e-12 (tools/core.pyx:118-122).
+template <class EvalMu>
+__device__ __forceinline__ double apply_beaming(int beam_opt, double I_hot, double Ep, double mu, const double* BV,
+                                                EvalMu&& eval_mu) {
+  const double ab = BV[2], bb = BV[3], cb = BV[4], db = BV[5];
+  const double Ec = pow(Ep, cb), Ed = pow(Ep, db);
+  const double f = 1.0 + ab * Ec * mu + bb * Ed * mu * mu;
+  double I = 0.0;
+  if (beam_opt == 1) I = f * I_hot;
+  else if (beam_opt == 2) I = 0.5 / (0.5 + (1.0 / 3.0) * ab * Ec + (1.0 / 4.0) * bb * Ed) * f * I_hot;
+  else if (beam_opt == 3) {              // trapezoid over mu, :173-192
+    const double nimu = BV[6];
+    const long n = (long)nimu;
+    double mu_i = 0.0, nom = 0.0, den = 0.0;
+    for (long im = 0; im < n; ++im) {
+      mu_i = mu_i + (1.0 / nimu);
+      const double dmu = (im == 0 || (double)im == nimu - 1) ? (0.5 / nimu) : (1.0 / nimu);
+      const double Ii = eval_mu(mu_i);
+      const double fi = 1.0 + ab * Ec * mu_i + bb * Ed * mu_i * mu_i;
+      den = den + mu_i * fi * Ii * dmu;
+      nom = nom + mu_i * Ii * dmu;
+    }
+    I = are_equal(den, 0.0) ? 0.0 : (nom / den) * f * I_hot;
+  }
+  return I < 0.0 ? 0.0 : I;
+}
+
 // geometry stage alone (used by the general integrator, which brings its own flux kernel)
 cudaError_t launch_azinv_geometry(const AzinvArgs& a, cudaStream_t stream);
 

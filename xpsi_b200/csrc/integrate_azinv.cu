@@ -637,11 +637,14 @@ __device__ __forceinline__ void slab_ctx_finish(SlabCtx& c, int tid) {     // af
 }
 
 // mu stencil of every lit leaf (geom != 0), weights stored [4][N_L]
+// clamp_low: beam_opt 3 only -- its mu sweep leaves the reference's stencil state at the top of the axis, so a
+// query below the table is walked down and clamped to the first node on every call (hot_Num4D.pyx:301-323)
 __device__ __forceinline__ void slab_ctx_leaf_stencils(const SlabCtx& c, const double* abb, const double* geom,
-                                                       int N_L, int tid) {
+                                                       int N_L, int tid, bool clamp_low = false) {
   for (int l = tid; l < N_L; l += kFluxThreads) {
     if (geom[l] == 0.0) continue;
-    const double v = abb[l];
+    double v = abb[l];
+    if (clamp_low && v < c.axMu[0]) v = c.axMu[0];
     const int b = lagrange_base(c.axMu, c.nmu, v);
     double w[4];
     lagrange_weights(c.axMu, b, v, w);
@@ -669,6 +672,26 @@ __device__ __forceinline__ double slab_ctx_eval(const SlabCtx& c, double v, int 
     sum += c.muw[x * N_L + l] * (wE0 * r[0] + wE1 * r[1] + wE2 * r[2] + wE3 * r[3]);
   }
   return sum < 0.0 ? 0.0 : sum;                                     // hot_Num4D.pyx:436-437
+}
+
+// the same for an arbitrary mu (beam_opt 3 integrates over mu, hot_wrapper.pyx:173-192)
+__device__ __noinline__ double slab_ctx_eval_mu(const SlabCtx& c, double v, double mu) {
+  const int j = interval_walk(c.axE, c.nrows, v, (int)((v - c.axE[0]) * c.inv_dE));
+  int bE = j - 1;
+  if (c.elo_tab + bE < 0) bE = -c.elo_tab;
+  if (c.elo_tab + bE > c.nE - 4) bE = c.nE - 4 - c.elo_tab;
+  double wE[4], wM[4];
+  lagrange_weights(c.axE, bE, v, wE);
+  const int bM = lagrange_base(c.axMu, c.nmu, mu);
+  lagrange_weights(c.axMu, bM, mu, wM);
+  const double* row = c.slab + (long)bM * c.nrows + bE;
+  double sum = 0.0;
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const double* r = row + x * c.nrows;
+    sum += wM[x] * (wE[0] * r[0] + wE[1] * r[1] + wE[2] * r[2] + wE[3] * r[3]);
+  }
+  return sum < 0.0 ? 0.0 : sum;
 }
 
 // ATM: hot atmosphere (1 BB, 2 Num4D).  CORR: elsewhere correction (0 none, 1 BB, 2 Num4D)
@@ -766,7 +789,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
     }
     __syncthreads();
     if (ATM == 2 || CORR == 2) {
-      if (ATM == 2) slab_ctx_leaf_stencils(hot, s_abb, s_geom, N_L, tid);
+      if (ATM == 2) slab_ctx_leaf_stencils(hot, s_abb, s_geom, N_L, tid, a.beam_opt == 3);
       if (CORR == 2) slab_ctx_leaf_stencils(els, s_abb, s_geom, N_L, tid);
     }
     for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
@@ -781,16 +804,14 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
         double I_E;
         if (ATM == 1) I_E = bb_intensity(s_E[e] / s_Z[l], kT);
         else I_E = slab_ctx_eval(hot, s_logE[e] - s_Z[l] - log_kT, l, N_L);
-        if (a.beam_opt != 0) {            // hot_wrapper.pyx:155-172 (options 1, 2)
+        if (a.beam_opt != 0) {            // hot_wrapper.pyx:155-199 (options 1-3)
           const double* BV = a.srcParams + (a.params_per_cell ? (cell0 + ih[1]) : ring) * a.n_params;
-          const double abb = BV[2], bbb = BV[3], cbb = BV[4], dbb = BV[5];
           const double Ep = (ATM == 2) ? s_E[e] * exp10(-s_Z[l]) : s_E[e] / s_Z[l];
-          const double mu_b = s_abb[l];
-          const double Ec = pow(Ep, cbb), Ed = pow(Ep, dbb);
-          double f = 1.0 + abb * Ec * mu_b + bbb * Ed * mu_b * mu_b;
-          if (a.beam_opt == 2) f *= 0.5 / (0.5 + (1.0 / 3.0) * abb * Ec + (1.0 / 4.0) * bbb * Ed);
-          I_E *= f;
-          if (I_E < 0.0) I_E = 0.0;       // hot_wrapper.pyx:197-199
+          const double t3 = (ATM == 2) ? pow(10.0, 3.0 * dh[10]) : 1.0;
+          const double v = s_logE[e] - s_Z[l] - log_kT;
+          I_E = apply_beaming(a.beam_opt, I_E * t3, Ep, s_abb[l], BV, [&](double mu_i) -> double {
+                  return (ATM == 2) ? slab_ctx_eval_mu(hot, v, mu_i) * t3 : bb_intensity(Ep, kT);
+                }) / t3;
         }
         double corr = 0.0;
         if (CORR == 1) {
@@ -995,7 +1016,7 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   const int corr = a.corrParams ? a.else_atm_ext : 0;
   if (atm != 1 && atm != 2) return cudaErrorNotSupported;
   if (corr != 0 && corr != 1 && corr != 2) return cudaErrorNotSupported;
-  if (a.beam_opt < 0 || a.beam_opt > 2 || (a.beam_opt != 0 && a.n_params < 6)) return cudaErrorNotSupported;
+  if (a.beam_opt < 0 || a.beam_opt > 3 || (a.beam_opt != 0 && a.n_params < 7)) return cudaErrorNotSupported;
   if (a.R_in <= 0.0) a.R_in = 1.0e6;
   if (!a.corrParams) a.else_atm_ext = 0;
   if ((atm == 2 && !a.ws_slab) || (corr == 2 && !a.ws_slab2)) return cudaErrorInvalidValue;

@@ -217,7 +217,11 @@ __global__ void __launch_bounds__(kGenThreads) k_general_flux(AzinvArgs a, int n
           if (G > 0.0) {
             Zv = tb[5 * N_L + m] + d * (tb[6 * N_L + m] + d * (tb[7 * N_L + m] + d * tb[8 * N_L + m]));
             Av = tb[9 * N_L + m] + d * (tb[10 * N_L + m] + d * (tb[11 * N_L + m] + d * tb[12 * N_L + m]));
-            if (ATM == 2) { bM = lagrange_base(hot.axMu, a.hot.nmu, Av); lagrange_weights(hot.axMu, bM, Av, wM); }
+            if (ATM == 2) {
+              // beam_opt 3: a query below the table is clamped to its first node on every call (see integrate_azinv.cu)
+              const double Aq = (a.beam_opt == 3 && Av < hot.axMu[0]) ? hot.axMu[0] : Av;
+              bM = lagrange_base(hot.axMu, a.hot.nmu, Aq); lagrange_weights(hot.axMu, bM, Aq, wM);
+            }
             if (CORR == 2) { bMc = lagrange_base(els.axMu, a.els.nmu, Av); lagrange_weights(els.axMu, bMc, Av, wMc); }
           } else G = 0.0;
         }
@@ -246,13 +250,16 @@ __global__ void __launch_bounds__(kGenThreads) k_general_flux(AzinvArgs a, int n
         double I_E;
         if (ATM == 1) I_E = bb_intensity(Ep, kT);
         else I_E = gen_slab_eval(hot, a.hot.nE, elo, nrows, logE_lane - log10(z) - log_kT, bm, w, &bad);
-        if (a.beam_opt != 0) {            // hot_wrapper.pyx:155-199 (options 1, 2), the cell's own parameters
-          const double ab = VEC[2], bb = VEC[3], cb = VEC[4], db = VEC[5];
-          const double Ec = pow(Ep, cb), Ed = pow(Ep, db);
-          double f = 1.0 + ab * Ec * abb + bb * Ed * abb * abb;
-          if (a.beam_opt == 2) f *= 0.5 / (0.5 + (1.0 / 3.0) * ab * Ec + (1.0 / 4.0) * bb * Ed);
-          I_E *= f;
-          if (I_E < 0.0) I_E = 0.0;
+        if (a.beam_opt != 0) {            // hot_wrapper.pyx:155-199 (options 1-3), the cell's own parameters
+          const double t3 = (ATM == 2) ? pow(10.0, 3.0 * VEC[0]) : 1.0;
+          const double v = logE_lane - log10(z) - log_kT;
+          I_E = apply_beaming(a.beam_opt, I_E * t3, Ep, abb, VEC, [&](double mu_i) -> double {
+                  if (ATM != 2) return bb_intensity(Ep, kT);
+                  double wi[4];
+                  const int bi = lagrange_base(hot.axMu, a.hot.nmu, mu_i);
+                  lagrange_weights(hot.axMu, bi, mu_i, wi);
+                  return gen_slab_eval(hot, a.hot.nE, elo, nrows, v, bi, wi, &bad) * t3;
+                }) / t3;
         }
         double corr = 0.0;
         if (CORR == 1) corr = bb_intensity(Ep, kT_c) * norm_c;
@@ -317,7 +324,7 @@ cudaError_t launch_integrate_general(AzinvArgs a, cudaStream_t stream) {
   const int corr = a.corrParams ? a.else_atm_ext : 0;
   if (atm != 1 && atm != 2) return cudaErrorNotSupported;
   if (corr != 0 && corr != 1 && corr != 2) return cudaErrorNotSupported;
-  if (a.beam_opt < 0 || a.beam_opt > 2 || (a.beam_opt != 0 && a.n_params < 6)) return cudaErrorNotSupported;
+  if (a.beam_opt < 0 || a.beam_opt > 3 || (a.beam_opt != 0 && a.n_params < 7)) return cudaErrorNotSupported;
   if ((atm == 2 || corr == 2) && a.slab_ne_max < 4) return cudaErrorInvalidValue;
   if (!a.corrParams) a.else_atm_ext = 0;
   a.general = 1;

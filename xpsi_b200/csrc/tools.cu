@@ -253,7 +253,9 @@ __global__ void k_intensity(IntensityArgs a) {
     const double kT = kKBOverKeV * pow(10.0, VEC[0]);
     return E * E * E / (exp(E / kT) - 1.0);
   };
-  double I = base(mu);
+  // beam_opt 3: the sweep leaves the reference's stencil at the top of the mu axis, so a query below the
+  // table is clamped to its first node (hot_Num4D.pyx:301-323)
+  double I = base((a.region == 0 && a.beam_opt == 3 && a.atm_ext == 2 && mu < a.atm.mu[0]) ? a.atm.mu[0] : mu);
   if (a.region == 0 && a.beam_opt != 0) {
     const double ab = VEC[2], bb = VEC[3], cb = VEC[4], db = VEC[5];
     const double Ec = pow(E, cb), Ed = pow(E, db);
