@@ -47,3 +47,15 @@ out.update({"plgb_background": bgr, "plgb_lnL": np.asarray(lnL_bg), "plgb_expect
             "plgb_shift": np.asarray(0.13)})
 np.savez_compressed(os.path.join(HERE, "tools.npz"), **out)
 print("tools.npz (+given-background likelihood)", os.path.getsize(os.path.join(HERE, "tools.npz")) // 1024, "KiB")
+
+# ---- tools.synthesise (row b / f4): expected counts and scales only, the Poisson draw is not recorded ----
+from xpsi.tools.synthesise import synthesise_exposure, synthesise_given_total_count_number  # noqa: E402
+bg_counts = bgr * 1000.0
+e1, _, s1 = synthesise_exposure(1000.0, edges, (comp,), (sig_phases,), np.array([0.13]), 5.0e4, bg_counts, gsl_seed=1)
+e2, _, s2a, s2b = synthesise_given_total_count_number(edges, 2.0e6, (comp,), (sig_phases,), np.array([0.13]), 5.0e4,
+                                                     bg_counts, gsl_seed=1)
+out = dict(np.load(os.path.join(HERE, "tools.npz")))
+out.update({"syn_bg_counts": bg_counts, "syn_exposure_expected": np.asarray(e1), "syn_exposure_scale": np.asarray(s1),
+            "syn_total_expected": np.asarray(e2), "syn_total_scales": np.array([s2a, s2b])})
+np.savez_compressed(os.path.join(HERE, "tools.npz"), **out)
+print("tools.npz (+synthesise)", os.path.getsize(os.path.join(HERE, "tools.npz")) // 1024, "KiB")

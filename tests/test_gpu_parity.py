@@ -4,6 +4,8 @@ reference build (tests/golden/make_golden.py).
 
 Tolerances are BASELINE.json's: pulse signals 1e-8 relative, lnL 1e-6 absolute.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -511,3 +513,23 @@ def test_surface_radiation_field_intensity():
         intensity(np.ones(2), np.ones(2), np.ones((2, 2)), None, 0, 'nowhere', 'BB')
     with pytest.raises(ValueError):
         intensity(np.ones(2), np.ones(2), np.ones((2, 2)), None, 0, 'hot', 'Num4D')
+
+
+def test_synthesise_expected_counts(c1):
+    """tools.synthesise_exposure / synthesise_given_total_count_number (synthesise.pyx:40-276): the expected
+    counts and normalisations against the reference; the Poisson draw is host-side and only sanity-checked."""
+    from xpsi_b200 import tools
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tools.npz"))
+    comp, sig_phases, edges = c1["marg_components_0"], c1["marg_component_phases_0"], c1["marg_phases"]
+    e1, syn1, s1 = tools.synthesise_exposure(1000.0, edges, (comp,), (sig_phases,), np.array([0.13]), 5.0e4,
+                                             d["syn_bg_counts"], gsl_seed=1)
+    assert rel_err(e1, d["syn_exposure_expected"]) < PULSE_RTOL
+    assert abs(s1 - float(d["syn_exposure_scale"])) <= 1e-12 * abs(s1)
+    e2, syn2, a2, b2 = tools.synthesise_given_total_count_number(edges, 2.0e6, (comp,), (sig_phases,),
+                                                                 np.array([0.13]), 5.0e4, d["syn_bg_counts"], gsl_seed=1)
+    assert rel_err(e2, d["syn_total_expected"]) < PULSE_RTOL
+    assert np.allclose([a2, b2], d["syn_total_scales"], rtol=1e-9, atol=0.0)
+    assert abs(e2.sum() - 2.05e6) < 1e-3 * 2.05e6
+    for syn, e in ((syn1, e1), (syn2, e2)):
+        assert syn.shape == e.shape and np.all(syn >= 0) and np.all(syn == np.round(syn))
+        assert abs(syn.sum() - e.sum()) < 6.0 * np.sqrt(e.sum())

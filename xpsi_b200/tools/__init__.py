@@ -106,3 +106,15 @@ def phase_interpolator(new_phases, phases, signal, phase_shift, allow_negative=0
         _lib.dptr(new_phases), new_phases.shape[0], _lib.dptr(phases), phases.shape[0], _lib.dptr(signal),
         signal.shape[0], float(phase_shift), int(bool(allow_negative)), _phase_interpolant, _lib.dptr(out)))
     return out
+
+
+def synthesise_exposure(*args, **kwargs):
+    """xpsi.tools.synthesise_exposure (xpsi/tools/synthesise.pyx:40-149); see tools/synthesise.py."""
+    from .synthesise import synthesise_exposure as f
+    return f(*args, **kwargs)
+
+
+def synthesise_given_total_count_number(*args, **kwargs):
+    """xpsi.tools.synthesise_given_total_count_number (xpsi/tools/synthesise.pyx:152-276)."""
+    from .synthesise import synthesise_given_total_count_number as f
+    return f(*args, **kwargs)
