@@ -249,6 +249,44 @@ typedef struct {
   int num_cells, min_sqrt_num_cells, max_sqrt_num_cells;
 } xpsi_b200_spot_batch;
 
+/* ---- optional model components of the batched pipeline ---------------------------------------------
+ * Set once after create.  elsewhere != 0 adds xpsi.Elsewhere (xpsi/Elsewhere.py): its time-invariant
+ * spectrum (integrator_for_time_invariance.pyx) is added to every phase column of member 0's signal
+ * (xpsi/Photosphere.py:589-592) and the hot members are integrated with the elsewhere correction
+ * (integrator_for_azimuthal_invariance.pyx:257-268,469-478).  attenuation != NULL applies
+ * xpsi.Interstellar.__call__ (xpsi/Interstellar.py:27-58) after the energy integration with the factor
+ * attenuation[j] ** att_power[b] (att_power from the batch extras; 1 when absent).  beam_opt is passed
+ * to the hot-region integrator (needs n_params >= 7 when non-zero).                                   */
+typedef struct {
+  int elsewhere;
+  int else_sqrt_num_cells, else_num_rays, else_atm_ext, else_image_order_limit;
+  const xpsi_b200_atmosphere* elsewhere_atmosphere;
+  const double* attenuation;                     /* NULL or [n_in], copied                           */
+  int beam_opt;
+} xpsi_b200_pipeline_extras;
+int xpsi_b200_pipeline_set_extras(xpsi_b200_pipeline* p, const xpsi_b200_pipeline_extras* extras);
+
+/* Per-batch inputs of the optional components, uploaded for the next evaluation of B parameter vectors.
+ * Parameter-level path (eval_spots): else_temperature [B] and att_power [B] are enough -- the closed
+ * Elsewhere mesh and its rays are embedded on the device (cellmesh/global_mesh.pyx, rays.pyx).
+ * Mesh-level path (eval): the caller passes the arrays Elsewhere.embed produced, in the layout of
+ * xpsi_b200_integrate_time_invariance with a leading [B] axis, plus the correction parameter rows
+ * of the hot members [B*M][max_rings][n_params].  Unused pointers may be NULL.                        */
+typedef struct {
+  const double* att_power;                       /* [B]                                              */
+  const double* else_temperature;                /* [B] log10 K (parameter-level path)               */
+  const double* else_cellArea;                   /* [B]                                              */
+  const double* else_radial; const double* else_r_s_over_r;          /* [B][n]                       */
+  const double* else_theta; const double* else_phi;                  /* [B][n][n]                    */
+  const double* else_srcParams;                  /* [B][n][n][2]                                     */
+  const double* else_deflection; const double* else_cos_alpha;       /* [B][n][else_num_rays]        */
+  const double* else_maxDeflection; const double* else_cos_gamma;    /* [B][n]                       */
+  const double* correction_srcParams;            /* [B*M][max_rings][n_params]                       */
+} xpsi_b200_batch_extras;
+int xpsi_b200_pipeline_upload_extras(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch_extras* host);
+/* Elsewhere spectrum [B][n_energies] of the last evaluation (photons/cm^2/s/keV before 1/d^2) */
+int xpsi_b200_pipeline_fetch_elsewhere(xpsi_b200_pipeline* p, int B, double* spectrum);
+
 /* embed B parameter vectors on the device (inputs of the next eval_resident) */
 int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200_spot_batch* host);
 /* re-run embed + the four stages on the spot batch already on the device (kernels only) */

@@ -533,3 +533,69 @@ def test_synthesise_expected_counts(c1):
     for syn, e in ((syn1, e1), (syn2, e2)):
         assert syn.shape == e.shape and np.all(syn >= 0) and np.all(syn == np.round(syn))
         assert abs(syn.sum() - e.sum()) < 6.0 * np.sqrt(e.sum())
+
+
+def test_m4_batched_pipeline_with_elsewhere_and_interstellar(m2):
+    """Config 4 through the batched pipeline: Elsewhere (time-invariant integrator + correction in the hot
+    members + Photosphere.py:589-592), per-theta interstellar attenuation, fold, likelihood -- first with the
+    reference's embedded arrays (mesh level), then from the parameter vector with every embed on the GPU."""
+    from conftest import GOLDEN
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.pipeline import BatchedLikelihood
+    d = np.load(os.path.join(GOLDEN, "m4_elsewhere.npz"))
+    table = syn.nsx_like_table()
+    matrix, edges = syn.nicer_like_response()[:2]
+    pipe = BatchedLikelihood(member_component=[0, 1], max_rings=64, max_azi=64, n_rays=200,
+                             energies=d["int0_energies"], leaves=d["int0_leaves"], phases=d["int0_phases"],
+                             hot_atm_ext=2, hot_atmosphere=table, image_order_limit=3, response=matrix,
+                             energy_edges=edges, counts=d["counts"], data_phases=np.linspace(0.0, 1.0, 33),
+                             exposure_time=syn.M2_EXPOSURE, max_batch=4)
+    N_H = float(d["column_density"])
+    n = int(d["else_sqrt_numPix"])
+    pipe.set_extras(elsewhere=dict(sqrt_num_cells=n, num_rays=int(d["else_numRays"]), atm_ext=2, atmosphere=table,
+                                   image_order_limit=int(d["else_image_order_limit"])),
+                    attenuation=d["attenuation"] ** (1.0 / N_H))
+    B = 3
+    ref = float(d["lnL_total"])
+    # ---- mesh level -------------------------------------------------------------------------------
+    batch = pipe.new_batch(B)
+    corr = np.zeros((B * 2, 64, 2))
+    for b in range(B):
+        batch.omega[b] = d["int0_omega"]; batch.inclination[b] = d["int0_inclination"]; batch.d_sq[b] = d["d_sq"]
+        batch.phase_shifts[b] = d["marg_phase_shifts"]
+        for m in range(2):
+            g = lambda k: d["int%d_%s" % (m, k)]
+            batch.set_member(b, m, g("cellArea"), g("theta"), g("phi"), g("radialCoords_of_parallels"),
+                             g("r_s_over_r"), g("srcCellParams"), g("deflection"), g("cos_alpha"), g("lag"),
+                             g("maxDeflection"), g("cos_gammaArray"))
+            c = g("correction_srcCellParams")
+            J = np.argmax(g("cellArea") > 0.0, axis=1)
+            corr[b * 2 + m, :c.shape[0]] = c[np.arange(c.shape[0]), J]
+    tile = lambda a: np.ascontiguousarray(np.broadcast_to(a, (B,) + np.shape(a)))
+    els = dict(cellArea=tile(float(d["else_cellArea"])), radial=tile(d["else_radialCoords_of_parallels"]),
+               r_s_over_r=tile(d["else_r_s_over_r"]), theta=tile(d["else_theta"]), phi=tile(d["else_phi"]),
+               srcParams=tile(d["else_srcCellParams"]), deflection=tile(d["else_deflection"]),
+               cos_alpha=tile(d["else_cos_alpha"]), maxDeflection=tile(d["else_maxDeflection"]),
+               cos_gamma=tile(d["else_cos_gammaArray"]))
+    pipe.upload_extras(B, att_power=np.full(B, N_H), elsewhere=els, correction_srcParams=corr)
+    lnL, status = pipe(batch)
+    print("M4 pipeline (mesh level) lnL", lnL, "ref", ref, "status", status)
+    assert (status == 0).all()
+    assert np.max(np.abs(lnL - ref)) < LNL_ATOL
+    spec = pipe.fetch_elsewhere(B)
+    assert rel_err(spec[1], d["else_flux"]) < PULSE_RTOL
+    flux, folded, expected = pipe.fetch(B)
+    for c in range(2):
+        assert rel_err(folded[2, c], d["marg_components_%d" % c]) < PULSE_RTOL
+    # ---- parameter level: closed mesh, spots, rays and correction rows all embedded on the GPU -------
+    thetas = np.tile(d["theta"], (B, 1))
+    spots = syn.m2_spot_batch(pipe, thetas[:, :11])
+    pipe.upload_extras(B, att_power=thetas[:, 12], else_temperature=thetas[:, 11])
+    lnL2, status2 = pipe.eval_spots(spots)
+    print("M4 pipeline (parameter level) lnL", lnL2, "diff", lnL2 - ref, "status", status2)
+    assert (status2 == 0).all()
+    assert np.max(np.abs(lnL2 - ref)) < 1e-5
+    spec2 = pipe.fetch_elsewhere(B)
+    err = rel_err(spec2[0], d["else_flux"])
+    print("GPU-embedded elsewhere spectrum rel err", err)
+    assert err < PULSE_RTOL

@@ -96,6 +96,21 @@ class SpotBatch(C.Structure):
     ]
 
 
+class PipelineExtras(C.Structure):
+    _fields_ = [
+        ("elsewhere", C.c_int), ("else_sqrt_num_cells", C.c_int), ("else_num_rays", C.c_int),
+        ("else_atm_ext", C.c_int), ("else_image_order_limit", C.c_int), ("elsewhere_atmosphere", C.c_void_p),
+        ("attenuation", c_double_p), ("beam_opt", C.c_int),
+    ]
+
+
+class BatchExtras(C.Structure):
+    _fields_ = [(f, c_double_p) for f in (
+        "att_power", "else_temperature", "else_cellArea", "else_radial", "else_r_s_over_r", "else_theta",
+        "else_phi", "else_srcParams", "else_deflection", "else_cos_alpha", "else_maxDeflection", "else_cos_gamma",
+        "correction_srcParams")]
+
+
 def _proto(name, restype, argtypes):
     f = getattr(lib, name)
     f.restype = restype
@@ -121,6 +136,9 @@ _proto("xpsi_b200_integrate_general", C.c_int,
         C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
         C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, c_double_p,
         C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, c_double_p])
+_proto("xpsi_b200_pipeline_set_extras", C.c_int, [C.c_void_p, C.POINTER(PipelineExtras)])
+_proto("xpsi_b200_pipeline_upload_extras", C.c_int, [C.c_void_p, C.c_int, C.POINTER(BatchExtras)])
+_proto("xpsi_b200_pipeline_fetch_elsewhere", C.c_int, [C.c_void_p, C.c_int, c_double_p])
 _proto("xpsi_b200_intensity", C.c_int,
        [C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p])
 _proto("xpsi_b200_integrate_time_invariance", C.c_int,
@@ -164,7 +182,8 @@ _proto("xpsi_b200_pipeline_stage_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)
 EXPORTED = [
     "xpsi_b200_last_error", "xpsi_b200_device_count", "xpsi_b200_set_device", "xpsi_b200_counters",
     "xpsi_b200_stream", "xpsi_b200_atmosphere_create", "xpsi_b200_atmosphere_destroy",
-    "xpsi_b200_integrate_azimuthal_invariance", "xpsi_b200_integrate_general", "xpsi_b200_intensity", "xpsi_b200_energy_integrator",
+    "xpsi_b200_integrate_azimuthal_invariance", "xpsi_b200_integrate_general", "xpsi_b200_intensity",
+    "xpsi_b200_pipeline_set_extras", "xpsi_b200_pipeline_upload_extras", "xpsi_b200_pipeline_fetch_elsewhere", "xpsi_b200_energy_integrator",
     "xpsi_b200_instrument_fold", "xpsi_b200_precomputation", "xpsi_b200_eval_marginal_likelihood",
     "xpsi_b200_pipeline_create", "xpsi_b200_pipeline_destroy", "xpsi_b200_pipeline_eval",
     "xpsi_b200_pipeline_upload", "xpsi_b200_pipeline_eval_resident", "xpsi_b200_pipeline_download",

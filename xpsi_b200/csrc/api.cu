@@ -51,6 +51,7 @@ struct Dev {
   Dev(const Dev&) = delete;
   Dev& operator=(const Dev&) = delete;
   ~Dev() { if (p) cudaFree(p); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
   cudaError_t alloc(size_t count) {
     if (count <= n && p) return cudaSuccess;
     if (p) { cudaFree(p); p = nullptr; }
@@ -632,6 +633,14 @@ struct xpsi_b200_pipeline {
   float embed_ms = 0.f; int embed_timed = 0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float stage_ms[4] = {0, 0, 0, 0};
+  // optional components (xpsi_b200_pipeline_set_extras)
+  xpsi_b200_pipeline_extras ex = {};
+  int else_slab_rows = 0, slab2_chunk = 0, slab2_ring = 0;
+  Dev<double> att_base, att_power, corr, ws_slab2;
+  int att_power_valid = 0, else_arrays_valid = 0, corr_valid = 0, else_temp_valid = 0;
+  Dev<double> x_temp, x_area, x_radial, x_rsr, x_theta, x_phi, x_params, x_defl, x_calpha, x_maxd, x_cgamma,
+      x_maxAlpha, x_grav, x_flux;
+  Dev<int> x_nrings, x_status;
 };
 
 namespace {
@@ -649,6 +658,24 @@ __global__ void k_member_status(const int* status_q, int B, int M, int* status, 
   int s = keep ? status[b] : 0;
   for (int m = 0; m < M; ++m) if (status_q[b * M + m] != 0 && s == 0) s = status_q[b * M + m];
   status[b] = s;
+}
+
+// Photosphere.py:589-592: add the (already normalised) elsewhere spectrum to every phase column of member 0;
+// flux holds raw ring sums that are later divided by E keV, so the spectrum is multiplied back first
+__global__ void k_add_spectrum(const double* spectrum, const double* energies, int B, int M, int N_E, int N_P,
+                               double* flux) {
+  const long n = (long)B * N_E * N_P;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(t / ((long)N_E * N_P));
+    const long r = t - (long)b * N_E * N_P;
+    const int e = (int)(r / N_P);
+    flux[(long)b * M * N_E * N_P + r] += spectrum[(long)b * N_E + e] * (energies[e] * 1.60217662e-16);   // keV, xpsi/global_imports.py:71
+  }
+}
+
+__global__ void k_merge_status(const int* src, int B, int* dst) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && dst[b] == 0 && src[b] != 0) dst[b] = src[b];
 }
 
 int pipeline_upload(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch* h) {
@@ -696,6 +723,35 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   a.phase_interp = c.phase_interpolant;
   a.R_in = 1.0e6;
   a.scale_by_energy = 0;
+  a.beam_opt = p->ex.beam_opt;
+  if (p->ex.elsewhere) {
+    // ---- Elsewhere: time-invariant spectrum of the closed mesh, then the correction in the hot members ----
+    if (!p->else_arrays_valid || !p->corr_valid)
+      return fail(XPSI_B200_EINVAL, "elsewhere is enabled but its per-batch inputs were not provided");
+    xb::TinvArgs t;
+    memset(&t, 0, sizeof(t));
+    t.Q = B; t.sqrt_numPix = p->ex.else_sqrt_num_cells; t.n_rays = p->ex.else_num_rays;
+    t.n_energies = c.n_energies; t.n_params = 2;
+    t.omega = p->omega.p; t.inclination = p->inclination.p; t.cellArea = p->x_area.p;
+    t.radial = p->x_radial.p; t.r_s_over_r = p->x_rsr.p; t.theta = p->x_theta.p; t.phi = p->x_phi.p;
+    t.srcParams = p->x_params.p; t.deflection = p->x_defl.p; t.cos_alpha = p->x_calpha.p;
+    t.maxDeflection = p->x_maxd.p; t.cos_gamma = p->x_cgamma.p; t.energies = p->energies.p;
+    t.atm_ext = p->ex.else_atm_ext;
+    if (t.atm_ext == XPSI_B200_ATM_NUM4D) { t.atm = p->ex.elsewhere_atmosphere->view; t.slab_rows = p->else_slab_rows; }
+    t.image_order_limit = p->ex.else_image_order_limit > 0 ? p->ex.else_image_order_limit : 0;
+    t.flux = p->x_flux.p; t.status = p->x_status.p;
+    CK(cudaMemsetAsync(p->x_flux.p, 0, (size_t)B * c.n_energies * sizeof(double), g_stream));
+    CK(cudaMemsetAsync(p->x_status.p, 0, B * sizeof(int), g_stream));
+    cudaError_t et = xb::launch_integrate_tinv(t, g_stream);
+    if (et != cudaSuccess) return cuda_fail(et, "launch_integrate_tinv");
+    g_launches += 2;
+    a.corrParams = p->corr.p; a.else_atm_ext = p->ex.else_atm_ext;
+    if (a.else_atm_ext == XPSI_B200_ATM_NUM4D) {
+      a.els = p->ex.elsewhere_atmosphere->view; a.ws_slab2 = p->ws_slab2.p;
+      if (p->slab2_chunk > a.slab_ne_max) a.slab_ne_max = p->slab2_chunk;
+      if (p->slab2_ring > a.slab_rows_ring) a.slab_rows_ring = p->slab2_ring;
+    }
+  }
   a.flux = p->flux.p; a.status = p->status_q.p;
   a.ws_leaf = p->ws_leaf.p; a.ws_hdr = p->ws_hdr.p; a.ws_ihdr = p->ws_ihdr.p; a.ws_slab = p->ws_slab.p;
   a.ws_mom = p->ws_mom.p; a.ws_meta = p->ws_meta.p; a.ws_cnt = p->ws_cnt.p; a.mom_cap = p->mom_cap;
@@ -703,6 +759,12 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   if (a.work) CK(cudaMemsetAsync(p->work.p, 0, 4 * sizeof(unsigned long long), g_stream));
   cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_integrate_azinv");
+  if (p->ex.elsewhere) {
+    int blocks = (int)(((long)B * c.n_energies * c.n_phases + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_add_spectrum<<<blocks, 256, 0, g_stream>>>(p->x_flux.p, p->energies.p, B, M, c.n_energies, c.n_phases, p->flux.p);
+    g_launches += 1 + (p->ex.else_atm_ext == XPSI_B200_ATM_NUM4D ? 1 : 0);
+  }
   CK(cudaEventRecord(p->ev[1], g_stream));
 
   xb::EnergyIntegArgs ei;
@@ -711,6 +773,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   ei.signal = p->flux.p; ei.raw_energies = p->energies.p; ei.div_b = p->d_sq.p; ei.q_per_b = M;
   ei.log10_energies = p->log10E.p; ei.log10_edges = p->log10_edges.p; ei.interp = c.phase_interpolant;
   ei.col_of_q = p->col_of_q.p; ei.accumulate = (M > C) ? 1 : 0; ei.out = p->xin.p;
+  if (p->att_base.p) { ei.attenuation = p->att_base.p; ei.att_power = p->att_power_valid ? p->att_power.p : nullptr; }
   if (ei.accumulate)
     CK(cudaMemsetAsync(p->xin.p, 0, (size_t)B * C * c.n_phases * c.n_in * sizeof(double), g_stream));
   e = xb::launch_energy_integrator(ei, g_stream);
@@ -726,6 +789,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   CK(cudaEventRecord(p->ev[3], g_stream));
 
   k_member_status<<<(B + 127) / 128, 128, 0, g_stream>>>(p->status_q.p, B, M, p->status.p, p->embed_status_valid);
+  if (p->ex.elsewhere) k_merge_status<<<(B + 127) / 128, 128, 0, g_stream>>>(p->x_status.p, B, p->status.p);
   p->embed_status_valid = 0;
   xb::MarginalArgs m;
   memset(&m, 0, sizeof(m));
@@ -745,6 +809,22 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
 
 int pipeline_embed_launch(xpsi_b200_pipeline* p) {
   CK(cudaEventRecord(p->ev_embed[0], g_stream));
+  if (p->ex.elsewhere) {
+    if (!p->else_temp_valid) return fail(XPSI_B200_EINVAL, "elsewhere is enabled but else_temperature was not uploaded");
+    p->embed_args.else_temperature = p->x_temp.p; p->embed_args.corrParams = p->corr.p;
+    xb::ClosedMeshArgs m;
+    memset(&m, 0, sizeof(m));
+    m.B = p->embed_args.B; m.n = p->ex.else_sqrt_num_cells; m.n_rays = p->ex.else_num_rays;
+    m.R_eq = p->embed_args.R_eq; m.r_s = p->embed_args.r_s; m.epsilon = p->embed_args.epsilon; m.zeta = p->embed_args.zeta;
+    m.temperature = p->x_temp.p; m.cellArea = p->x_area.p; m.theta = p->x_theta.p; m.phi = p->x_phi.p;
+    m.srcParams = p->x_params.p; m.radial = p->x_radial.p; m.r_s_over_r = p->x_rsr.p; m.cos_gamma = p->x_cgamma.p;
+    m.maxAlpha = p->x_maxAlpha.p; m.ring_gravity = p->x_grav.p; m.deflection = p->x_defl.p; m.cos_alpha = p->x_calpha.p;
+    m.maxDeflection = p->x_maxd.p; m.n_rings = p->x_nrings.p; m.status = p->embed_args.status;
+    cudaError_t ec = xb::launch_embed_closed(m, g_stream);
+    if (ec != cudaSuccess) return cuda_fail(ec, "launch_embed_closed");
+    p->else_arrays_valid = 1; p->corr_valid = 1;
+    g_launches += 2;
+  }
   cudaError_t e = xb::launch_embed_spots(p->embed_args, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_embed_spots");
   CK(cudaEventRecord(p->ev_embed[1], g_stream));
@@ -847,6 +927,83 @@ void xpsi_b200_pipeline_destroy(xpsi_b200_pipeline* p) {
   for (int i = 0; i < 5; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   for (int i = 0; i < 2; ++i) if (p->ev_embed[i]) cudaEventDestroy(p->ev_embed[i]);
   delete p;
+}
+
+int xpsi_b200_pipeline_set_extras(xpsi_b200_pipeline* p, const xpsi_b200_pipeline_extras* x) {
+  if (!p || !x) return fail(XPSI_B200_EINVAL, "null argument");
+  const xpsi_b200_pipeline_config& c = p->cfg;
+  if (x->beam_opt < 0 || x->beam_opt > 3) return fail(XPSI_B200_EINVAL, "beam_opt must be 0-3");
+  if (x->beam_opt != 0 && c.n_params < 7) return fail(XPSI_B200_EINVAL, "beam_opt needs n_params >= 7");
+  p->ex = *x;
+  p->ex.attenuation = nullptr;
+  p->att_power_valid = 0; p->else_arrays_valid = 0; p->corr_valid = 0; p->else_temp_valid = 0;
+  if (x->attenuation) CK(p->att_base.upload(x->attenuation, c.n_in));
+  else p->att_base.release();
+  CK(p->att_power.alloc(p->max_batch));
+  if (x->elsewhere) {
+    const int n = x->else_sqrt_num_cells, nr = x->else_num_rays;
+    if (n < 4 || n > 128 || (n & 1) || nr < 3) return fail(XPSI_B200_EINVAL, "bad elsewhere mesh dimensions");
+    if (x->else_atm_ext != XPSI_B200_ATM_BB && x->else_atm_ext != XPSI_B200_ATM_NUM4D)
+      return fail(XPSI_B200_EUNSUPPORTED, "else_atm_ext must be 1 (BB) or 2 (Num4D)");
+    if (x->else_atm_ext == XPSI_B200_ATM_NUM4D && !x->elsewhere_atmosphere)
+      return fail(XPSI_B200_EINVAL, "Num4D elsewhere needs a preloaded atmosphere");
+    if (c.n_params != 2 && x->beam_opt == 0) return fail(XPSI_B200_EUNSUPPORTED, "elsewhere needs n_params == 2");
+    if (c.n_energies > 256) return fail(XPSI_B200_EINVAL, "elsewhere supports at most 256 energies");
+    const size_t B = p->max_batch, Q = B * c.n_members;
+    CK(p->x_temp.alloc(B)); CK(p->x_area.alloc(B)); CK(p->x_radial.alloc(B * n)); CK(p->x_rsr.alloc(B * n));
+    CK(p->x_theta.alloc(B * n * n)); CK(p->x_phi.alloc(B * n * n)); CK(p->x_params.alloc(B * n * n * 2));
+    CK(p->x_defl.alloc(B * n * nr)); CK(p->x_calpha.alloc(B * n * nr)); CK(p->x_maxd.alloc(B * n));
+    CK(p->x_cgamma.alloc(B * n)); CK(p->x_maxAlpha.alloc(B * n)); CK(p->x_grav.alloc(B * n));
+    CK(p->x_flux.alloc(B * c.n_energies)); CK(p->x_nrings.alloc(B)); CK(p->x_status.alloc(B));
+    CK(p->corr.alloc(Q * c.max_rings * c.n_params));
+    if (x->else_atm_ext == XPSI_B200_ATM_NUM4D) {
+      const xb::AtmTable& t = x->elsewhere_atmosphere->view;
+      p->else_slab_rows = xb::tinv_slab_rows(t, c.energies, c.n_energies);
+      xb::azinv_slab_budgets(t, c.energies, c.n_energies, &p->slab2_chunk, &p->slab2_ring);
+      // the hot and the correction slabs share the per-ring stride: size both workspaces for the larger one
+      const int rows = p->slab2_ring > p->slab_rows_ring ? p->slab2_ring : p->slab_rows_ring;
+      const int nmu = (c.hot_atm_ext == XPSI_B200_ATM_NUM4D && p->atm->view.nmu > t.nmu) ? p->atm->view.nmu : t.nmu;
+      CK(p->ws_slab2.alloc(Q * c.max_rings * (size_t)nmu * rows));
+      if (c.hot_atm_ext == XPSI_B200_ATM_NUM4D && rows > p->slab_rows_ring)
+        CK(p->ws_slab.alloc(Q * c.max_rings * (size_t)nmu * rows));
+    }
+  }
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int xpsi_b200_pipeline_upload_extras(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch_extras* h) {
+  if (!p || !h || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
+  const xpsi_b200_pipeline_config& c = p->cfg;
+  if (h->att_power) { CK(p->att_power.upload(h->att_power, B)); p->att_power_valid = 1; }
+  if (p->ex.elsewhere) {
+    const size_t n = p->ex.else_sqrt_num_cells, nr = p->ex.else_num_rays;
+    if (h->else_temperature) { CK(p->x_temp.upload(h->else_temperature, B)); p->else_temp_valid = 1; }
+    if (h->else_cellArea) {
+      if (!h->else_radial || !h->else_r_s_over_r || !h->else_theta || !h->else_phi || !h->else_srcParams ||
+          !h->else_deflection || !h->else_cos_alpha || !h->else_maxDeflection || !h->else_cos_gamma)
+        return fail(XPSI_B200_EINVAL, "incomplete elsewhere arrays");
+      CK(p->x_area.upload(h->else_cellArea, B)); CK(p->x_radial.upload(h->else_radial, B * n));
+      CK(p->x_rsr.upload(h->else_r_s_over_r, B * n)); CK(p->x_theta.upload(h->else_theta, B * n * n));
+      CK(p->x_phi.upload(h->else_phi, B * n * n)); CK(p->x_params.upload(h->else_srcParams, B * n * n * 2));
+      CK(p->x_defl.upload(h->else_deflection, B * n * nr)); CK(p->x_calpha.upload(h->else_cos_alpha, B * n * nr));
+      CK(p->x_maxd.upload(h->else_maxDeflection, B * n)); CK(p->x_cgamma.upload(h->else_cos_gamma, B * n));
+      p->else_arrays_valid = 1;
+    }
+    if (h->correction_srcParams) {
+      CK(p->corr.upload(h->correction_srcParams, (size_t)B * c.n_members * c.max_rings * c.n_params));
+      p->corr_valid = 1;
+    }
+  }
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int xpsi_b200_pipeline_fetch_elsewhere(xpsi_b200_pipeline* p, int B, double* spectrum) {
+  if (!p || !p->ex.elsewhere || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "no elsewhere spectrum");
+  CK(p->x_flux.download(spectrum, (size_t)B * p->cfg.n_energies));
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
 }
 
 int xpsi_b200_pipeline_upload(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch* h) {

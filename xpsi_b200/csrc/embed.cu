@@ -16,6 +16,8 @@
 // *not* converged quantities are reproduced exactly: the 1000-node area table and its
 // Steffen inverse interpolation for the ring parallels, the equal-area ring/cell layout,
 // the 5-point boundary-cell test, the cos(alpha) ray grid.
+#include <string.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -229,6 +231,10 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
     a.maxAlpha[ring0 + i] = kHalfPi + acos(cg);                     // mesh.pyx:253
     a.srcParams[(ring0 + i) * 2 + 0] = a.temperature[q];            // HotRegion.py:965-994
     a.srcParams[(ring0 + i) * 2 + 1] = effective_gravity(mu, R_eq, zeta, eps);
+    if (a.corrParams) {      // elsewhere parameters on the spot's mesh (HotRegion.py:1019-1031, Elsewhere.py:308-331)
+      a.corrParams[(ring0 + i) * 2 + 0] = a.else_temperature[b];
+      a.corrParams[(ring0 + i) * 2 + 1] = a.srcParams[(ring0 + i) * 2 + 1];
+    }
   }
   if (tid == 0) { a.n_rings[q] = n; a.n_azi[q] = n; }
   __syncthreads();
@@ -361,12 +367,88 @@ __global__ void __launch_bounds__(128) k_rays(EmbedArgs a) {
     if (d != d || l != l || d < 0.0) s_bad = 1;                    // the reference patches such rays linearly
     a.cos_alpha[ring * N_R + j] = ca;
     a.deflection[ring * N_R + j] = d;
-    a.lag[ring * N_R + j] = (l - Ccal) * two_pi_f;
+    if (a.lag) a.lag[ring * N_R + j] = (l - Ccal) * two_pi_f;
     if (j >= N_R - 2) s_last[j - (N_R - 2)] = d;
     if (j == N_R - 1) a.maxDeflection[ring] = d;
   }
   __syncthreads();
   if (threadIdx.x == 0 && (s_bad || !(s_last[1] > s_last[0]))) atomicExch(a.status + b, kNumericalError);   // rays.pyx:327-331
+}
+
+// ---- closed mesh of the whole surface (cellmesh/global_mesh.pyx:18-147), for Elsewhere ------------------
+// One CTA per parameter vector.  Equal-area cells: n x n, ring colatitudes from the same 1000-node
+// area table + Steffen inverse the reference uses, southern rings mirrored (:118-123).
+__global__ void __launch_bounds__(kMeshThreads) k_closed_mesh(ClosedMeshArgs a) {
+  const int b = blockIdx.x, tid = threadIdx.x, n = a.n, nc = a.n / 2;
+  const double R_eq = a.R_eq[b], eps = a.epsilon[b], zeta = a.zeta[b], r_s = a.r_s[b];
+  __shared__ double s_area[kAreaNodes], s_colat[kAreaNodes];
+  __shared__ double s_par[128], s_theta[128];
+  // :55-60  cellArea = 2 * 2 pi * A(0, pi/2) / numCell;  eta = cellArea * n / 2 pi
+  const double cellA = 2.0 * kTwoPi * integrate_area(0.0, kHalfPi, eps, zeta, 0) / (double)(n * n);
+  const double eta = cellA * (double)n / kTwoPi;
+  for (int i = tid; i < kAreaNodes; i += kMeshThreads) {
+    const double c = kHalfPi + (0.0 - kHalfPi) * ((double)i / (double)(kAreaNodes - 1));   // linspace(pi/2, 0, 1000)
+    s_colat[i] = (i == kAreaNodes - 1) ? 0.0 : c;
+    s_area[i] = integrate_area(s_colat[i], kHalfPi, eps, zeta, 0);
+  }
+  __syncthreads();
+  for (int i = tid; i < nc - 1; i += kMeshThreads) {
+    double ie = (double)nc * eta;                      // the reference accumulates i_eta -= eta (:83-87)
+    for (int k = 0; k <= i; ++k) ie -= eta;
+    const int idx = interval_search(s_area, kAreaNodes, ie);
+    double val, der;
+    steffen_eval(s_area, s_colat, kAreaNodes, idx, ie, &val, &der);
+    s_par[i] = val;
+  }
+  __syncthreads();
+  const long ring0 = (long)b * n;
+  for (int i = tid; i < nc; i += kMeshThreads) {       // northern rings (:92-116)
+    const double l = (i == 0) ? 0.0 : s_par[i - 1];
+    const double u = (i == nc - 1) ? kHalfPi : s_par[i];
+    const double th = integrate_area(l, u, eps, zeta, 1) / eta;
+    const double mu = cos(th);
+    const double rn = radius_normalised(mu, eps, zeta);
+    const double f = f_theta(mu, rn, eps, zeta);
+    const double cg = 1.0 / sqrt(1.0 + f * f);
+    const double g = effective_gravity(mu, R_eq, zeta, eps);
+    const int im = n - 1 - i;                          // mirrored southern ring (:118-123)
+    s_theta[i] = th; s_theta[im] = kPi - th;
+    a.radial[ring0 + i] = rn * R_eq; a.radial[ring0 + im] = rn * R_eq;
+    a.r_s_over_r[ring0 + i] = r_s / (rn * R_eq); a.r_s_over_r[ring0 + im] = r_s / (rn * R_eq);   // Elsewhere.py:282
+    a.cos_gamma[ring0 + i] = cg; a.cos_gamma[ring0 + im] = cg;
+    a.maxAlpha[ring0 + i] = kHalfPi + acos(cg); a.maxAlpha[ring0 + im] = kHalfPi + acos(cg);
+    a.ring_gravity[ring0 + i] = g; a.ring_gravity[ring0 + im] = g;
+  }
+  if (tid == 0) { a.cellArea[b] = cellA * R_eq * R_eq; a.n_rings[b] = n; }
+  __syncthreads();
+  const double dphi = kTwoPi / (double)n;
+  const double start = -kPi + 0.5 * dphi, stop = kPi - 0.5 * dphi;
+  const double step = (stop - start) / (double)(n - 1);
+  const double T = a.temperature[b];
+  for (int t = tid; t < n * n; t += kMeshThreads) {
+    const int i = t / n, j = t - i * n;
+    const long c = (ring0 + i) * n + j;
+    a.theta[c] = s_theta[i];
+    a.phi[c] = (j == n - 1) ? stop : start + step * (double)j;      // numpy.linspace (:116-117)
+    a.srcParams[2 * c] = T;                                          // Elsewhere.py:308-331
+    a.srcParams[2 * c + 1] = a.ring_gravity[ring0 + i];
+  }
+}
+
+cudaError_t launch_embed_closed(ClosedMeshArgs a, cudaStream_t stream) {
+  if (a.n < 4 || a.n > 128 || (a.n & 1)) return cudaErrorInvalidValue;
+  k_closed_mesh<<<a.B, kMeshThreads, 0, stream>>>(a);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  EmbedArgs r;                                   // rays of the n rings (Elsewhere.py:270-300): no lag needed
+  memset(&r, 0, sizeof(r));
+  r.B = a.B; r.M = 1; r.max_rings = a.n; r.n_rays = a.n_rays;
+  r.R_eq = a.R_eq; r.r_s = a.r_s; r.n_rings = a.n_rings; r.r_s_over_r = a.r_s_over_r; r.maxAlpha = a.maxAlpha;
+  r.deflection = a.deflection; r.cos_alpha = a.cos_alpha; r.lag = nullptr; r.maxDeflection = a.maxDeflection;
+  r.status = a.status;
+  dim3 grid(a.n, a.B);
+  k_rays<<<grid, 128, 0, stream>>>(r);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_embed_spots(EmbedArgs a, cudaStream_t stream) {

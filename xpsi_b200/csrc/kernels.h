@@ -96,6 +96,8 @@ struct EmbedArgs {
   const double* R_eq; const double* r_s; const double* epsilon; const double* zeta;      // [B] Spacetime.py:110-188
   const double* colatitude; const double* ang_radius; const double* temperature;        // [B*M]
   const double* phi_shift;                        // [B*M] added to cell azimuths (pi if antiphased)
+  const double* else_temperature;                 // nullptr, or [B]: log10 T of Elsewhere (for corrParams)
+  double* corrParams;                             // nullptr, or [B*M][max_rings][2]: correction parameter rows
   // outputs: the integrator's per-instance inputs (padded layout of AzinvArgs)
   int* n_rings; int* n_azi;
   double* cellArea; double* phi; double* theta; double* radial; double* r_s_over_r; double* srcParams;
@@ -104,6 +106,20 @@ struct EmbedArgs {
   int* status;                                    // [B]
 };
 cudaError_t launch_embed_spots(EmbedArgs a, cudaStream_t stream);
+
+// f1: embed of the closed whole-surface mesh of Elsewhere (global_mesh.pyx + rays) into TinvArgs arrays
+struct ClosedMeshArgs {
+  int B, n, n_rays;                               // n = sqrt_num_cells (even)
+  const double* R_eq; const double* r_s; const double* epsilon; const double* zeta;      // [B]
+  const double* temperature;                      // [B] log10 T
+  double* cellArea;                               // [B]
+  double* theta; double* phi; double* srcParams;  // [B][n][n], [B][n][n], [B][n][n][2]
+  double* radial; double* r_s_over_r; double* cos_gamma; double* maxAlpha; double* ring_gravity;   // [B][n]
+  double* deflection; double* cos_alpha; double* maxDeflection;                          // [B][n][n_rays], [B][n]
+  int* n_rings;                                   // [B] scratch
+  int* status;                                    // [B]
+};
+cudaError_t launch_embed_closed(ClosedMeshArgs a, cudaStream_t stream);
 
 // a9: tools/energy_integrator.pyx:27-114, one spline per (signal q, phase column)
 struct EnergyIntegArgs {
@@ -119,6 +135,7 @@ struct EnergyIntegArgs {
   const int* col_of_q;               // nullptr => q
   int accumulate;
   const double* attenuation;         // nullptr or [n_in] (Interstellar.__call__)
+  const double* att_power;           // nullptr, or [Q/q_per_b]: the factor is attenuation[j] ** att_power[b]
   double* out;
 };
 cudaError_t launch_energy_integrator(EnergyIntegArgs a, cudaStream_t stream);

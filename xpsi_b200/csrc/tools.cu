@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kEIThreads) k_energy_integrator(EnergyIntegArg
         val = lo;
       }
     }
-    if (a.attenuation) val *= a.attenuation[j];
+    if (a.attenuation) val *= a.att_power ? pow(a.attenuation[j], a.att_power[q / a.q_per_b]) : a.attenuation[j];
     if (a.accumulate) atomicAdd(out + j, val); else out[j] = val;
   }
 }

@@ -204,6 +204,74 @@ class BatchedLikelihood:
         except Exception:
             pass
 
+    def set_extras(self, elsewhere=None, attenuation=None, beam_opt=0):
+        """Optional model components (set once).
+
+        ``elsewhere``: dict(sqrt_num_cells, num_rays, atm_ext, atmosphere=None, image_order_limit=None) adds
+        ``xpsi.Elsewhere`` (xpsi/Elsewhere.py:129-134 for the defaults the reference uses): its spectrum is
+        added to member 0 (xpsi/Photosphere.py:589-592) and the hot members get the elsewhere correction.
+        ``attenuation``: interstellar attenuation factor per instrument input interval at unit power
+        (xpsi/Interstellar.py:27-58); the per-theta power comes with ``upload_extras(att_power=...)``.
+        ``beam_opt``: beaming option of the hot regions (xpsi/HotRegion.py:184-200)."""
+        x = _lib.PipelineExtras()
+        self._extras_keep = []
+        if elsewhere is not None:
+            x.elsewhere = 1
+            x.else_sqrt_num_cells = int(elsewhere["sqrt_num_cells"])
+            x.else_num_rays = int(elsewhere["num_rays"])
+            x.else_atm_ext = int(elsewhere["atm_ext"])
+            x.else_image_order_limit = int(elsewhere.get("image_order_limit") or 0)
+            if x.else_atm_ext == 2:
+                atm = _lib.Atmosphere.get(elsewhere["atmosphere"])
+                self._extras_keep.append(atm)
+                x.elsewhere_atmosphere = atm.handle
+            self.elsewhere = dict(n=x.else_sqrt_num_cells, n_rays=x.else_num_rays)
+        if attenuation is not None:
+            att = np.ascontiguousarray(attenuation, dtype=np.float64)
+            if att.shape != (self.shape["n_in"],):
+                raise ValueError("one attenuation factor per instrument input interval is required")
+            self._extras_keep.append(att)
+            x.attenuation = _lib.dptr(att)
+        x.beam_opt = int(beam_opt)
+        _lib.check(_lib.lib.xpsi_b200_pipeline_set_extras(self.handle, C.byref(x)))
+
+    def upload_extras(self, B, att_power=None, else_temperature=None, elsewhere=None, correction_srcParams=None):
+        """Per-batch inputs of the optional components for the next evaluation.
+
+        theta-level path: ``else_temperature[B]`` (+ ``att_power[B]``).  Mesh-level path: ``elsewhere`` = dict of
+        the arrays ``Elsewhere.embed`` produced with a leading batch axis (cellArea[B], radial, r_s_over_r,
+        maxDeflection, cos_gamma [B,n], theta, phi [B,n,n], srcParams [B,n,n,2], deflection, cos_alpha
+        [B,n,num_rays]) and ``correction_srcParams[B*M, max_rings, n_params]``."""
+        x = _lib.BatchExtras()
+        keep = []
+
+        def put(field, arr, shape=None):
+            a = np.ascontiguousarray(arr, dtype=np.float64)
+            if shape is not None and a.shape != shape:
+                raise ValueError("%s must have shape %r, got %r" % (field, shape, a.shape))
+            keep.append(a)
+            setattr(x, field, _lib.dptr(a))
+        if att_power is not None:
+            put("att_power", att_power, (B,))
+        if else_temperature is not None:
+            put("else_temperature", else_temperature, (B,))
+        if elsewhere is not None:
+            n, nr = self.elsewhere["n"], self.elsewhere["n_rays"]
+            shapes = dict(cellArea=(B,), radial=(B, n), r_s_over_r=(B, n), theta=(B, n, n), phi=(B, n, n),
+                          srcParams=(B, n, n, 2), deflection=(B, n, nr), cos_alpha=(B, n, nr),
+                          maxDeflection=(B, n), cos_gamma=(B, n))
+            for k, shp in shapes.items():
+                put("else_" + k, elsewhere[k], shp)
+        if correction_srcParams is not None:
+            s = self.shape
+            put("correction_srcParams", correction_srcParams, (B * self.n_members, s["max_rings"], s["n_params"]))
+        _lib.check(_lib.lib.xpsi_b200_pipeline_upload_extras(self.handle, B, C.byref(x)))
+
+    def fetch_elsewhere(self, B):
+        out = np.empty((B, self.shape["n_energies"]))
+        _lib.check(_lib.lib.xpsi_b200_pipeline_fetch_elsewhere(self.handle, B, _lib.dptr(out)))
+        return out
+
     def new_batch(self, B, pinned=False):
         s = self.shape
         return HostBatch(B, self.n_members, self.n_components, s["max_rings"], s["max_azi"],
