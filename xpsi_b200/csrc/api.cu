@@ -94,7 +94,7 @@ std::vector<int> response_k_ranges(const double* m, int n_chan, int ld, int in0,
 }  // namespace
 
 struct xpsi_b200_atmosphere {
-  Dev<double> logT, logg, mu, logE, buf;
+  Dev<double> logT, logg, mu, logE, buf, mu_invden, E_invden;
   xb::AtmTable view;
 };
 
@@ -145,7 +145,26 @@ xpsi_b200_atmosphere* xpsi_b200_atmosphere_create(const double* logT, int nT, co
   if (e != cudaSuccess) { cuda_fail(e, "atmosphere_create"); delete a; return nullptr; }
   double dmin = 1e300;
   for (int i = 1; i < nE; ++i) dmin = fmin(dmin, logE[i] - logE[i - 1]);
-  a->view = xb::AtmTable{a->logT.p, a->logg.p, a->mu.p, a->logE.p, a->buf.p, nT, ng, nmu, nE, dmin};
+  // inverse Lagrange denominators per base node of the mu and E axes (hot_Num4D.pyx:386-409 "SPACE"), so the
+  // kernels' stencil weights need no divisions
+  auto invden = [](const double* p, int n) {
+    std::vector<double> v((size_t)(n - 3) * 4);
+    for (int b = 0; b + 3 < n; ++b) {
+      const double p0 = p[b], p1 = p[b + 1], p2 = p[b + 2], p3 = p[b + 3];
+      v[4 * b + 0] = 1.0 / (p0 - p1) / (p0 - p2) / (p0 - p3);
+      v[4 * b + 1] = 1.0 / (p1 - p0) / (p1 - p2) / (p1 - p3);
+      v[4 * b + 2] = 1.0 / (p2 - p0) / (p2 - p1) / (p2 - p3);
+      v[4 * b + 3] = 1.0 / (p3 - p0) / (p3 - p1) / (p3 - p2);
+    }
+    return v;
+  };
+  std::vector<double> im = invden(mu, nmu), ie = invden(logE, nE);
+  e = a->mu_invden.upload(im.data(), im.size());
+  if (e == cudaSuccess) e = a->E_invden.upload(ie.data(), ie.size());
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+  if (e != cudaSuccess) { cuda_fail(e, "atmosphere_create"); delete a; return nullptr; }
+  a->view = xb::AtmTable{a->logT.p, a->logg.p, a->mu.p, a->logE.p, a->buf.p, nT, ng, nmu, nE, dmin,
+                         a->mu_invden.p, a->E_invden.p};
   return a;
 }
 

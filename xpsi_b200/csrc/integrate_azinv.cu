@@ -597,6 +597,7 @@ struct SlabCtx {
   double* axE; double* invden; double* axMu; double* slab; double* muw; int* mub;
   int nrows, elo_tab, nE, nmu;
   double inv_dE, log_kT;
+  const double* mu_invden;            // global, [nmu-3][4]
 };
 
 __device__ __forceinline__ double* slab_ctx_carve(SlabCtx& c, double* sp, int N_L, int rows_max, int nmu) {
@@ -624,14 +625,10 @@ __device__ __forceinline__ bool slab_ctx_load(SlabCtx& c, const AtmTable& T, con
   return true;
 }
 
-__device__ __forceinline__ void slab_ctx_finish(SlabCtx& c, int tid) {     // after a barrier
-  for (int r = tid; r + 3 < c.nrows; r += kFluxThreads) {       // Lagrange denominators per base row
-    const double p0 = c.axE[r], p1 = c.axE[r + 1], p2 = c.axE[r + 2], p3 = c.axE[r + 3];
-    c.invden[4 * r + 0] = 1.0 / (p0 - p1) / (p0 - p2) / (p0 - p3);
-    c.invden[4 * r + 1] = 1.0 / (p1 - p0) / (p1 - p2) / (p1 - p3);
-    c.invden[4 * r + 2] = 1.0 / (p2 - p0) / (p2 - p1) / (p2 - p3);
-    c.invden[4 * r + 3] = 1.0 / (p3 - p0) / (p3 - p1) / (p3 - p2);
-  }
+__device__ __forceinline__ void slab_ctx_finish(SlabCtx& c, const AtmTable& T, int tid) {     // after a barrier
+  // Lagrange denominators per base row: copied from the table's precomputed list
+  for (int r = tid; r < 4 * (c.nrows - 3); r += kFluxThreads) c.invden[r] = __ldg(T.E_invden + 4 * c.elo_tab + r);
+  c.mu_invden = T.mu_invden;
   // mean spacing of the axis segment: first guess of the energy stencil (then walked)
   c.inv_dE = (c.nrows > 1) ? (double)(c.nrows - 1) / (c.axE[c.nrows - 1] - c.axE[0]) : 0.0;
 }
@@ -647,7 +644,12 @@ __device__ __forceinline__ void slab_ctx_leaf_stencils(const SlabCtx& c, const d
     if (clamp_low && v < c.axMu[0]) v = c.axMu[0];
     const int b = lagrange_base(c.axMu, c.nmu, v);
     double w[4];
-    lagrange_weights(c.axMu, b, v, w);
+    {
+      const double d0 = v - c.axMu[b], d1 = v - c.axMu[b + 1], d2 = v - c.axMu[b + 2], d3 = v - c.axMu[b + 3];
+      const double* iv = c.mu_invden + 4 * b;
+      w[0] = d1 * d2 * d3 * __ldg(iv); w[1] = d0 * d2 * d3 * __ldg(iv + 1);
+      w[2] = d0 * d1 * d3 * __ldg(iv + 2); w[3] = d0 * d1 * d2 * __ldg(iv + 3);
+    }
     c.mub[l] = b;
 #pragma unroll
     for (int x = 0; x < 4; ++x) c.muw[x * N_L + l] = w[x];
@@ -694,8 +696,22 @@ __device__ __noinline__ double slab_ctx_eval_mu(const SlabCtx& c, double v, doub
   return sum < 0.0 ? 0.0 : sum;
 }
 
+// beaming of one profile value; zstore is Z (blackbody) or log10 Z (Num4D), logT the ring's log10 T
+template <int ATM>
+__device__ __noinline__ double profile_beaming(int beam_opt, const SlabCtx& hot, double I_E, double E, double logE,
+                                               double zstore, double mu, double kT, double log_kT, double logT,
+                                               const double* BV) {
+  const double Ep = (ATM == 2) ? E * exp10(-zstore) : E / zstore;
+  const double t3 = (ATM == 2) ? pow(10.0, 3.0 * logT) : 1.0;
+  const double v = logE - zstore - log_kT;
+  return apply_beaming(beam_opt, I_E * t3, Ep, mu, BV, [&](double mu_i) -> double {
+           return (ATM == 2) ? slab_ctx_eval_mu(hot, v, mu_i) * t3 : bb_intensity(Ep, kT);
+         }) / t3;
+}
+
 // ATM: hot atmosphere (1 BB, 2 Num4D).  CORR: elsewhere correction (0 none, 1 BB, 2 Num4D)
-template <int ATM, int CORR>
+// BEAM: 0 = no beaming code at all (keeps the common instantiation free of the call's register pressure)
+template <int ATM, int CORR, int BEAM>
 __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flux(AzinvArgs a) {
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
   const int i = blockIdx.x / n_chunks;
@@ -769,8 +785,8 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
   __syncthreads();
   const int n_cells = s_ncell;
   if (n_cells == 0) return;
-  if (ATM == 2) slab_ctx_finish(hot, tid);
-  if (CORR == 2) slab_ctx_finish(els, tid);
+  if (ATM == 2) slab_ctx_finish(hot, a.hot, tid);
+  if (CORR == 2) slab_ctx_finish(els, a.els, tid);
 
   const int interp_kind = a.phase_interp;
   const int k = tid;                         // output phase owned in the accumulation stage
@@ -804,15 +820,9 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
         double I_E;
         if (ATM == 1) I_E = bb_intensity(s_E[e] / s_Z[l], kT);
         else I_E = slab_ctx_eval(hot, s_logE[e] - s_Z[l] - log_kT, l, N_L);
-        if (a.beam_opt != 0) {            // hot_wrapper.pyx:155-199 (options 1-3)
-          const double* BV = a.srcParams + (a.params_per_cell ? (cell0 + ih[1]) : ring) * a.n_params;
-          const double Ep = (ATM == 2) ? s_E[e] * exp10(-s_Z[l]) : s_E[e] / s_Z[l];
-          const double t3 = (ATM == 2) ? pow(10.0, 3.0 * dh[10]) : 1.0;
-          const double v = s_logE[e] - s_Z[l] - log_kT;
-          I_E = apply_beaming(a.beam_opt, I_E * t3, Ep, s_abb[l], BV, [&](double mu_i) -> double {
-                  return (ATM == 2) ? slab_ctx_eval_mu(hot, v, mu_i) * t3 : bb_intensity(Ep, kT);
-                }) / t3;
-        }
+        if (BEAM)                         // hot_wrapper.pyx:155-199 (options 1-3); kept out of line: rarely used
+          I_E = profile_beaming<ATM>(a.beam_opt, hot, I_E, s_E[e], s_logE[e], s_Z[l], s_abb[l], kT, log_kT, dh[10],
+                                     a.srcParams + (a.params_per_cell ? (cell0 + ih[1]) : ring) * a.n_params);
         double corr = 0.0;
         if (CORR == 1) {
           const double Z = (ATM == 2) ? exp10(s_Z[l]) : s_Z[l];
@@ -905,10 +915,18 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
         // moments prepared once per (ring, image) by k_azinv_moments; loads are coalesced over k
         const double* mom = a.ws_mom + slot * (long)a.mom_cap * 4 * N_P + k;
         const int2* meta = a.ws_meta + slot * (long)a.mom_cap * N_P + k;
+        // software pipeline: entry t+1 is in flight (L2) while entry t is consumed
+        double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+        int2 nm = make_int2(0, 0);
+        if (cnt > 0) { n0 = mom[0]; n1 = mom[N_P]; n2 = mom[2 * N_P]; n3 = mom[3 * N_P]; nm = meta[0]; }
         for (int t = 0; t < cnt; ++t) {
-          const double* e = mom + (long)t * 4 * N_P;
-          const double W0 = e[0], W1 = e[N_P], W2 = e[2 * N_P], W3 = e[3 * N_P];
-          const int2 mt = meta[(long)t * N_P];
+          const double W0 = n0, W1 = n1, W2 = n2, W3 = n3;
+          const int2 mt = nm;
+          if (t + 1 < cnt) {
+            const double* e = mom + (long)(t + 1) * 4 * N_P;
+            n0 = e[0]; n1 = e[N_P]; n2 = e[2 * N_P]; n3 = e[3 * N_P];
+            nm = meta[(long)(t + 1) * N_P];
+          }
           flush(mt.x, W0, W1, W2, W3, mt.y & 0xffff, mt.y >> 16);
         }
       } else {
@@ -999,12 +1017,17 @@ void azinv_slab_budgets(const AtmTable& t, const double* energies, int n_energie
   *rows_ring = rr > t.nE ? t.nE : rr;
 }
 
+template <int ATM, int CORR, int BEAM>
+static cudaError_t launch_flux_b(const AzinvArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(k_azinv_flux<ATM, CORR, BEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  k_azinv_flux<ATM, CORR, BEAM><<<grid, kFluxThreads, smem, stream>>>(a);
+  return cudaGetLastError();
+}
 template <int ATM, int CORR>
 static cudaError_t launch_flux(const AzinvArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
-  cudaError_t err = cudaFuncSetAttribute(k_azinv_flux<ATM, CORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (err != cudaSuccess) return err;
-  k_azinv_flux<ATM, CORR><<<grid, kFluxThreads, smem, stream>>>(a);
-  return cudaGetLastError();
+  return a.beam_opt != 0 ? launch_flux_b<ATM, CORR, 1>(a, grid, smem, stream)
+                         : launch_flux_b<ATM, CORR, 0>(a, grid, smem, stream);
 }
 
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {

@@ -14,6 +14,8 @@ struct AtmTable {
   const double* buf;                 // C-order [T][g][mu][E]
   int nT, ng, nmu, nE;
   double min_dlogE;                  // smallest spacing of the logE axis (host-computed)
+  const double* mu_invden;           // [nmu-3][4] inverse Lagrange denominators per base node (host-computed)
+  const double* E_invden;            // [nE-3][4]
 };
 
 // a1: integrator_for_azimuthal_invariance.integrate, batched over Q member instances.
