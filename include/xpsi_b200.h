@@ -234,9 +234,10 @@ typedef struct {
   const double* maxDeflection; const double* cos_gamma;                 /* [B*M][max_rings] */
 } xpsi_b200_batch;
 
-/* Parameter-level inputs for models whose hot-region members are simple circular spots (ST, ST-U):
- * the library then runs the embed (mesh + rays, replacing HotRegion.embed, xpsi/HotRegion.py:1033-1070,
- * mesh.pyx / mesh_tools.pyx / rays.pyx) on the GPU as well.                                          */
+/* Parameter-level inputs for hot regions made of circular members (ST, ST-U, and with the optional
+ * fields CST / EST / PST / CDT / EDT / PDT, polar caps included): the library then runs the embed
+ * (mesh + rays, replacing HotRegion.embed, xpsi/HotRegion.py:1033-1070, mesh.pyx / polar_mesh.pyx /
+ * mesh_tools.pyx / rays.pyx) on the GPU as well.                                                     */
 typedef struct {
   /* per theta [B]: derived spacetime scalars, xpsi/Spacetime.py:110-188 */
   const double* R_eq; const double* r_s; const double* epsilon; const double* zeta;
@@ -247,6 +248,16 @@ typedef struct {
   const double* phi_shift;                       /* radians added to cell azimuths (pi: antiphased) */
   double mode_frequency;                         /* Hz                                            */
   int num_cells, min_sqrt_num_cells, max_sqrt_num_cells;
+  /* optional (NULL: plain circular spots).  The region masking each member: the omission hole of a
+   * superseding member (omit_radius, omit_colatitude, omit_azimuth) or the superseding region inside a
+   * ceding member (super_radius, super_colatitude, -cede_azimuth), as HotRegion passes them to the mesh
+   * routines (xpsi/HotRegion.py:819-865); radius 0 = none.  Members covering a pole are meshed by the
+   * polar variant (cellmesh/polar_mesh.pyx) automatically.                                          */
+  const double* hole_radius; const double* hole_colatitude; const double* hole_azimuth;   /* [B*M] */
+  /* optional (NULL: every member allocates num_cells alone): superseding / ceding members of one hot
+   * region share num_cells (mesh_tools.pyx:1040-1060): partner[m] = index of the other member or -1,
+   * is_cede[m] = 1 for the ceding member                                                            */
+  const int* partner; const int* is_cede;         /* [M] */
 } xpsi_b200_spot_batch;
 
 /* ---- optional model components of the batched pipeline ---------------------------------------------

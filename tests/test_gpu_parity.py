@@ -599,3 +599,86 @@ def test_m4_batched_pipeline_with_elsewhere_and_interstellar(m2):
     err = rel_err(spec2[0], d["else_flux"])
     print("GPU-embedded elsewhere spectrum rel err", err)
     assert err < PULSE_RTOL
+
+
+def _embed_errors(e, q, g):
+    """errors of embedded member q (pipeline.fetch_embed) against the reference's integrator inputs g(key)"""
+    n = g("cellArea").shape[0]
+    full = g("cellArea").max()
+    return n, dict(
+        theta=np.max(np.abs(e["theta"][q, :n] - g("theta")[:, 0])),
+        phi=np.max(np.abs(e["phi"][q, :n, :n] - g("phi"))),
+        radial=np.max(np.abs(e["radial"][q, :n] / g("radialCoords_of_parallels") - 1.0)),
+        cos_gamma=np.max(np.abs(e["cos_gamma"][q, :n] - g("cos_gammaArray"))),
+        params=np.max(np.abs(e["srcParams"][q, :n] - g("srcCellParams")[:, 0, :])),
+        area=np.max(np.abs(e["cellArea"][q, :n, :n] - g("cellArea"))) / full,
+        cos_alpha=np.max(np.abs(e["cos_alpha"][q, :n] - g("cos_alpha"))),
+        deflection=np.max(np.abs(e["deflection"][q, :n] - g("deflection")) / np.maximum(g("deflection"), 1e-3)),
+        lag=np.max(np.abs(e["lag"][q, :n] - g("lag"))) / np.max(np.abs(g("lag"))),
+        maxDeflection=np.max(np.abs(e["maxDeflection"][q, :n] / g("maxDeflection") - 1.0)))
+
+
+def _check_embed(e, q, g, tag):
+    n, errs = _embed_errors(e, q, g)
+    print("embed", tag, "mesh", n, {k: float("%.2e" % v) for k, v in errs.items()})
+    assert e["n_rings"][q] == n, tag
+    # the radiating set must agree except for slivers below the reference's own quadrature tolerance
+    mism = (e["cellArea"][q, :n, :n] > 0) != (g("cellArea") > 0)
+    assert np.all(np.maximum(e["cellArea"][q, :n, :n], g("cellArea"))[mism] < 1e-7 * g("cellArea").max()), tag
+    assert errs["theta"] < 1e-12 and errs["phi"] < 1e-13 and errs["radial"] < 1e-13, tag
+    assert errs["cos_gamma"] < 1e-13 and errs["params"] < 1e-12, tag
+    assert errs["area"] < 1e-7, tag            # the reference integrates cell areas with CQUAD at epsrel 1e-8
+    assert errs["cos_alpha"] < 1e-13 and errs["deflection"] < 1e-11 and errs["lag"] < 1e-10, tag
+    assert errs["maxDeflection"] < 1e-11, tag
+
+
+def test_gpu_embed_of_omission_ceding_and_polar_regions(m2):
+    """f1: CST + PDT hot regions (omission hole; superseding + ceding members sharing the cell budget) and polar
+    caps (polar_mesh.pyx) embedded on the GPU from parameter values, against the reference's embed and lnL."""
+    from conftest import GOLDEN
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.pipeline import BatchedLikelihood
+    table = syn.nsx_like_table()
+    matrix, edges = syn.nicer_like_response()[:2]
+    # ---- M3: primary CST, secondary PDT -----------------------------------------------------------------
+    d = np.load(os.path.join(GOLDEN, "m3_cst_pdt.npz"))
+    th = dict(zip([str(n) for n in d["names"]], d["theta"]))
+    pipe = BatchedLikelihood(member_component=[0, 1, 1], max_rings=80, max_azi=80, n_rays=512,
+                             energies=d["int0_energies"], leaves=d["int0_leaves"], phases=d["int0_phases"],
+                             hot_atm_ext=2, hot_atmosphere=table, image_order_limit=3, response=matrix,
+                             energy_edges=edges, counts=d["counts"], data_phases=np.linspace(0.0, 1.0, 33),
+                             exposure_time=syn.M2_EXPOSURE, max_batch=2)
+    B = 2
+    sb = pipe.new_spot_batch(B, syn.M2_FREQUENCY, num_cells=1024, min_sqrt_num_cells=10, max_sqrt_num_cells=80)
+    one = np.ones(B)
+    sb.set_spacetime(th["mass"] * one, th["radius"] * one, th["distance"] * one, th["cos_inclination"] * one,
+                     syn.M2_FREQUENCY)
+    sb.phase_shifts[:, 0], sb.phase_shifts[:, 1] = th["p__phase_shift"], th["s__phase_shift"]
+    sb.set_region(0, super_colatitude=th["p__super_colatitude"] * one, super_radius=th["p__super_radius"] * one,
+                  super_temperature=th["p__super_temperature"] * one, omit_radius=th["p__omit_radius"] * one)
+    sb.set_region(1, 2, super_colatitude=th["s__super_colatitude"] * one, super_radius=th["s__super_radius"] * one,
+                  super_temperature=th["s__super_temperature"] * one, cede_colatitude=th["s__cede_colatitude"] * one,
+                  cede_radius=th["s__cede_radius"] * one, cede_azimuth=th["s__cede_azimuth"] * one,
+                  cede_temperature=th["s__cede_temperature"] * one, is_antiphased=True)
+    lnL, status = pipe.eval_spots(sb)
+    e = pipe.fetch_embed(B)
+    for m in range(3):
+        _check_embed(e, 3 + m, lambda k: d["int%d_%s" % (m, k)], "M3 member %d" % m)
+    print("M3 parameter-level lnL", lnL, "ref", float(d["lnL_total"]), "status", status)
+    assert (status == 0).all()
+    assert np.max(np.abs(lnL - float(d["lnL_total"]))) < 1e-4
+    # ---- polar caps ---------------------------------------------------------------------------------------
+    d = np.load(os.path.join(GOLDEN, "m5_polar.npz"))
+    pipe = BatchedLikelihood(member_component=[0, 1], max_rings=64, max_azi=64, n_rays=200,
+                             energies=d["int0_energies"], leaves=d["int0_leaves"], phases=d["int0_phases"],
+                             hot_atm_ext=2, hot_atmosphere=table, image_order_limit=3, response=matrix,
+                             energy_edges=edges, counts=d["counts"], data_phases=np.linspace(0.0, 1.0, 33),
+                             exposure_time=syn.M2_EXPOSURE, max_batch=2)
+    thetas = np.tile(d["theta"], (2, 1))
+    lnL, status = pipe.eval_spots(syn.m2_spot_batch(pipe, thetas))
+    e = pipe.fetch_embed(2)
+    for m in range(2):
+        _check_embed(e, m, lambda k: d["int%d_%s" % (m, k)], "polar member %d" % m)
+    print("polar-cap parameter-level lnL", lnL, "ref", float(d["lnL_total"]), "status", status)
+    assert (status == 0).all()
+    assert np.max(np.abs(lnL - float(d["lnL_total"]))) < 1e-4

@@ -93,6 +93,8 @@ class SpotBatch(C.Structure):
         ("colatitude", c_double_p), ("ang_radius", c_double_p), ("temperature", c_double_p),
         ("phi_shift", c_double_p), ("mode_frequency", C.c_double),
         ("num_cells", C.c_int), ("min_sqrt_num_cells", C.c_int), ("max_sqrt_num_cells", C.c_int),
+        ("hole_radius", c_double_p), ("hole_colatitude", c_double_p), ("hole_azimuth", c_double_p),
+        ("partner", c_int_p), ("is_cede", c_int_p),
     ]
 
 

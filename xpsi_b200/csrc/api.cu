@@ -643,7 +643,8 @@ struct xpsi_b200_pipeline {
   Dev<double> ws_leaf, ws_hdr, ws_slab, ws_mom; Dev<int> ws_ihdr, ws_cnt; Dev<int2> ws_meta;
   int mom_cap = 0;
   // embed inputs / scratch
-  Dev<double> e_Req, e_rs, e_eps, e_zeta, e_colat, e_rad, e_temp, e_phish, e_maxAlpha;
+  Dev<double> e_Req, e_rs, e_eps, e_zeta, e_colat, e_rad, e_temp, e_phish, e_maxAlpha, e_hrad, e_hcolat, e_hazi;
+  Dev<int> e_partner, e_iscede;
   int count_work = 0;
   int embed_status_valid = 0;        // status[] already carries embed failures for this batch
   xb::EmbedArgs embed_args;          // last uploaded spot batch (device pointers), for resident re-runs
@@ -1065,6 +1066,17 @@ int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200
   CK(p->e_Req.upload(h->R_eq, B)); CK(p->e_rs.upload(h->r_s, B)); CK(p->e_eps.upload(h->epsilon, B));
   CK(p->e_zeta.upload(h->zeta, B)); CK(p->e_colat.upload(h->colatitude, Q)); CK(p->e_rad.upload(h->ang_radius, Q));
   CK(p->e_temp.upload(h->temperature, Q)); CK(p->e_phish.upload(h->phi_shift, Q));
+  if (h->hole_radius) {
+    if (!h->hole_colatitude || !h->hole_azimuth) return fail(XPSI_B200_EINVAL, "incomplete hole arrays");
+    CK(p->e_hrad.upload(h->hole_radius, Q)); CK(p->e_hcolat.upload(h->hole_colatitude, Q));
+    CK(p->e_hazi.upload(h->hole_azimuth, Q));
+  }
+  if (h->partner) {
+    if (!h->is_cede) return fail(XPSI_B200_EINVAL, "partner needs is_cede");
+    for (size_t m = 0; m < M; ++m)
+      if (h->partner[m] >= (int)M || h->partner[m] == (int)m) return fail(XPSI_B200_EINVAL, "bad partner index");
+    CK(p->e_partner.upload(h->partner, M)); CK(p->e_iscede.upload(h->is_cede, M));
+  }
   CK(p->e_maxAlpha.alloc((size_t)p->max_batch * M * c.max_rings));
   CK(cudaMemsetAsync(p->status.p, 0, B * sizeof(int), g_stream));
   xb::EmbedArgs a;
@@ -1074,6 +1086,8 @@ int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200
   a.mode_frequency = h->mode_frequency;
   a.R_eq = p->e_Req.p; a.r_s = p->e_rs.p; a.epsilon = p->e_eps.p; a.zeta = p->e_zeta.p;
   a.colatitude = p->e_colat.p; a.ang_radius = p->e_rad.p; a.temperature = p->e_temp.p; a.phi_shift = p->e_phish.p;
+  if (h->hole_radius) { a.hole_radius = p->e_hrad.p; a.hole_colatitude = p->e_hcolat.p; a.hole_azimuth = p->e_hazi.p; }
+  if (h->partner) { a.partner = p->e_partner.p; a.is_cede = p->e_iscede.p; }
   a.n_rings = p->n_rings.p; a.n_azi = p->n_azi.p; a.cellArea = p->cellArea.p; a.phi = p->phi.p; a.theta = p->theta.p;
   a.radial = p->radial.p; a.r_s_over_r = p->rsr.p; a.srcParams = p->params.p; a.cos_gamma = p->cgamma.p;
   a.maxAlpha = p->e_maxAlpha.p; a.deflection = p->defl.p; a.cos_alpha = p->calpha.p; a.lag = p->lag.p;

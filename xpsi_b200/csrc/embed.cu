@@ -142,6 +142,135 @@ __device__ double spot_cell_area(double tha, double thb, double pa, double pb, d
   return tot;
 }
 
+// ---- generic regions: omission hole / superseding mask, ceding partner, polar caps -----------------
+// mesh_tools.pyx:262-271
+__device__ __forceinline__ double eval_phi(double theta, double THETA, double psi) {
+  double c = cos(psi) - cos(THETA) * cos(theta);
+  c /= sin(THETA) * sin(theta);
+  if (!(-1.0 <= c && c <= 1.0)) return -1.0;
+  return acos(c);
+}
+// mesh_tools.pyx:273-301: length of [LB, UB] inside [a, b]
+__device__ __forceinline__ double get_interval(double a, double b, double LB, double UB) {
+  int ac = (LB <= a && a <= UB), bc = (LB <= b && b <= UB);
+  if (ac == 0) ac = 2 * (int)(a > UB);
+  if (bc == 0) bc = 2 * (int)(b > UB);
+  if (ac == bc) return ac == 1 ? b - a : 0.0;
+  if (bc == 1 && ac == 0) return b - LB;
+  if (bc == 2 && ac == 1) return UB - a;
+  if (bc == 2 && ac == 0) return UB - LB;
+  return 0.0;
+}
+struct Region {            // the region being meshed and the region masking it (mesh.pyx naming: "cede" and "super")
+  double colat, radius, hRadius, hAzi, hColat;
+};
+// azimuthal width of the region minus its mask at colatitude theta, restricted to [pa, pb] when cell != 0
+// (cell_integrand mesh_tools.pyx:303-388, spot_integrand :690-771)
+__device__ double region_width(const Region& g, double theta, double pa, double pb, int cell) {
+  if (are_equal(theta, 0.0)) return 0.0;
+  double aLB, aUB, cLB, cUB;
+  aUB = eval_phi(theta, g.colat, g.radius);
+  if (are_equal(aUB, -1.0)) {
+    if (theta + g.colat < g.radius) { aUB = kPi; aLB = -kPi; }
+    else return 0.0;
+  } else aLB = -aUB;
+  if (fabs(theta - g.hColat) > g.hRadius) cLB = cUB = 0.0;
+  else {
+    cUB = eval_phi(theta, g.hColat, g.hRadius);
+    if (are_equal(cUB, -1.0)) return 0.0;
+    cLB = -cUB; cUB += g.hAzi; cLB += g.hAzi;
+    if (cUB > kPi) cUB -= kTwoPi;
+    if (cLB < -kPi) cLB += kTwoPi;
+  }
+  auto iv = [&](double LB, double UB) -> double { return cell ? get_interval(pa, pb, LB, UB) : UB - LB; };
+  if (cUB >= cLB) {
+    if (cLB >= aUB || cUB <= aLB) return iv(aLB, aUB);
+    if (cLB >= aLB && cUB <= aUB) return iv(aLB, cLB) + iv(cUB, aUB);
+    if (cLB < aLB && aLB < cUB && cUB <= aUB) return iv(cUB, aUB);
+    if (aLB <= cLB && cLB < aUB && aUB < cUB) return iv(aLB, cLB);
+    return 0.0;
+  }
+  if (cUB >= aUB || cLB <= aLB) return 0.0;
+  if (cUB >= aLB && cLB <= aUB) return iv(cUB, cLB);
+  if (cUB < aLB && aLB < cLB && cLB <= aUB) return iv(aLB, cLB);
+  if (aLB <= cUB && cUB < aUB && aUB < cLB) return iv(cUB, aUB);
+  return iv(aLB, aUB);
+}
+
+__constant__ double c_k15_x[8] = {0.991455371120812639206854697526329, 0.949107912342758524526189684047851,
+                                  0.864864423359769072789712788640926, 0.741531185599394439863864773280788,
+                                  0.586087235467691130294144838258730, 0.405845151377397166906606412076961,
+                                  0.207784955007898467600689403773245, 0.0};
+__constant__ double c_k15_w[8] = {0.022935322010529224963732008058970, 0.063092092629978553290700663189204,
+                                  0.104790010322250183839876322541518, 0.140653259715525918745189590510238,
+                                  0.169004726639267902826583426598550, 0.190350578064785409913256402421014,
+                                  0.204432940075298892414161999234649, 0.209482141084727828012999174891714};
+__constant__ double c_g7_w[4] = {0.129484966168869693270611432679082, 0.279705391489276667901467771423780,
+                                 0.381830050505118944950369775488975, 0.417959183673469387755102040816327};
+
+// Adaptive Gauss-Kronrod (7,15) by depth-first bisection: the reference integrates the same integrands with
+// CQUAD at epsrel 1e-8 (mesh_tools.pyx:465-473,852-860); kinks and square-root end points are resolved by
+// bisection until the panel's |K15 - G7| is below tol_abs.
+template <class F>
+__device__ double adaptive_gk15(const F& f, double A, double B, double tol_abs) {
+  if (!(B > A)) return 0.0;
+  double sa[44], sb[44];
+  int sd[44];
+  int top = 0;
+  sa[0] = A; sb[0] = B; sd[0] = 0; top = 1;
+  double total = 0.0;
+  while (top > 0) {
+    --top;
+    const double a = sa[top], b = sb[top];
+    const int depth = sd[top];
+    const double h = 0.5 * (b - a), m = 0.5 * (a + b);
+    const double fc = f(m);
+    double K = c_k15_w[7] * fc, G = c_g7_w[3] * fc;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const double dx = h * c_k15_x[k];
+      const double v = f(m - dx) + f(m + dx);
+      K += c_k15_w[k] * v;
+      if (k & 1) G += c_g7_w[k >> 1] * v;
+    }
+    K *= h; G *= h;
+    if (fabs(K - G) <= tol_abs || depth >= 40 || top + 2 > 44) total += K;
+    else {
+      sa[top] = a; sb[top] = m; sd[top] = depth + 1; ++top;
+      sa[top] = m; sb[top] = b; sd[top] = depth + 1; ++top;
+    }
+  }
+  return total;
+}
+
+// area of the region (minus mask) between colatitudes lo and hi / R_eq^2, integrated by one warp:
+// every lane takes a slice of the range (integrateSpot, mesh_tools.pyx:773-860, Lorentz = 0)
+__device__ double warp_region_area(const Region& g, double lo, double hi, double eps, double zeta, int lane) {
+  const double w = (hi - lo) / 32.0;
+  auto f = [&](double th) -> double { return region_width(g, th, 0.0, 0.0, 0) * area_element(th, eps, zeta, 0); };
+  const double part = adaptive_gk15(f, lo + w * lane, (lane == 31) ? hi : lo + w * (lane + 1), 1.0e-12);
+  return warp_sum(part);
+}
+
+// geometry of one member's bounding mesh: polar caps use the whole azimuth and start at the pole
+// (polar_mesh.pyx:53-61, mesh_tools.pyx:925-941)
+struct MeshFrame { double lo, hi, bphi; int polar, invert; };
+__device__ __forceinline__ MeshFrame mesh_frame(Region& g) {
+  MeshFrame m;
+  m.polar = (g.colat - g.radius < 0.0 || g.colat + g.radius > kPi);
+  m.invert = 0;
+  if (m.polar) {
+    m.lo = 0.0;
+    if (g.colat + g.radius > kPi) { m.invert = 1; m.hi = kPi - g.colat + g.radius; g.colat = kPi - g.colat; g.hColat = kPi - g.hColat; }
+    else m.hi = g.colat + g.radius;
+    m.bphi = kPi;
+  } else {
+    m.lo = g.colat - g.radius; m.hi = g.colat + g.radius;
+    m.bphi = asin(sin(g.radius) / sin(g.colat));
+  }
+  return m;
+}
+
 constexpr int kMeshThreads = 256;
 constexpr int kAreaNodes = 1000;          // mesh.pyx:40,88
 
@@ -149,40 +278,83 @@ constexpr int kAreaNodes = 1000;          // mesh.pyx:40,88
 __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
   const int q = blockIdx.x, b = q / a.M, tid = threadIdx.x;
   const double R_eq = a.R_eq[b], eps = a.epsilon[b], zeta = a.zeta[b], r_s = a.r_s[b];
-  const double TH = a.colatitude[q], rho = a.ang_radius[q];
+  const int m_idx = q - b * a.M;
+  Region g;
+  g.colat = a.colatitude[q]; g.radius = a.ang_radius[q];
+  g.hRadius = a.hole_radius ? a.hole_radius[q] : 0.0;
+  g.hColat = a.hole_radius ? a.hole_colatitude[q] : g.colat;
+  g.hAzi = a.hole_radius ? a.hole_azimuth[q] : 0.0;
+  const int partner = a.partner ? a.partner[m_idx] : -1;
   __shared__ double s_area[kAreaNodes], s_colat[kAreaNodes];
   __shared__ double s_par[128], s_theta[128];
   __shared__ double s_boxA, s_spotA;
   __shared__ int s_n;
-  const double lo = TH - rho, hi = TH + rho;
-  if (lo < 0.0 || hi > kPi || !(rho > 0.0)) {        // polar cap: polar_mesh.pyx, not covered
+  if (!(g.radius > 0.0)) {
     if (tid == 0) { a.n_rings[q] = 0; a.n_azi[q] = 0; atomicExch(a.status + b, kUnsupported); }
     return;
   }
-  const double bphi = asin(sin(rho) / sin(TH));                     // mesh.pyx:59
-  // ---- allocate_cells (mesh_tools.pyx:892-1000): bounding-box area vs spot area ------------
+  const MeshFrame fr = mesh_frame(g);              // a southern polar cap is meshed mirrored (g is transformed)
+  const double TH = g.colat, rho = g.radius;
+  const double lo = fr.lo, hi = fr.hi;
+  const bool generic = fr.polar || g.hRadius > 0.0 || partner >= 0;
+  const double bphi = fr.bphi;                                      // mesh.pyx:59 / pi for a polar cap
+  // ---- allocate_cells (mesh_tools.pyx:892-1099): bounding-mesh area vs region area ------------
   if (tid < 32) {
     const double h = 0.5 * (hi - lo), m = 0.5 * (hi + lo);
     double v = c_gl32_w[tid] * area_element(m + h * c_gl32_x[tid], eps, zeta, 0);
     v = warp_sum(v) * h;
-    // spot area: azimuthal width 2a(theta); sqrt substitution at both tangent parallels
-    const double cosT = cos(TH), sinT = sin(TH), cos_rho = cos(rho);
-    const double L = sqrt(m - lo), hh = 0.5 * L;
-    const double t = hh + hh * c_gl32_x[tid];
-    double s = c_gl32_w[tid] * 2.0 * t *
-               (2.0 * spot_halfwidth(lo + t * t, cosT, sinT, cos_rho) * area_element(lo + t * t, eps, zeta, 0) +
-                2.0 * spot_halfwidth(hi - t * t, cosT, sinT, cos_rho) * area_element(hi - t * t, eps, zeta, 0));
-    s = warp_sum(s) * hh;
-    if (tid == 0) {
-      s_boxA = 2.0 * bphi * v;
-      s_spotA = s;
-      double spotA = s;
-      if (are_equal(spotA * R_eq * R_eq, 0.0)) spotA = s_boxA / 1000.0;
-      double sq = ceil(sqrt((double)a.num_cells * s_boxA / spotA));
-      if (sq < a.min_sqrt) sq = a.min_sqrt; else if (sq > a.max_sqrt) sq = a.max_sqrt;
-      int n = (int)sq;
-      if (n % 2 != 0) n += 1;
-      s_n = n;
+    if (!generic) {
+      // spot area: azimuthal width 2a(theta); sqrt substitution at both tangent parallels
+      const double cosT = cos(TH), sinT = sin(TH), cos_rho = cos(rho);
+      const double L = sqrt(m - lo), hh = 0.5 * L;
+      const double t = hh + hh * c_gl32_x[tid];
+      double s = c_gl32_w[tid] * 2.0 * t *
+                 (2.0 * spot_halfwidth(lo + t * t, cosT, sinT, cos_rho) * area_element(lo + t * t, eps, zeta, 0) +
+                  2.0 * spot_halfwidth(hi - t * t, cosT, sinT, cos_rho) * area_element(hi - t * t, eps, zeta, 0));
+      s = warp_sum(s) * hh;
+      if (tid == 0) {
+        s_boxA = 2.0 * bphi * v;
+        s_spotA = s;
+        double spotA = s;
+        if (are_equal(spotA * R_eq * R_eq, 0.0)) spotA = s_boxA / 1000.0;
+        double sq = ceil(sqrt((double)a.num_cells * s_boxA / spotA));
+        if (sq < a.min_sqrt) sq = a.min_sqrt; else if (sq > a.max_sqrt) sq = a.max_sqrt;
+        int n = (int)sq;
+        if (n % 2 != 0) n += 1;
+        s_n = n;
+      }
+    } else {
+      const double boxA = 2.0 * bphi * v;
+      double ownA = warp_region_area(g, lo, hi, eps, zeta, tid);
+      if (are_equal(ownA * R_eq * R_eq, 0.0)) ownA = boxA / 1000.0;
+      double numCell = (double)a.num_cells;
+      if (partner >= 0) {            // superseding + ceding members share num_cells (:1040-1060)
+        const int qp = b * a.M + partner;
+        Region gp;
+        gp.colat = a.colatitude[qp]; gp.radius = a.ang_radius[qp];
+        gp.hRadius = a.hole_radius ? a.hole_radius[qp] : 0.0;
+        gp.hColat = a.hole_radius ? a.hole_colatitude[qp] : gp.colat;
+        gp.hAzi = a.hole_radius ? a.hole_azimuth[qp] : 0.0;
+        const MeshFrame fp = mesh_frame(gp);
+        const double hp = 0.5 * (fp.hi - fp.lo), mp = 0.5 * (fp.hi + fp.lo);
+        double vp = c_gl32_w[tid] * area_element(mp + hp * c_gl32_x[tid], eps, zeta, 0);
+        vp = warp_sum(vp) * hp;
+        double partA = warp_region_area(gp, fp.lo, fp.hi, eps, zeta, tid);
+        if (are_equal(partA * R_eq * R_eq, 0.0)) partA = 2.0 * fp.bphi * vp / 1000.0;
+        const int cede = a.is_cede[m_idx];
+        const double superA = cede ? partA : ownA, cedeA = cede ? ownA : partA;
+        const double y = cedeA / superA - 1.0;
+        const double superN = are_equal(y, 0.0) ? 0.5 * numCell : numCell * ((sqrt(1.0 + y) - 1.0) / y);
+        numCell = cede ? (are_equal(y, 0.0) ? 0.5 * numCell : numCell - superN) : superN;
+      }
+      if (tid == 0) {
+        s_boxA = boxA; s_spotA = ownA;
+        double sq = ceil(sqrt(numCell * boxA / ownA));
+        if (sq < a.min_sqrt) sq = a.min_sqrt; else if (sq > a.max_sqrt) sq = a.max_sqrt;
+        int n = (int)sq;
+        if (n % 2 != 0) n += 1;
+        s_n = n;
+      }
     }
   }
   __syncthreads();
@@ -224,7 +396,7 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
     const double rn = radius_normalised(mu, eps, zeta);
     const double f = f_theta(mu, rn, eps, zeta);
     const double cg = 1.0 / sqrt(1.0 + f * f);
-    a.theta[ring0 + i] = th;
+    a.theta[ring0 + i] = fr.invert ? kPi - th : th;                   // polar_mesh.pyx:419-422
     a.radial[ring0 + i] = rn * R_eq;
     a.r_s_over_r[ring0 + i] = r_s / (rn * R_eq);                   // HotRegion.py:913
     a.cos_gamma[ring0 + i] = cg;
@@ -241,6 +413,64 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
   // ---- cells (mesh.pyx:255-352 with superRadius = 0; mirror symmetry in azimuth) -----------------
   const double phi_shift = a.phi_shift[q];
   const int half = n / 2;
+  if (generic) {
+    // mask boundary points tangent to iso-coordinate curves (mesh.pyx:130-185, polar_mesh.pyx:129-178)
+    double sp[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    if (g.hRadius > 0.0) {
+      if (g.hColat - g.hRadius < 0.0) {
+        sp[0][0] = g.hRadius - g.hColat; sp[0][1] = g.hAzi + kPi;
+        if (sp[0][1] > kPi) sp[0][1] -= kTwoPi;
+        sp[1][0] = g.hColat + g.hRadius; sp[1][1] = g.hAzi;
+      } else if (g.hColat + g.hRadius > kPi) {
+        sp[0][0] = g.hColat - g.hRadius; sp[0][1] = g.hAzi;
+        sp[1][0] = kTwoPi - g.hColat - g.hRadius; sp[1][1] = g.hAzi + kPi;
+        if (sp[1][1] > kPi) sp[1][1] -= kTwoPi;
+      } else {
+        sp[0][0] = g.hColat - g.hRadius; sp[0][1] = g.hAzi;
+        sp[1][0] = acos(cos(g.hColat) / cos(g.hRadius));
+        sp[1][1] = g.hAzi + asin(sin(g.hRadius) / sin(g.hColat));
+        if (sp[1][1] > kPi) sp[1][1] -= kTwoPi;
+        sp[2][0] = g.hColat + g.hRadius; sp[2][1] = g.hAzi;
+        sp[3][0] = sp[1][0];
+        sp[3][1] = g.hAzi - asin(sin(g.hRadius) / sin(g.hColat));
+        if (sp[3][1] < -kPi) sp[3][1] += kTwoPi;
+      }
+    }
+    const bool mirror = are_equal(g.hColat, g.colat) && are_equal(g.hAzi, 0.0);     // mesh.pyx:187-191
+    const int j_max = mirror ? half : n;
+    for (int t = tid; t < n * j_max; t += kMeshThreads) {
+      const int i = t / j_max, j = t - i * j_max;
+      const double l = (i == 0) ? lo : s_par[i - 1];
+      const double u = (i == n - 1) ? hi : s_par[i];
+      double lft = -bphi;
+      for (int k = 0; k < j; ++k) lft += dphi;           // the reference accumulates leftmost += delta_phi
+      const double right = lft + dphi;
+      const double thc = s_theta[i], pc = lft + 0.5 * dphi;
+      int p1, p2, p3, p4, p5;
+      auto inside = [&](double th, double ph) -> int {
+        if (!(eval_psi(th, ph, g.colat) <= g.radius)) return 2;
+        return (g.hRadius <= eval_psi(th, ph - g.hAzi, g.hColat)) ? 1 : 0;
+      };
+      if (fr.polar && i == 0) {                           // polar_mesh.pyx:222-229: both upper corners are the pole
+        p1 = (g.colat <= g.radius) ? ((g.hRadius <= g.hColat) ? 1 : 0) : 2;
+        p3 = p1;
+      } else { p1 = inside(l, lft); p3 = inside(l, right); }
+      p2 = inside(u, lft); p4 = inside(u, right); p5 = inside(thc, pc);
+      bool integrate = !(p1 == p2 && p2 == p3 && p3 == p4 && p4 == p5);
+      if (!integrate && g.hRadius > 0.0)
+        for (int k = 0; k < 4; ++k)
+          if (l <= sp[k][0] && sp[k][0] <= u && lft <= sp[k][1] && sp[k][1] <= right) integrate = true;
+      double area = 0.0;
+      if (integrate) {
+        auto f = [&](double th) -> double { return region_width(g, th, lft, right, 1) * area_element(th, eps, zeta, 0); };
+        area = adaptive_gk15(f, l, u, 1.0e-11 * cellA);    // integrateCell, mesh_tools.pyx:429-473
+      } else if (p5 == 1) area = cellA;
+      area *= R_eq * R_eq;
+      const long row = (ring0 + i) * a.max_azi;
+      a.cellArea[row + j] = area;
+      if (mirror) a.cellArea[row + n - 1 - j] = area;
+    }
+  } else
   for (int t = tid; t < n * half; t += kMeshThreads) {
     const int i = t / half, j = t - i * half;
     const double l = (i == 0) ? lo : s_par[i - 1];

@@ -98,6 +98,11 @@ struct EmbedArgs {
   const double* R_eq; const double* r_s; const double* epsilon; const double* zeta;      // [B] Spacetime.py:110-188
   const double* colatitude; const double* ang_radius; const double* temperature;        // [B*M]
   const double* phi_shift;                        // [B*M] added to cell azimuths (pi if antiphased)
+  // optional (nullptr: plain circular spots): the region masking each member -- the omission hole of a
+  // superseding member, or the superseding region inside a ceding member (HotRegion.py:819-865) -- and the
+  // pairing of superseding / ceding members that share num_cells (mesh_tools.pyx:1040-1060)
+  const double* hole_radius; const double* hole_colatitude; const double* hole_azimuth;   // [B*M]
+  const int* partner; const int* is_cede;         // [M]: partner member index or -1; 1 = ceding member
   const double* else_temperature;                 // nullptr, or [B]: log10 T of Elsewhere (for corrParams)
   double* corrParams;                             // nullptr, or [B*M][max_rings][2]: correction parameter rows
   // outputs: the integrator's per-instance inputs (padded layout of AzinvArgs)

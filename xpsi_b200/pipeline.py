@@ -109,6 +109,39 @@ class SpotBatch:
         self.colatitude, self.ang_radius, self.temperature, self.phi_shift = z(B, M), z(B, M), z(B, M), z(B, M)
         self.mode_frequency = float(mode_frequency)
         self.num_cells, self.min_sqrt, self.max_sqrt = int(num_cells), int(min_sqrt_num_cells), int(max_sqrt_num_cells)
+        # optional: masking region of each member and superseding / ceding pairing (see set_region)
+        self.hole_radius = self.hole_colatitude = self.hole_azimuth = None
+        self.partner = self.is_cede = None
+
+    def set_region(self, super_member, cede_member=None, *, super_colatitude, super_radius, super_temperature,
+                   omit_colatitude=None, omit_radius=None, omit_azimuth=None, cede_colatitude=None,
+                   cede_radius=None, cede_azimuth=None, cede_temperature=None, is_antiphased=False):
+        """Fill the members of one hot region from ``xpsi.HotRegion`` parameter values (arrays over the batch),
+        the way ``HotRegion.embed`` hands them to the mesh routines (xpsi/HotRegion.py:819-865): the superseding
+        member is masked by the omission region, the ceding member by the superseding region."""
+        if self.hole_radius is None:
+            z = lambda: np.zeros((self.B, self.M), dtype=np.float64)
+            self.hole_radius, self.hole_colatitude, self.hole_azimuth = z(), z(), z()
+            self.hole_colatitude[:] = self.colatitude
+        pi_shift = np.pi if is_antiphased else 0.0
+        m = super_member
+        self.colatitude[:, m], self.ang_radius[:, m], self.temperature[:, m] = super_colatitude, super_radius, super_temperature
+        self.hole_radius[:, m] = 0.0 if omit_radius is None else omit_radius
+        self.hole_colatitude[:, m] = super_colatitude if omit_colatitude is None else omit_colatitude
+        self.hole_azimuth[:, m] = 0.0 if omit_azimuth is None else omit_azimuth
+        self.phi_shift[:, m] = -self.hole_azimuth[:, m] + pi_shift            # HotRegion.py:834-837
+        if cede_member is not None:
+            if self.partner is None:
+                self.partner = -np.ones(self.M, dtype=np.int32)
+                self.is_cede = np.zeros(self.M, dtype=np.int32)
+            c = cede_member
+            self.partner[m], self.partner[c], self.is_cede[c] = c, m, 1
+            self.colatitude[:, c], self.ang_radius[:, c], self.temperature[:, c] = cede_colatitude, cede_radius, cede_temperature
+            azi = np.zeros(self.B) if cede_azimuth is None else np.asarray(cede_azimuth, dtype=np.float64)
+            self.hole_radius[:, c], self.hole_colatitude[:, c] = super_radius, super_colatitude
+            self.hole_azimuth[:, c] = -azi                                     # HotRegion.py:865
+            self.phi_shift[:, c] = azi + pi_shift                              # HotRegion.py:867-870
+            self.hole_radius[:, m] = 0.0        # "omit=True and cede=True ignores the omission" (HotRegion.py:44)
 
     def set_spacetime(self, mass, radius, distance, cos_inclination, frequency):
         """Vectorised ``xpsi.Spacetime`` derived quantities (xpsi/Spacetime.py:110-188)."""
@@ -135,6 +168,11 @@ class SpotBatch:
             setattr(s, f, _lib.dptr(a))
         s.mode_frequency = self.mode_frequency
         s.num_cells, s.min_sqrt_num_cells, s.max_sqrt_num_cells = self.num_cells, self.min_sqrt, self.max_sqrt
+        if self.hole_radius is not None:
+            for f in ("hole_radius", "hole_colatitude", "hole_azimuth"):
+                setattr(s, f, _lib.dptr(getattr(self, f)))
+        if self.partner is not None:
+            s.partner, s.is_cede = _lib.iptr(self.partner), _lib.iptr(self.is_cede)
         return s
 
 
