@@ -252,6 +252,56 @@ __device__ double warp_region_area(const Region& g, double lo, double hi, double
   return warp_sum(part);
 }
 
+// colatitudes at which the small circle (centre colatitude TH at azimuth 0, angular radius rho) crosses the
+// meridian at azimuth ph, appended to bp when inside (lo, hi)
+__device__ __forceinline__ void circle_meridian_crossings(double TH, double rho, double ph, double lo, double hi,
+                                                          double* bp, int* nb) {
+  const double A = cos(TH), B = sin(TH) * cos(ph), Rn = sqrt(A * A + B * B), cr = cos(rho);
+  if (fabs(cr) <= Rn && Rn > 0.0) {
+    const double base = atan2(B, A), d = acos(cr / Rn);
+    for (int s = -1; s <= 1; s += 2) {
+      double t = base + s * d;
+      if (t < 0.0) t = -t;                       // the same great circle continued through the pole
+      if (t > kPi) t = kTwoPi - t;
+      if (t > lo && t < hi) bp[(*nb)++] = t;
+    }
+  }
+}
+
+// integrateCell (mesh_tools.pyx:429-473) for a region with a mask: the colatitude range is first split where
+// either boundary circle crosses the cell's meridians or touches a parallel, so every piece is either empty
+// or smooth up to square-root end points (no sliver can fall between quadrature nodes); the pieces are then
+// integrated adaptively (the two circles' mutual intersections are left to the bisection).
+__device__ double region_cell_area(const Region& g, double l, double u, double pa, double pb, double eps,
+                                   double zeta, double tol_abs) {
+  double bp[24];
+  int nb = 0;
+  bp[nb++] = l; bp[nb++] = u;
+  circle_meridian_crossings(g.colat, g.radius, pa, l, u, bp, &nb);
+  circle_meridian_crossings(g.colat, g.radius, pb, l, u, bp, &nb);
+  const double t0 = fabs(g.colat - g.radius), t1 = g.colat + g.radius;
+  if (t0 > l && t0 < u) bp[nb++] = t0;
+  if (t1 > l && t1 < u) bp[nb++] = t1;
+  if (g.hRadius > 0.0) {
+    circle_meridian_crossings(g.hColat, g.hRadius, pa - g.hAzi, l, u, bp, &nb);
+    circle_meridian_crossings(g.hColat, g.hRadius, pb - g.hAzi, l, u, bp, &nb);
+    const double h0 = fabs(g.hColat - g.hRadius), h1 = g.hColat + g.hRadius;
+    if (h0 > l && h0 < u) bp[nb++] = h0;
+    if (h1 > l && h1 < u) bp[nb++] = h1;
+  }
+  for (int i = 1; i < nb; ++i) {         // insertion sort
+    const double v = bp[i];
+    int j = i - 1;
+    while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; --j; }
+    bp[j + 1] = v;
+  }
+  auto f = [&](double th) -> double { return region_width(g, th, pa, pb, 1) * area_element(th, eps, zeta, 0); };
+  double tot = 0.0;
+  for (int i = 0; i + 1 < nb; ++i)
+    if (bp[i + 1] - bp[i] > 1.0e-15) tot += adaptive_gk15(f, bp[i], bp[i + 1], tol_abs);
+  return tot;
+}
+
 // geometry of one member's bounding mesh: polar caps use the whole azimuth and start at the pole
 // (polar_mesh.pyx:53-61, mesh_tools.pyx:925-941)
 struct MeshFrame { double lo, hi, bphi; int polar, invert; };
@@ -461,10 +511,8 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
         for (int k = 0; k < 4; ++k)
           if (l <= sp[k][0] && sp[k][0] <= u && lft <= sp[k][1] && sp[k][1] <= right) integrate = true;
       double area = 0.0;
-      if (integrate) {
-        auto f = [&](double th) -> double { return region_width(g, th, lft, right, 1) * area_element(th, eps, zeta, 0); };
-        area = adaptive_gk15(f, l, u, 1.0e-11 * cellA);    // integrateCell, mesh_tools.pyx:429-473
-      } else if (p5 == 1) area = cellA;
+      if (integrate) area = region_cell_area(g, l, u, lft, right, eps, zeta, 1.0e-12 * cellA);
+      else if (p5 == 1) area = cellA;
       area *= R_eq * R_eq;
       const long row = (ring0 + i) * a.max_azi;
       a.cellArea[row + j] = area;
