@@ -62,7 +62,7 @@ def theta_block(first, count):
 def make_pipeline(w, max_batch):
     from xpsi_b200.pipeline import BatchedLikelihood
     m2 = w["m2"]
-    pad = 44                     # ST-U spots at 32^2 cells allocate 36-42 rings over the prior
+    pad = 64                     # max_sqrt_num_cells: ST-U spots allocate 36-42 rings, polar caps up to 64
     return BatchedLikelihood(member_component=[0, 1], max_rings=pad, max_azi=pad, n_rays=200,
                              energies=m2["t0_int0_energies"], leaves=m2["t0_int0_leaves"],
                              phases=m2["t0_int0_phases"], hot_atm_ext=2, hot_atmosphere=w["table"],

@@ -243,12 +243,51 @@ __device__ double adaptive_gk15(const F& f, double A, double B, double tol_abs) 
   return total;
 }
 
-// area of the region (minus mask) between colatitudes lo and hi / R_eq^2, integrated by one warp:
-// every lane takes a slice of the range (integrateSpot, mesh_tools.pyx:773-860, Lorentz = 0)
+// area of the region (minus mask) between colatitudes lo and hi / R_eq^2, integrated by one warp
+// (integrateSpot, mesh_tools.pyx:773-860, Lorentz = 0; it only feeds the cell allocation).  The range is split
+// at the parallels tangent to either boundary circle, where the width behaves like a square root and a
+// theta = s + t^2 substitution makes the integrand smooth; every lane then takes a slice of each piece.
 __device__ double warp_region_area(const Region& g, double lo, double hi, double eps, double zeta, int lane) {
-  const double w = (hi - lo) / 32.0;
+  double bp[6];
+  int nb = 0;
+  bp[nb++] = lo; bp[nb++] = hi;
+  double tg[4];
+  int nt = 0;
+  tg[nt++] = fabs(g.colat - g.radius); tg[nt++] = g.colat + g.radius;
+  if (g.hRadius > 0.0) { tg[nt++] = fabs(g.hColat - g.hRadius); tg[nt++] = g.hColat + g.hRadius; }
+  for (int k = 0; k < nt; ++k) if (tg[k] > lo && tg[k] < hi) bp[nb++] = tg[k];
+  for (int i = 1; i < nb; ++i) {
+    const double v = bp[i];
+    int j = i - 1;
+    while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; --j; }
+    bp[j + 1] = v;
+  }
   auto f = [&](double th) -> double { return region_width(g, th, 0.0, 0.0, 0) * area_element(th, eps, zeta, 0); };
-  const double part = adaptive_gk15(f, lo + w * lane, (lane == 31) ? hi : lo + w * (lane + 1), 1.0e-12);
+  auto is_tangent = [&](double x) -> bool {
+    for (int k = 0; k < nt; ++k) if (fabs(x - tg[k]) < 1.0e-14) return true;
+    return false;
+  };
+  const double tol = 1.0e-11;
+  double part = 0.0;
+  for (int i = 0; i + 1 < nb; ++i) {
+    const double s0 = bp[i], s1 = bp[i + 1];
+    if (!(s1 - s0 > 1.0e-15)) continue;
+    const bool sing0 = is_tangent(s0), sing1 = is_tangent(s1);
+    if (!sing0 && !sing1) {
+      const double w = (s1 - s0) / 32.0;
+      part += adaptive_gk15(f, s0 + w * lane, s0 + w * (lane + 1), tol);
+      continue;
+    }
+    const double mid = (sing0 && sing1) ? 0.5 * (s0 + s1) : (sing0 ? s1 : s0);
+    if (sing0) {
+      const double w = sqrt(mid - s0) / 32.0;
+      part += adaptive_gk15([&](double t) -> double { return f(s0 + t * t) * 2.0 * t; }, w * lane, w * (lane + 1), tol);
+    }
+    if (sing1) {
+      const double w = sqrt(s1 - mid) / 32.0;
+      part += adaptive_gk15([&](double t) -> double { return f(s1 - t * t) * 2.0 * t; }, w * lane, w * (lane + 1), tol);
+    }
+  }
   return warp_sum(part);
 }
 
@@ -279,16 +318,16 @@ __device__ double region_cell_area(const Region& g, double l, double u, double p
   bp[nb++] = l; bp[nb++] = u;
   circle_meridian_crossings(g.colat, g.radius, pa, l, u, bp, &nb);
   circle_meridian_crossings(g.colat, g.radius, pb, l, u, bp, &nb);
-  const double t0 = fabs(g.colat - g.radius), t1 = g.colat + g.radius;
-  if (t0 > l && t0 < u) bp[nb++] = t0;
-  if (t1 > l && t1 < u) bp[nb++] = t1;
+  // parallels tangent to a boundary circle: the azimuthal width behaves like a square root there
+  double tg[4];
+  int nt = 0;
+  tg[nt++] = fabs(g.colat - g.radius); tg[nt++] = g.colat + g.radius;
   if (g.hRadius > 0.0) {
     circle_meridian_crossings(g.hColat, g.hRadius, pa - g.hAzi, l, u, bp, &nb);
     circle_meridian_crossings(g.hColat, g.hRadius, pb - g.hAzi, l, u, bp, &nb);
-    const double h0 = fabs(g.hColat - g.hRadius), h1 = g.hColat + g.hRadius;
-    if (h0 > l && h0 < u) bp[nb++] = h0;
-    if (h1 > l && h1 < u) bp[nb++] = h1;
+    tg[nt++] = fabs(g.hColat - g.hRadius); tg[nt++] = g.hColat + g.hRadius;
   }
+  for (int k = 0; k < nt; ++k) if (tg[k] > l && tg[k] < u) bp[nb++] = tg[k];
   for (int i = 1; i < nb; ++i) {         // insertion sort
     const double v = bp[i];
     int j = i - 1;
@@ -296,9 +335,21 @@ __device__ double region_cell_area(const Region& g, double l, double u, double p
     bp[j + 1] = v;
   }
   auto f = [&](double th) -> double { return region_width(g, th, pa, pb, 1) * area_element(th, eps, zeta, 0); };
+  auto is_tangent = [&](double x) -> bool {
+    for (int k = 0; k < nt; ++k) if (fabs(x - tg[k]) < 1.0e-14) return true;
+    return false;
+  };
   double tot = 0.0;
-  for (int i = 0; i + 1 < nb; ++i)
-    if (bp[i + 1] - bp[i] > 1.0e-15) tot += adaptive_gk15(f, bp[i], bp[i + 1], tol_abs);
+  for (int i = 0; i + 1 < nb; ++i) {
+    const double s0 = bp[i], s1 = bp[i + 1];
+    if (!(s1 - s0 > 1.0e-15)) continue;
+    const bool sing0 = is_tangent(s0), sing1 = is_tangent(s1);
+    if (!sing0 && !sing1) { tot += adaptive_gk15(f, s0, s1, tol_abs); continue; }
+    // theta = s0 + t^2 (or s1 - t^2) turns the square-root end point into a smooth integrand
+    const double mid = (sing0 && sing1) ? 0.5 * (s0 + s1) : (sing0 ? s1 : s0);
+    if (sing0) tot += adaptive_gk15([&](double t) -> double { return f(s0 + t * t) * 2.0 * t; }, 0.0, sqrt(mid - s0), tol_abs);
+    if (sing1) tot += adaptive_gk15([&](double t) -> double { return f(s1 - t * t) * 2.0 * t; }, 0.0, sqrt(s1 - mid), tol_abs);
+  }
   return tot;
 }
 
@@ -511,7 +562,7 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
         for (int k = 0; k < 4; ++k)
           if (l <= sp[k][0] && sp[k][0] <= u && lft <= sp[k][1] && sp[k][1] <= right) integrate = true;
       double area = 0.0;
-      if (integrate) area = region_cell_area(g, l, u, lft, right, eps, zeta, 1.0e-12 * cellA);
+      if (integrate) area = region_cell_area(g, l, u, lft, right, eps, zeta, 1.0e-11 * cellA);
       else if (p5 == 1) area = cellA;
       area *= R_eq * R_eq;
       const long row = (ring0 + i) * a.max_azi;

@@ -157,8 +157,8 @@ M2_BACKGROUND_RATE = 1.0e-3   # counts/s/channel, flat
 
 
 def m2_theta_batch(n, seed=20261017):
-    """``n`` ST-U parameter vectors, uniform in ``M2_BOUNDS`` (in-table
-    temperatures; non-overlapping, non-polar spots so the spot mesh applies)."""
+    """``n`` ST-U parameter vectors, uniform in ``M2_BOUNDS`` (in-table temperatures; the two spots cannot
+    overlap inside the box; spots covering a pole are kept -- the embed meshes them as polar caps)."""
     rng = np.random.default_rng(seed)
     out = np.empty((n, len(M2_NAMES)))
     k = 0
@@ -167,9 +167,6 @@ def m2_theta_batch(n, seed=20261017):
         th = M2_BOUNDS[:, 0] + u * (M2_BOUNDS[:, 1] - M2_BOUNDS[:, 0])
         # compactness: R >= 3 r_g  (TestRun_Num.py CustomPrior)
         if th[1] * KM < 3.0 * th[0] * GM_SUN:
-            continue
-        # neither spot may cover a pole (those use the polar mesh, polar_mesh.pyx)
-        if th[5] - th[6] < 0.02 or th[9] + th[10] > math.pi - 0.02:
             continue
         out[k] = th
         k += 1
