@@ -419,6 +419,27 @@ __device__ __forceinline__ void row_range(const P& axis, int nE, double vlo, dou
 }
 
 constexpr int kSlabThreads = 256;
+constexpr int kGSpan = 8;         // log g nodes the rings of one member may touch in the shared contraction
+
+// All lit rings of member q share log T and their log g stencils fit in kGSpan nodes?  Then the table is
+// contracted over T once per member (k_azinv_slab_member) instead of once per ring.  Block-uniform result.
+__device__ __forceinline__ bool member_uniform(const AzinvArgs& a, int q, int which, int tid, int nthreads) {
+  const int ho = which ? kCorrD : 0;
+  const long ring0 = (long)q * a.n_rings;
+  int first = -1;
+  for (int r = 0; r < a.n_rings; ++r) if (a.ws_ihdr[(ring0 + r) * kIHdr] != 0) { first = r; break; }
+  if (first < 0) return false;
+  const double T0 = a.ws_hdr[(ring0 + first) * kDHdr + ho + 10];
+  const int g0 = a.ws_ihdr[(ring0 + first) * kIHdr + (which ? 7 : 3)];
+  int ok = 1;
+  for (int r = tid; r < a.n_rings; r += nthreads) {
+    if (a.ws_ihdr[(ring0 + r) * kIHdr] == 0) continue;
+    if (a.ws_hdr[(ring0 + r) * kDHdr + ho + 10] != T0) ok = 0;
+    const int g = a.ws_ihdr[(ring0 + r) * kIHdr + (which ? 7 : 3)];
+    if (g - g0 > (kGSpan - 4) / 2 || g0 - g > (kGSpan - 4) / 2) ok = 0;      // => max - min + 4 <= kGSpan
+  }
+  return __syncthreads_and(ok) != 0;
+}
 
 // which = 0: hot atmosphere at the ring's parameters; 1: elsewhere atmosphere at the
 // ring's correction parameters (pyx:469-476)
@@ -458,6 +479,7 @@ __global__ void __launch_bounds__(kSlabThreads) k_azinv_slab(AzinvArgs a, int wh
   __syncthreads();
   const int elo = s_elo, nrows = s_nrows, nmu = T.nmu;
   if (nrows == 0) return;
+  if (member_uniform(a, q, which, tid, kSlabThreads)) return;   // k_azinv_slab_member contracts for all rings at once
   const int bT = ih[which ? 6 : 2], bG = ih[which ? 7 : 3];
   const long S0 = (long)T.ng * nmu * T.nE, S1 = (long)nmu * T.nE, S2 = T.nE;
   double* out = (which ? a.ws_slab2 : a.ws_slab) + ring * (long)nmu * a.slab_rows_ring;
@@ -474,6 +496,72 @@ __global__ void __launch_bounds__(kSlabThreads) k_azinv_slab(AzinvArgs a, int wh
       acc += s_wT[x] * inner;
     }
     out[(long)m * a.slab_rows_ring + e] = acc;
+  }
+}
+
+// One CTA per (mu row, member): V[g'] = sum_x wT[x] buf[bT+x][g'][mu][e] for the few log g nodes the member's
+// rings touch (4 loads each), then every ring's slab row is sum_y wG_ring[y] V[bG_ring + y] -- the table is
+// read once per member instead of once per ring (the rings differ only in log g and in the rows they reach).
+constexpr int kSlabMThreads = 192;
+
+__global__ void __launch_bounds__(kSlabMThreads) k_azinv_slab_member(AzinvArgs a, int which) {
+  const int m = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
+  const AtmTable& T = which ? a.els : a.hot;
+  const int ho = which ? kCorrD : 0;
+  const long ring0 = (long)q * a.n_rings;
+  extern __shared__ double smem[];
+  double* s_V = smem;                                          // [kGSpan][kSlabMThreads]
+  double* s_wG = s_V + kGSpan * kSlabMThreads;                 // [n_rings][4]
+  int* s_row = reinterpret_cast<int*>(s_wG + 4 * a.n_rings);   // [n_rings][3]: first row, rows, g offset
+  __shared__ int s_gmin, s_first;
+  if (!member_uniform(a, q, which, tid, kSlabMThreads)) return;
+  if (tid == 0) { s_gmin = 1 << 30; s_first = -1; }
+  __syncthreads();
+  for (int r = tid; r < a.n_rings; r += kSlabMThreads) {
+    const int* ih = a.ws_ihdr + (ring0 + r) * kIHdr;
+    const int lit = ih[0] != 0 && ih[which ? 9 : 5] > 0;
+    s_row[3 * r] = ih[which ? 8 : 4]; s_row[3 * r + 1] = lit ? ih[which ? 9 : 5] : 0;
+    if (lit) { atomicMin(&s_gmin, ih[which ? 7 : 3]); atomicMax(&s_first, r); }
+    const double* dh = a.ws_hdr + (ring0 + r) * kDHdr;
+    for (int y = 0; y < 4; ++y) s_wG[4 * r + y] = dh[ho + 6 + y];
+  }
+  __syncthreads();
+  if (s_first < 0) return;
+  const int gmin = s_gmin;
+  int gmax = gmin;
+  for (int r = 0; r < a.n_rings; ++r) {
+    if (s_row[3 * r + 1] == 0) continue;
+    const int g = a.ws_ihdr[(ring0 + r) * kIHdr + (which ? 7 : 3)];
+    if (tid == 0) s_row[3 * r + 2] = g - gmin;
+    gmax = max(gmax, g);
+  }
+  const int span = gmax - gmin + 4;                            // <= kGSpan by member_uniform
+  const int bT = a.ws_ihdr[(ring0 + s_first) * kIHdr + (which ? 6 : 2)];
+  const double* dh0 = a.ws_hdr + (ring0 + s_first) * kDHdr;
+  const double wT0 = dh0[ho + 2], wT1 = dh0[ho + 3], wT2 = dh0[ho + 4], wT3 = dh0[ho + 5];
+  const long S0 = (long)T.ng * T.nmu * T.nE, S1 = (long)T.nmu * T.nE, S2 = T.nE;
+  const int rows_stride = a.slab_rows_ring;
+  double* out_base = (which ? a.ws_slab2 : a.ws_slab) + ring0 * (long)T.nmu * rows_stride + (long)m * rows_stride;
+  __syncthreads();
+  for (int e0 = 0; e0 < T.nE; e0 += kSlabMThreads) {
+    const int e = e0 + tid;
+    if (e < T.nE) {
+      const double* base = T.buf + (long)bT * S0 + (long)gmin * S1 + (long)m * S2 + e;
+      for (int k = 0; k < span; ++k) {
+        const double* b = base + k * S1;
+        s_V[k * kSlabMThreads + tid] = wT0 * __ldg(b) + wT1 * __ldg(b + S0) + wT2 * __ldg(b + 2 * S0) + wT3 * __ldg(b + 3 * S0);
+      }
+      for (int r = 0; r < a.n_rings; ++r) {
+        const int nrows = s_row[3 * r + 1];
+        const int rel = e - s_row[3 * r];
+        if (nrows == 0 || rel < 0 || rel >= nrows) continue;
+        const double* V = s_V + s_row[3 * r + 2] * kSlabMThreads + tid;
+        const double* w = s_wG + 4 * r;
+        // same association as k_azinv_slab: sum_x wT[x] (sum_y wG[y] tab) == sum_y wG[y] (sum_x wT[x] tab) up to rounding
+        out_base[(long)r * T.nmu * rows_stride + rel] =
+            w[0] * V[0] + w[1] * V[kSlabMThreads] + w[2] * V[2 * kSlabMThreads] + w[3] * V[3 * kSlabMThreads];
+      }
+    }
   }
 }
 
@@ -1051,8 +1139,15 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   cudaError_t err;
   a.general = 0;
   if ((err = launch_azinv_geometry(a, stream)) != cudaSuccess) return err;
-  if (atm == 2) k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 0);
-  if (corr == 2) k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 1);
+  const size_t msm = ((size_t)kGSpan * kSlabMThreads + 4ul * a.n_rings) * sizeof(double) + 3ul * a.n_rings * sizeof(int);
+  if (atm == 2) {
+    k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 0);
+    k_azinv_slab_member<<<dim3(a.hot.nmu, a.Q), kSlabMThreads, msm, stream>>>(a, 0);
+  }
+  if (corr == 2) {
+    k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 1);
+    k_azinv_slab_member<<<dim3(a.els.nmu, a.Q), kSlabMThreads, msm, stream>>>(a, 1);
+  }
   if (a.ws_mom) {
     if (!a.ws_meta || !a.ws_cnt || a.mom_cap < 1 || a.n_azi > 0xffff) return cudaErrorInvalidValue;
     const size_t msm = (2ul * a.n_azi + a.n_leaves) * sizeof(double);
