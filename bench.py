@@ -335,19 +335,19 @@ def main_ours(args):
         "config": {"workload": "M2 ST-U NSX-shaped Num4D (35,14,67,166), 2 hot regions, 128 energies, "
                                "100 leaves/phases, 200 rays, 270x1500 response, 32 phase bins",
                    "batch_per_gpu": B,
-                   "theta": "distinct ST-U parameter vectors from the closed-form prior (seed 20261017); "
-                            "mesh + rays embedded on the GPU inside the timed region",
+                   "theta": "distinct ST-U parameter vectors from the closed-form prior (seed 20261017, polar caps "
+                            "included); mesh + rays embedded on the GPU inside the timed region",
                    "parallelism": "theta-sharded x%d, no data-path collective" % world,
                    "l2": "per-step working set larger than L2 (%.0f MB of workspaces/intermediates); only the "
                          "theta-independent atmosphere table and response stay L2-resident" % (ws_bytes / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "fp64", "kernel": "k_azinv_flux<2,0> (+ k_azinv_geometry, k_azinv_slab)",
+        "roofline": {"bound": "fp64", "kernel": "k_azinv_flux<2,0,0> (+ k_azinv_geometry, k_azinv_slab, k_azinv_slab_member, k_azinv_moments: the integrate stage)",
                      "achieved": achieved, "peak": float(peak[0]),
                      "unit": "TFLOP/s", "frac": achieved / float(peak[0]),
-                     "traffic": 7.71e6 * B,
-                     "traffic_source": "ncu --set full at batch 32 (dram read+write 246.9 MB per launch, profiles/r01d_k_azinv_flux_ncu_full.txt), scaled to this batch",
+                     "traffic": 8.15e6 * B,
+                     "traffic_source": "ncu --set full at batch 32 (dram read+write 260.9 MB per launch, profiles/r01f_k_azinv_flux_ncu_full.txt), scaled to this batch",
                      "peak_source": "in-run DFMA microbenchmark (MEASURED_PEAKS.json has no fp64 entry)",
                      "algorithmic_gflop_per_eval": {k: v / 1e9 for k, v in fl.items()},
                      "whole_path_tflops": whole, "whole_path_frac": whole / float(peak[0]),

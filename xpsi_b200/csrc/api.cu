@@ -272,7 +272,7 @@ static int integrate_member(
   a.ws_leaf = d_ws.p; a.ws_hdr = d_wh.p; a.ws_ihdr = d_wi.p; a.ws_slab = d_wslab.p; a.ws_slab2 = d_wslab2.p;
   cudaError_t e = general ? xb::launch_integrate_general(a, g_stream) : xb::launch_integrate_azinv(a, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, general ? "launch_integrate_general" : "launch_integrate_azinv");
-  g_launches += general ? 3 : ((hot_atm_ext == XPSI_B200_ATM_NUM4D) ? 4 : 3);
+  g_launches += general ? 3 : ((hot_atm_ext == XPSI_B200_ATM_NUM4D) ? 5 : 3);
   int status = 0;
   CK(d_flux.download(flux_out, (size_t)n_energies * n_phases));
   CK(d_status.download(&status, 1));
@@ -783,7 +783,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
     int blocks = (int)(((long)B * c.n_energies * c.n_phases + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_add_spectrum<<<blocks, 256, 0, g_stream>>>(p->x_flux.p, p->energies.p, B, M, c.n_energies, c.n_phases, p->flux.p);
-    g_launches += 1 + (p->ex.else_atm_ext == XPSI_B200_ATM_NUM4D ? 1 : 0);
+    g_launches += 1 + (p->ex.else_atm_ext == XPSI_B200_ATM_NUM4D ? 2 : 0);
   }
   CK(cudaEventRecord(p->ev[1], g_stream));
 
@@ -823,7 +823,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   e = xb::launch_marginal(m, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_marginal");
   CK(cudaEventRecord(p->ev[4], g_stream));
-  g_launches += 9 + (c.hot_atm_ext == XPSI_B200_ATM_NUM4D ? 1 : 0);   // expand, geometry, [slab], moments, flux, energy, fold, member-status, marginal, channel-sum
+  g_launches += 9 + (c.hot_atm_ext == XPSI_B200_ATM_NUM4D ? 2 : 0);   // expand, geometry, [slab, slab-member], moments, flux, energy, fold, member-status, marginal, channel-sum
   return 0;
 }
 
