@@ -689,3 +689,27 @@ def test_gpu_embed_of_omission_ceding_and_polar_regions(m2):
     print("polar-cap parameter-level lnL", lnL, "ref", float(d["lnL_total"]), "status", status)
     assert (status == 0).all()
     assert np.max(np.abs(lnL - float(d["lnL_total"]))) < 1e-4
+
+
+def test_likelihood_callable_mirrors_reference_conventions(m2):
+    """xpsi.Likelihood.__call__ (Likelihood.py:450-511) over the GPU pipeline: value, prior handling,
+    random-near-llzero on rejected / failed points, batched evaluation."""
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.likelihood import Likelihood
+    pipe = _m2_pipeline(m2, max_batch=8)
+    fill = lambda pl, P: syn.m2_spot_batch(pl, P)
+    like = Likelihood(pipe, fill, llzero=-1.0e90)
+    ref = float(m2["t0_lnL_total"])
+    v = like(m2["t0_theta"], force=True)
+    assert isinstance(v, float) and abs(v - ref) < 1e-4
+    assert like(m2["t0_theta"]) == v                                  # memoised
+    assert like() == v                                                # externally updated / cached vector
+    with_prior = Likelihood(pipe, fill, prior=lambda p: -3.5)
+    assert abs(with_prior(m2["t1_theta"]) - (float(m2["t1_lnL_total"]) - 3.5)) < 1e-4
+    rejected = Likelihood(pipe, fill, prior=lambda p: -np.inf)
+    r = rejected(m2["t0_theta"])
+    assert -1.0e90 <= r <= -1.0e89                                    # Likelihood.py:267-271
+    lnL, status = like.batch(np.array([m2["t0_theta"], m2["t1_theta"], m2["t0_theta"]]))
+    assert (status == 0).all() and abs(lnL[1] - float(m2["t1_lnL_total"])) < 1e-4 and abs(lnL[0] - lnL[2]) < 1e-7
+    with pytest.raises(TypeError):
+        Likelihood(pipe, fill)()

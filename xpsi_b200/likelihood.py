@@ -1,0 +1,72 @@
+"""Scalar / batched likelihood callable over the GPU pipeline, mirroring ``xpsi.Likelihood.__call__``
+(xpsi/Likelihood.py:450-511) for models whose hot regions the parameter-level embed covers.
+
+The reference's ``Likelihood`` walks a tree of parameter objects (``Star`` / ``Photosphere`` / ``HotRegion`` /
+``Signal``); here the model is the ``BatchedLikelihood`` pipeline plus one user function that maps an array of
+parameter vectors onto a ``SpotBatch`` (and, optionally, the per-batch extras) -- the vectorised equivalent of
+``super(Likelihood, self).__call__(p)`` followed by ``Star.update``.  The return conventions are the reference's:
+a float log-likelihood (plus the log-prior when a prior is given), or a random value near ``llzero`` when the prior
+is not finite, when a stage reports a numerical failure (the reference's ``PulseError`` / ``RayError`` handling,
+xpsi/Likelihood.py:346-358) or when the result is below ``llzero``.
+"""
+import numpy as np
+
+
+class Likelihood:
+    def __init__(self, pipeline, fill, prior=None, llzero=-1.0e90, max_batch=None):
+        """
+        :param pipeline: a :class:`xpsi_b200.pipeline.BatchedLikelihood`.
+        :param fill: ``fill(pipeline, P) -> SpotBatch`` for an array ``P[B, n_params]``; it may call
+                     ``pipeline.upload_extras`` for Elsewhere / interstellar inputs.
+        :param prior: optional callable ``prior(p) -> log-prior`` (``xpsi.Prior.__call__``).
+        """
+        self._pipe, self._fill, self._prior = pipeline, fill, prior
+        self.llzero = float(llzero)
+        self._max_batch = int(max_batch or pipeline.max_batch)
+        self._cached_p, self._cached_value = None, None
+        self.externally_updated = False
+
+    @property
+    def random_near_llzero(self):
+        """xpsi/Likelihood.py:267-271"""
+        return float(self.llzero * (0.1 + 0.9 * np.random.rand(1))[0])
+
+    def clear_cache(self):
+        self._cached_p, self._cached_value = None, None
+
+    def batch(self, P):
+        """log-likelihoods of the rows of ``P`` (no prior added); rows that fail carry ``nan`` and a status."""
+        P = np.atleast_2d(np.asarray(P, dtype=np.float64))
+        lnL = np.empty(P.shape[0])
+        status = np.empty(P.shape[0], dtype=np.int32)
+        for i in range(0, P.shape[0], self._max_batch):
+            blk = P[i:i + self._max_batch]
+            lnL[i:i + blk.shape[0]], status[i:i + blk.shape[0]] = self._pipe.eval_spots(self._fill(self._pipe, blk))
+        lnL[status != 0] = np.nan
+        return lnL, status
+
+    def __call__(self, p=None, reinitialise=False, force=False):
+        """Same signature and return convention as xpsi/Likelihood.py:450-511."""
+        if reinitialise or force:
+            self.clear_cache()
+        if p is None:
+            if self._cached_p is None:
+                raise TypeError('Parameter values have not been updated.')
+            p = self._cached_p
+        p = np.asarray(p, dtype=np.float64)
+        logprior = None
+        if self._prior is not None:
+            logprior = self._prior(p)
+            if not np.isfinite(logprior):
+                return self.random_near_llzero
+        if self._cached_p is not None and np.array_equal(p, self._cached_p):
+            loglikelihood = self._cached_value                      # memoised, Likelihood.py:489-490
+        else:
+            lnL, status = self.batch(p[None, :])
+            if status[0] != 0:                                      # numerical failure or slim early exit
+                return self.random_near_llzero
+            loglikelihood = float(lnL[0])
+            self._cached_p, self._cached_value = p.copy(), loglikelihood
+        if loglikelihood <= self.llzero:
+            return self.random_near_llzero
+        return loglikelihood + logprior if logprior is not None else loglikelihood
