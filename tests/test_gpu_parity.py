@@ -713,3 +713,77 @@ def test_likelihood_callable_mirrors_reference_conventions(m2):
     assert (status == 0).all() and abs(lnL[1] - float(m2["t1_lnL_total"])) < 1e-4 and abs(lnL[0] - lnL[2]) < 1e-7
     with pytest.raises(TypeError):
         Likelihood(pipe, fill)()
+
+
+def test_edge_cases_and_error_paths(c1):
+    """Edge cases the reference handles or rejects: meshes without radiating cells, dark rings, one image order,
+    a single energy; argument errors surface as exceptions with the library's message (never a silent fallback)."""
+    from xpsi_b200 import _lib
+    from xpsi_b200.cellmesh.integrator_for_azimuthal_invariance import integrate
+    from xpsi_b200.cellmesh.integrator import integrate as integrate_general
+    from xpsi_b200.tools import energy_integrator
+    base = list(_integrate_args(c1, "int0_", ()))
+    # nothing radiates -> zeros, status 0 (pyx:286-296 skips every ring)
+    a = list(base); a[11] = np.zeros_like(base[11])
+    for fn in (integrate, integrate_general):
+        status, flux = fn(*a)
+        assert status == 0 and flux.shape == c1["int0_flux"].shape and not flux.any()
+    # only a few rings radiate -> equals the sum restricted to those rings (rings are independent)
+    rad = np.zeros_like(base[11]); rad[3:6] = base[11][3:6]
+    a = list(base); a[11] = rad
+    s1, f_part = integrate(*a)
+    rad2 = np.array(base[11]); rad2[3:6] = 0
+    a = list(base); a[11] = rad2
+    s2, f_rest = integrate(*a)
+    s3, f_all = integrate(*base)
+    assert s1 == 0 and s2 == 0 and s3 == 0
+    assert _pulse_err(f_part + f_rest, f_all) < 1e-13
+    # image_order_limit = 1 keeps the primary image only and can only lower the flux
+    a = list(base); a[27] = 1
+    s4, f_one = integrate(*a)
+    assert s4 == 0 and np.all(f_one <= f_all * (1 + 1e-12)) and f_one.sum() > 0.9 * f_all.sum()
+    # a single energy is a valid call
+    a = list(base); a[19] = np.ascontiguousarray(base[19][40:41])
+    s5, f_single = integrate(*a)
+    assert s5 == 0 and _pulse_err(f_single, f_all[40:41]) < 1e-13
+    # argument errors
+    a = list(base); a[20] = np.ascontiguousarray(base[20][:4])        # fewer than 5 leaves
+    with pytest.raises(_lib.XpsiB200Error):
+        integrate(*a)
+    a = list(base); a[24] = 7                                          # unknown atmosphere extension
+    with pytest.raises(NotImplementedError):
+        integrate(*a)
+    a = list(base); a[21] = np.linspace(0.0, 2 * np.pi, 200)           # more phases than the kernels cover
+    with pytest.raises((_lib.XpsiB200Error, NotImplementedError)):
+        integrate(*a)
+    with pytest.raises(_lib.XpsiB200Error):                            # Akima needs >= 5 energies
+        energy_integrator(1, np.ones((3, 4)), np.log10([1.0, 2.0, 3.0]), np.log10([1.0, 1.5, 2.5]))
+
+
+def test_pipeline_properties_at_bench_batch_size(m2):
+    """Size-independent properties on a bench-sized batch (512 parameter vectors): results do not depend on the
+    position in the batch, a whole-cycle phase shift changes nothing, and the flux scales as 1/d^2."""
+    from xpsi_b200 import synthetic as syn
+    pipe = _m2_pipeline(m2, max_batch=512)
+    B = 512
+    thetas = np.vstack([m2["t0_theta"], m2["t1_theta"], syn.m2_theta_batch(B - 2)])
+    lnL, status = pipe.eval_spots(syn.m2_spot_batch(pipe, thetas))
+    assert np.isin(status, (0, 11)).all()
+    assert abs(lnL[0] - float(m2["t0_lnL_total"])) < 1e-4 and abs(lnL[1] - float(m2["t1_lnL_total"])) < 1e-4
+    perm = np.random.default_rng(0).permutation(B)
+    lnL_p, status_p = pipe.eval_spots(syn.m2_spot_batch(pipe, thetas[perm]))
+    ok = (status == 0)
+    assert (status_p == status[perm]).all()
+    assert np.max(np.abs(lnL_p[ok[perm]] - lnL[perm][ok[perm]])) < 1e-6      # ring sums use fp64 atomics (DESIGN s5.4)
+    shifted = np.array(thetas[:64]); shifted[:, 4] += 1.0; shifted[:, 8] -= 1.0
+    lnL_s, status_s = pipe.eval_spots(syn.m2_spot_batch(pipe, shifted))
+    good = (status[:64] == 0) & (status_s == 0)
+    assert good.sum() > 10 and np.max(np.abs(lnL_s[good] - lnL[:64][good])) < 1e-6
+    flux_a = pipe.fetch(64, folded=False, expected=False)[0]
+    far = np.array(thetas[:64]); far[:, 2] *= 2.0
+    pipe.eval_spots(syn.m2_spot_batch(pipe, far))
+    folded_far = pipe.fetch(64, flux=False, expected=False)[1]
+    pipe.eval_spots(syn.m2_spot_batch(pipe, thetas[:64]))
+    flux_b, folded_near, _ = pipe.fetch(64, expected=False)
+    assert rel_err(folded_far * 4.0, folded_near) < 1e-12                       # Likelihood.py:361-364
+    assert rel_err(flux_b, flux_a) < 1e-10
