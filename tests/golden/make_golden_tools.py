@@ -59,3 +59,22 @@ out.update({"syn_bg_counts": bg_counts, "syn_exposure_expected": np.asarray(e1),
             "syn_total_expected": np.asarray(e2), "syn_total_scales": np.array([s2a, s2b])})
 np.savez_compressed(os.path.join(HERE, "tools.npz"), **out)
 print("tools.npz (+synthesise)", os.path.getsize(os.path.join(HERE, "tools.npz")) // 1024, "KiB")
+
+# ---- eval_marginal_likelihood with more than 32 data phase bins (64 and a ragged 45) --------------------
+from xpsi.likelihoods.default_background_marginalisation import eval_marginal_likelihood, precomputation  # noqa: E402
+from xpsi.tools import phase_integrator as _pint  # noqa: E402
+out = dict(np.load(os.path.join(HERE, "tools.npz")))
+rng = np.random.default_rng(11)
+for nb in (64, 45):
+    ph = np.linspace(0.0, 1.0, nb + 1)
+    expec = _pint(1000.0, ph, comp, sig_phases, 0.13) + 2.0 * 1000.0 / nb
+    cnts = rng.poisson(expec).astype(np.double)
+    pre = precomputation(cnts.astype(np.int32))
+    sup = -1.0 * np.ones((comp.shape[0], 2)); sup[:, 0] = 0.0
+    res = eval_marginal_likelihood(1000.0, ph, cnts, (comp,), (sig_phases,), np.array([0.13]), pre, sup,
+                                   1000, 0.0, 1.0e-8, 1.0e-3, 10.0, -1.0e90)
+    out.update({"mbins%d_counts" % nb: cnts, "mbins%d_lnL" % nb: np.asarray(res[0]),
+                "mbins%d_expected" % nb: np.asarray(res[1]), "mbins%d_bg" % nb: np.asarray(res[2])})
+    print("marginal likelihood with %d bins: lnL = %.8f" % (nb, res[0]))
+np.savez_compressed(os.path.join(HERE, "tools.npz"), **out)
+print("tools.npz (+many-bin likelihood)", os.path.getsize(os.path.join(HERE, "tools.npz")) // 1024, "KiB")

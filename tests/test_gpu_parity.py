@@ -787,3 +787,21 @@ def test_pipeline_properties_at_bench_batch_size(m2):
     flux_b, folded_near, _ = pipe.fetch(64, expected=False)
     assert rel_err(folded_far * 4.0, folded_near) < 1e-12                       # Likelihood.py:361-364
     assert rel_err(flux_b, flux_a) < 1e-10
+
+
+def test_marginal_likelihood_with_more_than_32_phase_bins(c1):
+    """eval_marginal_likelihood with 64 and with a ragged 45 data phase bins (lanes own several bins)."""
+    from xpsi_b200.likelihoods import eval_marginal_likelihood, precomputation
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tools.npz"))
+    comp, sig_phases = c1["marg_components_0"], c1["marg_component_phases_0"]
+    sup = -1.0 * np.ones((comp.shape[0], 2)); sup[:, 0] = 0.0
+    for nb in (64, 45):
+        ph = np.linspace(0.0, 1.0, nb + 1)
+        cnts = d["mbins%d_counts" % nb]
+        pre = precomputation(cnts.astype(np.int32))
+        res = eval_marginal_likelihood(1000.0, ph, cnts, (comp,), (sig_phases,), np.array([0.13]), pre, sup,
+                                       1000, 0.0, 1.0e-8, 1.0e-3, 10.0, -1.0e90)
+        print(nb, "bins: lnL", res[0], "ref", float(d["mbins%d_lnL" % nb]))
+        assert abs(res[0] - float(d["mbins%d_lnL" % nb])) < LNL_ATOL
+        assert rel_err(res[1], d["mbins%d_expected" % nb]) < PULSE_RTOL
+        assert rel_err(res[2], d["mbins%d_bg" % nb]) < 1e-6

@@ -532,7 +532,7 @@ int xpsi_b200_eval_marginal_likelihood(
     double* mcl_background_given_support) {
   int rc = ensure_stream();
   if (rc) return rc;
-  if (n_bins < 1 || n_bins > 32) return fail(XPSI_B200_EUNSUPPORTED, "1..32 phase bins supported");
+  if (n_bins < 1 || n_bins > xb::marginal_max_bins()) return fail(XPSI_B200_EUNSUPPORTED, "1..128 phase bins supported");
   if (n_comp < 1 || n_chan < 1 || n_phases < 5) return fail(XPSI_B200_EINVAL, "bad dimensions");
   Dev<double> d_pulses, d_cph, d_sh, d_dph, d_cnt, d_pre, d_sup, d_bg, d_clnl, d_exp, d_mb, d_mbs, d_lnl;
   Dev<int> d_cst, d_st;
@@ -578,7 +578,7 @@ int xpsi_b200_poisson_likelihood_given_background(
     int allow_negative, int phase_interpolant, double* lnL, double* expected_counts) {
   int rc = ensure_stream();
   if (rc) return rc;
-  if (n_bins < 1 || n_bins > 32) return fail(XPSI_B200_EUNSUPPORTED, "1..32 phase bins supported");
+  if (n_bins < 1 || n_bins > xb::marginal_max_bins()) return fail(XPSI_B200_EUNSUPPORTED, "1..128 phase bins supported");
   if (n_comp < 1 || n_chan < 1 || n_phases < 5 || !background) return fail(XPSI_B200_EINVAL, "bad arguments");
   Dev<double> d_pulses, d_cph, d_sh, d_dph, d_cnt, d_pre, d_bg, d_clnl, d_exp, d_lnl, d_sup;
   Dev<int> d_cst, d_st;
@@ -861,7 +861,7 @@ extern "C" {
 xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* cfg, int max_batch) {
   if (ensure_stream() != 0) return nullptr;
   const xpsi_b200_pipeline_config& c = *cfg;
-  if (max_batch < 1 || c.n_components < 1 || c.n_members < c.n_components || c.n_bins < 1 || c.n_bins > 32 ||
+  if (max_batch < 1 || c.n_components < 1 || c.n_members < c.n_components || c.n_bins < 1 || c.n_bins > xb::marginal_max_bins() ||
       c.n_energies < 5 || c.n_leaves < 5 || c.n_phases < 5 ||
       (c.hot_atm_ext != XPSI_B200_ATM_BB && c.hot_atm_ext != XPSI_B200_ATM_NUM4D) ||
       (c.hot_atm_ext == XPSI_B200_ATM_NUM4D && !c.hot_atmosphere)) {

@@ -185,6 +185,7 @@ struct MarginalArgs {
   int* status;                       // [B]
 };
 cudaError_t launch_marginal(MarginalArgs a, cudaStream_t stream);
+int marginal_max_bins();           // lane j of a warp owns data phase bins j, j+32, ...: up to 128
 
 // surface_radiation_field.intensity (core.pyx:125-308): point-wise intensities from local variables
 struct IntensityArgs {

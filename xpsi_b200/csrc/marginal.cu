@@ -5,7 +5,7 @@
 //
 // One warp per (parameter vector, channel):
 //   * the channel's pulse of each component is splined in phase (the global
-//     phase interpolant), lane j integrates data phase bin j with the
+//     phase interpolant), lane j integrates data phase bins j, j+32, ... (BPL per lane) with the
 //     reference's shift / wrap / clip rules;
 //   * the Newton search for the ML background uses warp reductions over bins;
 //   * the marginal integral replaces GSL CQUAD by a fixed-order rule that is
@@ -19,7 +19,7 @@
 namespace xb {
 
 constexpr int kWarpsPerBlock = 4;
-constexpr int kMaxBins = 32;
+constexpr int kMaxBPL = 4;                 // bins per lane: up to 128 data phase bins
 
 __constant__ double c_gl8_x[8] = {
     -9.60289856497536176e-01, -7.96666477413626728e-01, -5.25532409916328991e-01,
@@ -60,7 +60,9 @@ __device__ __forceinline__ double log_integrand(const double* star, const double
   return x;
 }
 
+template <int BPL>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a) {
+  constexpr int kMaxBins = 32 * BPL;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int chan = blockIdx.x * kWarpsPerBlock + warp;
   const int b = blockIdx.y;
@@ -70,8 +72,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
   double* w_base = smem + N_P + (long)warp * (5 * N_P + 2 * kMaxBins);
   double* s_y = w_base;                                          // [N_P]
   double* s_c = s_y + N_P;                                       // [N_P][4]
-  double* s_star = s_c + 4 * N_P;                                // [32]
-  double* s_data = s_star + kMaxBins;                            // [32]
+  double* s_star = s_c + 4 * N_P;                                // [kMaxBins]
+  double* s_data = s_star + kMaxBins;                            // [kMaxBins]
   for (int i = threadIdx.x; i < N_P; i += blockDim.x) s_x[i] = a.comp_phases[i];
   __syncthreads();
   if (chan >= a.n_chan) return;            // whole warps only; no block barrier below
@@ -82,7 +84,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
   const bool periodic = (a.interp != kSteffen);
 
   // ---- expected star count rate per bin (compute_expected_counts.pyx:66-197) ----------
-  double star = 0.0;
+  double star[BPL];
+#pragma unroll
+  for (int j = 0; j < BPL; ++j) star[j] = 0.0;
   for (int c = 0; c < a.n_comp; ++c) {
     const double* pulse = a.pulses + (((long)b * a.n_comp + c) * a.n_chan + chan) * N_P;
     for (int i = lane; i < N_P; i += 32) s_y[i] = pulse[i];
@@ -93,36 +97,43 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
       s_c[4 * i] = s_y[i]; s_c[4 * i + 1] = bb; s_c[4 * i + 2] = cc; s_c[4 * i + 3] = dd;
     }
     __syncwarp();
-    if (lane < n) {
+#pragma unroll
+    for (int j = 0; j < BPL; ++j) {
+      const int bin = lane + 32 * j;
+      if (bin >= n) continue;
       const double shift = a.phase_shifts[(long)b * a.n_comp + c];
-      double pa = a.data_phases[lane] + shift;
-      double pb = a.data_phases[lane + 1] + shift;
+      double pa = a.data_phases[bin] + shift;
+      double pb = a.data_phases[bin + 1] + shift;
       if (are_equal(pb - pa, 1.0)) { pa = 0.0; pb = 1.0; }
       else { pa -= floor(pa); pb -= floor(pb); }
       if (pa < pb) {
         const double v = spline_integ(s_x, s_c, N_P, pa, pb);
-        if (v > 0.0 || a.allow_negative) star += v;
+        if (v > 0.0 || a.allow_negative) star[j] += v;
       } else {
         double v = spline_integ(s_x, s_c, N_P, pa, 1.0);
-        if (v > 0.0 || a.allow_negative) star += v;
+        if (v > 0.0 || a.allow_negative) star[j] += v;
         v = spline_integ(s_x, s_c, N_P, 0.0, pb);
-        if (v > 0.0 || a.allow_negative) star += v;
+        if (v > 0.0 || a.allow_negative) star[j] += v;
       }
     }
     __syncwarp();
   }
-  if (star < 0.0) star = 0.0;
+#pragma unroll
+  for (int j = 0; j < BPL; ++j) if (star[j] < 0.0) star[j] = 0.0;
   if (a.given_background) {
     // compute_expected_counts.pyx:300-305 + _poisson_likelihood_given_background.pyx:96-113
-    double term = 0.0, expec = 0.0;
+    double term = 0.0;
     int bad = 0;
-    if (lane < n) {
-      expec = (star + a.background[(long)chan * n + lane]) * T;
-      const double cnt = a.counts ? a.counts[(long)chan * n + lane] : 0.0;
-      if (expec > 0.0) term = cnt * log(expec) - expec;
-      else if (cnt == 0.0 && expec == 0.0) term = 0.0;
+#pragma unroll
+    for (int j = 0; j < BPL; ++j) {
+      const int bin = lane + 32 * j;
+      if (bin >= n) continue;
+      const double expec = (star[j] + a.background[(long)chan * n + bin]) * T;
+      const double cnt = a.counts ? a.counts[(long)chan * n + bin] : 0.0;
+      if (expec > 0.0) term += cnt * log(expec) - expec;
+      else if (cnt == 0.0 && expec == 0.0) {}
       else bad = 1;
-      if (a.expected) a.expected[((long)b * a.n_chan + chan) * n + lane] = expec;
+      if (a.expected) a.expected[((long)b * a.n_chan + chan) * n + bin] = expec;
     }
     const double sum = warp_sum(term);
     const unsigned anybad = __ballot_sync(0xffffffffu, bad);
@@ -132,16 +143,30 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
     }
     return;
   }
-  double d = 0.0;
-  if (lane < n) {
-    if (a.background) star += a.background[(long)chan * n + lane];
-    star *= nd;                                                // pyx:659-665
-    d = a.counts[(long)chan * n + lane];
-  } else star = 0.0;
-  s_star[lane] = star; s_data[lane] = d;
+  double d[BPL];
+  double sum_star = 0.0, sum_d = 0.0;
+#pragma unroll
+  for (int j = 0; j < BPL; ++j) {
+    const int bin = lane + 32 * j;
+    d[j] = 0.0;
+    if (bin < n) {
+      if (a.background) star[j] += a.background[(long)chan * n + bin];
+      star[j] *= nd;                                           // pyx:659-665
+      d[j] = a.counts[(long)chan * n + bin];
+    } else star[j] = 0.0;
+    s_star[bin] = star[j]; s_data[bin] = d[j];
+    sum_star += star[j]; sum_d += d[j];
+  }
   __syncwarp();
-  double av_STAR = warp_sum(star);
-  double av_DATA = warp_sum(d);
+  double av_STAR = warp_sum(sum_star);
+  double av_DATA = warp_sum(sum_d);
+  // sums over this lane's bins of f(star, data)
+  auto bins_sum = [&](auto f) -> double {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < BPL; ++j) if (lane + 32 * j < n) acc += f(star[j], d[j]);
+    return acc;
+  };
 
   int status = 0;
   double loglike = 0.0, B = 0.0;
@@ -166,10 +191,16 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
       double B_min = 0.0;
       B = av_DATA - av_STAR;
       if (B <= B_min) {                                        // pyx:309-332
-        const unsigned zero_star = __ballot_sync(0xffffffffu, lane < n && are_equal(star, 0.0));
+        bool any_zero = false;
+        double m = INFINITY;                      // smallest positive count among the bins
+#pragma unroll
+        for (int j = 0; j < BPL; ++j) {
+          if (lane + 32 * j >= n) continue;
+          if (are_equal(star[j], 0.0)) any_zero = true;
+          if (d[j] > 0.0) m = fmin(m, d[j]);
+        }
+        const unsigned zero_star = __ballot_sync(0xffffffffu, any_zero);
         if (zero_star) {
-          // smallest positive count among the bins
-          double m = (lane < n && d > 0.0) ? d : INFINITY;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
           if (isinf(m)) { B = 0.0; B_min = 0.0; }
@@ -181,9 +212,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
       // Newton iterations (pyx:336-352); delta() = pyx:140-173
       double std, dB;
       {
-        const double r = (lane < n) ? d / (star + B) : 0.0;
-        const double y = warp_sum(r);
-        const double x = warp_sum((lane < n) ? r / (star + B) : 0.0);
+        const double y = warp_sum(bins_sum([&](double s_, double d_) { return d_ / (s_ + B); }));
+        const double x = warp_sum(bins_sum([&](double s_, double d_) { return d_ / (s_ + B) / (s_ + B); }));
         std = sqrt(2.0 / (2.0 * x));
         dB = -1.0 * (2.0 * T - 2.0 * y) / (2.0 * x);
       }
@@ -194,14 +224,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
           if (B_min > 0.0) counter += 1; else counter = 2;
           B = B_min;
         }
-        const double r = (lane < n) ? d / (star + B) : 0.0;
-        const double y = warp_sum(r);
-        const double x = warp_sum((lane < n) ? r / (star + B) : 0.0);
+        const double y = warp_sum(bins_sum([&](double s_, double d_) { return d_ / (s_ + B); }));
+        const double x = warp_sum(bins_sum([&](double s_, double d_) { return d_ / (s_ + B) / (s_ + B); }));
         std = sqrt(2.0 / (2.0 * x));
         dB = -1.0 * (2.0 * T - 2.0 * y) / (2.0 * x);
         if (++iters > 500) { status = 2; break; }
       }
-      double std_est = warp_sum((lane < n) ? d / ((star + B) * (star + B)) : 0.0);
+      double std_est = warp_sum(bins_sum([&](double s_, double d_) { return d_ / ((s_ + B) * (s_ + B)); }));
       std_est = std_est > 0.0 ? sqrt(1.0 / std_est) : 1e90;
       double lower = B - a.sigmas * std_est;
       double upper = B + a.sigmas * std_est;
@@ -220,14 +249,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
       // A: log-integrand at the clipped ML background (pyx:397-408)
       double A;
       {
-        double term = 0.0;
-        if (lane < n) {
-          const double c = SCALE * (star + Bfi);
-          if (c > 0.0) term = d * log(c) - c;
-          else if (are_equal(c, 0.0) && are_equal(d, 0.0)) term = 0.0;
-          else term = a.llzero;
-        }
-        A = warp_sum(term);
+        const double llz = a.llzero;
+        A = warp_sum(bins_sum([&](double s_, double d_) {
+          const double c = SCALE * (s_ + Bfi);
+          if (c > 0.0) return d_ * log(c) - c;
+          if (are_equal(c, 0.0) && are_equal(d_, 0.0)) return 0.0;
+          return llz;
+        }));
       }
       // ---- marginal integral over [lower, upper] (replaces pyx:416-419) -------------
       double result = 0.0;
@@ -276,8 +304,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
   double Bc = B;
   if (Bc < sup0) Bc = sup0; else if (Bc > sup1 && sup1 > 0.0) Bc = sup1;
   if (lane == 0 && a.mcl_bg_support) a.mcl_bg_support[(long)b * a.n_chan + chan] = Bc * T;
-  if (a.expected && lane < n)
-    a.expected[((long)b * a.n_chan + chan) * n + lane] = (status == 0) ? SCALE * (star + Bc) : star;
+  if (a.expected) {
+#pragma unroll
+    for (int j = 0; j < BPL; ++j)
+      if (lane + 32 * j < n)
+        a.expected[((long)b * a.n_chan + chan) * n + lane + 32 * j] = (status == 0) ? SCALE * (star[j] + Bc) : star[j];
+  }
 }
 
 // ordered reduction over channels; the first failing channel decides the status
@@ -309,17 +341,26 @@ __global__ void k_sum_channels(const double* chan_lnL, const int* chan_status, i
   }
 }
 
-cudaError_t launch_marginal(MarginalArgs a, cudaStream_t stream) {
-  if (a.n_bins > kMaxBins || a.n_bins < 1) return cudaErrorNotSupported;
-  if (a.n_phases < 5) return cudaErrorInvalidValue;
-  const size_t smem = ((size_t)a.n_phases + kWarpsPerBlock * (5ul * a.n_phases + 2 * kMaxBins)) * sizeof(double);
+template <int BPL>
+static cudaError_t launch_marginal_bpl(const MarginalArgs& a, cudaStream_t stream) {
+  const size_t smem = ((size_t)a.n_phases + kWarpsPerBlock * (5ul * a.n_phases + 2 * 32 * BPL)) * sizeof(double);
   dim3 grid((a.n_chan + kWarpsPerBlock - 1) / kWarpsPerBlock, a.B);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_marginal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_marginal<BPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  k_marginal<<<grid, 32 * kWarpsPerBlock, smem, stream>>>(a);
-  cudaError_t err = cudaGetLastError();
+  k_marginal<BPL><<<grid, 32 * kWarpsPerBlock, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+int marginal_max_bins() { return 32 * kMaxBPL; }
+
+cudaError_t launch_marginal(MarginalArgs a, cudaStream_t stream) {
+  if (a.n_bins > 32 * kMaxBPL || a.n_bins < 1) return cudaErrorNotSupported;
+  if (a.n_phases < 5) return cudaErrorInvalidValue;
+  cudaError_t err = a.n_bins <= 32 ? launch_marginal_bpl<1>(a, stream)
+                    : a.n_bins <= 64 ? launch_marginal_bpl<2>(a, stream) : launch_marginal_bpl<4>(a, stream);
   if (err != cudaSuccess) return err;
   if (a.lnL) {
     k_sum_channels<<<a.B, 256, 0, stream>>>(a.chan_lnL, a.chan_status, a.n_chan, a.lnL, a.status);
