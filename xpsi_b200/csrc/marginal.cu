@@ -12,7 +12,7 @@
 //     converged far below the reference's epsrel: the log-integrand is concave
 //     in B, so the warp first brackets the super-level set {x(B) >= max-45} by
 //     probing 32 points at a time (zooming while it is under-resolved) and then
-//     applies 24 panels x 8-point Gauss-Legendre with one node per lane.
+//     applies 16 panels x 8-point Gauss-Legendre with one node per lane.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -278,10 +278,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
           lo = nlo; hi = nhi;
           if (resolved) break;
         }
-        const double hp = (hi - lo) / 24.0;
+        // 16 panels x 8-point Gauss-Legendre over the bracketed set: the integrand is close to a Gaussian
+        // about 19 sigma wide there, so a panel spans ~1.2 sigma and the rule is converged to ~1e-14
+        const double hp = (hi - lo) / 16.0;
         double acc = 0.0;
 #pragma unroll 1
-        for (int batch = 0; batch < 6; ++batch) {
+        for (int batch = 0; batch < 4; ++batch) {
           const int node = batch * 32 + lane;
           const int panel = node >> 3, g = node & 7;
           const double Bq = lo + hp * ((double)panel + 0.5 + 0.5 * c_gl8_x[g]);

@@ -106,7 +106,11 @@ __global__ void __launch_bounds__(kFoldThreads, 2) k_fold(FoldArgs a) {
   int kb = 0, ke = K;
   if (a.k_range) { kb = a.k_range[2 * mt]; ke = a.k_range[2 * mt + 1]; }
   kb = (kb / kBK) * kBK;
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;     // tx -> 8 columns (4 pairs), ty -> 4 rows
+  // thread tile 4 rows x 8 columns (4 pairs); a warp covers 4 row groups x 8 column groups so that every
+  // shared-memory read of the multiply loop is one wavefront: the A read touches 4 x 32 contiguous bytes,
+  // each B read 8 x 16 contiguous bytes (ncu: shared-memory bandwidth was the limiter with 2 x 16)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tx = (warp & 1) * 8 + (lane & 7), ty = (warp >> 1) * 4 + (lane >> 3);
   double acc[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
