@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(kEIThreads) k_energy_integrator(EnergyIntegArg
   }
   __syncthreads();
   const double xmin = s_x[0], xmax = s_x[N_E - 1];
+  const double inv_dx = (double)(N_E - 1) / (xmax - xmin);
   const int col = a.col_of_q ? a.col_of_q[q] : q;
   double* out = a.out + ((long)col * N_P + p) * n_in;
   for (int j = threadIdx.x; j < n_in; j += kEIThreads) {
@@ -56,8 +57,9 @@ __global__ void __launch_bounds__(kEIThreads) k_energy_integrator(EnergyIntegArg
       if (hi > xmax) hi = xmax;
       if (lo < xmin) lo = (xmin - lo <= 1.0e-9 * (1.0 + fabs(xmin))) ? xmin : nan("");
       if (lo == lo && hi > lo) {
-        const int ia = interval_search(s_x, N_E, lo);
-        const int ib = interval_search(s_x, N_E, hi);
+        // the energy grid is (near-)uniform in log10 E: guess the interval, then walk (same result as bisection)
+        const int ia = interval_walk(s_x, N_E, lo, (int)((lo - xmin) * inv_dx));
+        const int ib = interval_walk(s_x, N_E, hi, (int)((hi - xmin) * inv_dx));
         for (int i = ia; i <= ib; ++i) {
           const double x0 = s_x[i];
           const double r1 = (i == ia) ? lo - x0 : 0.0;
