@@ -35,6 +35,8 @@
 //     (pyx:593); intervals whose cubic is not provably non-negative (Bernstein
 //     coefficients) are flagged per energy and evaluated cell by cell.
 //   * rings/chunks are combined with fp64 RED atomics into flux[q, E, P].
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "azinv_shared.cuh"
@@ -708,8 +710,12 @@ __device__ __forceinline__ bool slab_ctx_load(SlabCtx& c, const AtmTable& T, con
   for (int r = tid; r < c.nrows; r += kFluxThreads) c.axE[r] = T.logE[c.elo_tab + r];
   const double* src = ring_slab + lo_c;
   const int sub = tid & 15, grp = tid >> 4;          // half a warp per mu row (a chunk reaches ~16 rows)
+  // asynchronous copy (LDGSTS): the rows are first needed two barriers later (stage 1 of the first image),
+  // so their L2 latency overlaps the cell list, the leaf arrays and the mu stencils
   for (int m = grp; m < T.nmu; m += kFluxThreads / 16)
-    for (int e = sub; e < c.nrows; e += 16) c.slab[m * c.nrows + e] = src[(long)m * rows_ring_stride + e];
+    for (int e = sub; e < c.nrows; e += 16)
+      __pipeline_memcpy_async(&c.slab[m * c.nrows + e], &src[(long)m * rows_ring_stride + e], sizeof(double));
+  __pipeline_commit();
   return true;
 }
 
@@ -897,6 +903,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
       if (CORR == 2) slab_ctx_leaf_stencils(els, s_abb, s_geom, N_L, tid);
     }
     for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
+    if (ATM == 2 || CORR == 2) __pipeline_wait_prior(0);          // slab rows have landed (no-op after the first image)
     __syncthreads();
     // ---- (1) leaf profile (pyx:445-478) -----------------------------------------------------
     for (int t = tid, e = 0, l = tid; t < ne * N_L; t += kFluxThreads, l += kFluxThreads) {
