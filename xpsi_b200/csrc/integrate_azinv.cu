@@ -684,14 +684,13 @@ __global__ void __launch_bounds__(kMomThreads) k_azinv_moments(AzinvArgs a) {
 // ===========================================================================
 // shared-memory view of one Num4D atmosphere inside a flux CTA
 struct SlabCtx {
-  double* axE; double* invden; double* axMu; double* slab; double* muw; int* mub;
+  double* axE; double* invden; double* axMu; double* slab;
   int nrows, elo_tab, nE, nmu;
   double inv_dE, log_kT;
   const double* mu_invden;            // global, [nmu-3][4]
 };
 
 __device__ __forceinline__ double* slab_ctx_carve(SlabCtx& c, double* sp, int N_L, int rows_max, int nmu) {
-  c.muw = sp; sp += 4 * N_L;
   c.axE = sp; sp += rows_max;
   c.invden = sp; sp += 4 * rows_max;
   c.axMu = sp; sp += nmu;
@@ -727,31 +726,23 @@ __device__ __forceinline__ void slab_ctx_finish(SlabCtx& c, const AtmTable& T, i
   c.inv_dE = (c.nrows > 1) ? (double)(c.nrows - 1) / (c.axE[c.nrows - 1] - c.axE[0]) : 0.0;
 }
 
-// mu stencil of every lit leaf (geom != 0), weights stored [4][N_L]
+// mu stencil of one leaf, kept in registers by the thread that owns the leaf
 // clamp_low: beam_opt 3 only -- its mu sweep leaves the reference's stencil state at the top of the axis, so a
 // query below the table is walked down and clamped to the first node on every call (hot_Num4D.pyx:301-323)
-__device__ __forceinline__ void slab_ctx_leaf_stencils(const SlabCtx& c, const double* abb, const double* geom,
-                                                       int N_L, int tid, bool clamp_low = false) {
-  for (int l = tid; l < N_L; l += kFluxThreads) {
-    if (geom[l] == 0.0) continue;
-    double v = abb[l];
-    if (clamp_low && v < c.axMu[0]) v = c.axMu[0];
-    const int b = lagrange_base(c.axMu, c.nmu, v);
-    double w[4];
-    {
-      const double d0 = v - c.axMu[b], d1 = v - c.axMu[b + 1], d2 = v - c.axMu[b + 2], d3 = v - c.axMu[b + 3];
-      const double* iv = c.mu_invden + 4 * b;
-      w[0] = d1 * d2 * d3 * __ldg(iv); w[1] = d0 * d2 * d3 * __ldg(iv + 1);
-      w[2] = d0 * d1 * d3 * __ldg(iv + 2); w[3] = d0 * d1 * d2 * __ldg(iv + 3);
-    }
-    c.mub[l] = b;
-#pragma unroll
-    for (int x = 0; x < 4; ++x) c.muw[x * N_L + l] = w[x];
-  }
+struct MuStencil { int b; double w[4]; };
+__device__ __forceinline__ MuStencil slab_ctx_mu_stencil(const SlabCtx& c, double v, bool clamp_low = false) {
+  if (clamp_low && v < c.axMu[0]) v = c.axMu[0];
+  MuStencil m;
+  m.b = lagrange_base(c.axMu, c.nmu, v);
+  const double d0 = v - c.axMu[m.b], d1 = v - c.axMu[m.b + 1], d2 = v - c.axMu[m.b + 2], d3 = v - c.axMu[m.b + 3];
+  const double* iv = c.mu_invden + 4 * m.b;
+  m.w[0] = d1 * d2 * d3 * __ldg(iv); m.w[1] = d0 * d2 * d3 * __ldg(iv + 1);
+  m.w[2] = d0 * d1 * d3 * __ldg(iv + 2); m.w[3] = d0 * d1 * d2 * __ldg(iv + 3);
+  return m;
 }
 
-// I / T^3 at log10(E'/kT) = v for leaf l: 4x4 (mu, E) stencil on the slab (hot_Num4D.pyx:416-437)
-__device__ __forceinline__ double slab_ctx_eval(const SlabCtx& c, double v, int l, int N_L) {
+// I / T^3 at log10(E'/kT) = v with the leaf's mu stencil: 4x4 (mu, E) stencil on the slab (hot_Num4D.pyx:416-437)
+__device__ __forceinline__ double slab_ctx_eval(const SlabCtx& c, double v, const MuStencil& ms) {
   const int j = interval_walk(c.axE, c.nrows, v, (int)((v - c.axE[0]) * c.inv_dE));
   int bE = j - 1;                                                   // base node (App. C.5)
   if (c.elo_tab + bE < 0) bE = -c.elo_tab;
@@ -760,12 +751,12 @@ __device__ __forceinline__ double slab_ctx_eval(const SlabCtx& c, double v, int 
   const double* iv = c.invden + 4 * bE;
   const double wE0 = d1 * d2 * d3 * iv[0], wE1 = d0 * d2 * d3 * iv[1],
                wE2 = d0 * d1 * d3 * iv[2], wE3 = d0 * d1 * d2 * iv[3];
-  const double* row = c.slab + (long)c.mub[l] * c.nrows + bE;
+  const double* row = c.slab + (long)ms.b * c.nrows + bE;
   double sum = 0.0;
 #pragma unroll
   for (int x = 0; x < 4; ++x) {
     const double* r = row + x * c.nrows;
-    sum += c.muw[x * N_L + l] * (wE0 * r[0] + wE1 * r[1] + wE2 * r[2] + wE3 * r[3]);
+    sum += ms.w[x] * (wE0 * r[0] + wE1 * r[1] + wE2 * r[2] + wE3 * r[3]);
   }
   return sum < 0.0 ? 0.0 : sum;                                     // hot_Num4D.pyx:436-437
 }
@@ -833,19 +824,13 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
   double* s_cphi = sp; sp += a.n_azi;
   double* s_carea = sp; sp += a.n_azi;
   double* s_PH = sp; sp += N_L;
-  double* s_Z = sp; sp += N_L;
   double* s_aux = sp; sp += N_L;          // 1/h of the leaf intervals
-  double* s_abb = sp; sp += N_L;          // mu*eta
-  double* s_geom = sp; sp += N_L;
   double* s_y = sp; sp += kNEC * N_L;
   double* s_coef = sp; sp += (long)kNEC * N_L * 4;
   SlabCtx hot, els;
   if (ATM == 2) sp = slab_ctx_carve(hot, sp, N_L, a.slab_ne_max, a.hot.nmu);
   if (CORR == 2) sp = slab_ctx_carve(els, sp, N_L, a.slab_ne_max, a.els.nmu);
-  int* ip = reinterpret_cast<int*>(sp);
-  hot.mub = ip; ip += N_L;
-  els.mub = ip; if (CORR == 2) ip += N_L;
-  unsigned* s_flag = reinterpret_cast<unsigned*>(ip);
+  unsigned* s_flag = reinterpret_cast<unsigned*>(sp);
 
   // ---- compact list of the ring's radiating cells (one warp: keeps azimuth order) ------
   if (tid < 32) {
@@ -891,44 +876,41 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
 
   for (int I = 0; I < n_img; ++I) {
     __syncthreads();
-    // ---- leaf arrays of this image ------------------------------------------------------
+    // ---- leaf arrays of this image: the lagged phases go to shared memory (every later stage needs them),
+    // redshift / mu*eta / geometry factor stay in the registers of the thread that owns the leaf ---------
     const double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
-    for (int l = tid; l < N_L; l += kFluxThreads) {
-      s_PH[l] = W[l]; s_Z[l] = W[N_L + l]; s_abb[l] = W[2 * N_L + l]; s_geom[l] = W[3 * N_L + l];
-      s_flag[l] = 0u;
-    }
-    __syncthreads();
-    if (ATM == 2 || CORR == 2) {
-      if (ATM == 2) slab_ctx_leaf_stencils(hot, s_abb, s_geom, N_L, tid, a.beam_opt == 3);
-      if (CORR == 2) slab_ctx_leaf_stencils(els, s_abb, s_geom, N_L, tid);
-    }
-    for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
+    for (int l = tid; l < N_L; l += kFluxThreads) { s_PH[l] = W[l]; s_flag[l] = 0u; }
     if (ATM == 2 || CORR == 2) __pipeline_wait_prior(0);          // slab rows have landed (no-op after the first image)
     __syncthreads();
-    // ---- (1) leaf profile (pyx:445-478) -----------------------------------------------------
-    for (int t = tid, e = 0, l = tid; t < ne * N_L; t += kFluxThreads, l += kFluxThreads) {
-      while (l >= N_L) { l -= N_L; ++e; }
-      double val = 0.0;
-      const double geom = s_geom[l];
-      if (geom != 0.0) {
-        // s_Z holds Z for a blackbody hot atmosphere, log10 Z for Num4D
+    for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
+    // ---- (1) leaf profile (pyx:445-478): thread = leaf, the mu stencil is shared by the chunk's energies -----
+    for (int l = tid; l < N_L; l += kFluxThreads) {
+      const double geom = W[3 * N_L + l];
+      if (geom == 0.0) {
+#pragma unroll
+        for (int e = 0; e < kNEC; ++e) s_y[e * N_L + l] = 0.0;
+        continue;
+      }
+      const double zst = W[N_L + l];            // Z for a blackbody hot atmosphere, log10 Z for Num4D
+      const double abb = W[2 * N_L + l];        // mu * eta
+      MuStencil ms_hot, ms_els;
+      if (ATM == 2) ms_hot = slab_ctx_mu_stencil(hot, abb, BEAM && a.beam_opt == 3);
+      if (CORR == 2) ms_els = slab_ctx_mu_stencil(els, abb);
+      const double Zlin = (CORR == 1 && ATM == 2) ? exp10(zst) : zst;
+      const double Zlog = (CORR == 2 && ATM != 2) ? log10(zst) : zst;
+#pragma unroll
+      for (int e = 0; e < kNEC; ++e) {
         double I_E;
-        if (ATM == 1) I_E = bb_intensity(s_E[e] / s_Z[l], kT);
-        else I_E = slab_ctx_eval(hot, s_logE[e] - s_Z[l] - log_kT, l, N_L);
+        if (ATM == 1) I_E = bb_intensity(s_E[e] / zst, kT);
+        else I_E = slab_ctx_eval(hot, s_logE[e] - zst - log_kT, ms_hot);
         if (BEAM)                         // hot_wrapper.pyx:155-199 (options 1-3); kept out of line: rarely used
-          I_E = profile_beaming<ATM>(a.beam_opt, hot, I_E, s_E[e], s_logE[e], s_Z[l], s_abb[l], kT, log_kT, dh[10],
+          I_E = profile_beaming<ATM>(a.beam_opt, hot, I_E, s_E[e], s_logE[e], zst, abb, kT, log_kT, dh[10],
                                      a.srcParams + (a.params_per_cell ? (cell0 + ih[1]) : ring) * a.n_params);
         double corr = 0.0;
-        if (CORR == 1) {
-          const double Z = (ATM == 2) ? exp10(s_Z[l]) : s_Z[l];
-          corr = bb_intensity(s_E[e] / Z, kT_c) * norm_c;
-        } else if (CORR == 2) {
-          const double logZ = (ATM == 2) ? s_Z[l] : log10(s_Z[l]);
-          corr = slab_ctx_eval(els, s_logE[e] - logZ - log_kT_c, l, N_L) * norm_c;
-        }
-        val = (I_E * norm - corr) * geom;                          // pyx:478
+        if (CORR == 1) corr = bb_intensity(s_E[e] / Zlin, kT_c) * norm_c;
+        else if (CORR == 2) corr = slab_ctx_eval(els, s_logE[e] - Zlog - log_kT_c, ms_els) * norm_c;
+        s_y[e * N_L + l] = (I_E * norm - corr) * geom;                 // pyx:478 (energies past ne repeat the first)
       }
-      s_y[e * N_L + l] = val;
     }
     __syncthreads();
     // ---- (2) phase-spline coefficients + positivity flags (pyx:566-569) ----------------------
@@ -1099,10 +1081,10 @@ cudaError_t launch_azinv_geometry(const AzinvArgs& a, cudaStream_t stream) {
 }
 
 static size_t flux_smem_bytes(const AzinvArgs& a, int atm, int corr) {
-  size_t d = 2ul * a.n_azi + 5ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 5;
-  if (atm == 2) d += 4ul * a.n_leaves + 5ul * a.slab_ne_max + a.hot.nmu + (size_t)a.hot.nmu * a.slab_ne_max;
-  if (corr == 2) d += 4ul * a.n_leaves + 5ul * a.slab_ne_max + a.els.nmu + (size_t)a.els.nmu * a.slab_ne_max;
-  return d * sizeof(double) + 3ul * a.n_leaves * sizeof(int);
+  size_t d = 2ul * a.n_azi + 2ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 5;
+  if (atm == 2) d += 5ul * a.slab_ne_max + a.hot.nmu + (size_t)a.hot.nmu * a.slab_ne_max;
+  if (corr == 2) d += 5ul * a.slab_ne_max + a.els.nmu + (size_t)a.els.nmu * a.slab_ne_max;
+  return d * sizeof(double) + (size_t)a.n_leaves * sizeof(int);
 }
 
 // Doppler spread of log10 Z over one ring allowed for when sizing buffers:
