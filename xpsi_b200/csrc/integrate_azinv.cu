@@ -797,7 +797,7 @@ __device__ __noinline__ double profile_beaming(int beam_opt, const SlabCtx& hot,
 // ATM: hot atmosphere (1 BB, 2 Num4D).  CORR: elsewhere correction (0 none, 1 BB, 2 Num4D)
 // BEAM: 0 = no beaming code at all (keeps the common instantiation free of the call's register pressure)
 template <int ATM, int CORR, int BEAM>
-__global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flux(AzinvArgs a) {
+__global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flux(AzinvArgs a) {
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
   const int i = blockIdx.x / n_chunks;
   const int chunk = blockIdx.x - i * n_chunks;
@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
   double* s_carea = sp; sp += a.n_azi;
   double* s_PH = sp; sp += N_L;
   double* s_aux = sp; sp += N_L;          // 1/h of the leaf intervals
-  double* s_y = sp; sp += kNEC * N_L;
+  // profile values live in slot 0 of their coefficient quad: s_coef[e][l] = (y, b, c, d)
   double* s_coef = sp; sp += (long)kNEC * N_L * 4;
   SlabCtx hot, els;
   if (ATM == 2) sp = slab_ctx_carve(hot, sp, N_L, a.slab_ne_max, a.hot.nmu);
@@ -888,7 +888,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
       const double geom = W[3 * N_L + l];
       if (geom == 0.0) {
 #pragma unroll
-        for (int e = 0; e < kNEC; ++e) s_y[e * N_L + l] = 0.0;
+        for (int e = 0; e < kNEC; ++e) s_coef[((long)e * N_L + l) * 4] = 0.0;
         continue;
       }
       const double zst = W[N_L + l];            // Z for a blackbody hot atmosphere, log10 Z for Num4D
@@ -909,7 +909,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
         double corr = 0.0;
         if (CORR == 1) corr = bb_intensity(s_E[e] / Zlin, kT_c) * norm_c;
         else if (CORR == 2) corr = slab_ctx_eval(els, s_logE[e] - Zlog - log_kT_c, ms_els) * norm_c;
-        s_y[e * N_L + l] = (I_E * norm - corr) * geom;                 // pyx:478 (energies past ne repeat the first)
+        s_coef[((long)e * N_L + l) * 4] = (I_E * norm - corr) * geom;  // pyx:478 (energies past ne repeat the first)
       }
     }
     __syncthreads();
@@ -924,11 +924,11 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 4) k_azinv_flu
       const int per = (N_L - 1 + kBlk - 1) / kBlk;
       const int l0 = blk * per, l1 = min(l0 + per, N_L - 1);
       if (e < ne && l0 < l1) {
-        const double* y = s_y + e * N_L;
+        const View y{s_coef + (long)e * N_L * 4, 4};          // node values: slot 0 of every quad of this energy
         auto emit = [&](int l, double b, double c, double d) {
           const double y0 = y[l];
-          double2* o = reinterpret_cast<double2*>(s_coef + ((long)e * N_L + l) * 4);
-          o[0] = make_double2(y0, b); o[1] = make_double2(c, d);
+          double* o = s_coef + ((long)e * N_L + l) * 4;       // slot 0 (y) is left alone: neighbours read it
+          o[1] = b; *reinterpret_cast<double2*>(o + 2) = make_double2(c, d);
           if (CORR == 0) {
             // Bernstein coefficients of the cubic on [0,h] (end values are the nodes themselves):
             // all >= 0  =>  the spline is >= 0 on the interval.  With the correction active the
@@ -1081,7 +1081,7 @@ cudaError_t launch_azinv_geometry(const AzinvArgs& a, cudaStream_t stream) {
 }
 
 static size_t flux_smem_bytes(const AzinvArgs& a, int atm, int corr) {
-  size_t d = 2ul * a.n_azi + 2ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 5;
+  size_t d = 2ul * a.n_azi + 2ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 4;
   if (atm == 2) d += 5ul * a.slab_ne_max + a.hot.nmu + (size_t)a.hot.nmu * a.slab_ne_max;
   if (corr == 2) d += 5ul * a.slab_ne_max + a.els.nmu + (size_t)a.els.nmu * a.slab_ne_max;
   return d * sizeof(double) + (size_t)a.n_leaves * sizeof(int);
