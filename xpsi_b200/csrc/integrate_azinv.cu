@@ -830,7 +830,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
   SlabCtx hot, els;
   if (ATM == 2) sp = slab_ctx_carve(hot, sp, N_L, a.slab_ne_max, a.hot.nmu);
   if (CORR == 2) sp = slab_ctx_carve(els, sp, N_L, a.slab_ne_max, a.els.nmu);
-  unsigned* s_flag = reinterpret_cast<unsigned*>(sp);
+  unsigned char* s_flag = reinterpret_cast<unsigned char*>(sp);     // [N_L][kNEC]: 1 = cubic may dip below zero
 
   // ---- compact list of the ring's radiating cells (one warp: keeps azimuth order) ------
   if (tid < 32) {
@@ -879,7 +879,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
     // ---- leaf arrays of this image: the lagged phases go to shared memory (every later stage needs them),
     // redshift / mu*eta / geometry factor stay in the registers of the thread that owns the leaf ---------
     const double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
-    for (int l = tid; l < N_L; l += kFluxThreads) { s_PH[l] = W[l]; s_flag[l] = 0u; }
+    for (int l = tid; l < N_L; l += kFluxThreads) s_PH[l] = W[l];
     if (ATM == 2 || CORR == 2) __pipeline_wait_prior(0);          // slab rows have landed (no-op after the first image)
     __syncthreads();
     for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
@@ -923,7 +923,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
       const int e = tid / kBlk, blk = tid - e * kBlk;
       const int per = (N_L - 1 + kBlk - 1) / kBlk;
       const int l0 = blk * per, l1 = min(l0 + per, N_L - 1);
-      if (e < ne && l0 < l1) {
+      if (l0 < l1) {                 // all kNEC energies (a short last chunk repeats its first energy)
         const View y{s_coef + (long)e * N_L * 4, 4};          // node values: slot 0 of every quad of this energy
         auto emit = [&](int l, double b, double c, double d) {
           const double y0 = y[l];
@@ -936,8 +936,8 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
             const double h = s_PH[l + 1] - s_PH[l];
             const double B1 = y0 + b * h * (1.0 / 3.0);
             const double B2 = y0 + h * ((2.0 / 3.0) * b + c * h * (1.0 / 3.0));
-            if (y0 < 0.0 || B1 < 0.0 || B2 < 0.0 || y[l + 1] < 0.0) atomicOr(&s_flag[l], 1u << e);
-          }
+            s_flag[l * kNEC + e] = (y0 < 0.0 || B1 < 0.0 || B2 < 0.0 || y[l + 1] < 0.0) ? 1 : 0;
+          } else s_flag[l * kNEC + e] = 0;
         };
         if (interp_kind == kSteffen) {
           for (int l = l0; l < l1; ++l) {
@@ -978,16 +978,15 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
     if (k < N_P) {
       const double ph_first = s_PH[0], ph_last = s_PH[N_L - 1];
       auto flush = [&](int m, double W0, double W1, double W2, double W3, int c_start, int c_end) {
-        const unsigned fl = s_flag[m];
+        static_assert(kNEC == 8, "one flag byte per energy, read as one 64-bit word");
+        const unsigned long long fl = *reinterpret_cast<const unsigned long long*>(s_flag + (long)m * kNEC);
         const double* cp = s_coef + (long)m * 4;
-        if (fl == 0u) {
+        if (fl == 0ull) {
 #pragma unroll
           for (int g = 0; g < kNEC; ++g) {
-            if (g < ne) {
-              const double2 lo = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4);
-              const double2 hi = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4 + 2);
-              acc[g] += lo.x * W0 + lo.y * W1 + hi.x * W2 + hi.y * W3;
-            }
+            const double2 lo = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4);
+            const double2 hi = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4 + 2);
+            acc[g] += lo.x * W0 + lo.y * W1 + hi.x * W2 + hi.y * W3;
           }
         } else {
           // some energy's cubic may dip below zero on this interval: the reference adds a cell
@@ -1001,7 +1000,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
             const double A = s_carea[cc];
 #pragma unroll
             for (int g = 0; g < kNEC; ++g) {
-              if (g < ne && ((fl >> g) & 1u)) {
+              if ((fl >> (8 * g)) & 1ull) {
                 const double* cg = cp + (long)g * N_L * 4;
                 const double f = cg[0] + d * (cg[1] + d * (cg[2] + d * cg[3]));
                 if (f > 0.0) acc[g] += A * f;
@@ -1010,7 +1009,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
           }
 #pragma unroll
           for (int g = 0; g < kNEC; ++g) {
-            if (g < ne && !((fl >> g) & 1u)) {
+            if (!((fl >> (8 * g)) & 1ull)) {
               const double* cg = cp + (long)g * N_L * 4;
               acc[g] += cg[0] * W0 + cg[1] * W1 + cg[2] * W2 + cg[3] * W3;
             }
@@ -1084,7 +1083,7 @@ static size_t flux_smem_bytes(const AzinvArgs& a, int atm, int corr) {
   size_t d = 2ul * a.n_azi + 2ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 4;
   if (atm == 2) d += 5ul * a.slab_ne_max + a.hot.nmu + (size_t)a.hot.nmu * a.slab_ne_max;
   if (corr == 2) d += 5ul * a.slab_ne_max + a.els.nmu + (size_t)a.els.nmu * a.slab_ne_max;
-  return d * sizeof(double) + (size_t)a.n_leaves * sizeof(int);
+  return d * sizeof(double) + (size_t)a.n_leaves * kNEC;
 }
 
 // Doppler spread of log10 Z over one ring allowed for when sizing buffers:
