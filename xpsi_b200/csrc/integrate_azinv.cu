@@ -936,7 +936,23 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
             const double h = s_PH[l + 1] - s_PH[l];
             const double B1 = y0 + b * h * (1.0 / 3.0);
             const double B2 = y0 + h * ((2.0 / 3.0) * b + c * h * (1.0 / 3.0));
-            s_flag[l * kNEC + e] = (y0 < 0.0 || B1 < 0.0 || B2 < 0.0 || y[l + 1] < 0.0) ? 1 : 0;
+            const double y1 = y[l + 1];
+            bool neg = (y0 < 0.0 || y1 < 0.0);
+            if (!neg && (B1 < 0.0 || B2 < 0.0)) {
+              // Bernstein is only sufficient: look at the cubic's interior critical points before giving up
+              // the fast path (b + 2 c t + 3 d t^2 = 0)
+              auto below = [&](double t) -> bool {
+                return t > 0.0 && t < h && (y0 + t * (b + t * (c + t * d))) < 0.0;
+              };
+              if (d != 0.0) {
+                const double disc = c * c - 3.0 * b * d;
+                if (disc >= 0.0) {
+                  const double sq = sqrt(disc), i3d = 1.0 / (3.0 * d);
+                  neg = below((-c - sq) * i3d) || below((-c + sq) * i3d);
+                }
+              } else if (c != 0.0) neg = below(-b / (2.0 * c));
+            }
+            s_flag[l * kNEC + e] = neg ? 1 : 0;
           } else s_flag[l * kNEC + e] = 0;
         };
         if (interp_kind == kSteffen) {
