@@ -386,4 +386,11 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=512, help="parameter vectors per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
-    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
+    rc = main_reference(a) if a.impl == "reference" else main_ours(a)
+    try:                                   # leave NCCL cleanly under torchrun
+        import torch.distributed as _dist
+        if _dist.is_available() and _dist.is_initialized():
+            _dist.destroy_process_group()
+    except Exception:
+        pass
+    sys.exit(rc)
