@@ -86,20 +86,28 @@ cudaError_t launch_energy_integrator(EnergyIntegArgs a, cudaStream_t stream) {
 // ---------------------------------------------------------------------------
 // Response contraction.  out[col][chan][p] = sum_k R[chan][in0+k] * X[col*P+p][k]
 //
-// fp64 has no tcgen05 kind, so this is a SIMT DFMA GEMM shaped for the problem:
-// M = channels (a few hundred), N = (theta, component, phase) columns (huge), K =
-// input intervals.  64(M) x 128(N) output tile per CTA, 16-deep K slabs staged in
-// shared memory k-major (conflict-free, 128-bit reads), each thread a 4x8 register
-// block, next slab prefetched into registers while the current one is multiplied.
-// A response is zero above the redistribution band: k_range gives, per 64-channel
-// tile, the span of input intervals with any non-zero entry, and the K loop only
-// visits that span (adding zeros changes nothing).
+// M = channels (a few hundred), N = (theta, component, phase) columns (huge), K = input intervals: a real
+// GEMM once batched, and the one place of the path where tensor cores apply -- in fp64, i.e. mma.sync
+// m8n8k4 (tcgen05 has no fp64 kind).  64(M) x 128(N) output tile per CTA, 16-deep K slabs staged through
+// registers into shared memory (next slab prefetched while the current one is multiplied).  A response is
+// zero above the redistribution band: k_range gives, per 64-channel tile, the span of input intervals with
+// any non-zero entry, and the K loop only visits that span (adding zeros changes nothing).
+//
+// Measured on this B200: DMMA 37 TFLOP/s vs DFMA 34 TFLOP/s from registers, so the pipe ceiling is the
+// same; what changes is the operand traffic.  A SIMT kernel needs (r + c) * 8 bytes of shared memory per
+// r x c FMAs of a thread tile and the 128 B/clk shared-memory path capped the earlier 4 x 8 (and an 8 x 8)
+// register-tile version at 42 % of the pipe (ncu: stalls on LDS data; profiles/r01f_k_fold_ncu_full.txt).
+// With a 32 x 32 warp tile built from 4 x 4 DMMA tiles a k-step of 4 costs 8 LDS.64 per lane for 16 DMMAs:
+// 0.5 byte per FMA, four times under the limit.  Both operands sit in shared memory as [row][k] with k
+// contiguous -- the layout of the response matrix and of the k-major signal -- so the staging stores need
+// no transposition; a row stride of 20 doubles makes every fragment read the minimal two wavefronts.
 // ---------------------------------------------------------------------------
 constexpr int kBM = 64, kBN = 128, kBK = 16, kFoldThreads = 256;
+constexpr int kMS = kBK + 4;                     // padded row stride (doubles)
 
-__global__ void __launch_bounds__(kFoldThreads, 2) k_fold(FoldArgs a) {
-  __shared__ __align__(16) double As[kBK][kBM];
-  __shared__ __align__(16) double Bs[kBK][kBN];
+__global__ void __launch_bounds__(kFoldThreads, 2) k_fold_mma(FoldArgs a) {
+  __shared__ __align__(16) double As[kBM][kMS];
+  __shared__ __align__(16) double Bs[kBN][kMS];
   const int mt = blockIdx.y;
   const int m0 = mt * kBM;                       // channel tile
   const long n0 = (long)blockIdx.x * kBN;        // (col,p) tile
@@ -108,17 +116,15 @@ __global__ void __launch_bounds__(kFoldThreads, 2) k_fold(FoldArgs a) {
   int kb = 0, ke = K;
   if (a.k_range) { kb = a.k_range[2 * mt]; ke = a.k_range[2 * mt + 1]; }
   kb = (kb / kBK) * kBK;
-  // thread tile 4 rows x 8 columns (4 pairs); a warp covers 4 row groups x 8 column groups so that every
-  // shared-memory read of the multiply loop is one wavefront: the A read touches 4 x 32 contiguous bytes,
-  // each B read 8 x 16 contiguous bytes (ncu: shared-memory bandwidth was the limiter with 2 x 16)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tx = (warp & 1) * 8 + (lane & 7), ty = (warp >> 1) * 4 + (lane >> 3);
-  double acc[4][8];
+  const int wm = warp >> 2, wn = warp & 3;       // 2 x 4 warps, 32 x 32 outputs each
+  const int fr = lane >> 2, fk = lane & 3;       // fragment row / k index of this lane
+  double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-  // loaders: A 64 rows x 16 k (4 per thread), B 128 rows x 16 k (8 per thread); k fastest in memory
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  // loaders: A 64 rows x 16 k (4 per thread), B 128 rows x 16 k (8 per thread); k fastest in memory and in smem
   const int ar = threadIdx.x / 4, ak = (threadIdx.x % 4) * 4;
   const int br = threadIdx.x / 2, bk = (threadIdx.x % 2) * 8;
   const bool a_ok = (m0 + ar) < a.n_chan;
@@ -134,44 +140,43 @@ __global__ void __launch_bounds__(kFoldThreads, 2) k_fold(FoldArgs a) {
   };
   if (kb < ke) fetch(kb);
   for (int k0 = kb; k0 < ke; k0 += kBK) {
+    *reinterpret_cast<double2*>(&As[ar][ak]) = make_double2(ra[0], ra[1]);
+    *reinterpret_cast<double2*>(&As[ar][ak + 2]) = make_double2(ra[2], ra[3]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) As[ak + u][ar] = ra[u];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) Bs[bk + u][br] = rb[u];
+    for (int u = 0; u < 8; u += 2) *reinterpret_cast<double2*>(&Bs[br][bk + u]) = make_double2(rb[u], rb[u + 1]);
     __syncthreads();
     if (k0 + kBK < ke) fetch(k0 + kBK);          // overlaps the multiply below
 #pragma unroll
-    for (int k = 0; k < kBK; ++k) {
-      const double2 a01 = *reinterpret_cast<const double2*>(&As[k][ty * 4]);
-      const double2 a23 = *reinterpret_cast<const double2*>(&As[k][ty * 4 + 2]);
-      const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-      double bv[8];
+    for (int k4 = 0; k4 < kBK; k4 += 4) {
+      double fa[4], fb[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // columns owned by a thread are {2 tx, 2 tx + 1} + 32 j: a warp reads 16 consecutive
-        // 16-byte words per j -- no bank conflicts
-        const double2 b2 = *reinterpret_cast<const double2*>(&Bs[k][tx * 2 + 32 * j]);
-        bv[2 * j] = b2.x; bv[2 * j + 1] = b2.y;
-      }
+      for (int i = 0; i < 4; ++i) fa[i] = As[wm * 32 + i * 8 + fr][k4 + fk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) fb[j] = Bs[wn * 32 + j * 8 + fr][k4 + fk];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] += av[i] * bv[j];
+        for (int j = 0; j < 4; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(fa[i]), "d"(fb[j]));
     }
     __syncthreads();
   }
+  // D fragment: row = lane / 4, columns 2 (lane % 4) + {0, 1} of each 8 x 8 tile
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+    const int m = m0 + wm * 32 + i * 8 + fr;
     if (m >= a.n_chan) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const long n = n0 + tx * 2 + 32 * (j >> 1) + (j & 1);
-      if (n >= N) continue;
-      const long col = n / a.n_phases;
-      const int p = (int)(n - col * a.n_phases);
-      a.out[(col * a.n_chan + m) * a.n_phases + p] = acc[i][j];
-    }
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const long n = n0 + wn * 32 + j * 8 + 2 * fk + c;
+        if (n >= N) continue;
+        const long col = n / a.n_phases;
+        const int p = (int)(n - col * a.n_phases);
+        a.out[(col * a.n_chan + m) * a.n_phases + p] = acc[i][j][c];
+      }
   }
 }
 
@@ -180,7 +185,7 @@ int fold_tile_rows() { return kBM; }
 cudaError_t launch_fold(FoldArgs a, cudaStream_t stream) {
   const long N = (long)a.n_cols * a.n_phases;
   dim3 grid((unsigned)((N + kBN - 1) / kBN), (unsigned)((a.n_chan + kBM - 1) / kBM));
-  k_fold<<<grid, kFoldThreads, 0, stream>>>(a);
+  k_fold_mma<<<grid, kFoldThreads, 0, stream>>>(a);
   return cudaGetLastError();
 }
 
