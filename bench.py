@@ -120,7 +120,7 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def flops_per_eval(work, n_evals, shape, n_regions, n_quad=192, n_newton=3):
+def flops_per_eval(work, n_evals, shape, n_regions, n_quad=65, n_newton=3):
     """F_total of SURVEY.md s8d from the integrator's measured work counters."""
     N_E, N_P, N_L = shape["n_energies"], shape["n_phases"], shape["n_phases"]
     N_in, N_chan, N_bins = shape["n_in"], shape["n_chan"], shape["n_bins"]
