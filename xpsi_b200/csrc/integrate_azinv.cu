@@ -653,13 +653,28 @@ __global__ void __launch_bounds__(kMomThreads) k_azinv_moments(AzinvArgs a) {
   double* s_cphi = smem;
   double* s_carea = s_cphi + a.n_azi;
   double* s_PH = s_carea + a.n_azi;
+  unsigned char* s_lit = reinterpret_cast<unsigned char*>(s_PH + N_L);      // [N_L] leaf lit, then [N_L] interval live
+  unsigned char* s_live = s_lit + N_L;
   if (tid < 32) { const int n = compact_cells(a, ring * a.n_azi, A_, tid, s_cphi, s_carea); if (tid == 0) s_ncell = n; }
   const int k = tid;
   const double phk = (k < N_P) ? a.phases[k] : 0.0;
   for (int I = 0; I < n_img; ++I) {
     __syncthreads();
     const double* W = leaf_ptr(a.ws_leaf, ring, a.n_img_max, I, N_L);
-    for (int l = tid; l < N_L; l += kMomThreads) s_PH[l] = W[l];
+    for (int l = tid; l < N_L; l += kMomThreads) { s_PH[l] = W[l]; s_lit[l] = (W[3 * N_L + l] != 0.0) ? 1 : 0; }
+    __syncthreads();
+    // An interval whose six surrounding leaves (m-2 .. m+3, periodic) are all dark carries an identically zero
+    // spline for either interpolant (Akima's node slopes use two intervals on each side): its entries are
+    // dropped, which is most of the work of the higher image orders.
+    for (int m = tid; m < N_L - 1; m += kMomThreads) {
+      int live = 0;
+      for (int dlt = -2; dlt <= 3; ++dlt) {
+        int l = m + dlt;
+        if (l < 0) l += N_L - 1; else if (l > N_L - 1) l -= N_L - 1;
+        live |= s_lit[l];
+      }
+      s_live[m] = (unsigned char)live;
+    }
     __syncthreads();
     if (k >= N_P) continue;
     const long slot = ring * a.n_img_max + I;
@@ -668,6 +683,7 @@ __global__ void __launch_bounds__(kMomThreads) k_azinv_moments(AzinvArgs a) {
     int cnt = 0;
     walk_cells(phk, s_PH, N_L, s_cphi, s_carea, s_ncell, a.status + q,
                [&](int m, double W0, double W1, double W2, double W3, int c0, int c1) {
+                 if (!s_live[m]) return;
                  if (cnt < cap) {
                    double* e = mom + (long)cnt * 4 * N_P + k;
                    e[0] = W0; e[N_P] = W1; e[2 * N_P] = W2; e[3 * N_P] = W3;
@@ -1185,7 +1201,7 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   }
   if (a.ws_mom) {
     if (!a.ws_meta || !a.ws_cnt || a.mom_cap < 1 || a.n_azi > 0xffff) return cudaErrorInvalidValue;
-    const size_t msm = (2ul * a.n_azi + a.n_leaves) * sizeof(double);
+    const size_t msm = (2ul * a.n_azi + a.n_leaves) * sizeof(double) + 2ul * a.n_leaves;
     k_azinv_moments<<<ggrid, kMomThreads, msm, stream>>>(a);
   }
   if ((err = cudaGetLastError()) != cudaSuccess) return err;
