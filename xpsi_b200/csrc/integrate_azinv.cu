@@ -1018,7 +1018,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
           for (int g = 0; g < kNEC; ++g) {
             const double2 lo = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4);
             const double2 hi = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4 + 2);
-            acc[g] += lo.x * W0 + lo.y * W1 + hi.x * W2 + hi.y * W3;
+            acc[g] = fma(hi.y, W3, fma(hi.x, W2, fma(lo.y, W1, fma(lo.x, W0, acc[g]))));      // 4 DFMA
           }
         } else {
           // some energy's cubic may dip below zero on this interval: the reference adds a cell
