@@ -69,3 +69,20 @@ xpsi.set_phase_interpolant('Akima')
 np.savez_compressed(os.path.join(HERE, "options.npz"), **out)
 print("options.npz", os.path.getsize(os.path.join(HERE, "options.npz")) // 1024, "KiB",
       "disc effect", float(np.max(np.abs(out["disk_flux_20000"] / out["disk_flux_none"].max() - out["disk_flux_none"] / out["disk_flux_none"].max()))))
+
+# ---- odd number of leaves (the middle leaf is its own mirror, pyx:416-419) and N_P != N_L, both integrators ----
+from xpsi.cellmesh.integrator import integrate as integrate_general  # noqa: E402
+out = dict(np.load(os.path.join(HERE, "options.npz")))
+for nl, nph in ((65, 50), (33, 128)):
+    a = args_of(c1, "int0_", ())
+    a[19] = np.ascontiguousarray(c1["int0_energies"][::8])            # 16 energies keep the fixture small
+    a[20] = np.linspace(0.0, 2.0 * np.pi, nl)
+    a[21] = 2.0 * np.pi * np.linspace(0.0, 1.0, nph)
+    s, f = integrate(*a)
+    assert s == 0
+    out["odd_%d_%d_azinv" % (nl, nph)] = np.array(f)
+    s, f = integrate_general(*a)
+    assert s == 0
+    out["odd_%d_%d_general" % (nl, nph)] = np.array(f)
+np.savez_compressed(os.path.join(HERE, "options.npz"), **out)
+print("options.npz (+odd leaf counts)", os.path.getsize(os.path.join(HERE, "options.npz")) // 1024, "KiB")

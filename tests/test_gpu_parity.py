@@ -805,3 +805,19 @@ def test_marginal_likelihood_with_more_than_32_phase_bins(c1):
         assert abs(res[0] - float(d["mbins%d_lnL" % nb])) < LNL_ATOL
         assert rel_err(res[1], d["mbins%d_expected" % nb]) < PULSE_RTOL
         assert rel_err(res[2], d["mbins%d_bg" % nb]) < 1e-6
+
+
+def test_odd_leaf_counts_and_unequal_phase_grids(c1):
+    """N_L odd (the middle leaf is its own mirror, pyx:416-419), N_P != N_L up to the 128-phase limit."""
+    from test_oracle import _odd_leaf_cases
+    from xpsi_b200.cellmesh.integrator_for_azimuthal_invariance import integrate
+    from xpsi_b200.cellmesh.integrator import integrate as integrate_general
+    for nl, nph, a, ref_az, ref_gen in _odd_leaf_cases(c1):
+        status, flux = integrate(*a)
+        err = _pulse_err(flux, ref_az)
+        print("N_L", nl, "N_P", nph, "azimuthal-invariance rel err", err)
+        assert status == 0 and err < PULSE_RTOL
+        status, flux = integrate_general(*a)
+        err = _pulse_err(flux, ref_gen)
+        print("N_L", nl, "N_P", nph, "general rel err", err)
+        assert status == 0 and err < PULSE_RTOL

@@ -255,3 +255,24 @@ def _point_err(out, ref):
 def test_oracle_intensity_seam():
     for name, a, ref in _intensity_cases():
         assert _point_err(orc.intensity(*a), ref) < 1e-9, name
+
+
+def _odd_leaf_cases(c1):
+    """odd leaf counts (the middle leaf is its own mirror) and N_P != N_L; reference outputs in options.npz"""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "options.npz"))
+    cases = []
+    for nl, nph in ((65, 50), (33, 128)):
+        a = list(_integrate_args(c1, "int0_", ()))
+        a[19] = np.ascontiguousarray(c1["int0_energies"][::8])
+        a[20] = np.linspace(0.0, 2.0 * np.pi, nl)
+        a[21] = 2.0 * np.pi * np.linspace(0.0, 1.0, nph)
+        cases.append((nl, nph, a, d["odd_%d_%d_azinv" % (nl, nph)], d["odd_%d_%d_general" % (nl, nph)]))
+    return cases
+
+
+def test_oracle_odd_leaf_counts(c1):
+    for nl, nph, a, ref_az, ref_gen in _odd_leaf_cases(c1):
+        status, flux = orc.integrate(*a)
+        assert status == 0 and _pulse_err(flux, ref_az) < 1e-12, (nl, nph)
+        status, flux = orc.integrate_general(*a)
+        assert status == 0 and _pulse_err(flux, ref_gen) < 1e-12, (nl, nph)
