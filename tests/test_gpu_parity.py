@@ -821,3 +821,35 @@ def test_odd_leaf_counts_and_unequal_phase_grids(c1):
         err = _pulse_err(flux, ref_gen)
         print("N_L", nl, "N_P", nph, "general rel err", err)
         assert status == 0 and err < PULSE_RTOL
+
+
+def test_known_answer_from_parameters_entirely_on_gpu(c1):
+    """The reference's published known answer (xpsi/tests/test_likelihood.py:134: lnL = -47881.27817666349 for
+    theta = [1.4, 10, 1, cos 60deg, 0, 70deg, 0.75, 6.8], blackbody ST model, 314 Hz) reproduced from the
+    parameter vector with every stage -- embed, integrate, fold, likelihood -- on the GPU."""
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.pipeline import BatchedLikelihood
+    matrix, edges = syn.c1_response()[:2]
+    d, p = c1, "marg_"
+    pipe = BatchedLikelihood(member_component=[0], max_rings=64, max_azi=64, n_rays=int(c1["int0_numRays"]),
+                             energies=c1["int0_energies"], leaves=c1["int0_leaves"], phases=c1["int0_phases"],
+                             hot_atm_ext=1, image_order_limit=int(c1["int0_image_order_limit"]), response=matrix,
+                             energy_edges=edges, counts=d[p + "counts"], data_phases=d[p + "phases"],
+                             exposure_time=float(d[p + "exposure_time"]), support=d[p + "support"], max_batch=4)
+    th = c1["theta"]
+    B = 3
+    sb = pipe.new_spot_batch(B, 314.0, num_cells=1024, min_sqrt_num_cells=16, max_sqrt_num_cells=64)
+    one = np.ones(B)
+    sb.set_spacetime(th[0] * one, th[1] * one, th[2] * one, th[3] * one, 314.0)
+    sb.phase_shifts[:, 0] = th[4]
+    sb.colatitude[:, 0], sb.ang_radius[:, 0], sb.temperature[:, 0] = th[5], th[6], th[7]
+    sb.phi_shift[:, 0] = np.pi                                         # is_antiphased (main.py:122-128)
+    lnL, status = pipe.eval_spots(sb)
+    known = float(c1["known_answer_lnL"])
+    print("known-answer lnL from theta", lnL, "reference", known, "diff", lnL - known)
+    assert (status == 0).all()
+    assert known == -47881.27817666349
+    assert np.max(np.abs(lnL - known)) < 1e-5 * abs(known)            # the reference's own rtol
+    assert np.max(np.abs(lnL - float(c1["lnL_total"]))) < LNL_ATOL    # and the 1e-6 bar against the shim build
+    e = pipe.fetch_embed(B)
+    _check_embed(e, 1, lambda k: c1["int0_" + k], "C1 spot")
