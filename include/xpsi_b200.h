@@ -258,6 +258,10 @@ typedef struct {
    * region share num_cells (mesh_tools.pyx:1040-1060): partner[m] = index of the other member or -1,
    * is_cede[m] = 1 for the ceding member                                                            */
   const int* partner; const int* is_cede;         /* [M] */
+  /* optional (NULL: zeros) when the pipeline was created with n_params > 2: the uniform local variables
+   * that follow (log T, log g) in srcCellParams, e.g. the beaming parameters (abb, bbb, cbb, dbb, nimu) of
+   * examples_modeling_tutorial/modules/CustomHotRegion_Beaming.py:149-178                            */
+  const double* extra_params;                     /* [B*M][n_params-2] */
 } xpsi_b200_spot_batch;
 
 /* ---- optional model components of the batched pipeline ---------------------------------------------

@@ -853,3 +853,32 @@ def test_known_answer_from_parameters_entirely_on_gpu(c1):
     assert np.max(np.abs(lnL - float(c1["lnL_total"]))) < LNL_ATOL    # and the 1e-6 bar against the shim build
     e = pipe.fetch_embed(B)
     _check_embed(e, 1, lambda k: c1["int0_" + k], "C1 spot")
+
+
+def test_theta_level_pipeline_with_beaming_parameters(m2):
+    """Custom hot regions with beaming parameters (CustomHotRegion_Beaming.py:149-178: srcCellParams columns
+    T, g, abb, bbb, cbb, dbb, nimu) through the parameter-level pipeline; the secondary's flux is checked against
+    the reference integrator's output for the same beaming parameters (options.npz)."""
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.pipeline import BatchedLikelihood
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "options.npz"))
+    matrix, edges = syn.nicer_like_response()[:2]
+    beam = d["beam_params_m2"][0, 0, 2:]
+    for opt in (2, 3):
+        pipe = BatchedLikelihood(member_component=[0, 1], max_rings=64, max_azi=64, n_rays=200,
+                                 energies=m2["t0_int0_energies"], leaves=m2["t0_int0_leaves"],
+                                 phases=m2["t0_int0_phases"], hot_atm_ext=2, hot_atmosphere=syn.nsx_like_table(),
+                                 image_order_limit=3, response=matrix, energy_edges=edges, counts=m2["counts"],
+                                 data_phases=np.linspace(0.0, 1.0, 33), exposure_time=syn.M2_EXPOSURE,
+                                 n_params=7, max_batch=2)
+        pipe.set_extras(beam_opt=opt)
+        spots = syn.m2_spot_batch(pipe, np.array([m2["t0_theta"], m2["t0_theta"]]))
+        spots.extra_params = np.tile(beam, (2, 2, 1))
+        lnL, status = pipe.eval_spots(spots)
+        assert (status == 0).all() or np.isin(status, (0, 11)).all()
+        flux = pipe.fetch(2, folded=False, expected=False)[0]
+        got = flux[3] / (m2["t0_int0_energies"][:, None] * 1.60217662e-16)      # theta 1, member 1
+        err = _pulse_err(got, d["beam%d_m2" % opt])
+        print("beam_opt", opt, "parameter-level flux vs reference integrator rel err", err, "lnL", lnL)
+        assert err < PULSE_RTOL
+        assert abs(lnL[0] - lnL[1]) < 1e-6

@@ -94,7 +94,7 @@ class SpotBatch(C.Structure):
         ("phi_shift", c_double_p), ("mode_frequency", C.c_double),
         ("num_cells", C.c_int), ("min_sqrt_num_cells", C.c_int), ("max_sqrt_num_cells", C.c_int),
         ("hole_radius", c_double_p), ("hole_colatitude", c_double_p), ("hole_azimuth", c_double_p),
-        ("partner", c_int_p), ("is_cede", c_int_p),
+        ("partner", c_int_p), ("is_cede", c_int_p), ("extra_params", c_double_p),
     ]
 
 

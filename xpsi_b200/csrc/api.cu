@@ -643,7 +643,7 @@ struct xpsi_b200_pipeline {
   Dev<double> ws_leaf, ws_hdr, ws_slab, ws_mom; Dev<int> ws_ihdr, ws_cnt; Dev<int2> ws_meta;
   int mom_cap = 0;
   // embed inputs / scratch
-  Dev<double> e_Req, e_rs, e_eps, e_zeta, e_colat, e_rad, e_temp, e_phish, e_maxAlpha, e_hrad, e_hcolat, e_hazi;
+  Dev<double> e_Req, e_rs, e_eps, e_zeta, e_colat, e_rad, e_temp, e_phish, e_maxAlpha, e_hrad, e_hcolat, e_hazi, e_extra;
   Dev<int> e_partner, e_iscede;
   int count_work = 0;
   int embed_status_valid = 0;        // status[] already carries embed failures for this batch
@@ -967,7 +967,6 @@ int xpsi_b200_pipeline_set_extras(xpsi_b200_pipeline* p, const xpsi_b200_pipelin
       return fail(XPSI_B200_EUNSUPPORTED, "else_atm_ext must be 1 (BB) or 2 (Num4D)");
     if (x->else_atm_ext == XPSI_B200_ATM_NUM4D && !x->elsewhere_atmosphere)
       return fail(XPSI_B200_EINVAL, "Num4D elsewhere needs a preloaded atmosphere");
-    if (c.n_params != 2 && x->beam_opt == 0) return fail(XPSI_B200_EUNSUPPORTED, "elsewhere needs n_params == 2");
     if (c.n_energies > 256) return fail(XPSI_B200_EINVAL, "elsewhere supports at most 256 energies");
     const size_t B = p->max_batch, Q = B * c.n_members;
     CK(p->x_temp.alloc(B)); CK(p->x_area.alloc(B)); CK(p->x_radial.alloc(B * n)); CK(p->x_rsr.alloc(B * n));
@@ -1059,7 +1058,7 @@ int xpsi_b200_pipeline_eval(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch*
 int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200_spot_batch* h) {
   if (!p || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
   const xpsi_b200_pipeline_config& c = p->cfg;
-  if (c.n_params != 2) return fail(XPSI_B200_EUNSUPPORTED, "spot embed needs n_params == 2 (log T, log g)");
+  if (c.n_params < 2) return fail(XPSI_B200_EUNSUPPORTED, "spot embed needs n_params >= 2 (log T, log g, ...)");
   const size_t M = c.n_members, Q = (size_t)B * M;
   CK(p->omega.upload(h->omega, B)); CK(p->inclination.upload(h->inclination, B)); CK(p->d_sq.upload(h->d_sq, B));
   CK(p->shifts.upload(h->phase_shifts, (size_t)B * c.n_components));
@@ -1071,6 +1070,7 @@ int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200
     CK(p->e_hrad.upload(h->hole_radius, Q)); CK(p->e_hcolat.upload(h->hole_colatitude, Q));
     CK(p->e_hazi.upload(h->hole_azimuth, Q));
   }
+  if (h->extra_params && c.n_params > 2) CK(p->e_extra.upload(h->extra_params, Q * (c.n_params - 2)));
   if (h->partner) {
     if (!h->is_cede) return fail(XPSI_B200_EINVAL, "partner needs is_cede");
     for (size_t m = 0; m < M; ++m)
@@ -1088,6 +1088,7 @@ int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200
   a.colatitude = p->e_colat.p; a.ang_radius = p->e_rad.p; a.temperature = p->e_temp.p; a.phi_shift = p->e_phish.p;
   if (h->hole_radius) { a.hole_radius = p->e_hrad.p; a.hole_colatitude = p->e_hcolat.p; a.hole_azimuth = p->e_hazi.p; }
   if (h->partner) { a.partner = p->e_partner.p; a.is_cede = p->e_iscede.p; }
+  if (h->extra_params && c.n_params > 2) a.extra_params = p->e_extra.p;
   a.n_rings = p->n_rings.p; a.n_azi = p->n_azi.p; a.cellArea = p->cellArea.p; a.phi = p->phi.p; a.theta = p->theta.p;
   a.radial = p->radial.p; a.r_s_over_r = p->rsr.p; a.srcParams = p->params.p; a.cos_gamma = p->cgamma.p;
   a.maxAlpha = p->e_maxAlpha.p; a.deflection = p->defl.p; a.cos_alpha = p->calpha.p; a.lag = p->lag.p;

@@ -502,11 +502,18 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
     a.r_s_over_r[ring0 + i] = r_s / (rn * R_eq);                   // HotRegion.py:913
     a.cos_gamma[ring0 + i] = cg;
     a.maxAlpha[ring0 + i] = kHalfPi + acos(cg);                     // mesh.pyx:253
-    a.srcParams[(ring0 + i) * 2 + 0] = a.temperature[q];            // HotRegion.py:965-994
-    a.srcParams[(ring0 + i) * 2 + 1] = effective_gravity(mu, R_eq, zeta, eps);
+    const int np_ = a.n_params;
+    double* sp_ = a.srcParams + (ring0 + i) * np_;
+    sp_[0] = a.temperature[q];                                      // HotRegion.py:965-994
+    sp_[1] = effective_gravity(mu, R_eq, zeta, eps);
+    // further uniform local variables of a custom hot region, e.g. the beaming parameters of
+    // examples_modeling_tutorial/modules/CustomHotRegion_Beaming.py:149-178
+    for (int x = 2; x < np_; ++x) sp_[x] = a.extra_params ? a.extra_params[(long)q * (np_ - 2) + (x - 2)] : 0.0;
     if (a.corrParams) {      // elsewhere parameters on the spot's mesh (HotRegion.py:1019-1031, Elsewhere.py:308-331)
-      a.corrParams[(ring0 + i) * 2 + 0] = a.else_temperature[b];
-      a.corrParams[(ring0 + i) * 2 + 1] = a.srcParams[(ring0 + i) * 2 + 1];
+      double* cp_ = a.corrParams + (ring0 + i) * np_;
+      cp_[0] = a.else_temperature[b];
+      cp_[1] = sp_[1];
+      for (int x = 2; x < np_; ++x) cp_[x] = 0.0;
     }
   }
   if (tid == 0) { a.n_rings[q] = n; a.n_azi[q] = n; }
@@ -781,7 +788,7 @@ cudaError_t launch_embed_closed(ClosedMeshArgs a, cudaStream_t stream) {
 }
 
 cudaError_t launch_embed_spots(EmbedArgs a, cudaStream_t stream) {
-  if (a.max_rings > 128 || a.n_params != 2) return cudaErrorInvalidValue;
+  if (a.max_rings > 128 || a.n_params < 2) return cudaErrorInvalidValue;
   k_spot_mesh<<<a.B * a.M, kMeshThreads, 0, stream>>>(a);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return err;

@@ -103,8 +103,9 @@ struct EmbedArgs {
   // pairing of superseding / ceding members that share num_cells (mesh_tools.pyx:1040-1060)
   const double* hole_radius; const double* hole_colatitude; const double* hole_azimuth;   // [B*M]
   const int* partner; const int* is_cede;         // [M]: partner member index or -1; 1 = ceding member
+  const double* extra_params;                     // nullptr, or [B*M][n_params-2]: local variables after (log T, log g)
   const double* else_temperature;                 // nullptr, or [B]: log10 T of Elsewhere (for corrParams)
-  double* corrParams;                             // nullptr, or [B*M][max_rings][2]: correction parameter rows
+  double* corrParams;                             // nullptr, or [B*M][max_rings][n_params]: correction parameter rows
   // outputs: the integrator's per-instance inputs (padded layout of AzinvArgs)
   int* n_rings; int* n_azi;
   double* cellArea; double* phi; double* theta; double* radial; double* r_s_over_r; double* srcParams;

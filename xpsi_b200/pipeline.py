@@ -112,6 +112,8 @@ class SpotBatch:
         # optional: masking region of each member and superseding / ceding pairing (see set_region)
         self.hole_radius = self.hole_colatitude = self.hole_azimuth = None
         self.partner = self.is_cede = None
+        # optional [B, M, n_params-2]: local variables after (log T, log g), e.g. beaming parameters
+        self.extra_params = None
 
     def set_region(self, super_member, cede_member=None, *, super_colatitude, super_radius, super_temperature,
                    omit_colatitude=None, omit_radius=None, omit_azimuth=None, cede_colatitude=None,
@@ -173,6 +175,11 @@ class SpotBatch:
                 setattr(s, f, _lib.dptr(getattr(self, f)))
         if self.partner is not None:
             s.partner, s.is_cede = _lib.iptr(self.partner), _lib.iptr(self.is_cede)
+        if self.extra_params is not None:
+            self.extra_params = np.ascontiguousarray(self.extra_params, dtype=np.float64)
+            if self.extra_params.shape[:2] != (self.B, self.M):
+                raise ValueError("extra_params must have shape [B, M, n_params-2]")
+            s.extra_params = _lib.dptr(self.extra_params)
         return s
 
 
