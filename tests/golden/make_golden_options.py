@@ -86,3 +86,37 @@ for nl, nph in ((65, 50), (33, 128)):
     out["odd_%d_%d_general" % (nl, nph)] = np.array(f)
 np.savez_compressed(os.path.join(HERE, "options.npz"), **out)
 print("options.npz (+odd leaf counts)", os.path.getsize(os.path.join(HERE, "options.npz")) // 1024, "KiB")
+
+# ---- 'Cubic' interpolants (tools/core.pyx:84-116: cspline_periodic in phase, cspline in energy) ----------
+from xpsi.tools import energy_integrator, energy_interpolator, phase_integrator, phase_interpolator  # noqa: E402
+from xpsi.likelihoods.default_background_marginalisation import eval_marginal_likelihood  # noqa: E402
+out = dict(np.load(os.path.join(HERE, "options.npz")))
+xpsi.set_phase_interpolant('Cubic')
+xpsi.set_energy_interpolant('Cubic')
+try:
+    a = args_of(c1, "int0_", ())
+    a[19] = np.ascontiguousarray(c1["int0_energies"][::8])
+    s, f = integrate(*a); assert s == 0
+    out["cubic_azinv"] = np.array(f)
+    s, f = integrate_general(*a); assert s == 0
+    out["cubic_general"] = np.array(f)
+    sig = np.ascontiguousarray(c1["int0_flux"] / c1["d_sq"])
+    out["cubic_eint"] = energy_integrator(1, sig, c1["eint_log10_energies"], c1["eint_log10_edges"])
+    comp = c1["marg_components_0"]
+    pulse = np.ascontiguousarray(comp[::8])
+    out["cubic_pint"] = phase_integrator(1000.0, c1["marg_phases"], pulse, c1["marg_component_phases_0"], 0.37)
+    out["cubic_pitp"] = phase_interpolator(np.linspace(0.0, 1.0, 41), c1["marg_component_phases_0"], pulse, -0.2)
+    flux4 = np.ascontiguousarray(c1["int0_flux"][:, ::4])
+    log10E = np.log10(c1["int0_energies"])
+    out["cubic_new_E"] = np.linspace(log10E[0], log10E[-1], 57)
+    out["cubic_eitp"] = energy_interpolator(1, flux4, log10E, out["cubic_new_E"])
+    res = eval_marginal_likelihood(float(c1["marg_exposure_time"]), c1["marg_phases"], c1["marg_counts"], (comp,),
+                                   (c1["marg_component_phases_0"],), c1["marg_phase_shifts"], c1["marg_precomp"],
+                                   c1["marg_support"], 1000, 0.0, 1.0e-8, 1.0e-3, 10.0, -1.0e90)
+    out["cubic_lnL"] = np.asarray(res[0])
+    print("Cubic: lnL", res[0])
+finally:
+    xpsi.set_phase_interpolant('Akima')
+    xpsi.set_energy_interpolant('Steffen')
+np.savez_compressed(os.path.join(HERE, "options.npz"), **out)
+print("options.npz (+Cubic interpolants)", os.path.getsize(os.path.join(HERE, "options.npz")) // 1024, "KiB")

@@ -882,3 +882,46 @@ def test_theta_level_pipeline_with_beaming_parameters(m2):
         print("beam_opt", opt, "parameter-level flux vs reference integrator rel err", err, "lnL", lnL)
         assert err < PULSE_RTOL
         assert abs(lnL[0] - lnL[1]) < 1e-6
+
+
+def test_cubic_interpolants(c1):
+    """'Cubic' interpolants (tools/core.pyx:84-116: cspline_periodic in phase, natural cspline in energy) in every
+    kernel that builds a spline: both pulse integrators, energy integrator, phase / energy tools, likelihood."""
+    from xpsi_b200 import tools
+    from xpsi_b200.cellmesh.integrator_for_azimuthal_invariance import integrate
+    from xpsi_b200.cellmesh.integrator import integrate as integrate_general
+    from xpsi_b200.likelihoods import eval_marginal_likelihood
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "options.npz"))
+    a = list(_integrate_args(c1, "int0_", ()))
+    a[19] = np.ascontiguousarray(c1["int0_energies"][::8])
+    comp = c1["marg_components_0"]
+    pulse = np.ascontiguousarray(comp[::8])
+    try:
+        tools.set_phase_interpolant("Cubic")
+        tools.set_energy_interpolant("Cubic")
+        s, f = integrate(*a)
+        err = _pulse_err(f, d["cubic_azinv"]); print("Cubic azimuthal-invariance integrator", err)
+        assert s == 0 and err < PULSE_RTOL
+        s, f = integrate_general(*a)
+        err = _pulse_err(f, d["cubic_general"]); print("Cubic general integrator", err)
+        assert s == 0 and err < PULSE_RTOL
+        sig = np.ascontiguousarray(c1["int0_flux"] / c1["d_sq"])
+        e = rel_err(tools.energy_integrator(1, sig, c1["eint_log10_energies"], c1["eint_log10_edges"]), d["cubic_eint"])
+        print("Cubic energy integrator", e); assert e < PULSE_RTOL
+        e = rel_err(tools.phase_integrator(1000.0, c1["marg_phases"], pulse, c1["marg_component_phases_0"], 0.37),
+                    d["cubic_pint"])
+        print("Cubic phase integrator", e); assert e < PULSE_RTOL
+        e = rel_err(tools.phase_interpolator(np.linspace(0.0, 1.0, 41), c1["marg_component_phases_0"], pulse, -0.2),
+                    d["cubic_pitp"])
+        print("Cubic phase interpolator", e); assert e < PULSE_RTOL
+        flux4 = np.ascontiguousarray(c1["int0_flux"][:, ::4])
+        e = rel_err(tools.energy_interpolator(1, flux4, np.log10(c1["int0_energies"]), d["cubic_new_E"]), d["cubic_eitp"])
+        print("Cubic energy interpolator", e); assert e < PULSE_RTOL
+        res = eval_marginal_likelihood(float(c1["marg_exposure_time"]), c1["marg_phases"], c1["marg_counts"], (comp,),
+                                       (c1["marg_component_phases_0"],), c1["marg_phase_shifts"], c1["marg_precomp"],
+                                       c1["marg_support"], 1000, 0.0, 1.0e-8, 1.0e-3, 10.0, -1.0e90)
+        print("Cubic lnL", res[0], "ref", float(d["cubic_lnL"]))
+        assert abs(res[0] - float(d["cubic_lnL"])) < LNL_ATOL
+    finally:
+        tools.set_phase_interpolant("Akima")
+        tools.set_energy_interpolant("Steffen")

@@ -276,3 +276,15 @@ def test_oracle_odd_leaf_counts(c1):
         assert status == 0 and _pulse_err(flux, ref_az) < 1e-12, (nl, nph)
         status, flux = orc.integrate_general(*a)
         assert status == 0 and _pulse_err(flux, ref_gen) < 1e-12, (nl, nph)
+
+
+def test_oracle_cubic_interpolant(c1):
+    """'Cubic' phase interpolant (cspline_periodic) through both integrators, the energy integrator and the
+    marginal likelihood, against the reference with xpsi.set_phase_interpolant('Cubic')."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "options.npz"))
+    a = list(_integrate_args(c1, "int0_", ()))
+    a[19] = np.ascontiguousarray(c1["int0_energies"][::8])
+    s, f = orc.integrate(*a, phase_interpolant="Cubic")
+    assert s == 0 and _pulse_err(f, d["cubic_azinv"]) < 1e-11
+    s, f = orc.integrate_general(*a, phase_interpolant="Cubic")
+    assert s == 0 and _pulse_err(f, d["cubic_general"]) < 1e-11

@@ -197,8 +197,9 @@ static int integrate_member(
     return fail(XPSI_B200_EUNSUPPORTED, "hot_atm_ext must be 1 (BB) or 2 (Num4D)");
   if (hot_atm_ext == XPSI_B200_ATM_NUM4D && !hot_atmosphere)
     return fail(XPSI_B200_EINVAL, "Num4D needs a preloaded atmosphere");
-  if (phase_interpolant != 0 && phase_interpolant != 1)
-    return fail(XPSI_B200_EUNSUPPORTED, "phase interpolant must be Akima (0) or Steffen (1)");
+  if (phase_interpolant < 0 || phase_interpolant > 2)
+    return fail(XPSI_B200_EINVAL, "phase interpolant must be Akima (0), Steffen (1) or Cubic (2)");
+  if (phase_interpolant == 2 && n_leaves > 260) return fail(XPSI_B200_EUNSUPPORTED, "Cubic interpolant: at most 260 leaves");
   if (n_rings < 1 || n_azi < 1 || numRays < 3 || n_energies < 1 || n_leaves < 5 || n_phases < 1 || n_params < 1)
     return fail(XPSI_B200_EINVAL, "bad dimensions");
 
@@ -424,7 +425,8 @@ static int row_spline_call(const double* x, int n_nodes, const double* y, int n_
                            long ors, long ocs) {
   int rc = ensure_stream();
   if (rc) return rc;
-  if (interp != 0 && interp != 1) return fail(XPSI_B200_EUNSUPPORTED, "interpolant must be Akima (0) or Steffen (1)");
+  if (interp < 0 || interp > 2) return fail(XPSI_B200_EINVAL, "interpolant must be Akima (0), Steffen (1) or Cubic (2)");
+  if (interp == 2 && n_nodes > 260) return fail(XPSI_B200_EUNSUPPORTED, "Cubic interpolant: at most 260 nodes");
   if (n_nodes < (interp == 0 ? 5 : 3) || n_rows < 1 || n_out < 1) return fail(XPSI_B200_EINVAL, "bad dimensions");
   Dev<double> d_x, d_y, d_q, d_o;
   CK(d_x.upload(x, n_nodes)); CK(d_y.upload(y, y_count)); CK(d_q.upload(q, n_q));

@@ -188,6 +188,80 @@ __device__ __forceinline__ void interp_coeffs(int kind, bool periodic, const X& 
   else akima_coeffs(x, y, n, i, periodic, b, c, d);
 }
 
+// ---- C2 cubic spline (GSL cspline / cspline_periodic) -----------------------------------------
+// Unlike Akima / Steffen this interpolant is global: the second-derivative-like coefficients c_i solve a
+// tridiagonal system (natural end conditions c_0 = c_{n-1} = 0) or a cyclic one (periodic: c_0 = c_{n-1}),
+// solved here by one thread with the Thomas algorithm (plus a Sherman-Morrison correction for the cyclic
+// corner entries).  The interval polynomial is y_i + t (b_i + t (c_i + t d_i)) with
+// b_i = dy/dx - dx (c_{i+1} + 2 c_i) / 3,  d_i = (c_{i+1} - c_i) / (3 dx).
+constexpr int kMaxCubicNodes = 260;
+
+template <class X, class Y>
+__device__ void cspline_second(const X& x, const Y& y, int n, bool periodic, double* c) {
+  double cp[kMaxCubicNodes], q[kMaxCubicNodes];
+  if (!periodic) {
+    c[0] = 0.0; c[n - 1] = 0.0;
+    const int m = n - 2;
+    if (m <= 0) return;
+    // row i (unknown c_{i+1}): sub h_i, diag 2 (h_i + h_{i+1}), super h_{i+1}, rhs 3 (dy_{i+1}/h_{i+1} - dy_i/h_i)
+    for (int i = 0; i < m; ++i) {
+      const double hi = x[i + 1] - x[i], hi1 = x[i + 2] - x[i + 1];
+      const double g = 3.0 * ((y[i + 2] - y[i + 1]) / hi1 - (y[i + 1] - y[i]) / hi);
+      const double diag = 2.0 * (hi1 + hi);
+      if (i == 0) { cp[0] = hi1 / diag; c[1] = g / diag; }
+      else {
+        const double den = diag - hi * cp[i - 1];
+        cp[i] = hi1 / den;
+        c[i + 1] = (g - hi * c[i]) / den;
+      }
+    }
+    for (int i = m - 2; i >= 0; --i) c[i + 1] -= cp[i] * c[i + 2];
+    return;
+  }
+  const int m = n - 1;                      // unknowns u_i = c_{i+1}, i = 0 .. m-1 (c_0 = c_{n-1})
+  if (m < 3) { for (int i = 0; i < n; ++i) c[i] = 0.0; return; }
+  auto hh = [&](int i) -> double { return (i < m) ? x[i + 1] - x[i] : x[1] - x[0]; };          // h_i, cyclic
+  auto dy = [&](int i) -> double { return (i < m) ? y[i + 1] - y[i] : y[1] - y[0]; };
+  const double h0 = hh(0);
+  const double diag0 = 2.0 * (hh(0) + hh(1));
+  const double gam = -diag0;
+  // Thomas on T (diag_0 - gam, diag_{m-1} - h0 h0 / gam) for rhs g -> c[1..m] and for u = (gam, 0, ..., 0, h0) -> q
+  for (int i = 0; i < m; ++i) {
+    const double hi = hh(i), hi1 = hh(i + 1);
+    const double g = 3.0 * (dy(i + 1) / hi1 - dy(i) / hi);
+    double diag = 2.0 * (hi + hi1);
+    if (i == 0) diag -= gam;
+    if (i == m - 1) diag -= h0 * h0 / gam;
+    const double u = (i == 0) ? gam : ((i == m - 1) ? h0 : 0.0);
+    if (i == 0) { cp[0] = hi1 / diag; c[1] = g / diag; q[0] = u / diag; }
+    else {
+      const double den = diag - hi * cp[i - 1];
+      cp[i] = hi1 / den;
+      c[i + 1] = (g - hi * c[i]) / den;
+      q[i] = (u - hi * q[i - 1]) / den;
+    }
+  }
+  for (int i = m - 2; i >= 0; --i) { c[i + 1] -= cp[i] * c[i + 2]; q[i] -= cp[i] * q[i + 1]; }
+  const double fact = (c[1] + h0 * c[m] / gam) / (1.0 + q[0] + h0 * q[m - 1] / gam);
+  for (int i = 0; i < m; ++i) c[i + 1] -= fact * q[i];
+  c[0] = c[m];
+}
+
+// coefficient quads (y, b, c, d) of every interval, written with stride `qs` doubles between intervals
+template <class X, class Y>
+__device__ void cspline_quads(const X& x, const Y& y, int n, bool periodic, double* out, int qs) {
+  double c[kMaxCubicNodes];
+  cspline_second(x, y, n, periodic, c);
+  for (int i = 0; i + 1 < n; ++i) {
+    const double dx = x[i + 1] - x[i], dyv = y[i + 1] - y[i];
+    double* o = out + (long)i * qs;
+    o[0] = y[i];
+    o[1] = dyv / dx - dx * (c[i + 1] + 2.0 * c[i]) / 3.0;
+    o[2] = c[i];
+    o[3] = (c[i + 1] - c[i]) / (3.0 * dx);
+  }
+}
+
 // exact integral of y0 + t(b + t(c + t d)) for t in [r1, r2]
 __device__ __forceinline__ double cubic_piece_integral(double y0, double b, double c, double d,
                                                        double r1, double r2) {

@@ -971,7 +971,17 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
             s_flag[l * kNEC + e] = neg ? 1 : 0;
           } else s_flag[l * kNEC + e] = 0;
         };
-        if (interp_kind == kSteffen) {
+        if (interp_kind == kCubic) {
+          // global C2 spline (cspline_periodic): one thread per energy solves the cyclic system
+          if (blk == 0) {
+            double cc[kMaxCubicNodes];
+            cspline_second(s_PH, y, N_L, true, cc);
+            for (int l = 0; l < N_L - 1; ++l) {
+              const double dx = s_PH[l + 1] - s_PH[l], dyv = y[l + 1] - y[l];
+              emit(l, dyv / dx - dx * (cc[l + 1] + 2.0 * cc[l]) / 3.0, cc[l], (cc[l + 1] - cc[l]) / (3.0 * dx));
+            }
+          }
+        } else if (interp_kind == kSteffen) {
           for (int l = l0; l < l1; ++l) {
             double b, c, d;
             steffen_coeffs(s_PH, y, N_L, l, &b, &c, &d);
@@ -1171,6 +1181,7 @@ static cudaError_t launch_flux(const AzinvArgs& a, dim3 grid, size_t smem, cudaS
 
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   if (a.n_phases > kFluxThreads) return cudaErrorInvalidValue;
+  if (a.phase_interp == kCubic && a.n_leaves > kMaxCubicNodes) return cudaErrorInvalidValue;
   if (a.n_img_max > kMaxImages || a.n_img_max < 1) return cudaErrorInvalidValue;
   if (!a.ws_leaf || !a.ws_ihdr || !a.ws_hdr || !a.log10_energies) return cudaErrorInvalidValue;
   a.ws_chunk = a.ws_ihdr + (size_t)a.Q * a.n_rings * kIHdr;      // 8-byte aligned: kIHdr is even

@@ -135,8 +135,20 @@ __global__ void __launch_bounds__(kGenThreads) k_general_flux(AzinvArgs a, int n
     double* tb = s_tab + (long)I * 13 * N_L;
     const double* PH = tb;
     double b, c, d;
-    interp_coeffs(a.phase_interp, true, PH, tb + 1 * N_L, N_L, l, &b, &c, &d);
-    tb[2 * N_L + l] = b; tb[3 * N_L + l] = c; tb[4 * N_L + l] = d;
+    if (a.phase_interp != kCubic) {
+      interp_coeffs(a.phase_interp, true, PH, tb + 1 * N_L, N_L, l, &b, &c, &d);
+      tb[2 * N_L + l] = b; tb[3 * N_L + l] = c; tb[4 * N_L + l] = d;
+    } else if (l == 0) {             // global C2 spline: one thread per image solves the cyclic system
+      double cc[kMaxCubicNodes];
+      const double* yg = tb + 1 * N_L;
+      cspline_second(PH, yg, N_L, true, cc);
+      for (int i = 0; i < N_L - 1; ++i) {
+        const double dx = PH[i + 1] - PH[i], dyv = yg[i + 1] - yg[i];
+        tb[2 * N_L + i] = dyv / dx - dx * (cc[i + 1] + 2.0 * cc[i]) / 3.0;
+        tb[3 * N_L + i] = cc[i];
+        tb[4 * N_L + i] = (cc[i + 1] - cc[i]) / (3.0 * dx);
+      }
+    }
     steffen_coeffs(PH, tb + 5 * N_L, N_L, l, &b, &c, &d);
     tb[6 * N_L + l] = b; tb[7 * N_L + l] = c; tb[8 * N_L + l] = d;
     steffen_coeffs(PH, tb + 9 * N_L, N_L, l, &b, &c, &d);
@@ -318,6 +330,7 @@ __global__ void k_general_scale(double* flux, const double* energies, int Q, int
 
 cudaError_t launch_integrate_general(AzinvArgs a, cudaStream_t stream) {
   if (a.n_phases > 32 * kGenWarps) return cudaErrorInvalidValue;
+  if (a.phase_interp == kCubic && a.n_leaves > kMaxCubicNodes) return cudaErrorInvalidValue;
   if (a.n_img_max > kMaxImages || a.n_img_max < 1) return cudaErrorInvalidValue;
   if (!a.ws_leaf || !a.ws_ihdr || !a.ws_hdr || !a.log10_energies) return cudaErrorInvalidValue;
   const int atm = a.hot_atm_ext;

@@ -91,6 +91,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
     const double* pulse = a.pulses + (((long)b * a.n_comp + c) * a.n_chan + chan) * N_P;
     for (int i = lane; i < N_P; i += 32) s_y[i] = pulse[i];
     __syncwarp();
+    if (a.interp == kCubic) {          // global C2 spline: one lane solves the cyclic system
+      if (lane == 0) cspline_quads(s_x, s_y, N_P, true, s_c, 4);
+    } else
     for (int i = lane; i < N_P - 1; i += 32) {
       double bb, cc, dd;
       interp_coeffs(a.interp, periodic, s_x, s_y, N_P, i, &bb, &cc, &dd);
@@ -361,6 +364,7 @@ int marginal_max_bins() { return 32 * kMaxBPL; }
 cudaError_t launch_marginal(MarginalArgs a, cudaStream_t stream) {
   if (a.n_bins > 32 * kMaxBPL || a.n_bins < 1) return cudaErrorNotSupported;
   if (a.n_phases < 5) return cudaErrorInvalidValue;
+  if (a.interp == kCubic && a.n_phases > kMaxCubicNodes) return cudaErrorInvalidValue;
   cudaError_t err = a.n_bins <= 32 ? launch_marginal_bpl<1>(a, stream)
                     : a.n_bins <= 64 ? launch_marginal_bpl<2>(a, stream) : launch_marginal_bpl<4>(a, stream);
   if (err != cudaSuccess) return err;

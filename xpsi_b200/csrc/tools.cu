@@ -37,6 +37,9 @@ __global__ void __launch_bounds__(kEIThreads) k_energy_integrator(EnergyIntegArg
   }
   __syncthreads();
   const bool periodic = (a.interp != kSteffen);
+  if (a.interp == kCubic) {            // global C2 spline: one thread solves the (cyclic) system
+    if (threadIdx.x == 0) cspline_quads(s_x, s_y, N_E, true, s_c, 4);
+  } else
   for (int i = threadIdx.x; i < N_E - 1; i += kEIThreads) {
     double b, c, d;
     interp_coeffs(a.interp, periodic, s_x, s_y, N_E, i, &b, &c, &d);
@@ -77,6 +80,7 @@ __global__ void __launch_bounds__(kEIThreads) k_energy_integrator(EnergyIntegArg
 
 cudaError_t launch_energy_integrator(EnergyIntegArgs a, cudaStream_t stream) {
   if (a.n_energies < 5) return cudaErrorInvalidValue;       // Akima needs >= 5 nodes
+  if (a.interp == kCubic && a.n_energies > kMaxCubicNodes) return cudaErrorInvalidValue;
   const size_t smem = (size_t)a.n_energies * 6 * sizeof(double);
   dim3 grid(a.n_phases, a.Q);
   k_energy_integrator<<<grid, kEIThreads, smem, stream>>>(a);
@@ -326,6 +330,9 @@ __global__ void __launch_bounds__(kRowThreads) k_row_spline(RowSplineArgs a) {
     for (int i = threadIdx.x; i < n; i += kRowThreads) s_y[i] = log10(s_y[i]);
     __syncthreads();
   }
+  if (a.interp == kCubic) {            // global C2 spline (periodic for the phase tools, natural in energy)
+    if (threadIdx.x == 0) cspline_quads(s_x, s_y, n, a.periodic != 0, s_c, 4);
+  } else
   for (int i = threadIdx.x; i < n - 1; i += kRowThreads) {
     double b, c, d;
     interp_coeffs(a.interp, a.periodic != 0, s_x, s_y, n, i, &b, &c, &d);

@@ -72,8 +72,6 @@ def energy_interpolator(N_Ts, signal, energies, new_energies):
     signal = _lib.as_f8(signal, 2)
     energies = _lib.as_f8(energies, 1)
     new_energies = _lib.as_f8(new_energies, 1)
-    if _energy_interpolant == 2:
-        raise NotImplementedError("xpsi_b200: the 'Cubic' energy interpolant is not covered")
     out = np.empty((new_energies.shape[0], signal.shape[1]), dtype=np.float64)
     _lib.check(_lib.lib.xpsi_b200_energy_interpolator(
         _lib.dptr(signal), signal.shape[0], signal.shape[1], _lib.dptr(energies), _lib.dptr(new_energies),
