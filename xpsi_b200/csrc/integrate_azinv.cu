@@ -812,7 +812,9 @@ __device__ __noinline__ double profile_beaming(int beam_opt, const SlabCtx& hot,
 
 // ATM: hot atmosphere (1 BB, 2 Num4D).  CORR: elsewhere correction (0 none, 1 BB, 2 Num4D)
 // BEAM: 0 = no beaming code at all (keeps the common instantiation free of the call's register pressure)
-template <int ATM, int CORR, int BEAM>
+// CUBIC: 1 = the global C2 phase spline (its solver needs 6 KB of per-thread local memory, kept out of the
+// default instantiation)
+template <int ATM, int CORR, int BEAM, int CUBIC>
 __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flux(AzinvArgs a) {
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
   const int i = blockIdx.x / n_chunks;
@@ -971,7 +973,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
             s_flag[l * kNEC + e] = neg ? 1 : 0;
           } else s_flag[l * kNEC + e] = 0;
         };
-        if (interp_kind == kCubic) {
+        if (CUBIC) {
           // global C2 spline (cspline_periodic): one thread per energy solves the cyclic system
           if (blk == 0) {
             double cc[kMaxCubicNodes];
@@ -1166,17 +1168,19 @@ void azinv_slab_budgets(const AtmTable& t, const double* energies, int n_energie
   *rows_ring = rr > t.nE ? t.nE : rr;
 }
 
-template <int ATM, int CORR, int BEAM>
+template <int ATM, int CORR, int BEAM, int CUBIC>
 static cudaError_t launch_flux_b(const AzinvArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
-  cudaError_t err = cudaFuncSetAttribute(k_azinv_flux<ATM, CORR, BEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = cudaFuncSetAttribute(k_azinv_flux<ATM, CORR, BEAM, CUBIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  k_azinv_flux<ATM, CORR, BEAM><<<grid, kFluxThreads, smem, stream>>>(a);
+  k_azinv_flux<ATM, CORR, BEAM, CUBIC><<<grid, kFluxThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 template <int ATM, int CORR>
 static cudaError_t launch_flux(const AzinvArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
-  return a.beam_opt != 0 ? launch_flux_b<ATM, CORR, 1>(a, grid, smem, stream)
-                         : launch_flux_b<ATM, CORR, 0>(a, grid, smem, stream);
+  const bool cubic = a.phase_interp == kCubic;
+  if (a.beam_opt != 0)
+    return cubic ? launch_flux_b<ATM, CORR, 1, 1>(a, grid, smem, stream) : launch_flux_b<ATM, CORR, 1, 0>(a, grid, smem, stream);
+  return cubic ? launch_flux_b<ATM, CORR, 0, 1>(a, grid, smem, stream) : launch_flux_b<ATM, CORR, 0, 0>(a, grid, smem, stream);
 }
 
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
