@@ -78,3 +78,27 @@ for nb in (64, 45):
     print("marginal likelihood with %d bins: lnL = %.8f" % (nb, res[0]))
 np.savez_compressed(os.path.join(HERE, "tools.npz"), **out)
 print("tools.npz (+many-bin likelihood)", os.path.getsize(os.path.join(HERE, "tools.npz")) // 1024, "KiB")
+
+# ---- time-invariant component (Everywhere(time_invariant=True)): one signal column, phase-averaged data ----
+# compute_expected_counts.pyx:190-192 stores the rate in the first bin instead of integrating a spline
+ev = np.load(os.path.join(HERE, "m4_everywhere.npz"))
+from xpsi.tools import energy_integrator as _eint  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from xpsi_b200 import synthetic as _syn  # noqa: E402
+_matrix, _edges = _syn.nicer_like_response()[:2]
+spec = np.ascontiguousarray(ev["num4d_flux"].reshape(-1, 1) / (1.2 * 3.08567758e19) ** 2)
+integ = _eint(1, spec, np.log10(ev["num4d_energies"]), np.log10(_edges))
+folded = np.ascontiguousarray(np.dot(_matrix, integ))                    # [n_chan, 1]
+T_ev = 2.0e4
+one_bin = np.array([0.0, 1.0])
+cnts = np.random.default_rng(21).poisson(folded * T_ev + 3.0).astype(np.double)
+pre = precomputation(cnts.astype(np.int32))
+sup = -1.0 * np.ones((folded.shape[0], 2)); sup[:, 0] = 0.0
+res = eval_marginal_likelihood(T_ev, one_bin, cnts, (folded,), (np.array([0.0]),), np.array([0.0]), pre, sup,
+                               1000, 0.0, 1.0e-8, 1.0e-3, 10.0, -1.0e90)
+out = dict(np.load(os.path.join(HERE, "tools.npz")))
+out.update({"tinv_folded": folded, "tinv_counts": cnts, "tinv_exposure": np.asarray(T_ev),
+            "tinv_lnL": np.asarray(res[0]), "tinv_expected": np.asarray(res[1]), "tinv_bg": np.asarray(res[2])})
+np.savez_compressed(os.path.join(HERE, "tools.npz"), **out)
+print("time-invariant likelihood lnL = %.8f" % res[0])
+print("tools.npz (+time-invariant likelihood)", os.path.getsize(os.path.join(HERE, "tools.npz")) // 1024, "KiB")

@@ -925,3 +925,18 @@ def test_cubic_interpolants(c1):
     finally:
         tools.set_phase_interpolant("Akima")
         tools.set_energy_interpolant("Steffen")
+
+
+def test_time_invariant_component_likelihood():
+    """Everywhere(time_invariant=True): a single signal column with phase-averaged data -- the rate is stored in the
+    first bin without a phase spline (compute_expected_counts.pyx:190-192)."""
+    from xpsi_b200.likelihoods import eval_marginal_likelihood, precomputation
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tools.npz"))
+    folded, cnts = d["tinv_folded"], d["tinv_counts"]
+    sup = -1.0 * np.ones((folded.shape[0], 2)); sup[:, 0] = 0.0
+    res = eval_marginal_likelihood(float(d["tinv_exposure"]), np.array([0.0, 1.0]), cnts, (folded,), (np.array([0.0]),),
+                                   np.array([0.0]), precomputation(cnts.astype(np.int32)), sup,
+                                   1000, 0.0, 1.0e-8, 1.0e-3, 10.0, -1.0e90)
+    print("time-invariant lnL", res[0], "ref", float(d["tinv_lnL"]))
+    assert abs(res[0] - float(d["tinv_lnL"])) < LNL_ATOL
+    assert rel_err(res[1], d["tinv_expected"]) < PULSE_RTOL and rel_err(res[2], d["tinv_bg"]) < 1e-6

@@ -535,7 +535,7 @@ int xpsi_b200_eval_marginal_likelihood(
   int rc = ensure_stream();
   if (rc) return rc;
   if (n_bins < 1 || n_bins > xb::marginal_max_bins()) return fail(XPSI_B200_EUNSUPPORTED, "1..128 phase bins supported");
-  if (n_comp < 1 || n_chan < 1 || n_phases < 5) return fail(XPSI_B200_EINVAL, "bad dimensions");
+  if (n_comp < 1 || n_chan < 1 || (n_phases < 5 && n_phases != 1)) return fail(XPSI_B200_EINVAL, "bad dimensions");
   Dev<double> d_pulses, d_cph, d_sh, d_dph, d_cnt, d_pre, d_sup, d_bg, d_clnl, d_exp, d_mb, d_mbs, d_lnl;
   Dev<int> d_cst, d_st;
   const size_t np = (size_t)n_chan * n_phases;
@@ -581,7 +581,7 @@ int xpsi_b200_poisson_likelihood_given_background(
   int rc = ensure_stream();
   if (rc) return rc;
   if (n_bins < 1 || n_bins > xb::marginal_max_bins()) return fail(XPSI_B200_EUNSUPPORTED, "1..128 phase bins supported");
-  if (n_comp < 1 || n_chan < 1 || n_phases < 5 || !background) return fail(XPSI_B200_EINVAL, "bad arguments");
+  if (n_comp < 1 || n_chan < 1 || (n_phases < 5 && n_phases != 1) || !background) return fail(XPSI_B200_EINVAL, "bad arguments");
   Dev<double> d_pulses, d_cph, d_sh, d_dph, d_cnt, d_pre, d_bg, d_clnl, d_exp, d_lnl, d_sup;
   Dev<int> d_cst, d_st;
   const size_t np = (size_t)n_chan * n_phases;

@@ -89,6 +89,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
   for (int j = 0; j < BPL; ++j) star[j] = 0.0;
   for (int c = 0; c < a.n_comp; ++c) {
     const double* pulse = a.pulses + (((long)b * a.n_comp + c) * a.n_chan + chan) * N_P;
+    if (N_P == 1) {                    // time-invariant component: stored in the first bin, not integrated
+      if (lane == 0) star[0] = pulse[0];                         // compute_expected_counts.pyx:190-192
+      continue;
+    }
     for (int i = lane; i < N_P; i += 32) s_y[i] = pulse[i];
     __syncwarp();
     if (a.interp == kCubic) {          // global C2 spline: one lane solves the cyclic system
@@ -363,7 +367,7 @@ int marginal_max_bins() { return 32 * kMaxBPL; }
 
 cudaError_t launch_marginal(MarginalArgs a, cudaStream_t stream) {
   if (a.n_bins > 32 * kMaxBPL || a.n_bins < 1) return cudaErrorNotSupported;
-  if (a.n_phases < 5) return cudaErrorInvalidValue;
+  if (a.n_phases < 5 && a.n_phases != 1) return cudaErrorInvalidValue;     // 1: time-invariant components
   if (a.interp == kCubic && a.n_phases > kMaxCubicNodes) return cudaErrorInvalidValue;
   cudaError_t err = a.n_bins <= 32 ? launch_marginal_bpl<1>(a, stream)
                     : a.n_bins <= 64 ? launch_marginal_bpl<2>(a, stream) : launch_marginal_bpl<4>(a, stream);
