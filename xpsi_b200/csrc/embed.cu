@@ -353,6 +353,80 @@ __device__ double region_cell_area(const Region& g, double l, double u, double p
   return tot;
 }
 
+// The same adaptive rule evaluated by a whole warp: lane k < 15 owns Kronrod node k of the current panel, the
+// sums are warp reductions and every lane takes the same accept / bisect decision (no divergence, and the
+// serial chain is 15 times shorter than one thread per cell, which left 255 threads of a polar-cap CTA
+// waiting for the few that owned boundary cells).
+template <class F>
+__device__ double warp_adaptive_gk15(const F& f, double A, double B, double tol_abs, int lane) {
+  if (!(B > A)) return 0.0;
+  double sa[44], sb[44];
+  int sd[44];
+  int top = 1;
+  sa[0] = A; sb[0] = B; sd[0] = 0;
+  // node / weights of this lane: lanes 0..6 left of centre, 7 centre, 8..14 right of centre, 15.. idle
+  const int kk = lane < 7 ? lane : (lane == 7 ? 7 : (lane < 15 ? 14 - lane : 7));
+  const double xk = lane < 7 ? -c_k15_x[kk] : (lane < 15 ? c_k15_x[kk] : 0.0);
+  const double wk = lane < 15 ? c_k15_w[kk] : 0.0;
+  const double wg = (lane < 15 && ((kk & 1) || kk == 7)) ? c_g7_w[kk == 7 ? 3 : (kk >> 1)] : 0.0;
+  double total = 0.0;
+  while (top > 0) {
+    --top;
+    const double a = sa[top], b = sb[top];
+    const int depth = sd[top];
+    const double h = 0.5 * (b - a), m = 0.5 * (a + b);
+    const double fv = lane < 15 ? f(m + h * xk) : 0.0;
+    const double K = warp_sum(wk * fv) * h, G = warp_sum(wg * fv) * h;
+    if (fabs(K - G) <= tol_abs || depth >= 40 || top + 2 > 44) total += K;
+    else {
+      sa[top] = a; sb[top] = m; sd[top] = depth + 1; ++top;
+      sa[top] = m; sb[top] = b; sd[top] = depth + 1; ++top;
+    }
+  }
+  return total;
+}
+
+// region_cell_area evaluated by a warp (all lanes pass the same arguments and receive the same result)
+__device__ double warp_region_cell_area(const Region& g, double l, double u, double pa, double pb, double eps,
+                                        double zeta, double tol_abs, int lane) {
+  double bp[24];
+  int nb = 0;
+  bp[nb++] = l; bp[nb++] = u;
+  circle_meridian_crossings(g.colat, g.radius, pa, l, u, bp, &nb);
+  circle_meridian_crossings(g.colat, g.radius, pb, l, u, bp, &nb);
+  double tg[4];
+  int nt = 0;
+  tg[nt++] = fabs(g.colat - g.radius); tg[nt++] = g.colat + g.radius;
+  if (g.hRadius > 0.0) {
+    circle_meridian_crossings(g.hColat, g.hRadius, pa - g.hAzi, l, u, bp, &nb);
+    circle_meridian_crossings(g.hColat, g.hRadius, pb - g.hAzi, l, u, bp, &nb);
+    tg[nt++] = fabs(g.hColat - g.hRadius); tg[nt++] = g.hColat + g.hRadius;
+  }
+  for (int k = 0; k < nt; ++k) if (tg[k] > l && tg[k] < u) bp[nb++] = tg[k];
+  for (int i = 1; i < nb; ++i) {
+    const double v = bp[i];
+    int j = i - 1;
+    while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; --j; }
+    bp[j + 1] = v;
+  }
+  auto f = [&](double th) -> double { return region_width(g, th, pa, pb, 1) * area_element(th, eps, zeta, 0); };
+  auto is_tangent = [&](double x) -> bool {
+    for (int k = 0; k < nt; ++k) if (fabs(x - tg[k]) < 1.0e-14) return true;
+    return false;
+  };
+  double tot = 0.0;
+  for (int i = 0; i + 1 < nb; ++i) {
+    const double s0 = bp[i], s1 = bp[i + 1];
+    if (!(s1 - s0 > 1.0e-15)) continue;
+    const bool sing0 = is_tangent(s0), sing1 = is_tangent(s1);
+    if (!sing0 && !sing1) { tot += warp_adaptive_gk15(f, s0, s1, tol_abs, lane); continue; }
+    const double mid = (sing0 && sing1) ? 0.5 * (s0 + s1) : (sing0 ? s1 : s0);
+    if (sing0) tot += warp_adaptive_gk15([&](double t) -> double { return f(s0 + t * t) * 2.0 * t; }, 0.0, sqrt(mid - s0), tol_abs, lane);
+    if (sing1) tot += warp_adaptive_gk15([&](double t) -> double { return f(s1 - t * t) * 2.0 * t; }, 0.0, sqrt(s1 - mid), tol_abs, lane);
+  }
+  return tot;
+}
+
 // geometry of one member's bounding mesh: polar caps use the whole azimuth and start at the pole
 // (polar_mesh.pyx:53-61, mesh_tools.pyx:925-941)
 struct MeshFrame { double lo, hi, bphi; int polar, invert; };
@@ -389,7 +463,9 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
   __shared__ double s_area[kAreaNodes], s_colat[kAreaNodes];
   __shared__ double s_par[128], s_theta[128];
   __shared__ double s_boxA, s_spotA;
-  __shared__ int s_n;
+  __shared__ int s_n, s_nb;
+  constexpr int kBListCap = 4096;
+  __shared__ unsigned short s_blist[kBListCap];            // boundary cells of a generic member (second pass)
   if (!(g.radius > 0.0)) {
     if (tid == 0) { a.n_rings[q] = 0; a.n_azi[q] = 0; atomicExch(a.status + b, kUnsupported); }
     return;
@@ -546,6 +622,8 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
     }
     const bool mirror = are_equal(g.hColat, g.colat) && are_equal(g.hAzi, 0.0);     // mesh.pyx:187-191
     const int j_max = mirror ? half : n;
+    if (tid == 0) s_nb = 0;
+    __syncthreads();
     for (int t = tid; t < n * j_max; t += kMeshThreads) {
       const int i = t / j_max, j = t - i * j_max;
       const double l = (i == 0) ? lo : s_par[i - 1];
@@ -568,13 +646,33 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
       if (!integrate && g.hRadius > 0.0)
         for (int k = 0; k < 4; ++k)
           if (l <= sp[k][0] && sp[k][0] <= u && lft <= sp[k][1] && sp[k][1] <= right) integrate = true;
-      double area = 0.0;
-      if (integrate) area = region_cell_area(g, l, u, lft, right, eps, zeta, 1.0e-11 * cellA);
-      else if (p5 == 1) area = cellA;
-      area *= R_eq * R_eq;
+      if (integrate) {                                    // boundary cell: second pass, one warp each
+        const int slot = atomicAdd(&s_nb, 1);
+        if (slot < kBListCap) { s_blist[slot] = (unsigned short)t; continue; }
+      }
+      const double area = integrate ? region_cell_area(g, l, u, lft, right, eps, zeta, 1.0e-11 * cellA) * R_eq * R_eq
+                                    : ((p5 == 1) ? cellA * R_eq * R_eq : 0.0);
       const long row = (ring0 + i) * a.max_azi;
       a.cellArea[row + j] = area;
       if (mirror) a.cellArea[row + n - 1 - j] = area;
+    }
+    __syncthreads();
+    // second pass: one warp per boundary cell (integrateCell, mesh_tools.pyx:429-473)
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n_list = min(s_nb, kBListCap);
+    for (int w = warp; w < n_list; w += kMeshThreads / 32) {
+      const int t = s_blist[w];
+      const int i = t / j_max, j = t - i * j_max;
+      const double l = (i == 0) ? lo : s_par[i - 1];
+      const double u = (i == n - 1) ? hi : s_par[i];
+      double lft = -bphi;
+      for (int k = 0; k < j; ++k) lft += dphi;
+      const double area = warp_region_cell_area(g, l, u, lft, lft + dphi, eps, zeta, 1.0e-11 * cellA, lane) * R_eq * R_eq;
+      if (lane == 0) {
+        const long row = (ring0 + i) * a.max_azi;
+        a.cellArea[row + j] = area;
+        if (mirror) a.cellArea[row + n - 1 - j] = area;
+      }
     }
   } else
   for (int t = tid; t < n * half; t += kMeshThreads) {
