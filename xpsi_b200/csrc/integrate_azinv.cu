@@ -328,10 +328,54 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
       }
     }
     s_inv2[tid] = (Inv == 2);
-    if (Inv != 2) {
-      for (int m = 1; m < N_L; ++m)
-        if (PH[m] <= PH[m - 1]) { s_mono[tid] = 1; break; }          // pyx:556-563
+  } else if (tid == 32 || tid == 33) {
+    // While warp 0 replays the visibility state machines, two idle threads prepare the ring's atmosphere
+    // headers (their table-axis searches are chains of dependent global loads): thread 32 the hot
+    // atmosphere, thread 33 the elsewhere atmosphere of the correction.  They do not depend on the replay;
+    // a ring that turns out dark is skipped through ih[0] = 0 whatever its header holds.
+    double* dh = a.ws_hdr + ring * kDHdr;
+    int* ih = a.ws_ihdr + ring * kIHdr;
+    if (tid == 32) {
+      const double* VEC = a.srcParams + (a.params_per_cell ? (cell0 + J) : ring) * a.n_params;
+      const double kT = kKBOverKeV * pow(10.0, VEC[0]);
+      dh[10] = VEC[0]; dh[12] = kT; dh[13] = log10(kT);
+      dh[14] = (ATM == 2) ? (kErg / kHKeV) * pow(10.0, 3.0 * VEC[0]) : kErg * kPlanckDistConst;
+      if (ATM == 2) {              // (T,g) stencil of the ring, hot_Num4D.pyx:295-409
+        View vT{a.hot.logT, 1}, vG{a.hot.logg, 1};
+        const int bT = lagrange_base(vT, a.hot.nT, VEC[0]);
+        const int bG = lagrange_base(vG, a.hot.ng, VEC[1]);
+        double w[4];
+        lagrange_weights(vT, bT, VEC[0], w);
+        for (int x = 0; x < 4; ++x) dh[2 + x] = w[x];
+        lagrange_weights(vG, bG, VEC[1], w);
+        for (int x = 0; x < 4; ++x) dh[6 + x] = w[x];
+        ih[2] = bT; ih[3] = bG;
+        dh[11] = VEC[1];
+      }
+    } else if (a.corrParams) {     // elsewhere atmosphere at the ring's correction parameters
+      const double* CV = a.corrParams + (a.params_per_cell ? (cell0 + J) : ring) * a.n_params;
+      const double kTc = kKBOverKeV * pow(10.0, CV[0]);
+      dh[kCorrD + 10] = CV[0]; dh[kCorrD + 12] = kTc; dh[kCorrD + 13] = log10(kTc);
+      dh[kCorrD + 14] = (a.else_atm_ext == 2) ? kErg / kHKeV * pow(10.0, 3.0 * CV[0]) : kErg * kPlanckDistConst;
+      if (a.else_atm_ext == 2) {
+        View vT{a.els.logT, 1}, vG{a.els.logg, 1};
+        const int bT = lagrange_base(vT, a.els.nT, CV[0]);
+        const int bG = lagrange_base(vG, a.els.ng, CV[1]);
+        double w[4];
+        lagrange_weights(vT, bT, CV[0], w);
+        for (int x = 0; x < 4; ++x) dh[kCorrD + 2 + x] = w[x];
+        lagrange_weights(vG, bG, CV[1], w);
+        for (int x = 0; x < 4; ++x) dh[kCorrD + 6 + x] = w[x];
+        ih[6] = bT; ih[7] = bG;
+        dh[kCorrD + 11] = CV[1];
+      }
     }
+  }
+  __syncthreads();
+  // lagged phases must increase strictly (pyx:556-563): checked by all threads
+  for (int t = tid; t < n_img * N_L; t += kGeomThreads) {
+    const int I = t / N_L, m = t - I * N_L;
+    if (m > 0 && !s_inv2[I] && s_phase[t] <= s_phase[t - 1]) s_mono[I] = 1;
   }
   __syncthreads();
   if (tid == 0) {
@@ -357,48 +401,12 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
     int* ih = a.ws_ihdr + ring * kIHdr;
     double* dh = a.ws_hdr + ring * kDHdr;
     ih[0] = n; ih[1] = J;
-    const double* VEC = a.srcParams + (a.params_per_cell ? (cell0 + J) : ring) * a.n_params;
     double zlo = 1e300, zhi = -1e300;
     for (int I = 0; I < n; ++I) {
       if (s_zhi[I] == 0ull) continue;
       zlo = fmin(zlo, key_order(s_zlo[I])); zhi = fmax(zhi, key_order(s_zhi[I]));
     }
-    dh[0] = zlo; dh[1] = zhi; dh[10] = VEC[0];
-    {
-      const double kT = kKBOverKeV * pow(10.0, VEC[0]);
-      dh[12] = kT; dh[13] = log10(kT);
-      dh[14] = (ATM == 2) ? (kErg / kHKeV) * pow(10.0, 3.0 * VEC[0]) : kErg * kPlanckDistConst;
-    }
-    if (a.corrParams && n > 0) {   // elsewhere atmosphere at the ring's correction parameters
-      const double* CV = a.corrParams + (a.params_per_cell ? (cell0 + J) : ring) * a.n_params;
-      const double kTc = kKBOverKeV * pow(10.0, CV[0]);
-      dh[kCorrD + 10] = CV[0]; dh[kCorrD + 12] = kTc; dh[kCorrD + 13] = log10(kTc);
-      dh[kCorrD + 14] = (a.else_atm_ext == 2) ? kErg / kHKeV * pow(10.0, 3.0 * CV[0]) : kErg * kPlanckDistConst;
-      if (a.else_atm_ext == 2) {
-        View vT{a.els.logT, 1}, vG{a.els.logg, 1};
-        const int bT = lagrange_base(vT, a.els.nT, CV[0]);
-        const int bG = lagrange_base(vG, a.els.ng, CV[1]);
-        double w[4];
-        lagrange_weights(vT, bT, CV[0], w);
-        for (int x = 0; x < 4; ++x) dh[kCorrD + 2 + x] = w[x];
-        lagrange_weights(vG, bG, CV[1], w);
-        for (int x = 0; x < 4; ++x) dh[kCorrD + 6 + x] = w[x];
-        ih[6] = bT; ih[7] = bG;
-        dh[kCorrD + 11] = CV[1];
-      }
-    }
-    if (ATM == 2 && n > 0) {     // (T,g) stencil of the ring, hot_Num4D.pyx:295-409
-      View vT{a.hot.logT, 1}, vG{a.hot.logg, 1};
-      const int bT = lagrange_base(vT, a.hot.nT, VEC[0]);
-      const int bG = lagrange_base(vG, a.hot.ng, VEC[1]);
-      double w[4];
-      lagrange_weights(vT, bT, VEC[0], w);
-      for (int x = 0; x < 4; ++x) dh[2 + x] = w[x];
-      lagrange_weights(vG, bG, VEC[1], w);
-      for (int x = 0; x < 4; ++x) dh[6 + x] = w[x];
-      ih[2] = bT; ih[3] = bG;
-      dh[11] = VEC[1];
-    }
+    dh[0] = zlo; dh[1] = zhi;
   }
   __syncthreads();
   n_img = s_nimg;
