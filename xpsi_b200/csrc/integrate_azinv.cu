@@ -514,61 +514,62 @@ __global__ void __launch_bounds__(kSlabThreads) k_azinv_slab(AzinvArgs a, int wh
 // read once per member instead of once per ring (the rings differ only in log g and in the rows they reach).
 constexpr int kSlabMThreads = 192;
 
+constexpr int kSlabMRows = 4;           // mu rows per CTA: the ring headers are staged once for all of them
+
 __global__ void __launch_bounds__(kSlabMThreads) k_azinv_slab_member(AzinvArgs a, int which) {
-  const int m = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
+  const int q = blockIdx.y, tid = threadIdx.x;
   const AtmTable& T = which ? a.els : a.hot;
   const int ho = which ? kCorrD : 0;
   const long ring0 = (long)q * a.n_rings;
   extern __shared__ double smem[];
   double* s_V = smem;                                          // [kGSpan][kSlabMThreads]
   double* s_wG = s_V + kGSpan * kSlabMThreads;                 // [n_rings][4]
-  int* s_row = reinterpret_cast<int*>(s_wG + 4 * a.n_rings);   // [n_rings][3]: first row, rows, g offset
-  __shared__ int s_gmin, s_first;
+  int* s_row = reinterpret_cast<int*>(s_wG + 4 * a.n_rings);   // [n_rings][3]: first row, rows, g base
+  __shared__ int s_gmin, s_gmax, s_first, s_nlit;
   if (!member_uniform(a, q, which, tid, kSlabMThreads)) return;
-  if (tid == 0) { s_gmin = 1 << 30; s_first = -1; }
+  if (tid == 0) { s_gmin = 1 << 30; s_gmax = -1; s_first = -1; s_nlit = 0; }
   __syncthreads();
+  // lit rings, compacted: slot -> (first row, rows, g base), weights and the ring index
+  int* s_ring = s_row + 3 * a.n_rings;                         // [n_rings]
   for (int r = tid; r < a.n_rings; r += kSlabMThreads) {
     const int* ih = a.ws_ihdr + (ring0 + r) * kIHdr;
-    const int lit = ih[0] != 0 && ih[which ? 9 : 5] > 0;
-    s_row[3 * r] = ih[which ? 8 : 4]; s_row[3 * r + 1] = lit ? ih[which ? 9 : 5] : 0;
-    if (lit) { atomicMin(&s_gmin, ih[which ? 7 : 3]); atomicMax(&s_first, r); }
+    if (ih[0] == 0 || ih[which ? 9 : 5] <= 0) continue;
+    const int slot = atomicAdd(&s_nlit, 1);
+    const int g = ih[which ? 7 : 3];
+    s_row[3 * slot] = ih[which ? 8 : 4]; s_row[3 * slot + 1] = ih[which ? 9 : 5]; s_row[3 * slot + 2] = g;
+    s_ring[slot] = r;
+    atomicMin(&s_gmin, g); atomicMax(&s_gmax, g); atomicMax(&s_first, r);
     const double* dh = a.ws_hdr + (ring0 + r) * kDHdr;
-    for (int y = 0; y < 4; ++y) s_wG[4 * r + y] = dh[ho + 6 + y];
+    for (int y = 0; y < 4; ++y) s_wG[4 * slot + y] = dh[ho + 6 + y];
   }
   __syncthreads();
   if (s_first < 0) return;
-  const int gmin = s_gmin;
-  int gmax = gmin;
-  for (int r = 0; r < a.n_rings; ++r) {
-    if (s_row[3 * r + 1] == 0) continue;
-    const int g = a.ws_ihdr[(ring0 + r) * kIHdr + (which ? 7 : 3)];
-    if (tid == 0) s_row[3 * r + 2] = g - gmin;
-    gmax = max(gmax, g);
-  }
-  const int span = gmax - gmin + 4;                            // <= kGSpan by member_uniform
+  const int gmin = s_gmin, n_lit = s_nlit;
+  const int span = s_gmax - gmin + 4;                          // <= kGSpan by member_uniform
   const int bT = a.ws_ihdr[(ring0 + s_first) * kIHdr + (which ? 6 : 2)];
   const double* dh0 = a.ws_hdr + (ring0 + s_first) * kDHdr;
   const double wT0 = dh0[ho + 2], wT1 = dh0[ho + 3], wT2 = dh0[ho + 4], wT3 = dh0[ho + 5];
   const long S0 = (long)T.ng * T.nmu * T.nE, S1 = (long)T.nmu * T.nE, S2 = T.nE;
   const int rows_stride = a.slab_rows_ring;
-  double* out_base = (which ? a.ws_slab2 : a.ws_slab) + ring0 * (long)T.nmu * rows_stride + (long)m * rows_stride;
-  __syncthreads();
-  for (int e0 = 0; e0 < T.nE; e0 += kSlabMThreads) {
-    const int e = e0 + tid;
-    if (e < T.nE) {
+  for (int mi = 0; mi < kSlabMRows; ++mi) {
+    const int m = blockIdx.x * kSlabMRows + mi;
+    if (m >= T.nmu) break;
+    double* out_base = (which ? a.ws_slab2 : a.ws_slab) + ring0 * (long)T.nmu * rows_stride + (long)m * rows_stride;
+    for (int e0 = 0; e0 < T.nE; e0 += kSlabMThreads) {
+      const int e = e0 + tid;
+      if (e >= T.nE) continue;
       const double* base = T.buf + (long)bT * S0 + (long)gmin * S1 + (long)m * S2 + e;
-      for (int k = 0; k < span; ++k) {
+      for (int k = 0; k < span; ++k) {                         // own column of s_V: no barrier needed
         const double* b = base + k * S1;
         s_V[k * kSlabMThreads + tid] = wT0 * __ldg(b) + wT1 * __ldg(b + S0) + wT2 * __ldg(b + 2 * S0) + wT3 * __ldg(b + 3 * S0);
       }
-      for (int r = 0; r < a.n_rings; ++r) {
-        const int nrows = s_row[3 * r + 1];
-        const int rel = e - s_row[3 * r];
-        if (nrows == 0 || rel < 0 || rel >= nrows) continue;
-        const double* V = s_V + s_row[3 * r + 2] * kSlabMThreads + tid;
-        const double* w = s_wG + 4 * r;
-        // same association as k_azinv_slab: sum_x wT[x] (sum_y wG[y] tab) == sum_y wG[y] (sum_x wT[x] tab) up to rounding
-        out_base[(long)r * T.nmu * rows_stride + rel] =
+      for (int sl = 0; sl < n_lit; ++sl) {
+        const int rel = e - s_row[3 * sl];
+        if (rel < 0 || rel >= s_row[3 * sl + 1]) continue;
+        const double* V = s_V + (s_row[3 * sl + 2] - gmin) * kSlabMThreads + tid;
+        const double* w = s_wG + 4 * sl;
+        // same contraction as k_azinv_slab with the sums exchanged (equal up to rounding)
+        out_base[(long)s_ring[sl] * T.nmu * rows_stride + rel] =
             w[0] * V[0] + w[1] * V[kSlabMThreads] + w[2] * V[2 * kSlabMThreads] + w[3] * V[3 * kSlabMThreads];
       }
     }
@@ -1213,14 +1214,14 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   cudaError_t err;
   a.general = 0;
   if ((err = launch_azinv_geometry(a, stream)) != cudaSuccess) return err;
-  const size_t msm = ((size_t)kGSpan * kSlabMThreads + 4ul * a.n_rings) * sizeof(double) + 3ul * a.n_rings * sizeof(int);
+  const size_t msm = ((size_t)kGSpan * kSlabMThreads + 4ul * a.n_rings) * sizeof(double) + 4ul * a.n_rings * sizeof(int);
   if (atm == 2) {
     k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 0);
-    k_azinv_slab_member<<<dim3(a.hot.nmu, a.Q), kSlabMThreads, msm, stream>>>(a, 0);
+    k_azinv_slab_member<<<dim3((a.hot.nmu + kSlabMRows - 1) / kSlabMRows, a.Q), kSlabMThreads, msm, stream>>>(a, 0);
   }
   if (corr == 2) {
     k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 1);
-    k_azinv_slab_member<<<dim3(a.els.nmu, a.Q), kSlabMThreads, msm, stream>>>(a, 1);
+    k_azinv_slab_member<<<dim3((a.els.nmu + kSlabMRows - 1) / kSlabMRows, a.Q), kSlabMThreads, msm, stream>>>(a, 1);
   }
   if (a.ws_mom) {
     if (!a.ws_meta || !a.ws_cnt || a.mom_cap < 1 || a.n_azi > 0xffff) return cudaErrorInvalidValue;
