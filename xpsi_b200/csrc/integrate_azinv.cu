@@ -852,8 +852,12 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
   double* s_carea = sp; sp += a.n_azi;
   double* s_PH = sp; sp += N_L;
   double* s_aux = sp; sp += N_L;          // 1/h of the leaf intervals
-  // profile values live in slot 0 of their coefficient quad: s_coef[e][l] = (y, b, c, d)
+  // cubic pieces of the chunk's energies in two planes of 16-byte pairs: s_lo[e][l] = (y, b), s_hi[e][l] = (c, d).
+  // Threads of a warp read consecutive l in the accumulation stage, so each plane is read at a 16-byte stride
+  // (one wavefront per 8 lanes); interleaved (y, b, c, d) quads put lanes i and i+4 on the same banks.
   double* s_coef = sp; sp += (long)kNEC * N_L * 4;
+  double2* s_lo = reinterpret_cast<double2*>(s_coef);
+  double2* s_hi = s_lo + (long)kNEC * N_L;
   SlabCtx hot, els;
   if (ATM == 2) sp = slab_ctx_carve(hot, sp, N_L, a.slab_ne_max, a.hot.nmu);
   if (CORR == 2) sp = slab_ctx_carve(els, sp, N_L, a.slab_ne_max, a.els.nmu);
@@ -915,7 +919,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
       const double geom = W[3 * N_L + l];
       if (geom == 0.0) {
 #pragma unroll
-        for (int e = 0; e < kNEC; ++e) s_coef[((long)e * N_L + l) * 4] = 0.0;
+        for (int e = 0; e < kNEC; ++e) s_coef[((long)e * N_L + l) * 2] = 0.0;
         continue;
       }
       const double zst = W[N_L + l];            // Z for a blackbody hot atmosphere, log10 Z for Num4D
@@ -936,7 +940,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
         double corr = 0.0;
         if (CORR == 1) corr = bb_intensity(s_E[e] / Zlin, kT_c) * norm_c;
         else if (CORR == 2) corr = slab_ctx_eval(els, s_logE[e] - Zlog - log_kT_c, ms_els) * norm_c;
-        s_coef[((long)e * N_L + l) * 4] = (I_E * norm - corr) * geom;  // pyx:478 (energies past ne repeat the first)
+        s_coef[((long)e * N_L + l) * 2] = (I_E * norm - corr) * geom;  // pyx:478 (energies past ne repeat the first)
       }
     }
     __syncthreads();
@@ -951,11 +955,11 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
       const int per = (N_L - 1 + kBlk - 1) / kBlk;
       const int l0 = blk * per, l1 = min(l0 + per, N_L - 1);
       if (l0 < l1) {                 // all kNEC energies (a short last chunk repeats its first energy)
-        const View y{s_coef + (long)e * N_L * 4, 4};          // node values: slot 0 of every quad of this energy
+        const View y{s_coef + (long)e * N_L * 2, 2};          // node values: slot 0 of every (y, b) pair of this energy
         auto emit = [&](int l, double b, double c, double d) {
           const double y0 = y[l];
-          double* o = s_coef + ((long)e * N_L + l) * 4;       // slot 0 (y) is left alone: neighbours read it
-          o[1] = b; *reinterpret_cast<double2*>(o + 2) = make_double2(c, d);
+          s_coef[((long)e * N_L + l) * 2 + 1] = b;            // slot 0 (y) is left alone: neighbours read it
+          s_hi[(long)e * N_L + l] = make_double2(c, d);
           if (CORR == 0) {
             // Bernstein coefficients of the cubic on [0,h] (end values are the nodes themselves):
             // all >= 0  =>  the spline is >= 0 on the interval.  With the correction active the
@@ -1033,12 +1037,13 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
       auto flush = [&](int m, double W0, double W1, double W2, double W3, int c_start, int c_end) {
         static_assert(kNEC == 8, "one flag byte per energy, read as one 64-bit word");
         const unsigned long long fl = *reinterpret_cast<const unsigned long long*>(s_flag + (long)m * kNEC);
-        const double* cp = s_coef + (long)m * 4;
+        const double2* lop = s_lo + m;
+        const double2* hip = s_hi + m;
         if (fl == 0ull) {
 #pragma unroll
           for (int g = 0; g < kNEC; ++g) {
-            const double2 lo = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4);
-            const double2 hi = *reinterpret_cast<const double2*>(cp + (long)g * N_L * 4 + 2);
+            const double2 lo = lop[g * N_L];
+            const double2 hi = hip[g * N_L];
             acc[g] = fma(hi.y, W3, fma(hi.x, W2, fma(lo.y, W1, fma(lo.x, W0, acc[g]))));      // 4 DFMA
           }
         } else {
@@ -1054,8 +1059,8 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
 #pragma unroll
             for (int g = 0; g < kNEC; ++g) {
               if ((fl >> (8 * g)) & 1ull) {
-                const double* cg = cp + (long)g * N_L * 4;
-                const double f = cg[0] + d * (cg[1] + d * (cg[2] + d * cg[3]));
+                const double2 lo = lop[g * N_L], hi = hip[g * N_L];
+                const double f = lo.x + d * (lo.y + d * (hi.x + d * hi.y));
                 if (f > 0.0) acc[g] += A * f;
               }
             }
@@ -1063,8 +1068,8 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
 #pragma unroll
           for (int g = 0; g < kNEC; ++g) {
             if (!((fl >> (8 * g)) & 1ull)) {
-              const double* cg = cp + (long)g * N_L * 4;
-              acc[g] += cg[0] * W0 + cg[1] * W1 + cg[2] * W2 + cg[3] * W3;
+              const double2 lo = lop[g * N_L], hi = hip[g * N_L];
+              acc[g] += lo.x * W0 + lo.y * W1 + hi.x * W2 + hi.y * W3;
             }
           }
         }
