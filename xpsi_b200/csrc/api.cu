@@ -260,12 +260,13 @@ static int integrate_member(
   a.phase_interp = phase_interpolant;
   a.scale_by_energy = 1;
   a.flux = d_flux.p; a.status = d_status.p;
-  Dev<double> d_ws, d_wh, d_wslab, d_wslab2; Dev<int> d_wi;
+  Dev<double> d_ws, d_wh, d_wslab, d_wslab2, d_wcells; Dev<int> d_wi;
   {
     size_t nl, nh, ni, ns;
     xb::azinv_workspace_sizes(a, &nl, &nh, &ni, &ns);
     CK(d_ws.alloc(nl)); CK(d_wh.alloc(nh)); CK(d_wi.alloc(ni));
     if (!general) {
+      CK(d_wcells.alloc(2ul * n_rings * n_azi)); a.ws_cells = d_wcells.p;
       CK(d_wslab.alloc(ns));
       if (a.else_atm_ext == XPSI_B200_ATM_NUM4D) CK(d_wslab2.alloc(ns));
     }
@@ -273,7 +274,7 @@ static int integrate_member(
   a.ws_leaf = d_ws.p; a.ws_hdr = d_wh.p; a.ws_ihdr = d_wi.p; a.ws_slab = d_wslab.p; a.ws_slab2 = d_wslab2.p;
   cudaError_t e = general ? xb::launch_integrate_general(a, g_stream) : xb::launch_integrate_azinv(a, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, general ? "launch_integrate_general" : "launch_integrate_azinv");
-  g_launches += general ? 3 : ((hot_atm_ext == XPSI_B200_ATM_NUM4D) ? 5 : 3);
+  g_launches += general ? 3 : ((hot_atm_ext == XPSI_B200_ATM_NUM4D) ? 6 : 4);
   int status = 0;
   CK(d_flux.download(flux_out, (size_t)n_energies * n_phases));
   CK(d_status.download(&status, 1));
@@ -642,7 +643,7 @@ struct xpsi_b200_pipeline {
   Dev<double> flux, xin, folded, chan_lnL, expected, lnL;
   Dev<int> chan_status, status_q, status;
   Dev<unsigned long long> work;
-  Dev<double> ws_leaf, ws_hdr, ws_slab, ws_mom; Dev<int> ws_ihdr, ws_cnt; Dev<int2> ws_meta;
+  Dev<double> ws_leaf, ws_hdr, ws_slab, ws_mom, ws_cells; Dev<int> ws_ihdr, ws_cnt; Dev<int2> ws_meta;
   int mom_cap = 0;
   // embed inputs / scratch
   Dev<double> e_Req, e_rs, e_eps, e_zeta, e_colat, e_rad, e_temp, e_phish, e_maxAlpha, e_hrad, e_hcolat, e_hazi, e_extra;
@@ -777,6 +778,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   a.flux = p->flux.p; a.status = p->status_q.p;
   a.ws_leaf = p->ws_leaf.p; a.ws_hdr = p->ws_hdr.p; a.ws_ihdr = p->ws_ihdr.p; a.ws_slab = p->ws_slab.p;
   a.ws_mom = p->ws_mom.p; a.ws_meta = p->ws_meta.p; a.ws_cnt = p->ws_cnt.p; a.mom_cap = p->mom_cap;
+  a.ws_cells = p->ws_cells.p;
   a.work = p->count_work ? p->work.p : nullptr;
   if (a.work) CK(cudaMemsetAsync(p->work.p, 0, 4 * sizeof(unsigned long long), g_stream));
   cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
@@ -934,6 +936,7 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
     size_t nm, nt, nc;
     xb::azinv_moment_sizes(w, &nm, &nt, &nc);
     ok(p->ws_mom.alloc(nm)); ok(p->ws_meta.alloc(nt)); ok(p->ws_cnt.alloc(nc));
+    ok(p->ws_cells.alloc(Q * c.max_rings * 2 * (size_t)c.max_azi));
     p->mom_cap = w.mom_cap;
   }
   for (int i = 0; i < 5; ++i) ok(cudaEventCreate(&p->ev[i]));

@@ -94,10 +94,11 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
   __shared__ int s_J, s_jhalf, s_nimg;
   __shared__ int s_inv2[kMaxImages], s_dom[kMaxImages], s_mono[kMaxImages];
   __shared__ unsigned long long s_zlo[kMaxImages], s_zhi[kMaxImages];   // order-preserving keys
+  __shared__ unsigned long long s_mlo[kMaxImages], s_mhi[kMaxImages];   // same for mu*eta
 
   // ---- does the ring radiate? (pyx:286-296); a null mask means cellArea > 0 (HotRegion.py:965)
   if (tid == 0) { s_J = A_; s_jhalf = N_R - 1; }
-  if (tid < kMaxImages) { s_inv2[tid] = 0; s_dom[tid] = 0; s_mono[tid] = 0; s_zlo[tid] = ~0ull; s_zhi[tid] = 0ull; }
+  if (tid < kMaxImages) { s_inv2[tid] = 0; s_dom[tid] = 0; s_mono[tid] = 0; s_zlo[tid] = ~0ull; s_zhi[tid] = 0ull; s_mlo[tid] = ~0ull; s_mhi[tid] = 0ull; }
   __syncthreads();
   for (int j = tid; j < A_; j += kGeomThreads) {
     const bool rad = a.radiates ? (a.radiates[cell0 + j] == 1) : (a.cellArea[cell0 + j] > 0.0);
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
       atomicMin(&s_zlo[I], order_key(zstore));
       atomicMax(&s_zhi[I], order_key(zstore));
       wAbb[kdx] = mu * eta;
+      if (ATM == 2) { atomicMin(&s_mlo[I], order_key(mu * eta)); atomicMax(&s_mhi[I], order_key(mu * eta)); }
       wGeom[kdx] = mu * fabs(deriv) * Grav_z * eta * eta * eta / superlum;
       s_ptrue[I * N_L + kdx] = a.leaves[kdx] + lagv;
     }
@@ -407,6 +409,22 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
       zlo = fmin(zlo, key_order(s_zlo[I])); zhi = fmax(zhi, key_order(s_zhi[I]));
     }
     dh[0] = zlo; dh[1] = zhi;
+    if (ATM == 2) {
+      // mu rows of the table the ring's lit leaves reach: [m0, m1) packed into ih[11] (the flux CTAs copy only these)
+      double mlo = 1e300, mhi = -1e300;
+      for (int I = 0; I < n; ++I) {
+        if (s_mhi[I] == 0ull) continue;
+        mlo = fmin(mlo, key_order(s_mlo[I])); mhi = fmax(mhi, key_order(s_mhi[I]));
+      }
+      int m0 = 0, m1 = a.hot.nmu;
+      if (mlo <= mhi) {
+        View vM{a.hot.mu, 1};
+        m0 = lagrange_base(vM, a.hot.nmu, mlo);
+        m1 = min(lagrange_base(vM, a.hot.nmu, mhi) + 4, a.hot.nmu);
+      }
+      dh[15] = mlo; dh[kCorrD + 15] = mhi;
+      ih[11] = m0 | (m1 << 16);
+    }
   }
   __syncthreads();
   n_img = s_nimg;
@@ -644,6 +662,17 @@ __device__ __forceinline__ int compact_cells(const AzinvArgs& a, long cell0, int
   return base;
 }
 
+// the compact list alone, for launches without a moments workspace (one warp per ring)
+__global__ void __launch_bounds__(32) k_azinv_cells(AzinvArgs a) {
+  const int i = blockIdx.x, q = blockIdx.y;
+  const long ring = (long)q * a.n_rings + i;
+  if (a.ws_ihdr[ring * kIHdr] == 0) return;
+  const int A_ = a.n_azi_q ? a.n_azi_q[q] : a.n_azi;
+  double* gc = a.ws_cells + ring * 2 * (long)a.n_azi;
+  const int n = compact_cells(a, ring * a.n_azi, A_, threadIdx.x, gc, gc + a.n_azi);
+  if (threadIdx.x == 0) a.ws_ihdr[ring * kIHdr + 10] = n;
+}
+
 // ===========================================================================
 // moments: the cell walk is identical for all energy chunks of a ring, so it is done once per
 // (ring, image order) here and handed to the flux CTAs through an L2-resident workspace
@@ -667,6 +696,15 @@ __global__ void __launch_bounds__(kMomThreads) k_azinv_moments(AzinvArgs a) {
   if (tid < 32) { const int n = compact_cells(a, ring * a.n_azi, A_, tid, s_cphi, s_carea); if (tid == 0) s_ncell = n; }
   const int k = tid;
   const double phk = (k < N_P) ? a.phases[k] : 0.0;
+  __syncthreads();
+  // the compact list is also what the flux CTAs of this ring need (slow path only): published once here
+  // instead of being rebuilt by each of the ring's energy chunks
+  {
+    double* gc = a.ws_cells + ring * 2 * (long)a.n_azi;
+    const int n = s_ncell;
+    for (int j = tid; j < n; j += kMomThreads) { gc[j] = s_cphi[j]; gc[a.n_azi + j] = s_carea[j]; }
+    if (tid == 0) a.ws_ihdr[ring * kIHdr + 10] = n;
+  }
   for (int I = 0; I < n_img; ++I) {
     __syncthreads();
     const double* W = leaf_ptr(a.ws_leaf, ring, a.n_img_max, I, N_L);
@@ -710,15 +748,15 @@ __global__ void __launch_bounds__(kMomThreads) k_azinv_moments(AzinvArgs a) {
 // shared-memory view of one Num4D atmosphere inside a flux CTA
 struct SlabCtx {
   double* axE; double* invden; double* axMu; double* slab;
-  int nrows, elo_tab, nE, nmu;
+  int nrows, elo_tab, nE, nmu;            // nrows is even (rows are copied 16 bytes at a time)
   double inv_dE, log_kT;
   const double* mu_invden;            // global, [nmu-3][4]
 };
 
 __device__ __forceinline__ double* slab_ctx_carve(SlabCtx& c, double* sp, int N_L, int rows_max, int nmu) {
-  c.axE = sp; sp += rows_max;
+  c.axE = sp; sp += rows_max;                       // rows_max is even: every piece stays 16-byte aligned
   c.invden = sp; sp += 4 * rows_max;
-  c.axMu = sp; sp += nmu;
+  c.axMu = sp; sp += (nmu + 1) & ~1;
   c.slab = sp; sp += (long)nmu * rows_max;
   return sp;
 }
@@ -726,29 +764,36 @@ __device__ __forceinline__ double* slab_ctx_carve(SlabCtx& c, double* sp, int N_
 // copy the rows of the ring's slab this chunk reaches; returns false if they do not fit
 __device__ __forceinline__ bool slab_ctx_load(SlabCtx& c, const AtmTable& T, const double* ring_slab,
                                               int elo_ring, int2 chunk_rows, int rows_ring_stride,
-                                              int rows_max, int tid) {
+                                              int rows_max, int tid, int m0, int m1) {
   c.nrows = chunk_rows.y; c.elo_tab = chunk_rows.x; c.nE = T.nE; c.nmu = T.nmu;
+  int lo_c = c.elo_tab - elo_ring;
+  if (lo_c & 1) { --lo_c; --c.elo_tab; ++c.nrows; }  // start on an even row of the ring's slab: 16-byte aligned source
+  c.nrows = (c.nrows + 1) & ~1;                      // (rows_ring_stride is even, so a padding row stays inside the ring's slab)
   if (c.nrows > rows_max) return false;
-  const int lo_c = c.elo_tab - elo_ring;
   for (int m = tid; m < T.nmu; m += kFluxThreads) c.axMu[m] = T.mu[m];
-  for (int r = tid; r < c.nrows; r += kFluxThreads) c.axE[r] = T.logE[c.elo_tab + r];
+  // a padding row past the end of the table gets an unreachable axis value (its slab entries are never read:
+  // the chunk's row range already holds every stencil)
+  for (int r = tid; r < c.nrows; r += kFluxThreads) c.axE[r] = (c.elo_tab + r < T.nE) ? T.logE[c.elo_tab + r] : 1.0e300;
+  // [m0, m1): only the mu rows the ring's lit leaves reach (from the ring header)
   const double* src = ring_slab + lo_c;
-  const int sub = tid & 15, grp = tid >> 4;          // half a warp per mu row (a chunk reaches ~16 rows)
-  // asynchronous copy (LDGSTS): the rows are first needed two barriers later (stage 1 of the first image),
-  // so their L2 latency overlaps the cell list, the leaf arrays and the mu stencils
-  for (int m = grp; m < T.nmu; m += kFluxThreads / 16)
-    for (int e = sub; e < c.nrows; e += 16)
-      __pipeline_memcpy_async(&c.slab[m * c.nrows + e], &src[(long)m * rows_ring_stride + e], sizeof(double));
+  const int half = c.nrows >> 1;
+  const int sub = tid & 7, grp = tid >> 3;           // 8 lanes x 16 bytes per mu row (a chunk reaches ~16 rows)
+  // asynchronous copy (LDGSTS.128): the rows are first needed two barriers later (stage 1 of the first image),
+  // so their L2 latency overlaps the leaf arrays and the mu stencils
+  for (int m = m0 + grp; m < m1; m += kFluxThreads / 8)
+    for (int e = sub; e < half; e += 8)
+      __pipeline_memcpy_async(&c.slab[m * c.nrows + 2 * e], &src[(long)m * rows_ring_stride + 2 * e], 2 * sizeof(double));
   __pipeline_commit();
   return true;
 }
 
 __device__ __forceinline__ void slab_ctx_finish(SlabCtx& c, const AtmTable& T, int tid) {     // after a barrier
   // Lagrange denominators per base row: copied from the table's precomputed list
-  for (int r = tid; r < 4 * (c.nrows - 3); r += kFluxThreads) c.invden[r] = __ldg(T.E_invden + 4 * c.elo_tab + r);
+  const int nv = min(c.nrows, c.nE - c.elo_tab);                     // rows inside the table
+  for (int r = tid; r < 4 * (nv - 3); r += kFluxThreads) c.invden[r] = __ldg(T.E_invden + 4 * c.elo_tab + r);
   c.mu_invden = T.mu_invden;
   // mean spacing of the axis segment: first guess of the energy stencil (then walked)
-  c.inv_dE = (c.nrows > 1) ? (double)(c.nrows - 1) / (c.axE[c.nrows - 1] - c.axE[0]) : 0.0;
+  c.inv_dE = (nv > 1) ? (double)(nv - 1) / (c.axE[nv - 1] - c.axE[0]) : 0.0;
 }
 
 // mu stencil of one leaf, kept in registers by the thread that owns the leaf
@@ -835,7 +880,6 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
   const int n_img = ih[0];
   if (n_img == 0) return;
   const double* dh = a.ws_hdr + ring * kDHdr;
-  const int A_ = a.n_azi_q ? a.n_azi_q[q] : a.n_azi;
   const int N_E = a.n_energies, N_L = a.n_leaves, N_P = a.n_phases;
   const long cell0 = ring * a.n_azi;
   const int e0 = chunk * kNEC;
@@ -843,13 +887,14 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
   const int n_img_max = a.n_img_max;
 
   extern __shared__ double smem[];
-  __shared__ int s_ncell;
   __shared__ double s_E[kNEC], s_logE[kNEC];
   const double kT = dh[12], log_kT = dh[13], norm = dh[14];
   const double kT_c = dh[kCorrD + 12], log_kT_c = dh[kCorrD + 13], norm_c = dh[kCorrD + 14];
   double* sp = smem;
-  double* s_cphi = sp; sp += a.n_azi;
-  double* s_carea = sp; sp += a.n_azi;
+  // radiating cells of the ring in azimuth order (azimuths, then areas at + n_azi): published once per ring by
+  // k_azinv_moments / k_azinv_cells; only the slow paths below read them.  The address is formed where it is
+  // used: no registers across the hot loop
+  auto cells = [&]() -> const double* { return a.ws_cells + ring * 2 * (long)a.n_azi; };
   double* s_PH = sp; sp += N_L;
   double* s_aux = sp; sp += N_L;          // 1/h of the leaf intervals
   // cubic pieces of the chunk's energies in two planes of 16-byte pairs: s_lo[e][l] = (y, b), s_hi[e][l] = (c, d).
@@ -858,17 +903,15 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
   double* s_coef = sp; sp += (long)kNEC * N_L * 4;
   double2* s_lo = reinterpret_cast<double2*>(s_coef);
   double2* s_hi = s_lo + (long)kNEC * N_L;
+  unsigned char* s_flag = reinterpret_cast<unsigned char*>(sp);     // [N_L][kNEC]: 1 = cubic may dip below zero
+  sp += (N_L + 1) & ~1;                                             // kNEC = 8 flag bytes = one double per leaf
   SlabCtx hot, els;
   if (ATM == 2) sp = slab_ctx_carve(hot, sp, N_L, a.slab_ne_max, a.hot.nmu);
   if (CORR == 2) sp = slab_ctx_carve(els, sp, N_L, a.slab_ne_max, a.els.nmu);
-  unsigned char* s_flag = reinterpret_cast<unsigned char*>(sp);     // [N_L][kNEC]: 1 = cubic may dip below zero
 
   // ---- compact list of the ring's radiating cells (one warp: keeps azimuth order) ------
-  if (tid < 32) {
-    const int n = compact_cells(a, cell0, A_, tid, s_cphi, s_carea);
-    if (tid == 0) s_ncell = n;
-  } else if (tid < 32 + kNEC) {
-    const int e = tid - 32;
+  if (tid < kNEC) {
+    const int e = tid;
     s_E[e] = a.energies[e0 + (e < ne ? e : 0)];
     s_logE[e] = a.log10_energies[e0 + (e < ne ? e : 0)];
   }
@@ -877,8 +920,9 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
   if (ATM == 2) {
     const int2 cr = reinterpret_cast<const int2*>(a.ws_chunk)[ring * n_chunks + chunk];
     hot.log_kT = log_kT;
+    const int mrows = BEAM ? (a.hot.nmu << 16) : ih[11];     // beaming option 3 sweeps the whole mu axis
     if (!slab_ctx_load(hot, a.hot, a.ws_slab + ring * (long)a.hot.nmu * a.slab_rows_ring, ih[4], cr,
-                       a.slab_rows_ring, a.slab_ne_max, tid)) {
+                       a.slab_rows_ring, a.slab_ne_max, tid, mrows & 0xffff, mrows >> 16)) {
       if (tid == 0) atomicExch(a.status + q, kUnsupported);   // budget too small: refuse, never clamp
       return;
     }
@@ -887,13 +931,13 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
     const int2 cr = reinterpret_cast<const int2*>(a.ws_chunk)[((long)a.Q * a.n_rings + ring) * n_chunks + chunk];
     els.log_kT = log_kT_c;
     if (!slab_ctx_load(els, a.els, a.ws_slab2 + ring * (long)a.els.nmu * a.slab_rows_ring, ih[8], cr,
-                       a.slab_rows_ring, a.slab_ne_max, tid)) {
+                       a.slab_rows_ring, a.slab_ne_max, tid, 0, a.els.nmu)) {
       if (tid == 0) atomicExch(a.status + q, kUnsupported);
       return;
     }
   }
   __syncthreads();
-  const int n_cells = s_ncell;
+  const int n_cells = ih[10];
   if (n_cells == 0) return;
   if (ATM == 2) slab_ctx_finish(hot, a.hot, tid);
   if (CORR == 2) slab_ctx_finish(els, a.els, tid);
@@ -1050,12 +1094,13 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
           // some energy's cubic may dip below zero on this interval: the reference adds a cell
           // only where the spline is positive (pyx:593), so go cell by cell for those energies
           const double xm = s_PH[m];
+          const double* s_cphi = cells();
           for (int cc = c_start; cc < c_end; ++cc) {
             double xr = phk + s_cphi[cc];
             if (xr > ph_last) { while (xr > ph_last) xr -= kTwoPi; }
             else if (xr < ph_first) { while (xr < ph_first) xr += kTwoPi; }
             const double d = xr - xm;
-            const double A = s_carea[cc];
+            const double A = s_cphi[a.n_azi + cc];
 #pragma unroll
             for (int g = 0; g < kNEC; ++g) {
               if ((fl >> (8 * g)) & 1ull) {
@@ -1095,7 +1140,7 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
           flush(mt.x, W0, W1, W2, W3, mt.y & 0xffff, mt.y >> 16);
         }
       } else {
-        walk_cells(phk, s_PH, N_L, s_cphi, s_carea, n_cells, a.status + q, flush);
+        walk_cells(phk, s_PH, N_L, cells(), cells() + a.n_azi, n_cells, a.status + q, flush);
       }
     }
   }
@@ -1138,10 +1183,11 @@ cudaError_t launch_azinv_geometry(const AzinvArgs& a, cudaStream_t stream) {
 }
 
 static size_t flux_smem_bytes(const AzinvArgs& a, int atm, int corr) {
-  size_t d = 2ul * a.n_azi + 2ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 4;
-  if (atm == 2) d += 5ul * a.slab_ne_max + a.hot.nmu + (size_t)a.hot.nmu * a.slab_ne_max;
-  if (corr == 2) d += 5ul * a.slab_ne_max + a.els.nmu + (size_t)a.els.nmu * a.slab_ne_max;
-  return d * sizeof(double) + (size_t)a.n_leaves * kNEC;
+  size_t d = 2ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 4;
+  if (atm == 2) d += 5ul * a.slab_ne_max + ((a.hot.nmu + 1) & ~1) + (size_t)a.hot.nmu * a.slab_ne_max;
+  if (corr == 2) d += 5ul * a.slab_ne_max + ((a.els.nmu + 1) & ~1) + (size_t)a.els.nmu * a.slab_ne_max;
+  d += (a.n_leaves + 1) & ~1;              // flag bytes: kNEC = 8 per leaf
+  return d * sizeof(double);
 }
 
 // Doppler spread of log10 Z over one ring allowed for when sizing buffers:
@@ -1169,17 +1215,20 @@ void azinv_workspace_sizes(const AzinvArgs& a, size_t* leaf_doubles, size_t* hdr
 
 void azinv_slab_budgets(const AtmTable& t, const double* energies, int n_energies, int* rows_chunk,
                         int* rows_ring) {
-  if (t.min_dlogE <= 0.0) { *rows_chunk = t.nE; *rows_ring = t.nE; return; }
+  if (t.min_dlogE <= 0.0) { *rows_chunk = (t.nE + 1) & ~1; *rows_ring = (t.nE + 1) & ~1; return; }
   double span = 0.0;
   for (int e0 = 0; e0 < n_energies; e0 += kNEC) {
     const int e1 = (e0 + kNEC < n_energies ? e0 + kNEC : n_energies) - 1;
     const double s = log10(energies[e1] / energies[e0]);
     if (s > span) span = s;
   }
-  int rc = (int)ceil((span + kDopplerDex) / t.min_dlogE) + 6;
+  // chunk rows: + 2 for the 16-byte alignment of the copies (even first row, even row count); both budgets even
+  int rc = (int)ceil((span + kDopplerDex) / t.min_dlogE) + 6 + 2;
   int rr = (int)ceil((log10(energies[n_energies - 1] / energies[0]) + kDopplerDex) / t.min_dlogE) + 6;
-  *rows_chunk = rc > t.nE ? t.nE : rc;
-  *rows_ring = rr > t.nE ? t.nE : rr;
+  const int nE_even = (t.nE + 1) & ~1;
+  rc = (rc + 1) & ~1; rr = (rr + 1) & ~1;
+  *rows_chunk = rc > nE_even ? nE_even : rc;
+  *rows_ring = rr > nE_even ? nE_even : rr;
 }
 
 template <int ATM, int CORR, int BEAM, int CUBIC>
@@ -1228,11 +1277,12 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
     k_azinv_slab<<<ggrid, kSlabThreads, 0, stream>>>(a, 1);
     k_azinv_slab_member<<<dim3((a.els.nmu + kSlabMRows - 1) / kSlabMRows, a.Q), kSlabMThreads, msm, stream>>>(a, 1);
   }
+  if (!a.ws_cells) return cudaErrorInvalidValue;
   if (a.ws_mom) {
     if (!a.ws_meta || !a.ws_cnt || a.mom_cap < 1 || a.n_azi > 0xffff) return cudaErrorInvalidValue;
     const size_t msm = (2ul * a.n_azi + a.n_leaves) * sizeof(double) + 2ul * a.n_leaves;
     k_azinv_moments<<<ggrid, kMomThreads, msm, stream>>>(a);
-  }
+  } else k_azinv_cells<<<ggrid, 32, 0, stream>>>(a);
   if ((err = cudaGetLastError()) != cudaSuccess) return err;
   if (atm == 1 && corr == 0) err = launch_flux<1, 0>(a, fgrid, fsm, stream);
   else if (atm == 1 && corr == 1) err = launch_flux<1, 1>(a, fgrid, fsm, stream);

@@ -57,6 +57,7 @@ struct AzinvArgs {
   double* ws_slab2;                  // same for a Num4D elsewhere correction
   // optional: interval moments of the cell walk, shared by a ring's energy chunks (azinv_moment_sizes)
   double* ws_mom; int2* ws_meta; int* ws_cnt; int mom_cap;
+  double* ws_cells;                  // with ws_mom: [Q][n_rings][2][n_azi] compact (azimuth, area) lists of the radiating cells
   unsigned long long* work;          // nullptr or [4]: H half-leaf visits, V visible leaves,
                                      //   RI (ring,image) pairs reaching the phase stage, K radiating cells over RI
 };
