@@ -768,7 +768,8 @@ __device__ __forceinline__ bool slab_ctx_load(SlabCtx& c, const AtmTable& T, con
   c.nrows = chunk_rows.y; c.elo_tab = chunk_rows.x; c.nE = T.nE; c.nmu = T.nmu;
   int lo_c = c.elo_tab - elo_ring;
   if (lo_c & 1) { --lo_c; --c.elo_tab; ++c.nrows; }  // start on an even row of the ring's slab: 16-byte aligned source
-  c.nrows = (c.nrows + 1) & ~1;                      // (rows_ring_stride is even, so a padding row stays inside the ring's slab)
+  c.nrows = (c.nrows + 1) & ~1;
+  if ((c.nrows & 3) == 0) c.nrows += 2;              // row stride = 2 (mod 4) doubles: mu rows 1..7 apart fall on different banks
   if (c.nrows > rows_max) return false;
   for (int m = tid; m < T.nmu; m += kFluxThreads) c.axMu[m] = T.mu[m];
   // a padding row past the end of the table gets an unreachable axis value (its slab entries are never read:
@@ -776,7 +777,7 @@ __device__ __forceinline__ bool slab_ctx_load(SlabCtx& c, const AtmTable& T, con
   for (int r = tid; r < c.nrows; r += kFluxThreads) c.axE[r] = (c.elo_tab + r < T.nE) ? T.logE[c.elo_tab + r] : 1.0e300;
   // [m0, m1): only the mu rows the ring's lit leaves reach (from the ring header)
   const double* src = ring_slab + lo_c;
-  const int half = c.nrows >> 1;
+  const int half = min(c.nrows, rows_ring_stride - lo_c) >> 1;      // padding rows past the ring's slab row are not copied
   const int sub = tid & 7, grp = tid >> 3;           // 8 lanes x 16 bytes per mu row (a chunk reaches ~16 rows)
   // asynchronous copy (LDGSTS.128): the rows are first needed two barriers later (stage 1 of the first image),
   // so their L2 latency overlaps the leaf arrays and the mu stencils
@@ -888,6 +889,8 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
 
   extern __shared__ double smem[];
   __shared__ double s_E[kNEC], s_logE[kNEC];
+  constexpr int kLitWords = 8;                    // lit-leaf bits of the current image (used when N_L <= 256)
+  __shared__ unsigned s_litmask[kLitWords];
   const double kT = dh[12], log_kT = dh[13], norm = dh[14];
   const double kT_c = dh[kCorrD + 12], log_kT_c = dh[kCorrD + 13], norm_c = dh[kCorrD + 14];
   double* sp = smem;
@@ -959,8 +962,14 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
     __syncthreads();
     for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
     // ---- (1) leaf profile (pyx:445-478): thread = leaf, the mu stencil is shared by the chunk's energies -----
-    for (int l = tid; l < N_L; l += kFluxThreads) {
-      const double geom = W[3 * N_L + l];
+    for (int lb = 0; lb < N_L; lb += kFluxThreads) {
+      const int l = lb + tid;
+      const double geom = (l < N_L) ? W[3 * N_L + l] : 0.0;
+      {                                     // which leaves are lit: lets stage 2 skip blocks of dark intervals
+        const unsigned lit = __ballot_sync(0xffffffffu, geom != 0.0);
+        if ((tid & 31) == 0 && (l >> 5) < kLitWords) s_litmask[l >> 5] = lit;
+      }
+      if (l >= N_L) continue;
       if (geom == 0.0) {
 #pragma unroll
         for (int e = 0; e < kNEC; ++e) s_coef[((long)e * N_L + l) * 2] = 0.0;
@@ -998,7 +1007,21 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
       const int e = tid / kBlk, blk = tid - e * kBlk;
       const int per = (N_L - 1 + kBlk - 1) / kBlk;
       const int l0 = blk * per, l1 = min(l0 + per, N_L - 1);
-      if (l0 < l1) {                 // all kNEC energies (a short last chunk repeats its first energy)
+      // a block whose leaves l0-2 .. l1+2 (periodic) are all dark holds identically zero cubics for every
+      // interpolant (Akima's node slopes reach two intervals to each side): nothing to compute
+      bool dark = (!CUBIC && l0 < l1 && N_L <= 32 * kLitWords);
+      for (int l = l0 - 2; dark && l <= l1 + 2; ++l) {
+        int lw = l;
+        if (lw < 0) lw += N_L - 1; else if (lw > N_L - 1) lw -= N_L - 1;
+        if ((s_litmask[lw >> 5] >> (lw & 31)) & 1u) dark = false;
+      }
+      if (dark) {
+        for (int l = l0; l < l1; ++l) {
+          s_coef[((long)e * N_L + l) * 2 + 1] = 0.0;
+          s_hi[(long)e * N_L + l] = make_double2(0.0, 0.0);
+          s_flag[l * kNEC + e] = 0;
+        }
+      } else if (l0 < l1) {          // all kNEC energies (a short last chunk repeats its first energy)
         const View y{s_coef + (long)e * N_L * 2, 2};          // node values: slot 0 of every (y, b) pair of this energy
         auto emit = [&](int l, double b, double c, double d) {
           const double y0 = y[l];
@@ -1215,19 +1238,23 @@ void azinv_workspace_sizes(const AzinvArgs& a, size_t* leaf_doubles, size_t* hdr
 
 void azinv_slab_budgets(const AtmTable& t, const double* energies, int n_energies, int* rows_chunk,
                         int* rows_ring) {
-  if (t.min_dlogE <= 0.0) { *rows_chunk = (t.nE + 1) & ~1; *rows_ring = (t.nE + 1) & ~1; return; }
+  if (t.min_dlogE <= 0.0) { int rc = t.nE + 1; while ((rc & 3) != 2) ++rc; *rows_chunk = rc; *rows_ring = (t.nE + 1) & ~1; return; }
   double span = 0.0;
   for (int e0 = 0; e0 < n_energies; e0 += kNEC) {
     const int e1 = (e0 + kNEC < n_energies ? e0 + kNEC : n_energies) - 1;
     const double s = log10(energies[e1] / energies[e0]);
     if (s > span) span = s;
   }
-  // chunk rows: + 2 for the 16-byte alignment of the copies (even first row, even row count); both budgets even
-  int rc = (int)ceil((span + kDopplerDex) / t.min_dlogE) + 6 + 2;
+  // chunk rows: + 1 for starting on an even row (16-byte aligned copies), then up to the next count = 2 (mod 4)
+  // (the shared-memory row stride, slab_ctx_load); the ring budget is even
+  int rc = (int)ceil((span + kDopplerDex) / t.min_dlogE) + 6;
   int rr = (int)ceil((log10(energies[n_energies - 1] / energies[0]) + kDopplerDex) / t.min_dlogE) + 6;
+  if (rc > t.nE) rc = t.nE;
+  rc += 1;
+  while ((rc & 3) != 2) ++rc;
   const int nE_even = (t.nE + 1) & ~1;
-  rc = (rc + 1) & ~1; rr = (rr + 1) & ~1;
-  *rows_chunk = rc > nE_even ? nE_even : rc;
+  rr = (rr + 1) & ~1;
+  *rows_chunk = rc;
   *rows_ring = rr > nE_even ? nE_even : rr;
 }
 
