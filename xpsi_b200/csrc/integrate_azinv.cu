@@ -20,10 +20,11 @@
 //   energy rows the ring can reach, written to an L2-resident workspace.
 //
 // k_azinv_flux<ATM>  one CTA per (q, ring, chunk of 8 energies): thousands of
-//   small CTAs, ~50 KB of shared memory each, 4 resident per SM.
-//   * Num4D: the ~16 energy rows of the ring's slab this chunk can reach are
-//     copied to shared memory; every intensity is then a 4x4 stencil on-chip
-//     with precomputed Lagrange denominators.
+//   small CTAs, ~42 KB of shared memory each, 5 resident per SM.
+//   * Num4D: the (mu, energy-row) tile of the ring's slab this chunk can reach
+//     (67 x ~22 doubles) is fetched into shared memory by one TMA tensor copy
+//     (cp.async.bulk.tensor.2d, completion on an mbarrier); every intensity is
+//     then a 4x4 stencil on-chip with precomputed Lagrange denominators.
 //   * the leaf profile and its phase-spline (Akima periodic / Steffen)
 //     coefficients are built in shared memory.
 //   * accumulation over the ring's cells uses interval moments: for an output
@@ -35,7 +36,9 @@
 //     (pyx:593); intervals whose cubic is not provably non-negative (Bernstein
 //     coefficients) are flagged per energy and evaluated cell by cell.
 //   * rings/chunks are combined with fp64 RED atomics into flux[q, E, P].
-#include <cuda_pipeline.h>
+#include <string.h>
+#include <cuda.h>            // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no -lcuda)
+#include <cuda/ptx>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -94,11 +97,10 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
   __shared__ int s_J, s_jhalf, s_nimg;
   __shared__ int s_inv2[kMaxImages], s_dom[kMaxImages], s_mono[kMaxImages];
   __shared__ unsigned long long s_zlo[kMaxImages], s_zhi[kMaxImages];   // order-preserving keys
-  __shared__ unsigned long long s_mlo[kMaxImages], s_mhi[kMaxImages];   // same for mu*eta
 
   // ---- does the ring radiate? (pyx:286-296); a null mask means cellArea > 0 (HotRegion.py:965)
   if (tid == 0) { s_J = A_; s_jhalf = N_R - 1; }
-  if (tid < kMaxImages) { s_inv2[tid] = 0; s_dom[tid] = 0; s_mono[tid] = 0; s_zlo[tid] = ~0ull; s_zhi[tid] = 0ull; s_mlo[tid] = ~0ull; s_mhi[tid] = 0ull; }
+  if (tid < kMaxImages) { s_inv2[tid] = 0; s_dom[tid] = 0; s_mono[tid] = 0; s_zlo[tid] = ~0ull; s_zhi[tid] = 0ull; }
   __syncthreads();
   for (int j = tid; j < A_; j += kGeomThreads) {
     const bool rad = a.radiates ? (a.radiates[cell0 + j] == 1) : (a.cellArea[cell0 + j] > 0.0);
@@ -228,7 +230,6 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
       atomicMin(&s_zlo[I], order_key(zstore));
       atomicMax(&s_zhi[I], order_key(zstore));
       wAbb[kdx] = mu * eta;
-      if (ATM == 2) { atomicMin(&s_mlo[I], order_key(mu * eta)); atomicMax(&s_mhi[I], order_key(mu * eta)); }
       wGeom[kdx] = mu * fabs(deriv) * Grav_z * eta * eta * eta / superlum;
       s_ptrue[I * N_L + kdx] = a.leaves[kdx] + lagv;
     }
@@ -409,22 +410,6 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
       zlo = fmin(zlo, key_order(s_zlo[I])); zhi = fmax(zhi, key_order(s_zhi[I]));
     }
     dh[0] = zlo; dh[1] = zhi;
-    if (ATM == 2) {
-      // mu rows of the table the ring's lit leaves reach: [m0, m1) packed into ih[11] (the flux CTAs copy only these)
-      double mlo = 1e300, mhi = -1e300;
-      for (int I = 0; I < n; ++I) {
-        if (s_mhi[I] == 0ull) continue;
-        mlo = fmin(mlo, key_order(s_mlo[I])); mhi = fmax(mhi, key_order(s_mhi[I]));
-      }
-      int m0 = 0, m1 = a.hot.nmu;
-      if (mlo <= mhi) {
-        View vM{a.hot.mu, 1};
-        m0 = lagrange_base(vM, a.hot.nmu, mlo);
-        m1 = min(lagrange_base(vM, a.hot.nmu, mhi) + 4, a.hot.nmu);
-      }
-      dh[15] = mlo; dh[kCorrD + 15] = mhi;
-      ih[11] = m0 | (m1 << 16);
-    }
   }
   __syncthreads();
   n_img = s_nimg;
@@ -753,39 +738,35 @@ struct SlabCtx {
   const double* mu_invden;            // global, [nmu-3][4]
 };
 
+// The slab comes first in dynamic shared memory (TMA destinations want 128-byte alignment); the small axis
+// arrays are carved later
+__device__ __forceinline__ double* slab_ctx_carve_slab(SlabCtx& c, double* sp, int rows_max, int nmu) {
+  c.slab = sp; sp += ((long)nmu * rows_max + 15) & ~15l;
+  return sp;
+}
 __device__ __forceinline__ double* slab_ctx_carve(SlabCtx& c, double* sp, int N_L, int rows_max, int nmu) {
   c.axE = sp; sp += rows_max;                       // rows_max is even: every piece stays 16-byte aligned
   c.invden = sp; sp += 4 * rows_max;
   c.axMu = sp; sp += (nmu + 1) & ~1;
-  c.slab = sp; sp += (long)nmu * rows_max;
   return sp;
 }
 
-// copy the rows of the ring's slab this chunk reaches; returns false if they do not fit
-__device__ __forceinline__ bool slab_ctx_load(SlabCtx& c, const AtmTable& T, const double* ring_slab,
-                                              int elo_ring, int2 chunk_rows, int rows_ring_stride,
-                                              int rows_max, int tid, int m0, int m1) {
-  c.nrows = chunk_rows.y; c.elo_tab = chunk_rows.x; c.nE = T.nE; c.nmu = T.nmu;
-  int lo_c = c.elo_tab - elo_ring;
-  if (lo_c & 1) { --lo_c; --c.elo_tab; ++c.nrows; }  // start on an even row of the ring's slab: 16-byte aligned source
-  c.nrows = (c.nrows + 1) & ~1;
-  if ((c.nrows & 3) == 0) c.nrows += 2;              // row stride = 2 (mod 4) doubles: mu rows 1..7 apart fall on different banks
-  if (c.nrows > rows_max) return false;
+// Rows of the ring's slab this chunk reaches: the (mu, energy-row) tile [nmu][rows_max] starting at the chunk's first
+// row is fetched by ONE TMA tensor copy (cp.async.bulk.tensor.2d) issued by thread 0 -- columns past the ring's slab
+// row are zero-filled by the copy engine and are never read (the chunk's row range already holds every stencil).
+__device__ __forceinline__ void slab_ctx_load(SlabCtx& c, const AtmTable& T, const CUtensorMap* tmap, long ring,
+                                              int elo_ring, int2 chunk_rows, int rows_max, int tid,
+                                              uint64_t* mbar) {
+  c.nrows = rows_max; c.elo_tab = chunk_rows.x; c.nE = T.nE; c.nmu = T.nmu;
+  // the tile must start on a 16-byte boundary of global memory: an even row of the ring's slab
+  if ((c.elo_tab - elo_ring) & 1) --c.elo_tab;
+  if (tid == 0) {
+    const int coords[2] = {c.elo_tab - elo_ring, (int)(ring * T.nmu)};
+    cuda::ptx::cp_async_bulk_tensor(cuda::ptx::space_cluster, cuda::ptx::space_global, c.slab, tmap, coords, mbar);
+  }
   for (int m = tid; m < T.nmu; m += kFluxThreads) c.axMu[m] = T.mu[m];
-  // a padding row past the end of the table gets an unreachable axis value (its slab entries are never read:
-  // the chunk's row range already holds every stencil)
+  // tile rows past the end of the table get an unreachable axis value
   for (int r = tid; r < c.nrows; r += kFluxThreads) c.axE[r] = (c.elo_tab + r < T.nE) ? T.logE[c.elo_tab + r] : 1.0e300;
-  // [m0, m1): only the mu rows the ring's lit leaves reach (from the ring header)
-  const double* src = ring_slab + lo_c;
-  const int half = min(c.nrows, rows_ring_stride - lo_c) >> 1;      // padding rows past the ring's slab row are not copied
-  const int sub = tid & 7, grp = tid >> 3;           // 8 lanes x 16 bytes per mu row (a chunk reaches ~16 rows)
-  // asynchronous copy (LDGSTS.128): the rows are first needed two barriers later (stage 1 of the first image),
-  // so their L2 latency overlaps the leaf arrays and the mu stencils
-  for (int m = m0 + grp; m < m1; m += kFluxThreads / 8)
-    for (int e = sub; e < half; e += 8)
-      __pipeline_memcpy_async(&c.slab[m * c.nrows + 2 * e], &src[(long)m * rows_ring_stride + 2 * e], 2 * sizeof(double));
-  __pipeline_commit();
-  return true;
 }
 
 __device__ __forceinline__ void slab_ctx_finish(SlabCtx& c, const AtmTable& T, int tid) {     // after a barrier
@@ -870,7 +851,8 @@ __device__ __noinline__ double profile_beaming(int beam_opt, const SlabCtx& hot,
 // CUBIC: 1 = the global C2 phase spline (its solver needs 6 KB of per-thread local memory, kept out of the
 // default instantiation)
 template <int ATM, int CORR, int BEAM, int CUBIC>
-__global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flux(AzinvArgs a) {
+__global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5)
+k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __grid_constant__ CUtensorMap tm_els) {
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
   const int i = blockIdx.x / n_chunks;
   const int chunk = blockIdx.x - i * n_chunks;
@@ -887,13 +869,17 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
   const int ne = min(kNEC, N_E - e0);
   const int n_img_max = a.n_img_max;
 
-  extern __shared__ double smem[];
+  extern __shared__ __align__(128) double smem[];
   __shared__ double s_E[kNEC], s_logE[kNEC];
+  __shared__ __align__(8) uint64_t s_mbar;                // completion barrier of the slab copies
   constexpr int kLitWords = 8;                    // lit-leaf bits of the current image (used when N_L <= 256)
   __shared__ unsigned s_litmask[kLitWords];
   const double kT = dh[12], log_kT = dh[13], norm = dh[14];
   const double kT_c = dh[kCorrD + 12], log_kT_c = dh[kCorrD + 13], norm_c = dh[kCorrD + 14];
   double* sp = smem;
+  SlabCtx hot, els;
+  if (ATM == 2) sp = slab_ctx_carve_slab(hot, sp, a.slab_ne_max, a.hot.nmu);
+  if (CORR == 2) sp = slab_ctx_carve_slab(els, sp, a.slab_ne_max, a.els.nmu);
   // radiating cells of the ring in azimuth order (azimuths, then areas at + n_azi): published once per ring by
   // k_azinv_moments / k_azinv_cells; only the slow paths below read them.  The address is formed where it is
   // used: no registers across the hot loop
@@ -908,7 +894,6 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
   double2* s_hi = s_lo + (long)kNEC * N_L;
   unsigned char* s_flag = reinterpret_cast<unsigned char*>(sp);     // [N_L][kNEC]: 1 = cubic may dip below zero
   sp += (N_L + 1) & ~1;                                             // kNEC = 8 flag bytes = one double per leaf
-  SlabCtx hot, els;
   if (ATM == 2) sp = slab_ctx_carve(hot, sp, N_L, a.slab_ne_max, a.hot.nmu);
   if (CORR == 2) sp = slab_ctx_carve(els, sp, N_L, a.slab_ne_max, a.els.nmu);
 
@@ -919,29 +904,35 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
     s_logE[e] = a.log10_energies[e0 + (e < ne ? e : 0)];
   }
 
-  // ---- Num4D: copy the rows of the ring's slab(s) this chunk reaches ------------------------
+  // ---- Num4D: fetch the tile of the ring's slab(s) this chunk reaches (TMA) ------------------------
+  const int n_cells = ih[10];
+  if (n_cells == 0) return;                   // (before any copy is in flight)
+  int2 cr_hot = make_int2(0, 0), cr_els = make_int2(0, 0);
+  if (ATM == 2) cr_hot = reinterpret_cast<const int2*>(a.ws_chunk)[ring * n_chunks + chunk];
+  if (CORR == 2) cr_els = reinterpret_cast<const int2*>(a.ws_chunk)[((long)a.Q * a.n_rings + ring) * n_chunks + chunk];
+  // rows needed, counting the one in front when the chunk starts on an odd row of the ring's slab (tile alignment)
+  if ((ATM == 2 && cr_hot.y + ((cr_hot.x - ih[4]) & 1) > a.slab_ne_max) ||
+      (CORR == 2 && cr_els.y + ((cr_els.x - ih[8]) & 1) > a.slab_ne_max)) {
+    if (tid == 0) atomicExch(a.status + q, kUnsupported);   // budget too small: refuse, never clamp
+    return;
+  }
+  if ((ATM == 2 || CORR == 2) && tid == 0) {
+    cuda::ptx::mbarrier_init(&s_mbar, 1);
+    cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+    const unsigned bytes = (unsigned)(((ATM == 2) ? a.hot.nmu : 0) + ((CORR == 2) ? a.els.nmu : 0)) *
+                           (unsigned)a.slab_ne_max * (unsigned)sizeof(double);
+    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared,
+                                         &s_mbar, bytes);
+  }
   if (ATM == 2) {
-    const int2 cr = reinterpret_cast<const int2*>(a.ws_chunk)[ring * n_chunks + chunk];
     hot.log_kT = log_kT;
-    const int mrows = BEAM ? (a.hot.nmu << 16) : ih[11];     // beaming option 3 sweeps the whole mu axis
-    if (!slab_ctx_load(hot, a.hot, a.ws_slab + ring * (long)a.hot.nmu * a.slab_rows_ring, ih[4], cr,
-                       a.slab_rows_ring, a.slab_ne_max, tid, mrows & 0xffff, mrows >> 16)) {
-      if (tid == 0) atomicExch(a.status + q, kUnsupported);   // budget too small: refuse, never clamp
-      return;
-    }
+    slab_ctx_load(hot, a.hot, &tm_hot, ring, ih[4], cr_hot, a.slab_ne_max, tid, &s_mbar);
   }
   if (CORR == 2) {
-    const int2 cr = reinterpret_cast<const int2*>(a.ws_chunk)[((long)a.Q * a.n_rings + ring) * n_chunks + chunk];
     els.log_kT = log_kT_c;
-    if (!slab_ctx_load(els, a.els, a.ws_slab2 + ring * (long)a.els.nmu * a.slab_rows_ring, ih[8], cr,
-                       a.slab_rows_ring, a.slab_ne_max, tid, 0, a.els.nmu)) {
-      if (tid == 0) atomicExch(a.status + q, kUnsupported);
-      return;
-    }
+    slab_ctx_load(els, a.els, &tm_els, ring, ih[8], cr_els, a.slab_ne_max, tid, &s_mbar);
   }
   __syncthreads();
-  const int n_cells = ih[10];
-  if (n_cells == 0) return;
   if (ATM == 2) slab_ctx_finish(hot, a.hot, tid);
   if (CORR == 2) slab_ctx_finish(els, a.els, tid);
 
@@ -958,7 +949,8 @@ __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5) k_azinv_flu
     // redshift / mu*eta / geometry factor stay in the registers of the thread that owns the leaf ---------
     const double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
     for (int l = tid; l < N_L; l += kFluxThreads) s_PH[l] = W[l];
-    if (ATM == 2 || CORR == 2) __pipeline_wait_prior(0);          // slab rows have landed (no-op after the first image)
+    if ((ATM == 2 || CORR == 2) && I == 0)                        // the slab tile has landed
+      while (!cuda::ptx::mbarrier_try_wait_parity(&s_mbar, 0u)) {}
     __syncthreads();
     for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
     // ---- (1) leaf profile (pyx:445-478): thread = leaf, the mu stencil is shared by the chunk's energies -----
@@ -1207,8 +1199,8 @@ cudaError_t launch_azinv_geometry(const AzinvArgs& a, cudaStream_t stream) {
 
 static size_t flux_smem_bytes(const AzinvArgs& a, int atm, int corr) {
   size_t d = 2ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 4;
-  if (atm == 2) d += 5ul * a.slab_ne_max + ((a.hot.nmu + 1) & ~1) + (size_t)a.hot.nmu * a.slab_ne_max;
-  if (corr == 2) d += 5ul * a.slab_ne_max + ((a.els.nmu + 1) & ~1) + (size_t)a.els.nmu * a.slab_ne_max;
+  if (atm == 2) d += 5ul * a.slab_ne_max + ((a.hot.nmu + 1) & ~1) + (((size_t)a.hot.nmu * a.slab_ne_max + 15) & ~15ul);
+  if (corr == 2) d += 5ul * a.slab_ne_max + ((a.els.nmu + 1) & ~1) + (((size_t)a.els.nmu * a.slab_ne_max + 15) & ~15ul);
   d += (a.n_leaves + 1) & ~1;              // flag bytes: kNEC = 8 per leaf
   return d * sizeof(double);
 }
@@ -1258,11 +1250,42 @@ void azinv_slab_budgets(const AtmTable& t, const double* energies, int n_energie
   *rows_ring = rr > nE_even ? nE_even : rr;
 }
 
+// 2-D tensor map over a slab workspace viewed as [Q * n_rings * nmu rows][slab_rows_ring doubles]; one box is the
+// (mu, energy-row) tile [nmu][slab_ne_max] a flux CTA keeps in shared memory
+static cudaError_t encode_slab_map(CUtensorMap* tm, const double* ws, const AzinvArgs& a, int nmu) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (qres != cudaDriverEntryPointSuccess || !ptr) return cudaErrorNotSupported;
+    fn = reinterpret_cast<EncodeFn>(ptr);
+  }
+  if (nmu > 256 || a.slab_ne_max > 256 || (a.slab_rows_ring & 1) || (a.slab_ne_max & 1)) return cudaErrorNotSupported;
+  const cuuint64_t gdim[2] = {(cuuint64_t)a.slab_rows_ring, (cuuint64_t)a.Q * a.n_rings * nmu};
+  const cuuint64_t gstride[1] = {(cuuint64_t)a.slab_rows_ring * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)a.slab_ne_max, (cuuint32_t)nmu};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ws), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int ATM, int CORR, int BEAM, int CUBIC>
 static cudaError_t launch_flux_b(const AzinvArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
-  cudaError_t err = cudaFuncSetAttribute(k_azinv_flux<ATM, CORR, BEAM, CUBIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  CUtensorMap tm_hot, tm_els;
+  memset(&tm_hot, 0, sizeof(tm_hot)); memset(&tm_els, 0, sizeof(tm_els));
+  cudaError_t err;
+  if (ATM == 2 && (err = encode_slab_map(&tm_hot, a.ws_slab, a, a.hot.nmu)) != cudaSuccess) return err;
+  if (CORR == 2 && (err = encode_slab_map(&tm_els, a.ws_slab2, a, a.els.nmu)) != cudaSuccess) return err;
+  err = cudaFuncSetAttribute(k_azinv_flux<ATM, CORR, BEAM, CUBIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  k_azinv_flux<ATM, CORR, BEAM, CUBIC><<<grid, kFluxThreads, smem, stream>>>(a);
+  k_azinv_flux<ATM, CORR, BEAM, CUBIC><<<grid, kFluxThreads, smem, stream>>>(a, tm_hot, tm_els);
   return cudaGetLastError();
 }
 template <int ATM, int CORR>
