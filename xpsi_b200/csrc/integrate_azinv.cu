@@ -876,10 +876,10 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
   __shared__ unsigned s_litmask[kLitWords];
   const double kT = dh[12], log_kT = dh[13], norm = dh[14];
   const double kT_c = dh[kCorrD + 12], log_kT_c = dh[kCorrD + 13], norm_c = dh[kCorrD + 14];
+  // layout: the arrays of the accumulation loop first, at offsets that depend on N_L only (their addresses are
+  // re-formed inside the loop rather than held in registers), then the TMA tile(s) on a 128-byte boundary
   double* sp = smem;
   SlabCtx hot, els;
-  if (ATM == 2) sp = slab_ctx_carve_slab(hot, sp, a.slab_ne_max, a.hot.nmu);
-  if (CORR == 2) sp = slab_ctx_carve_slab(els, sp, a.slab_ne_max, a.els.nmu);
   // radiating cells of the ring in azimuth order (azimuths, then areas at + n_azi): published once per ring by
   // k_azinv_moments / k_azinv_cells; only the slow paths below read them.  The address is formed where it is
   // used: no registers across the hot loop
@@ -893,7 +893,10 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
   double2* s_lo = reinterpret_cast<double2*>(s_coef);
   double2* s_hi = s_lo + (long)kNEC * N_L;
   unsigned char* s_flag = reinterpret_cast<unsigned char*>(sp);     // [N_L][kNEC]: 1 = cubic may dip below zero
-  sp += (N_L + 1) & ~1;                                             // kNEC = 8 flag bytes = one double per leaf
+  sp += N_L;                                                        // kNEC = 8 flag bytes = one double per leaf
+  sp = smem + (((sp - smem) + 15) & ~15l);
+  if (ATM == 2) sp = slab_ctx_carve_slab(hot, sp, a.slab_ne_max, a.hot.nmu);
+  if (CORR == 2) sp = slab_ctx_carve_slab(els, sp, a.slab_ne_max, a.els.nmu);
   if (ATM == 2) sp = slab_ctx_carve(hot, sp, N_L, a.slab_ne_max, a.hot.nmu);
   if (CORR == 2) sp = slab_ctx_carve(els, sp, N_L, a.slab_ne_max, a.els.nmu);
 
@@ -1140,18 +1143,16 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
         // moments prepared once per (ring, image) by k_azinv_moments; loads are coalesced over k
         const double* mom = a.ws_mom + slot * (long)a.mom_cap * 4 * N_P + k;
         const int2* meta = a.ws_meta + slot * (long)a.mom_cap * N_P + k;
-        // software pipeline: entry t+1 is in flight (L2) while entry t is consumed
+        // software pipeline: entry t+1 is in flight (L2) while entry t is consumed; the two pointers are bumped
+        // (no per-entry 64-bit index arithmetic)
         double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
         int2 nm = make_int2(0, 0);
         if (cnt > 0) { n0 = mom[0]; n1 = mom[N_P]; n2 = mom[2 * N_P]; n3 = mom[3 * N_P]; nm = meta[0]; }
-        for (int t = 0; t < cnt; ++t) {
+        for (int t = 1; t <= cnt; ++t) {
           const double W0 = n0, W1 = n1, W2 = n2, W3 = n3;
           const int2 mt = nm;
-          if (t + 1 < cnt) {
-            const double* e = mom + (long)(t + 1) * 4 * N_P;
-            n0 = e[0]; n1 = e[N_P]; n2 = e[2 * N_P]; n3 = e[3 * N_P];
-            nm = meta[(long)(t + 1) * N_P];
-          }
+          mom += 4 * N_P; meta += N_P;
+          if (t < cnt) { n0 = mom[0]; n1 = mom[N_P]; n2 = mom[2 * N_P]; n3 = mom[3 * N_P]; nm = meta[0]; }
           flush(mt.x, W0, W1, W2, W3, mt.y & 0xffff, mt.y >> 16);
         }
       } else {
@@ -1198,10 +1199,10 @@ cudaError_t launch_azinv_geometry(const AzinvArgs& a, cudaStream_t stream) {
 }
 
 static size_t flux_smem_bytes(const AzinvArgs& a, int atm, int corr) {
-  size_t d = 2ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 4;
+  size_t d = 2ul * a.n_leaves + (size_t)kNEC * a.n_leaves * 4 + a.n_leaves;     // phases, 1/h, cubic pieces, flags
+  d = (d + 15) & ~15ul;
   if (atm == 2) d += 5ul * a.slab_ne_max + ((a.hot.nmu + 1) & ~1) + (((size_t)a.hot.nmu * a.slab_ne_max + 15) & ~15ul);
   if (corr == 2) d += 5ul * a.slab_ne_max + ((a.els.nmu + 1) & ~1) + (((size_t)a.els.nmu * a.slab_ne_max + 15) & ~15ul);
-  d += (a.n_leaves + 1) & ~1;              // flag bytes: kNEC = 8 per leaf
   return d * sizeof(double);
 }
 
