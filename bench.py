@@ -184,13 +184,21 @@ def run_reference_sample(per_proc, procs):
     return n_total / slowest, n_total, slowest, wall_incl_setup, lnLs
 
 
+_JSON_FD = 1
+
+
+def emit(line):
+    """The one JSON line, written to the process's original stdout."""
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     procs = len(os.sched_getaffinity(0))
     if not reference_available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref not built on this box"})
         return 0
     per_proc = 4
     vals = []
@@ -214,7 +222,7 @@ def main_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -373,7 +381,7 @@ def main_ours(args):
         else:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                     "sample": "oracle/_ref absent on this box"}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -386,6 +394,11 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=512, help="parameter vectors per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
+    # stdout carries exactly one JSON line: whatever libraries print on fd 1 (NCCL's version banner under
+    # torchrun, warnings of the reference package) is sent to stderr
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     rc = main_reference(a) if a.impl == "reference" else main_ours(a)
     try:                                   # leave NCCL cleanly under torchrun
         import torch.distributed as _dist
