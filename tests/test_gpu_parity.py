@@ -940,3 +940,25 @@ def test_time_invariant_component_likelihood():
     print("time-invariant lnL", res[0], "ref", float(d["tinv_lnL"]))
     assert abs(res[0] - float(d["tinv_lnL"])) < LNL_ATOL
     assert rel_err(res[1], d["tinv_expected"]) < PULSE_RTOL and rel_err(res[2], d["tinv_bg"]) < 1e-6
+
+
+@pytest.mark.parametrize("shape,stride", [((5, 4, 9, 41), 1), ((6, 5, 67, 165), 1), ((4, 4, 5, 23), 1),
+                                          ((35, 14, 67, 166), 4), ((7, 4, 33, 91), 3)])
+def test_num4d_tables_of_odd_and_small_shapes(m2, shape, stride):
+    """Atmosphere tables whose axes are odd-sized, short or coarse: the slab tile a flux CTA fetches (one TMA box
+    of [n_mu][rows] doubles starting on an even row) then runs past the ring's slab row or past the end of the
+    table, and the row budgets shrink to a handful of rows.  Checked against the oracle on the M2 mesh and rays."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import oracle as orc
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.cellmesh.integrator_for_azimuthal_invariance import integrate
+    table = syn.nsx_like_table(shape)
+    args = list(_integrate_args(m2, "t0_int0_", table))
+    args[19] = np.ascontiguousarray(args[19][::stride])        # sparser energies: wider chunks, more rows per tile
+    status, flux = integrate(*args)
+    ref_status, ref = orc.integrate(*args)
+    assert status == 0 and ref_status == 0
+    err = _pulse_err(flux, ref)
+    print("table shape", shape, "energy stride", stride, "flux rel err vs oracle", err)
+    assert err < PULSE_RTOL
