@@ -850,7 +850,9 @@ __device__ __noinline__ double profile_beaming(int beam_opt, const SlabCtx& hot,
 // BEAM: 0 = no beaming code at all (keeps the common instantiation free of the call's register pressure)
 // CUBIC: 1 = the global C2 phase spline (its solver needs 6 KB of per-thread local memory, kept out of the
 // default instantiation)
-template <int ATM, int CORR, int BEAM, int CUBIC>
+// NLP: 0, or the compile-time value of n_leaves = n_phases (common grids get instantiations whose shared-memory
+// and workspace offsets are immediates instead of per-access integer arithmetic)
+template <int ATM, int CORR, int BEAM, int CUBIC, int NLP>
 __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5)
 k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __grid_constant__ CUtensorMap tm_els) {
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
@@ -863,7 +865,7 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
   const int n_img = ih[0];
   if (n_img == 0) return;
   const double* dh = a.ws_hdr + ring * kDHdr;
-  const int N_E = a.n_energies, N_L = a.n_leaves, N_P = a.n_phases;
+  const int N_E = a.n_energies, N_L = NLP ? NLP : a.n_leaves, N_P = NLP ? NLP : a.n_phases;
   const long cell0 = ring * a.n_azi;
   const int e0 = chunk * kNEC;
   const int ne = min(kNEC, N_E - e0);
@@ -1277,6 +1279,15 @@ static cudaError_t encode_slab_map(CUtensorMap* tm, const double* ws, const Azin
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+template <int ATM, int CORR, int BEAM, int CUBIC, int NLP>
+static cudaError_t launch_flux_n(const AzinvArgs& a, dim3 grid, size_t smem, cudaStream_t stream,
+                                 const CUtensorMap& tm_hot, const CUtensorMap& tm_els) {
+  cudaError_t err = cudaFuncSetAttribute(k_azinv_flux<ATM, CORR, BEAM, CUBIC, NLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  k_azinv_flux<ATM, CORR, BEAM, CUBIC, NLP><<<grid, kFluxThreads, smem, stream>>>(a, tm_hot, tm_els);
+  return cudaGetLastError();
+}
+
 template <int ATM, int CORR, int BEAM, int CUBIC>
 static cudaError_t launch_flux_b(const AzinvArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
   CUtensorMap tm_hot, tm_els;
@@ -1284,10 +1295,12 @@ static cudaError_t launch_flux_b(const AzinvArgs& a, dim3 grid, size_t smem, cud
   cudaError_t err;
   if (ATM == 2 && (err = encode_slab_map(&tm_hot, a.ws_slab, a, a.hot.nmu)) != cudaSuccess) return err;
   if (CORR == 2 && (err = encode_slab_map(&tm_els, a.ws_slab2, a, a.els.nmu)) != cudaSuccess) return err;
-  err = cudaFuncSetAttribute(k_azinv_flux<ATM, CORR, BEAM, CUBIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (err != cudaSuccess) return err;
-  k_azinv_flux<ATM, CORR, BEAM, CUBIC><<<grid, kFluxThreads, smem, stream>>>(a, tm_hot, tm_els);
-  return cudaGetLastError();
+  // the plain configurations get instantiations for the usual leaf / phase grids
+  if (!BEAM && !CUBIC && a.n_leaves == a.n_phases) {
+    if (a.n_leaves == 100) return launch_flux_n<ATM, CORR, 0, 0, 100>(a, grid, smem, stream, tm_hot, tm_els);
+    if (a.n_leaves == 64) return launch_flux_n<ATM, CORR, 0, 0, 64>(a, grid, smem, stream, tm_hot, tm_els);
+  }
+  return launch_flux_n<ATM, CORR, BEAM, CUBIC, 0>(a, grid, smem, stream, tm_hot, tm_els);
 }
 template <int ATM, int CORR>
 static cudaError_t launch_flux(const AzinvArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
