@@ -954,10 +954,10 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
     // redshift / mu*eta / geometry factor stay in the registers of the thread that owns the leaf ---------
     const double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
     for (int l = tid; l < N_L; l += kFluxThreads) s_PH[l] = W[l];
-    if ((ATM == 2 || CORR == 2) && I == 0)                        // the slab tile has landed
-      while (!cuda::ptx::mbarrier_try_wait_parity(&s_mbar, 0u)) {}
     __syncthreads();
     for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
+    if ((ATM == 2 || CORR == 2) && I == 0)                        // the slab tile has landed (first use: stage 1);
+      while (!cuda::ptx::mbarrier_try_wait_parity(&s_mbar, 0u, 2000u)) {}   // suspended waits, not a hot spin
     // ---- (1) leaf profile (pyx:445-478): thread = leaf, the mu stencil is shared by the chunk's energies -----
     for (int lb = 0; lb < N_L; lb += kFluxThreads) {
       const int l = lb + tid;
