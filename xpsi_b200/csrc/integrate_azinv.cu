@@ -994,6 +994,18 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
       }
     }
     __syncthreads();
+    // the accumulation stage's first loads (entry count, first moment entry of this thread's phase) are issued
+    // here, so their L2 latency is spent under stage 2 instead of at the head of stage 3
+    const long slot = ring * n_img_max + I;
+    int cnt = -1;
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+    int2 nm = make_int2(0, 0);
+    if (k < N_P && a.ws_mom) {
+      const double* mom = a.ws_mom + slot * (long)a.mom_cap * 4 * N_P + k;
+      cnt = a.ws_cnt[slot * N_P + k];
+      n0 = mom[0]; n1 = mom[N_P]; n2 = mom[2 * N_P]; n3 = mom[3 * N_P];
+      nm = a.ws_meta[slot * (long)a.mom_cap * N_P + k];
+    }
     // ---- (2) phase-spline coefficients + positivity flags (pyx:566-569) ----------------------
     // thread = (energy, block of consecutive leaf intervals): the five interval slopes of Akima's rule slide
     // along the block in registers, so an interval costs one new slope and one division (the weight
@@ -1139,17 +1151,12 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
           }
         }
       };
-      const long slot = ring * n_img_max + I;
-      const int cnt = a.ws_mom ? a.ws_cnt[slot * N_P + k] : -1;
       if (cnt >= 0) {
         // moments prepared once per (ring, image) by k_azinv_moments; loads are coalesced over k
         const double* mom = a.ws_mom + slot * (long)a.mom_cap * 4 * N_P + k;
         const int2* meta = a.ws_meta + slot * (long)a.mom_cap * N_P + k;
         // software pipeline: entry t+1 is in flight (L2) while entry t is consumed; the two pointers are bumped
         // (no per-entry 64-bit index arithmetic)
-        double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
-        int2 nm = make_int2(0, 0);
-        if (cnt > 0) { n0 = mom[0]; n1 = mom[N_P]; n2 = mom[2 * N_P]; n3 = mom[3 * N_P]; nm = meta[0]; }
         for (int t = 1; t <= cnt; ++t) {
           const double W0 = n0, W1 = n1, W2 = n2, W3 = n3;
           const int2 mt = nm;
