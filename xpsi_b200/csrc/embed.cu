@@ -103,7 +103,7 @@ __device__ __forceinline__ double gl16_piece(const G& g, double s0, double s1, b
 }
 
 // area of cell [tha,thb] x [pa,pb] inside the spot / R_eq^2 (mesh_tools.pyx:303-388,429-473, superRadius = 0)
-__device__ double spot_cell_area(double tha, double thb, double pa, double pb, double eps, double zeta,
+__device__ __noinline__ double spot_cell_area(double tha, double thb, double pa, double pb, double eps, double zeta,
                                  double TH, double rho) {
   const double cosT = cos(TH), sinT = sin(TH), cos_rho = cos(rho);
   const double lo = fmax(tha, TH - rho), hi = fmin(thb, TH + rho);
@@ -166,7 +166,7 @@ struct Region {            // the region being meshed and the region masking it 
 };
 // azimuthal width of the region minus its mask at colatitude theta, restricted to [pa, pb] when cell != 0
 // (cell_integrand mesh_tools.pyx:303-388, spot_integrand :690-771)
-__device__ double region_width(const Region& g, double theta, double pa, double pb, int cell) {
+__device__ __noinline__ double region_width(const Region& g, double theta, double pa, double pb, int cell) {
   if (are_equal(theta, 0.0)) return 0.0;
   double aLB, aUB, cLB, cUB;
   aUB = eval_phi(theta, g.colat, g.radius);
@@ -212,7 +212,7 @@ __constant__ double c_g7_w[4] = {0.129484966168869693270611432679082, 0.27970539
 // CQUAD at epsrel 1e-8 (mesh_tools.pyx:465-473,852-860); kinks and square-root end points are resolved by
 // bisection until the panel's |K15 - G7| is below tol_abs.
 template <class F>
-__device__ double adaptive_gk15(const F& f, double A, double B, double tol_abs) {
+__device__ __noinline__ double adaptive_gk15(const F& f, double A, double B, double tol_abs) {
   if (!(B > A)) return 0.0;
   double sa[44], sb[44];
   int sd[44];
@@ -247,7 +247,7 @@ __device__ double adaptive_gk15(const F& f, double A, double B, double tol_abs) 
 // (integrateSpot, mesh_tools.pyx:773-860, Lorentz = 0; it only feeds the cell allocation).  The range is split
 // at the parallels tangent to either boundary circle, where the width behaves like a square root and a
 // theta = s + t^2 substitution makes the integrand smooth; every lane then takes a slice of each piece.
-__device__ double warp_region_area(const Region& g, double lo, double hi, double eps, double zeta, int lane) {
+__device__ __noinline__ double warp_region_area(const Region& g, double lo, double hi, double eps, double zeta, int lane) {
   double bp[6];
   int nb = 0;
   bp[nb++] = lo; bp[nb++] = hi;
@@ -311,7 +311,7 @@ __device__ __forceinline__ void circle_meridian_crossings(double TH, double rho,
 // either boundary circle crosses the cell's meridians or touches a parallel, so every piece is either empty
 // or smooth up to square-root end points (no sliver can fall between quadrature nodes); the pieces are then
 // integrated adaptively (the two circles' mutual intersections are left to the bisection).
-__device__ double region_cell_area(const Region& g, double l, double u, double pa, double pb, double eps,
+__device__ __noinline__ double region_cell_area(const Region& g, double l, double u, double pa, double pb, double eps,
                                    double zeta, double tol_abs) {
   double bp[24];
   int nb = 0;
@@ -358,7 +358,7 @@ __device__ double region_cell_area(const Region& g, double l, double u, double p
 // serial chain is 15 times shorter than one thread per cell, which left 255 threads of a polar-cap CTA
 // waiting for the few that owned boundary cells).
 template <class F>
-__device__ double warp_adaptive_gk15(const F& f, double A, double B, double tol_abs, int lane) {
+__device__ __noinline__ double warp_adaptive_gk15(const F& f, double A, double B, double tol_abs, int lane) {
   if (!(B > A)) return 0.0;
   double sa[44], sb[44];
   int sd[44];
@@ -387,7 +387,7 @@ __device__ double warp_adaptive_gk15(const F& f, double A, double B, double tol_
 }
 
 // region_cell_area evaluated by a warp (all lanes pass the same arguments and receive the same result)
-__device__ double warp_region_cell_area(const Region& g, double l, double u, double pa, double pb, double eps,
+__device__ __noinline__ double warp_region_cell_area(const Region& g, double l, double u, double pa, double pb, double eps,
                                         double zeta, double tol_abs, int lane) {
   double bp[24];
   int nb = 0;
