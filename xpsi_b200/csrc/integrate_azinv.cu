@@ -862,7 +862,14 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
   const int tid = threadIdx.x;
   const long ring = (long)q * a.n_rings + i;
   const int* ih = a.ws_ihdr + ring * kIHdr;
+  // everything the set-up needs from the headers is requested at once (one L2 round trip instead of a chain:
+  // the loads behind the early exits would otherwise wait for the ones in front of them)
   const int n_img = ih[0];
+  const int n_cells = ih[10];
+  int2 cr_hot = make_int2(0, 0), cr_els = make_int2(0, 0);
+  if (ATM == 2) cr_hot = reinterpret_cast<const int2*>(a.ws_chunk)[ring * n_chunks + chunk];
+  if (CORR == 2) cr_els = reinterpret_cast<const int2*>(a.ws_chunk)[((long)a.Q * a.n_rings + ring) * n_chunks + chunk];
+  const int elo_hot = (ATM == 2) ? ih[4] : 0, elo_els = (CORR == 2) ? ih[8] : 0;
   if (n_img == 0) return;
   const double* dh = a.ws_hdr + ring * kDHdr;
   const int N_E = a.n_energies, N_L = NLP ? NLP : a.n_leaves, N_P = NLP ? NLP : a.n_phases;
@@ -910,14 +917,10 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
   }
 
   // ---- Num4D: fetch the tile of the ring's slab(s) this chunk reaches (TMA) ------------------------
-  const int n_cells = ih[10];
   if (n_cells == 0) return;                   // (before any copy is in flight)
-  int2 cr_hot = make_int2(0, 0), cr_els = make_int2(0, 0);
-  if (ATM == 2) cr_hot = reinterpret_cast<const int2*>(a.ws_chunk)[ring * n_chunks + chunk];
-  if (CORR == 2) cr_els = reinterpret_cast<const int2*>(a.ws_chunk)[((long)a.Q * a.n_rings + ring) * n_chunks + chunk];
   // rows needed, counting the one in front when the chunk starts on an odd row of the ring's slab (tile alignment)
-  if ((ATM == 2 && cr_hot.y + ((cr_hot.x - ih[4]) & 1) > a.slab_ne_max) ||
-      (CORR == 2 && cr_els.y + ((cr_els.x - ih[8]) & 1) > a.slab_ne_max)) {
+  if ((ATM == 2 && cr_hot.y + ((cr_hot.x - elo_hot) & 1) > a.slab_ne_max) ||
+      (CORR == 2 && cr_els.y + ((cr_els.x - elo_els) & 1) > a.slab_ne_max)) {
     if (tid == 0) atomicExch(a.status + q, kUnsupported);   // budget too small: refuse, never clamp
     return;
   }
@@ -931,11 +934,11 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
   }
   if (ATM == 2) {
     hot.log_kT = log_kT;
-    slab_ctx_load(hot, a.hot, &tm_hot, ring, ih[4], cr_hot, a.slab_ne_max, tid, &s_mbar);
+    slab_ctx_load(hot, a.hot, &tm_hot, ring, elo_hot, cr_hot, a.slab_ne_max, tid, &s_mbar);
   }
   if (CORR == 2) {
     els.log_kT = log_kT_c;
-    slab_ctx_load(els, a.els, &tm_els, ring, ih[8], cr_els, a.slab_ne_max, tid, &s_mbar);
+    slab_ctx_load(els, a.els, &tm_els, ring, elo_els, cr_els, a.slab_ne_max, tid, &s_mbar);
   }
   __syncthreads();
   if (ATM == 2) slab_ctx_finish(hot, a.hot, tid);
@@ -954,6 +957,10 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
     // redshift / mu*eta / geometry factor stay in the registers of the thread that owns the leaf ---------
     const double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
     for (int l = tid; l < N_L; l += kFluxThreads) s_PH[l] = W[l];
+    // this thread's first leaf (geometry factor, redshift, mu*eta): requested before the barrier
+    const bool pre_ok = tid < N_L;
+    const double pre_geom = pre_ok ? W[3 * N_L + tid] : 0.0;
+    const double pre_zst = pre_ok ? W[N_L + tid] : 1.0, pre_abb = pre_ok ? W[2 * N_L + tid] : 0.0;
     __syncthreads();
     for (int l = tid; l < N_L - 1; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
     if ((ATM == 2 || CORR == 2) && I == 0)                        // the slab tile has landed (first use: stage 1);
@@ -961,7 +968,7 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
     // ---- (1) leaf profile (pyx:445-478): thread = leaf, the mu stencil is shared by the chunk's energies -----
     for (int lb = 0; lb < N_L; lb += kFluxThreads) {
       const int l = lb + tid;
-      const double geom = (l < N_L) ? W[3 * N_L + l] : 0.0;
+      const double geom = (lb == 0) ? pre_geom : ((l < N_L) ? W[3 * N_L + l] : 0.0);
       {                                     // which leaves are lit: lets stage 2 skip blocks of dark intervals
         const unsigned lit = __ballot_sync(0xffffffffu, geom != 0.0);
         if ((tid & 31) == 0 && (l >> 5) < kLitWords) s_litmask[l >> 5] = lit;
@@ -972,8 +979,8 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
         for (int e = 0; e < kNEC; ++e) s_coef[((long)e * N_L + l) * 2] = 0.0;
         continue;
       }
-      const double zst = W[N_L + l];            // Z for a blackbody hot atmosphere, log10 Z for Num4D
-      const double abb = W[2 * N_L + l];        // mu * eta
+      const double zst = (lb == 0) ? pre_zst : W[N_L + l];          // Z for a blackbody hot atmosphere, log10 Z for Num4D
+      const double abb = (lb == 0) ? pre_abb : W[2 * N_L + l];      // mu * eta
       MuStencil ms_hot, ms_els;
       if (ATM == 2) ms_hot = slab_ctx_mu_stencil(hot, abb, BEAM && a.beam_opt == 3);
       if (CORR == 2) ms_els = slab_ctx_mu_stencil(els, abb);
