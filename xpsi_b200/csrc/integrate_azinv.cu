@@ -767,12 +767,13 @@ __device__ __forceinline__ void slab_ctx_load(SlabCtx& c, const AtmTable& T, con
   for (int m = tid; m < T.nmu; m += kFluxThreads) c.axMu[m] = T.mu[m];
   // tile rows past the end of the table get an unreachable axis value
   for (int r = tid; r < c.nrows; r += kFluxThreads) c.axE[r] = (c.elo_tab + r < T.nE) ? T.logE[c.elo_tab + r] : 1.0e300;
-}
-
-__device__ __forceinline__ void slab_ctx_finish(SlabCtx& c, const AtmTable& T, int tid) {     // after a barrier
   // Lagrange denominators per base row: copied from the table's precomputed list
   const int nv = min(c.nrows, c.nE - c.elo_tab);                     // rows inside the table
   for (int r = tid; r < 4 * (nv - 3); r += kFluxThreads) c.invden[r] = __ldg(T.E_invden + 4 * c.elo_tab + r);
+}
+
+__device__ __forceinline__ void slab_ctx_finish(SlabCtx& c, const AtmTable& T, int tid) {     // after a barrier
+  const int nv = min(c.nrows, c.nE - c.elo_tab);                     // rows inside the table
   c.mu_invden = T.mu_invden;
   // mean spacing of the axis segment: first guess of the energy stencil (then walked)
   c.inv_dE = (nv > 1) ? (double)(nv - 1) / (c.axE[nv - 1] - c.axE[0]) : 0.0;
