@@ -354,8 +354,8 @@ def main_ours(args):
         "roofline": {"bound": "fp64", "kernel": "k_azinv_flux<2,0,0> (+ k_azinv_geometry, k_azinv_slab, k_azinv_slab_member, k_azinv_moments: the integrate stage)",
                      "achieved": achieved, "peak": float(peak[0]),
                      "unit": "TFLOP/s", "frac": achieved / float(peak[0]),
-                     "traffic": 7.82e6 * B,
-                     "traffic_source": "ncu --set full at batch 32 (dram read+write 250.1 MB per launch, profiles/r01k_k_azinv_flux_ncu_full.txt), scaled to this batch",
+                     "traffic": 7.86e6 * B,
+                     "traffic_source": "ncu --set full at batch 32 (dram read+write 251.4 MB per launch, profiles/r01l_k_azinv_flux_ncu_full.txt), scaled to this batch",
                      "peak_source": "in-run DFMA microbenchmark (MEASURED_PEAKS.json has no fp64 entry)",
                      "algorithmic_gflop_per_eval": {k: v / 1e9 for k, v in fl.items()},
                      "whole_path_tflops": whole, "whole_path_frac": whole / float(peak[0]),
