@@ -634,7 +634,7 @@ struct xpsi_b200_pipeline {
   // constants
   Dev<double> energies, log10E, leaves, phases, phase_cycles, log10_edges, response, data_phases, counts,
       support, precomp;
-  Dev<int> col_of_q, k_range;
+  Dev<int> col_of_q, k_range; Dev<int2> ei_span;
   // per-batch inputs
   Dev<double> omega, inclination, d_sq, shifts, omega_q, incl_q, cellArea, phi, theta, radial, rsr, params,
       defl, calpha, lag, maxd, cgamma;
@@ -796,6 +796,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   ei.Q = Q; ei.n_energies = c.n_energies; ei.n_phases = c.n_phases; ei.n_in = c.n_in;
   ei.signal = p->flux.p; ei.raw_energies = p->energies.p; ei.div_b = p->d_sq.p; ei.q_per_b = M;
   ei.log10_energies = p->log10E.p; ei.log10_edges = p->log10_edges.p; ei.interp = c.phase_interpolant;
+  ei.span = p->ei_span.p;
   ei.col_of_q = p->col_of_q.p; ei.accumulate = (M > C) ? 1 : 0; ei.out = p->xin.p;
   if (p->att_base.p) { ei.attenuation = p->att_base.p; ei.att_power = p->att_power_valid ? p->att_power.p : nullptr; }
   if (ei.accumulate)
@@ -895,6 +896,11 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
   ok(p->energies.upload(c.energies, c.n_energies)); ok(p->log10E.upload(l10E.data(), c.n_energies));
   ok(p->leaves.upload(c.leaves, c.n_leaves)); ok(p->phases.upload(c.phases, c.n_phases));
   ok(p->phase_cycles.upload(cyc.data(), c.n_phases)); ok(p->log10_edges.upload(l10edges.data(), c.n_in + 1));
+  {
+    std::vector<int2> span(c.n_in);
+    xb::energy_span_table(l10E.data(), c.n_energies, l10edges.data(), c.n_in, span.data());
+    ok(p->ei_span.upload(span.data(), span.size()));
+  }
   ok(p->response.upload(c.response, (size_t)c.n_chan * c.n_in));
   {
     std::vector<int> kr = response_k_ranges(c.response, c.n_chan, c.n_in, 0, c.n_in);

@@ -145,8 +145,13 @@ struct EnergyIntegArgs {
   int accumulate;
   const double* attenuation;         // nullptr or [n_in] (Interstellar.__call__)
   const double* att_power;           // nullptr, or [Q/q_per_b]: the factor is attenuation[j] ** att_power[b]
+  const int2* span;                  // nullptr, or [n_in]: energy intervals holding the (clamped) ends of input
+                                     //   interval j -- the grids are theta-independent, so the pipeline looks them
+                                     //   up once on the host (energy_span_table) instead of per (phase, q) on the device
   double* out;
 };
+// span table of EnergyIntegArgs (host): same clamping and search contract as the kernel's own lookup
+void energy_span_table(const double* log10_energies, int n_energies, const double* log10_edges, int n_in, int2* out);
 cudaError_t launch_energy_integrator(EnergyIntegArgs a, cudaStream_t stream);
 
 // a11: Instrument.__call__  C[col][chan][p] = sum_in R[chan][in] X[(col,p)][in]

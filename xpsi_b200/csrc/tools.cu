@@ -61,8 +61,12 @@ __global__ void __launch_bounds__(kEIThreads) k_energy_integrator(EnergyIntegArg
       if (lo < xmin) lo = (xmin - lo <= 1.0e-9 * (1.0 + fabs(xmin))) ? xmin : nan("");
       if (lo == lo && hi > lo) {
         // the energy grid is (near-)uniform in log10 E: guess the interval, then walk (same result as bisection)
-        const int ia = interval_walk(s_x, N_E, lo, (int)((lo - xmin) * inv_dx));
-        const int ib = interval_walk(s_x, N_E, hi, (int)((hi - xmin) * inv_dx));
+        int ia, ib;
+        if (a.span) { const int2 sp = a.span[j]; ia = sp.x; ib = sp.y; }
+        else {
+          ia = interval_walk(s_x, N_E, lo, (int)((lo - xmin) * inv_dx));
+          ib = interval_walk(s_x, N_E, hi, (int)((hi - xmin) * inv_dx));
+        }
         for (int i = ia; i <= ib; ++i) {
           const double x0 = s_x[i];
           const double r1 = (i == ia) ? lo - x0 : 0.0;
@@ -75,6 +79,26 @@ __global__ void __launch_bounds__(kEIThreads) k_energy_integrator(EnergyIntegArg
     }
     if (a.attenuation) val *= a.att_power ? pow(a.attenuation[j], a.att_power[q / a.q_per_b]) : a.attenuation[j];
     if (a.accumulate) atomicAdd(out + j, val); else out[j] = val;
+  }
+}
+
+// largest i in [0, n-2] with x[i] <= q (the contract of interval_search / interval_walk)
+static int host_interval(const double* x, int n, double q) {
+  int lo = 0, hi = n - 1;
+  while (hi > lo + 1) { const int mid = (hi + lo) >> 1; if (x[mid] > q) hi = mid; else lo = mid; }
+  return lo;
+}
+
+void energy_span_table(const double* x, int n_energies, const double* edges, int n_in, int2* out) {
+  const double xmin = x[0], xmax = x[n_energies - 1];
+  for (int j = 0; j < n_in; ++j) {
+    double lo = edges[j], hi = edges[j + 1];
+    out[j] = make_int2(0, 0);
+    if (!(lo > xmax) && !(j > 0 && edges[j] > xmax)) {          // the kernel's conditions, in the kernel's order
+      if (hi > xmax) hi = xmax;
+      if (lo < xmin) { if (xmin - lo <= 1.0e-9 * (1.0 + fabs(xmin))) lo = xmin; else continue; }
+      if (hi > lo) out[j] = make_int2(host_interval(x, n_energies, lo), host_interval(x, n_energies, hi));
+    }
   }
 }
 
