@@ -201,11 +201,25 @@ def last_error():
     return lib.xpsi_b200_last_error().decode("utf-8", "replace")
 
 
-def check(rc):
-    """Raise on API/CUDA failures (negative codes); pass the rest through."""
+class XpsiB200NumericalError(XpsiB200Error):
+    """The reference's numerical ``ERROR`` return reached a wrapper that has no ``(1, None)`` convention."""
+
+
+def check(rc, allow=()):
+    """Raise on every non-zero return code that the caller does not list in ``allow``.
+
+    Negative codes are API / CUDA failures (``XpsiB200Error``); ``EUNSUPPORTED`` is a configuration outside
+    the kernels' coverage (``NotImplementedError``, never a silent wrong answer); the remaining positive
+    codes (``ENUMERICAL``, ``ESLIM``, ``EQUADRATURE``) are numerical outcomes that a wrapper must either map
+    onto the reference's convention itself (and then allow here) or surface as an exception.
+    """
+    if rc == OK or rc in allow:
+        return rc
     if rc < 0:
         raise XpsiB200Error("libxpsi_b200 error %d: %s" % (rc, last_error()))
-    return rc
+    if rc == EUNSUPPORTED:
+        raise NotImplementedError("xpsi_b200: " + last_error())
+    raise XpsiB200NumericalError("libxpsi_b200 numerical status %d: %s" % (rc, last_error()))
 
 
 def counters():

@@ -34,14 +34,29 @@ class Likelihood:
     def clear_cache(self):
         self._cached_p, self._cached_value = None, None
 
-    def batch(self, P):
-        """log-likelihoods of the rows of ``P`` (no prior added); rows that fail carry ``nan`` and a status."""
+    # statuses that the reference turns into a random value near llzero: numerical error in a compiled stage
+    # (PulseError / RayError handling, xpsi/Likelihood.py:346-358), the slim early exit and a non-positive
+    # marginal integral (default_background_marginalisation.pyx:677-684,702-706)
+    NUMERICAL_STATUSES = (1, 11, 12)
+
+    def batch(self, P, strict=True):
+        """log-likelihoods of the rows of ``P`` (no prior added); rows whose evaluation ended numerically
+        (statuses 1, 11, 12) carry ``nan`` and the status.  A row with status 3 is a configuration outside the
+        kernels' coverage -- the reference would have evaluated it -- and raises ``NotImplementedError``
+        (``strict=False`` returns it as ``nan`` / 3 instead, for callers that inspect ``status`` themselves)."""
         P = np.atleast_2d(np.asarray(P, dtype=np.float64))
         lnL = np.empty(P.shape[0])
         status = np.empty(P.shape[0], dtype=np.int32)
         for i in range(0, P.shape[0], self._max_batch):
             blk = P[i:i + self._max_batch]
             lnL[i:i + blk.shape[0]], status[i:i + blk.shape[0]] = self._pipe.eval_spots(self._fill(self._pipe, blk))
+        bad = ~np.isin(status, (0,) + self.NUMERICAL_STATUSES)
+        if strict and bad.any():
+            k = int(np.flatnonzero(bad)[0])
+            raise NotImplementedError("xpsi_b200: parameter vector %d of the batch needs a configuration the "
+                                      "kernels do not cover (status %d; e.g. more mesh rings than max_rings, a "
+                                      "zero-radius member, the Num4D slab budget): the result would not be the "
+                                      "reference's" % (k, int(status[k])))
         lnL[status != 0] = np.nan
         return lnL, status
 
@@ -63,7 +78,7 @@ class Likelihood:
             loglikelihood = self._cached_value                      # memoised, Likelihood.py:489-490
         else:
             lnL, status = self.batch(p[None, :])
-            if status[0] != 0:                                      # numerical failure or slim early exit
+            if status[0] != 0:                  # numerical failure or slim early exit (status 3 raised in batch)
                 return self.random_near_llzero
             loglikelihood = float(lnL[0])
             self._cached_p, self._cached_value = p.copy(), loglikelihood

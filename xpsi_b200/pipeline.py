@@ -24,6 +24,7 @@ class HostBatch:
     def __init__(self, B, M, C_, max_rings, max_azi, n_rays, n_params, pinned=False):
         self.B, self.M = B, M
         Q = B * M
+        self._pins = []
         alloc = self._pinned if pinned else np.zeros
         self.omega = alloc((B,), np.float64)
         self.inclination = alloc((B,), np.float64)
@@ -43,13 +44,10 @@ class HostBatch:
         self.maxDeflection = alloc((Q, max_rings), np.float64)
         self.cos_gamma = alloc((Q, max_rings), np.float64)
 
-    _pins = []
-
-    @staticmethod
-    def _pinned(shape, dtype):
+    def _pinned(self, shape, dtype):
         import torch   # device-memory plumbing only: page-locked host staging
         t = torch.zeros(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32).pin_memory()
-        HostBatch._pins.append(t)      # the numpy view below borrows the tensor's storage
+        self._pins.append(t)           # the numpy view below borrows the tensor's storage; freed with the batch
         return t.numpy()
 
     def set_member(self, b, m, cellArea, theta, phi, radial, r_s_over_r, srcCellParams,
@@ -332,7 +330,12 @@ class BatchedLikelihood:
         return lnL, status
 
     def new_spot_batch(self, B, mode_frequency, **kw):
-        return SpotBatch(B, self.n_members, self.n_components, mode_frequency, **kw)
+        sb = SpotBatch(B, self.n_members, self.n_components, mode_frequency, **kw)
+        if sb.max_sqrt > min(self.shape["max_rings"], self.shape["max_azi"]):
+            raise ValueError("max_sqrt_num_cells = %d exceeds the pipeline's padded mesh (%d x %d): the embed "
+                             "would refuse every parameter vector that allocates more rings"
+                             % (sb.max_sqrt, self.shape["max_rings"], self.shape["max_azi"]))
+        return sb
 
     def eval_spots(self, spots):
         """theta-level call: embed (mesh + rays) on the GPU, then the four likelihood stages."""

@@ -173,6 +173,35 @@ def m2_theta_batch(n, seed=20261017):
     return out
 
 
+def m2_bench_thetas(first, count):
+    """Rows ``[first, first+count)`` of the deterministic ST-U parameter-vector list that the bench, the
+    sweep and the parity fixtures share: row 0 is ``M2_TRUE`` and row 1 is ``m2_theta_batch(4)[1]`` (the two
+    parameter vectors of the golden fixture ``m2_stu_nsx.npz``), followed by ``m2_theta_batch`` draws."""
+    head = np.vstack([M2_TRUE, m2_theta_batch(4)[1]])
+    full = np.vstack([head, m2_theta_batch(first + count)])
+    return np.ascontiguousarray(full[first:first + count])
+
+
+def m2_near_truth_thetas(n, seed=7, scale=2.0e-3):
+    """``n`` parameter vectors scattered around ``M2_TRUE`` (Gaussian, ``scale`` x the prior width per
+    parameter): the region a converged sampler spends its time in, |lnL| ~ 4e4-1e5 for the fixture data."""
+    rng = np.random.default_rng(seed)
+    width = M2_BOUNDS[:, 1] - M2_BOUNDS[:, 0]
+    return M2_TRUE[None, :] + scale * width[None, :] * rng.standard_normal((n, len(M2_NAMES)))
+
+
+def m2_compact_thetas():
+    """12 parameter vectors with stars close to the photon-sphere limit ``R = 3 r_g`` (mass 2.2, radius set
+    from ``R / r_g``): six whose rays bend by more than 2 pi (three image orders are summed under
+    ``image_order_limit = 3``) and six with two image orders.  The remaining parameters are rows 2..13 of the
+    bench list.  Outside the prior box of ``M2_BOUNDS`` but inside the reference's strict parameter bounds."""
+    x = np.array([3.005, 3.01, 3.02, 3.03, 3.035, 3.04, 3.06, 3.1, 3.15, 3.2, 3.3, 3.45])
+    th = m2_bench_thetas(2, x.size)
+    th[:, 0] = 2.2
+    th[:, 1] = x * 2.2 * GM_SUN / KM
+    return th
+
+
 def m2_spot_batch(pipe, thetas):
     """Map ST-U parameter vectors (order ``M2_NAMES``) onto the pipeline's parameter-level inputs:
     two circular spots, the secondary antiphased with ``T_s = T_p - M2_SECONDARY_DT``
