@@ -309,6 +309,18 @@ int xpsi_b200_pipeline_eval_spots_resident(xpsi_b200_pipeline* p, int B);
 /* embed + evaluate + download: theta-level end-to-end call */
 int xpsi_b200_pipeline_eval_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200_spot_batch* host,
                                   double* lnL, int* status);
+/* Sweep of N parameter vectors (the reference's scatter / evaluate / gather loop over importance samples or
+ * live points, xpsi/Sample.py:287-336, for one rank's share): the parameter-level inputs are uploaded ONCE
+ * (att_power[N] / else_temperature[N] as in the batch extras, NULL when unused), sweep_run evaluates rows
+ * [first, first+count) in blocks of <= max_batch without synchronising (embed + four stages per block, results
+ * kept on the device), sweep_download copies lnL / status of a row range back.  sweep_results hands out the
+ * device arrays lnL[N] / status[N] so that a collective can read them in place.                            */
+int xpsi_b200_pipeline_sweep_upload(xpsi_b200_pipeline* p, long long N, const xpsi_b200_spot_batch* host,
+                                    const double* att_power, const double* else_temperature);
+int xpsi_b200_pipeline_sweep_run(xpsi_b200_pipeline* p, long long first, long long count);
+int xpsi_b200_pipeline_sweep_download(xpsi_b200_pipeline* p, long long first, long long count, double* lnL,
+                                      int* status);
+int xpsi_b200_pipeline_sweep_results(xpsi_b200_pipeline* p, double** lnL, int** status);
 /* fetch the embedded integrator inputs of the last embed (any pointer may be NULL) */
 int xpsi_b200_pipeline_fetch_embed(xpsi_b200_pipeline* p, int B, int* n_rings, double* cellArea, double* phi,
                                    double* theta, double* radial, double* srcParams, double* cos_gamma,
@@ -326,11 +338,13 @@ int xpsi_b200_pipeline_download(xpsi_b200_pipeline* p, int B, double* lnL, int* 
 /* optional: fetch intermediate device results of the last eval (NULL to skip) */
 int xpsi_b200_pipeline_fetch(xpsi_b200_pipeline* p, int B, double* flux /*[B*M][E][P] raw*/,
                              double* folded /*[B][C][chan][P]*/, double* expected /*[B][chan][bins]*/);
-/* algorithmic-work counters of the integrator: enable!=0 makes later evals
- * count; out (if non-NULL and counting was on) receives H, V, RI, K of the last eval */
+/* algorithmic-work counters of the integrator: enable!=0 resets the counters and makes
+ * later evals count (accumulating over evals); out (if non-NULL and counting was on) receives H, V, RI, K
+ * summed over the evals since then */
 int xpsi_b200_pipeline_work_counters(xpsi_b200_pipeline* p, int enable, unsigned long long out[4]);
-/* per-stage device time of the last evaluation in ms: integrate, energy, fold, marginal, embed */
-int xpsi_b200_pipeline_stage_ms(xpsi_b200_pipeline* p, float ms[5]);
+/* per-stage device time of the last evaluation in ms: integrate, energy, fold, marginal, embed, and the
+ * flux kernel alone (part of integrate) */
+int xpsi_b200_pipeline_stage_ms(xpsi_b200_pipeline* p, float ms[6]);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 
 PULSE_RTOL = 1.0e-8
 LNL_ATOL = 1.0e-6
+THETA_GOLDEN_LNL_ATOL = 5.0e-8     # lnL from theta (GPU embed) on the golden parameter vectors: 10x the measured 4.7e-9
 
 
 def _integrate_args(d, prefix, atmosphere):
@@ -421,8 +422,9 @@ def test_theta_level_likelihood_with_gpu_embed(m2):
     for b, t in enumerate((0, 1, 0)):
         ref = float(m2["t%d_lnL_total" % t])
         print("theta-level lnL", lnL[b], "ref", ref, "diff", lnL[b] - ref)
-        # mesh areas are only defined to the reference's own 1e-8 quadrature tolerance
-        assert abs(lnL[b] - ref) < 1e-4
+        # measured 4.7e-9 (|lnL| = 3.8e4): the golden vectors' reference meshes are converged (tests/test_theta_parity.py
+        # covers the prior draws whose reference mesh is not)
+        assert abs(lnL[b] - ref) < THETA_GOLDEN_LNL_ATOL
 
 
 def test_poisson_likelihood_given_background(c1):
@@ -594,7 +596,7 @@ def test_m4_batched_pipeline_with_elsewhere_and_interstellar(m2):
     lnL2, status2 = pipe.eval_spots(spots)
     print("M4 pipeline (parameter level) lnL", lnL2, "diff", lnL2 - ref, "status", status2)
     assert (status2 == 0).all()
-    assert np.max(np.abs(lnL2 - ref)) < 1e-5
+    assert np.max(np.abs(lnL2 - ref)) < THETA_GOLDEN_LNL_ATOL               # measured 2.6e-10
     spec2 = pipe.fetch_elsewhere(B)
     err = rel_err(spec2[0], d["else_flux"])
     print("GPU-embedded elsewhere spectrum rel err", err)
@@ -671,9 +673,9 @@ def test_gpu_embed_of_omission_ceding_and_polar_regions(m2):
     e = pipe.fetch_embed(B)
     for m in range(3):
         _check_embed(e, 3 + m, lambda k: d["int%d_%s" % (m, k)], "M3 member %d" % m)
-    print("M3 parameter-level lnL", lnL, "ref", float(d["lnL_total"]), "status", status)
+    print("M3 parameter-level lnL", lnL, "ref", float(d["lnL_total"]), "diff", lnL - float(d["lnL_total"]), "status", status)
     assert (status == 0).all()
-    assert np.max(np.abs(lnL - float(d["lnL_total"]))) < 1e-4
+    assert np.max(np.abs(lnL - float(d["lnL_total"]))) < LNL_ATOL
     # ---- polar caps ---------------------------------------------------------------------------------------
     d = np.load(os.path.join(GOLDEN, "m5_polar.npz"))
     pipe = BatchedLikelihood(member_component=[0, 1], max_rings=64, max_azi=64, n_rays=200,
@@ -686,9 +688,9 @@ def test_gpu_embed_of_omission_ceding_and_polar_regions(m2):
     e = pipe.fetch_embed(2)
     for m in range(2):
         _check_embed(e, m, lambda k: d["int%d_%s" % (m, k)], "polar member %d" % m)
-    print("polar-cap parameter-level lnL", lnL, "ref", float(d["lnL_total"]), "status", status)
+    print("polar-cap parameter-level lnL", lnL, "ref", float(d["lnL_total"]), "diff", lnL - float(d["lnL_total"]), "status", status)
     assert (status == 0).all()
-    assert np.max(np.abs(lnL - float(d["lnL_total"]))) < 1e-4
+    assert np.max(np.abs(lnL - float(d["lnL_total"]))) < LNL_ATOL
 
 
 def test_likelihood_callable_mirrors_reference_conventions(m2):
@@ -701,16 +703,16 @@ def test_likelihood_callable_mirrors_reference_conventions(m2):
     like = Likelihood(pipe, fill, llzero=-1.0e90)
     ref = float(m2["t0_lnL_total"])
     v = like(m2["t0_theta"], force=True)
-    assert isinstance(v, float) and abs(v - ref) < 1e-4
+    assert isinstance(v, float) and abs(v - ref) < THETA_GOLDEN_LNL_ATOL
     assert like(m2["t0_theta"]) == v                                  # memoised
     assert like() == v                                                # externally updated / cached vector
     with_prior = Likelihood(pipe, fill, prior=lambda p: -3.5)
-    assert abs(with_prior(m2["t1_theta"]) - (float(m2["t1_lnL_total"]) - 3.5)) < 1e-4
+    assert abs(with_prior(m2["t1_theta"]) - (float(m2["t1_lnL_total"]) - 3.5)) < THETA_GOLDEN_LNL_ATOL
     rejected = Likelihood(pipe, fill, prior=lambda p: -np.inf)
     r = rejected(m2["t0_theta"])
     assert -1.0e90 <= r <= -1.0e89                                    # Likelihood.py:267-271
     lnL, status = like.batch(np.array([m2["t0_theta"], m2["t1_theta"], m2["t0_theta"]]))
-    assert (status == 0).all() and abs(lnL[1] - float(m2["t1_lnL_total"])) < 1e-4 and abs(lnL[0] - lnL[2]) < 1e-7
+    assert (status == 0).all() and abs(lnL[1] - float(m2["t1_lnL_total"])) < THETA_GOLDEN_LNL_ATOL and abs(lnL[0] - lnL[2]) < 1e-7
     with pytest.raises(TypeError):
         Likelihood(pipe, fill)()
 
@@ -769,7 +771,7 @@ def test_pipeline_properties_at_bench_batch_size(m2):
     thetas = np.vstack([m2["t0_theta"], m2["t1_theta"], syn.m2_theta_batch(B - 2)])
     lnL, status = pipe.eval_spots(syn.m2_spot_batch(pipe, thetas))
     assert np.isin(status, (0, 11)).all()
-    assert abs(lnL[0] - float(m2["t0_lnL_total"])) < 1e-4 and abs(lnL[1] - float(m2["t1_lnL_total"])) < 1e-4
+    assert abs(lnL[0] - float(m2["t0_lnL_total"])) < THETA_GOLDEN_LNL_ATOL and abs(lnL[1] - float(m2["t1_lnL_total"])) < THETA_GOLDEN_LNL_ATOL
     perm = np.random.default_rng(0).permutation(B)
     lnL_p, status_p = pipe.eval_spots(syn.m2_spot_batch(pipe, thetas[perm]))
     ok = (status == 0)

@@ -180,6 +180,10 @@ _proto("xpsi_b200_pipeline_eval_spots_resident", C.c_int, [C.c_void_p, C.c_int])
 _proto("xpsi_b200_pipeline_eval_spots", C.c_int, [C.c_void_p, C.c_int, C.POINTER(SpotBatch), c_double_p, c_int_p])
 _proto("xpsi_b200_pipeline_fetch_embed", C.c_int, [C.c_void_p, C.c_int, c_int_p] + [c_double_p] * 10)
 _proto("xpsi_b200_pipeline_stage_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)])
+_proto("xpsi_b200_pipeline_sweep_upload", C.c_int, [C.c_void_p, C.c_longlong, C.POINTER(SpotBatch), c_double_p, c_double_p])
+_proto("xpsi_b200_pipeline_sweep_run", C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong])
+_proto("xpsi_b200_pipeline_sweep_download", C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, c_double_p, c_int_p])
+_proto("xpsi_b200_pipeline_sweep_results", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)])
 
 EXPORTED = [
     "xpsi_b200_last_error", "xpsi_b200_device_count", "xpsi_b200_set_device", "xpsi_b200_counters",
@@ -194,6 +198,8 @@ EXPORTED = [
     "xpsi_b200_energy_interpolator", "xpsi_b200_integrate_time_invariance", "xpsi_b200_interstellar_attenuate",
     "xpsi_b200_pipeline_embed_spots", "xpsi_b200_pipeline_eval_spots", "xpsi_b200_pipeline_fetch_embed",
     "xpsi_b200_pipeline_eval_spots_resident", "xpsi_b200_poisson_likelihood_given_background",
+    "xpsi_b200_pipeline_sweep_upload", "xpsi_b200_pipeline_sweep_run", "xpsi_b200_pipeline_sweep_download",
+    "xpsi_b200_pipeline_sweep_results",
 ]
 
 

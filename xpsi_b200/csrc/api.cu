@@ -655,6 +655,7 @@ struct xpsi_b200_pipeline {
   cudaEvent_t ev_embed[2] = {nullptr, nullptr};
   float embed_ms = 0.f; int embed_timed = 0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_flux[2] = {nullptr, nullptr};
   float stage_ms[4] = {0, 0, 0, 0};
   // optional components (xpsi_b200_pipeline_set_extras)
   xpsi_b200_pipeline_extras ex = {};
@@ -664,6 +665,16 @@ struct xpsi_b200_pipeline {
   Dev<double> x_temp, x_area, x_radial, x_rsr, x_theta, x_phi, x_params, x_defl, x_calpha, x_maxd, x_cgamma,
       x_maxAlpha, x_grav, x_flux;
   Dev<int> x_nrings, x_status;
+  // sweep store: N parameter vectors uploaded once, evaluated block by block (xpsi_b200_pipeline_sweep_*)
+  struct SpotStore {
+    size_t N = 0;
+    Dev<double> omega, incl, d_sq, shifts, Req, rs, eps, zeta, colat, rad, temp, phish, hrad, hcolat, hazi, extra,
+        att_power, else_temp, lnL;
+    Dev<int> status;
+    int has_hole = 0, has_partner = 0, has_extra = 0, has_att = 0, has_else = 0;
+    double mode_frequency = 0.0;
+    int num_cells = 0, min_sqrt = 0, max_sqrt = 0;
+  } store;
 };
 
 namespace {
@@ -779,8 +790,8 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   a.ws_leaf = p->ws_leaf.p; a.ws_hdr = p->ws_hdr.p; a.ws_ihdr = p->ws_ihdr.p; a.ws_slab = p->ws_slab.p;
   a.ws_mom = p->ws_mom.p; a.ws_meta = p->ws_meta.p; a.ws_cnt = p->ws_cnt.p; a.mom_cap = p->mom_cap;
   a.ws_cells = p->ws_cells.p;
-  a.work = p->count_work ? p->work.p : nullptr;
-  if (a.work) CK(cudaMemsetAsync(p->work.p, 0, 4 * sizeof(unsigned long long), g_stream));
+  a.work = p->count_work ? p->work.p : nullptr;       // accumulates over evaluations; reset by work_counters()
+  a.ev_flux[0] = p->ev_flux[0]; a.ev_flux[1] = p->ev_flux[1];
   cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_integrate_azinv");
   if (p->ex.elsewhere) {
@@ -947,6 +958,8 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
   }
   for (int i = 0; i < 5; ++i) ok(cudaEventCreate(&p->ev[i]));
   for (int i = 0; i < 2; ++i) ok(cudaEventCreate(&p->ev_embed[i]));
+  for (int i = 0; i < 2; ++i) ok(cudaEventCreate(&p->ev_flux[i]));
+  ok(cudaMemsetAsync(p->work.p, 0, 4 * sizeof(unsigned long long), g_stream));
   ok(cudaStreamSynchronize(g_stream));
   if (e != cudaSuccess) { cuda_fail(e, "pipeline_create"); delete p; return nullptr; }
   g_launches += 1;
@@ -957,6 +970,7 @@ void xpsi_b200_pipeline_destroy(xpsi_b200_pipeline* p) {
   if (!p) return;
   for (int i = 0; i < 5; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   for (int i = 0; i < 2; ++i) if (p->ev_embed[i]) cudaEventDestroy(p->ev_embed[i]);
+  for (int i = 0; i < 2; ++i) if (p->ev_flux[i]) cudaEventDestroy(p->ev_flux[i]);
   delete p;
 }
 
@@ -1066,6 +1080,37 @@ int xpsi_b200_pipeline_eval(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch*
   return xpsi_b200_pipeline_download(p, B, lnL, status);
 }
 
+// device-side embed arguments over the pipeline's own per-batch arrays
+static int set_embed_args(xpsi_b200_pipeline* p, int B, double mode_frequency, int num_cells, int min_sqrt,
+                          int max_sqrt, bool hole, bool partner, bool extra) {
+  const xpsi_b200_pipeline_config& c = p->cfg;
+  const size_t M = c.n_members;
+  CK(p->e_maxAlpha.alloc((size_t)p->max_batch * M * c.max_rings));
+  xb::EmbedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.M = (int)M; a.max_rings = c.max_rings; a.max_azi = c.max_azi; a.n_rays = c.n_rays; a.n_params = c.n_params;
+  a.num_cells = num_cells; a.min_sqrt = min_sqrt; a.max_sqrt = max_sqrt;
+  a.mode_frequency = mode_frequency;
+  a.R_eq = p->e_Req.p; a.r_s = p->e_rs.p; a.epsilon = p->e_eps.p; a.zeta = p->e_zeta.p;
+  a.colatitude = p->e_colat.p; a.ang_radius = p->e_rad.p; a.temperature = p->e_temp.p; a.phi_shift = p->e_phish.p;
+  if (hole) { a.hole_radius = p->e_hrad.p; a.hole_colatitude = p->e_hcolat.p; a.hole_azimuth = p->e_hazi.p; }
+  if (partner) { a.partner = p->e_partner.p; a.is_cede = p->e_iscede.p; }
+  if (extra) a.extra_params = p->e_extra.p;
+  a.n_rings = p->n_rings.p; a.n_azi = p->n_azi.p; a.cellArea = p->cellArea.p; a.phi = p->phi.p; a.theta = p->theta.p;
+  a.radial = p->radial.p; a.r_s_over_r = p->rsr.p; a.srcParams = p->params.p; a.cos_gamma = p->cgamma.p;
+  a.maxAlpha = p->e_maxAlpha.p; a.deflection = p->defl.p; a.cos_alpha = p->calpha.p; a.lag = p->lag.p;
+  a.maxDeflection = p->maxd.p; a.status = p->status.p;
+  p->embed_args = a; p->embed_ready = 1;
+  return 0;
+}
+
+static int check_partner(const xpsi_b200_spot_batch* h, size_t M) {
+  if (!h->is_cede) return fail(XPSI_B200_EINVAL, "partner needs is_cede");
+  for (size_t m = 0; m < M; ++m)
+    if (h->partner[m] >= (int)M || h->partner[m] == (int)m) return fail(XPSI_B200_EINVAL, "bad partner index");
+  return 0;
+}
+
 int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200_spot_batch* h) {
   if (!p || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
   const xpsi_b200_pipeline_config& c = p->cfg;
@@ -1083,29 +1128,114 @@ int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200
   }
   if (h->extra_params && c.n_params > 2) CK(p->e_extra.upload(h->extra_params, Q * (c.n_params - 2)));
   if (h->partner) {
-    if (!h->is_cede) return fail(XPSI_B200_EINVAL, "partner needs is_cede");
-    for (size_t m = 0; m < M; ++m)
-      if (h->partner[m] >= (int)M || h->partner[m] == (int)m) return fail(XPSI_B200_EINVAL, "bad partner index");
+    int rc = check_partner(h, M);
+    if (rc) return rc;
     CK(p->e_partner.upload(h->partner, M)); CK(p->e_iscede.upload(h->is_cede, M));
   }
-  CK(p->e_maxAlpha.alloc((size_t)p->max_batch * M * c.max_rings));
   CK(cudaMemsetAsync(p->status.p, 0, B * sizeof(int), g_stream));
-  xb::EmbedArgs a;
-  memset(&a, 0, sizeof(a));
-  a.B = B; a.M = (int)M; a.max_rings = c.max_rings; a.max_azi = c.max_azi; a.n_rays = c.n_rays; a.n_params = c.n_params;
-  a.num_cells = h->num_cells; a.min_sqrt = h->min_sqrt_num_cells; a.max_sqrt = h->max_sqrt_num_cells;
-  a.mode_frequency = h->mode_frequency;
-  a.R_eq = p->e_Req.p; a.r_s = p->e_rs.p; a.epsilon = p->e_eps.p; a.zeta = p->e_zeta.p;
-  a.colatitude = p->e_colat.p; a.ang_radius = p->e_rad.p; a.temperature = p->e_temp.p; a.phi_shift = p->e_phish.p;
-  if (h->hole_radius) { a.hole_radius = p->e_hrad.p; a.hole_colatitude = p->e_hcolat.p; a.hole_azimuth = p->e_hazi.p; }
-  if (h->partner) { a.partner = p->e_partner.p; a.is_cede = p->e_iscede.p; }
-  if (h->extra_params && c.n_params > 2) a.extra_params = p->e_extra.p;
-  a.n_rings = p->n_rings.p; a.n_azi = p->n_azi.p; a.cellArea = p->cellArea.p; a.phi = p->phi.p; a.theta = p->theta.p;
-  a.radial = p->radial.p; a.r_s_over_r = p->rsr.p; a.srcParams = p->params.p; a.cos_gamma = p->cgamma.p;
-  a.maxAlpha = p->e_maxAlpha.p; a.deflection = p->defl.p; a.cos_alpha = p->calpha.p; a.lag = p->lag.p;
-  a.maxDeflection = p->maxd.p; a.status = p->status.p;
-  p->embed_args = a; p->embed_ready = 1;
+  int rc = set_embed_args(p, B, h->mode_frequency, h->num_cells, h->min_sqrt_num_cells, h->max_sqrt_num_cells,
+                          h->hole_radius != nullptr, h->partner != nullptr, h->extra_params && c.n_params > 2);
+  if (rc) return rc;
   return pipeline_embed_launch(p);
+}
+
+// ---- sweep: N parameter vectors resident on the device, evaluated in blocks of <= max_batch ------------------
+int xpsi_b200_pipeline_sweep_upload(xpsi_b200_pipeline* p, long long N, const xpsi_b200_spot_batch* h,
+                                    const double* att_power, const double* else_temperature) {
+  if (!p || !h || N < 1) return fail(XPSI_B200_EINVAL, "bad sweep size");
+  const xpsi_b200_pipeline_config& c = p->cfg;
+  if (c.n_params < 2) return fail(XPSI_B200_EUNSUPPORTED, "spot embed needs n_params >= 2 (log T, log g, ...)");
+  if (p->ex.elsewhere && !else_temperature) return fail(XPSI_B200_EINVAL, "elsewhere is enabled: else_temperature[N] is required");
+  auto& s = p->store;
+  const size_t n = (size_t)N, M = c.n_members, Q = n * M;
+  CK(s.omega.upload(h->omega, n)); CK(s.incl.upload(h->inclination, n)); CK(s.d_sq.upload(h->d_sq, n));
+  CK(s.shifts.upload(h->phase_shifts, n * c.n_components));
+  CK(s.Req.upload(h->R_eq, n)); CK(s.rs.upload(h->r_s, n)); CK(s.eps.upload(h->epsilon, n)); CK(s.zeta.upload(h->zeta, n));
+  CK(s.colat.upload(h->colatitude, Q)); CK(s.rad.upload(h->ang_radius, Q)); CK(s.temp.upload(h->temperature, Q));
+  CK(s.phish.upload(h->phi_shift, Q));
+  s.has_hole = h->hole_radius != nullptr;
+  if (s.has_hole) {
+    if (!h->hole_colatitude || !h->hole_azimuth) return fail(XPSI_B200_EINVAL, "incomplete hole arrays");
+    CK(s.hrad.upload(h->hole_radius, Q)); CK(s.hcolat.upload(h->hole_colatitude, Q)); CK(s.hazi.upload(h->hole_azimuth, Q));
+  }
+  s.has_extra = h->extra_params && c.n_params > 2;
+  if (s.has_extra) CK(s.extra.upload(h->extra_params, Q * (c.n_params - 2)));
+  s.has_partner = h->partner != nullptr;
+  if (s.has_partner) {
+    int rc = check_partner(h, M);
+    if (rc) return rc;
+    CK(p->e_partner.upload(h->partner, M)); CK(p->e_iscede.upload(h->is_cede, M));
+  }
+  s.has_att = att_power != nullptr;
+  if (s.has_att) CK(s.att_power.upload(att_power, n));
+  s.has_else = else_temperature != nullptr;
+  if (s.has_else) CK(s.else_temp.upload(else_temperature, n));
+  CK(s.lnL.alloc(n)); CK(s.status.alloc(n));
+  s.mode_frequency = h->mode_frequency; s.num_cells = h->num_cells;
+  s.min_sqrt = h->min_sqrt_num_cells; s.max_sqrt = h->max_sqrt_num_cells;
+  s.N = n;
+  CK(cudaStreamSynchronize(g_stream));          // the host arrays may go away after the call
+  return 0;
+}
+
+int xpsi_b200_pipeline_sweep_run(xpsi_b200_pipeline* p, long long first, long long count) {
+  if (!p || first < 0 || count < 1 || (size_t)(first + count) > p->store.N)
+    return fail(XPSI_B200_EINVAL, "sweep range outside the uploaded parameter vectors");
+  const xpsi_b200_pipeline_config& c = p->cfg;
+  auto& s = p->store;
+  const size_t M = c.n_members, Cn = c.n_components;
+  // block rows [off, off + cnt) of a store array -> the pipeline's per-batch array (sized for max_batch once)
+  auto d2d = [&](Dev<double>& dst, const Dev<double>& src, size_t off, size_t cnt) -> cudaError_t {
+    const size_t per = cnt / ((size_t)((first + count - off) < p->max_batch ? (first + count - off) : p->max_batch));
+    cudaError_t e = dst.alloc(per * (size_t)p->max_batch);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(dst.p, src.p + off, cnt * sizeof(double), cudaMemcpyDeviceToDevice, g_stream);
+  };
+  for (long long off = first; off < first + count; off += p->max_batch) {
+    const size_t B = (size_t)((first + count - off) < p->max_batch ? (first + count - off) : p->max_batch);
+    const size_t o = (size_t)off;
+    CK(d2d(p->omega, s.omega, o, B)); CK(d2d(p->inclination, s.incl, o, B)); CK(d2d(p->d_sq, s.d_sq, o, B));
+    CK(d2d(p->shifts, s.shifts, o * Cn, B * Cn));
+    CK(d2d(p->e_Req, s.Req, o, B)); CK(d2d(p->e_rs, s.rs, o, B)); CK(d2d(p->e_eps, s.eps, o, B));
+    CK(d2d(p->e_zeta, s.zeta, o, B));
+    CK(d2d(p->e_colat, s.colat, o * M, B * M)); CK(d2d(p->e_rad, s.rad, o * M, B * M));
+    CK(d2d(p->e_temp, s.temp, o * M, B * M)); CK(d2d(p->e_phish, s.phish, o * M, B * M));
+    if (s.has_hole) {
+      CK(d2d(p->e_hrad, s.hrad, o * M, B * M)); CK(d2d(p->e_hcolat, s.hcolat, o * M, B * M));
+      CK(d2d(p->e_hazi, s.hazi, o * M, B * M));
+    }
+    if (s.has_extra) CK(d2d(p->e_extra, s.extra, o * M * (c.n_params - 2), B * M * (c.n_params - 2)));
+    if (s.has_att) { CK(d2d(p->att_power, s.att_power, o, B)); p->att_power_valid = 1; }
+    if (s.has_else) { CK(d2d(p->x_temp, s.else_temp, o, B)); p->else_temp_valid = 1; }
+    CK(cudaMemsetAsync(p->status.p, 0, B * sizeof(int), g_stream));
+    int rc = set_embed_args(p, (int)B, s.mode_frequency, s.num_cells, s.min_sqrt, s.max_sqrt, s.has_hole,
+                            s.has_partner, s.has_extra);
+    if (rc) return rc;
+    rc = pipeline_embed_launch(p);
+    if (rc) return rc;
+    rc = pipeline_run(p, (int)B);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(s.lnL.p + o, p->lnL.p, B * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+    CK(cudaMemcpyAsync(s.status.p + o, p->status.p, B * sizeof(int), cudaMemcpyDeviceToDevice, g_stream));
+  }
+  return 0;
+}
+
+int xpsi_b200_pipeline_sweep_download(xpsi_b200_pipeline* p, long long first, long long count, double* lnL, int* status) {
+  if (!p || first < 0 || count < 1 || (size_t)(first + count) > p->store.N)
+    return fail(XPSI_B200_EINVAL, "sweep range outside the uploaded parameter vectors");
+  g_d2h += (long long)(count * (sizeof(double) + sizeof(int)));
+  CK(cudaMemcpyAsync(lnL, p->store.lnL.p + first, count * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(status, p->store.status.p + first, count * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int xpsi_b200_pipeline_sweep_results(xpsi_b200_pipeline* p, double** lnL, int** status) {
+  if (!p || !p->store.N) return fail(XPSI_B200_EINVAL, "no sweep uploaded");
+  if (lnL) *lnL = p->store.lnL.p;
+  if (status) *status = p->store.status.p;
+  return 0;
 }
 
 int xpsi_b200_pipeline_eval_spots_resident(xpsi_b200_pipeline* p, int B) {
@@ -1162,16 +1292,18 @@ int xpsi_b200_pipeline_work_counters(xpsi_b200_pipeline* p, int enable, unsigned
     CK(cudaMemcpyAsync(out, p->work.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
   }
+  if (enable) CK(cudaMemsetAsync(p->work.p, 0, 4 * sizeof(unsigned long long), g_stream));   // counts accumulate from here
   p->count_work = enable;
   return 0;
 }
 
-int xpsi_b200_pipeline_stage_ms(xpsi_b200_pipeline* p, float ms[5]) {
+int xpsi_b200_pipeline_stage_ms(xpsi_b200_pipeline* p, float ms[6]) {
   if (!p) return fail(XPSI_B200_EINVAL, "null pipeline");
   CK(cudaEventSynchronize(p->ev[4]));
   for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms[i], p->ev[i], p->ev[i + 1]));
   ms[4] = 0.f;
   if (p->embed_timed) CK(cudaEventElapsedTime(&ms[4], p->ev_embed[0], p->ev_embed[1]));
+  CK(cudaEventElapsedTime(&ms[5], p->ev_flux[0], p->ev_flux[1]));      // the flux kernel alone (inside integrate)
   return 0;
 }
 

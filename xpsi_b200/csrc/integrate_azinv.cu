@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
   const double Lorentz = sqrt(1.0 - beta * beta);
   const double maxDefl = a.maxDeflection[ring];
   int n_img = a.image_order_limit > 0 ? a.image_order_limit : (int)ceil(maxDefl / kPi);
-  if (n_img > n_img_max) n_img = n_img_max;
+  const bool clamped = n_img > n_img_max;      // more image orders inferred than the kernels keep
+  if (clamped) n_img = n_img_max;
   __syncthreads();
   const int jhalf = s_jhalf;        // first ray with deflection > pi/2 (clamped)
 
@@ -388,6 +389,8 @@ __global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
     while (n < n_img && !s_inv2[n]) { bad |= s_dom[n] | s_mono[n]; ++n; }
     if (n < n_img) bad |= s_dom[n];          // that order's leaf loop did run
     if (bad) { atomicExch(a.status + q, kNumericalError); n = 0; }
+    // every kept order was visible and the reference would have gone on to the next one: refuse, never truncate
+    else if (clamped && n == n_img) { atomicExch(a.status + q, kUnsupported); n = 0; }
     if (a.work && !bad) {        // algorithmic-work counters for the roofline
       const int reached = (n < n_img) ? n + 1 : n;
       unsigned long long V = 0, Kc = 0;
@@ -1363,6 +1366,7 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
     k_azinv_moments<<<ggrid, kMomThreads, msm, stream>>>(a);
   } else k_azinv_cells<<<ggrid, 32, 0, stream>>>(a);
   if ((err = cudaGetLastError()) != cudaSuccess) return err;
+  if (a.ev_flux[0]) cudaEventRecord(a.ev_flux[0], stream);
   if (atm == 1 && corr == 0) err = launch_flux<1, 0>(a, fgrid, fsm, stream);
   else if (atm == 1 && corr == 1) err = launch_flux<1, 1>(a, fgrid, fsm, stream);
   else if (atm == 1 && corr == 2) err = launch_flux<1, 2>(a, fgrid, fsm, stream);
@@ -1370,6 +1374,7 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   else if (atm == 2 && corr == 1) err = launch_flux<2, 1>(a, fgrid, fsm, stream);
   else err = launch_flux<2, 2>(a, fgrid, fsm, stream);
   if (err != cudaSuccess) return err;
+  if (a.ev_flux[1]) cudaEventRecord(a.ev_flux[1], stream);
   err = cudaGetLastError();
   if (err != cudaSuccess) return err;
   if (a.scale_by_energy) {

@@ -60,6 +60,7 @@ struct AzinvArgs {
   double* ws_cells;                  // with ws_mom: [Q][n_rings][2][n_azi] compact (azimuth, area) lists of the radiating cells
   unsigned long long* work;          // nullptr or [4]: H half-leaf visits, V visible leaves,
                                      //   RI (ring,image) pairs reaching the phase stage, K radiating cells over RI
+  cudaEvent_t ev_flux[2];            // host side only: recorded around the flux kernel when non-null (roofline timing)
 };
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream);
 // a2: cellmesh/integrator.pyx (no azimuthal invariance); same argument block, parameters read per cell.

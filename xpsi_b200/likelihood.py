@@ -27,6 +27,33 @@ class Likelihood:
         self.externally_updated = False
 
     @property
+    def pipeline(self):
+        return self._pipe
+
+    def _filled(self, P):
+        """``fill`` may return the spot batch alone (it then uploads per-block extras itself) or
+        ``(spots, dict(att_power=..., else_temperature=...))``."""
+        r = self._fill(self._pipe, P)
+        return r if isinstance(r, tuple) else (r, None)
+
+    def sweep_local(self, P, download=True):
+        """All rows of ``P`` on this GPU with the parameter vectors resident on the device: one upload, blocks of
+        ``max_batch``, one download (``download=False`` leaves the results on the device for a collective,
+        ``pipeline.sweep_device_results()``).  No prior, statuses as in :meth:`batch`."""
+        P = np.atleast_2d(np.asarray(P, dtype=np.float64))
+        spots, extras = self._filled(P)
+        if extras is None and (self._pipe.shape.get("has_elsewhere") or self._pipe.shape.get("has_attenuation")):
+            raise ValueError("sweeps of a pipeline with Elsewhere / interstellar components need a fill function "
+                             "that returns (spots, dict(att_power=..., else_temperature=...))")
+        self._pipe.sweep_upload(spots, **(extras or {}))
+        self._pipe.sweep_run()
+        if not download:
+            return None
+        lnL, status = self._pipe.sweep_download()
+        lnL[status != 0] = np.nan
+        return lnL, status
+
+    @property
     def random_near_llzero(self):
         """xpsi/Likelihood.py:267-271"""
         return float(self.llzero * (0.1 + 0.9 * np.random.rand(1))[0])
@@ -49,7 +76,10 @@ class Likelihood:
         status = np.empty(P.shape[0], dtype=np.int32)
         for i in range(0, P.shape[0], self._max_batch):
             blk = P[i:i + self._max_batch]
-            lnL[i:i + blk.shape[0]], status[i:i + blk.shape[0]] = self._pipe.eval_spots(self._fill(self._pipe, blk))
+            spots, extras = self._filled(blk)
+            if extras is not None:
+                self._pipe.upload_extras(blk.shape[0], **extras)
+            lnL[i:i + blk.shape[0]], status[i:i + blk.shape[0]] = self._pipe.eval_spots(spots)
         bad = ~np.isin(status, (0,) + self.NUMERICAL_STATUSES)
         if strict and bad.any():
             k = int(np.flatnonzero(bad)[0])

@@ -181,6 +181,16 @@ class SpotBatch:
         return s
 
 
+class _DeviceArray:
+    """A device buffer owned by the pipeline, exposed through ``__cuda_array_interface__`` (version 3)."""
+
+    def __init__(self, ptr, n, typestr, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr=typestr, data=(int(ptr), False), version=3,
+                                             strides=None, stream=None)   # ordered by the caller
+        # (the producer is the library's stream, ``xpsi_b200_stream()``: consume under that stream)
+
+
 class BatchedLikelihood:
     """Device-resident likelihood for a fixed model configuration.
 
@@ -277,6 +287,8 @@ class BatchedLikelihood:
             x.attenuation = _lib.dptr(att)
         x.beam_opt = int(beam_opt)
         _lib.check(_lib.lib.xpsi_b200_pipeline_set_extras(self.handle, C.byref(x)))
+        self.shape["has_elsewhere"] = elsewhere is not None
+        self.shape["has_attenuation"] = attenuation is not None
 
     def upload_extras(self, B, att_power=None, else_temperature=None, elsewhere=None, correction_srcParams=None):
         """Per-batch inputs of the optional components for the next evaluation.
@@ -388,17 +400,62 @@ class BatchedLikelihood:
         return f, g, e
 
     def count_work(self, enable=True):
-        """Toggle the integrator's algorithmic-work counters; returns the counters of the
-        last counted eval as dict(H, V, RI, K)."""
+        """Toggle the integrator's algorithmic-work counters; returns dict(H, V, RI, K) summed
+        over the evaluations since counting was last enabled (enabling resets them)."""
         out = (C.c_ulonglong * 4)()
         _lib.check(_lib.lib.xpsi_b200_pipeline_work_counters(self.handle, int(enable), out))
         return dict(H=out[0], V=out[1], RI=out[2], K=out[3])
+
+    # ---- sweep: N parameter vectors resident on the device, evaluated block by block -------------------
+    def sweep_upload(self, spots, att_power=None, else_temperature=None):
+        """Upload the parameter-level inputs of ``spots.B`` parameter vectors once (any N; evaluation
+        proceeds in blocks of ``max_batch``)."""
+        st = spots.struct()
+        keep = []
+
+        def opt(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != (spots.B,):
+                raise ValueError("per-theta extras must have shape (%d,)" % spots.B)
+            keep.append(a)
+            return _lib.dptr(a)
+        _lib.check(_lib.lib.xpsi_b200_pipeline_sweep_upload(self.handle, spots.B, C.byref(st), opt(att_power),
+                                                            opt(else_temperature)))
+        self._sweep_n = spots.B
+
+    def sweep_run(self, first=0, count=None):
+        """Queue embed + the four stages for rows ``[first, first+count)`` of the uploaded sweep (no sync)."""
+        count = self._sweep_n - first if count is None else count
+        _lib.check(_lib.lib.xpsi_b200_pipeline_sweep_run(self.handle, first, count))
+
+    def sweep_download(self, first=0, count=None):
+        count = self._sweep_n - first if count is None else count
+        lnL = np.empty(count, dtype=np.float64)
+        status = np.empty(count, dtype=np.int32)
+        _lib.check(_lib.lib.xpsi_b200_pipeline_sweep_download(self.handle, first, count, _lib.dptr(lnL),
+                                                              _lib.iptr(status)))
+        return lnL, status
+
+    def sweep_device_results(self):
+        """Device arrays ``lnL[N]`` (float64) and ``status[N]`` (int32) of the sweep as objects exposing
+        ``__cuda_array_interface__`` -- what a collective reads in place (``torch.as_tensor(obj, device=...)``)."""
+        a, b = C.c_void_p(), C.c_void_p()
+        _lib.check(_lib.lib.xpsi_b200_pipeline_sweep_results(self.handle, C.byref(a), C.byref(b)))
+        return (_DeviceArray(a.value, self._sweep_n, "<f8", self), _DeviceArray(b.value, self._sweep_n, "<i4", self))
+
+    def sweep_spots(self, spots, att_power=None, else_temperature=None):
+        """Upload once, evaluate every block, download once: ``(lnL[N], status[N])``."""
+        self.sweep_upload(spots, att_power, else_temperature)
+        self.sweep_run()
+        return self.sweep_download()
 
     def eval_spots_resident(self, B):
         """embed + four stages on the spot batch already uploaded by ``embed_spots`` (kernels only)."""
         _lib.check(_lib.lib.xpsi_b200_pipeline_eval_spots_resident(self.handle, B))
 
     def stage_ms(self):
-        ms = (C.c_float * 5)()
+        ms = (C.c_float * 6)()
         _lib.check(_lib.lib.xpsi_b200_pipeline_stage_ms(self.handle, ms))
-        return dict(embed=ms[4], integrate=ms[0], energy=ms[1], fold=ms[2], marginal=ms[3])
+        return dict(embed=ms[4], integrate=ms[0], energy=ms[1], fold=ms[2], marginal=ms[3], flux_kernel=ms[5])

@@ -158,19 +158,27 @@ M2_BACKGROUND_RATE = 1.0e-3   # counts/s/channel, flat
 
 def m2_theta_batch(n, seed=20261017):
     """``n`` ST-U parameter vectors, uniform in ``M2_BOUNDS`` (in-table temperatures; the two spots cannot
-    overlap inside the box; spots covering a pole are kept -- the embed meshes them as polar caps)."""
+    overlap inside the box; spots covering a pole are kept -- the embed meshes them as polar caps).  The list is
+    a prefix-stable stream: row k is the same whatever ``n`` (11 uniforms per candidate, in order)."""
     rng = np.random.default_rng(seed)
-    out = np.empty((n, len(M2_NAMES)))
+    d = len(M2_NAMES)
+    out = np.empty((n, d))
     k = 0
     while k < n:
-        u = rng.uniform(size=len(M2_NAMES))
+        u = rng.uniform(size=(max(n - k, 16), d))
         th = M2_BOUNDS[:, 0] + u * (M2_BOUNDS[:, 1] - M2_BOUNDS[:, 0])
         # compactness: R >= 3 r_g  (TestRun_Num.py CustomPrior)
-        if th[1] * KM < 3.0 * th[0] * GM_SUN:
-            continue
-        out[k] = th
-        k += 1
+        th = th[th[:, 1] * KM >= 3.0 * th[:, 0] * GM_SUN]
+        take = min(n - k, th.shape[0])
+        out[k:k + take] = th[:take]
+        k += take
     return out
+
+
+def m2_prior():
+    """The prior of the list above as a vectorised ``xpsi.Prior`` stand-in (xpsi_b200.sampling.BoxPrior)."""
+    from .sampling import BoxPrior
+    return BoxPrior(M2_NAMES, M2_BOUNDS, rules=(lambda P: P[:, 1] * KM >= 3.0 * P[:, 0] * GM_SUN,))
 
 
 def m2_bench_thetas(first, count):
