@@ -163,16 +163,18 @@ int xpsi_b200_instrument_fold(const double* matrix, int n_rows, int n_cols, int 
 
 /* ---- likelihoods.precomputation / eval_marginal_likelihood -----------------------
  * replace xpsi/likelihoods/default_background_marginalisation.pyx:38-68 and :450-734.
- * components: n_comp arrays [n_chan][n_phases] sharing one phase grid
- * component_phases[n_phases] (cycles).  background may be NULL.  Returns 0,
+ * components: n_comp arrays, component c is [n_chan][n_phases[c]] on its own phase
+ * grid component_phases[c][n_phases[c]] (cycles), as compute_expected_counts.pyx:66-197
+ * takes them (n_phases[c] = 1: a time-invariant component); allow_negative: NULL (no
+ * component may contribute negatively) or one flag per component.  background may be NULL.  Returns 0,
  * XPSI_B200_ESLIM or XPSI_B200_EQUADRATURE (the two cases where the reference
  * returns a random near-llzero value); *lnL is then unspecified.               */
 int xpsi_b200_precomputation(const int* counts, int n_chan, int n_bins, double* out);
 int xpsi_b200_eval_marginal_likelihood(
     double exposure_time, const double* phases, int n_bins, const double* counts, int n_chan,
-    const double* const* components, int n_comp, const double* component_phases, int n_phases,
+    const double* const* components, int n_comp, const double* const* component_phases, const int* n_phases,
     const double* phase_shifts, const double* neg_sum_ln_data_factorial, const double* support,
-    double epsilon, double sigmas, double llzero, int allow_negative, double slim,
+    double epsilon, double sigmas, double llzero, const int* allow_negative, double slim,
     const double* background, int phase_interpolant,
     double* lnL, double* expected_counts, double* mcl_background,
     double* mcl_background_given_support);
@@ -186,9 +188,9 @@ int xpsi_b200_eval_marginal_likelihood(
  * random near-llzero penalty (zero expectation in a bin with counts).                  */
 int xpsi_b200_poisson_likelihood_given_background(
     double exposure_time, const double* phases, int n_bins, const double* counts, int n_chan,
-    const double* const* components, int n_comp, const double* component_phases, int n_phases,
+    const double* const* components, int n_comp, const double* const* component_phases, const int* n_phases,
     const double* phase_shifts, const double* background, const double* neg_sum_ln_data_factorial,
-    int allow_negative, int phase_interpolant, double* lnL, double* expected_counts);
+    const int* allow_negative, int phase_interpolant, double* lnL, double* expected_counts);
 
 /* ---- batched likelihood pipeline (additional API) -------------
  * One handle holds every theta-independent constant on the device; eval takes a
@@ -280,6 +282,11 @@ typedef struct {
   int beam_opt;
 } xpsi_b200_pipeline_extras;
 int xpsi_b200_pipeline_set_extras(xpsi_b200_pipeline* p, const xpsi_b200_pipeline_extras* extras);
+/* on != 0: the ring / energy-chunk contributions to a member's signal are combined by a two-stage reduction in
+ * fixed order (no floating-point atomics): lnL is then bitwise reproducible from run to run and independent of
+ * the position of a parameter vector in its batch (samplers that resume or replay compare lnL bitwise).  Costs
+ * one extra pass over [B*M][max_rings][n_energies][n_phases] doubles of workspace.                          */
+int xpsi_b200_pipeline_set_deterministic(xpsi_b200_pipeline* p, int on);
 
 /* Per-batch inputs of the optional components, uploaded for the next evaluation of B parameter vectors.
  * Parameter-level path (eval_spots): else_temperature [B] and att_power [B] are enough -- the closed

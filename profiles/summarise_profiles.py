@@ -96,12 +96,12 @@ def main():
         for name, v in step.items():
             kernels.setdefault(name, {})["step_ms_cold"] = v
             kernels[name]["step_share"] = v / tot
-        out_csv = os.path.join(ROOT, "profiles", tag + "_launches.csv")
-        open(out_csv, "w").writelines(lines)
+
     out = {"tag": tag, "batch": batch, "source": "ncu --set full --clock-control none, one launch per kernel of one "
            "bench step (profiles/make_profiles.sh); step_share from the gpu__time_duration launch list of the same command",
            "kernels": kernels}
-    with open(os.path.join(ROOT, "profiles", tag + "_kernels.json"), "w") as f:
+    outdir = os.path.join(ROOT, sys.argv[3]) if len(sys.argv) > 3 else os.path.join(ROOT, "profiles")
+    with open(os.path.join(outdir, tag + "_kernels.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     for name, k in sorted(kernels.items(), key=lambda kv: -kv[1].get("step_share", 0)):
         print("%-26s %6.2f%% of step  %8.3f ms  fp64 %5.1f%%  issue %5.1f%%  regs %3d  dram %8.1f MB"

@@ -160,12 +160,12 @@ _proto("xpsi_b200_instrument_fold", C.c_int,
        [c_double_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p])
 _proto("xpsi_b200_precomputation", C.c_int, [c_int_p, C.c_int, C.c_int, c_double_p])
 _proto("xpsi_b200_eval_marginal_likelihood", C.c_int,
-       [C.c_double, c_double_p, C.c_int, c_double_p, C.c_int, C.POINTER(c_double_p), C.c_int, c_double_p,
-        C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double, C.c_double, C.c_int,
+       [C.c_double, c_double_p, C.c_int, c_double_p, C.c_int, C.POINTER(c_double_p), C.c_int, C.POINTER(c_double_p),
+        c_int_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double, C.c_double, c_int_p,
         C.c_double, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p])
 _proto("xpsi_b200_poisson_likelihood_given_background", C.c_int,
-       [C.c_double, c_double_p, C.c_int, c_double_p, C.c_int, C.POINTER(c_double_p), C.c_int, c_double_p,
-        C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p])
+       [C.c_double, c_double_p, C.c_int, c_double_p, C.c_int, C.POINTER(c_double_p), C.c_int, C.POINTER(c_double_p),
+        c_int_p, c_double_p, c_double_p, c_double_p, c_int_p, C.c_int, c_double_p, c_double_p])
 _proto("xpsi_b200_pipeline_create", C.c_void_p, [C.POINTER(PipelineConfig), C.c_int])
 _proto("xpsi_b200_pipeline_destroy", None, [C.c_void_p])
 _proto("xpsi_b200_pipeline_eval", C.c_int, [C.c_void_p, C.c_int, C.POINTER(Batch), c_double_p, c_int_p])
@@ -180,6 +180,7 @@ _proto("xpsi_b200_pipeline_eval_spots_resident", C.c_int, [C.c_void_p, C.c_int])
 _proto("xpsi_b200_pipeline_eval_spots", C.c_int, [C.c_void_p, C.c_int, C.POINTER(SpotBatch), c_double_p, c_int_p])
 _proto("xpsi_b200_pipeline_fetch_embed", C.c_int, [C.c_void_p, C.c_int, c_int_p] + [c_double_p] * 10)
 _proto("xpsi_b200_pipeline_stage_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)])
+_proto("xpsi_b200_pipeline_set_deterministic", C.c_int, [C.c_void_p, C.c_int])
 _proto("xpsi_b200_pipeline_sweep_upload", C.c_int, [C.c_void_p, C.c_longlong, C.POINTER(SpotBatch), c_double_p, c_double_p])
 _proto("xpsi_b200_pipeline_sweep_run", C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong])
 _proto("xpsi_b200_pipeline_sweep_download", C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, c_double_p, c_int_p])
@@ -199,7 +200,7 @@ EXPORTED = [
     "xpsi_b200_pipeline_embed_spots", "xpsi_b200_pipeline_eval_spots", "xpsi_b200_pipeline_fetch_embed",
     "xpsi_b200_pipeline_eval_spots_resident", "xpsi_b200_poisson_likelihood_given_background",
     "xpsi_b200_pipeline_sweep_upload", "xpsi_b200_pipeline_sweep_run", "xpsi_b200_pipeline_sweep_download",
-    "xpsi_b200_pipeline_sweep_results",
+    "xpsi_b200_pipeline_sweep_results", "xpsi_b200_pipeline_set_deterministic",
 ]
 
 

@@ -526,26 +526,63 @@ int xpsi_b200_precomputation(const int* counts, int n_chan, int n_bins, double* 
   return 0;
 }
 
+}  // extern "C"
+
+namespace {
+// components with their own phase grids -> padded device arrays: pulses [n_comp][n_chan][Pmax], grids [n_comp][Pmax]
+struct CompUpload { Dev<double> pulses, grids; Dev<int> n_nodes, allow; int Pmax = 0; bool uniform = true; };
+
+int upload_components(CompUpload& u, const double* const* components, int n_comp, int n_chan,
+                      const double* const* component_phases, const int* n_phases, const int* allow_negative) {
+  u.Pmax = 0;
+  for (int c = 0; c < n_comp; ++c) {
+    if (n_phases[c] < 5 && n_phases[c] != 1) return fail(XPSI_B200_EINVAL, "a component needs 1 (time-invariant) or >= 5 phases");
+    if (n_phases[c] > u.Pmax) u.Pmax = n_phases[c];
+  }
+  u.uniform = true;
+  for (int c = 1; c < n_comp; ++c) {
+    if (n_phases[c] != n_phases[0]) { u.uniform = false; break; }
+    for (int i = 0; i < n_phases[0]; ++i)
+      if (component_phases[c][i] != component_phases[0][i]) { u.uniform = false; break; }
+  }
+  const size_t P = (size_t)u.Pmax, np = (size_t)n_chan * P;
+  CK(u.pulses.alloc(np * n_comp));
+  CK(u.grids.alloc(P * n_comp));
+  if (!u.uniform) {
+    CK(cudaMemsetAsync(u.pulses.p, 0, np * n_comp * sizeof(double), g_stream));
+    CK(cudaMemsetAsync(u.grids.p, 0, P * n_comp * sizeof(double), g_stream));
+  }
+  for (int c = 0; c < n_comp; ++c) {
+    const size_t w = (size_t)n_phases[c] * sizeof(double);
+    g_h2d += (long long)(w * (n_chan + 1));
+    CK(cudaMemcpy2DAsync(u.pulses.p + c * np, P * sizeof(double), components[c], w, w, n_chan, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(u.grids.p + c * P, component_phases[c], w, cudaMemcpyHostToDevice, g_stream));
+  }
+  CK(u.n_nodes.upload(n_phases, n_comp));
+  if (allow_negative) CK(u.allow.upload(allow_negative, n_comp));
+  return 0;
+}
+}  // namespace
+
+extern "C" {
 int xpsi_b200_eval_marginal_likelihood(
     double exposure_time, const double* phases, int n_bins, const double* counts, int n_chan,
-    const double* const* components, int n_comp, const double* component_phases, int n_phases,
+    const double* const* components, int n_comp, const double* const* component_phases, const int* n_phases,
     const double* phase_shifts, const double* precomp, const double* support, double epsilon,
-    double sigmas, double llzero, int allow_negative, double slim, const double* background,
+    double sigmas, double llzero, const int* allow_negative, double slim, const double* background,
     int phase_interpolant, double* lnL, double* expected_counts, double* mcl_background,
     double* mcl_background_given_support) {
   int rc = ensure_stream();
   if (rc) return rc;
   if (n_bins < 1 || n_bins > xb::marginal_max_bins()) return fail(XPSI_B200_EUNSUPPORTED, "1..128 phase bins supported");
-  if (n_comp < 1 || n_chan < 1 || (n_phases < 5 && n_phases != 1)) return fail(XPSI_B200_EINVAL, "bad dimensions");
-  Dev<double> d_pulses, d_cph, d_sh, d_dph, d_cnt, d_pre, d_sup, d_bg, d_clnl, d_exp, d_mb, d_mbs, d_lnl;
+  if (n_comp < 1 || n_chan < 1 || !component_phases || !n_phases) return fail(XPSI_B200_EINVAL, "bad dimensions");
+  Dev<double> d_sh, d_dph, d_cnt, d_pre, d_sup, d_bg, d_clnl, d_exp, d_mb, d_mbs, d_lnl;
   Dev<int> d_cst, d_st;
-  const size_t np = (size_t)n_chan * n_phases;
-  CK(d_pulses.alloc(np * n_comp));
-  for (int c = 0; c < n_comp; ++c) {
-    g_h2d += (long long)(np * sizeof(double));
-    CK(cudaMemcpyAsync(d_pulses.p + c * np, components[c], np * sizeof(double), cudaMemcpyHostToDevice, g_stream));
-  }
-  CK(d_cph.upload(component_phases, n_phases)); CK(d_sh.upload(phase_shifts, n_comp));
+  CompUpload cu;
+  rc = upload_components(cu, components, n_comp, n_chan, component_phases, n_phases, allow_negative);
+  if (rc) return rc;
+  const int n_phases_max = cu.Pmax;
+  CK(d_sh.upload(phase_shifts, n_comp));
   CK(d_dph.upload(phases, n_bins + 1)); CK(d_cnt.upload(counts, (size_t)n_chan * n_bins));
   CK(d_pre.upload(precomp, n_chan)); CK(d_sup.upload(support, (size_t)n_chan * 2));
   if (background) CK(d_bg.upload(background, (size_t)n_chan * n_bins));
@@ -554,11 +591,13 @@ int xpsi_b200_eval_marginal_likelihood(
   CK(cudaMemsetAsync(d_st.p, 0, sizeof(int), g_stream));
   xb::MarginalArgs a;
   memset(&a, 0, sizeof(a));
-  a.B = 1; a.n_comp = n_comp; a.n_chan = n_chan; a.n_phases = n_phases; a.n_bins = n_bins;
-  a.pulses = d_pulses.p; a.comp_phases = d_cph.p; a.phase_shifts = d_sh.p; a.data_phases = d_dph.p;
+  a.B = 1; a.n_comp = n_comp; a.n_chan = n_chan; a.n_phases = n_phases_max; a.n_bins = n_bins;
+  a.pulses = cu.pulses.p; a.comp_phases = cu.grids.p; a.phase_shifts = d_sh.p; a.data_phases = d_dph.p;
+  if (!cu.uniform) a.comp_n_phases = cu.n_nodes.p;
+  if (allow_negative) a.comp_allow_negative = cu.allow.p;
   a.counts = d_cnt.p; a.precomp = d_pre.p; a.support = d_sup.p; a.background = background ? d_bg.p : nullptr;
   a.exposure_time = exposure_time; a.epsilon = epsilon; a.sigmas = sigmas; a.llzero = llzero; a.slim = slim;
-  a.allow_negative = allow_negative; a.interp = phase_interpolant;
+  a.allow_negative = 0; a.interp = phase_interpolant;
   a.chan_lnL = d_clnl.p; a.chan_status = d_cst.p; a.expected = d_exp.p; a.mcl_bg = d_mb.p;
   a.mcl_bg_support = d_mbs.p; a.lnL = d_lnl.p; a.status = d_st.p;
   cudaError_t e = xb::launch_marginal(a, g_stream);
@@ -576,22 +615,20 @@ int xpsi_b200_eval_marginal_likelihood(
 
 int xpsi_b200_poisson_likelihood_given_background(
     double exposure_time, const double* phases, int n_bins, const double* counts, int n_chan,
-    const double* const* components, int n_comp, const double* component_phases, int n_phases,
+    const double* const* components, int n_comp, const double* const* component_phases, const int* n_phases,
     const double* phase_shifts, const double* background, const double* neg_sum_ln_data_factorial,
-    int allow_negative, int phase_interpolant, double* lnL, double* expected_counts) {
+    const int* allow_negative, int phase_interpolant, double* lnL, double* expected_counts) {
   int rc = ensure_stream();
   if (rc) return rc;
   if (n_bins < 1 || n_bins > xb::marginal_max_bins()) return fail(XPSI_B200_EUNSUPPORTED, "1..128 phase bins supported");
-  if (n_comp < 1 || n_chan < 1 || (n_phases < 5 && n_phases != 1) || !background) return fail(XPSI_B200_EINVAL, "bad arguments");
-  Dev<double> d_pulses, d_cph, d_sh, d_dph, d_cnt, d_pre, d_bg, d_clnl, d_exp, d_lnl, d_sup;
+  if (n_comp < 1 || n_chan < 1 || !component_phases || !n_phases || !background) return fail(XPSI_B200_EINVAL, "bad arguments");
+  Dev<double> d_sh, d_dph, d_cnt, d_pre, d_bg, d_clnl, d_exp, d_lnl, d_sup;
   Dev<int> d_cst, d_st;
-  const size_t np = (size_t)n_chan * n_phases;
-  CK(d_pulses.alloc(np * n_comp));
-  for (int c = 0; c < n_comp; ++c) {
-    g_h2d += (long long)(np * sizeof(double));
-    CK(cudaMemcpyAsync(d_pulses.p + c * np, components[c], np * sizeof(double), cudaMemcpyHostToDevice, g_stream));
-  }
-  CK(d_cph.upload(component_phases, n_phases)); CK(d_sh.upload(phase_shifts, n_comp));
+  CompUpload cu;
+  rc = upload_components(cu, components, n_comp, n_chan, component_phases, n_phases, allow_negative);
+  if (rc) return rc;
+  const int n_phases_max = cu.Pmax;
+  CK(d_sh.upload(phase_shifts, n_comp));
   CK(d_dph.upload(phases, n_bins + 1));
   if (counts) CK(d_cnt.upload(counts, (size_t)n_chan * n_bins));
   if (neg_sum_ln_data_factorial) CK(d_pre.upload(neg_sum_ln_data_factorial, n_chan));
@@ -603,11 +640,13 @@ int xpsi_b200_poisson_likelihood_given_background(
   CK(cudaMemsetAsync(d_st.p, 0, sizeof(int), g_stream));
   xb::MarginalArgs a;
   memset(&a, 0, sizeof(a));
-  a.B = 1; a.n_comp = n_comp; a.n_chan = n_chan; a.n_phases = n_phases; a.n_bins = n_bins;
-  a.pulses = d_pulses.p; a.comp_phases = d_cph.p; a.phase_shifts = d_sh.p; a.data_phases = d_dph.p;
+  a.B = 1; a.n_comp = n_comp; a.n_chan = n_chan; a.n_phases = n_phases_max; a.n_bins = n_bins;
+  a.pulses = cu.pulses.p; a.comp_phases = cu.grids.p; a.phase_shifts = d_sh.p; a.data_phases = d_dph.p;
+  if (!cu.uniform) a.comp_n_phases = cu.n_nodes.p;
+  if (allow_negative) a.comp_allow_negative = cu.allow.p;
   a.counts = counts ? d_cnt.p : nullptr; a.precomp = neg_sum_ln_data_factorial ? d_pre.p : nullptr;
   a.support = d_sup.p; a.background = d_bg.p; a.exposure_time = exposure_time; a.slim = -1.0;
-  a.allow_negative = allow_negative; a.interp = phase_interpolant; a.given_background = 1;
+  a.allow_negative = 0; a.interp = phase_interpolant; a.given_background = 1;
   a.chan_lnL = d_clnl.p; a.chan_status = d_cst.p; a.expected = d_exp.p; a.lnL = d_lnl.p; a.status = d_st.p;
   cudaError_t e = xb::launch_marginal(a, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_marginal");
@@ -643,8 +682,9 @@ struct xpsi_b200_pipeline {
   Dev<double> flux, xin, folded, chan_lnL, expected, lnL;
   Dev<int> chan_status, status_q, status;
   Dev<unsigned long long> work;
-  Dev<double> ws_leaf, ws_hdr, ws_slab, ws_mom, ws_cells; Dev<int> ws_ihdr, ws_cnt; Dev<int2> ws_meta;
-  int mom_cap = 0;
+  Dev<double> ws_leaf, ws_hdr, ws_slab, ws_cells, ws_tiles, flux_part; Dev<int> ws_ihdr, ws_tmeta; Dev<int2> ws_thdr;
+  int tile_cap = 0;
+  int deterministic = 0;             // ring sums by a two-stage ordered reduction instead of fp64 atomics
   // embed inputs / scratch
   Dev<double> e_Req, e_rs, e_eps, e_zeta, e_colat, e_rad, e_temp, e_phish, e_maxAlpha, e_hrad, e_hcolat, e_hazi, e_extra;
   Dev<int> e_partner, e_iscede;
@@ -788,8 +828,9 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   }
   a.flux = p->flux.p; a.status = p->status_q.p;
   a.ws_leaf = p->ws_leaf.p; a.ws_hdr = p->ws_hdr.p; a.ws_ihdr = p->ws_ihdr.p; a.ws_slab = p->ws_slab.p;
-  a.ws_mom = p->ws_mom.p; a.ws_meta = p->ws_meta.p; a.ws_cnt = p->ws_cnt.p; a.mom_cap = p->mom_cap;
+  a.ws_tiles = p->ws_tiles.p; a.ws_tmeta = p->ws_tmeta.p; a.ws_thdr = p->ws_thdr.p; a.tile_cap = p->tile_cap;
   a.ws_cells = p->ws_cells.p;
+  a.flux_part = p->deterministic ? p->flux_part.p : nullptr;
   a.work = p->count_work ? p->work.p : nullptr;       // accumulates over evaluations; reset by work_counters()
   a.ev_flux[0] = p->ev_flux[0]; a.ev_flux[1] = p->ev_flux[1];
   cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
@@ -839,7 +880,9 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   e = xb::launch_marginal(m, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_marginal");
   CK(cudaEventRecord(p->ev[4], g_stream));
-  g_launches += 9 + (c.hot_atm_ext == XPSI_B200_ATM_NUM4D ? 2 : 0);   // expand, geometry, [slab, slab-member], moments, flux, energy, fold, member-status, marginal, channel-sum
+  // expand, geometry, [slab, slab-member], tiles, flux (tensor-core + scalar for overflow rings), [ring reduction],
+  // energy, fold, member-status, marginal, channel-sum
+  g_launches += 10 + (c.hot_atm_ext == XPSI_B200_ATM_NUM4D ? 2 : 0) + (p->deterministic ? 1 : 0);
   return 0;
 }
 
@@ -947,14 +990,15 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
     size_t nl, nh, ni, ns;
     xb::azinv_workspace_sizes(w, &nl, &nh, &ni, &ns);
     ok(p->ws_leaf.alloc(nl)); ok(p->ws_hdr.alloc(nh)); ok(p->ws_ihdr.alloc(ni)); ok(p->ws_slab.alloc(ns));
-    // moment workspace: 24 leaf intervals per output phase covers spots up to ~0.7 rad in azimuthal
-    // half-width at 100 leaves; wider rings fall back to walking inside the flux CTA
-    w.n_phases = c.n_phases; w.mom_cap = 24;
-    size_t nm, nt, nc;
-    xb::azinv_moment_sizes(w, &nm, &nt, &nc);
-    ok(p->ws_mom.alloc(nm)); ok(p->ws_meta.alloc(nt)); ok(p->ws_cnt.alloc(nc));
+    // interval-moment tiles (B operands of the tensor-core accumulation): 48 steps per 8-phase tile cover rings
+    // whose cells reach ~41 leaf intervals (99 % of the ST-U prior's rings at 100 leaves); wider rings are
+    // integrated by the scalar flux kernel, which walks the cells itself
+    w.n_phases = c.n_phases; w.tile_cap = 48;
+    size_t td, tm, tq;
+    xb::azinv_tile_sizes(w, &td, &tm, &tq);
+    ok(p->ws_tiles.alloc(td)); ok(p->ws_tmeta.alloc(tm)); ok(p->ws_thdr.alloc(tq));
     ok(p->ws_cells.alloc(Q * c.max_rings * 2 * (size_t)c.max_azi));
-    p->mom_cap = w.mom_cap;
+    p->tile_cap = w.tile_cap;
   }
   for (int i = 0; i < 5; ++i) ok(cudaEventCreate(&p->ev[i]));
   for (int i = 0; i < 2; ++i) ok(cudaEventCreate(&p->ev_embed[i]));
@@ -972,6 +1016,16 @@ void xpsi_b200_pipeline_destroy(xpsi_b200_pipeline* p) {
   for (int i = 0; i < 2; ++i) if (p->ev_embed[i]) cudaEventDestroy(p->ev_embed[i]);
   for (int i = 0; i < 2; ++i) if (p->ev_flux[i]) cudaEventDestroy(p->ev_flux[i]);
   delete p;
+}
+
+int xpsi_b200_pipeline_set_deterministic(xpsi_b200_pipeline* p, int on) {
+  if (!p) return fail(XPSI_B200_EINVAL, "null pipeline");
+  if (on) {
+    const xpsi_b200_pipeline_config& c = p->cfg;
+    CK(p->flux_part.alloc((size_t)p->max_batch * c.n_members * c.max_rings * c.n_energies * c.n_phases));
+  }
+  p->deterministic = on ? 1 : 0;
+  return 0;
 }
 
 int xpsi_b200_pipeline_set_extras(xpsi_b200_pipeline* p, const xpsi_b200_pipeline_extras* x) {
@@ -1184,29 +1238,30 @@ int xpsi_b200_pipeline_sweep_run(xpsi_b200_pipeline* p, long long first, long lo
   const xpsi_b200_pipeline_config& c = p->cfg;
   auto& s = p->store;
   const size_t M = c.n_members, Cn = c.n_components;
-  // block rows [off, off + cnt) of a store array -> the pipeline's per-batch array (sized for max_batch once)
-  auto d2d = [&](Dev<double>& dst, const Dev<double>& src, size_t off, size_t cnt) -> cudaError_t {
-    const size_t per = cnt / ((size_t)((first + count - off) < p->max_batch ? (first + count - off) : p->max_batch));
+  // rows of a store array starting at element `at` -> the pipeline's per-batch array (sized for max_batch once);
+  // `per` = elements per parameter vector
+  auto d2d = [&](Dev<double>& dst, const Dev<double>& src, size_t at, size_t rows, size_t per) -> cudaError_t {
     cudaError_t e = dst.alloc(per * (size_t)p->max_batch);
     if (e != cudaSuccess) return e;
-    return cudaMemcpyAsync(dst.p, src.p + off, cnt * sizeof(double), cudaMemcpyDeviceToDevice, g_stream);
+    return cudaMemcpyAsync(dst.p, src.p + at, rows * per * sizeof(double), cudaMemcpyDeviceToDevice, g_stream);
   };
   for (long long off = first; off < first + count; off += p->max_batch) {
     const size_t B = (size_t)((first + count - off) < p->max_batch ? (first + count - off) : p->max_batch);
     const size_t o = (size_t)off;
-    CK(d2d(p->omega, s.omega, o, B)); CK(d2d(p->inclination, s.incl, o, B)); CK(d2d(p->d_sq, s.d_sq, o, B));
-    CK(d2d(p->shifts, s.shifts, o * Cn, B * Cn));
-    CK(d2d(p->e_Req, s.Req, o, B)); CK(d2d(p->e_rs, s.rs, o, B)); CK(d2d(p->e_eps, s.eps, o, B));
-    CK(d2d(p->e_zeta, s.zeta, o, B));
-    CK(d2d(p->e_colat, s.colat, o * M, B * M)); CK(d2d(p->e_rad, s.rad, o * M, B * M));
-    CK(d2d(p->e_temp, s.temp, o * M, B * M)); CK(d2d(p->e_phish, s.phish, o * M, B * M));
+    const size_t X = (size_t)(c.n_params > 2 ? c.n_params - 2 : 0);
+    CK(d2d(p->omega, s.omega, o, B, 1)); CK(d2d(p->inclination, s.incl, o, B, 1)); CK(d2d(p->d_sq, s.d_sq, o, B, 1));
+    CK(d2d(p->shifts, s.shifts, o * Cn, B, Cn));
+    CK(d2d(p->e_Req, s.Req, o, B, 1)); CK(d2d(p->e_rs, s.rs, o, B, 1)); CK(d2d(p->e_eps, s.eps, o, B, 1));
+    CK(d2d(p->e_zeta, s.zeta, o, B, 1));
+    CK(d2d(p->e_colat, s.colat, o * M, B, M)); CK(d2d(p->e_rad, s.rad, o * M, B, M));
+    CK(d2d(p->e_temp, s.temp, o * M, B, M)); CK(d2d(p->e_phish, s.phish, o * M, B, M));
     if (s.has_hole) {
-      CK(d2d(p->e_hrad, s.hrad, o * M, B * M)); CK(d2d(p->e_hcolat, s.hcolat, o * M, B * M));
-      CK(d2d(p->e_hazi, s.hazi, o * M, B * M));
+      CK(d2d(p->e_hrad, s.hrad, o * M, B, M)); CK(d2d(p->e_hcolat, s.hcolat, o * M, B, M));
+      CK(d2d(p->e_hazi, s.hazi, o * M, B, M));
     }
-    if (s.has_extra) CK(d2d(p->e_extra, s.extra, o * M * (c.n_params - 2), B * M * (c.n_params - 2)));
-    if (s.has_att) { CK(d2d(p->att_power, s.att_power, o, B)); p->att_power_valid = 1; }
-    if (s.has_else) { CK(d2d(p->x_temp, s.else_temp, o, B)); p->else_temp_valid = 1; }
+    if (s.has_extra) CK(d2d(p->e_extra, s.extra, o * M * X, B, M * X));
+    if (s.has_att) { CK(d2d(p->att_power, s.att_power, o, B, 1)); p->att_power_valid = 1; }
+    if (s.has_else) { CK(d2d(p->x_temp, s.else_temp, o, B, 1)); p->else_temp_valid = 1; }
     CK(cudaMemsetAsync(p->status.p, 0, B * sizeof(int), g_stream));
     int rc = set_embed_args(p, (int)B, s.mode_frequency, s.num_cells, s.min_sqrt, s.max_sqrt, s.has_hole,
                             s.has_partner, s.has_extra);

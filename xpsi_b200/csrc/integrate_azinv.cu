@@ -731,6 +731,106 @@ __global__ void __launch_bounds__(kMomThreads) k_azinv_moments(AzinvArgs a) {
 }
 
 // ===========================================================================
+// moments as tensor-core operands: the same walk, written as dense tiles.  For one image and one tile of 8
+// consecutive output phases the touched leaf intervals form one cyclically contiguous run (cells ascend in
+// azimuth, phases ascend), so the tile is a band: step s of the tile is interval (m_start + s) mod (N_L - 1) and
+// holds, for each of its 8 phases, the four moments W_0..W_3 (zeros where the phase does not reach the interval).
+// One step is then the B operand of one m8n8k4 DMMA: D[energy][phase] += C[energy][p] * W[p][phase].
+// ===========================================================================
+constexpr int kTilePhases = 8;
+
+__global__ void __launch_bounds__(kMomThreads) k_azinv_tiles(AzinvArgs a) {
+  const int i = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
+  const long ring = (long)q * a.n_rings + i;
+  int* ih = a.ws_ihdr + ring * kIHdr;
+  const int n_img = ih[0];
+  if (n_img == 0) return;
+  const int A_ = a.n_azi_q ? a.n_azi_q[q] : a.n_azi;
+  const int N_L = a.n_leaves, N_P = a.n_phases, cap = a.tile_cap, NI = N_L - 1;
+  const int n_tiles = (N_P + kTilePhases - 1) / kTilePhases;
+  extern __shared__ double smem[];
+  __shared__ int s_ncell, s_over;
+  double* s_cphi = smem;
+  double* s_carea = s_cphi + a.n_azi;
+  double* s_PH = s_carea + a.n_azi;
+  unsigned char* s_lit = reinterpret_cast<unsigned char*>(s_PH + N_L);
+  unsigned char* s_live = s_lit + N_L;
+  if (tid < 32) { const int n = compact_cells(a, ring * a.n_azi, A_, tid, s_cphi, s_carea); if (tid == 0) { s_ncell = n; s_over = 0; } }
+  const int k = tid, tile = k >> 3, kk = k & 7;
+  const bool active = k < N_P, in_tile = tile < n_tiles;
+  const double phk = active ? a.phases[k] : 0.0;
+  __syncthreads();
+  {
+    double* gc = a.ws_cells + ring * 2 * (long)a.n_azi;
+    const int n = s_ncell;
+    for (int j = tid; j < n; j += kMomThreads) { gc[j] = s_cphi[j]; gc[a.n_azi + j] = s_carea[j]; }
+    if (tid == 0) ih[10] = n;
+  }
+  const int n_cells = s_ncell;
+  for (int I = 0; I < n_img; ++I) {
+    __syncthreads();
+    const double* W = leaf_ptr(a.ws_leaf, ring, a.n_img_max, I, N_L);
+    for (int l = tid; l < N_L; l += kMomThreads) { s_PH[l] = W[l]; s_lit[l] = (W[3 * N_L + l] != 0.0) ? 1 : 0; }
+    __syncthreads();
+    for (int m = tid; m < NI; m += kMomThreads) {       // see k_azinv_moments: dark neighbourhoods carry zero cubics
+      int live = 0;
+      for (int dlt = -2; dlt <= 3; ++dlt) {
+        int l = m + dlt;
+        if (l < 0) l += NI; else if (l > NI) l -= NI;
+        live |= s_lit[l];
+      }
+      s_live[m] = (unsigned char)live;
+    }
+    __syncthreads();
+    // interval of this phase's first cell; the tile starts at the one of its first phase
+    int m_first = 0;
+    if (active && n_cells > 0) {
+      const double ph_first = s_PH[0], ph_last = s_PH[N_L - 1];
+      double xr = phk + s_cphi[0];
+      if (xr > ph_last) { while (xr > ph_last) xr -= kTwoPi; }
+      else if (xr < ph_first) { while (xr < ph_first) xr += kTwoPi; }
+      if (xr >= ph_first && xr <= ph_last) m_first = interval_search(s_PH, N_L, xr);
+    }
+    const int m_start = __shfl_sync(0xffffffffu, m_first, (tid & 31) & ~(kTilePhases - 1));
+    const long slot = ring * a.n_img_max + I;
+    const long tbase = (slot * n_tiles + (in_tile ? tile : 0)) * cap;
+    double* tp = a.ws_tiles + tbase * 32 + kk * 4;
+    int* mp = a.ws_tmeta + tbase * kTilePhases + kk;
+    int next = 0, u_off = 0, prev_m = -1;
+    bool over = false;
+    auto put = [&](int s, double W0, double W1, double W2, double W3, int cells) {
+      double2* d = reinterpret_cast<double2*>(tp + (long)s * 32);
+      d[0] = make_double2(W0, W1); d[1] = make_double2(W2, W3);
+      mp[(long)s * kTilePhases] = cells;
+    };
+    if (active && in_tile)
+      walk_cells(phk, s_PH, N_L, s_cphi, s_carea, n_cells, a.status + q,
+                 [&](int m, double W0, double W1, double W2, double W3, int c0, int c1) {
+                   if (prev_m < 0) u_off = (m < m_start) ? NI : 0;       // this phase has wrapped, the tile's first one not yet
+                   else if (m <= prev_m) u_off += NI;                     // whole-turn wrap of the walk
+                   prev_m = m;
+                   if (!s_live[m] || over) return;
+                   const int st = m + u_off - m_start;
+                   if (st < next || st >= cap) { over = true; return; }
+                   for (; next < st; ++next) put(next, 0.0, 0.0, 0.0, 0.0, 0);
+                   put(st, W0, W1, W2, W3, c0 | (c1 << 16));
+                   next = st + 1;
+                 });
+    int ns = over ? cap + 1 : next;
+#pragma unroll
+    for (int o = 1; o < kTilePhases; o <<= 1) ns = max(ns, __shfl_xor_sync(0xffffffffu, ns, o));
+    if (ns <= cap) ns = min((ns + 3) & ~3, cap);      // whole groups of four steps (zero steps add nothing); cap % 4 == 0
+    if (in_tile) {
+      if (ns > cap) { if (kk == 0) s_over = 1; }
+      else for (; next < ns; ++next) put(next, 0.0, 0.0, 0.0, 0.0, 0);
+      if (kk == 0) a.ws_thdr[slot * n_tiles + tile] = make_int2(m_start, ns > cap ? -1 : ns);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) ih[11] = s_over;       // 1: some tile of this ring overflowed -> the ring goes to the scalar flux kernel
+}
+
+// ===========================================================================
 // flux
 // ===========================================================================
 // shared-memory view of one Num4D atmosphere inside a flux CTA
@@ -875,6 +975,7 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
   if (CORR == 2) cr_els = reinterpret_cast<const int2*>(a.ws_chunk)[((long)a.Q * a.n_rings + ring) * n_chunks + chunk];
   const int elo_hot = (ATM == 2) ? ih[4] : 0, elo_els = (CORR == 2) ? ih[8] : 0;
   if (n_img == 0) return;
+  if (a.ws_tiles && ih[11] == 0) return;        // this ring's tiles fit: k_azinv_flux_mma integrates it
   const double* dh = a.ws_hdr + ring * kDHdr;
   const int N_E = a.n_energies, N_L = NLP ? NLP : a.n_leaves, N_P = NLP ? NLP : a.n_phases;
   const long cell0 = ring * a.n_azi;
@@ -1182,11 +1283,349 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
   }
   // ---- ring/chunk contribution -> flux[q, e, k] -------------------------------------------------
   if (k < N_P) {
-    double* flux_q = a.flux + (long)q * N_E * N_P;
+    if (a.flux_part) {                      // deterministic mode: this CTA's slot of the partial sums
+      double* part = a.flux_part + (ring * (long)N_E) * N_P;
 #pragma unroll
-    for (int g = 0; g < kNEC; ++g)
-      if (g < ne && acc[g] != 0.0) atomicAdd(flux_q + (long)(e0 + g) * N_P + k, acc[g]);
+      for (int g = 0; g < kNEC; ++g)
+        if (g < ne) part[(long)(e0 + g) * N_P + k] = acc[g];
+    } else {
+      double* flux_q = a.flux + (long)q * N_E * N_P;
+#pragma unroll
+      for (int g = 0; g < kNEC; ++g)
+        if (g < ne && acc[g] != 0.0) atomicAdd(flux_q + (long)(e0 + g) * N_P + k, acc[g]);
+    }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same integrator with the accumulation stage on the fp64 tensor cores.
+//
+// Stage 3 of k_azinv_flux spends 4 FMAs per (phase, interval, energy) on 32 bytes of per-thread coefficient
+// reads: the 128 B/clk shared-memory path caps it at a quarter of the DFMA rate.  Here a warp owns tiles of 8
+// output phases; for every step of a tile (k_azinv_tiles) one m8n8k4 DMMA multiplies the interval's cubic pieces
+// for the chunk's 8 energies (A: [energy][p], one conflict-free 256-byte row of shared memory) by the 8 phases'
+// moments (B: [p][phase], one coalesced 256-byte line from L2): 1 byte of shared memory per FMA instead of 8,
+// one issue slot per 256 FMAs instead of 8.  The accumulators are the D fragments (2 doubles per lane and tile),
+// carried across image orders.  Intervals whose cubic may dip below zero for some energy (pyx:593 adds a cell only
+// where the spline is positive) enter the DMMA with that energy's row zeroed and are redone cell by cell by the
+// warp afterwards.  Rings with a tile that does not fit tile_cap steps are left to k_azinv_flux (ih[11]).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kRow = 33;     // doubles per leaf row of the coefficient plane: [8 energies][y, b, c, d] + one flag word
+
+template <int ATM, int CORR, int NLP>
+__global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5)
+k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __grid_constant__ CUtensorMap tm_els) {
+  const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
+  const int i = blockIdx.x / n_chunks;
+  const int chunk = blockIdx.x - i * n_chunks;
+  const int q = blockIdx.y;
+  const int tid = threadIdx.x;
+  const long ring = (long)q * a.n_rings + i;
+  const int* ih = a.ws_ihdr + ring * kIHdr;
+  const int n_img = ih[0];
+  const int n_cells = ih[10];
+  const int scalar_ring = ih[11];
+  int2 cr_hot = make_int2(0, 0), cr_els = make_int2(0, 0);
+  if (ATM == 2) cr_hot = reinterpret_cast<const int2*>(a.ws_chunk)[ring * n_chunks + chunk];
+  if (CORR == 2) cr_els = reinterpret_cast<const int2*>(a.ws_chunk)[((long)a.Q * a.n_rings + ring) * n_chunks + chunk];
+  const int elo_hot = (ATM == 2) ? ih[4] : 0, elo_els = (CORR == 2) ? ih[8] : 0;
+  if (n_img == 0 || scalar_ring) return;
+  const double* dh = a.ws_hdr + ring * kDHdr;
+  const int N_E = a.n_energies, N_L = NLP ? NLP : a.n_leaves, N_P = NLP ? NLP : a.n_phases;
+  const int NI = N_L - 1;
+  const int n_tiles = (N_P + kTilePhases - 1) / kTilePhases;
+  const int e0 = chunk * kNEC;
+  const int ne = min(kNEC, N_E - e0);
+  const int n_img_max = a.n_img_max;
+
+  extern __shared__ __align__(128) double smem[];
+  __shared__ double s_E[kNEC], s_logE[kNEC];
+  __shared__ __align__(8) uint64_t s_mbar;
+  constexpr int kLitWords = 8;
+  __shared__ unsigned s_litmask[kLitWords];
+  __shared__ unsigned long long s_fmask[4];          // bit m: some energy's cubic may dip below zero on interval m
+  const double kT = dh[12], log_kT = dh[13], norm = dh[14];
+  const double kT_c = dh[kCorrD + 12], log_kT_c = dh[kCorrD + 13], norm_c = dh[kCorrD + 14];
+  double* sp = smem;
+  SlabCtx hot, els;
+  double* s_PH = sp; sp += N_L;
+  double* s_aux = sp; sp += N_L;
+  double* s_coef = sp; sp += (long)N_L * kRow;       // [leaf][energy][y b c d], flag bytes in the 33rd double
+  sp = smem + (((sp - smem) + 15) & ~15l);
+  if (ATM == 2) sp = slab_ctx_carve_slab(hot, sp, a.slab_ne_max, a.hot.nmu);
+  if (CORR == 2) sp = slab_ctx_carve_slab(els, sp, a.slab_ne_max, a.els.nmu);
+  if (ATM == 2) sp = slab_ctx_carve(hot, sp, N_L, a.slab_ne_max, a.hot.nmu);
+  if (CORR == 2) sp = slab_ctx_carve(els, sp, N_L, a.slab_ne_max, a.els.nmu);
+
+  if (tid < kNEC) {
+    const int e = tid;
+    s_E[e] = a.energies[e0 + (e < ne ? e : 0)];
+    s_logE[e] = a.log10_energies[e0 + (e < ne ? e : 0)];
+  }
+  if (n_cells == 0) return;
+  if ((ATM == 2 && cr_hot.y + ((cr_hot.x - elo_hot) & 1) > a.slab_ne_max) ||
+      (CORR == 2 && cr_els.y + ((cr_els.x - elo_els) & 1) > a.slab_ne_max)) {
+    if (tid == 0) atomicExch(a.status + q, kUnsupported);
+    return;
+  }
+  if ((ATM == 2 || CORR == 2) && tid == 0) {
+    cuda::ptx::mbarrier_init(&s_mbar, 1);
+    cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+    const unsigned bytes = (unsigned)(((ATM == 2) ? a.hot.nmu : 0) + ((CORR == 2) ? a.els.nmu : 0)) *
+                           (unsigned)a.slab_ne_max * (unsigned)sizeof(double);
+    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared,
+                                         &s_mbar, bytes);
+  }
+  if (ATM == 2) { hot.log_kT = log_kT; slab_ctx_load(hot, a.hot, &tm_hot, ring, elo_hot, cr_hot, a.slab_ne_max, tid, &s_mbar); }
+  if (CORR == 2) { els.log_kT = log_kT_c; slab_ctx_load(els, a.els, &tm_els, ring, elo_els, cr_els, a.slab_ne_max, tid, &s_mbar); }
+  __syncthreads();
+  if (ATM == 2) slab_ctx_finish(hot, a.hot, tid);
+  if (CORR == 2) slab_ctx_finish(els, a.els, tid);
+
+  const int interp_kind = a.phase_interp;
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kFluxThreads / 32, kTilesPerWarp = (kFluxThreads / kTilePhases + kWarps - 1) / kWarps;
+  double acc[kTilesPerWarp][2];            // D fragments: energy lane / 4, phases 2 (lane % 4) + {0, 1} of the tile
+#pragma unroll
+  for (int t = 0; t < kTilesPerWarp; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+
+  for (int I = 0; I < n_img; ++I) {
+    __syncthreads();
+    const double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
+    for (int l = tid; l < N_L; l += kFluxThreads) s_PH[l] = W[l];
+    const bool pre_ok = tid < N_L;
+    const double pre_geom = pre_ok ? W[3 * N_L + tid] : 0.0;
+    const double pre_zst = pre_ok ? W[N_L + tid] : 1.0, pre_abb = pre_ok ? W[2 * N_L + tid] : 0.0;
+    __syncthreads();
+    for (int l = tid; l < NI; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
+    if (tid < 4) s_fmask[tid] = 0ull;
+    if ((ATM == 2 || CORR == 2) && I == 0)
+      while (!cuda::ptx::mbarrier_try_wait_parity(&s_mbar, 0u, 2000u)) {}
+    // ---- (1) leaf profile: thread = leaf ------------------------------------------------------------------
+    for (int lb = 0; lb < N_L; lb += kFluxThreads) {
+      const int l = lb + tid;
+      const double geom = (lb == 0) ? pre_geom : ((l < N_L) ? W[3 * N_L + l] : 0.0);
+      {
+        const unsigned lit = __ballot_sync(0xffffffffu, geom != 0.0);
+        if ((tid & 31) == 0 && (l >> 5) < kLitWords) s_litmask[l >> 5] = lit;
+      }
+      if (l >= N_L) continue;
+      double* row = s_coef + (long)l * kRow;
+      if (geom == 0.0) {
+#pragma unroll
+        for (int e = 0; e < kNEC; ++e) row[e * 4] = 0.0;
+        continue;
+      }
+      const double zst = (lb == 0) ? pre_zst : W[N_L + l];
+      const double abb = (lb == 0) ? pre_abb : W[2 * N_L + l];
+      MuStencil ms_hot, ms_els;
+      if (ATM == 2) ms_hot = slab_ctx_mu_stencil(hot, abb, false);
+      if (CORR == 2) ms_els = slab_ctx_mu_stencil(els, abb);
+      const double Zlin = (CORR == 1 && ATM == 2) ? exp10(zst) : zst;
+      const double Zlog = (CORR == 2 && ATM != 2) ? log10(zst) : zst;
+#pragma unroll
+      for (int e = 0; e < kNEC; ++e) {
+        double I_E;
+        if (ATM == 1) I_E = bb_intensity(s_E[e] / zst, kT);
+        else I_E = slab_ctx_eval(hot, s_logE[e] - zst - log_kT, ms_hot);
+        double corr = 0.0;
+        if (CORR == 1) corr = bb_intensity(s_E[e] / Zlin, kT_c) * norm_c;
+        else if (CORR == 2) corr = slab_ctx_eval(els, s_logE[e] - Zlog - log_kT_c, ms_els) * norm_c;
+        row[e * 4] = (I_E * norm - corr) * geom;
+      }
+    }
+    __syncthreads();
+    // ---- (2) cubic pieces + positivity flags: thread = (energy, block of consecutive intervals) -------------
+    {
+      constexpr int kBlk = kFluxThreads / kNEC;
+      const int e = tid / kBlk, blk = tid - e * kBlk;
+      const int per = (NI + kBlk - 1) / kBlk;
+      const int l0 = blk * per, l1 = min(l0 + per, NI);
+      bool dark = (l0 < l1 && N_L <= 32 * kLitWords);
+      for (int l = l0 - 2; dark && l <= l1 + 2; ++l) {
+        int lw = l;
+        if (lw < 0) lw += NI; else if (lw > NI) lw -= NI;
+        if ((s_litmask[lw >> 5] >> (lw & 31)) & 1u) dark = false;
+      }
+      auto flag_of = [&](int l) -> unsigned char* { return reinterpret_cast<unsigned char*>(s_coef + (long)l * kRow + 32) + e; };
+      if (dark) {
+        for (int l = l0; l < l1; ++l) {
+          double* c = s_coef + (long)l * kRow + e * 4;
+          c[1] = 0.0; c[2] = 0.0; c[3] = 0.0;
+          *flag_of(l) = 0;
+        }
+      } else if (l0 < l1) {
+        const View y{s_coef + e * 4, kRow};
+        auto emit = [&](int l, double b, double c, double d) {
+          double* cf = s_coef + (long)l * kRow + e * 4;
+          const double y0 = cf[0];
+          cf[1] = b; cf[2] = c; cf[3] = d;
+          bool neg = false;
+          if (CORR == 0) {
+            const double h = s_PH[l + 1] - s_PH[l];
+            const double B1 = y0 + b * h * (1.0 / 3.0);
+            const double B2 = y0 + h * ((2.0 / 3.0) * b + c * h * (1.0 / 3.0));
+            const double y1 = y[l + 1];
+            neg = (y0 < 0.0 || y1 < 0.0);
+            if (!neg && (B1 < 0.0 || B2 < 0.0)) {
+              auto below = [&](double t) -> bool {
+                return t > 0.0 && t < h && (y0 + t * (b + t * (c + t * d))) < 0.0;
+              };
+              if (d != 0.0) {
+                const double disc = c * c - 3.0 * b * d;
+                if (disc >= 0.0) {
+                  const double sq = sqrt(disc), i3d = 1.0 / (3.0 * d);
+                  neg = below((-c - sq) * i3d) || below((-c + sq) * i3d);
+                }
+              } else if (c != 0.0) neg = below(-b / (2.0 * c));
+            }
+          }
+          *flag_of(l) = neg ? 1 : 0;
+          if (neg) atomicOr(&s_fmask[l >> 6], 1ull << (l & 63));
+        };
+        if (interp_kind == kSteffen) {
+          for (int l = l0; l < l1; ++l) {
+            double b, c, d;
+            steffen_coeffs(s_PH, y, N_L, l, &b, &c, &d);
+            emit(l, b, c, d);
+          }
+        } else {
+          auto slope = [&](int ii) -> double {
+            if (ii < 0) ii += NI; else if (ii > N_L - 2) ii -= NI;
+            return (y[ii + 1] - y[ii]) * s_aux[ii];
+          };
+          double mm2 = slope(l0 - 2), mm1 = slope(l0 - 1), m0 = slope(l0), mp1 = slope(l0 + 1);
+          double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
+          double alpha = (NE != 0.0) ? fabs(mm1 - mm2) / NE : 0.0;
+          for (int l = l0; l < l1; ++l) {
+            const double mp2 = slope(l + 2);
+            const double NE_next = fabs(mp2 - mp1) + fabs(m0 - mm1);
+            const double alpha1 = (NE_next != 0.0) ? fabs(m0 - mm1) / NE_next : 0.0;
+            double b, c, d;
+            if (NE == 0.0) { b = m0; c = 0.0; d = 0.0; }
+            else {
+              const double tL = (NE_next == 0.0) ? m0 : (1.0 - alpha1) * m0 + alpha1 * mp1;
+              const double ihh = s_aux[l];
+              b = (1.0 - alpha) * mm1 + alpha * m0;
+              c = (3.0 * m0 - 2.0 * b - tL) * ihh;
+              d = (b + tL - 2.0 * m0) * (ihh * ihh);
+            }
+            emit(l, b, c, d);
+            mm2 = mm1; mm1 = m0; m0 = mp1; mp1 = mp2; NE = NE_next; alpha = alpha1;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- (3) tiles x cubic pieces on the tensor cores ------------------------------------------------------
+    // Every interval enters with its true cubic (no masking in the loop); where a cubic may dip below zero the
+    // cells on its negative part are taken out again afterwards: sum_j A_j max(f, 0) = sum_j A_j f - sum_{f<0} A_j f.
+    const long slot = ring * n_img_max + I;
+    const int fe = lane >> 2;                                  // energy row of this lane's A element / D fragment
+    const unsigned long long fm0 = s_fmask[0], fm1 = s_fmask[1], fm2 = s_fmask[2], fm3 = s_fmask[3];
+    const bool any_flag = (fm0 | fm1 | fm2 | fm3) != 0ull;
+    const unsigned row_bytes = kRow * 8u, wrap_bytes = (unsigned)NI * row_bytes;
+    const unsigned coef0 = (unsigned)__cvta_generic_to_shared(s_coef) + (unsigned)lane * 8u;
+#pragma unroll
+    for (int t = 0; t < kTilesPerWarp; ++t) {
+      const int tile = warp + t * kWarps;
+      if (tile >= n_tiles) break;
+      const int2 th = a.ws_thdr[slot * n_tiles + tile];        // (first interval, steps: a multiple of 4)
+      const int ns = th.y;
+      const double* bp = a.ws_tiles + ((slot * n_tiles + tile) * (long)a.tile_cap) * 32 + lane;
+      unsigned off = coef0 + (unsigned)th.x * row_bytes;
+      const unsigned end = coef0 + wrap_bytes;
+      for (int s0 = 0; s0 < ns; s0 += 4) {
+        const double b0 = bp[0], b1 = bp[32], b2 = bp[64], b3 = bp[96];
+        bp += 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double av;
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(av) : "r"(off));
+          const double bv = (j == 0) ? b0 : (j == 1) ? b1 : (j == 2) ? b2 : b3;
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(av), "d"(bv));
+          off += row_bytes;
+          if (off >= end) off -= wrap_bytes;
+        }
+      }
+      if (any_flag) {
+        // flagged (interval, energy) pairs of this tile, cell by cell: lane = (energy pair e, e + 4; phase of the tile)
+        const int kk = lane & 7, eg = lane >> 3;
+        const int k = tile * kTilePhases + kk;
+        const double phk = (k < N_P) ? a.phases[k] : 0.0;
+        const double ph_first = s_PH[0], ph_last = s_PH[N_L - 1];
+        const double* cl = a.ws_cells + ring * 2 * (long)a.n_azi;
+        const int* mt = a.ws_tmeta + ((slot * n_tiles + tile) * (long)a.tile_cap) * kTilePhases + kk;
+        double s_lo = 0.0, s_hi = 0.0;
+        int m = th.x;
+        for (int s = 0; s < ns; ++s) {
+          if (((m < 64 ? fm0 : m < 128 ? fm1 : m < 192 ? fm2 : fm3) >> (m & 63)) & 1ull) {     // N_L <= 256 (launcher)
+            const double* row = s_coef + (long)m * kRow;
+            const unsigned long long fw = *reinterpret_cast<const unsigned long long*>(row + 32);
+            const bool f_lo = (fw >> (8 * eg)) & 1ull, f_hi = (fw >> (8 * (eg + 4))) & 1ull;
+            const int cells = mt[(long)s * kTilePhases];
+            const int c_start = cells & 0xffff, c_end = cells >> 16;
+            if ((f_lo || f_hi) && k < N_P) {
+              const double xm = s_PH[m];
+              const double* cl_ = row + eg * 4;
+              const double* ch_ = row + (eg + 4) * 4;
+              for (int cc = c_start; cc < c_end; ++cc) {
+                double xr = phk + cl[cc];
+                if (xr > ph_last) { while (xr > ph_last) xr -= kTwoPi; }
+                else if (xr < ph_first) { while (xr < ph_first) xr += kTwoPi; }
+                const double d = xr - xm;
+                const double A = cl[a.n_azi + cc];
+                if (f_lo) { const double f = cl_[0] + d * (cl_[1] + d * (cl_[2] + d * cl_[3])); if (f < 0.0) s_lo -= A * f; }
+                if (f_hi) { const double f = ch_[0] + d * (ch_[1] + d * (ch_[2] + d * ch_[3])); if (f < 0.0) s_hi -= A * f; }
+              }
+            }
+          }
+          if (++m == NI) m = 0;
+        }
+        // hand the corrections to the lanes that own D[energy][phase]: energy fe = lane / 4, phases 2 (lane % 4) + {0, 1}
+        const int src = (fe & 3) * 8 + 2 * (lane & 3);
+        const double a0 = __shfl_sync(0xffffffffu, s_lo, src), a1 = __shfl_sync(0xffffffffu, s_lo, src + 1);
+        const double b0 = __shfl_sync(0xffffffffu, s_hi, src), b1 = __shfl_sync(0xffffffffu, s_hi, src + 1);
+        acc[t][0] += (fe < 4) ? a0 : b0;
+        acc[t][1] += (fe < 4) ? a1 : b1;
+      }
+    }
+  }
+  // ---- ring/chunk contribution -> flux[q, e, k] (RED) or its slot of the partial sums (deterministic mode) ----
+  {
+    const int fe = lane >> 2;
+    double* out = a.flux_part ? a.flux_part + (ring * (long)N_E) * N_P : a.flux + (long)q * N_E * N_P;
+#pragma unroll
+    for (int t = 0; t < kTilesPerWarp; ++t) {
+      const int tile = warp + t * kWarps;
+      if (tile >= n_tiles || fe >= ne) continue;
+      const int k0 = tile * kTilePhases + 2 * (lane & 3);
+      double* o = out + (long)(e0 + fe) * N_P + k0;
+      if (a.flux_part) {
+        if (k0 < N_P) o[0] = acc[t][0];
+        if (k0 + 1 < N_P) o[1] = acc[t][1];
+      } else {
+        if (k0 < N_P && acc[t][0] != 0.0) atomicAdd(o, acc[t][0]);
+        if (k0 + 1 < N_P && acc[t][1] != 0.0) atomicAdd(o + 1, acc[t][1]);
+      }
+    }
+  }
+}
+
+// deterministic mode: flux[q, e, k] = sum over the member's lit rings, in ring order, of the partial sums
+__global__ void __launch_bounds__(128) k_azinv_reduce_rings(AzinvArgs a) {
+  const int e = blockIdx.x, q = blockIdx.y, k = threadIdx.x;
+  if (k >= a.n_phases) return;
+  const int R_ = a.n_rings_q ? a.n_rings_q[q] : a.n_rings;
+  double sum = 0.0;
+  for (int r = 0; r < R_; ++r) {
+    const long ring = (long)q * a.n_rings + r;
+    const int* ih = a.ws_ihdr + ring * kIHdr;
+    if (ih[0] == 0 || ih[10] == 0) continue;
+    sum += a.flux_part[(ring * (long)a.n_energies + e) * a.n_phases + k];
+  }
+  a.flux[((long)q * a.n_energies + e) * a.n_phases + k] = sum;
 }
 
 // flux[q, e, k] /= E_e keV   (pyx:610-612)
@@ -1236,6 +1675,14 @@ void azinv_moment_sizes(const AzinvArgs& a, size_t* mom_doubles, size_t* meta_in
   *mom_doubles = slots * a.mom_cap * 4 * a.n_phases;
   *meta_int2 = slots * a.mom_cap * a.n_phases;
   *cnt_ints = slots * a.n_phases;
+}
+
+void azinv_tile_sizes(const AzinvArgs& a, size_t* tile_doubles, size_t* tmeta_ints, size_t* thdr_int2) {
+  const size_t slots = (size_t)a.Q * a.n_rings * a.n_img_max;
+  const size_t n_tiles = (size_t)(a.n_phases + kTilePhases - 1) / kTilePhases;
+  *tile_doubles = slots * n_tiles * a.tile_cap * 32;
+  *tmeta_ints = slots * n_tiles * a.tile_cap * kTilePhases;
+  *thdr_int2 = slots * n_tiles;
 }
 
 void azinv_workspace_sizes(const AzinvArgs& a, size_t* leaf_doubles, size_t* hdr_doubles, size_t* ihdr_ints,
@@ -1306,6 +1753,38 @@ static cudaError_t launch_flux_n(const AzinvArgs& a, dim3 grid, size_t smem, cud
   return cudaGetLastError();
 }
 
+static size_t flux_mma_smem_bytes(const AzinvArgs& a, int atm, int corr) {
+  size_t d = 2ul * a.n_leaves + (size_t)a.n_leaves * kRow;                     // phases, 1/h, coefficient rows
+  d = (d + 15) & ~15ul;
+  if (atm == 2) d += 5ul * a.slab_ne_max + ((a.hot.nmu + 1) & ~1) + (((size_t)a.hot.nmu * a.slab_ne_max + 15) & ~15ul);
+  if (corr == 2) d += 5ul * a.slab_ne_max + ((a.els.nmu + 1) & ~1) + (((size_t)a.els.nmu * a.slab_ne_max + 15) & ~15ul);
+  return d * sizeof(double);
+}
+
+template <int ATM, int CORR, int NLP>
+static cudaError_t launch_flux_mma_n(const AzinvArgs& a, dim3 grid, size_t smem, cudaStream_t stream,
+                                     const CUtensorMap& tm_hot, const CUtensorMap& tm_els) {
+  cudaError_t err = cudaFuncSetAttribute(k_azinv_flux_mma<ATM, CORR, NLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  k_azinv_flux_mma<ATM, CORR, NLP><<<grid, kFluxThreads, smem, stream>>>(a, tm_hot, tm_els);
+  return cudaGetLastError();
+}
+
+// the tensor-core flux kernel (rings whose tiles fit); the scalar kernel launched behind it takes the other rings
+template <int ATM, int CORR>
+static cudaError_t launch_flux_mma(const AzinvArgs& a, dim3 grid, cudaStream_t stream) {
+  CUtensorMap tm_hot, tm_els;
+  memset(&tm_hot, 0, sizeof(tm_hot)); memset(&tm_els, 0, sizeof(tm_els));
+  cudaError_t err;
+  if (ATM == 2 && (err = encode_slab_map(&tm_hot, a.ws_slab, a, a.hot.nmu)) != cudaSuccess) return err;
+  if (CORR == 2 && (err = encode_slab_map(&tm_els, a.ws_slab2, a, a.els.nmu)) != cudaSuccess) return err;
+  const size_t smem = flux_mma_smem_bytes(a, ATM, CORR);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (a.n_leaves == a.n_phases && a.n_leaves == 100) return launch_flux_mma_n<ATM, CORR, 100>(a, grid, smem, stream, tm_hot, tm_els);
+  if (a.n_leaves == a.n_phases && a.n_leaves == 64) return launch_flux_mma_n<ATM, CORR, 64>(a, grid, smem, stream, tm_hot, tm_els);
+  return launch_flux_mma_n<ATM, CORR, 0>(a, grid, smem, stream, tm_hot, tm_els);
+}
+
 template <int ATM, int CORR, int BEAM, int CUBIC>
 static cudaError_t launch_flux_b(const AzinvArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
   CUtensorMap tm_hot, tm_els;
@@ -1360,13 +1839,31 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
     k_azinv_slab_member<<<dim3((a.els.nmu + kSlabMRows - 1) / kSlabMRows, a.Q), kSlabMThreads, msm, stream>>>(a, 1);
   }
   if (!a.ws_cells) return cudaErrorInvalidValue;
-  if (a.ws_mom) {
+  // tensor-core accumulation: plain configurations only (no beaming, not the global C2 spline)
+  if (a.ws_tiles && (a.beam_opt != 0 || a.phase_interp == kCubic || !a.ws_tmeta || !a.ws_thdr || a.tile_cap < 8 ||
+                     (a.tile_cap & 3) || a.n_leaves > 256 || a.n_azi > 0xffff)) {
+    a.ws_tiles = nullptr;
+  }
+  if (a.ws_tiles) a.ws_mom = nullptr;       // rings whose tiles overflow walk their cells inside the scalar kernel
+  if (a.ws_tiles) {
+    const size_t msm = (2ul * a.n_azi + a.n_leaves) * sizeof(double) + 2ul * a.n_leaves;
+    k_azinv_tiles<<<ggrid, kMomThreads, msm, stream>>>(a);
+  } else if (a.ws_mom) {
     if (!a.ws_meta || !a.ws_cnt || a.mom_cap < 1 || a.n_azi > 0xffff) return cudaErrorInvalidValue;
     const size_t msm = (2ul * a.n_azi + a.n_leaves) * sizeof(double) + 2ul * a.n_leaves;
     k_azinv_moments<<<ggrid, kMomThreads, msm, stream>>>(a);
   } else k_azinv_cells<<<ggrid, 32, 0, stream>>>(a);
   if ((err = cudaGetLastError()) != cudaSuccess) return err;
   if (a.ev_flux[0]) cudaEventRecord(a.ev_flux[0], stream);
+  if (a.ws_tiles) {
+    if (atm == 1 && corr == 0) err = launch_flux_mma<1, 0>(a, fgrid, stream);
+    else if (atm == 1 && corr == 1) err = launch_flux_mma<1, 1>(a, fgrid, stream);
+    else if (atm == 1 && corr == 2) err = launch_flux_mma<1, 2>(a, fgrid, stream);
+    else if (atm == 2 && corr == 0) err = launch_flux_mma<2, 0>(a, fgrid, stream);
+    else if (atm == 2 && corr == 1) err = launch_flux_mma<2, 1>(a, fgrid, stream);
+    else err = launch_flux_mma<2, 2>(a, fgrid, stream);
+    if (err != cudaSuccess) return err;
+  }
   if (atm == 1 && corr == 0) err = launch_flux<1, 0>(a, fgrid, fsm, stream);
   else if (atm == 1 && corr == 1) err = launch_flux<1, 1>(a, fgrid, fsm, stream);
   else if (atm == 1 && corr == 2) err = launch_flux<1, 2>(a, fgrid, fsm, stream);
@@ -1377,6 +1874,10 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   if (a.ev_flux[1]) cudaEventRecord(a.ev_flux[1], stream);
   err = cudaGetLastError();
   if (err != cudaSuccess) return err;
+  if (a.flux_part) {
+    k_azinv_reduce_rings<<<dim3(a.n_energies, a.Q), 128, 0, stream>>>(a);
+    if ((err = cudaGetLastError()) != cudaSuccess) return err;
+  }
   if (a.scale_by_energy) {
     const long n = (long)a.Q * a.n_energies * a.n_phases;
     int blocks = (int)((n + 255) / 256);

@@ -60,8 +60,17 @@ struct AzinvArgs {
   double* ws_cells;                  // with ws_mom: [Q][n_rings][2][n_azi] compact (azimuth, area) lists of the radiating cells
   unsigned long long* work;          // nullptr or [4]: H half-leaf visits, V visible leaves,
                                      //   RI (ring,image) pairs reaching the phase stage, K radiating cells over RI
+  // optional (instead of ws_mom): the same interval moments as dense per-(image, 8-phase tile) B operands of the
+  // tensor-core accumulation stage (azinv_tile_sizes): ws_tiles [slot][tile][tile_cap][32] doubles (lane = phase-in-
+  // tile * 4 + moment order), ws_tmeta [slot][tile][tile_cap][8] ints (cell range of each phase in that interval),
+  // ws_thdr [slot][tile] = (first interval, steps or -1 when the tile needs more than tile_cap steps)
+  double* ws_tiles; int* ws_tmeta; int2* ws_thdr; int tile_cap;
+  // optional: deterministic two-stage ring reduction.  Every (ring, energy chunk) CTA stores its sum into
+  // flux_part [Q][n_rings][N_E][N_P] and k_azinv_reduce_rings adds the lit rings in index order (no atomics)
+  double* flux_part;
   cudaEvent_t ev_flux[2];            // host side only: recorded around the flux kernel when non-null (roofline timing)
 };
+void azinv_tile_sizes(const AzinvArgs& a, size_t* tile_doubles, size_t* tmeta_ints, size_t* thdr_int2);
 cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream);
 // a2: cellmesh/integrator.pyx (no azimuthal invariance); same argument block, parameters read per cell.
 // Uses ws_leaf / ws_hdr / ws_ihdr only; slab_ne_max = energy rows a CTA may hold (general_slab_rows)
@@ -173,7 +182,11 @@ int fold_tile_rows();
 struct MarginalArgs {
   int B, n_comp, n_chan, n_phases, n_bins;
   const double* pulses;              // [B][n_comp][n_chan][n_phases]  count rate
-  const double* comp_phases;         // [n_phases] cycles (shared by components)
+  const double* comp_phases;         // [n_phases] cycles shared by the components, or with comp_n_phases
+                                     //   [n_comp][n_phases]: one grid per component (n_phases = the longest,
+                                     //   compute_expected_counts.pyx:66-197 takes component_phases[i] per component)
+  const int* comp_n_phases;          // nullptr, or [n_comp] nodes of each component's grid (1 = time-invariant)
+  const int* comp_allow_negative;    // nullptr (allow_negative applies to all), or [n_comp]
   const double* phase_shifts;        // [B][n_comp]
   const double* data_phases;         // [n_bins + 1]
   const double* counts;              // [n_chan][n_bins]

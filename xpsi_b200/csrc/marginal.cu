@@ -67,14 +67,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
   const int chan = blockIdx.x * kWarpsPerBlock + warp;
   const int b = blockIdx.y;
   const int N_P = a.n_phases, n = a.n_bins;
+  const int n_grids = a.comp_n_phases ? a.n_comp : 1;            // one phase grid per component, or one for all
   extern __shared__ double smem[];
-  double* s_x = smem;                                            // comp phases (shared by warps)
-  double* w_base = smem + N_P + (long)warp * (5 * N_P + 2 * kMaxBins);
+  double* s_xall = smem;                                         // comp phases (shared by warps)
+  double* w_base = smem + (long)n_grids * N_P + (long)warp * (5 * N_P + 2 * kMaxBins);
   double* s_y = w_base;                                          // [N_P]
   double* s_c = s_y + N_P;                                       // [N_P][4]
   double* s_star = s_c + 4 * N_P;                                // [kMaxBins]
   double* s_data = s_star + kMaxBins;                            // [kMaxBins]
-  for (int i = threadIdx.x; i < N_P; i += blockDim.x) s_x[i] = a.comp_phases[i];
+  for (int i = threadIdx.x; i < n_grids * N_P; i += blockDim.x) s_xall[i] = a.comp_phases[i];
   __syncthreads();
   if (chan >= a.n_chan) return;            // whole warps only; no block barrier below
 
@@ -89,18 +90,21 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
   for (int j = 0; j < BPL; ++j) star[j] = 0.0;
   for (int c = 0; c < a.n_comp; ++c) {
     const double* pulse = a.pulses + (((long)b * a.n_comp + c) * a.n_chan + chan) * N_P;
-    if (N_P == 1) {                    // time-invariant component: stored in the first bin, not integrated
+    const int Nc = a.comp_n_phases ? a.comp_n_phases[c] : N_P;   // nodes of this component's phase grid
+    const double* s_x = s_xall + (a.comp_n_phases ? (long)c * N_P : 0);
+    const bool allow_neg = a.comp_allow_negative ? (a.comp_allow_negative[c] != 0) : (a.allow_negative != 0);
+    if (Nc == 1) {                     // time-invariant component: stored in the first bin, not integrated
       if (lane == 0) star[0] = pulse[0];                         // compute_expected_counts.pyx:190-192
       continue;
     }
-    for (int i = lane; i < N_P; i += 32) s_y[i] = pulse[i];
+    for (int i = lane; i < Nc; i += 32) s_y[i] = pulse[i];
     __syncwarp();
     if (a.interp == kCubic) {          // global C2 spline: one lane solves the cyclic system
-      if (lane == 0) cspline_quads(s_x, s_y, N_P, true, s_c, 4);
+      if (lane == 0) cspline_quads(s_x, s_y, Nc, true, s_c, 4);
     } else
-    for (int i = lane; i < N_P - 1; i += 32) {
+    for (int i = lane; i < Nc - 1; i += 32) {
       double bb, cc, dd;
-      interp_coeffs(a.interp, periodic, s_x, s_y, N_P, i, &bb, &cc, &dd);
+      interp_coeffs(a.interp, periodic, s_x, s_y, Nc, i, &bb, &cc, &dd);
       s_c[4 * i] = s_y[i]; s_c[4 * i + 1] = bb; s_c[4 * i + 2] = cc; s_c[4 * i + 3] = dd;
     }
     __syncwarp();
@@ -114,13 +118,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
       if (are_equal(pb - pa, 1.0)) { pa = 0.0; pb = 1.0; }
       else { pa -= floor(pa); pb -= floor(pb); }
       if (pa < pb) {
-        const double v = spline_integ(s_x, s_c, N_P, pa, pb);
-        if (v > 0.0 || a.allow_negative) star[j] += v;
+        const double v = spline_integ(s_x, s_c, Nc, pa, pb);
+        if (v > 0.0 || allow_neg) star[j] += v;
       } else {
-        double v = spline_integ(s_x, s_c, N_P, pa, 1.0);
-        if (v > 0.0 || a.allow_negative) star[j] += v;
-        v = spline_integ(s_x, s_c, N_P, 0.0, pb);
-        if (v > 0.0 || a.allow_negative) star[j] += v;
+        double v = spline_integ(s_x, s_c, Nc, pa, 1.0);
+        if (v > 0.0 || allow_neg) star[j] += v;
+        v = spline_integ(s_x, s_c, Nc, 0.0, pb);
+        if (v > 0.0 || allow_neg) star[j] += v;
       }
     }
     __syncwarp();
@@ -352,7 +356,8 @@ __global__ void k_sum_channels(const double* chan_lnL, const int* chan_status, i
 
 template <int BPL>
 static cudaError_t launch_marginal_bpl(const MarginalArgs& a, cudaStream_t stream) {
-  const size_t smem = ((size_t)a.n_phases + kWarpsPerBlock * (5ul * a.n_phases + 2 * 32 * BPL)) * sizeof(double);
+  const size_t n_grids = a.comp_n_phases ? a.n_comp : 1;
+  const size_t smem = (n_grids * a.n_phases + kWarpsPerBlock * (5ul * a.n_phases + 2 * 32 * BPL)) * sizeof(double);
   dim3 grid((a.n_chan + kWarpsPerBlock - 1) / kWarpsPerBlock, a.B);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   if (smem > 48 * 1024) {

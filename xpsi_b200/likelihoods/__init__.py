@@ -44,29 +44,22 @@ def eval_marginal_likelihood(exposure_time, phases, counts, components, componen
         raise TypeError('Background upper limit cannot be set to 0.')
     if ((support[:, 1] > 0) & (support[:, 1] - support[:, 0] < 0)).any():
         raise TypeError('Background upper limit must be higher than the lower limit.')
-    for c, p in zip(comps, cph):
-        if c.shape != (n_chan, cph[0].shape[0]) or not np.array_equal(p, cph[0]):
-            raise NotImplementedError("xpsi_b200: components must share one phase grid")
-    if isinstance(allow_negative, (bool, np.bool_, int)):
-        allow = int(bool(allow_negative))
-    else:
-        vals = [bool(v) for v in allow_negative]
-        if len(vals) != len(comps):
-            raise ValueError('Number of allow_negative declarations does not match the number of components..')
-        if any(v != vals[0] for v in vals):
-            raise NotImplementedError("xpsi_b200: per-component allow_negative must be uniform")
-        allow = int(vals[0])
+    if counts.shape[1] != phases.shape[0] - 1 or precomp.shape[0] != n_chan or shifts.shape[0] != len(comps):
+        raise ValueError("counts / phases / neg_sum_ln_data_factorial / phase_shifts shapes do not match")
+    arr, parr, nph = _component_arrays(comps, cph, n_chan)
+    allow = _allow_flags(allow_negative, len(comps))
     bg = _lib.as_f8(background, 2) if background is not None else None
+    if bg is not None and bg.shape != counts.shape:
+        raise ValueError("background must have the shape of the data")
     n_bins = phases.shape[0] - 1
-    arr = (_lib.c_double_p * len(comps))(*[_lib.dptr(c) for c in comps])
     lnL = C.c_double(0.0)
     star = np.zeros((n_chan, n_bins), dtype=np.float64)
     mcl = np.zeros(n_chan, dtype=np.float64)
     mcl_s = np.zeros(n_chan, dtype=np.float64)
     rc = _lib.lib.xpsi_b200_eval_marginal_likelihood(
         float(exposure_time), _lib.dptr(phases), n_bins, _lib.dptr(counts), n_chan, arr, len(comps),
-        _lib.dptr(cph[0]), cph[0].shape[0], _lib.dptr(shifts), _lib.dptr(precomp), _lib.dptr(support),
-        float(epsilon), float(sigmas), float(llzero), allow, float(slim),
+        parr, _lib.iptr(nph), _lib.dptr(shifts), _lib.dptr(precomp), _lib.dptr(support),
+        float(epsilon), float(sigmas), float(llzero), _lib.iptr(allow), float(slim),
         _lib.dptr(bg) if bg is not None else None, phase_interpolant_id(),
         C.cast(C.pointer(lnL), _lib.c_double_p), _lib.dptr(star), _lib.dptr(mcl), _lib.dptr(mcl_s))
     if rc in (_lib.ESLIM, _lib.EQUADRATURE):
@@ -77,13 +70,35 @@ def eval_marginal_likelihood(exposure_time, phases, counts, components, componen
     return (lnL.value, star, mcl, mcl_s)
 
 
+def _component_arrays(comps, cph, n_chan):
+    """Pointer tables of the components and of their phase grids (one grid per component, as
+    compute_expected_counts.pyx:66-197 takes them) and the node counts."""
+    if len(comps) != len(cph):
+        raise ValueError("one phase grid per component is required")
+    for c, p in zip(comps, cph):
+        if c.shape != (n_chan, p.shape[0]):
+            raise ValueError("a component of shape %r does not match %d channels x %d phases"
+                             % (c.shape, n_chan, p.shape[0]))
+    arr = (_lib.c_double_p * len(comps))(*[_lib.dptr(c) for c in comps])
+    parr = (_lib.c_double_p * len(cph))(*[_lib.dptr(p) for p in cph])
+    nph = np.array([p.shape[0] for p in cph], dtype=np.int32)
+    return arr, parr, nph
+
+
+def _allow_flags(allow_negative, n_comp):
+    """One flag per component (default_background_marginalisation.pyx:497-508)."""
+    if isinstance(allow_negative, (bool, np.bool_, int)):
+        return np.full(n_comp, int(bool(allow_negative)), dtype=np.int32)
+    vals = [int(bool(v)) for v in allow_negative]
+    if len(vals) != n_comp:
+        raise ValueError('Number of allow_negative declarations does not match the number of components..')
+    return np.array(vals, dtype=np.int32)
+
+
 def _components(components, component_phases, n_chan):
     comps = [_lib.as_f8(c, 2) for c in components]
     cph = [_lib.as_f8(p, 1) for p in component_phases]
-    for c, p in zip(comps, cph):
-        if c.shape != (n_chan, cph[0].shape[0]) or not np.array_equal(p, cph[0]):
-            raise NotImplementedError("xpsi_b200: components must share one phase grid")
-    return comps, cph[0]
+    return comps, cph
 
 
 def poisson_likelihood_given_background(exposure_time, phases, counts, components, component_phases,
@@ -98,13 +113,17 @@ def poisson_likelihood_given_background(exposure_time, phases, counts, component
     shifts = _lib.as_f8(phase_shifts, 1)
     pre = _lib.as_f8(neg_sum_ln_data_factorial, 1) if neg_sum_ln_data_factorial is not None else None
     n_chan, n_bins = counts.shape
-    arr = (_lib.c_double_p * len(comps))(*[_lib.dptr(c) for c in comps])
+    if bg.shape != counts.shape or phases.shape[0] != n_bins + 1 or shifts.shape[0] != len(comps) or \
+            (pre is not None and pre.shape[0] != n_chan):
+        raise ValueError("counts / background / phases / phase_shifts shapes do not match")
+    arr, parr, nph = _component_arrays(comps, cph, n_chan)
+    allow = _allow_flags(allow_negative, len(comps))
     lnL = C.c_double(0.0)
     expec = np.zeros((n_chan, n_bins), dtype=np.float64)
     rc = _lib.lib.xpsi_b200_poisson_likelihood_given_background(
         float(exposure_time), _lib.dptr(phases), n_bins, _lib.dptr(counts), n_chan, arr, len(comps),
-        _lib.dptr(cph), cph.shape[0], _lib.dptr(shifts), _lib.dptr(bg), _lib.dptr(pre) if pre is not None else None,
-        int(bool(allow_negative)), phase_interpolant_id(), C.cast(C.pointer(lnL), _lib.c_double_p), _lib.dptr(expec))
+        parr, _lib.iptr(nph), _lib.dptr(shifts), _lib.dptr(bg), _lib.dptr(pre) if pre is not None else None,
+        _lib.iptr(allow), phase_interpolant_id(), C.cast(C.pointer(lnL), _lib.c_double_p), _lib.dptr(expec))
     if rc == _lib.EQUADRATURE:
         return (-1.0e90 * (0.1 + 0.9 * np.random.rand()), expec)
     if rc == _lib.EUNSUPPORTED:
@@ -121,11 +140,14 @@ def expected_counts(exposure_time, phases, components, component_phases, phase_s
     bg = _lib.as_f8(background, 2)
     comps, cph = _components(components, component_phases, bg.shape[0])
     shifts = _lib.as_f8(phase_shifts, 1)
-    arr = (_lib.c_double_p * len(comps))(*[_lib.dptr(c) for c in comps])
+    if bg.shape[1] != phases.shape[0] - 1 or shifts.shape[0] != len(comps):
+        raise ValueError("background / phases / phase_shifts shapes do not match")
+    arr, parr, nph = _component_arrays(comps, cph, bg.shape[0])
+    allow = _allow_flags(allow_negative, len(comps))
     expec = np.zeros(bg.shape, dtype=np.float64)
     rc = _lib.lib.xpsi_b200_poisson_likelihood_given_background(
         float(exposure_time), _lib.dptr(phases), phases.shape[0] - 1, None, bg.shape[0], arr, len(comps),
-        _lib.dptr(cph), cph.shape[0], _lib.dptr(shifts), _lib.dptr(bg), None, int(bool(allow_negative)),
+        parr, _lib.iptr(nph), _lib.dptr(shifts), _lib.dptr(bg), None, _lib.iptr(allow),
         phase_interpolant_id(), None, _lib.dptr(expec))
     _lib.check(rc)
     return expec

@@ -257,6 +257,11 @@ class BatchedLikelihood:
         except Exception:
             pass
 
+    def set_deterministic(self, on=True):
+        """Ring sums by an ordered two-stage reduction instead of fp64 atomics: lnL becomes bitwise reproducible
+        (run to run, and whatever the position of a parameter vector in its batch)."""
+        _lib.check(_lib.lib.xpsi_b200_pipeline_set_deterministic(self.handle, int(bool(on))))
+
     def set_extras(self, elsewhere=None, attenuation=None, beam_opt=0):
         """Optional model components (set once).
 
