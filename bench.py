@@ -122,7 +122,9 @@ def flops_per_eval(work, n_evals, shape, n_regions, n_quad=65, n_newton=3):
 
 def ncu_artefact():
     """Per-kernel ncu numbers committed under profiles/ (regenerated by profiles/make_profiles.sh)."""
-    path = os.path.join(ROOT, "profiles", "r02_kernels.json")
+    import glob
+    found = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_kernels.json")))
+    path = found[-1] if found else os.path.join(ROOT, "profiles", "r02_kernels.json")
     try:
         with open(path) as f:
             return json.load(f), os.path.relpath(path, ROOT)
@@ -429,10 +431,11 @@ def main_ours(args):
     def tf(flop_per_eval, ms):                       # algorithmic TFLOP/s of a stage over one block
         return flop_per_eval * B / (ms * 1e-3) / 1e12 if ms > 0 else None
     art, art_path = ncu_artefact()
-    flux_art = (art or {}).get("kernels", {}).get("k_azinv_flux")
+    # the flux stage = k_azinv_flux_mma (tensor-core accumulation) + k_azinv_flux (rings whose tiles overflow)
+    flux_arts = [(art or {}).get("kernels", {}).get(n) for n in ("k_azinv_flux_mma", "k_azinv_flux")]
     traffic = None
-    if flux_art and flux_art.get("dram_bytes") and art.get("batch"):
-        traffic = flux_art["dram_bytes"] * B / art["batch"]
+    if flux_arts[0] and flux_arts[0].get("dram_bytes") and art.get("batch"):
+        traffic = sum(f_["dram_bytes"] for f_ in flux_arts if f_ and f_.get("dram_bytes")) * B / art["batch"]
     a_flux = tf(fl["flux_kernel"], stage["flux_kernel"])
     per_kernel = {
         "k_azinv_flux": {"ms": stage["flux_kernel"], "tflops": a_flux, "frac": a_flux / pk},
@@ -447,9 +450,10 @@ def main_ours(args):
     if art:
         for name, kv in art.get("kernels", {}).items():
             for key, val in per_kernel.items():
-                if key.startswith(name):
-                    val["ncu"] = {k_: kv.get(k_) for k_ in ("fp64_pipe_active_pct", "issue_active_pct", "dram_bytes",
-                                                            "registers", "duration_ms", "l2_hit_pct") if k_ in kv}
+                if name and (key == name or (key == "k_azinv_flux" and name == "k_azinv_flux_mma")):
+                    val["ncu"] = {k_: kv.get(k_) for k_ in ("fp64_pipe_active_pct", "dmma_pipe_active_pct",
+                                                            "issue_active_pct", "dram_bytes", "registers",
+                                                            "duration_ms", "l2_hit_pct") if k_ in kv}
     whole = fl["total"] * value / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -468,7 +472,7 @@ def main_ours(args):
                   "blocks_per_rank": blocks, "sharding": "round-robin rows (xpsi_b200.sampling.shard_indices)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "fp64", "kernel": "k_azinv_flux<2,0,0,0,100>", "achieved": a_flux, "peak": pk,
+        "roofline": {"bound": "fp64", "kernel": "k_azinv_flux_mma<2,0,100> (+ k_azinv_flux<2,0,0,0,100> for overflow rings)", "achieved": a_flux, "peak": pk,
                      "unit": "TFLOP/s", "frac": a_flux / pk, "traffic": traffic,
                      "traffic_source": ("%s (ncu --set full at batch %d, scaled to batch %d)" % (art_path, art["batch"], B))
                      if traffic else None,

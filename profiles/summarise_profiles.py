@@ -26,7 +26,7 @@ KEYS = {
     "launch__occupancy_limit_shared_mem": "occ_limit_smem",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_active_pct",
-    "smsp__issue_active.avg.pct": "issue_active_pct",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
     "dram__bytes_read.sum": "dram_read",
     "dram__bytes_write.sum": "dram_write",
     "lts__t_sector_hit_rate.pct": "l2_hit_pct",
@@ -34,6 +34,12 @@ KEYS = {
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts",
     "smsp__inst_executed.sum": "warp_instructions",
     "sm__inst_executed_pipe_tensor.sum": "tensor_instructions",
+    "sm__inst_executed_pipe_fp64.sum": "fp64_pipe_instructions",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active": "fmaheavy_pipe_active_pct",
+    "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active": "shared_pipe_active_pct",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active": "dmma_pipe_active_pct",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "lsu_pipe_pct",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active": "alu_pipe_pct",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio": "stall_short_scoreboard",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard",
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio": "stall_wait",
@@ -44,6 +50,13 @@ KEYS = {
 }
 UNIT_SCALE = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "nsecond": 1e-6, "s": 1e3, "second": 1e3,
               "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def clean(full):
+    """'void xb::k_azinv_flux_mma<(int)2, ...>(xb::AzinvArgs, ...)' -> 'k_azinv_flux_mma'"""
+    name = re.sub(r"<.*", "", full).split("(")[0].strip()
+    name = name.split()[-1] if name else name
+    return name.split("::")[-1]
 
 
 def num(v):
@@ -60,8 +73,8 @@ def main():
     col = {h: i for i, h in enumerate(hdr)}
     kernels = {}
     for r in rows[2:]:
-        name = re.sub(r"<.*", "", r[col["Kernel Name"]]).split("(")[0].strip()
         full = r[col["Kernel Name"]]
+        name = clean(full)
         k = {"instantiation": full}
         for h, key in KEYS.items():
             if h not in col:
@@ -89,7 +102,7 @@ def main():
         for r in lr[1:]:
             if len(r) <= lh.get("Metric Value", 0) or r[lh["Metric Name"]] != "gpu__time_duration.sum":
                 continue
-            name = re.sub(r"<.*", "", r[lh["Kernel Name"]]).split("(")[0].strip()
+            name = clean(r[lh["Kernel Name"]])
             v = num(r[lh["Metric Value"]]) * UNIT_SCALE.get(r[lh["Metric Unit"]], 1.0)
             step[name] = step.get(name, 0.0) + v
         tot = sum(step.values())
@@ -104,9 +117,9 @@ def main():
     with open(os.path.join(outdir, tag + "_kernels.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     for name, k in sorted(kernels.items(), key=lambda kv: -kv[1].get("step_share", 0)):
-        print("%-26s %6.2f%% of step  %8.3f ms  fp64 %5.1f%%  issue %5.1f%%  regs %3d  dram %8.1f MB"
+        print("%-26s %6.2f%% of step  %8.3f ms  fp64 %5.1f%%  dmma %5.1f%%  issue %5.1f%%  regs %3d  dram %8.1f MB"
               % (name, 100 * k.get("step_share", 0), k.get("duration_ms", 0), k.get("fp64_pipe_active_pct", 0),
-                 k.get("issue_active_pct", 0), int(k.get("registers", 0)), k.get("dram_bytes", 0) / 1e6))
+                 k.get("dmma_pipe_active_pct", 0), k.get("issue_active_pct", 0), int(k.get("registers", 0)), k.get("dram_bytes", 0) / 1e6))
 
 
 if __name__ == "__main__":
