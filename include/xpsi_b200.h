@@ -207,7 +207,12 @@ typedef struct {
   int n_rays, n_params;
   int n_energies; const double* energies;        /* keV */
   int n_leaves; const double* leaves;            /* rad */
-  int n_phases; const double* phases;            /* rad; cycles = phases / 2 pi          */
+  int n_phases; const double* phases;            /* rad; cycles = phases / 2 pi.  n_phases == 1: the star is an
+                                                  * Everywhere(time_invariant=True) surface (xpsi/Everywhere.py:
+                                                  * 577-601, Photosphere.py:560-566) -- no hot regions (n_members =
+                                                  * n_components = 1, mesh fields ignored); the closed-surface
+                                                  * settings come with set_extras (the "elsewhere" fields) and its
+                                                  * temperature with else_temperature                             */
   int hot_atm_ext; const xpsi_b200_atmosphere* hot_atmosphere;
   int image_order_limit;
   int phase_interpolant;
@@ -264,6 +269,10 @@ typedef struct {
    * that follow (log T, log g) in srcCellParams, e.g. the beaming parameters (abb, bbb, cbb, dbb, nimu) of
    * examples_modeling_tutorial/modules/CustomHotRegion_Beaming.py:149-178                            */
   const double* extra_params;                     /* [B*M][n_params-2] */
+  /* optional (NULL: num_cells / min / max above apply to every member): the cell budget of the hot region each
+   * member belongs to, [M][3] = (sqrt_num_cells^2, min_sqrt_num_cells, max_sqrt_num_cells) -- hot regions of one
+   * model may be constructed with different resolutions (xpsi/HotRegion.py:122-140)                       */
+  const int* member_cells;
 } xpsi_b200_spot_batch;
 
 /* ---- optional model components of the batched pipeline ---------------------------------------------
@@ -308,6 +317,35 @@ typedef struct {
 int xpsi_b200_pipeline_upload_extras(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch_extras* host);
 /* Elsewhere spectrum [B][n_energies] of the last evaluation (photons/cm^2/s/keV before 1/d^2) */
 int xpsi_b200_pipeline_fetch_elsewhere(xpsi_b200_pipeline* p, int B, double* spectrum);
+
+/* ---- several signals per likelihood (xpsi/Likelihood.py:346-420,494-500; docs/source/Instrument_synergy.ipynb) ----
+ * The reference integrates the photosphere once at the energies the signals share (Likelihood.py:102-107,316-318)
+ * and registers that signal with every Signal object: energy integration onto the instrument's input intervals,
+ * the signal's interstellar attenuation (Signal.py:431-439), the response fold (Instrument.py:146-197) and the
+ * signal's own likelihood call; the joint log-likelihood is the sum.  add_signal registers one more
+ * (instrument, data) pair behind the same integrator stage and returns its index (the signal of the pipeline
+ * configuration is 0), or a negative error code.  A parameter vector whose evaluation fails in any signal keeps
+ * the first non-zero status.  Arrays are copied.                                                              */
+typedef struct {
+  int n_in; const double* energy_edges;          /* [n_in+1] keV                                     */
+  int n_chan; const double* response;            /* [n_chan][n_in]                                   */
+  int n_bins; const double* data_phases;         /* [n_bins+1] cycles                                */
+  const double* counts;                          /* [n_chan][n_bins]                                 */
+  const double* support;                         /* [n_chan][2]                                      */
+  double exposure_time, epsilon, sigmas, llzero, slim;
+  int allow_negative;
+  const double* attenuation;                     /* NULL or [n_in]: attenuation[j] ** att_power[b]   */
+} xpsi_b200_signal_config;
+int xpsi_b200_pipeline_add_signal(xpsi_b200_pipeline* p, const xpsi_b200_signal_config* signal);
+int xpsi_b200_pipeline_n_signals(xpsi_b200_pipeline* p);
+/* per-signal phase shifts [B][n_signals] in cycles, added to the hot regions' shifts for that signal
+ * (Signal.shifts, xpsi/Signal.py:581-583); NULL switches them off again */
+int xpsi_b200_pipeline_upload_signal_shifts(xpsi_b200_pipeline* p, int B, const double* shifts);
+int xpsi_b200_pipeline_sweep_upload_signal_shifts(xpsi_b200_pipeline* p, long long N, const double* shifts);
+/* folded signal [B][n_components][n_chan][n_phases], expected counts [B][n_chan][n_bins] and log-likelihood [B]
+ * of one signal of the last evaluation (any pointer may be NULL) */
+int xpsi_b200_pipeline_fetch_signal(xpsi_b200_pipeline* p, int signal, int B, double* folded, double* expected,
+                                    double* lnL);
 
 /* embed B parameter vectors on the device (inputs of the next eval_resident) */
 int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200_spot_batch* host);

@@ -95,6 +95,7 @@ class SpotBatch(C.Structure):
         ("num_cells", C.c_int), ("min_sqrt_num_cells", C.c_int), ("max_sqrt_num_cells", C.c_int),
         ("hole_radius", c_double_p), ("hole_colatitude", c_double_p), ("hole_azimuth", c_double_p),
         ("partner", c_int_p), ("is_cede", c_int_p), ("extra_params", c_double_p),
+        ("member_cells", c_int_p),
     ]
 
 
@@ -111,6 +112,18 @@ class BatchExtras(C.Structure):
         "att_power", "else_temperature", "else_cellArea", "else_radial", "else_r_s_over_r", "else_theta",
         "else_phi", "else_srcParams", "else_deflection", "else_cos_alpha", "else_maxDeflection", "else_cos_gamma",
         "correction_srcParams")]
+
+
+class SignalConfig(C.Structure):
+    _fields_ = [
+        ("n_in", C.c_int), ("energy_edges", c_double_p),
+        ("n_chan", C.c_int), ("response", c_double_p),
+        ("n_bins", C.c_int), ("data_phases", c_double_p),
+        ("counts", c_double_p), ("support", c_double_p),
+        ("exposure_time", C.c_double), ("epsilon", C.c_double), ("sigmas", C.c_double),
+        ("llzero", C.c_double), ("slim", C.c_double), ("allow_negative", C.c_int),
+        ("attenuation", c_double_p),
+    ]
 
 
 def _proto(name, restype, argtypes):
@@ -185,6 +198,11 @@ _proto("xpsi_b200_pipeline_sweep_upload", C.c_int, [C.c_void_p, C.c_longlong, C.
 _proto("xpsi_b200_pipeline_sweep_run", C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong])
 _proto("xpsi_b200_pipeline_sweep_download", C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, c_double_p, c_int_p])
 _proto("xpsi_b200_pipeline_sweep_results", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)])
+_proto("xpsi_b200_pipeline_add_signal", C.c_int, [C.c_void_p, C.POINTER(SignalConfig)])
+_proto("xpsi_b200_pipeline_n_signals", C.c_int, [C.c_void_p])
+_proto("xpsi_b200_pipeline_upload_signal_shifts", C.c_int, [C.c_void_p, C.c_int, c_double_p])
+_proto("xpsi_b200_pipeline_sweep_upload_signal_shifts", C.c_int, [C.c_void_p, C.c_longlong, c_double_p])
+_proto("xpsi_b200_pipeline_fetch_signal", C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p])
 
 EXPORTED = [
     "xpsi_b200_last_error", "xpsi_b200_device_count", "xpsi_b200_set_device", "xpsi_b200_counters",
@@ -201,6 +219,8 @@ EXPORTED = [
     "xpsi_b200_pipeline_eval_spots_resident", "xpsi_b200_poisson_likelihood_given_background",
     "xpsi_b200_pipeline_sweep_upload", "xpsi_b200_pipeline_sweep_run", "xpsi_b200_pipeline_sweep_download",
     "xpsi_b200_pipeline_sweep_results", "xpsi_b200_pipeline_set_deterministic",
+    "xpsi_b200_pipeline_add_signal", "xpsi_b200_pipeline_n_signals", "xpsi_b200_pipeline_upload_signal_shifts",
+    "xpsi_b200_pipeline_sweep_upload_signal_shifts", "xpsi_b200_pipeline_fetch_signal",
 ]
 
 

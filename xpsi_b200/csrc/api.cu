@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -687,7 +688,7 @@ struct xpsi_b200_pipeline {
   int deterministic = 0;             // ring sums by a two-stage ordered reduction instead of fp64 atomics
   // embed inputs / scratch
   Dev<double> e_Req, e_rs, e_eps, e_zeta, e_colat, e_rad, e_temp, e_phish, e_maxAlpha, e_hrad, e_hcolat, e_hazi, e_extra;
-  Dev<int> e_partner, e_iscede;
+  Dev<int> e_partner, e_iscede, e_member_cells;
   int count_work = 0;
   int embed_status_valid = 0;        // status[] already carries embed failures for this batch
   xb::EmbedArgs embed_args;          // last uploaded spot batch (device pointers), for resident re-runs
@@ -705,13 +706,26 @@ struct xpsi_b200_pipeline {
   Dev<double> x_temp, x_area, x_radial, x_rsr, x_theta, x_phi, x_params, x_defl, x_calpha, x_maxd, x_cgamma,
       x_maxAlpha, x_grav, x_flux;
   Dev<int> x_nrings, x_status;
+  // further signals (instruments / data sets) registered from the same photosphere signal
+  // (xpsi/Likelihood.py:346-420 loops over the signals of a photosphere): xpsi_b200_pipeline_add_signal
+  struct SignalPart {
+    int n_in = 0, n_chan = 0, n_bins = 0, allow_negative = 0;
+    double exposure_time = 0, epsilon = 0, sigmas = 0, llzero = 0, slim = 0;
+    Dev<double> log10_edges, response, data_phases, counts, support, precomp, att_base;
+    Dev<int> k_range; Dev<int2> ei_span;
+    Dev<double> xin, folded, chan_lnL, expected, lnL; Dev<int> chan_status;
+  };
+  std::vector<std::unique_ptr<SignalPart>> more;
+  Dev<double> sig_shift, sig_shifts_s;   // [B][n_signals] instrument phase shifts (xpsi/Signal.py:581-583), scratch [B][C]
+  int sig_shift_valid = 0;
+  int tinv_only = 0;                  // the star is an Everywhere(time_invariant=True) surface: one phase column
   // sweep store: N parameter vectors uploaded once, evaluated block by block (xpsi_b200_pipeline_sweep_*)
   struct SpotStore {
     size_t N = 0;
     Dev<double> omega, incl, d_sq, shifts, Req, rs, eps, zeta, colat, rad, temp, phish, hrad, hcolat, hazi, extra,
-        att_power, else_temp, lnL;
+        att_power, else_temp, lnL, sig_shift;
     Dev<int> status;
-    int has_hole = 0, has_partner = 0, has_extra = 0, has_att = 0, has_else = 0;
+    int has_hole = 0, has_partner = 0, has_extra = 0, has_att = 0, has_else = 0, has_sig_shift = 0, has_member_cells = 0;
     double mode_frequency = 0.0;
     int num_cells = 0, min_sqrt = 0, max_sqrt = 0;
   } store;
@@ -747,6 +761,18 @@ __global__ void k_add_spectrum(const double* spectrum, const double* energies, i
   }
 }
 
+// shifts of signal s = hot-region shifts + the signal's own phase shift (xpsi/Signal.py:581-583)
+__global__ void k_signal_shifts(const double* shifts, const double* sig_shift, int B, int C, int S, int s, double* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < B * C) out[t] = shifts[t] + sig_shift[(t / C) * S + s];
+}
+
+// joint log-likelihood: sum over the signals (xpsi/Likelihood.py:494-500)
+__global__ void k_add_lnL(const double* part, int B, double* lnL) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) lnL[b] += part[b];
+}
+
 __global__ void k_merge_status(const int* src, int B, int* dst) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B && dst[b] == 0 && src[b] != 0) dst[b] = src[b];
@@ -773,9 +799,48 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   const int M = c.n_members, C = c.n_components, Q = B * M;
   const size_t nflux = (size_t)Q * c.n_energies * c.n_phases;
   CK(cudaEventRecord(p->ev[0], g_stream));
-  k_expand_scalars<<<(Q + 127) / 128, 128, 0, g_stream>>>(p->omega.p, p->inclination.p, B, M, p->omega_q.p, p->incl_q.p);
   CK(cudaMemsetAsync(p->flux.p, 0, nflux * sizeof(double), g_stream));
   CK(cudaMemsetAsync(p->status_q.p, 0, Q * sizeof(int), g_stream));
+  // time-invariant spectrum of the closed surface mesh: Elsewhere (xpsi/Elsewhere.py:393-442) or, for a
+  // pipeline created with one phase column, Everywhere(time_invariant=True) (xpsi/Everywhere.py:577-601)
+  auto run_closed_surface = [&]() -> int {
+    if (!p->else_arrays_valid || (!p->tinv_only && !p->corr_valid))
+      return fail(XPSI_B200_EINVAL, "the closed surface (elsewhere / everywhere) is enabled but its per-batch inputs were not provided");
+    xb::TinvArgs t;
+    memset(&t, 0, sizeof(t));
+    t.Q = B; t.sqrt_numPix = p->ex.else_sqrt_num_cells; t.n_rays = p->ex.else_num_rays;
+    t.n_energies = c.n_energies; t.n_params = 2;
+    t.omega = p->omega.p; t.inclination = p->inclination.p; t.cellArea = p->x_area.p;
+    t.radial = p->x_radial.p; t.r_s_over_r = p->x_rsr.p; t.theta = p->x_theta.p; t.phi = p->x_phi.p;
+    t.srcParams = p->x_params.p; t.deflection = p->x_defl.p; t.cos_alpha = p->x_calpha.p;
+    t.maxDeflection = p->x_maxd.p; t.cos_gamma = p->x_cgamma.p; t.energies = p->energies.p;
+    t.atm_ext = p->ex.else_atm_ext;
+    if (t.atm_ext == XPSI_B200_ATM_NUM4D) { t.atm = p->ex.elsewhere_atmosphere->view; t.slab_rows = p->else_slab_rows; }
+    t.image_order_limit = p->ex.else_image_order_limit > 0 ? p->ex.else_image_order_limit : 0;
+    t.flux = p->x_flux.p; t.status = p->x_status.p;
+    CK(cudaMemsetAsync(p->x_flux.p, 0, (size_t)B * c.n_energies * sizeof(double), g_stream));
+    CK(cudaMemsetAsync(p->x_status.p, 0, B * sizeof(int), g_stream));
+    cudaError_t et = xb::launch_integrate_tinv(t, g_stream);
+    if (et != cudaSuccess) return cuda_fail(et, "launch_integrate_tinv");
+    g_launches += 2;
+    return 0;
+  };
+  auto add_spectrum = [&]() {
+    int blocks = (int)(((long)B * c.n_energies * c.n_phases + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_add_spectrum<<<blocks, 256, 0, g_stream>>>(p->x_flux.p, p->energies.p, B, M, c.n_energies, c.n_phases, p->flux.p);
+    g_launches += 1;
+  };
+  cudaError_t e = cudaSuccess;
+  if (p->tinv_only) {
+    // Photosphere.py:560-566: the star's signal is the Everywhere spectrum, one phase column
+    if (!p->ex.elsewhere) return fail(XPSI_B200_EINVAL, "a time-invariant pipeline needs the closed-surface settings (set_extras)");
+    int rc = run_closed_surface();
+    if (rc) return rc;
+    add_spectrum();
+    CK(cudaEventRecord(p->ev_flux[0], g_stream)); CK(cudaEventRecord(p->ev_flux[1], g_stream));
+  } else {
+  k_expand_scalars<<<(Q + 127) / 128, 128, 0, g_stream>>>(p->omega.p, p->inclination.p, B, M, p->omega_q.p, p->incl_q.p);
   xb::AzinvArgs a;
   memset(&a, 0, sizeof(a));
   a.Q = Q; a.n_rings = c.max_rings; a.n_azi = c.max_azi; a.n_rays = c.n_rays; a.n_energies = c.n_energies;
@@ -800,25 +865,8 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   a.beam_opt = p->ex.beam_opt;
   if (p->ex.elsewhere) {
     // ---- Elsewhere: time-invariant spectrum of the closed mesh, then the correction in the hot members ----
-    if (!p->else_arrays_valid || !p->corr_valid)
-      return fail(XPSI_B200_EINVAL, "elsewhere is enabled but its per-batch inputs were not provided");
-    xb::TinvArgs t;
-    memset(&t, 0, sizeof(t));
-    t.Q = B; t.sqrt_numPix = p->ex.else_sqrt_num_cells; t.n_rays = p->ex.else_num_rays;
-    t.n_energies = c.n_energies; t.n_params = 2;
-    t.omega = p->omega.p; t.inclination = p->inclination.p; t.cellArea = p->x_area.p;
-    t.radial = p->x_radial.p; t.r_s_over_r = p->x_rsr.p; t.theta = p->x_theta.p; t.phi = p->x_phi.p;
-    t.srcParams = p->x_params.p; t.deflection = p->x_defl.p; t.cos_alpha = p->x_calpha.p;
-    t.maxDeflection = p->x_maxd.p; t.cos_gamma = p->x_cgamma.p; t.energies = p->energies.p;
-    t.atm_ext = p->ex.else_atm_ext;
-    if (t.atm_ext == XPSI_B200_ATM_NUM4D) { t.atm = p->ex.elsewhere_atmosphere->view; t.slab_rows = p->else_slab_rows; }
-    t.image_order_limit = p->ex.else_image_order_limit > 0 ? p->ex.else_image_order_limit : 0;
-    t.flux = p->x_flux.p; t.status = p->x_status.p;
-    CK(cudaMemsetAsync(p->x_flux.p, 0, (size_t)B * c.n_energies * sizeof(double), g_stream));
-    CK(cudaMemsetAsync(p->x_status.p, 0, B * sizeof(int), g_stream));
-    cudaError_t et = xb::launch_integrate_tinv(t, g_stream);
-    if (et != cudaSuccess) return cuda_fail(et, "launch_integrate_tinv");
-    g_launches += 2;
+    int rc = run_closed_surface();
+    if (rc) return rc;
     a.corrParams = p->corr.p; a.else_atm_ext = p->ex.else_atm_ext;
     if (a.else_atm_ext == XPSI_B200_ATM_NUM4D) {
       a.els = p->ex.elsewhere_atmosphere->view; a.ws_slab2 = p->ws_slab2.p;
@@ -833,53 +881,79 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   a.flux_part = p->deterministic ? p->flux_part.p : nullptr;
   a.work = p->count_work ? p->work.p : nullptr;       // accumulates over evaluations; reset by work_counters()
   a.ev_flux[0] = p->ev_flux[0]; a.ev_flux[1] = p->ev_flux[1];
-  cudaError_t e = xb::launch_integrate_azinv(a, g_stream);
+  e = xb::launch_integrate_azinv(a, g_stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_integrate_azinv");
   if (p->ex.elsewhere) {
-    int blocks = (int)(((long)B * c.n_energies * c.n_phases + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    k_add_spectrum<<<blocks, 256, 0, g_stream>>>(p->x_flux.p, p->energies.p, B, M, c.n_energies, c.n_phases, p->flux.p);
-    g_launches += 1 + (p->ex.else_atm_ext == XPSI_B200_ATM_NUM4D ? 2 : 0);
+    add_spectrum();
+    g_launches += (p->ex.else_atm_ext == XPSI_B200_ATM_NUM4D ? 2 : 0);
+  }
   }
   CK(cudaEventRecord(p->ev[1], g_stream));
 
-  xb::EnergyIntegArgs ei;
-  memset(&ei, 0, sizeof(ei));
-  ei.Q = Q; ei.n_energies = c.n_energies; ei.n_phases = c.n_phases; ei.n_in = c.n_in;
-  ei.signal = p->flux.p; ei.raw_energies = p->energies.p; ei.div_b = p->d_sq.p; ei.q_per_b = M;
-  ei.log10_energies = p->log10E.p; ei.log10_edges = p->log10_edges.p; ei.interp = c.phase_interpolant;
-  ei.span = p->ei_span.p;
-  ei.col_of_q = p->col_of_q.p; ei.accumulate = (M > C) ? 1 : 0; ei.out = p->xin.p;
-  if (p->att_base.p) { ei.attenuation = p->att_base.p; ei.att_power = p->att_power_valid ? p->att_power.p : nullptr; }
-  if (ei.accumulate)
-    CK(cudaMemsetAsync(p->xin.p, 0, (size_t)B * C * c.n_phases * c.n_in * sizeof(double), g_stream));
-  e = xb::launch_energy_integrator(ei, g_stream);
-  if (e != cudaSuccess) return cuda_fail(e, "launch_energy_integrator");
-  CK(cudaEventRecord(p->ev[2], g_stream));
-
-  xb::FoldArgs f;
-  f.n_cols = B * C; f.n_phases = c.n_phases; f.n_in = c.n_in; f.n_chan = c.n_chan;
-  f.matrix = p->response.p; f.ld_matrix = c.n_in; f.in0 = 0; f.x = p->xin.p; f.out = p->folded.p;
-  f.k_range = p->k_range.p;
-  e = xb::launch_fold(f, g_stream);
-  if (e != cudaSuccess) return cuda_fail(e, "launch_fold");
-  CK(cudaEventRecord(p->ev[3], g_stream));
-
+  // ---- per signal: energy integration onto the instrument's input intervals (+ interstellar attenuation),
+  // response fold, marginal likelihood.  Signal 0 is the one of the pipeline configuration; the others were
+  // registered with xpsi_b200_pipeline_add_signal and read the same photosphere signal (p->flux).
+  const int P_sig = c.n_phases;
+  const int S = 1 + (int)p->more.size();
   k_member_status<<<(B + 127) / 128, 128, 0, g_stream>>>(p->status_q.p, B, M, p->status.p, p->embed_status_valid);
   if (p->ex.elsewhere) k_merge_status<<<(B + 127) / 128, 128, 0, g_stream>>>(p->x_status.p, B, p->status.p);
   p->embed_status_valid = 0;
-  xb::MarginalArgs m;
-  memset(&m, 0, sizeof(m));
-  m.B = B; m.n_comp = C; m.n_chan = c.n_chan; m.n_phases = c.n_phases; m.n_bins = c.n_bins;
-  m.pulses = p->folded.p; m.comp_phases = p->phase_cycles.p; m.phase_shifts = p->shifts.p;
-  m.data_phases = p->data_phases.p; m.counts = p->counts.p; m.precomp = p->precomp.p; m.support = p->support.p;
-  m.exposure_time = c.exposure_time; m.epsilon = c.epsilon; m.sigmas = c.sigmas; m.llzero = c.llzero;
-  m.slim = c.slim; m.allow_negative = c.allow_negative; m.interp = c.phase_interpolant;
-  m.chan_lnL = p->chan_lnL.p; m.chan_status = p->chan_status.p; m.expected = p->expected.p;
-  m.lnL = p->lnL.p; m.status = p->status.p;
-  e = xb::launch_marginal(m, g_stream);
-  if (e != cudaSuccess) return cuda_fail(e, "launch_marginal");
-  CK(cudaEventRecord(p->ev[4], g_stream));
+  for (int s = 0; s < S; ++s) {
+    xpsi_b200_pipeline::SignalPart* sp = s ? p->more[s - 1].get() : nullptr;
+    const int n_in = sp ? sp->n_in : c.n_in, n_chan = sp ? sp->n_chan : c.n_chan, n_bins = sp ? sp->n_bins : c.n_bins;
+    double* xin = sp ? sp->xin.p : p->xin.p;
+    double* folded = sp ? sp->folded.p : p->folded.p;
+    xb::EnergyIntegArgs ei;
+    memset(&ei, 0, sizeof(ei));
+    ei.Q = Q; ei.n_energies = c.n_energies; ei.n_phases = P_sig; ei.n_in = n_in;
+    ei.signal = p->flux.p; ei.raw_energies = p->energies.p; ei.div_b = p->d_sq.p; ei.q_per_b = M;
+    ei.log10_energies = p->log10E.p; ei.log10_edges = sp ? sp->log10_edges.p : p->log10_edges.p;
+    ei.interp = c.phase_interpolant;
+    ei.span = sp ? sp->ei_span.p : p->ei_span.p;
+    ei.col_of_q = p->col_of_q.p; ei.accumulate = (M > C) ? 1 : 0; ei.out = xin;
+    const double* att = sp ? sp->att_base.p : p->att_base.p;
+    if (att) { ei.attenuation = att; ei.att_power = p->att_power_valid ? p->att_power.p : nullptr; }
+    if (ei.accumulate)
+      CK(cudaMemsetAsync(xin, 0, (size_t)B * C * P_sig * n_in * sizeof(double), g_stream));
+    e = xb::launch_energy_integrator(ei, g_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_energy_integrator");
+    if (s == 0) CK(cudaEventRecord(p->ev[2], g_stream));
+
+    xb::FoldArgs f;
+    f.n_cols = B * C; f.n_phases = P_sig; f.n_in = n_in; f.n_chan = n_chan;
+    f.matrix = sp ? sp->response.p : p->response.p; f.ld_matrix = n_in; f.in0 = 0; f.x = xin; f.out = folded;
+    f.k_range = sp ? sp->k_range.p : p->k_range.p;
+    e = xb::launch_fold(f, g_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_fold");
+    if (s == 0) CK(cudaEventRecord(p->ev[3], g_stream));
+
+    const double* shifts = p->shifts.p;
+    if (p->sig_shift_valid) {
+      k_signal_shifts<<<(B * C + 127) / 128, 128, 0, g_stream>>>(p->shifts.p, p->sig_shift.p, B, C, S, s, p->sig_shifts_s.p);
+      shifts = p->sig_shifts_s.p;
+      g_launches += 1;
+    }
+    xb::MarginalArgs m;
+    memset(&m, 0, sizeof(m));
+    m.B = B; m.n_comp = C; m.n_chan = n_chan; m.n_phases = P_sig; m.n_bins = n_bins;
+    m.pulses = folded; m.comp_phases = p->phase_cycles.p; m.phase_shifts = shifts;
+    m.data_phases = sp ? sp->data_phases.p : p->data_phases.p; m.counts = sp ? sp->counts.p : p->counts.p;
+    m.precomp = sp ? sp->precomp.p : p->precomp.p; m.support = sp ? sp->support.p : p->support.p;
+    m.exposure_time = sp ? sp->exposure_time : c.exposure_time; m.epsilon = sp ? sp->epsilon : c.epsilon;
+    m.sigmas = sp ? sp->sigmas : c.sigmas; m.llzero = sp ? sp->llzero : c.llzero;
+    m.slim = sp ? sp->slim : c.slim; m.allow_negative = sp ? sp->allow_negative : c.allow_negative;
+    m.interp = c.phase_interpolant;
+    m.chan_lnL = sp ? sp->chan_lnL.p : p->chan_lnL.p; m.chan_status = sp ? sp->chan_status.p : p->chan_status.p;
+    m.expected = sp ? sp->expected.p : p->expected.p;
+    m.lnL = sp ? sp->lnL.p : p->lnL.p; m.status = p->status.p;      // a status raised by an earlier signal is kept
+    e = xb::launch_marginal(m, g_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_marginal");
+    if (sp) {
+      k_add_lnL<<<(B + 127) / 128, 128, 0, g_stream>>>(sp->lnL.p, B, p->lnL.p);
+      g_launches += 5;        // energy, fold, marginal, channel-sum, add
+    }
+  }
+  CK(cudaEventRecord(p->ev[4], g_stream));     // with several signals the "marginal" stage time covers signals 1..S-1 whole
   // expand, geometry, [slab, slab-member], tiles, flux (tensor-core + scalar for overflow rings), [ring reduction],
   // energy, fold, member-status, marginal, channel-sum
   g_launches += 10 + (c.hot_atm_ext == XPSI_B200_ATM_NUM4D ? 2 : 0) + (p->deterministic ? 1 : 0);
@@ -904,12 +978,14 @@ int pipeline_embed_launch(xpsi_b200_pipeline* p) {
     p->else_arrays_valid = 1; p->corr_valid = 1;
     g_launches += 2;
   }
-  cudaError_t e = xb::launch_embed_spots(p->embed_args, g_stream);
-  if (e != cudaSuccess) return cuda_fail(e, "launch_embed_spots");
+  if (!p->tinv_only) {
+    cudaError_t e = xb::launch_embed_spots(p->embed_args, g_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_embed_spots");
+    g_launches += 2;
+  }
   CK(cudaEventRecord(p->ev_embed[1], g_stream));
   p->embed_status_valid = 1;
   p->embed_timed = 1;
-  g_launches += 2;
   return 0;
 }
 
@@ -921,7 +997,8 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
   if (ensure_stream() != 0) return nullptr;
   const xpsi_b200_pipeline_config& c = *cfg;
   if (max_batch < 1 || c.n_components < 1 || c.n_members < c.n_components || c.n_bins < 1 || c.n_bins > xb::marginal_max_bins() ||
-      c.n_energies < 5 || c.n_leaves < 5 || c.n_phases < 5 ||
+      c.n_energies < 5 || (c.n_phases != 1 && (c.n_leaves < 5 || c.n_phases < 5)) ||
+      (c.n_phases == 1 && (c.n_members != 1 || c.n_components != 1)) ||
       (c.hot_atm_ext != XPSI_B200_ATM_BB && c.hot_atm_ext != XPSI_B200_ATM_NUM4D) ||
       (c.hot_atm_ext == XPSI_B200_ATM_NUM4D && !c.hot_atmosphere)) {
     g_err = "pipeline_create: invalid configuration";
@@ -930,11 +1007,13 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
   xpsi_b200_pipeline* p = new xpsi_b200_pipeline();
   p->cfg = c;
   p->max_batch = max_batch;
+  p->tinv_only = (c.n_phases == 1);       // Everywhere(time_invariant=True): no hot regions, one phase column
+  if (p->tinv_only) { p->cfg.max_rings = 0; p->cfg.max_azi = 0; p->cfg.n_leaves = 0; }
   p->atm = c.hot_atmosphere;
   p->member_component.assign(c.member_component, c.member_component + c.n_members);
   p->cfg.member_component = p->member_component.data();
   const int M = c.n_members, C = c.n_components;
-  const size_t B = max_batch, Q = B * M, R = c.max_rings, A = c.max_azi;
+  const size_t B = max_batch, Q = B * M, R = p->cfg.max_rings, A = p->cfg.max_azi;
   std::vector<double> l10E(c.n_energies), l10edges(c.n_in + 1), cyc(c.n_phases);
   for (int i = 0; i < c.n_energies; ++i) l10E[i] = log10(c.energies[i]);
   for (int i = 0; i <= c.n_in; ++i) l10edges[i] = log10(c.energy_edges[i]);
@@ -948,7 +1027,8 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
   cudaError_t e = cudaSuccess;
   auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
   ok(p->energies.upload(c.energies, c.n_energies)); ok(p->log10E.upload(l10E.data(), c.n_energies));
-  ok(p->leaves.upload(c.leaves, c.n_leaves)); ok(p->phases.upload(c.phases, c.n_phases));
+  if (!p->tinv_only) ok(p->leaves.upload(c.leaves, c.n_leaves));
+  ok(p->phases.upload(c.phases, c.n_phases));
   ok(p->phase_cycles.upload(cyc.data(), c.n_phases)); ok(p->log10_edges.upload(l10edges.data(), c.n_in + 1));
   {
     std::vector<int2> span(c.n_in);
@@ -976,7 +1056,7 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
   ok(p->folded.alloc(B * C * c.n_chan * c.n_phases)); ok(p->chan_lnL.alloc(B * c.n_chan));
   ok(p->chan_status.alloc(B * c.n_chan)); ok(p->expected.alloc(B * c.n_chan * c.n_bins));
   ok(p->lnL.alloc(B)); ok(p->status_q.alloc(Q)); ok(p->status.alloc(B)); ok(p->work.alloc(4));
-  {
+  if (!p->tinv_only) {
     xb::AzinvArgs w;
     memset(&w, 0, sizeof(w));
     w.Q = (int)Q; w.n_rings = c.max_rings; w.n_leaves = c.n_leaves; w.hot_atm_ext = c.hot_atm_ext;
@@ -1070,6 +1150,98 @@ int xpsi_b200_pipeline_set_extras(xpsi_b200_pipeline* p, const xpsi_b200_pipelin
   return 0;
 }
 
+
+// ---- further signals of the same photosphere (xpsi/Likelihood.py:346-420, :494-500) --------------------------
+int xpsi_b200_pipeline_add_signal(xpsi_b200_pipeline* p, const xpsi_b200_signal_config* sc) {
+  if (!p || !sc) return fail(XPSI_B200_EINVAL, "null argument");
+  const xpsi_b200_pipeline_config& c = p->cfg;
+  if (sc->n_in < 1 || sc->n_chan < 1 || sc->n_bins < 1 || !sc->energy_edges || !sc->response || !sc->data_phases ||
+      !sc->counts || !sc->support)
+    return fail(XPSI_B200_EINVAL, "add_signal: incomplete signal configuration");
+  if (sc->n_bins > xb::marginal_max_bins())
+    return fail(XPSI_B200_EUNSUPPORTED, "add_signal: more data phase bins than the marginal kernel covers");
+  std::unique_ptr<xpsi_b200_pipeline::SignalPart> sp(new xpsi_b200_pipeline::SignalPart());
+  sp->n_in = sc->n_in; sp->n_chan = sc->n_chan; sp->n_bins = sc->n_bins; sp->allow_negative = sc->allow_negative;
+  sp->exposure_time = sc->exposure_time; sp->epsilon = sc->epsilon; sp->sigmas = sc->sigmas; sp->llzero = sc->llzero;
+  sp->slim = sc->slim;
+  std::vector<double> l10E(c.n_energies), l10edges(sc->n_in + 1);
+  for (int i = 0; i < c.n_energies; ++i) l10E[i] = log10(c.energies[i]);
+  for (int i = 0; i <= sc->n_in; ++i) l10edges[i] = log10(sc->energy_edges[i]);
+  std::vector<int2> span(sc->n_in);
+  xb::energy_span_table(l10E.data(), c.n_energies, l10edges.data(), sc->n_in, span.data());
+  std::vector<int> kr = response_k_ranges(sc->response, sc->n_chan, sc->n_in, 0, sc->n_in);
+  std::vector<int> icounts((size_t)sc->n_chan * sc->n_bins);
+  for (size_t i = 0; i < icounts.size(); ++i) icounts[i] = (int)sc->counts[i];
+  Dev<int> d_ic;
+  CK(sp->log10_edges.upload(l10edges.data(), l10edges.size())); CK(sp->ei_span.upload(span.data(), span.size()));
+  CK(sp->response.upload(sc->response, (size_t)sc->n_chan * sc->n_in)); CK(sp->k_range.upload(kr.data(), kr.size()));
+  CK(sp->data_phases.upload(sc->data_phases, sc->n_bins + 1));
+  CK(sp->counts.upload(sc->counts, (size_t)sc->n_chan * sc->n_bins)); CK(sp->support.upload(sc->support, (size_t)sc->n_chan * 2));
+  if (sc->attenuation) CK(sp->att_base.upload(sc->attenuation, sc->n_in));
+  CK(d_ic.upload(icounts.data(), icounts.size())); CK(sp->precomp.alloc(sc->n_chan));
+  cudaError_t e = xb::launch_precomputation(d_ic.p, sc->n_chan, sc->n_bins, sp->precomp.p, g_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_precomputation");
+  const size_t B = p->max_batch, C = c.n_components;
+  CK(sp->xin.alloc(B * C * c.n_phases * sc->n_in)); CK(sp->folded.alloc(B * C * sc->n_chan * c.n_phases));
+  CK(sp->chan_lnL.alloc(B * sc->n_chan)); CK(sp->chan_status.alloc(B * sc->n_chan));
+  CK(sp->expected.alloc(B * sc->n_chan * sc->n_bins)); CK(sp->lnL.alloc(B));
+  CK(p->att_power.alloc(p->max_batch));
+  CK(cudaStreamSynchronize(g_stream));          // the host temporaries go away
+  g_launches += 1;
+  p->more.push_back(std::move(sp));
+  p->sig_shift_valid = 0;
+  return (int)p->more.size();                    // index of the new signal (the configuration's signal is 0)
+}
+
+int xpsi_b200_pipeline_n_signals(xpsi_b200_pipeline* p) { return p ? 1 + (int)p->more.size() : 0; }
+
+int xpsi_b200_pipeline_upload_signal_shifts(xpsi_b200_pipeline* p, int B, const double* shifts) {
+  if (!p || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
+  if (!shifts) { p->sig_shift_valid = 0; return 0; }
+  const size_t S = 1 + p->more.size();
+  CK(p->sig_shift.upload(shifts, (size_t)B * S));
+  CK(p->sig_shifts_s.alloc((size_t)p->max_batch * p->cfg.n_components));
+  CK(cudaStreamSynchronize(g_stream));
+  p->sig_shift_valid = 1;
+  return 0;
+}
+
+int xpsi_b200_pipeline_fetch_signal(xpsi_b200_pipeline* p, int signal, int B, double* folded, double* expected, double* lnL) {
+  if (!p || B < 1 || B > p->max_batch || signal < 0 || signal > (int)p->more.size())
+    return fail(XPSI_B200_EINVAL, "bad signal index or batch size");
+  const xpsi_b200_pipeline_config& c = p->cfg;
+  if (signal == 0) {
+    if (folded) CK(p->folded.download(folded, (size_t)B * c.n_components * c.n_chan * c.n_phases));
+    if (expected) CK(p->expected.download(expected, (size_t)B * c.n_chan * c.n_bins));
+    if (lnL) {
+      // the configuration's signal alone: the joint value minus the other signals' terms is not kept; recompute
+      // from the channel terms (ordered sum, as k_sum_channels)
+      std::vector<double> ch((size_t)B * c.n_chan);
+      CK(p->chan_lnL.download(ch.data(), ch.size()));
+      CK(cudaStreamSynchronize(g_stream));
+      for (int b = 0; b < B; ++b) { double s = 0.0; for (int k = 0; k < c.n_chan; ++k) s += ch[(size_t)b * c.n_chan + k]; lnL[b] = s; }
+    }
+  } else {
+    xpsi_b200_pipeline::SignalPart* sp = p->more[signal - 1].get();
+    if (folded) CK(sp->folded.download(folded, (size_t)B * c.n_components * sp->n_chan * c.n_phases));
+    if (expected) CK(sp->expected.download(expected, (size_t)B * sp->n_chan * sp->n_bins));
+    if (lnL) CK(sp->lnL.download(lnL, B));
+  }
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int xpsi_b200_pipeline_sweep_upload_signal_shifts(xpsi_b200_pipeline* p, long long N, const double* shifts) {
+  if (!p || N < 1 || (size_t)N != p->store.N) return fail(XPSI_B200_EINVAL, "signal shifts must match the uploaded sweep");
+  if (!shifts) { p->store.has_sig_shift = 0; return 0; }
+  const size_t S = 1 + p->more.size();
+  CK(p->store.sig_shift.upload(shifts, (size_t)N * S));
+  CK(p->sig_shifts_s.alloc((size_t)p->max_batch * p->cfg.n_components));
+  CK(cudaStreamSynchronize(g_stream));
+  p->store.has_sig_shift = 1;
+  return 0;
+}
+
 int xpsi_b200_pipeline_upload_extras(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch_extras* h) {
   if (!p || !h || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
   const xpsi_b200_pipeline_config& c = p->cfg;
@@ -1136,7 +1308,7 @@ int xpsi_b200_pipeline_eval(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch*
 
 // device-side embed arguments over the pipeline's own per-batch arrays
 static int set_embed_args(xpsi_b200_pipeline* p, int B, double mode_frequency, int num_cells, int min_sqrt,
-                          int max_sqrt, bool hole, bool partner, bool extra) {
+                          int max_sqrt, bool hole, bool partner, bool extra, bool member_cells = false) {
   const xpsi_b200_pipeline_config& c = p->cfg;
   const size_t M = c.n_members;
   CK(p->e_maxAlpha.alloc((size_t)p->max_batch * M * c.max_rings));
@@ -1150,6 +1322,7 @@ static int set_embed_args(xpsi_b200_pipeline* p, int B, double mode_frequency, i
   if (hole) { a.hole_radius = p->e_hrad.p; a.hole_colatitude = p->e_hcolat.p; a.hole_azimuth = p->e_hazi.p; }
   if (partner) { a.partner = p->e_partner.p; a.is_cede = p->e_iscede.p; }
   if (extra) a.extra_params = p->e_extra.p;
+  if (member_cells) a.member_cells = p->e_member_cells.p;
   a.n_rings = p->n_rings.p; a.n_azi = p->n_azi.p; a.cellArea = p->cellArea.p; a.phi = p->phi.p; a.theta = p->theta.p;
   a.radial = p->radial.p; a.r_s_over_r = p->rsr.p; a.srcParams = p->params.p; a.cos_gamma = p->cgamma.p;
   a.maxAlpha = p->e_maxAlpha.p; a.deflection = p->defl.p; a.cos_alpha = p->calpha.p; a.lag = p->lag.p;
@@ -1186,9 +1359,11 @@ int xpsi_b200_pipeline_embed_spots(xpsi_b200_pipeline* p, int B, const xpsi_b200
     if (rc) return rc;
     CK(p->e_partner.upload(h->partner, M)); CK(p->e_iscede.upload(h->is_cede, M));
   }
+  if (h->member_cells) CK(p->e_member_cells.upload(h->member_cells, 3 * M));
   CK(cudaMemsetAsync(p->status.p, 0, B * sizeof(int), g_stream));
   int rc = set_embed_args(p, B, h->mode_frequency, h->num_cells, h->min_sqrt_num_cells, h->max_sqrt_num_cells,
-                          h->hole_radius != nullptr, h->partner != nullptr, h->extra_params && c.n_params > 2);
+                          h->hole_radius != nullptr, h->partner != nullptr, h->extra_params && c.n_params > 2,
+                          h->member_cells != nullptr);
   if (rc) return rc;
   return pipeline_embed_launch(p);
 }
@@ -1220,10 +1395,13 @@ int xpsi_b200_pipeline_sweep_upload(xpsi_b200_pipeline* p, long long N, const xp
     if (rc) return rc;
     CK(p->e_partner.upload(h->partner, M)); CK(p->e_iscede.upload(h->is_cede, M));
   }
+  s.has_member_cells = h->member_cells != nullptr;
+  if (s.has_member_cells) CK(p->e_member_cells.upload(h->member_cells, 3 * M));
   s.has_att = att_power != nullptr;
   if (s.has_att) CK(s.att_power.upload(att_power, n));
   s.has_else = else_temperature != nullptr;
   if (s.has_else) CK(s.else_temp.upload(else_temperature, n));
+  s.has_sig_shift = 0;
   CK(s.lnL.alloc(n)); CK(s.status.alloc(n));
   s.mode_frequency = h->mode_frequency; s.num_cells = h->num_cells;
   s.min_sqrt = h->min_sqrt_num_cells; s.max_sqrt = h->max_sqrt_num_cells;
@@ -1262,9 +1440,10 @@ int xpsi_b200_pipeline_sweep_run(xpsi_b200_pipeline* p, long long first, long lo
     if (s.has_extra) CK(d2d(p->e_extra, s.extra, o * M * X, B, M * X));
     if (s.has_att) { CK(d2d(p->att_power, s.att_power, o, B, 1)); p->att_power_valid = 1; }
     if (s.has_else) { CK(d2d(p->x_temp, s.else_temp, o, B, 1)); p->else_temp_valid = 1; }
+    if (s.has_sig_shift) { const size_t S = 1 + p->more.size(); CK(d2d(p->sig_shift, s.sig_shift, o * S, B, S)); p->sig_shift_valid = 1; }
     CK(cudaMemsetAsync(p->status.p, 0, B * sizeof(int), g_stream));
     int rc = set_embed_args(p, (int)B, s.mode_frequency, s.num_cells, s.min_sqrt, s.max_sqrt, s.has_hole,
-                            s.has_partner, s.has_extra);
+                            s.has_partner, s.has_extra, s.has_member_cells);
     if (rc) return rc;
     rc = pipeline_embed_launch(p);
     if (rc) return rc;

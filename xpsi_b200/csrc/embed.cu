@@ -476,6 +476,9 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
   const bool generic = fr.polar || g.hRadius > 0.0 || partner >= 0;
   const double bphi = fr.bphi;                                      // mesh.pyx:59 / pi for a polar cap
   // ---- allocate_cells (mesh_tools.pyx:892-1099): bounding-mesh area vs region area ------------
+  const int cells_num = a.member_cells ? a.member_cells[3 * m_idx] : a.num_cells;
+  const double cells_min = a.member_cells ? (double)a.member_cells[3 * m_idx + 1] : a.min_sqrt;
+  const double cells_max = a.member_cells ? (double)a.member_cells[3 * m_idx + 2] : a.max_sqrt;
   if (tid < 32) {
     const double h = 0.5 * (hi - lo), m = 0.5 * (hi + lo);
     double v = c_gl32_w[tid] * area_element(m + h * c_gl32_x[tid], eps, zeta, 0);
@@ -494,8 +497,8 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
         s_spotA = s;
         double spotA = s;
         if (are_equal(spotA * R_eq * R_eq, 0.0)) spotA = s_boxA / 1000.0;
-        double sq = ceil(sqrt((double)a.num_cells * s_boxA / spotA));
-        if (sq < a.min_sqrt) sq = a.min_sqrt; else if (sq > a.max_sqrt) sq = a.max_sqrt;
+        double sq = ceil(sqrt((double)cells_num * s_boxA / spotA));
+        if (sq < cells_min) sq = cells_min; else if (sq > cells_max) sq = cells_max;
         int n = (int)sq;
         if (n % 2 != 0) n += 1;
         s_n = n;
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
       const double boxA = 2.0 * bphi * v;
       double ownA = warp_region_area(g, lo, hi, eps, zeta, tid);
       if (are_equal(ownA * R_eq * R_eq, 0.0)) ownA = boxA / 1000.0;
-      double numCell = (double)a.num_cells;
+      double numCell = (double)cells_num;
       if (partner >= 0) {            // superseding + ceding members share num_cells (:1040-1060)
         const int qp = b * a.M + partner;
         Region gp;
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
       if (tid == 0) {
         s_boxA = boxA; s_spotA = ownA;
         double sq = ceil(sqrt(numCell * boxA / ownA));
-        if (sq < a.min_sqrt) sq = a.min_sqrt; else if (sq > a.max_sqrt) sq = a.max_sqrt;
+        if (sq < cells_min) sq = cells_min; else if (sq > cells_max) sq = cells_max;
         int n = (int)sq;
         if (n % 2 != 0) n += 1;
         s_n = n;

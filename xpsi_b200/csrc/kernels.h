@@ -114,6 +114,8 @@ struct EmbedArgs {
   // pairing of superseding / ceding members that share num_cells (mesh_tools.pyx:1040-1060)
   const double* hole_radius; const double* hole_colatitude; const double* hole_azimuth;   // [B*M]
   const int* partner; const int* is_cede;         // [M]: partner member index or -1; 1 = ceding member
+  const int* member_cells;                        // nullptr, or [M][3]: (num_cells, min_sqrt, max_sqrt) of the hot
+                                                  // region each member belongs to (regions may differ)
   const double* extra_params;                     // nullptr, or [B*M][n_params-2]: local variables after (log T, log g)
   const double* else_temperature;                 // nullptr, or [B]: log10 T of Elsewhere (for corrParams)
   double* corrParams;                             // nullptr, or [B*M][max_rings][n_params]: correction parameter rows

@@ -32,7 +32,7 @@ class Likelihood:
 
     def _filled(self, P):
         """``fill`` may return the spot batch alone (it then uploads per-block extras itself) or
-        ``(spots, dict(att_power=..., else_temperature=...))``."""
+        ``(spots, dict(att_power=..., else_temperature=..., signal_shifts=...))``."""
         r = self._fill(self._pipe, P)
         return r if isinstance(r, tuple) else (r, None)
 
@@ -78,7 +78,12 @@ class Likelihood:
             blk = P[i:i + self._max_batch]
             spots, extras = self._filled(blk)
             if extras is not None:
-                self._pipe.upload_extras(blk.shape[0], **extras)
+                extras = dict(extras)
+                sig = extras.pop("signal_shifts", None)
+                if extras:
+                    self._pipe.upload_extras(blk.shape[0], **extras)
+                if sig is not None or len(getattr(self._pipe, "signals", ())) > 1:
+                    self._pipe.upload_signal_shifts(blk.shape[0], sig)
             lnL[i:i + blk.shape[0]], status[i:i + blk.shape[0]] = self._pipe.eval_spots(spots)
         bad = ~np.isin(status, (0,) + self.NUMERICAL_STATUSES)
         if strict and bad.any():

@@ -112,6 +112,9 @@ class SpotBatch:
         self.partner = self.is_cede = None
         # optional [B, M, n_params-2]: local variables after (log T, log g), e.g. beaming parameters
         self.extra_params = None
+        # optional int [M, 3]: (num_cells, min_sqrt_num_cells, max_sqrt_num_cells) of the hot region each member
+        # belongs to, when the regions were constructed with different resolutions
+        self.member_cells = None
 
     def set_region(self, super_member, cede_member=None, *, super_colatitude, super_radius, super_temperature,
                    omit_colatitude=None, omit_radius=None, omit_azimuth=None, cede_colatitude=None,
@@ -178,6 +181,11 @@ class SpotBatch:
             if self.extra_params.shape[:2] != (self.B, self.M):
                 raise ValueError("extra_params must have shape [B, M, n_params-2]")
             s.extra_params = _lib.dptr(self.extra_params)
+        if self.member_cells is not None:
+            self.member_cells = np.ascontiguousarray(self.member_cells, dtype=np.int32)
+            if self.member_cells.shape != (self.M, 3):
+                raise ValueError("member_cells must have shape [M, 3]")
+            s.member_cells = _lib.iptr(self.member_cells)
         return s
 
 
@@ -201,8 +209,8 @@ class BatchedLikelihood:
     ``eval_marginal_likelihood`` settings (``CustomSignal``).
     """
 
-    def __init__(self, *, member_component, max_rings, max_azi, n_rays, energies, leaves, phases,
-                 hot_atm_ext, hot_atmosphere=None, image_order_limit=None, response, energy_edges,
+    def __init__(self, *, member_component=(0,), max_rings=0, max_azi=0, n_rays=0, energies, leaves=None, phases=None,
+                 hot_atm_ext=1, hot_atmosphere=None, image_order_limit=None, response, energy_edges,
                  counts, data_phases, exposure_time, support=None, epsilon=1.0e-3, sigmas=10.0,
                  llzero=-1.0e90, slim=20.0, allow_negative=False, n_params=2, max_batch=64,
                  phase_interpolant='Akima'):
@@ -215,6 +223,14 @@ class BatchedLikelihood:
         mc = keep(member_component, np.int32)
         self.n_members = int(mc.size)
         self.n_components = int(mc.max()) + 1
+        # ``phases=None`` (or one phase): the star is an ``Everywhere(time_invariant=True)`` surface
+        # (xpsi/Everywhere.py:577-601) -- no hot regions, one phase column; its mesh settings come with
+        # ``set_extras(everywhere=...)``
+        self.time_invariant = phases is None or np.size(phases) == 1
+        if self.time_invariant:
+            if self.n_members != 1:
+                raise ValueError("a time-invariant (Everywhere) pipeline has exactly one member")
+            phases, leaves = np.zeros(1), np.zeros(1)
         energies, leaves, phases = keep(energies), keep(leaves), keep(phases)
         response, energy_edges = keep(response), keep(energy_edges)
         counts, data_phases = keep(counts), keep(data_phases)
@@ -228,7 +244,7 @@ class BatchedLikelihood:
         cfg.n_components, cfg.n_members, cfg.member_component = self.n_components, self.n_members, _lib.iptr(mc)
         cfg.max_rings, cfg.max_azi, cfg.n_rays, cfg.n_params = int(max_rings), int(max_azi), int(n_rays), int(n_params)
         cfg.n_energies, cfg.energies = energies.size, _lib.dptr(energies)
-        cfg.n_leaves, cfg.leaves = leaves.size, _lib.dptr(leaves)
+        cfg.n_leaves, cfg.leaves = (0 if self.time_invariant else leaves.size), _lib.dptr(leaves)
         cfg.n_phases, cfg.phases = phases.size, _lib.dptr(phases)
         cfg.hot_atm_ext = int(hot_atm_ext)
         cfg.hot_atmosphere = self.atm.handle if self.atm is not None else None
@@ -248,6 +264,67 @@ class BatchedLikelihood:
         self.handle = _lib.lib.xpsi_b200_pipeline_create(C.byref(cfg), self.max_batch)
         if not self.handle:
             raise _lib.XpsiB200Error("pipeline_create failed: %s" % _lib.last_error())
+        self.signals = [dict(n_chan=n_chan, n_in=n_in, n_bins=data_phases.size - 1)]
+
+    def add_signal(self, *, response, energy_edges, counts, data_phases, exposure_time, support=None, epsilon=1.0e-3,
+                   sigmas=10.0, llzero=-1.0e90, slim=20.0, allow_negative=False, attenuation=None):
+        """Register one more (instrument, data) pair behind the same integrator stage -- a second ``xpsi.Signal``
+        of the photosphere (xpsi/Likelihood.py:346-420; docs/source/Instrument_synergy.ipynb).  The photosphere
+        signal is computed once at the pipeline's energies (the reference gives all signals of a photosphere one
+        energy array, Likelihood.py:102-107); this signal gets its own energy integration, interstellar
+        attenuation (``attenuation[n_in]`` at unit power, raised to the batch's ``att_power``), response fold and
+        background-marginalised likelihood, and the joint log-likelihood is the sum (Likelihood.py:494-500).
+        Returns the signal's index (the constructor's signal is 0)."""
+        response = np.ascontiguousarray(response, dtype=np.float64)
+        n_chan, n_in = response.shape
+        energy_edges = np.ascontiguousarray(energy_edges, dtype=np.float64)
+        counts = np.ascontiguousarray(counts, dtype=np.float64)
+        data_phases = np.ascontiguousarray(data_phases, dtype=np.float64)
+        if energy_edges.shape != (n_in + 1,) or counts.shape != (n_chan, data_phases.size - 1):
+            raise ValueError("add_signal: response [n_chan, n_in], energy_edges [n_in+1], counts [n_chan, n_bins] "
+                             "and data_phases [n_bins+1] do not fit together")
+        if support is None:
+            support = -1.0 * np.ones((n_chan, 2))
+            support[:, 0] = 0.0
+        support = np.ascontiguousarray(support, dtype=np.float64)
+        sc = _lib.SignalConfig()
+        sc.n_in, sc.energy_edges = n_in, _lib.dptr(energy_edges)
+        sc.n_chan, sc.response = n_chan, _lib.dptr(response)
+        sc.n_bins, sc.data_phases = data_phases.size - 1, _lib.dptr(data_phases)
+        sc.counts, sc.support = _lib.dptr(counts), _lib.dptr(support)
+        sc.exposure_time, sc.epsilon, sc.sigmas = float(exposure_time), float(epsilon), float(sigmas)
+        sc.llzero, sc.slim, sc.allow_negative = float(llzero), float(slim), int(bool(allow_negative))
+        if attenuation is not None:
+            att = np.ascontiguousarray(attenuation, dtype=np.float64)
+            if att.shape != (n_in,):
+                raise ValueError("one attenuation factor per instrument input interval is required")
+            sc.attenuation = _lib.dptr(att)
+        idx = _lib.lib.xpsi_b200_pipeline_add_signal(self.handle, C.byref(sc))
+        if idx < 0:
+            _lib.check(idx)
+        self.signals.append(dict(n_chan=n_chan, n_in=n_in, n_bins=data_phases.size - 1))
+        return idx
+
+    def upload_signal_shifts(self, B, shifts):
+        """``shifts[B, n_signals]`` in cycles: each signal's own phase shift, added to the hot regions' shifts for
+        that signal (``Signal.shifts``, xpsi/Signal.py:581-583); ``None`` switches them off."""
+        if shifts is None:
+            _lib.check(_lib.lib.xpsi_b200_pipeline_upload_signal_shifts(self.handle, B, None))
+            return
+        a = np.ascontiguousarray(shifts, dtype=np.float64)
+        if a.shape != (B, len(self.signals)):
+            raise ValueError("signal shifts must have shape (%d, %d)" % (B, len(self.signals)))
+        _lib.check(_lib.lib.xpsi_b200_pipeline_upload_signal_shifts(self.handle, B, _lib.dptr(a)))
+
+    def fetch_signal(self, signal, B):
+        """``(folded[B, C, n_chan, n_phases], expected[B, n_chan, n_bins], lnL[B])`` of one signal."""
+        g = self.signals[signal]
+        f = np.empty((B, self.n_components, g["n_chan"], self.shape["n_phases"]))
+        e = np.empty((B, g["n_chan"], g["n_bins"]))
+        l = np.empty(B)
+        _lib.check(_lib.lib.xpsi_b200_pipeline_fetch_signal(self.handle, signal, B, _lib.dptr(f), _lib.dptr(e),
+                                                            _lib.dptr(l)))
+        return f, e, l
 
     def __del__(self):
         try:
@@ -262,8 +339,12 @@ class BatchedLikelihood:
         (run to run, and whatever the position of a parameter vector in its batch)."""
         _lib.check(_lib.lib.xpsi_b200_pipeline_set_deterministic(self.handle, int(bool(on))))
 
-    def set_extras(self, elsewhere=None, attenuation=None, beam_opt=0):
+    def set_extras(self, elsewhere=None, attenuation=None, beam_opt=0, everywhere=None):
         """Optional model components (set once).
+
+        ``everywhere`` (time-invariant pipelines only): the same dict as ``elsewhere`` -- the closed equal-area
+        surface mesh of ``xpsi.Everywhere`` (xpsi/Everywhere.py:117-123 for the defaults) with a uniform
+        temperature; the spectrum IS the star's signal (xpsi/Photosphere.py:560-566), one phase column.
 
         ``elsewhere``: dict(sqrt_num_cells, num_rays, atm_ext, atmosphere=None, image_order_limit=None) adds
         ``xpsi.Elsewhere`` (xpsi/Elsewhere.py:129-134 for the defaults the reference uses): its spectrum is
@@ -273,6 +354,12 @@ class BatchedLikelihood:
         ``beam_opt``: beaming option of the hot regions (xpsi/HotRegion.py:184-200)."""
         x = _lib.PipelineExtras()
         self._extras_keep = []
+        if everywhere is not None:
+            if not self.time_invariant or elsewhere is not None:
+                raise ValueError("everywhere= belongs to a time-invariant pipeline (phases=None) without elsewhere")
+            elsewhere = everywhere
+        elif self.time_invariant and elsewhere is not None:
+            raise ValueError("a time-invariant pipeline takes everywhere=, not elsewhere=")
         if elsewhere is not None:
             x.elsewhere = 1
             x.else_sqrt_num_cells = int(elsewhere["sqrt_num_cells"])
@@ -348,7 +435,7 @@ class BatchedLikelihood:
 
     def new_spot_batch(self, B, mode_frequency, **kw):
         sb = SpotBatch(B, self.n_members, self.n_components, mode_frequency, **kw)
-        if sb.max_sqrt > min(self.shape["max_rings"], self.shape["max_azi"]):
+        if not self.time_invariant and sb.max_sqrt > min(self.shape["max_rings"], self.shape["max_azi"]):
             raise ValueError("max_sqrt_num_cells = %d exceeds the pipeline's padded mesh (%d x %d): the embed "
                              "would refuse every parameter vector that allocates more rings"
                              % (sb.max_sqrt, self.shape["max_rings"], self.shape["max_azi"]))
@@ -412,9 +499,9 @@ class BatchedLikelihood:
         return dict(H=out[0], V=out[1], RI=out[2], K=out[3])
 
     # ---- sweep: N parameter vectors resident on the device, evaluated block by block -------------------
-    def sweep_upload(self, spots, att_power=None, else_temperature=None):
+    def sweep_upload(self, spots, att_power=None, else_temperature=None, signal_shifts=None):
         """Upload the parameter-level inputs of ``spots.B`` parameter vectors once (any N; evaluation
-        proceeds in blocks of ``max_batch``)."""
+        proceeds in blocks of ``max_batch``).  ``signal_shifts[N, n_signals]``: see ``upload_signal_shifts``."""
         st = spots.struct()
         keep = []
 
@@ -429,6 +516,11 @@ class BatchedLikelihood:
         _lib.check(_lib.lib.xpsi_b200_pipeline_sweep_upload(self.handle, spots.B, C.byref(st), opt(att_power),
                                                             opt(else_temperature)))
         self._sweep_n = spots.B
+        if signal_shifts is not None:
+            a = np.ascontiguousarray(signal_shifts, dtype=np.float64)
+            if a.shape != (spots.B, len(self.signals)):
+                raise ValueError("signal shifts must have shape (%d, %d)" % (spots.B, len(self.signals)))
+            _lib.check(_lib.lib.xpsi_b200_pipeline_sweep_upload_signal_shifts(self.handle, spots.B, _lib.dptr(a)))
 
     def sweep_run(self, first=0, count=None):
         """Queue embed + the four stages for rows ``[first, first+count)`` of the uploaded sweep (no sync)."""
@@ -450,9 +542,9 @@ class BatchedLikelihood:
         _lib.check(_lib.lib.xpsi_b200_pipeline_sweep_results(self.handle, C.byref(a), C.byref(b)))
         return (_DeviceArray(a.value, self._sweep_n, "<f8", self), _DeviceArray(b.value, self._sweep_n, "<i4", self))
 
-    def sweep_spots(self, spots, att_power=None, else_temperature=None):
+    def sweep_spots(self, spots, att_power=None, else_temperature=None, signal_shifts=None):
         """Upload once, evaluate every block, download once: ``(lnL[N], status[N])``."""
-        self.sweep_upload(spots, att_power, else_temperature)
+        self.sweep_upload(spots, att_power, else_temperature, signal_shifts)
         self.sweep_run()
         return self.sweep_download()
 
