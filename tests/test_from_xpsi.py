@@ -157,4 +157,3 @@ def test_from_xpsi_every_configuration(ref):
     with quiet:
         like = mm.build_two_signals(g["counts_N"], g["counts_X"])[0]
     _check(from_xpsi.from_xpsi(like, max_batch=4), g["theta"], g["lnL_total"], "two signals")
-    rec.restore()

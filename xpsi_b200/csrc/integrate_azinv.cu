@@ -950,6 +950,17 @@ __device__ __noinline__ double profile_beaming(int beam_opt, const SlabCtx& hot,
          }) / t3;
 }
 
+// a / s for 0 <= a <= s, s > 0.  Both are first scaled by the power of two that puts s in [1, 2): exact, so the
+// quotient is the IEEE one, but the division stays on its in-line path whatever the magnitude of the profile
+// (slope differences of a dim energy channel are < 2^-120 or 0, which sent half of all divisions of stage 2 to the
+// out-of-line denormal-safe routine: profiles/r02d, 6 % of the kernel's instructions)
+__device__ __forceinline__ double ratio_scaled(double a, double s) {
+  const int e = (__double2hiint(s) >> 20) & 0x7ff;
+  const double sc = __hiloint2double((2046 - e) << 20, 0);
+  const double an = a * sc, sn = s * sc;
+  return (an < 0x1p-100) ? 0.0 : an / sn;      // a weight in [0, 1]: below 1e-30 it is zero to every digit it touches
+}
+
 // ATM: hot atmosphere (1 BB, 2 Num4D).  CORR: elsewhere correction (0 none, 1 BB, 2 Num4D)
 // BEAM: 0 = no beaming code at all (keeps the common instantiation free of the call's register pressure)
 // CUBIC: 1 = the global C2 phase spline (its solver needs 6 KB of per-thread local memory, kept out of the
@@ -1198,11 +1209,11 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
           };
           double mm2 = slope(l0 - 2), mm1 = slope(l0 - 1), m0 = slope(l0), mp1 = slope(l0 + 1);
           double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
-          double alpha = (NE != 0.0) ? fabs(mm1 - mm2) / NE : 0.0;
+          double alpha = (NE != 0.0) ? ratio_scaled(fabs(mm1 - mm2), NE) : 0.0;
           for (int l = l0; l < l1; ++l) {
             const double mp2 = slope(l + 2);
             const double NE_next = fabs(mp2 - mp1) + fabs(m0 - mm1);
-            const double alpha1 = (NE_next != 0.0) ? fabs(m0 - mm1) / NE_next : 0.0;
+            const double alpha1 = (NE_next != 0.0) ? ratio_scaled(fabs(m0 - mm1), NE_next) : 0.0;
             double b, c, d;
             if (NE == 0.0) { b = m0; c = 0.0; d = 0.0; }
             else {
@@ -1311,6 +1322,7 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
 // warp afterwards.  Rings with a tile that does not fit tile_cap steps are left to k_azinv_flux (ih[11]).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kRow = 33;     // doubles per leaf row of the coefficient plane: [8 energies][y, b, c, d] + one flag word
+
 
 template <int ATM, int CORR, int NLP>
 __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5)
@@ -1496,11 +1508,11 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
           };
           double mm2 = slope(l0 - 2), mm1 = slope(l0 - 1), m0 = slope(l0), mp1 = slope(l0 + 1);
           double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
-          double alpha = (NE != 0.0) ? fabs(mm1 - mm2) / NE : 0.0;
+          double alpha = (NE != 0.0) ? ratio_scaled(fabs(mm1 - mm2), NE) : 0.0;
           for (int l = l0; l < l1; ++l) {
             const double mp2 = slope(l + 2);
             const double NE_next = fabs(mp2 - mp1) + fabs(m0 - mm1);
-            const double alpha1 = (NE_next != 0.0) ? fabs(m0 - mm1) / NE_next : 0.0;
+            const double alpha1 = (NE_next != 0.0) ? ratio_scaled(fabs(m0 - mm1), NE_next) : 0.0;
             double b, c, d;
             if (NE == 0.0) { b = m0; c = 0.0; d = 0.0; }
             else {
