@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxpsi_b200.so")
+# XPSI_B200_LIB: development only (timing kernel variants built by dev/build_variants.sh side by side)
+LIB_PATH = os.environ.get("XPSI_B200_LIB") or os.path.join(_HERE, "libxpsi_b200.so")
 
 if not os.path.isfile(LIB_PATH):
     raise ImportError(

@@ -950,15 +950,11 @@ __device__ __noinline__ double profile_beaming(int beam_opt, const SlabCtx& hot,
          }) / t3;
 }
 
-// a / s for 0 <= a <= s, s > 0.  Both are first scaled by the power of two that puts s in [1, 2): exact, so the
-// quotient is the IEEE one, but the division stays on its in-line path whatever the magnitude of the profile
-// (slope differences of a dim energy channel are < 2^-120 or 0, which sent half of all divisions of stage 2 to the
-// out-of-line denormal-safe routine: profiles/r02d, 6 % of the kernel's instructions)
+// a / s for 0 <= a <= s, s > 0: the Akima weight of stage 2.  Bit-identical to the plain quotient.
 __device__ __forceinline__ double ratio_scaled(double a, double s) {
-  const int e = (__double2hiint(s) >> 20) & 0x7ff;
-  const double sc = __hiloint2double((2046 - e) << 20, 0);
-  const double an = a * sc, sn = s * sc;
-  return (an < 0x1p-100) ? 0.0 : an / sn;      // a weight in [0, 1]: below 1e-30 it is zero to every digit it touches
+  // a zero numerator (a locally straight profile) is what sends the IEEE division out of line: divide s by s instead
+  const double q = ((a == 0.0) ? s : a) / s;
+  return (a == 0.0) ? 0.0 : q;
 }
 
 // ATM: hot atmosphere (1 BB, 2 Num4D).  CORR: elsewhere correction (0 none, 1 BB, 2 Num4D)
@@ -1321,8 +1317,84 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
 // where the spline is positive) enter the DMMA with that energy's row zeroed and are redone cell by cell by the
 // warp afterwards.  Rings with a tile that does not fit tile_cap steps are left to k_azinv_flux (ih[11]).
 // ---------------------------------------------------------------------------------------------------------
+#ifndef XB_S2_UNROLL
+#define XB_S2_UNROLL 1       // unroll factor of the stage-2 interval loop (0: the whole block of a thread)
+#endif
 constexpr int kRow = 33;     // doubles per leaf row of the coefficient plane: [8 energies][y, b, c, d] + one flag word
 
+
+// Build-time experiment switches of k_azinv_flux_mma (dev/build_variants.sh + dev/time_step.py time them side by side
+// on the GPU box).  Measured at batch 512 on the bench workload, flux stage (profiles/r02f_variants.txt): the kernel
+// answers to none of them by more than 2 % -- out-of-line rare paths -1.6 %, rolled tile loop +0.5 %, stage-1 unroll
+// 4 / 2 +0.8 %, stage-2 unroll 2 / full +2.7 % / +16 %, set-bit walk of the flagged intervals +3 %.
+#ifndef XB_S1_UNROLL
+#define XB_S1_UNROLL 8
+#endif
+constexpr int kS1Unroll = XB_S1_UNROLL;
+#ifndef XB_ROLL_TILES
+#define XB_ROLL_TILES 0
+#endif
+#ifndef XB_NOINLINE_EXACT
+#define XB_NOINLINE_EXACT 1
+#endif
+#ifndef XB_NOINLINE_FLAGGED
+#define XB_NOINLINE_FLAGGED 1
+#endif
+// exact test behind an inconclusive Bernstein test: does y0 + t (b + t (c + t d)) go below zero inside (0, h)?
+// Rare, and kept out of line: the flux kernel is large enough for instruction fetch to show in its stall reasons.
+__device__ __noinline__ bool cubic_dips_below(double y0, double b, double c, double d, double h) {
+  auto below = [&](double t) -> bool { return t > 0.0 && t < h && (y0 + t * (b + t * (c + t * d))) < 0.0; };
+  if (d != 0.0) {
+    const double disc = c * c - 3.0 * b * d;
+    if (disc >= 0.0) {
+      const double sq = sqrt(disc), i3d = 1.0 / (3.0 * d);
+      return below((-c - sq) * i3d) || below((-c + sq) * i3d);
+    }
+    return false;
+  }
+  if (c != 0.0) return below(-b / (2.0 * c));
+  return false;
+}
+
+// cell-by-cell correction of one 8-phase tile for the (interval, energy) pairs whose cubic may dip below zero
+// (lane = (energy pair eg, eg + 4; phase kk of the tile)); out of line for the same reason
+__device__ __noinline__ double2 flagged_tile_correction(const double* s_coef, const double* s_PH, int N_L, int N_P, int tile,
+                                                         int2 th, int lane, unsigned long long fm0, unsigned long long fm1,
+                                                         unsigned long long fm2, unsigned long long fm3,
+                                                         const double* phases, const double* cl, int n_azi, const int* mt) {
+  const int kk = lane & 7, eg = lane >> 3, NI = N_L - 1, ns = th.y;
+  const int k = tile * kTilePhases + kk;
+  const double phk = (k < N_P) ? phases[k] : 0.0;
+  const double ph_first = s_PH[0], ph_last = s_PH[N_L - 1];
+  mt += kk;
+  double s_lo = 0.0, s_hi = 0.0;
+  int m = th.x;
+  for (int s = 0; s < ns; ++s) {
+    if (((m < 64 ? fm0 : m < 128 ? fm1 : m < 192 ? fm2 : fm3) >> (m & 63)) & 1ull) {     // N_L <= 256 (launcher)
+      const double* row = s_coef + (long)m * kRow;
+      const unsigned long long fw = *reinterpret_cast<const unsigned long long*>(row + 32);
+      const bool f_lo = (fw >> (8 * eg)) & 1ull, f_hi = (fw >> (8 * (eg + 4))) & 1ull;
+      const int cells = mt[(long)s * kTilePhases];
+      const int c_start = cells & 0xffff, c_end = cells >> 16;
+      if ((f_lo || f_hi) && k < N_P) {
+        const double xm = s_PH[m];
+        const double* cl_ = row + eg * 4;
+        const double* ch_ = row + (eg + 4) * 4;
+        for (int cc = c_start; cc < c_end; ++cc) {
+          double xr = phk + cl[cc];
+          if (xr > ph_last) { while (xr > ph_last) xr -= kTwoPi; }
+          else if (xr < ph_first) { while (xr < ph_first) xr += kTwoPi; }
+          const double d = xr - xm;
+          const double A = cl[n_azi + cc];
+          if (f_lo) { const double f = cl_[0] + d * (cl_[1] + d * (cl_[2] + d * cl_[3])); if (f < 0.0) s_lo -= A * f; }
+          if (f_hi) { const double f = ch_[0] + d * (ch_[1] + d * (ch_[2] + d * ch_[3])); if (f < 0.0) s_hi -= A * f; }
+        }
+      }
+    }
+    if (++m == NI) m = 0;
+  }
+  return make_double2(s_lo, s_hi);
+}
 
 template <int ATM, int CORR, int NLP>
 __global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5)
@@ -1435,7 +1507,7 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
       if (CORR == 2) ms_els = slab_ctx_mu_stencil(els, abb);
       const double Zlin = (CORR == 1 && ATM == 2) ? exp10(zst) : zst;
       const double Zlog = (CORR == 2 && ATM != 2) ? log10(zst) : zst;
-#pragma unroll
+#pragma unroll kS1Unroll
       for (int e = 0; e < kNEC; ++e) {
         double I_E;
         if (ATM == 1) I_E = bb_intensity(s_E[e] / zst, kT);
@@ -1480,6 +1552,9 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
             const double y1 = y[l + 1];
             neg = (y0 < 0.0 || y1 < 0.0);
             if (!neg && (B1 < 0.0 || B2 < 0.0)) {
+#if XB_NOINLINE_EXACT
+              neg = cubic_dips_below(y0, b, c, d, h);
+#else
               auto below = [&](double t) -> bool {
                 return t > 0.0 && t < h && (y0 + t * (b + t * (c + t * d))) < 0.0;
               };
@@ -1490,6 +1565,7 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
                   neg = below((-c - sq) * i3d) || below((-c + sq) * i3d);
                 }
               } else if (c != 0.0) neg = below(-b / (2.0 * c));
+#endif
             }
           }
           *flag_of(l) = neg ? 1 : 0;
@@ -1509,6 +1585,10 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
           double mm2 = slope(l0 - 2), mm1 = slope(l0 - 1), m0 = slope(l0), mp1 = slope(l0 + 1);
           double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
           double alpha = (NE != 0.0) ? ratio_scaled(fabs(mm1 - mm2), NE) : 0.0;
+          // with the leaf count known at compile time the block length is too: the loop is fully unrolled, which
+          // lets the slopes / weights of the next interval start while the positivity test of this one finishes
+          constexpr int kPerC = NLP ? (XB_S2_UNROLL ? XB_S2_UNROLL : (NLP - 1 + kBlk - 1) / kBlk) : 1;
+#pragma unroll kPerC
           for (int l = l0; l < l1; ++l) {
             const double mp2 = slope(l + 2);
             const double NE_next = fabs(mp2 - mp1) + fabs(m0 - mm1);
@@ -1538,10 +1618,17 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
     const bool any_flag = (fm0 | fm1 | fm2 | fm3) != 0ull;
     const unsigned row_bytes = kRow * 8u, wrap_bytes = (unsigned)NI * row_bytes;
     const unsigned coef0 = (unsigned)__cvta_generic_to_shared(s_coef) + (unsigned)lane * 8u;
+    // XB_ROLL_TILES: one copy of the tile body instead of kTilesPerWarp; the accumulators of the tiles a warp is
+    // not working on then live in local memory (2 loads + 2 stores per tile and image, L1 hits)
+#if XB_ROLL_TILES
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int t = 0; t < kTilesPerWarp; ++t) {
       const int tile = warp + t * kWarps;
       if (tile >= n_tiles) break;
+      double acc0 = acc[t][0], acc1 = acc[t][1];
       const int2 th = a.ws_thdr[slot * n_tiles + tile];        // (first interval, steps: a multiple of 4)
       const int ns = th.y;
       const double* bp = a.ws_tiles + ((slot * n_tiles + tile) * (long)a.tile_cap) * 32 + lane;
@@ -1556,12 +1643,18 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
           asm volatile("ld.shared.f64 %0, [%1];" : "=d"(av) : "r"(off));
           const double bv = (j == 0) ? b0 : (j == 1) ? b1 : (j == 2) ? b2 : b3;
           asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                       : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(av), "d"(bv));
+                       : "+d"(acc0), "+d"(acc1) : "d"(av), "d"(bv));
           off += row_bytes;
           if (off >= end) off -= wrap_bytes;
         }
       }
       if (any_flag) {
+#if XB_NOINLINE_FLAGGED
+        const double2 corr2 = flagged_tile_correction(
+            s_coef, s_PH, N_L, N_P, tile, th, lane, fm0, fm1, fm2, fm3, a.phases, a.ws_cells + ring * 2 * (long)a.n_azi,
+            a.n_azi, a.ws_tmeta + ((slot * n_tiles + tile) * (long)a.tile_cap) * kTilePhases);
+        const double s_lo = corr2.x, s_hi = corr2.y;
+#else
         // flagged (interval, energy) pairs of this tile, cell by cell: lane = (energy pair e, e + 4; phase of the tile)
         const int kk = lane & 7, eg = lane >> 3;
         const int k = tile * kTilePhases + kk;
@@ -1595,13 +1688,15 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
           }
           if (++m == NI) m = 0;
         }
+#endif
         // hand the corrections to the lanes that own D[energy][phase]: energy fe = lane / 4, phases 2 (lane % 4) + {0, 1}
         const int src = (fe & 3) * 8 + 2 * (lane & 3);
         const double a0 = __shfl_sync(0xffffffffu, s_lo, src), a1 = __shfl_sync(0xffffffffu, s_lo, src + 1);
         const double b0 = __shfl_sync(0xffffffffu, s_hi, src), b1 = __shfl_sync(0xffffffffu, s_hi, src + 1);
-        acc[t][0] += (fe < 4) ? a0 : b0;
-        acc[t][1] += (fe < 4) ? a1 : b1;
+        acc0 += (fe < 4) ? a0 : b0;
+        acc1 += (fe < 4) ? a1 : b1;
       }
+      acc[t][0] = acc0; acc[t][1] = acc1;
     }
   }
   // ---- ring/chunk contribution -> flux[q, e, k] (RED) or its slot of the partial sums (deterministic mode) ----
