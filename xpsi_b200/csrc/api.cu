@@ -703,6 +703,7 @@ struct xpsi_b200_pipeline {
   int else_slab_rows = 0, slab2_chunk = 0, slab2_ring = 0;
   Dev<double> att_base, att_power, corr, ws_slab2;
   int att_power_valid = 0, else_arrays_valid = 0, corr_valid = 0, else_temp_valid = 0;
+  int extras_B = 0;                  // batch size the per-batch extras on the device were uploaded for
   Dev<double> x_temp, x_area, x_radial, x_rsr, x_theta, x_phi, x_params, x_defl, x_calpha, x_maxd, x_cgamma,
       x_maxAlpha, x_grav, x_flux;
   Dev<int> x_nrings, x_status;
@@ -798,6 +799,10 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   const xpsi_b200_pipeline_config& c = p->cfg;
   const int M = c.n_members, C = c.n_components, Q = B * M;
   const size_t nflux = (size_t)Q * c.n_energies * c.n_phases;
+  // per-batch extras (attenuation powers, elsewhere / correction arrays, signal shifts) belong to ONE batch: a run
+  // with another batch size would read stale or uninitialised entries
+  if ((p->att_power_valid || p->else_arrays_valid || p->else_temp_valid || p->sig_shift_valid) && p->extras_B != B)
+    return fail(XPSI_B200_EINVAL, "the per-batch extras on the device were uploaded for a different batch size");
   CK(cudaEventRecord(p->ev[0], g_stream));
   CK(cudaMemsetAsync(p->flux.p, 0, nflux * sizeof(double), g_stream));
   CK(cudaMemsetAsync(p->status_q.p, 0, Q * sizeof(int), g_stream));
@@ -1198,6 +1203,8 @@ int xpsi_b200_pipeline_n_signals(xpsi_b200_pipeline* p) { return p ? 1 + (int)p-
 int xpsi_b200_pipeline_upload_signal_shifts(xpsi_b200_pipeline* p, int B, const double* shifts) {
   if (!p || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
   if (!shifts) { p->sig_shift_valid = 0; return 0; }
+  if (p->extras_B != B) { p->att_power_valid = 0; p->else_arrays_valid = 0; p->corr_valid = 0; p->else_temp_valid = 0; }
+  p->extras_B = B;
   const size_t S = 1 + p->more.size();
   CK(p->sig_shift.upload(shifts, (size_t)B * S));
   CK(p->sig_shifts_s.alloc((size_t)p->max_batch * p->cfg.n_components));
@@ -1245,6 +1252,8 @@ int xpsi_b200_pipeline_sweep_upload_signal_shifts(xpsi_b200_pipeline* p, long lo
 int xpsi_b200_pipeline_upload_extras(xpsi_b200_pipeline* p, int B, const xpsi_b200_batch_extras* h) {
   if (!p || !h || B < 1 || B > p->max_batch) return fail(XPSI_B200_EINVAL, "bad batch size");
   const xpsi_b200_pipeline_config& c = p->cfg;
+  if (p->extras_B != B) { p->att_power_valid = 0; p->else_arrays_valid = 0; p->corr_valid = 0; p->else_temp_valid = 0; p->sig_shift_valid = 0; }
+  p->extras_B = B;
   if (h->att_power) { CK(p->att_power.upload(h->att_power, B)); p->att_power_valid = 1; }
   if (p->ex.elsewhere) {
     const size_t n = p->ex.else_sqrt_num_cells, nr = p->ex.else_num_rays;
@@ -1438,6 +1447,7 @@ int xpsi_b200_pipeline_sweep_run(xpsi_b200_pipeline* p, long long first, long lo
       CK(d2d(p->e_hazi, s.hazi, o * M, B, M));
     }
     if (s.has_extra) CK(d2d(p->e_extra, s.extra, o * M * X, B, M * X));
+    p->extras_B = (int)B;
     if (s.has_att) { CK(d2d(p->att_power, s.att_power, o, B, 1)); p->att_power_valid = 1; }
     if (s.has_else) { CK(d2d(p->x_temp, s.else_temp, o, B, 1)); p->else_temp_valid = 1; }
     if (s.has_sig_shift) { const size_t S = 1 + p->more.size(); CK(d2d(p->sig_shift, s.sig_shift, o * S, B, S)); p->sig_shift_valid = 1; }
