@@ -10,6 +10,7 @@ sys.path.insert(0, ROOT)
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--blocks", type=int, default=6)
+ap.add_argument("--deterministic", action="store_true")
 a = ap.parse_args()
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -18,6 +19,8 @@ from xpsi_b200 import _lib, synthetic as syn  # noqa: E402
 
 w = bench.load_workload()
 pipe = bench.make_pipeline(w, a.batch)
+if a.deterministic:
+    pipe.set_deterministic(True)
 P = syn.m2_bench_thetas(0, a.batch * (a.blocks + 2))
 pipe.sweep_upload(syn.m2_spot_batch(pipe, P))
 pipe.sweep_run(0, a.batch * 2)

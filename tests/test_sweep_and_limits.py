@@ -135,6 +135,14 @@ def test_capability_limits_are_refused_loudly():
             g("maxDeflection"), g("cos_gammaArray"), g("energies"), g("leaves"), g("phases"), (), (), 1, 1, 0, 7]
     with pytest.raises(refused):
         integrate(*args)
+    # per-batch extras belong to the batch size they were uploaded for: evaluating another size is refused
+    # instead of reading stale attenuation powers
+    pipe = _pipeline(4)
+    pipe.set_extras(attenuation=np.exp(-0.3 * (0.2025 + 0.005 * np.arange(1500)) ** -2.5))
+    pipe.upload_extras(2, att_power=np.array([0.5, 0.7]))
+    pipe.eval_spots(syn.m2_spot_batch(pipe, P[:2]))
+    with pytest.raises(refused):
+        pipe.eval_spots(syn.m2_spot_batch(pipe, P))
 
 
 def test_deterministic_mode_is_bitwise_reproducible():
