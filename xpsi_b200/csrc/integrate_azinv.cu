@@ -857,6 +857,7 @@ __device__ __forceinline__ double* slab_ctx_carve(SlabCtx& c, double* sp, int N_
 // Rows of the ring's slab this chunk reaches: the (mu, energy-row) tile [nmu][rows_max] starting at the chunk's first
 // row is fetched by ONE TMA tensor copy (cp.async.bulk.tensor.2d) issued by thread 0 -- columns past the ring's slab
 // row are zero-filled by the copy engine and are never read (the chunk's row range already holds every stencil).
+template <int NT = kFluxThreads>
 __device__ __forceinline__ void slab_ctx_load(SlabCtx& c, const AtmTable& T, const CUtensorMap* tmap, long ring,
                                               int elo_ring, int2 chunk_rows, int rows_max, int tid,
                                               uint64_t* mbar) {
@@ -867,12 +868,12 @@ __device__ __forceinline__ void slab_ctx_load(SlabCtx& c, const AtmTable& T, con
     const int coords[2] = {c.elo_tab - elo_ring, (int)(ring * T.nmu)};
     cuda::ptx::cp_async_bulk_tensor(cuda::ptx::space_cluster, cuda::ptx::space_global, c.slab, tmap, coords, mbar);
   }
-  for (int m = tid; m < T.nmu; m += kFluxThreads) c.axMu[m] = T.mu[m];
+  for (int m = tid; m < T.nmu; m += NT) c.axMu[m] = T.mu[m];
   // tile rows past the end of the table get an unreachable axis value
-  for (int r = tid; r < c.nrows; r += kFluxThreads) c.axE[r] = (c.elo_tab + r < T.nE) ? T.logE[c.elo_tab + r] : 1.0e300;
+  for (int r = tid; r < c.nrows; r += NT) c.axE[r] = (c.elo_tab + r < T.nE) ? T.logE[c.elo_tab + r] : 1.0e300;
   // Lagrange denominators per base row: copied from the table's precomputed list
   const int nv = min(c.nrows, c.nE - c.elo_tab);                     // rows inside the table
-  for (int r = tid; r < 4 * (nv - 3); r += kFluxThreads) c.invden[r] = __ldg(T.E_invden + 4 * c.elo_tab + r);
+  for (int r = tid; r < 4 * (nv - 3); r += NT) c.invden[r] = __ldg(T.E_invden + 4 * c.elo_tab + r);
 }
 
 __device__ __forceinline__ void slab_ctx_finish(SlabCtx& c, const AtmTable& T, int tid) {     // after a barrier
@@ -1331,6 +1332,16 @@ constexpr int kRow = 33;     // doubles per leaf row of the coefficient plane: [
 #define XB_S1_UNROLL 8
 #endif
 constexpr int kS1Unroll = XB_S1_UNROLL;
+// threads per CTA and resident CTAs per SM of the tensor-core flux kernel (every stage is written for any multiple
+// of 32 threads: stage 1 strides over leaves, stage 2 deals kMmaThreads / 8 interval blocks per energy, stage 3 deals
+// the 8-phase tiles over the warps)
+#ifndef XB_MMA_THREADS
+#define XB_MMA_THREADS 128
+#endif
+#ifndef XB_MMA_CTAS
+#define XB_MMA_CTAS 5
+#endif
+constexpr int kMmaThreads = XB_MMA_THREADS, kMmaCtas = XB_MMA_CTAS;
 #ifndef XB_ROLL_TILES
 #define XB_ROLL_TILES 0
 #endif
@@ -1397,7 +1408,7 @@ __device__ __noinline__ double2 flagged_tile_correction(const double* s_coef, co
 }
 
 template <int ATM, int CORR, int NLP>
-__global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5)
+__global__ void __launch_bounds__(kMmaThreads, (CORR == 2) ? 3 : kMmaCtas)
 k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __grid_constant__ CUtensorMap tm_els) {
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
   const int i = blockIdx.x / n_chunks;
@@ -1460,15 +1471,15 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
     cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared,
                                          &s_mbar, bytes);
   }
-  if (ATM == 2) { hot.log_kT = log_kT; slab_ctx_load(hot, a.hot, &tm_hot, ring, elo_hot, cr_hot, a.slab_ne_max, tid, &s_mbar); }
-  if (CORR == 2) { els.log_kT = log_kT_c; slab_ctx_load(els, a.els, &tm_els, ring, elo_els, cr_els, a.slab_ne_max, tid, &s_mbar); }
+  if (ATM == 2) { hot.log_kT = log_kT; slab_ctx_load<kMmaThreads>(hot, a.hot, &tm_hot, ring, elo_hot, cr_hot, a.slab_ne_max, tid, &s_mbar); }
+  if (CORR == 2) { els.log_kT = log_kT_c; slab_ctx_load<kMmaThreads>(els, a.els, &tm_els, ring, elo_els, cr_els, a.slab_ne_max, tid, &s_mbar); }
   __syncthreads();
   if (ATM == 2) slab_ctx_finish(hot, a.hot, tid);
   if (CORR == 2) slab_ctx_finish(els, a.els, tid);
 
   const int interp_kind = a.phase_interp;
   const int lane = tid & 31, warp = tid >> 5;
-  constexpr int kWarps = kFluxThreads / 32, kTilesPerWarp = (kFluxThreads / kTilePhases + kWarps - 1) / kWarps;
+  constexpr int kWarps = kMmaThreads / 32, kTilesPerWarp = (kMmaThreads / kTilePhases + kWarps - 1) / kWarps;
   double acc[kTilesPerWarp][2];            // D fragments: energy lane / 4, phases 2 (lane % 4) + {0, 1} of the tile
 #pragma unroll
   for (int t = 0; t < kTilesPerWarp; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
@@ -1476,17 +1487,17 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
   for (int I = 0; I < n_img; ++I) {
     __syncthreads();
     const double* W = leaf_ptr(a.ws_leaf, ring, n_img_max, I, N_L);
-    for (int l = tid; l < N_L; l += kFluxThreads) s_PH[l] = W[l];
+    for (int l = tid; l < N_L; l += kMmaThreads) s_PH[l] = W[l];
     const bool pre_ok = tid < N_L;
     const double pre_geom = pre_ok ? W[3 * N_L + tid] : 0.0;
     const double pre_zst = pre_ok ? W[N_L + tid] : 1.0, pre_abb = pre_ok ? W[2 * N_L + tid] : 0.0;
     __syncthreads();
-    for (int l = tid; l < NI; l += kFluxThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
+    for (int l = tid; l < NI; l += kMmaThreads) s_aux[l] = 1.0 / (s_PH[l + 1] - s_PH[l]);
     if (tid < 4) s_fmask[tid] = 0ull;
     if ((ATM == 2 || CORR == 2) && I == 0)
       while (!cuda::ptx::mbarrier_try_wait_parity(&s_mbar, 0u, 2000u)) {}
     // ---- (1) leaf profile: thread = leaf ------------------------------------------------------------------
-    for (int lb = 0; lb < N_L; lb += kFluxThreads) {
+    for (int lb = 0; lb < N_L; lb += kMmaThreads) {
       const int l = lb + tid;
       const double geom = (lb == 0) ? pre_geom : ((l < N_L) ? W[3 * N_L + l] : 0.0);
       {
@@ -1521,7 +1532,7 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
     __syncthreads();
     // ---- (2) cubic pieces + positivity flags: thread = (energy, block of consecutive intervals) -------------
     {
-      constexpr int kBlk = kFluxThreads / kNEC;
+      constexpr int kBlk = kMmaThreads / kNEC;
       const int e = tid / kBlk, blk = tid - e * kBlk;
       const int per = (NI + kBlk - 1) / kBlk;
       const int l0 = blk * per, l1 = min(l0 + per, NI);
@@ -1873,7 +1884,7 @@ static cudaError_t launch_flux_mma_n(const AzinvArgs& a, dim3 grid, size_t smem,
                                      const CUtensorMap& tm_hot, const CUtensorMap& tm_els) {
   cudaError_t err = cudaFuncSetAttribute(k_azinv_flux_mma<ATM, CORR, NLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  k_azinv_flux_mma<ATM, CORR, NLP><<<grid, kFluxThreads, smem, stream>>>(a, tm_hot, tm_els);
+  k_azinv_flux_mma<ATM, CORR, NLP><<<grid, kMmaThreads, smem, stream>>>(a, tm_hot, tm_els);
   return cudaGetLastError();
 }
 
@@ -1885,7 +1896,11 @@ static cudaError_t launch_flux_mma(const AzinvArgs& a, dim3 grid, cudaStream_t s
   cudaError_t err;
   if (ATM == 2 && (err = encode_slab_map(&tm_hot, a.ws_slab, a, a.hot.nmu)) != cudaSuccess) return err;
   if (CORR == 2 && (err = encode_slab_map(&tm_els, a.ws_slab2, a, a.els.nmu)) != cudaSuccess) return err;
+#ifdef XB_PAD_SMEM
+  const size_t smem = flux_mma_smem_bytes(a, ATM, CORR) + XB_PAD_SMEM;       // occupancy experiment (dev/build_variants.sh)
+#else
   const size_t smem = flux_mma_smem_bytes(a, ATM, CORR);
+#endif
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   if (a.n_leaves == a.n_phases && a.n_leaves == 100) return launch_flux_mma_n<ATM, CORR, 100>(a, grid, smem, stream, tm_hot, tm_els);
   if (a.n_leaves == a.n_phases && a.n_leaves == 64) return launch_flux_mma_n<ATM, CORR, 64>(a, grid, smem, stream, tm_hot, tm_els);
