@@ -720,18 +720,35 @@ __global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
 // against the 16-point one and, where they disagree beyond 1e-13, the interval is bisected adaptively
 // towards the near-singular end (rays grazing the photon sphere: the integrand tends to 1/x there and the
 // deflection grows like -log(1 - b / b_ph); stars with R -> 3 r_g reach 6 pi and more).
+#ifndef XB_FAST_RAYS
+#define XB_FAST_RAYS 1
+#endif
+// p1 (MODE 0) / p0 (MODE 1) arrive as the reciprocal 1 / (R / r_s - 1) resp. 1 / (r_c / r_s - 1), formed once per ray:
+// one reciprocal square root and one division per node instead of a square root and three divisions
 template <int MODE>
 __device__ __forceinline__ void ray_integrand(double x, double p0, double p1, double* fd, double* fl) {
   const double o = 1.0 - x * x;
-  if (MODE == 0) {            // outDef / outLag (:75-90): p0 = sin^2 alpha, p1 = R / r_s
-    const double f = sqrt(1.0 - p0 + x * x * p0 * (2.0 - x * x - o * o / (p1 - 1.0)));
-    *fd = x / f;
-    *fl = x / (f + f * f);
-  } else {                    // inDef / inLag (:62-73): p0 = r_c / r_s
-    const double X = 1.0 / sqrt(2.0 - x * x - o * o / (p0 - 1.0));
+#if XB_FAST_RAYS
+  if (MODE == 0) {            // outDef / outLag (:75-90): p0 = sin^2 alpha, p1 = 1 / (R / r_s - 1)
+    const double r = rsqrt(1.0 - p0 + x * x * p0 * (2.0 - x * x - o * o * p1));      // 1 / f
+    *fd = x * r;
+    *fl = x * r * r / (r + 1.0);                                                     // x / (f + f^2)
+  } else {                    // inDef / inLag (:62-73): p0 = 1 / (r_c / r_s - 1)
+    const double X = rsqrt(2.0 - x * x - o * o * p0);
     *fd = X;
     *fl = X * X / (x + X);
   }
+#else
+  if (MODE == 0) {
+    const double f = sqrt(1.0 - p0 + x * x * p0 * (2.0 - x * x - o * o * p1));
+    *fd = x / f;
+    *fl = x / (f + f * f);
+  } else {
+    const double X = 1.0 / sqrt(2.0 - x * x - o * o * p0);
+    *fd = X;
+    *fl = X * X / (x + X);
+  }
+#endif
 }
 template <int N, int MODE>
 __device__ __forceinline__ void ray_panel(double lo, double hi, double p0, double p1, double* d, double* l) {
@@ -794,7 +811,7 @@ __device__ __forceinline__ void ray_integrals(double cos_alpha, double r_s, doub
   const bool guarded = (b > 0.95 * b_ph) && (b < 1.02 * b_ph);
   if (b <= b_ph) {
     double sd, sl;
-    ray_pair<0>(guarded, 0.0, 1.0, sas, 1.0 / u, &sd, &sl);
+    ray_pair<0>(guarded, 0.0, 1.0, sas, 1.0 / (1.0 / u - 1.0), &sd, &sl);
     *defl = sd * 2.0 * b * u;
     *lag = sl * 2.0 * b * b * u * r_s;
   } else {
@@ -806,13 +823,14 @@ __device__ __forceinline__ void ray_integrals(double cos_alpha, double r_s, doub
       if (wR != wR) wR = 0.0;
     }
     double d0, l0;                                   // integrals over [wR, 1]
-    ray_pair<1>(guarded, wR, 1.0, rc, 0.0, &d0, &l0);
+    const double irc = 1.0 / (rc - 1.0);
+    ray_pair<1>(guarded, wR, 1.0, irc, 0.0, &d0, &l0);
     if (alpha <= kHalfPi) {
       *defl = d0 * 2.0 * b / rc;
       *lag = l0 * 2.0 * b * b * r_s / rc;
     } else {
       double d1, l1;                                 // integrals over [0, 1]
-      ray_pair<1>(guarded, 0.0, 1.0, rc, 0.0, &d1, &l1);
+      ray_pair<1>(guarded, 0.0, 1.0, irc, 0.0, &d1, &l1);
       *defl = 2.0 * b * (2.0 * d1 - d0) / rc;
       *lag = 2.0 * b * b * r_s * (2.0 * l1 - l0) / rc;
       *lag += 2.0 * r_s * (1.0 / u - rc + log((1.0 / u - 1.0) / (rc - 1.0)));
