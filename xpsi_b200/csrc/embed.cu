@@ -1,8 +1,10 @@
-// GPU "embed": cell mesh of a circular hot spot and its rays, from model parameters.
+// GPU "embed": cell meshes of hot-region members and of the closed surface, and their rays, from model parameters.
 //
-// Replaces, for a simple circular superseding region away from the poles (the ST / ST-U
-// families: no omission, no ceding member), the per-parameter-vector producer of all
-// integrator inputs:
+// Replaces the per-parameter-vector producer of all integrator inputs for hot regions made of
+// circular members -- plain spots, superseding members with an omission hole, ceding members masked by their
+// superseding region (the two sharing the region's cell budget), members covering a rotational pole (polar
+// variant, cellmesh/polar_mesh.pyx) -- and for the closed equal-area mesh of Elsewhere / Everywhere
+// (cellmesh/global_mesh.pyx):
 //   xpsi/HotRegion.py:774-870  __construct_cellMesh -> mesh_tools.allocate_cells (:892-1000),
 //                              mesh.construct_spot_cellMesh (mesh.pyx:18-417)
 //   xpsi/HotRegion.py:903-951  __compute_rays -> rays.compute_rays (rays.pyx:249-390)
