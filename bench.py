@@ -344,6 +344,12 @@ def main_ours(args):
     mine = np.concatenate([np.arange((s * world + rank) * B, (s * world + rank + 1) * B) for s in range(n_steps_all)])
     pipe.sweep_upload(syn.m2_spot_batch(pipe, thetas_all[mine]))
     pipe.sweep_run(0, W * B)
+    if dist is not None:
+        # warm-up of the collective as well (same payload size, same stream): the first all_gather of a size
+        # pays NCCL's lazy channel set-up (~10 ms), which is not part of a steady-state step
+        with torch.cuda.stream(stream):
+            warm = torch.zeros(2 * K * B, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(torch.empty(world * warm.numel(), dtype=torch.float64, device=dev), warm)
     torch.cuda.synchronize()
     k0 = _lib.counters()[0]
     sampler = ClockSampler(local)
