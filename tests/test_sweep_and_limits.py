@@ -173,3 +173,29 @@ def test_deterministic_mode_is_bitwise_reproducible():
     pipe.set_deterministic(False)
     lnL_b, st_b = pipe.eval_spots(spots(P))
     assert np.allclose(lnL_b[ok], lnL_a[ok], rtol=1e-13)
+
+
+def test_chunks_handed_back_to_the_scalar_kernel_give_the_same_signal():
+    """The tensor-core flux kernel hands a (ring, energy chunk) back to the scalar kernel when GSL's Akima takes
+    different slopes on the two sides of a node (two exactly straight segments meeting: never for a physical
+    profile).  XPSI_B200_FORCE_REDO=1 hands *every* chunk back: the member signals must agree with the tensor-core
+    result to rounding -- no chunk lost, none counted twice."""
+    from xpsi_b200 import synthetic as syn
+    P = syn.m2_bench_thetas(0, 6)
+    pipe = _pipeline(8)
+    spots = syn.m2_spot_batch(pipe, P)
+    lnL_a, st_a = pipe.eval_spots(spots)
+    flux_a = pipe.fetch(6, folded=False, expected=False)[0]
+    os.environ["XPSI_B200_FORCE_REDO"] = "1"
+    try:
+        lnL_b, st_b = pipe.eval_spots(spots)
+        flux_b = pipe.fetch(6, folded=False, expected=False)[0]
+    finally:
+        del os.environ["XPSI_B200_FORCE_REDO"]
+    assert np.array_equal(st_a, st_b)
+    rel = np.abs(flux_a - flux_b).max() / np.abs(flux_a).max()
+    print("tensor-core vs handed-back (scalar kernel) member signals: max rel diff %.2e; lnL diff %.2e"
+          % (rel, np.nanmax(np.abs(lnL_a - lnL_b))))
+    assert rel < 1e-12
+    ok = st_a == 0
+    assert np.max(np.abs(lnL_a[ok] - lnL_b[ok])) < 1e-7

@@ -813,7 +813,12 @@ __global__ void __launch_bounds__(kMomThreads) k_azinv_tiles(AzinvArgs a) {
                    const int st = m + u_off - m_start;
                    if (st < next || st >= cap) { over = true; return; }
                    for (; next < st; ++next) put(next, 0.0, 0.0, 0.0, 0.0, 0);
-                   put(st, W0, W1, W2, W3, c0 | (c1 << 16));
+                   // moments of the Hermite basis on the interval (s = delta / h): what multiplies
+                   // (y_m, y_m+1, t_m, t_m+1) in sum_j A_j f(delta_j)
+                   const double ih = 1.0 / (s_PH[m + 1] - s_PH[m]);
+                   const double u2 = W2 * ih, u3 = W3 * (ih * ih);
+                   const double H01 = ih * (3.0 * u2 - 2.0 * u3);
+                   put(st, W0 - H01, H01, W1 - 2.0 * u2 + u3, u3 - u2, c0 | (c1 << 16));
                    next = st + 1;
                  });
     int ns = over ? cap + 1 : next;
@@ -983,7 +988,8 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
   if (CORR == 2) cr_els = reinterpret_cast<const int2*>(a.ws_chunk)[((long)a.Q * a.n_rings + ring) * n_chunks + chunk];
   const int elo_hot = (ATM == 2) ? ih[4] : 0, elo_els = (CORR == 2) ? ih[8] : 0;
   if (n_img == 0) return;
-  if (a.ws_tiles && ih[11] == 0) return;        // this ring's tiles fit: k_azinv_flux_mma integrates it
+  // this ring's tiles fit: k_azinv_flux_mma integrates it -- unless it handed this chunk back (degenerate Akima node)
+  if (a.ws_tiles && ih[11] == 0 && !(a.ws_redo && a.ws_redo[ring * n_chunks + chunk])) return;
   const double* dh = a.ws_hdr + ring * kDHdr;
   const int N_E = a.n_energies, N_L = NLP ? NLP : a.n_leaves, N_P = NLP ? NLP : a.n_phases;
   const long cell0 = ring * a.n_azi;
@@ -1318,39 +1324,35 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
 // where the spline is positive) enter the DMMA with that energy's row zeroed and are redone cell by cell by the
 // warp afterwards.  Rings with a tile that does not fit tile_cap steps are left to k_azinv_flux (ih[11]).
 // ---------------------------------------------------------------------------------------------------------
-#ifndef XB_S2_UNROLL
-#define XB_S2_UNROLL 1       // unroll factor of the stage-2 interval loop (0: the whole block of a thread)
-#endif
-constexpr int kRow = 33;     // doubles per leaf row of the coefficient plane: [8 energies][y, b, c, d] + one flag word
+// Node-form (Hermite) coefficient rows of the tensor-core flux kernel: per leaf [8 energies: value y][8 energies: node
+// slope t][flag word][pad].  The cubic on interval m is y_m h00 + y_{m+1} h01 + t_m h10 + t_{m+1} h11, so the A operand
+// of step m is (y_m, y_{m+1}, t_m, t_{m+1}) per energy -- two rows of 16 doubles instead of one row of 32 monomial
+// coefficients: the plane shrinks from 26.4 KB to 16 KB at 100 leaves and a sixth CTA fits on the SM.  Row stride 20
+// = 4 (mod 16): rows m and m + 1 of a fragment read fall on complementary banks (2 wavefronts, the minimum for 256
+// bytes), and the stage-2 accesses of 4 node blocks x 8 energies per warp cover every bank exactly twice.
+constexpr int kRowH = 20;
 
 
-// Build-time experiment switches of k_azinv_flux_mma (dev/build_variants.sh + dev/time_step.py time them side by side
-// on the GPU box).  Measured at batch 512 on the bench workload, flux stage (profiles/r02f_variants.txt): the kernel
-// answers to none of them by more than 2 % -- out-of-line rare paths -1.6 %, rolled tile loop +0.5 %, stage-1 unroll
-// 4 / 2 +0.8 %, stage-2 unroll 2 / full +2.7 % / +16 %, set-bit walk of the flagged intervals +3 %.
+// Build-time parameters of k_azinv_flux_mma (dev/build_variants.sh + dev/time_step.py time variants side by side on
+// the GPU box; profiles/r02f_variants.txt, r02j_variants.txt).  With the node-form rows the kernel needs 31 KB of
+// shared memory, so 7 CTAs fit an SM if they stay within 72 registers: that takes the rolled tile loop (the
+// accumulators of the tiles a warp is not working on live in local memory) and a stage-1 energy loop unrolled by 2.
 #ifndef XB_S1_UNROLL
-#define XB_S1_UNROLL 8
+#define XB_S1_UNROLL 2
 #endif
 constexpr int kS1Unroll = XB_S1_UNROLL;
-// threads per CTA and resident CTAs per SM of the tensor-core flux kernel (every stage is written for any multiple
-// of 32 threads: stage 1 strides over leaves, stage 2 deals kMmaThreads / 8 interval blocks per energy, stage 3 deals
-// the 8-phase tiles over the warps)
+#ifndef XB_ROLL_TILES
+#define XB_ROLL_TILES 1
+#endif
+// threads per CTA and resident CTAs per SM (every stage is written for any multiple of 32 threads: stage 1 strides
+// over leaves, stage 2 deals kMmaThreads / 8 node blocks per energy, stage 3 deals the 8-phase tiles over the warps)
 #ifndef XB_MMA_THREADS
 #define XB_MMA_THREADS 128
 #endif
 #ifndef XB_MMA_CTAS
-#define XB_MMA_CTAS 5
+#define XB_MMA_CTAS 7
 #endif
 constexpr int kMmaThreads = XB_MMA_THREADS, kMmaCtas = XB_MMA_CTAS;
-#ifndef XB_ROLL_TILES
-#define XB_ROLL_TILES 0
-#endif
-#ifndef XB_NOINLINE_EXACT
-#define XB_NOINLINE_EXACT 1
-#endif
-#ifndef XB_NOINLINE_FLAGGED
-#define XB_NOINLINE_FLAGGED 1
-#endif
 // exact test behind an inconclusive Bernstein test: does y0 + t (b + t (c + t d)) go below zero inside (0, h)?
 // Rare, and kept out of line: the flux kernel is large enough for instruction fetch to show in its stall reasons.
 __device__ __noinline__ bool cubic_dips_below(double y0, double b, double c, double d, double h) {
@@ -1368,7 +1370,8 @@ __device__ __noinline__ bool cubic_dips_below(double y0, double b, double c, dou
 }
 
 // cell-by-cell correction of one 8-phase tile for the (interval, energy) pairs whose cubic may dip below zero
-// (lane = (energy pair eg, eg + 4; phase kk of the tile)); out of line for the same reason
+// (lane = (energy pair eg, eg + 4; phase kk of the tile)); out of line for the same reason.  The monomial pieces are
+// rebuilt from the node form where they are needed.
 __device__ __noinline__ double2 flagged_tile_correction(const double* s_coef, const double* s_PH, int N_L, int N_P, int tile,
                                                          int2 th, int lane, unsigned long long fm0, unsigned long long fm1,
                                                          unsigned long long fm2, unsigned long long fm3,
@@ -1382,23 +1385,35 @@ __device__ __noinline__ double2 flagged_tile_correction(const double* s_coef, co
   int m = th.x;
   for (int s = 0; s < ns; ++s) {
     if (((m < 64 ? fm0 : m < 128 ? fm1 : m < 192 ? fm2 : fm3) >> (m & 63)) & 1ull) {     // N_L <= 256 (launcher)
-      const double* row = s_coef + (long)m * kRow;
-      const unsigned long long fw = *reinterpret_cast<const unsigned long long*>(row + 32);
+      const double* row = s_coef + (long)m * kRowH;
+      const unsigned long long fw = *reinterpret_cast<const unsigned long long*>(row + 16);
       const bool f_lo = (fw >> (8 * eg)) & 1ull, f_hi = (fw >> (8 * (eg + 4))) & 1ull;
       const int cells = mt[(long)s * kTilePhases];
       const int c_start = cells & 0xffff, c_end = cells >> 16;
       if ((f_lo || f_hi) && k < N_P) {
         const double xm = s_PH[m];
-        const double* cl_ = row + eg * 4;
-        const double* ch_ = row + (eg + 4) * 4;
+        const double ih = 1.0 / (s_PH[m + 1] - xm);
+        double yl = 0.0, bl = 0.0, cl2 = 0.0, dl = 0.0, yh = 0.0, bh = 0.0, ch2 = 0.0, dh2 = 0.0;
+        if (f_lo) {
+          const double y1 = row[kRowH + eg], t1 = row[kRowH + 8 + eg];
+          yl = row[eg]; bl = row[8 + eg];
+          const double sl = (y1 - yl) * ih;
+          cl2 = (3.0 * sl - 2.0 * bl - t1) * ih; dl = (bl + t1 - 2.0 * sl) * (ih * ih);
+        }
+        if (f_hi) {
+          const double y1 = row[kRowH + eg + 4], t1 = row[kRowH + 8 + eg + 4];
+          yh = row[eg + 4]; bh = row[8 + eg + 4];
+          const double sl = (y1 - yh) * ih;
+          ch2 = (3.0 * sl - 2.0 * bh - t1) * ih; dh2 = (bh + t1 - 2.0 * sl) * (ih * ih);
+        }
         for (int cc = c_start; cc < c_end; ++cc) {
           double xr = phk + cl[cc];
           if (xr > ph_last) { while (xr > ph_last) xr -= kTwoPi; }
           else if (xr < ph_first) { while (xr < ph_first) xr += kTwoPi; }
           const double d = xr - xm;
           const double A = cl[n_azi + cc];
-          if (f_lo) { const double f = cl_[0] + d * (cl_[1] + d * (cl_[2] + d * cl_[3])); if (f < 0.0) s_lo -= A * f; }
-          if (f_hi) { const double f = ch_[0] + d * (ch_[1] + d * (ch_[2] + d * ch_[3])); if (f < 0.0) s_hi -= A * f; }
+          if (f_lo) { const double f = yl + d * (bl + d * (cl2 + d * dl)); if (f < 0.0) s_lo -= A * f; }
+          if (f_hi) { const double f = yh + d * (bh + d * (ch2 + d * dh2)); if (f < 0.0) s_hi -= A * f; }
         }
       }
     }
@@ -1445,7 +1460,7 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
   SlabCtx hot, els;
   double* s_PH = sp; sp += N_L;
   double* s_aux = sp; sp += N_L;
-  double* s_coef = sp; sp += (long)N_L * kRow;       // [leaf][energy][y b c d], flag bytes in the 33rd double
+  double* s_coef = sp; sp += (long)N_L * kRowH;      // [leaf][y x 8 | t x 8 | flag bytes | pad]
   sp = smem + (((sp - smem) + 15) & ~15l);
   if (ATM == 2) sp = slab_ctx_carve_slab(hot, sp, a.slab_ne_max, a.hot.nmu);
   if (CORR == 2) sp = slab_ctx_carve_slab(els, sp, a.slab_ne_max, a.els.nmu);
@@ -1505,10 +1520,10 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
         if ((tid & 31) == 0 && (l >> 5) < kLitWords) s_litmask[l >> 5] = lit;
       }
       if (l >= N_L) continue;
-      double* row = s_coef + (long)l * kRow;
+      double* row = s_coef + (long)l * kRowH;
       if (geom == 0.0) {
 #pragma unroll
-        for (int e = 0; e < kNEC; ++e) row[e * 4] = 0.0;
+        for (int e = 0; e < kNEC; e += 2) *reinterpret_cast<double2*>(row + e) = make_double2(0.0, 0.0);
         continue;
       }
       const double zst = (lb == 0) ? pre_zst : W[N_L + l];
@@ -1526,100 +1541,88 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
         double corr = 0.0;
         if (CORR == 1) corr = bb_intensity(s_E[e] / Zlin, kT_c) * norm_c;
         else if (CORR == 2) corr = slab_ctx_eval(els, s_logE[e] - Zlog - log_kT_c, ms_els) * norm_c;
-        row[e * 4] = (I_E * norm - corr) * geom;
+        row[e] = (I_E * norm - corr) * geom;
       }
     }
     __syncthreads();
-    // ---- (2) cubic pieces + positivity flags: thread = (energy, block of consecutive intervals) -------------
+    // ---- (2) node slopes + positivity flags: thread = (block of consecutive nodes, energy), energy fastest -----
+    // Akima and Steffen are Hermite interpolants: the piece on interval l is fixed by (y_l, y_l+1) and the node
+    // slopes (t_l, t_l+1).  GSL's Akima takes a different slope on the two sides of a node in one degenerate case
+    // (gsl akima.c: interval l has NE != 0, interval l + 1 has NE == 0 and the two interval slopes differ -- two
+    // exactly straight segments meeting at the node); such a chunk is handed to the scalar kernel, which keeps
+    // per-interval pieces (ws_redo).
+    int irregular = a.force_redo;            // test hook: hand every chunk back (exercises the ws_redo plumbing)
     {
       constexpr int kBlk = kMmaThreads / kNEC;
-      const int e = tid / kBlk, blk = tid - e * kBlk;
-      const int per = (NI + kBlk - 1) / kBlk;
-      const int l0 = blk * per, l1 = min(l0 + per, NI);
+      const int e = tid & (kNEC - 1), blk = tid / kNEC;
+      const int per = (N_L + kBlk - 1) / kBlk;
+      const int l0 = blk * per, l1 = min(l0 + per, N_L);           // nodes [l0, l1), intervals [l0, min(l1, NI))
       bool dark = (l0 < l1 && N_L <= 32 * kLitWords);
-      for (int l = l0 - 2; dark && l <= l1 + 2; ++l) {
+      for (int l = l0 - 2; dark && l <= l1 + 3; ++l) {
         int lw = l;
         if (lw < 0) lw += NI; else if (lw > NI) lw -= NI;
         if ((s_litmask[lw >> 5] >> (lw & 31)) & 1u) dark = false;
       }
-      auto flag_of = [&](int l) -> unsigned char* { return reinterpret_cast<unsigned char*>(s_coef + (long)l * kRow + 32) + e; };
+      double* col = s_coef + e;                                    // y at [l * kRowH], t at [l * kRowH + 8]
+      auto flag_of = [&](int l) -> unsigned char* { return reinterpret_cast<unsigned char*>(s_coef + (long)l * kRowH + 16) + e; };
       if (dark) {
-        for (int l = l0; l < l1; ++l) {
-          double* c = s_coef + (long)l * kRow + e * 4;
-          c[1] = 0.0; c[2] = 0.0; c[3] = 0.0;
-          *flag_of(l) = 0;
-        }
+        for (int l = l0; l < l1; ++l) { col[(long)l * kRowH + 8] = 0.0; *flag_of(l) = 0; }
       } else if (l0 < l1) {
-        const View y{s_coef + e * 4, kRow};
-        auto emit = [&](int l, double b, double c, double d) {
-          double* cf = s_coef + (long)l * kRow + e * 4;
-          const double y0 = cf[0];
-          cf[1] = b; cf[2] = c; cf[3] = d;
+        const View y{col, kRowH};
+        // interval l - 1 is complete once the slope of node l is known
+        auto finish = [&](int li, double t0, double t1) {
           bool neg = false;
           if (CORR == 0) {
-            const double h = s_PH[l + 1] - s_PH[l];
-            const double B1 = y0 + b * h * (1.0 / 3.0);
-            const double B2 = y0 + h * ((2.0 / 3.0) * b + c * h * (1.0 / 3.0));
-            const double y1 = y[l + 1];
+            const double y0 = y[li], y1 = y[li + 1];
+            const double h = s_PH[li + 1] - s_PH[li];
+            const double B1 = y0 + t0 * h * (1.0 / 3.0);
+            const double B2 = y1 - t1 * h * (1.0 / 3.0);
             neg = (y0 < 0.0 || y1 < 0.0);
             if (!neg && (B1 < 0.0 || B2 < 0.0)) {
-#if XB_NOINLINE_EXACT
-              neg = cubic_dips_below(y0, b, c, d, h);
-#else
-              auto below = [&](double t) -> bool {
-                return t > 0.0 && t < h && (y0 + t * (b + t * (c + t * d))) < 0.0;
-              };
-              if (d != 0.0) {
-                const double disc = c * c - 3.0 * b * d;
-                if (disc >= 0.0) {
-                  const double sq = sqrt(disc), i3d = 1.0 / (3.0 * d);
-                  neg = below((-c - sq) * i3d) || below((-c + sq) * i3d);
-                }
-              } else if (c != 0.0) neg = below(-b / (2.0 * c));
-#endif
+              const double ih = s_aux[li], sl = (y1 - y0) * ih;
+              neg = cubic_dips_below(y0, t0, (3.0 * sl - 2.0 * t0 - t1) * ih, (t0 + t1 - 2.0 * sl) * (ih * ih), h);
             }
           }
-          *flag_of(l) = neg ? 1 : 0;
-          if (neg) atomicOr(&s_fmask[l >> 6], 1ull << (l & 63));
+          *flag_of(li) = neg ? 1 : 0;
+          if (neg) atomicOr(&s_fmask[li >> 6], 1ull << (li & 63));
         };
+        const int l_end = min(l1, NI);                              // last node whose slope this thread needs
         if (interp_kind == kSteffen) {
-          for (int l = l0; l < l1; ++l) {
-            double b, c, d;
-            steffen_coeffs(s_PH, y, N_L, l, &b, &c, &d);
-            emit(l, b, c, d);
+          double t_prev = 0.0;
+          for (int l = l0; l <= l_end; ++l) {
+            const double t = steffen_node_slope(s_PH, y, N_L, l);
+            if (l > l0) finish(l - 1, t_prev, t);
+            if (l < l1) col[(long)l * kRowH + 8] = t;
+            t_prev = t;
           }
         } else {
           auto slope = [&](int ii) -> double {
             if (ii < 0) ii += NI; else if (ii > N_L - 2) ii -= NI;
             return (y[ii + 1] - y[ii]) * s_aux[ii];
           };
-          double mm2 = slope(l0 - 2), mm1 = slope(l0 - 1), m0 = slope(l0), mp1 = slope(l0 + 1);
-          double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
-          double alpha = (NE != 0.0) ? ratio_scaled(fabs(mm1 - mm2), NE) : 0.0;
-          // with the leaf count known at compile time the block length is too: the loop is fully unrolled, which
-          // lets the slopes / weights of the next interval start while the positivity test of this one finishes
-          constexpr int kPerC = NLP ? (XB_S2_UNROLL ? XB_S2_UNROLL : (NLP - 1 + kBlk - 1) / kBlk) : 1;
-#pragma unroll kPerC
-          for (int l = l0; l < l1; ++l) {
-            const double mp2 = slope(l + 2);
-            const double NE_next = fabs(mp2 - mp1) + fabs(m0 - mm1);
-            const double alpha1 = (NE_next != 0.0) ? ratio_scaled(fabs(m0 - mm1), NE_next) : 0.0;
-            double b, c, d;
-            if (NE == 0.0) { b = m0; c = 0.0; d = 0.0; }
-            else {
-              const double tL = (NE_next == 0.0) ? m0 : (1.0 - alpha1) * m0 + alpha1 * mp1;
-              const double ihh = s_aux[l];
-              b = (1.0 - alpha) * mm1 + alpha * m0;
-              c = (3.0 * m0 - 2.0 * b - tL) * ihh;
-              d = (b + tL - 2.0 * m0) * (ihh * ihh);
+          double mm2 = slope(l0 - 2), mm1 = slope(l0 - 1), m0 = slope(l0);
+          double t_prev = 0.0, NE_prev = 0.0;
+          for (int l = l0; l <= l_end; ++l) {
+            const double mp1 = slope(l + 1);
+            const double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
+            const double alpha = (NE != 0.0) ? ratio_scaled(fabs(mm1 - mm2), NE) : 0.0;
+            const double t = (NE == 0.0) ? m0 : (1.0 - alpha) * mm1 + alpha * m0;      // gsl: b of interval l
+            if (l > l0) {
+              if (NE_prev != 0.0 && NE == 0.0 && mm1 != m0) irregular = 1;
+              finish(l - 1, t_prev, t);
             }
-            emit(l, b, c, d);
-            mm2 = mm1; mm1 = m0; m0 = mp1; mp1 = mp2; NE = NE_next; alpha = alpha1;
+            if (l < l1) col[(long)l * kRowH + 8] = t;
+            t_prev = t; NE_prev = NE;
+            mm2 = mm1; mm1 = m0; m0 = mp1;
           }
         }
       }
     }
-    __syncthreads();
+    if (__syncthreads_or(irregular)) {
+      // nothing of this chunk has left the CTA yet (the accumulators are written after the last image)
+      if (tid == 0) a.ws_redo[ring * n_chunks + chunk] = 1;
+      return;
+    }
     // ---- (3) tiles x cubic pieces on the tensor cores ------------------------------------------------------
     // Every interval enters with its true cubic (no masking in the loop); where a cubic may dip below zero the
     // cells on its negative part are taken out again afterwards: sum_j A_j max(f, 0) = sum_j A_j f - sum_{f<0} A_j f.
@@ -1627,8 +1630,10 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
     const int fe = lane >> 2;                                  // energy row of this lane's A element / D fragment
     const unsigned long long fm0 = s_fmask[0], fm1 = s_fmask[1], fm2 = s_fmask[2], fm3 = s_fmask[3];
     const bool any_flag = (fm0 | fm1 | fm2 | fm3) != 0ull;
-    const unsigned row_bytes = kRow * 8u, wrap_bytes = (unsigned)NI * row_bytes;
-    const unsigned coef0 = (unsigned)__cvta_generic_to_shared(s_coef) + (unsigned)lane * 8u;
+    // A fragment of step m: lane (energy fe = lane / 4, p = lane % 4) reads y_m, y_m+1, t_m, t_m+1 for p = 0..3
+    const unsigned row_bytes = kRowH * 8u, wrap_bytes = (unsigned)NI * row_bytes;
+    const unsigned coef0 = (unsigned)__cvta_generic_to_shared(s_coef) +
+                           (unsigned)(((lane & 1) * kRowH + ((lane >> 1) & 1) * 8 + fe) * 8);
     // XB_ROLL_TILES: one copy of the tile body instead of kTilesPerWarp; the accumulators of the tiles a warp is
     // not working on then live in local memory (2 loads + 2 stores per tile and image, L1 hits)
 #if XB_ROLL_TILES
@@ -1660,46 +1665,10 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
         }
       }
       if (any_flag) {
-#if XB_NOINLINE_FLAGGED
         const double2 corr2 = flagged_tile_correction(
             s_coef, s_PH, N_L, N_P, tile, th, lane, fm0, fm1, fm2, fm3, a.phases, a.ws_cells + ring * 2 * (long)a.n_azi,
             a.n_azi, a.ws_tmeta + ((slot * n_tiles + tile) * (long)a.tile_cap) * kTilePhases);
         const double s_lo = corr2.x, s_hi = corr2.y;
-#else
-        // flagged (interval, energy) pairs of this tile, cell by cell: lane = (energy pair e, e + 4; phase of the tile)
-        const int kk = lane & 7, eg = lane >> 3;
-        const int k = tile * kTilePhases + kk;
-        const double phk = (k < N_P) ? a.phases[k] : 0.0;
-        const double ph_first = s_PH[0], ph_last = s_PH[N_L - 1];
-        const double* cl = a.ws_cells + ring * 2 * (long)a.n_azi;
-        const int* mt = a.ws_tmeta + ((slot * n_tiles + tile) * (long)a.tile_cap) * kTilePhases + kk;
-        double s_lo = 0.0, s_hi = 0.0;
-        int m = th.x;
-        for (int s = 0; s < ns; ++s) {
-          if (((m < 64 ? fm0 : m < 128 ? fm1 : m < 192 ? fm2 : fm3) >> (m & 63)) & 1ull) {     // N_L <= 256 (launcher)
-            const double* row = s_coef + (long)m * kRow;
-            const unsigned long long fw = *reinterpret_cast<const unsigned long long*>(row + 32);
-            const bool f_lo = (fw >> (8 * eg)) & 1ull, f_hi = (fw >> (8 * (eg + 4))) & 1ull;
-            const int cells = mt[(long)s * kTilePhases];
-            const int c_start = cells & 0xffff, c_end = cells >> 16;
-            if ((f_lo || f_hi) && k < N_P) {
-              const double xm = s_PH[m];
-              const double* cl_ = row + eg * 4;
-              const double* ch_ = row + (eg + 4) * 4;
-              for (int cc = c_start; cc < c_end; ++cc) {
-                double xr = phk + cl[cc];
-                if (xr > ph_last) { while (xr > ph_last) xr -= kTwoPi; }
-                else if (xr < ph_first) { while (xr < ph_first) xr += kTwoPi; }
-                const double d = xr - xm;
-                const double A = cl[a.n_azi + cc];
-                if (f_lo) { const double f = cl_[0] + d * (cl_[1] + d * (cl_[2] + d * cl_[3])); if (f < 0.0) s_lo -= A * f; }
-                if (f_hi) { const double f = ch_[0] + d * (ch_[1] + d * (ch_[2] + d * ch_[3])); if (f < 0.0) s_hi -= A * f; }
-              }
-            }
-          }
-          if (++m == NI) m = 0;
-        }
-#endif
         // hand the corrections to the lanes that own D[energy][phase]: energy fe = lane / 4, phases 2 (lane % 4) + {0, 1}
         const int src = (fe & 3) * 8 + 2 * (lane & 3);
         const double a0 = __shfl_sync(0xffffffffu, s_lo, src), a1 = __shfl_sync(0xffffffffu, s_lo, src + 1);
@@ -1872,7 +1841,7 @@ static cudaError_t launch_flux_n(const AzinvArgs& a, dim3 grid, size_t smem, cud
 }
 
 static size_t flux_mma_smem_bytes(const AzinvArgs& a, int atm, int corr) {
-  size_t d = 2ul * a.n_leaves + (size_t)a.n_leaves * kRow;                     // phases, 1/h, coefficient rows
+  size_t d = 2ul * a.n_leaves + (size_t)a.n_leaves * kRowH;                    // phases, 1/h, node-form rows
   d = (d + 15) & ~15ul;
   if (atm == 2) d += 5ul * a.slab_ne_max + ((a.hot.nmu + 1) & ~1) + (((size_t)a.hot.nmu * a.slab_ne_max + 15) & ~15ul);
   if (corr == 2) d += 5ul * a.slab_ne_max + ((a.els.nmu + 1) & ~1) + (((size_t)a.els.nmu * a.slab_ne_max + 15) & ~15ul);
@@ -1966,7 +1935,12 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
                      (a.tile_cap & 3) || a.n_leaves > 256 || a.n_azi > 0xffff)) {
     a.ws_tiles = nullptr;
   }
+  if (a.ws_tiles && !a.ws_redo) a.ws_tiles = nullptr;
   if (a.ws_tiles) a.ws_mom = nullptr;       // rings whose tiles overflow walk their cells inside the scalar kernel
+  if (a.ws_tiles) {
+    cudaError_t em = cudaMemsetAsync(a.ws_redo, 0, (size_t)a.Q * a.n_rings * n_chunks * sizeof(int), stream);
+    if (em != cudaSuccess) return em;
+  }
   if (a.ws_tiles) {
     const size_t msm = (2ul * a.n_azi + a.n_leaves) * sizeof(double) + 2ul * a.n_leaves;
     k_azinv_tiles<<<ggrid, kMomThreads, msm, stream>>>(a);

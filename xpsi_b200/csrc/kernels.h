@@ -62,9 +62,12 @@ struct AzinvArgs {
                                      //   RI (ring,image) pairs reaching the phase stage, K radiating cells over RI
   // optional (instead of ws_mom): the same interval moments as dense per-(image, 8-phase tile) B operands of the
   // tensor-core accumulation stage (azinv_tile_sizes): ws_tiles [slot][tile][tile_cap][32] doubles (lane = phase-in-
-  // tile * 4 + moment order), ws_tmeta [slot][tile][tile_cap][8] ints (cell range of each phase in that interval),
+  // tile * 4 + Hermite-basis moment H00, H01, H10, H11), ws_tmeta [slot][tile][tile_cap][8] ints (cell range of each phase in that interval),
   // ws_thdr [slot][tile] = (first interval, steps or -1 when the tile needs more than tile_cap steps)
   double* ws_tiles; int* ws_tmeta; int2* ws_thdr; int tile_cap;
+  int* ws_redo;                      // with ws_tiles: [Q][n_rings][n_chunks], set by the tensor-core kernel for a chunk it
+                                     // hands back to the scalar kernel (zeroed by the launcher)
+  int force_redo;                    // test hook (XPSI_B200_FORCE_REDO=1): every chunk is handed back
   // optional: deterministic two-stage ring reduction.  Every (ring, energy chunk) CTA stores its sum into
   // flux_part [Q][n_rings][N_E][N_P] and k_azinv_reduce_rings adds the lit rings in index order (no atomics)
   double* flux_part;
