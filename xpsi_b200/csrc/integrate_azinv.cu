@@ -1346,6 +1346,9 @@ constexpr int kS1Unroll = XB_S1_UNROLL;
 #endif
 // threads per CTA and resident CTAs per SM (every stage is written for any multiple of 32 threads: stage 1 strides
 // over leaves, stage 2 deals kMmaThreads / 8 node blocks per energy, stage 3 deals the 8-phase tiles over the warps)
+#ifndef XB_FLAG_BITWALK
+#define XB_FLAG_BITWALK 1    // flagged-interval correction walks the set bits of the mask instead of every step of the tile
+#endif
 #ifndef XB_MMA_THREADS
 #define XB_MMA_THREADS 128
 #endif
@@ -1382,9 +1385,23 @@ __device__ __noinline__ double2 flagged_tile_correction(const double* s_coef, co
   const double ph_first = s_PH[0], ph_last = s_PH[N_L - 1];
   mt += kk;
   double s_lo = 0.0, s_hi = 0.0;
+#if XB_FLAG_BITWALK
+  // the flagged intervals are few: visit the set bits (warp-uniform) instead of testing every step of the tile
+#pragma unroll 1
+  for (int w = 0; w < 4; ++w) {
+    unsigned long long bits = (w == 0) ? fm0 : (w == 1) ? fm1 : (w == 2) ? fm2 : fm3;
+    while (bits) {
+      const int m = w * 64 + __ffsll((long long)bits) - 1;
+      bits &= bits - 1ull;
+      int s = m - th.x;
+      if (s < 0) s += NI;
+      if (s >= ns) continue;
+      {
+#else
   int m = th.x;
   for (int s = 0; s < ns; ++s) {
     if (((m < 64 ? fm0 : m < 128 ? fm1 : m < 192 ? fm2 : fm3) >> (m & 63)) & 1ull) {     // N_L <= 256 (launcher)
+#endif
       const double* row = s_coef + (long)m * kRowH;
       const unsigned long long fw = *reinterpret_cast<const unsigned long long*>(row + 16);
       const bool f_lo = (fw >> (8 * eg)) & 1ull, f_hi = (fw >> (8 * (eg + 4))) & 1ull;
@@ -1417,8 +1434,13 @@ __device__ __noinline__ double2 flagged_tile_correction(const double* s_coef, co
         }
       }
     }
+#if XB_FLAG_BITWALK
+    }
+  }
+#else
     if (++m == NI) m = 0;
   }
+#endif
   return make_double2(s_lo, s_hi);
 }
 
