@@ -684,7 +684,7 @@ struct xpsi_b200_pipeline {
   Dev<double> flux, xin, folded, chan_lnL, expected, lnL;
   Dev<int> chan_status, status_q, status;
   Dev<unsigned long long> work;
-  Dev<double> ws_leaf, ws_hdr, ws_slab, ws_cells, ws_tiles, flux_part; Dev<int> ws_ihdr, ws_tmeta, ws_redo; Dev<int2> ws_thdr;
+  Dev<double> ws_leaf, ws_hdr, ws_slab, ws_cells, ws_tiles, flux_part; Dev<int> ws_ihdr, ws_tmeta, ws_redo, ws_ovf; Dev<int2> ws_thdr;
   int tile_cap = 0;
   int deterministic = 0;             // ring sums by a two-stage ordered reduction instead of fp64 atomics
   // embed inputs / scratch
@@ -883,7 +883,7 @@ int pipeline_run(xpsi_b200_pipeline* p, int B) {
   a.flux = p->flux.p; a.status = p->status_q.p;
   a.ws_leaf = p->ws_leaf.p; a.ws_hdr = p->ws_hdr.p; a.ws_ihdr = p->ws_ihdr.p; a.ws_slab = p->ws_slab.p;
   a.ws_tiles = p->ws_tiles.p; a.ws_tmeta = p->ws_tmeta.p; a.ws_thdr = p->ws_thdr.p; a.tile_cap = p->tile_cap;
-  a.ws_redo = p->ws_redo.p;
+  a.ws_redo = p->ws_redo.p; a.ws_ovf = p->ws_ovf.p;
   { const char* fr = getenv("XPSI_B200_FORCE_REDO"); a.force_redo = (fr && fr[0] == '1') ? 1 : 0; }
   a.ws_cells = p->ws_cells.p;
   a.flux_part = p->deterministic ? p->flux_part.p : nullptr;
@@ -1086,6 +1086,7 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
     xb::azinv_tile_sizes(w, &td, &tm, &tq);
     ok(p->ws_tiles.alloc(td)); ok(p->ws_tmeta.alloc(tm)); ok(p->ws_thdr.alloc(tq));
     ok(p->ws_redo.alloc(Q * c.max_rings * (size_t)((c.n_energies + 7) / 8)));
+    ok(p->ws_ovf.alloc(1 + 2 * Q * c.max_rings));
     ok(p->ws_cells.alloc(Q * c.max_rings * 2 * (size_t)c.max_azi));
     p->tile_cap = w.tile_cap;
   }

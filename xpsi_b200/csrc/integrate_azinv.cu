@@ -832,7 +832,13 @@ __global__ void __launch_bounds__(kMomThreads) k_azinv_tiles(AzinvArgs a) {
     }
   }
   __syncthreads();
-  if (tid == 0) ih[11] = s_over;       // 1: some tile of this ring overflowed -> the ring goes to the scalar flux kernel
+  if (tid == 0) {
+    ih[11] = s_over;       // 1: some tile of this ring overflowed -> the ring goes to the scalar flux kernel
+    if (s_over && a.ws_ovf) {            // ... through the compact list the scalar kernel strides over
+      a.ws_ovf[1 + a.Q * a.n_rings + ring] = 1;
+      a.ws_ovf[1 + atomicAdd(a.ws_ovf, 1)] = (int)ring;
+    }
+  }
 }
 
 // ===========================================================================
@@ -970,15 +976,14 @@ __device__ __forceinline__ double ratio_scaled(double a, double s) {
 // NLP: 0, or the compile-time value of n_leaves = n_phases (common grids get instantiations whose shared-memory
 // and workspace offsets are immediates instead of per-access integer arithmetic)
 template <int ATM, int CORR, int BEAM, int CUBIC, int NLP>
-__global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5)
-k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __grid_constant__ CUtensorMap tm_els) {
+__device__ __forceinline__ void azinv_flux_body(const AzinvArgs& a, const CUtensorMap* tm_hot, const CUtensorMap* tm_els,
+                                                const int i, const int chunk, const int q, int* s_mbar_live) {
   const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
-  const int i = blockIdx.x / n_chunks;
-  const int chunk = blockIdx.x - i * n_chunks;
-  const int q = blockIdx.y;
   const int tid = threadIdx.x;
   const long ring = (long)q * a.n_rings + i;
   const int* ih = a.ws_ihdr + ring * kIHdr;
+  // chunk handed back by the tensor-core kernel (degenerate Akima node)?  Requested with the headers
+  const int redo = (a.ws_tiles && a.ws_redo) ? a.ws_redo[ring * n_chunks + chunk] : 0;
   // everything the set-up needs from the headers is requested at once (one L2 round trip instead of a chain:
   // the loads behind the early exits would otherwise wait for the ones in front of them)
   const int n_img = ih[0];
@@ -989,7 +994,7 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
   const int elo_hot = (ATM == 2) ? ih[4] : 0, elo_els = (CORR == 2) ? ih[8] : 0;
   if (n_img == 0) return;
   // this ring's tiles fit: k_azinv_flux_mma integrates it -- unless it handed this chunk back (degenerate Akima node)
-  if (a.ws_tiles && ih[11] == 0 && !(a.ws_redo && a.ws_redo[ring * n_chunks + chunk])) return;
+  if (a.ws_tiles && ih[11] == 0 && !redo) return;
   const double* dh = a.ws_hdr + ring * kDHdr;
   const int N_E = a.n_energies, N_L = NLP ? NLP : a.n_leaves, N_P = NLP ? NLP : a.n_phases;
   const long cell0 = ring * a.n_azi;
@@ -1044,6 +1049,9 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
     return;
   }
   if ((ATM == 2 || CORR == 2) && tid == 0) {
+    // list mode runs the body several times per CTA: the barrier of the previous work item is invalidated first
+    if (*s_mbar_live) asm volatile("mbarrier.inval.shared.b64 [%0];" :: "r"((unsigned)__cvta_generic_to_shared(&s_mbar)) : "memory");
+    *s_mbar_live = 1;
     cuda::ptx::mbarrier_init(&s_mbar, 1);
     cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
     const unsigned bytes = (unsigned)(((ATM == 2) ? a.hot.nmu : 0) + ((CORR == 2) ? a.els.nmu : 0)) *
@@ -1053,11 +1061,11 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
   }
   if (ATM == 2) {
     hot.log_kT = log_kT;
-    slab_ctx_load(hot, a.hot, &tm_hot, ring, elo_hot, cr_hot, a.slab_ne_max, tid, &s_mbar);
+    slab_ctx_load(hot, a.hot, tm_hot, ring, elo_hot, cr_hot, a.slab_ne_max, tid, &s_mbar);
   }
   if (CORR == 2) {
     els.log_kT = log_kT_c;
-    slab_ctx_load(els, a.els, &tm_els, ring, elo_els, cr_els, a.slab_ne_max, tid, &s_mbar);
+    slab_ctx_load(els, a.els, tm_els, ring, elo_els, cr_els, a.slab_ne_max, tid, &s_mbar);
   }
   __syncthreads();
   if (ATM == 2) slab_ctx_finish(hot, a.hot, tid);
@@ -1308,6 +1316,32 @@ k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __gr
       for (int g = 0; g < kNEC; ++g)
         if (g < ne && acc[g] != 0.0) atomicAdd(flux_q + (long)(e0 + g) * N_P + k, acc[g]);
     }
+  }
+}
+
+
+// Grid: (ring x energy chunk, member instance) -- or, with a.ovf_list_mode, (energy chunk, G) CTAs that stride over
+// the compact list of rings the tensor-core kernel does not cover (tiles overflowed, or a chunk was handed back): the
+// list is short (about 1 % of the rings), and a million CTAs that only find "nothing to do" cost 1.3-1.7 ms.
+template <int ATM, int CORR, int BEAM, int CUBIC, int NLP>
+__global__ void __launch_bounds__(kFluxThreads, (CORR == 2) ? 3 : 5)
+k_azinv_flux(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const __grid_constant__ CUtensorMap tm_els) {
+  __shared__ int s_mbar_live;
+  if (threadIdx.x == 0) s_mbar_live = 0;
+  if (a.ovf_list_mode) {
+    const int cnt = a.ws_ovf[0];
+    for (int k = blockIdx.y; k < cnt; k += gridDim.y) {
+      const int ring = a.ws_ovf[1 + k];
+      __syncthreads();                       // the previous work item is done with shared memory (and s_mbar_live is visible)
+      azinv_flux_body<ATM, CORR, BEAM, CUBIC, NLP>(a, &tm_hot, &tm_els, ring % a.n_rings, (int)blockIdx.x, ring / a.n_rings,
+                                                   &s_mbar_live);
+    }
+  } else {
+    const int n_chunks = (a.n_energies + kNEC - 1) / kNEC;
+    const int i = blockIdx.x / n_chunks;
+    __syncthreads();
+    azinv_flux_body<ATM, CORR, BEAM, CUBIC, NLP>(a, &tm_hot, &tm_els, i, (int)(blockIdx.x - i * n_chunks), (int)blockIdx.y,
+                                                 &s_mbar_live);
   }
 }
 
@@ -1642,7 +1676,11 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
     }
     if (__syncthreads_or(irregular)) {
       // nothing of this chunk has left the CTA yet (the accumulators are written after the last image)
-      if (tid == 0) a.ws_redo[ring * n_chunks + chunk] = 1;
+      if (tid == 0) {
+        a.ws_redo[ring * n_chunks + chunk] = 1;
+        if (a.ws_ovf && atomicExch(a.ws_ovf + 1 + a.Q * a.n_rings + ring, 1) == 0)
+          a.ws_ovf[1 + atomicAdd(a.ws_ovf, 1)] = (int)ring;
+      }
       return;
     }
     // ---- (3) tiles x cubic pieces on the tensor cores ------------------------------------------------------
@@ -1962,7 +2000,13 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
   if (a.ws_tiles) {
     cudaError_t em = cudaMemsetAsync(a.ws_redo, 0, (size_t)a.Q * a.n_rings * n_chunks * sizeof(int), stream);
     if (em != cudaSuccess) return em;
+    // ws_ovf = [count | ring list (Q * n_rings) | listed flags (Q * n_rings)]: count and flags start at zero
+    if (a.ws_ovf) {
+      if ((em = cudaMemsetAsync(a.ws_ovf, 0, sizeof(int), stream)) != cudaSuccess) return em;
+      if ((em = cudaMemsetAsync(a.ws_ovf + 1 + (size_t)a.Q * a.n_rings, 0, (size_t)a.Q * a.n_rings * sizeof(int), stream)) != cudaSuccess) return em;
+    }
   }
+  a.ovf_list_mode = 0;
   if (a.ws_tiles) {
     const size_t msm = (2ul * a.n_azi + a.n_leaves) * sizeof(double) + 2ul * a.n_leaves;
     k_azinv_tiles<<<ggrid, kMomThreads, msm, stream>>>(a);
@@ -1981,6 +2025,12 @@ cudaError_t launch_integrate_azinv(AzinvArgs a, cudaStream_t stream) {
     else if (atm == 2 && corr == 1) err = launch_flux_mma<2, 1>(a, fgrid, stream);
     else err = launch_flux_mma<2, 2>(a, fgrid, stream);
     if (err != cudaSuccess) return err;
+  }
+  if (a.ws_tiles && a.ws_ovf) {       // the scalar kernel only has the listed rings to do
+    a.ovf_list_mode = 1;
+    int G = a.Q * a.n_rings;
+    if (G > 148 * 4) G = 148 * 4;
+    fgrid = dim3(n_chunks, G);
   }
   if (atm == 1 && corr == 0) err = launch_flux<1, 0>(a, fgrid, fsm, stream);
   else if (atm == 1 && corr == 1) err = launch_flux<1, 1>(a, fgrid, fsm, stream);

@@ -68,6 +68,9 @@ struct AzinvArgs {
   int* ws_redo;                      // with ws_tiles: [Q][n_rings][n_chunks], set by the tensor-core kernel for a chunk it
                                      // hands back to the scalar kernel (zeroed by the launcher)
   int force_redo;                    // test hook (XPSI_B200_FORCE_REDO=1): every chunk is handed back
+  int* ws_ovf;                       // with ws_tiles: [1 + 2 Q n_rings]: count, compact list of the rings the scalar kernel
+                                     // has to visit (overflowed tiles or a handed-back chunk), per-ring "listed" flags
+  int ovf_list_mode;                 // set by the launcher: the scalar kernel strides over that list
   // optional: deterministic two-stage ring reduction.  Every (ring, energy chunk) CTA stores its sum into
   // flux_part [Q][n_rings][N_E][N_P] and k_azinv_reduce_rings adds the lit rings in index order (no atomics)
   double* flux_part;
