@@ -452,7 +452,10 @@ constexpr int kMeshThreads = 256;
 constexpr int kAreaNodes = 1000;          // mesh.pyx:40,88
 
 // One CTA per member instance q.
-__global__ void __launch_bounds__(kMeshThreads) k_spot_mesh(EmbedArgs a) {
+#ifndef XB_MESH_CTAS
+#define XB_MESH_CTAS 2
+#endif
+__global__ void __launch_bounds__(kMeshThreads, XB_MESH_CTAS) k_spot_mesh(EmbedArgs a) {
   const int q = blockIdx.x, b = q / a.M, tid = threadIdx.x;
   const double R_eq = a.R_eq[b], eps = a.epsilon[b], zeta = a.zeta[b], r_s = a.r_s[b];
   const int m_idx = q - b * a.M;

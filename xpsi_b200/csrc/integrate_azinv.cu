@@ -80,7 +80,10 @@ __device__ __forceinline__ double key_order(unsigned long long k) {
 // geometry
 // ===========================================================================
 template <int ATM>
-__global__ void __launch_bounds__(kGeomThreads) k_azinv_geometry(AzinvArgs a) {
+#ifndef XB_GEOM_CTAS
+#define XB_GEOM_CTAS 8      // 64 registers: the kernel waits on its serial visibility replay, more resident CTAs hide it (19.38 -> 18.98 ms integrate)
+#endif
+__global__ void __launch_bounds__(kGeomThreads, XB_GEOM_CTAS) k_azinv_geometry(AzinvArgs a) {
   const int i = blockIdx.x;                 // ring
   const int q = blockIdx.y;                 // member instance
   const int tid = threadIdx.x;
