@@ -845,7 +845,10 @@ __device__ __forceinline__ void ray_integrals(double cos_alpha, double r_s, doub
 }
 
 // grid (ring, q); threads over rays
-__global__ void __launch_bounds__(128) k_rays(EmbedArgs a) {
+#ifndef XB_RAYS_CTAS
+#define XB_RAYS_CTAS 10     // 48 registers (embed 3.20 -> 2.88 ms)
+#endif
+__global__ void __launch_bounds__(128, XB_RAYS_CTAS) k_rays(EmbedArgs a) {
   const int i = blockIdx.x, q = blockIdx.y, b = q / a.M;
   const int n = a.n_rings[q];
   if (i >= n) return;

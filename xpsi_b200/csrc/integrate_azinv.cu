@@ -525,7 +525,10 @@ constexpr int kSlabMThreads = 192;
 
 constexpr int kSlabMRows = 4;           // mu rows per CTA: the ring headers are staged once for all of them
 
-__global__ void __launch_bounds__(kSlabMThreads) k_azinv_slab_member(AzinvArgs a, int which) {
+#ifndef XB_SLABM_CTAS
+#define XB_SLABM_CTAS 6     // 56 registers: store-latency bound, more resident CTAs (integrate 18.97 -> 18.39 ms)
+#endif
+__global__ void __launch_bounds__(kSlabMThreads, XB_SLABM_CTAS) k_azinv_slab_member(AzinvArgs a, int which) {
   const int q = blockIdx.y, tid = threadIdx.x;
   const AtmTable& T = which ? a.els : a.hot;
   const int ho = which ? kCorrD : 0;

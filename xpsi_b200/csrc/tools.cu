@@ -133,7 +133,10 @@ cudaError_t launch_energy_integrator(EnergyIntegArgs a, cudaStream_t stream) {
 constexpr int kBM = 64, kBN = 128, kBK = 16, kFoldThreads = 256;
 constexpr int kMS = kBK + 4;                     // padded row stride (doubles)
 
-__global__ void __launch_bounds__(kFoldThreads, 2) k_fold_mma(FoldArgs a) {
+#ifndef XB_FOLD_CTAS
+#define XB_FOLD_CTAS 2
+#endif
+__global__ void __launch_bounds__(kFoldThreads, XB_FOLD_CTAS) k_fold_mma(FoldArgs a) {
   __shared__ __align__(16) double As[kBM][kMS];
   __shared__ __align__(16) double Bs[kBN][kMS];
   const int mt = blockIdx.y;
