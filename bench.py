@@ -344,12 +344,24 @@ def main_ours(args):
     mine = np.concatenate([np.arange((s * world + rank) * B, (s * world + rank + 1) * B) for s in range(n_steps_all)])
     pipe.sweep_upload(syn.m2_spot_batch(pipe, thetas_all[mine]))
     pipe.sweep_run(0, W * B)
-    if dist is not None:
-        # warm-up of the collective as well (same payload size, same stream): the first all_gather of a size
-        # pays NCCL's lazy channel set-up (~10 ms), which is not part of a steady-state step
-        with torch.cuda.stream(stream):
-            warm = torch.zeros(2 * K * B, dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(torch.empty(world * warm.numel(), dtype=torch.float64, device=dev), warm)
+
+    def gather_results():
+        """The path's only collective: every rank's [lnL | status] for its K*B rows (NCCL over NVLink)."""
+        d_lnL, d_st = pipe.sweep_device_results()
+        t_lnL = torch.as_tensor(d_lnL, device=dev)[W * B:]
+        t_st = torch.as_tensor(d_st, device=dev)[W * B:]
+        if dist is None:
+            return None
+        payload = torch.cat([t_lnL, t_st.to(torch.float64)])
+        gathered = torch.empty(world * payload.numel(), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(gathered, payload)
+        return gathered
+
+    # warm-up of the collective as well (same code, same payload size, same stream): the first all_gather of a size
+    # pays NCCL's lazy channel set-up and torch's caching allocator its first cudaMalloc of every block (~10-20 ms
+    # together), neither of which belongs to a steady-state step
+    with torch.cuda.stream(stream):
+        gather_results()
     torch.cuda.synchronize()
     k0 = _lib.counters()[0]
     sampler = ClockSampler(local)
@@ -361,14 +373,7 @@ def main_ours(args):
         ev[0].record()
         pipe.sweep_run(W * B, K * B)
         ev[1].record()
-        d_lnL, d_st = pipe.sweep_device_results()
-        t_lnL = torch.as_tensor(d_lnL, device=dev)[W * B:]
-        t_st = torch.as_tensor(d_st, device=dev)[W * B:]
-        if dist is not None:
-            # the path's only collective: every rank's [lnL | status] for its K*B rows (NCCL over NVLink)
-            payload = torch.cat([t_lnL, t_st.to(torch.float64)])
-            gathered = torch.empty(world * payload.numel(), dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(gathered, payload)
+        gather_results()
         ev[2].record()
     torch.cuda.synchronize()
     barrier()
