@@ -1375,8 +1375,9 @@ constexpr int kRowH = 20;
 
 // Build-time parameters of k_azinv_flux_mma (dev/build_variants.sh + dev/time_step.py time variants side by side on
 // the GPU box; profiles/r02f_variants.txt, r02j_variants.txt).  With the node-form rows the kernel needs 31 KB of
-// shared memory, so 7 CTAs fit an SM if they stay within 72 registers: that takes the rolled tile loop (the
-// accumulators of the tiles a warp is not working on live in local memory) and a stage-1 energy loop unrolled by 2.
+// shared memory: 7 CTAs fit an SM within 72 registers, 6 within 80.  Both take the rolled tile loop (the accumulators of
+// the tiles a warp is not working on live in local memory) and a stage-1 energy loop unrolled by 2; 6 CTAs with two
+// independent DMMA chains per tile (80 registers) are 3 % faster than 7 CTAs with one (72).
 #ifndef XB_S1_UNROLL
 #define XB_S1_UNROLL 2
 #endif
@@ -1386,6 +1387,9 @@ constexpr int kS1Unroll = XB_S1_UNROLL;
 #endif
 // threads per CTA and resident CTAs per SM (every stage is written for any multiple of 32 threads: stage 1 strides
 // over leaves, stage 2 deals kMmaThreads / 8 node blocks per energy, stage 3 deals the 8-phase tiles over the warps)
+#ifndef XB_DUAL_ACC
+#define XB_DUAL_ACC 1        // even and odd steps of a tile on two independent DMMA chains
+#endif
 #ifndef XB_FLAG_BITWALK
 #define XB_FLAG_BITWALK 1    // flagged-interval correction walks the set bits of the mask instead of every step of the tile
 #endif
@@ -1393,7 +1397,7 @@ constexpr int kS1Unroll = XB_S1_UNROLL;
 #define XB_MMA_THREADS 128
 #endif
 #ifndef XB_MMA_CTAS
-#define XB_MMA_CTAS 7
+#define XB_MMA_CTAS 6
 #endif
 constexpr int kMmaThreads = XB_MMA_THREADS, kMmaCtas = XB_MMA_CTAS;
 // exact test behind an inconclusive Bernstein test: does y0 + t (b + t (c + t d)) go below zero inside (0, h)?
@@ -1716,6 +1720,9 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
       const double* bp = a.ws_tiles + ((slot * n_tiles + tile) * (long)a.tile_cap) * 32 + lane;
       unsigned off = coef0 + (unsigned)th.x * row_bytes;
       const unsigned end = coef0 + wrap_bytes;
+#if XB_DUAL_ACC
+      double accB0 = 0.0, accB1 = 0.0;          // odd steps: a second, independent DMMA chain
+#endif
       for (int s0 = 0; s0 < ns; s0 += 4) {
         const double b0 = bp[0], b1 = bp[32], b2 = bp[64], b3 = bp[96];
         bp += 128;
@@ -1724,12 +1731,21 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
           double av;
           asm volatile("ld.shared.f64 %0, [%1];" : "=d"(av) : "r"(off));
           const double bv = (j == 0) ? b0 : (j == 1) ? b1 : (j == 2) ? b2 : b3;
+#if XB_DUAL_ACC
+          if (j & 1)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(accB0), "+d"(accB1) : "d"(av), "d"(bv));
+          else
+#endif
           asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                        : "+d"(acc0), "+d"(acc1) : "d"(av), "d"(bv));
           off += row_bytes;
           if (off >= end) off -= wrap_bytes;
         }
       }
+#if XB_DUAL_ACC
+      acc0 += accB0; acc1 += accB1;
+#endif
       if (any_flag) {
         const double2 corr2 = flagged_tile_correction(
             s_coef, s_PH, N_L, N_P, tile, th, lane, fm0, fm1, fm2, fm3, a.phases, a.ws_cells + ring * 2 * (long)a.n_azi,
