@@ -1387,6 +1387,10 @@ constexpr int kS1Unroll = XB_S1_UNROLL;
 #endif
 // threads per CTA and resident CTAs per SM (every stage is written for any multiple of 32 threads: stage 1 strides
 // over leaves, stage 2 deals kMmaThreads / 8 node blocks per energy, stage 3 deals the 8-phase tiles over the warps)
+#ifndef XB_S2_UNROLL
+#define XB_S2_UNROLL 1
+#endif
+constexpr int kS2Unroll = XB_S2_UNROLL;
 #ifndef XB_DUAL_ACC
 #define XB_DUAL_ACC 1        // even and odd steps of a tile on two independent DMMA chains
 #endif
@@ -1668,6 +1672,7 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
           };
           double mm2 = slope(l0 - 2), mm1 = slope(l0 - 1), m0 = slope(l0);
           double t_prev = 0.0, NE_prev = 0.0;
+#pragma unroll kS2Unroll
           for (int l = l0; l <= l_end; ++l) {
             const double mp1 = slope(l + 1);
             const double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
