@@ -448,7 +448,10 @@ __device__ __forceinline__ MeshFrame mesh_frame(Region& g) {
   return m;
 }
 
-constexpr int kMeshThreads = 256;
+#ifndef XB_MESH_THREADS
+#define XB_MESH_THREADS 256
+#endif
+constexpr int kMeshThreads = XB_MESH_THREADS;
 constexpr int kAreaNodes = 1000;          // mesh.pyx:40,88
 
 // One CTA per member instance q.
