@@ -13,7 +13,11 @@ positional order, same return conventions):
     xpsi_b200.interstellar.Interstellar
     xpsi_b200.likelihoods.precomputation / eval_marginal_likelihood / poisson_likelihood_given_background
     xpsi_b200.likelihood.Likelihood                 (xpsi.Likelihood.__call__ over the pipeline)
-    xpsi_b200.pipeline.BatchedLikelihood            (additional, batched; embed on the GPU)
+    xpsi_b200.pipeline.BatchedLikelihood            (additional, batched; embed on the GPU; several signals, Elsewhere,
+                                                     Everywhere, interstellar attenuation)
+    xpsi_b200.from_xpsi.from_xpsi                   (GPU likelihood from a constructed xpsi.Likelihood object)
+    xpsi_b200.dropin.install                        (rebinds the compiled seams inside an imported xpsi package)
+    xpsi_b200.sampling                              (vectorised prior, UltraNest-shaped callables, sharded sweep, importance)
 
 Everything computes on the GPU through libxpsi_b200.so; there is no CPU path.
 ``xpsi_b200.synthetic`` (pure numpy) defines the synthetic workloads.
