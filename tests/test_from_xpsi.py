@@ -157,3 +157,32 @@ def test_from_xpsi_every_configuration(ref):
     with quiet:
         like = mm.build_two_signals(g["counts_N"], g["counts_X"])[0]
     _check(from_xpsi.from_xpsi(like, max_batch=4), g["theta"], g["lnL_total"], "two signals")
+
+
+@pytest.mark.gpu
+def test_from_xpsi_blocks_overlap_fill_and_evaluation(ref):
+    """Several blocks through ``from_xpsi(like).batch``: the parameter walk of block k + 1 runs in a worker thread
+    while block k is on the GPU; the result must equal the one of the vectorised fill function, row by row."""
+    import time
+    mg, m3, m4, mm = ref
+    from xpsi_b200 import from_xpsi
+    from xpsi_b200 import synthetic as syn
+    from xpsi_b200.likelihood import Likelihood
+    m2 = np.load(os.path.join(GOLDEN, "m2_stu_nsx.npz"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        like = mg.build_m2(mg.Recorder(), m2["counts"])[0]
+    gpu = from_xpsi.from_xpsi(like, max_batch=512)
+    P = syn.m2_bench_thetas(0, 2304)                       # 4.5 blocks
+    gpu.batch(P[:512])                                     # warm-up
+    t0 = time.perf_counter()
+    lnL, st = gpu.batch(P)
+    t1 = time.perf_counter()
+    direct = Likelihood(gpu.pipeline, lambda pl, X: syn.m2_spot_batch(pl, X))
+    t2 = time.perf_counter()
+    lnL_d, st_d = direct.batch(P)
+    t3 = time.perf_counter()
+    print("\nfrom_xpsi(like).batch: %.0f evals/s (parameter walk through the reference's objects, overlapped); "
+          "vectorised fill: %.0f evals/s" % (P.shape[0] / (t1 - t0), P.shape[0] / (t3 - t2)))
+    assert np.array_equal(st, st_d)
+    ok = st == 0
+    assert np.max(np.abs(lnL[ok] - lnL_d[ok])) < 1e-7

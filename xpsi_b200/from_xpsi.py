@@ -48,13 +48,13 @@ def _same(values, what):
     return v0
 
 
-def _param(obj, name):
-    """``obj[name]``, 0 for a parameter the region was constructed without (e.g. no ``cede_temperature`` when
-    ``cede=False``; xpsi/HotRegion.py:300-480 creates the temperature parameters conditionally)."""
+def _resolve(obj, name):
+    """The ``Parameter`` object ``obj[name]`` evaluates, or ``None`` when the object was constructed without it
+    (read as 0: e.g. no ``cede_temperature`` when ``cede=False``, xpsi/HotRegion.py:300-480)."""
     try:
-        return obj[name]
+        return obj.get_param(name)
     except KeyError:
-        return 0.0
+        return None
 
 
 def _subspace_call(obj):
@@ -134,6 +134,14 @@ class _Model:
             if h.beam_opt != 0:
                 raise NotImplementedError("xpsi_b200.from_xpsi: beaming parameters live in a user subclass of "
                                           "HotRegion; pass a fill function with extra_params instead")
+        # the parameter objects behind every value the walk reads, resolved once (obj[name] = get_param(name).evaluate(obj)
+        # with two linear scans over the names per call, xpsi/ParameterSubspace.py:112-130,185-189)
+        self._p_st = [_resolve(self.st, n) for n in ("mass", "radius", "distance", "cos_inclination", "frequency")]
+        self._p_mode = _resolve(ph, "mode_frequency")
+        self._p_regions = [[_resolve(h, n) for n in _REGION_PARAMS] for h in self.regions]
+        self._p_else = (_resolve(self.elsewhere, "elsewhere_temperature") if self.elsewhere is not None else
+                        _resolve(self.everywhere, "temperature") if self.everywhere is not None else None)
+        self._p_sig = [_resolve(s_, "phase_shift") for s_ in self.signals]
         # members: superseding member of every region, followed by its ceding member when the region has one
         self.member_region, self.member_is_cede = [], []
         for r, h in enumerate(self.regions):
@@ -222,18 +230,16 @@ class _Model:
         st, ph = self.st, self.ph
         for b in range(B):
             self.set_vector(P[b])
-            st_v[b] = (st['mass'], st['radius'], st['distance'], st['cos_inclination'], st['frequency'])
-            mode_f[b] = ph['mode_frequency']
+            st_v[b] = [p.evaluate(st) for p in self._p_st]
+            mode_f[b] = self._p_mode.evaluate(ph)
             for r, h in enumerate(self.regions):
-                reg_v[b, r] = [_param(h, n) for n in _REGION_PARAMS]
-            if self.elsewhere is not None:
-                else_T[b] = self.elsewhere['elsewhere_temperature']
-            elif self.everywhere is not None:
-                else_T[b] = self.everywhere['temperature']
+                reg_v[b, r] = [p.evaluate(h) if p is not None else 0.0 for p in self._p_regions[r]]
+            if else_T is not None:
+                else_T[b] = self._p_else.evaluate(self.elsewhere if self.elsewhere is not None else self.everywhere)
             if nh is not None:
                 nh[b] = self.column.evaluate(self.interstellar)
             if sig_shift is not None:
-                sig_shift[b] = [s['phase_shift'] for s in self.signals]
+                sig_shift[b] = [p.evaluate(s_) for p, s_ in zip(self._p_sig, self.signals)]
         if np.any(mode_f != mode_f[0]):
             raise NotImplementedError("xpsi_b200.from_xpsi: mode_frequency must be the same for a whole batch")
         M = max(len(self.member_region), 1)

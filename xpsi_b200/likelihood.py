@@ -74,17 +74,37 @@ class Likelihood:
         P = np.atleast_2d(np.asarray(P, dtype=np.float64))
         lnL = np.empty(P.shape[0])
         status = np.empty(P.shape[0], dtype=np.int32)
-        for i in range(0, P.shape[0], self._max_batch):
-            blk = P[i:i + self._max_batch]
-            spots, extras = self._filled(blk)
-            if extras is not None:
-                extras = dict(extras)
-                sig = extras.pop("signal_shifts", None)
-                if extras:
-                    self._pipe.upload_extras(blk.shape[0], **extras)
-                if sig is not None or len(getattr(self._pipe, "signals", ())) > 1:
-                    self._pipe.upload_signal_shifts(blk.shape[0], sig)
-            lnL[i:i + blk.shape[0]], status[i:i + blk.shape[0]] = self._pipe.eval_spots(spots)
+        starts = list(range(0, P.shape[0], self._max_batch))
+        # the host-side fill of block k + 1 (parameter walk, array packing) runs in a worker thread while block k is on
+        # the GPU (the ctypes call releases the GIL) -- only for fill functions that hand their per-batch extras back
+        # by value; one that uploads extras itself must not run ahead of the evaluation
+        pool = None
+        nxt = self._filled(P[0:self._max_batch]) if starts else None
+        overlap = len(starts) > 1 and (nxt[1] is not None or not (self._pipe.shape.get("has_elsewhere") or
+                                                                   self._pipe.shape.get("has_attenuation")))
+        if overlap:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = ThreadPoolExecutor(max_workers=1)
+        try:
+            for k, i in enumerate(starts):
+                blk = P[i:i + self._max_batch]
+                spots, extras = nxt.result() if hasattr(nxt, "result") else nxt
+                if k + 1 < len(starts):
+                    nb = P[starts[k + 1]:starts[k + 1] + self._max_batch]
+                    nxt = pool.submit(self._filled, nb) if overlap else None
+                if extras is not None:
+                    extras = dict(extras)
+                    sig = extras.pop("signal_shifts", None)
+                    if extras:
+                        self._pipe.upload_extras(blk.shape[0], **extras)
+                    if sig is not None or len(getattr(self._pipe, "signals", ())) > 1:
+                        self._pipe.upload_signal_shifts(blk.shape[0], sig)
+                lnL[i:i + blk.shape[0]], status[i:i + blk.shape[0]] = self._pipe.eval_spots(spots)
+                if not overlap and k + 1 < len(starts):
+                    nxt = self._filled(P[starts[k + 1]:starts[k + 1] + self._max_batch])
+        finally:
+            if pool is not None:
+                pool.shutdown(wait=True)
         bad = ~np.isin(status, (0,) + self.NUMERICAL_STATUSES)
         if strict and bad.any():
             k = int(np.flatnonzero(bad)[0])
