@@ -488,6 +488,13 @@ def main_ours(args):
                      "traffic_source": ("%s (ncu --set full at batch %d, scaled to batch %d)" % (art_path, art["batch"], B))
                      if traffic else None,
                      "peak_source": "in-run DFMA microbenchmark (MEASURED_PEAKS.json has no fp64 entry)",
+                     "what": "achieved = flops of the reference formulation (SURVEY s8d model x the integrator's work "
+                             "counters) / measured time of the flux kernels: a figure of merit against the reference "
+                             "algorithm; the hardware counters of the same kernel are in ncu_counters",
+                     "ncu_counters": ({k_: (flux_arts[0] or {}).get(k_) for k_ in
+                                       ("fp64_pipe_active_pct", "dmma_pipe_active_pct", "issue_active_pct",
+                                        "warps_active_pct", "registers", "l2_hit_pct", "duration_ms")}
+                                      if flux_arts[0] else None),
                      "algorithmic_gflop_per_eval": {k_: v / 1e9 for k_, v in fl.items()},
                      "per_kernel": per_kernel,
                      "whole_path_tflops": whole, "whole_path_frac": whole / pk,
