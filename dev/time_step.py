@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--blocks", type=int, default=6)
 ap.add_argument("--deterministic", action="store_true")
+ap.add_argument("--dump", default=None, help="save lnL / status of the evaluated rows (npz)")
 a = ap.parse_args()
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -39,6 +40,8 @@ for b in range(a.blocks):
     for k, v in pipe.stage_ms().items():
         acc[k] = acc.get(k, 0.0) + v
 lnL, st = pipe.sweep_download(0, a.batch * (a.blocks + 2))
+if a.dump:
+    np.savez(a.dump, lnL=lnL, status=st)
 print(os.environ.get("XPSI_B200_LIB", "in-tree"), "batch", a.batch, "ms/block %.3f" % (tot / a.blocks),
       "evals/s %.0f" % (a.batch * a.blocks / tot * 1e3), {k: round(v / a.blocks, 3) for k, v in acc.items()},
       "lnL checksum %.10e" % float(np.nansum(np.where(st == 0, lnL, 0.0))))
