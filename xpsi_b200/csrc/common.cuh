@@ -165,6 +165,15 @@ __device__ __forceinline__ void akima_coeffs(const X& x, const Y& y, int n, int 
                     akima_slope(x, y, n, i + 2, periodic), x[i + 1] - x[i], b, c, d);
 }
 
+// the same with the interval slopes m_0 .. m_{n-2} computed once (sm[i], the identical expression) instead of five
+// times per interval: the ghost slopes at the two ends still go through akima_slope
+template <class X, class Y>
+__device__ __forceinline__ void akima_coeffs_cached(const double* sm, const X& x, const Y& y, int n, int i, bool periodic,
+                                                    double* b, double* c, double* d) {
+  auto m = [&](int k) -> double { return (k >= 0 && k <= n - 2) ? sm[k] : akima_slope(x, y, n, k, periodic); };
+  akima_from_slopes(m(i - 2), m(i - 1), sm[i], m(i + 1), m(i + 2), x[i + 1] - x[i], b, c, d);
+}
+
 // Steffen in the same (b,c,d) form: y = y_i + t(b + t(c + t d))
 template <class X, class Y>
 __device__ __forceinline__ void steffen_coeffs(const X& x, const Y& y, int n, int i, double* b,

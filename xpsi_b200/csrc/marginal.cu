@@ -74,10 +74,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
   const int n_grids = a.comp_n_phases ? a.n_comp : 1;            // one phase grid per component, or one for all
   extern __shared__ double smem[];
   double* s_xall = smem;                                         // comp phases (shared by warps)
-  double* w_base = smem + (long)n_grids * N_P + (long)warp * (5 * N_P + 2 * kMaxBins);
+  double* w_base = smem + (long)n_grids * N_P + (long)warp * (6 * N_P + 2 * kMaxBins);
   double* s_y = w_base;                                          // [N_P]
   double* s_c = s_y + N_P;                                       // [N_P][4]
-  double* s_star = s_c + 4 * N_P;                                // [kMaxBins]
+  double* s_m = s_c + 4 * N_P;                                   // [N_P] interval slopes (Akima)
+  double* s_star = s_m + N_P;                                    // [kMaxBins]
   double* s_data = s_star + kMaxBins;                            // [kMaxBins]
   for (int i = threadIdx.x; i < n_grids * N_P; i += blockDim.x) s_xall[i] = a.comp_phases[i];
   __syncthreads();
@@ -105,6 +106,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_marginal(MarginalArgs a
     __syncwarp();
     if (a.interp == kCubic) {          // global C2 spline: one lane solves the cyclic system
       if (lane == 0) cspline_quads(s_x, s_y, Nc, true, s_c, 4);
+    } else if (a.interp == kAkima) {
+      // interval slopes once per interval (each is needed by five neighbours)
+      for (int i = lane; i < Nc - 1; i += 32) s_m[i] = (s_y[i + 1] - s_y[i]) / (s_x[i + 1] - s_x[i]);
+      __syncwarp();
+      for (int i = lane; i < Nc - 1; i += 32) {
+        double bb, cc, dd;
+        akima_coeffs_cached(s_m, s_x, s_y, Nc, i, periodic, &bb, &cc, &dd);
+        s_c[4 * i] = s_y[i]; s_c[4 * i + 1] = bb; s_c[4 * i + 2] = cc; s_c[4 * i + 3] = dd;
+      }
     } else
     for (int i = lane; i < Nc - 1; i += 32) {
       double bb, cc, dd;
@@ -363,7 +373,7 @@ __global__ void k_sum_channels(const double* chan_lnL, const int* chan_status, i
 template <int BPL>
 static cudaError_t launch_marginal_bpl(const MarginalArgs& a, cudaStream_t stream) {
   const size_t n_grids = a.comp_n_phases ? a.n_comp : 1;
-  const size_t smem = (n_grids * a.n_phases + kWarpsPerBlock * (5ul * a.n_phases + 2 * 32 * BPL)) * sizeof(double);
+  const size_t smem = (n_grids * a.n_phases + kWarpsPerBlock * (6ul * a.n_phases + 2 * 32 * BPL)) * sizeof(double);
   dim3 grid((a.n_chan + kWarpsPerBlock - 1) / kWarpsPerBlock, a.B);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   if (smem > 48 * 1024) {

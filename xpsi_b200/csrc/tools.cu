@@ -39,6 +39,16 @@ __global__ void __launch_bounds__(kEIThreads) k_energy_integrator(EnergyIntegArg
   const bool periodic = (a.interp != kSteffen);
   if (a.interp == kCubic) {            // global C2 spline: one thread solves the (cyclic) system
     if (threadIdx.x == 0) cspline_quads(s_x, s_y, N_E, true, s_c, 4);
+  } else if (a.interp == kAkima) {
+    // interval slopes once (each is needed by five neighbouring intervals)
+    double* s_m = s_c + 4 * N_E;
+    for (int i = threadIdx.x; i < N_E - 1; i += kEIThreads) s_m[i] = (s_y[i + 1] - s_y[i]) / (s_x[i + 1] - s_x[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < N_E - 1; i += kEIThreads) {
+      double b, c, d;
+      akima_coeffs_cached(s_m, s_x, s_y, N_E, i, periodic, &b, &c, &d);
+      s_c[4 * i] = s_y[i]; s_c[4 * i + 1] = b; s_c[4 * i + 2] = c; s_c[4 * i + 3] = d;
+    }
   } else
   for (int i = threadIdx.x; i < N_E - 1; i += kEIThreads) {
     double b, c, d;
@@ -105,7 +115,7 @@ void energy_span_table(const double* x, int n_energies, const double* edges, int
 cudaError_t launch_energy_integrator(EnergyIntegArgs a, cudaStream_t stream) {
   if (a.n_energies < 5) return cudaErrorInvalidValue;       // Akima needs >= 5 nodes
   if (a.interp == kCubic && a.n_energies > kMaxCubicNodes) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)a.n_energies * 6 * sizeof(double);
+  const size_t smem = (size_t)a.n_energies * 7 * sizeof(double);
   dim3 grid(a.n_phases, a.Q);
   k_energy_integrator<<<grid, kEIThreads, smem, stream>>>(a);
   return cudaGetLastError();
