@@ -101,7 +101,9 @@ class ClockSampler(threading.Thread):
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "sm_min_mhz": min(sm) if sm else None, "power_w": float(np.median(pw)) if pw else None,
                 "reasons": reasons, "samples": len(sm)}
 
 
@@ -397,12 +399,15 @@ def main_ours(args):
     sampling.sweep(like, P_all[:min(n_sweep, 2 * B * world)], device=dev)          # warm-up
     c0 = _lib.counters()
     info = {}
+    sweep_sampler = ClockSampler(local)
+    sweep_sampler.start()
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     lnL_s, st_s = sampling.sweep(like, P_all, device=dev, info=info)
     wall = time.perf_counter() - t0
     barrier()
+    sweep_clocks = sweep_sampler.stop()
     c1 = _lib.counters()
     blocks = -(-info["rows"] // B)
     walls, busy, gath = all_ranks(wall), all_ranks(info["device_ms"]), all_ranks(info["gather_ms"])
@@ -480,7 +485,8 @@ def main_ours(args):
                         "all_gather + D2H inside the timed region (once per sweep); strong scaling" % (n_sweep, world, B)},
         "sweep": {"n_theta": n_sweep, "wall_s": max(walls), "wall_s_by_rank": walls, "device_busy_ms_by_rank": busy,
                   "gather_ms_by_rank": gath, "busy_spread": (max(busy) - min(busy)) / max(busy) if max(busy) > 0 else None,
-                  "blocks_per_rank": blocks, "sharding": "round-robin rows (xpsi_b200.sampling.shard_indices)"},
+                  "blocks_per_rank": blocks, "sharding": "round-robin rows (xpsi_b200.sampling.shard_indices)",
+                  "clocks": sweep_clocks},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "kernel": "k_azinv_flux_mma<2,0,100> (+ k_azinv_flux<2,0,0,0,100> for overflow rings)", "achieved": a_flux, "peak": pk,
