@@ -10,4 +10,8 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_
 grep -E "ERROR SUMMARY|passed|failed" gpurun_out/${TAG}_memcheck.log | tail -3
 (timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_multi_signal.py -q -m gpu -x -k "two_signals" > gpurun_out/${TAG}_racecheck.log 2>&1; echo racecheck rc=$?)
 grep -E "RACECHECK SUMMARY|passed|failed" gpurun_out/${TAG}_racecheck.log | tail -3
+(timeout 600 compute-sanitizer --tool initcheck --print-limit 300 --error-exitcode 9 python -m pytest tests/test_multi_signal.py tests/test_gpu_parity.py tests/test_sweep_and_limits.py -q -m gpu -x -k "two_signals or everywhere_star or m2_batched_pipeline or m3_cst or omission or handed_back" > gpurun_out/${TAG}_initcheck.log 2>&1; echo initcheck rc=$?)
+grep -E "ERROR SUMMARY|passed|failed" gpurun_out/${TAG}_initcheck.log | tail -3
+(timeout 300 compute-sanitizer --tool synccheck --error-exitcode 9 python -m pytest tests/test_multi_signal.py -q -m gpu -x -k "two_signals" > gpurun_out/${TAG}_synccheck.log 2>&1; echo synccheck rc=$?)
+grep -E "ERROR SUMMARY|passed|failed" gpurun_out/${TAG}_synccheck.log | tail -3
 python dev/latency.py 2>&1 | tail -6 > gpurun_out/${TAG}_latency.log; cat gpurun_out/${TAG}_latency.log

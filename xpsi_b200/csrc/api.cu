@@ -267,6 +267,7 @@ static int integrate_member(
     size_t nl, nh, ni, ns;
     xb::azinv_workspace_sizes(a, &nl, &nh, &ni, &ns);
     CK(d_ws.alloc(nl)); CK(d_wh.alloc(nh)); CK(d_wi.alloc(ni));
+    CK(cudaMemsetAsync(d_wi.p, 0, ni * sizeof(int), g_stream));
     if (!general) {
       CK(d_wcells.alloc(2ul * n_rings * n_azi)); a.ws_cells = d_wcells.p;
       CK(d_wslab.alloc(ns));
@@ -1060,6 +1061,17 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
   ok(p->radial.alloc(Q * R)); ok(p->rsr.alloc(Q * R)); ok(p->params.alloc(Q * R * c.n_params));
   ok(p->defl.alloc(Q * R * c.n_rays)); ok(p->calpha.alloc(Q * R * c.n_rays)); ok(p->lag.alloc(Q * R * c.n_rays));
   ok(p->maxd.alloc(Q * R)); ok(p->cgamma.alloc(Q * R));
+  // the padded mesh and ray arrays are zeroed once: rings and cells a spot does not use are never read by the
+  // integrators, but fetch_embed copies whole arrays to the host
+  if (e == cudaSuccess) {
+    ok(cudaMemsetAsync(p->n_rings.p, 0, Q * sizeof(int), g_stream)); ok(cudaMemsetAsync(p->n_azi.p, 0, Q * sizeof(int), g_stream));
+    ok(cudaMemsetAsync(p->cellArea.p, 0, Q * R * A * sizeof(double), g_stream)); ok(cudaMemsetAsync(p->phi.p, 0, Q * R * A * sizeof(double), g_stream));
+    ok(cudaMemsetAsync(p->theta.p, 0, Q * R * sizeof(double), g_stream)); ok(cudaMemsetAsync(p->radial.p, 0, Q * R * sizeof(double), g_stream));
+    ok(cudaMemsetAsync(p->params.p, 0, Q * R * c.n_params * sizeof(double), g_stream));
+    ok(cudaMemsetAsync(p->defl.p, 0, Q * R * c.n_rays * sizeof(double), g_stream)); ok(cudaMemsetAsync(p->calpha.p, 0, Q * R * c.n_rays * sizeof(double), g_stream));
+    ok(cudaMemsetAsync(p->lag.p, 0, Q * R * c.n_rays * sizeof(double), g_stream));
+    ok(cudaMemsetAsync(p->maxd.p, 0, Q * R * sizeof(double), g_stream)); ok(cudaMemsetAsync(p->cgamma.p, 0, Q * R * sizeof(double), g_stream));
+  }
   ok(p->flux.alloc(Q * c.n_energies * c.n_phases)); ok(p->xin.alloc(B * C * c.n_phases * c.n_in));
   ok(p->folded.alloc(B * C * c.n_chan * c.n_phases)); ok(p->chan_lnL.alloc(B * c.n_chan));
   ok(p->chan_status.alloc(B * c.n_chan)); ok(p->expected.alloc(B * c.n_chan * c.n_bins));
@@ -1078,6 +1090,8 @@ xpsi_b200_pipeline* xpsi_b200_pipeline_create(const xpsi_b200_pipeline_config* c
     size_t nl, nh, ni, ns;
     xb::azinv_workspace_sizes(w, &nl, &nh, &ni, &ns);
     ok(p->ws_leaf.alloc(nl)); ok(p->ws_hdr.alloc(nh)); ok(p->ws_ihdr.alloc(ni)); ok(p->ws_slab.alloc(ns));
+    // header words of rings a spot does not use are read (and ignored) before the ring's image count is looked at
+    if (e == cudaSuccess) ok(cudaMemsetAsync(p->ws_ihdr.p, 0, ni * sizeof(int), g_stream));
     // interval-moment tiles (B operands of the tensor-core accumulation): 48 steps per 8-phase tile cover rings
     // whose cells reach ~41 leaf intervals (99 % of the ST-U prior's rings at 100 leaves); wider rings are
     // integrated by the scalar flux kernel, which walks the cells itself
