@@ -408,6 +408,7 @@ def main_ours(args):
     wall = time.perf_counter() - t0
     barrier()
     sweep_clocks = sweep_sampler.stop()
+    sweep_last_block = {k_: round(v, 3) for k_, v in pipe.stage_ms().items()}
     c1 = _lib.counters()
     blocks = -(-info["rows"] // B)
     walls, busy, gath = all_ranks(wall), all_ranks(info["device_ms"]), all_ranks(info["gather_ms"])
@@ -486,7 +487,7 @@ def main_ours(args):
         "sweep": {"n_theta": n_sweep, "wall_s": max(walls), "wall_s_by_rank": walls, "device_busy_ms_by_rank": busy,
                   "gather_ms_by_rank": gath, "busy_spread": (max(busy) - min(busy)) / max(busy) if max(busy) > 0 else None,
                   "blocks_per_rank": blocks, "sharding": "round-robin rows (xpsi_b200.sampling.shard_indices)",
-                  "clocks": sweep_clocks},
+                  "clocks": sweep_clocks, "last_block_stage_ms": sweep_last_block},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "kernel": "k_azinv_flux_mma<2,0,100> (+ k_azinv_flux<2,0,0,0,100> for overflow rings)", "achieved": a_flux, "peak": pk,
