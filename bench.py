@@ -396,7 +396,9 @@ def main_ours(args):
     # ---- e2e: config 5, a sweep of n_sweep distinct parameter vectors through the public API -----------------
     n_sweep = args.sweep
     P_all = syn.m2_bench_thetas(0, n_sweep)
-    sampling.sweep(like, P_all[:min(n_sweep, 2 * B * world)], device=dev)          # warm-up
+    # warm-up: one sweep of the same size (the sweep store on the device is allocated for N rows on first use and
+    # reused afterwards, like every other buffer of the path)
+    sampling.sweep(like, P_all, device=dev)
     c0 = _lib.counters()
     info = {}
     sweep_sampler = ClockSampler(local)
