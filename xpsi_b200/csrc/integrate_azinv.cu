@@ -1391,6 +1391,9 @@ constexpr int kS1Unroll = XB_S1_UNROLL;
 #define XB_S2_UNROLL 1
 #endif
 constexpr int kS2Unroll = XB_S2_UNROLL;
+#ifndef XB_B_LOAD
+#define XB_B_LOAD 0          // B rows of the tensor-core stage: 0 plain ld.global, 1 .cg (L2 only), 2 .cs (streaming), 3 .nc
+#endif
 #ifndef XB_DUAL_ACC
 #define XB_DUAL_ACC 1        // even and odd steps of a tile on two independent DMMA chains
 #endif
@@ -1729,7 +1732,15 @@ k_azinv_flux_mma(AzinvArgs a, const __grid_constant__ CUtensorMap tm_hot, const 
       double accB0 = 0.0, accB1 = 0.0;          // odd steps: a second, independent DMMA chain
 #endif
       for (int s0 = 0; s0 < ns; s0 += 4) {
+#if XB_B_LOAD == 1
+        const double b0 = __ldcg(bp), b1 = __ldcg(bp + 32), b2 = __ldcg(bp + 64), b3 = __ldcg(bp + 96);
+#elif XB_B_LOAD == 2
+        const double b0 = __ldcs(bp), b1 = __ldcs(bp + 32), b2 = __ldcs(bp + 64), b3 = __ldcs(bp + 96);
+#elif XB_B_LOAD == 3
+        const double b0 = __ldg(bp), b1 = __ldg(bp + 32), b2 = __ldg(bp + 64), b3 = __ldg(bp + 96);
+#else
         const double b0 = bp[0], b1 = bp[32], b2 = bp[64], b3 = bp[96];
+#endif
         bp += 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
